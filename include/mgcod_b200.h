@@ -1,0 +1,136 @@
+/*
+ * mgcod_b200.h — C-ABI of the B200 engine that replaces Mgcod's gene-finder boundary.
+ *
+ * What it replaces in the reference (gatech-genemark/Mgcod):
+ *   - bin/data.py:39-54   Data.run_mgm(): four fork/exec of dependencies/gmhmmp2
+ *                         (-M mgm_<code>.mod -s <fasta> -f gff -o <pred>/mgm_<code>_<species>.gff)
+ *   - bin/data.py:56-106  Data.extract_gene_coords(): re-reading the four GFF files
+ *   - bin/pipeline.py:139-155, 157-385   per-file / per-window log-odds sums and argmax labels
+ *   - bin/multiprocess_mgcod.py:140-145  process-level fan-out over genomes (here: one batch of contigs)
+ *
+ * Conventions: plain pointers and sizes; every function returns 0 on success and a negative
+ * MGC_E_* code on failure, with a message available from mgc_last_error() (thread-local).
+ * No function falls back to a CPU path: engine functions fail with MGC_E_CUDA when no
+ * sm_100 device is usable.
+ */
+#ifndef MGCOD_B200_H
+#define MGCOD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MGC_OK 0
+#define MGC_E_ARG (-1)     /* bad argument */
+#define MGC_E_IO (-2)      /* file cannot be read / written */
+#define MGC_E_PARSE (-3)   /* malformed .mod or FASTA (gmhmmp2 prints "error, ..." and exits non-zero) */
+#define MGC_E_CUDA (-4)    /* no usable device / CUDA failure */
+#define MGC_E_ALPHABET (-5)/* sequence contains letters outside ACGT (not supported by this build) */
+#define MGC_E_NOMEM (-6)
+
+#define MGC_MAX_MODELS 8
+
+typedef struct mgc_model mgc_model;     /* parsed parameter file (host) */
+typedef struct mgc_engine mgc_engine;   /* one per process per GPU: device tables + scratch + stream */
+typedef struct mgc_result mgc_result;   /* genes of one decoded batch, host side */
+
+/* One predicted gene == one CDS line of gmhmmp2's GFF (format string in SURVEY.md §8b). */
+typedef struct {
+    int32_t contig;        /* index into the batch */
+    int32_t left, right;   /* 1-based inclusive, as GFF columns 4,5 */
+    int8_t strand;         /* +1 / -1 */
+    int8_t domain;         /* 0 bacteria, 1 archaea  (attribute gene_type) */
+    int8_t partial_left;   /* attribute "partial XY": X */
+    int8_t partial_right;  /*                         Y */
+    int32_t gc;            /* attribute gc */
+    double logodd;         /* column 6 before %.2f formatting */
+} mgc_gene;
+
+/* Device-side timings of the last decode, milliseconds (CUDA events on the engine's stream). */
+typedef struct {
+    float h2d, pack, orf_find, orf_score, order, chain, aggregate, d2h, total;
+    int64_t n_orfs, n_starts, n_candidates, n_genes; /* summed over models */
+    int32_t kernel_launches;
+} mgc_stats;
+
+const char *mgc_version(void);
+const char *mgc_last_error(void);
+int mgc_device_count(void);
+
+/* ---- parameter files (replaces gmhmmp2's ParameterParser; host only, no GPU needed) ---- */
+int mgc_model_load(const char *mod_path, mgc_model **out);
+void mgc_model_free(mgc_model *m);
+/* info[0]=gcode [1]=cod_order [2]=non_order [3]=gene_min_length [4]=#bacterial sections [5]=#archaeal */
+int mgc_model_info(const mgc_model *m, int32_t info[6]);
+
+/* ---- engine ---- */
+/* models[i] is decoded as "label i" (Mgcod order: 11, 4, 15, 101 — bin/pipeline.py:53-54). */
+int mgc_engine_create(int device, const mgc_model *const *models, int n_models, mgc_engine **out);
+void mgc_engine_destroy(mgc_engine *e);
+
+/*
+ * Decode a batch of contigs under every model of the engine.
+ *   seq            concatenated ASCII sequences (host memory, pinned or pageable)
+ *   offsets[n+1]   contig i occupies seq[offsets[i] .. offsets[i+1])
+ * Equivalent to running gmhmmp2 once per model on a multi-FASTA of these contigs.
+ */
+int mgc_decode_batch(mgc_engine *e, const char *seq, const int64_t *offsets, int32_t n_contigs,
+                     mgc_result **out);
+
+/* Two-step form used by the benchmark: copy + pack once, decode many times with inputs resident in HBM. */
+int mgc_upload_batch(mgc_engine *e, const char *seq, const int64_t *offsets, int32_t n_contigs);
+int mgc_decode_resident(mgc_engine *e, mgc_result **out);
+
+int mgc_engine_stats(const mgc_engine *e, mgc_stats *out);
+
+/* ---- results ---- */
+int64_t mgc_result_num_genes(const mgc_result *r, int model);
+/* genes of one model ordered by (contig, left); pointer valid until mgc_result_free */
+const mgc_gene *mgc_result_genes(const mgc_result *r, int model);
+/* trailer value "total_logodd" per contig (chain score incl. overlap penalties) */
+const double *mgc_result_contig_totals(const mgc_result *r, int model);
+/* sum over all genes of round(logodd,2) in 1/100 units — Pipeline.classify_complete_sequence */
+int mgc_result_model_cents(const mgc_result *r, int64_t *cents /*[n_models]*/);
+void mgc_result_free(mgc_result *r);
+
+/*
+ * Sliding-window labels (bin/pipeline.py:157-385) computed on the device from the genes of the
+ * last decode.  For contig c: windows start at 0, stride, ... < len; window [start, start+w).
+ *   stride[c]      per-contig stride (the host resolves the 2500/5000 default, pipeline.py:172-183)
+ *   win_offsets    [n_contigs+1] prefix of window counts, filled by the caller via mgc_window_counts
+ *   labels         [total windows] argmax label (0..n_models-1)
+ *   cents          [total windows * n_models] window sums in 1/100 units
+ */
+int mgc_window_counts(const int64_t *contig_len, const int32_t *stride, int32_t n_contigs, int32_t window,
+                      int32_t consecutive, int short_contigs, int64_t *win_offsets);
+int mgc_window_labels(mgc_engine *e, const int32_t *stride, int32_t window, int32_t consecutive,
+                      int short_contigs, const int64_t *win_offsets, int32_t *labels, int64_t *cents);
+
+/* ---- testing hook: the pruned candidate list (total > 0) of the last decode, in chain order ----
+ * Mirrors what `gmhmmp2 --debug 1` prints per start point; used by the parity tests only. */
+typedef struct {
+    int32_t contig, left, right;   /* 0-based inclusive, forward coordinates */
+    int32_t strand, gc, domain, partial_start, partial_stop;
+    double total, cum;
+} mgc_candidate;
+int64_t mgc_debug_candidates(mgc_engine *e, int model, mgc_candidate *out, int64_t cap);
+
+/* ---- text writers (gmhmmp2 Output::PrintGenes_GFF / _LST; bin/data.py reads the GFF back) ---- */
+int mgc_write_gff(const mgc_result *r, int model, const char *const *contig_ids, const int64_t *contig_len,
+                  int32_t n_contigs, const char *seq_file_name, const char *mod_file_name, int gcode,
+                  const char *out_path, const char *format /* "gff" | "lst" */);
+
+/* ---- synthetic workload (BASELINE.json config 5) — host only ---- */
+/* Draws contig lengths ~ L^-2 on [min_len,max_len] until total >= total_bp; returns count. */
+int64_t mgc_synth_lengths(uint64_t seed, int64_t total_bp, int32_t min_len, int32_t max_len, int64_t *lens,
+                          int64_t cap);
+/* Fills seq (sum of lens bytes, ACGT) with gene-like content; truth_code[c] receives 11/4/15/101. */
+int mgc_synth_contigs(uint64_t seed, const int64_t *lens, int64_t n, char *seq, int32_t *truth_code,
+                      int threads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,107 @@
+// mgc_device.cuh — device-side data layout and small bit-parallel helpers (sm_100a).
+//
+// Sequence layout in HBM ("bit planes"): every contig owns a slot of `slot_words` 32-bit words per
+// plane (slot_words = ceil(L/32)+1 rounded up to a multiple of 4, so slots start on 16-byte
+// boundaries and a trailing zero word always exists).  Letter code = 2*hi + lo with A=0 C=1 G=2 T=3;
+// bit b of word w is the letter at contig position 32*w + b.  The reverse-complement strand is stored
+// the same way in a second region (strand 1) at the same slot offset: rc position j = L-1-j forward.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "mgc_model.hpp"
+
+namespace mgc {
+
+struct DevModel {
+    int gcode, kc, kn, min_len, nsec, kr, knr;
+    int stop_sel;   // bit0 TAA, bit1 TAG, bit2 TGA are stops under this genetic code
+    int atg_only;   // genetic code 1
+    int nfull, nnon, nramp, nnramp;
+    const double *lc_full, *ln_full, *lc_ramp, *ln_ramp;
+    const SectionScalars *sc;
+    int map[2][101];
+};
+
+// one stop-delimited ORF that has at least one start candidate of sufficient length
+struct OrfRec {
+    int32_t contig;
+    int32_t t;          // strand-local position of the first nt of the (real or virtual) stop codon
+    uint32_t base;      // first entry in the starts array
+    uint32_t n;         // number of starts
+    uint32_t sf;        // bit0: strand (1 = reverse complement); bit8: stop codon missing (ORF runs into the right edge)
+};
+
+// a start/stop pair with total > 0, forward coordinates, 0-based inclusive
+struct Cand {
+    int32_t contig;
+    int32_t left, right;
+    uint32_t orf;       // id of the ORF record (groups reverse-strand starts sharing a stop)
+    double total;
+    int16_t gc;
+    int8_t strand;      // +1 / -1
+    uint8_t flags;      // bit0 domain (1 = archaea), bit1 partial start, bit2 partial stop
+    int32_t len;
+};
+static_assert(sizeof(Cand) == 32, "Cand must be 32 bytes");
+
+constexpr int32_t GPTR_UNSET = (int32_t)0x80808080;
+
+struct ChainBufs {
+    const Cand *sorted;
+    const uint32_t *bend;   // bucket ends (bucket b spans [b ? bend[b-1] : 0, bend[b]))
+    double *cum;            // per sorted entry
+    int32_t *prev;          // per sorted entry (index into sorted, -1 none)
+    int32_t *gptr;          // per ORF record: shared back-pointer of reverse-strand ORFs (GPTR_UNSET until first use)
+    // available predecessor states, appended in right-end order, stored at the contig's sorted range
+    int32_t *av_right, *av_left, *av_ls;  // av_ls = len * 2 + (strand < 0)
+    int32_t *av_idx;
+    double *av_cum, *av_pmax;
+    int32_t *av_parg;
+    int32_t *chain;         // traceback output, contig-local, stored at the contig's sorted range
+    int32_t *gene_count;    // per contig
+    double *contig_total;   // per contig
+};
+
+struct Planes {
+    const uint32_t *lo, *hi;  // [2][W + 4]
+    int64_t W;                // words per strand region
+};
+
+__device__ __forceinline__ uint32_t frame_pattern(int r) {
+    // bits b with b % 3 == r
+    return r == 0 ? 0x49249249u : (r == 1 ? 0x92492492u : 0x24924924u);
+}
+
+// letters of 32 consecutive positions starting at word w (needs w+1 for the two look-ahead letters)
+struct CodonMasks {
+    uint32_t start, taa, tag, tga;
+};
+
+__device__ __forceinline__ CodonMasks codon_masks(uint32_t l0, uint32_t h0, uint32_t l1n, uint32_t h1n, int atg_only) {
+    uint32_t l1 = __funnelshift_r(l0, l1n, 1), h1 = __funnelshift_r(h0, h1n, 1);
+    uint32_t l2 = __funnelshift_r(l0, l1n, 2), h2 = __funnelshift_r(h0, h1n, 2);
+    uint32_t T0 = h0 & l0, A0 = ~h0 & ~l0, C0 = ~h0 & l0;
+    uint32_t T1 = h1 & l1, A1 = ~h1 & ~l1, G1 = h1 & ~l1;
+    uint32_t A2 = ~h2 & ~l2, G2 = h2 & ~l2;
+    CodonMasks m;
+    m.start = T1 & G2 & (atg_only ? A0 : ~C0);
+    m.taa = T0 & A1 & A2;
+    m.tag = T0 & A1 & G2;
+    m.tga = T0 & G1 & A2;
+    return m;
+}
+
+__device__ __forceinline__ uint32_t stop_mask(const CodonMasks &m, int stop_sel) {
+    return ((stop_sel & 1) ? m.taa : 0u) | ((stop_sel & 2) ? m.tag : 0u) | ((stop_sel & 4) ? m.tga : 0u);
+}
+
+// bits [from, to] (inclusive, 0..31) set
+__device__ __forceinline__ uint32_t bit_range(int from, int to) {
+    if (from > to) return 0u;
+    uint32_t hi = to >= 31 ? 0xffffffffu : ((1u << (to + 1)) - 1u);
+    uint32_t lo = from <= 0 ? 0u : ((1u << from) - 1u);
+    return hi & ~lo;
+}
+
+}  // namespace mgc

@@ -1,0 +1,629 @@
+// mgc_engine.cu — host orchestration of the CUDA path and the C-ABI entry points (include/mgcod_b200.h).
+//
+// One mgc_engine per process per GPU: device copies of the model tables, the resident batch (planes,
+// GC prefix), per-model scratch, one stream.  Nothing here falls back to a CPU path: without a usable
+// device mgc_engine_create fails with MGC_E_CUDA.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "mgc_device.cuh"
+#include "mgc_kernels.hpp"
+#include "mgc_model.hpp"
+#include "mgc_util.hpp"
+
+using namespace mgc;
+
+struct mgc_model {
+    Model m;
+};
+
+struct mgc_result {
+    int n_models = 0;
+    int32_t n_contigs = 0;
+    std::vector<std::vector<mgc_gene>> genes;
+    std::vector<std::vector<double>> contig_totals;
+    std::vector<int64_t> cents;
+};
+
+namespace {
+
+#define CUDA_TRY(expr)                                                                                 \
+    do {                                                                                               \
+        cudaError_t _e = (expr);                                                                       \
+        if (_e != cudaSuccess)                                                                         \
+            throw std::runtime_error(std::string("CUDA: ") + cudaGetErrorString(_e) + " at " #expr);   \
+    } while (0)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    void ensure(size_t need) {
+        if (need <= bytes) return;
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+        cudaError_t e = cudaMalloc(&p, need);
+        if (e != cudaSuccess) throw std::runtime_error(std::string("CUDA: out of device memory (") + std::to_string(need) + " bytes)");
+        bytes = need;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct PerModel {
+    DevBuf lc_full, ln_full, lc_ramp, ln_ramp, sc;
+    DevBuf orfs, starts, surv, sorted, bcount, cum, prev, gptr;
+    DevBuf av_right, av_left, av_ls, av_idx, av_cum, av_pmax, av_parg, chain, gene_count, gene_off, contig_total, genes;
+};
+
+constexpr int N_EVENTS = 10;
+
+}  // namespace
+
+struct mgc_engine {
+    int device = 0, n_sm = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[N_EVENTS];
+    int n_models = 0;
+    std::vector<Model> models;
+    std::vector<PerModel> pm;
+    DevBuf d_models;
+    // resident batch
+    int32_t n_contigs = 0;
+    int64_t total_nt = 0, W = 0;
+    std::vector<int64_t> h_aoff, h_cwoff;
+    std::vector<int32_t> h_clen, h_order;
+    DevBuf ascii, aoff, cwoff, clen, grp2contig, order, lo, hi, gc, tile_sums, flags;
+    // pointer tables + counters (device)
+    DevBuf t_orfs, t_starts, t_surv, t_sorted, t_bcount, t_gene_off, t_genes, t_chainbufs;
+    DevBuf counters;     // [M][8] unsigned long long: 0 orfs, 1 starts
+    DevBuf surv_counters;  // [M]
+    DevBuf work_counters;  // [M] int
+    DevBuf model_cents;    // [M]
+    DevBuf gene_totals;    // [M] uint32 grand totals of the gene scans
+    DevBuf win_stride, win_off, win_labels, win_cents;
+    uint32_t cap_orf = 0, cap_starts = 0, cap_surv = 0;
+    bool have_batch = false, have_genes = false;
+    mgc_stats stats;
+};
+
+namespace {
+
+void upload_models(mgc_engine *e) {
+    std::vector<DevModel> dm(e->n_models);
+    for (int i = 0; i < e->n_models; i++) {
+        const Model &m = e->models[i];
+        PerModel &p = e->pm[i];
+        auto up = [&](DevBuf &b, const void *src, size_t bytes) {
+            b.ensure(std::max<size_t>(bytes, 16));
+            CUDA_TRY(cudaMemcpy(b.p, src, bytes, cudaMemcpyHostToDevice));
+        };
+        up(p.lc_full, m.lc_full.data(), m.lc_full.size() * sizeof(double));
+        up(p.ln_full, m.ln_full.data(), m.ln_full.size() * sizeof(double));
+        up(p.lc_ramp, m.lc_ramp.data(), m.lc_ramp.size() * sizeof(double));
+        up(p.ln_ramp, m.ln_ramp.data(), m.ln_ramp.size() * sizeof(double));
+        up(p.sc, m.sc.data(), m.sc.size() * sizeof(SectionScalars));
+        DevModel &d = dm[i];
+        d.gcode = m.gcode;
+        d.kc = m.cod_order;
+        d.kn = m.non_order;
+        d.min_len = std::max(m.min_len, 6);
+        d.nsec = m.nsec;
+        d.kr = m.cod_order > 0 ? m.cod_order : 1;
+        d.knr = m.non_order > 0 ? m.non_order : 1;
+        switch (m.gcode) {
+            case 4: case 25: d.stop_sel = 1 | 2; break;   // TAA TAG
+            case 15: d.stop_sel = 1 | 4; break;           // TAA TGA
+            case 101: d.stop_sel = 2 | 4; break;          // TAG TGA
+            default: d.stop_sel = 7;
+        }
+        d.atg_only = m.gcode == 1;
+        d.nfull = (int)pow4(d.kc + 1);
+        d.nnon = (int)pow4(d.kn + 1);
+        d.nramp = (int)pow4(d.kr);
+        d.nnramp = (int)pow4(d.knr);
+        d.lc_full = p.lc_full.as<double>();
+        d.ln_full = p.ln_full.as<double>();
+        d.lc_ramp = p.lc_ramp.as<double>();
+        d.ln_ramp = p.ln_ramp.as<double>();
+        d.sc = p.sc.as<SectionScalars>();
+        std::memcpy(d.map, m.map, sizeof(d.map));
+    }
+    e->d_models.ensure(sizeof(DevModel) * e->n_models);
+    CUDA_TRY(cudaMemcpy(e->d_models.p, dm.data(), sizeof(DevModel) * e->n_models, cudaMemcpyHostToDevice));
+}
+
+void ensure_batch_buffers(mgc_engine *e) {
+    const int M = e->n_models;
+    const int64_t W = e->W, nt = e->total_nt;
+    e->lo.ensure((size_t)(2 * W + 8) * 4);
+    e->hi.ensure((size_t)(2 * W + 8) * 4);
+    e->gc.ensure((size_t)(W + 8) * 4);
+    const int64_t nb = W / 4;
+    const int64_t scan_n = std::max<int64_t>(std::max<int64_t>(W, nb), e->n_contigs + 1);
+    e->tile_sums.ensure((size_t)(scan_n / 2048 + 8) * 4);
+    e->grp2contig.ensure((size_t)(W / 4 + 8) * 4);
+    e->flags.ensure(64);
+    e->cap_orf = (uint32_t)std::min<int64_t>(nt / 16 + 8192, 0x7fffff00);
+    e->cap_starts = (uint32_t)std::min<int64_t>(nt / 4 + 8192, 0x7fffff00);
+    e->cap_surv = (uint32_t)std::min<int64_t>(nt / 16 + 8192, 0x7fffff00);
+    std::vector<void *> t_orfs(M), t_starts(M), t_surv(M), t_sorted(M), t_bcount(M), t_gene_off(M), t_genes(M);
+    std::vector<ChainBufs> cb(M);
+    for (int i = 0; i < M; i++) {
+        PerModel &p = e->pm[i];
+        p.orfs.ensure((size_t)e->cap_orf * sizeof(OrfRec));
+        p.starts.ensure((size_t)e->cap_starts * 4);
+        p.surv.ensure((size_t)e->cap_surv * sizeof(Cand));
+        p.sorted.ensure((size_t)e->cap_surv * sizeof(Cand));
+        p.bcount.ensure((size_t)(nb + 8) * 4);
+        p.cum.ensure((size_t)e->cap_surv * 8);
+        p.prev.ensure((size_t)e->cap_surv * 4);
+        p.gptr.ensure((size_t)e->cap_orf * 4);
+        p.av_right.ensure((size_t)e->cap_surv * 4);
+        p.av_left.ensure((size_t)e->cap_surv * 4);
+        p.av_ls.ensure((size_t)e->cap_surv * 4);
+        p.av_idx.ensure((size_t)e->cap_surv * 4);
+        p.av_cum.ensure((size_t)e->cap_surv * 8);
+        p.av_pmax.ensure((size_t)e->cap_surv * 8);
+        p.av_parg.ensure((size_t)e->cap_surv * 4);
+        p.chain.ensure((size_t)e->cap_surv * 4);
+        p.gene_count.ensure((size_t)(e->n_contigs + 8) * 4);
+        p.gene_off.ensure((size_t)(e->n_contigs + 8) * 4);
+        p.contig_total.ensure((size_t)(e->n_contigs + 8) * 8);
+        p.genes.ensure((size_t)e->cap_surv * sizeof(mgc_gene));
+        t_orfs[i] = p.orfs.p; t_starts[i] = p.starts.p; t_surv[i] = p.surv.p; t_sorted[i] = p.sorted.p;
+        t_bcount[i] = p.bcount.p; t_gene_off[i] = p.gene_off.p; t_genes[i] = p.genes.p;
+        ChainBufs &c = cb[i];
+        c.sorted = p.sorted.as<Cand>();
+        c.bend = p.bcount.as<uint32_t>();
+        c.cum = p.cum.as<double>();
+        c.prev = p.prev.as<int32_t>();
+        c.gptr = p.gptr.as<int32_t>();
+        c.av_right = p.av_right.as<int32_t>();
+        c.av_left = p.av_left.as<int32_t>();
+        c.av_ls = p.av_ls.as<int32_t>();
+        c.av_idx = p.av_idx.as<int32_t>();
+        c.av_cum = p.av_cum.as<double>();
+        c.av_pmax = p.av_pmax.as<double>();
+        c.av_parg = p.av_parg.as<int32_t>();
+        c.chain = p.chain.as<int32_t>();
+        c.gene_count = p.gene_count.as<int32_t>();
+        c.contig_total = p.contig_total.as<double>();
+    }
+    auto up = [&](DevBuf &b, const void *src, size_t bytes) {
+        b.ensure(bytes);
+        CUDA_TRY(cudaMemcpy(b.p, src, bytes, cudaMemcpyHostToDevice));
+    };
+    up(e->t_orfs, t_orfs.data(), M * sizeof(void *));
+    up(e->t_starts, t_starts.data(), M * sizeof(void *));
+    up(e->t_surv, t_surv.data(), M * sizeof(void *));
+    up(e->t_sorted, t_sorted.data(), M * sizeof(void *));
+    up(e->t_bcount, t_bcount.data(), M * sizeof(void *));
+    up(e->t_gene_off, t_gene_off.data(), M * sizeof(void *));
+    up(e->t_genes, t_genes.data(), M * sizeof(void *));
+    up(e->t_chainbufs, cb.data(), M * sizeof(ChainBufs));
+    e->counters.ensure((size_t)M * 8 * 8);
+    e->surv_counters.ensure((size_t)M * 8);
+    e->work_counters.ensure((size_t)M * 4);
+    e->model_cents.ensure((size_t)M * 8);
+    e->gene_totals.ensure((size_t)M * 4);
+}
+
+void do_upload(mgc_engine *e, const char *seq, const int64_t *offsets, int32_t n) {
+    if (n <= 0) throw std::invalid_argument("n_contigs must be positive");
+    CUDA_TRY(cudaSetDevice(e->device));
+    e->have_batch = e->have_genes = false;
+    e->n_contigs = n;
+    e->h_aoff.assign(offsets, offsets + n + 1);
+    e->h_clen.resize(n);
+    e->h_cwoff.resize(n + 1);
+    int64_t w = 0, nt = 0;
+    for (int32_t c = 0; c < n; c++) {
+        int64_t L = offsets[c + 1] - offsets[c];
+        if (L < 0 || L > 0x7ffffff0) throw std::invalid_argument("contig length out of range");
+        e->h_clen[c] = (int32_t)L;
+        e->h_cwoff[c] = w;
+        int64_t words = (L + 31) / 32 + 1;
+        w += (words + 3) / 4 * 4;
+        nt += L;
+    }
+    e->h_cwoff[n] = w;
+    if (w * 64 >= 0xffffffffLL) throw std::invalid_argument("batch too large: at most ~2e9 nt per decode call");
+    e->W = w;
+    e->total_nt = nt;
+    e->h_order.resize(n);
+    std::iota(e->h_order.begin(), e->h_order.end(), 0);
+    std::stable_sort(e->h_order.begin(), e->h_order.end(), [&](int a, int b) { return e->h_clen[a] > e->h_clen[b]; });
+    ensure_batch_buffers(e);
+    const int64_t a0 = offsets[0], a1 = offsets[n];
+    e->ascii.ensure((size_t)(a1 - a0) + 64);
+    e->aoff.ensure((size_t)(n + 1) * 8);
+    e->cwoff.ensure((size_t)(n + 1) * 8);
+    e->clen.ensure((size_t)n * 4);
+    e->order.ensure((size_t)n * 4);
+    std::vector<int64_t> rel(n + 1);
+    for (int32_t c = 0; c <= n; c++) rel[c] = offsets[c] - a0;
+    cudaStream_t st = e->stream;
+    CUDA_TRY(cudaEventRecord(e->ev[0], st));
+    CUDA_TRY(cudaMemcpyAsync(e->ascii.p, seq + a0, (size_t)(a1 - a0), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(e->aoff.p, rel.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(e->cwoff.p, e->h_cwoff.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(e->clen.p, e->h_clen.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(e->order.p, e->h_order.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    launch_groups(e->cwoff.as<int64_t>(), n, e->W / 4, e->grp2contig.as<int32_t>(), st);
+    CUDA_TRY(cudaEventRecord(e->ev[1], st));
+    CUDA_TRY(cudaStreamSynchronize(st));  // rel[] is a stack-local staging buffer
+    CUDA_TRY(cudaGetLastError());
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]);
+    e->stats = mgc_stats();
+    e->stats.h2d = ms;
+    e->have_batch = true;
+}
+
+mgc_result *do_decode(mgc_engine *e) {
+    if (!e->have_batch) throw std::invalid_argument("no batch uploaded");
+    CUDA_TRY(cudaSetDevice(e->device));
+    const int M = e->n_models;
+    const int32_t n = e->n_contigs;
+    const int64_t W = e->W, nb = W / 4;
+    cudaStream_t st = e->stream;
+    int launches = 0;
+    float h2d = e->stats.h2d;
+    e->stats = mgc_stats();
+    e->stats.h2d = h2d;
+    e->have_genes = false;
+
+    CUDA_TRY(cudaEventRecord(e->ev[0], st));
+    CUDA_TRY(cudaMemsetAsync(e->flags.p, 0, 64, st));
+    CUDA_TRY(cudaMemsetAsync(e->counters.p, 0, (size_t)M * 64, st));
+    CUDA_TRY(cudaMemsetAsync(e->surv_counters.p, 0, (size_t)M * 8, st));
+    CUDA_TRY(cudaMemsetAsync(e->work_counters.p, 0, (size_t)M * 4, st));
+    CUDA_TRY(cudaMemsetAsync(e->model_cents.p, 0, (size_t)M * 8, st));
+    for (int i = 0; i < M; i++) CUDA_TRY(cudaMemsetAsync(e->pm[i].bcount.p, 0, (size_t)(nb + 8) * 4, st));
+    // pack + GC prefix
+    launch_pack(e->ascii.as<char>(), e->aoff.as<int64_t>(), e->cwoff.as<int64_t>(), e->clen.as<int32_t>(),
+                e->grp2contig.as<int32_t>(), W, e->lo.as<uint32_t>(), e->hi.as<uint32_t>(), e->gc.as<uint32_t>(),
+                e->flags.as<int>(), st);
+    launches += 1;
+    launches += launch_exclusive_scan(e->gc.as<uint32_t>(), e->gc.as<uint32_t>(), e->tile_sums.as<uint32_t>(), W, nullptr, st);
+    CUDA_TRY(cudaEventRecord(e->ev[1], st));
+    Planes pl;
+    pl.lo = e->lo.as<uint32_t>();
+    pl.hi = e->hi.as<uint32_t>();
+    pl.W = W;
+    launch_orf_find(pl, e->cwoff.as<int64_t>(), e->clen.as<int32_t>(), e->grp2contig.as<int32_t>(), e->d_models.as<DevModel>(), M,
+                    e->t_orfs.as<OrfRec *>(), e->t_starts.as<uint32_t *>(), e->counters.as<unsigned long long>(), e->cap_orf,
+                    e->cap_starts, st);
+    launches += 1;
+    CUDA_TRY(cudaEventRecord(e->ev[2], st));
+    launch_orf_score(pl, e->gc.as<uint32_t>(), e->cwoff.as<int64_t>(), e->clen.as<int32_t>(), e->d_models.as<DevModel>(), M,
+                     e->t_orfs.as<OrfRec *>(), e->t_starts.as<uint32_t *>(), e->counters.as<unsigned long long>(),
+                     e->t_surv.as<Cand *>(), e->t_bcount.as<uint32_t *>(), e->surv_counters.as<unsigned long long>(), e->cap_orf,
+                     e->cap_surv, e->t_chainbufs.as<ChainBufs>(), e->n_sm, st);
+    launches += 1;
+    CUDA_TRY(cudaEventRecord(e->ev[3], st));
+    for (int i = 0; i < M; i++)
+        launches += launch_exclusive_scan(e->pm[i].bcount.as<uint32_t>(), e->pm[i].bcount.as<uint32_t>(), e->tile_sums.as<uint32_t>(),
+                                          nb, nullptr, st);
+    launch_scatter(e->t_surv.as<const Cand *>(), e->t_sorted.as<Cand *>(), e->t_bcount.as<uint32_t *>(),
+                   e->surv_counters.as<unsigned long long>(), e->cwoff.as<int64_t>(), e->cap_surv, M, e->n_sm, st);
+    launches += 1;
+    CUDA_TRY(cudaEventRecord(e->ev[4], st));
+    launch_chain(e->t_chainbufs.as<ChainBufs>(), e->cwoff.as<int64_t>(), e->clen.as<int32_t>(), e->order.as<int32_t>(), n,
+                 e->work_counters.as<int>(), M, e->n_sm, st);
+    launches += 1;
+    CUDA_TRY(cudaEventRecord(e->ev[5], st));
+    for (int i = 0; i < M; i++) {
+        // gene_count[n] = 0 so that the exclusive scan yields the total at gene_off[n]
+        CUDA_TRY(cudaMemsetAsync(e->pm[i].gene_count.as<int32_t>() + n, 0, 4, st));
+        launches += launch_exclusive_scan(e->pm[i].gene_count.as<uint32_t>(), e->pm[i].gene_off.as<uint32_t>(),
+                                          e->tile_sums.as<uint32_t>(), (int64_t)n + 1, e->gene_totals.as<uint32_t>() + i, st);
+    }
+    launch_gather(e->t_chainbufs.as<ChainBufs>(), e->t_gene_off.as<const uint32_t *>(), e->t_genes.as<mgc_gene *>(),
+                  e->cwoff.as<int64_t>(), e->clen.as<int32_t>(), n, e->model_cents.as<long long>(), M, e->n_sm, st);
+    launches += 1;
+    CUDA_TRY(cudaEventRecord(e->ev[6], st));
+
+    // small read-backs
+    std::vector<unsigned long long> h_counters((size_t)M * 8), h_surv(M);
+    std::vector<uint32_t> h_gtot(M);
+    std::vector<long long> h_cents(M);
+    int h_flags[16];
+    CUDA_TRY(cudaMemcpyAsync(h_counters.data(), e->counters.p, (size_t)M * 64, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(h_surv.data(), e->surv_counters.p, (size_t)M * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(h_gtot.data(), e->gene_totals.p, (size_t)M * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(h_cents.data(), e->model_cents.p, (size_t)M * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(h_flags, e->flags.p, 64, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaGetLastError());
+    if (h_flags[0]) throw AlphabetError("sequence contains letters outside ACGT; ambiguous letters are not supported by this build");
+    for (int i = 0; i < M; i++) {
+        if (h_counters[(size_t)i * 8] > e->cap_orf || h_counters[(size_t)i * 8 + 1] > e->cap_starts || h_surv[i] > e->cap_surv)
+            throw std::runtime_error("device scratch exhausted (ORFs " + std::to_string(h_counters[(size_t)i * 8]) + ", starts " +
+                                     std::to_string(h_counters[(size_t)i * 8 + 1]) + ", candidates " + std::to_string(h_surv[i]) + ")");
+        e->stats.n_orfs += (int64_t)h_counters[(size_t)i * 8];
+        e->stats.n_starts += (int64_t)h_counters[(size_t)i * 8 + 1];
+        e->stats.n_candidates += (int64_t)h_surv[i];
+        e->stats.n_genes += h_gtot[i];
+    }
+    // genes
+    auto *res = new mgc_result();
+    res->n_models = M;
+    res->n_contigs = n;
+    res->genes.resize(M);
+    res->contig_totals.resize(M);
+    res->cents.assign(h_cents.begin(), h_cents.end());
+    for (int i = 0; i < M; i++) {
+        res->genes[i].resize(h_gtot[i]);
+        res->contig_totals[i].resize(n);
+        if (h_gtot[i])
+            CUDA_TRY(cudaMemcpyAsync(res->genes[i].data(), e->pm[i].genes.p, (size_t)h_gtot[i] * sizeof(mgc_gene), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(res->contig_totals[i].data(), e->pm[i].contig_total.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_TRY(cudaEventRecord(e->ev[7], st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    float ms;
+    cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]); e->stats.pack = ms;
+    cudaEventElapsedTime(&ms, e->ev[1], e->ev[2]); e->stats.orf_find = ms;
+    cudaEventElapsedTime(&ms, e->ev[2], e->ev[3]); e->stats.orf_score = ms;
+    cudaEventElapsedTime(&ms, e->ev[3], e->ev[4]); e->stats.order = ms;
+    cudaEventElapsedTime(&ms, e->ev[4], e->ev[5]); e->stats.chain = ms;
+    cudaEventElapsedTime(&ms, e->ev[5], e->ev[6]); e->stats.aggregate = ms;
+    cudaEventElapsedTime(&ms, e->ev[6], e->ev[7]); e->stats.d2h = ms;
+    cudaEventElapsedTime(&ms, e->ev[0], e->ev[7]); e->stats.total = ms;
+    e->stats.kernel_launches = launches;
+    e->have_genes = true;
+    return res;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C-ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char *mgc_version(void) { return "mgcod_b200 0.1 (GeneMark.hmm-2 v1.17 compatible decoding, sm_100a)"; }
+
+const char *mgc_last_error(void) { return mgc::last_error().c_str(); }
+
+int mgc_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int mgc_model_load(const char *mod_path, mgc_model **out) {
+    if (!mod_path || !out) return mgc::set_error(MGC_E_ARG, "null argument");
+    try {
+        auto *m = new mgc_model();
+        m->m = parse_model_file(mod_path);
+        *out = m;
+        return MGC_OK;
+    } catch (const std::exception &ex) {
+        std::string msg = ex.what();
+        return mgc::set_error(msg.find("cannot open") != std::string::npos ? MGC_E_IO : MGC_E_PARSE, msg);
+    }
+}
+
+void mgc_model_free(mgc_model *m) { delete m; }
+
+int mgc_model_info(const mgc_model *m, int32_t info[6]) {
+    if (!m || !info) return mgc::set_error(MGC_E_ARG, "null argument");
+    info[0] = m->m.gcode; info[1] = m->m.cod_order; info[2] = m->m.non_order;
+    info[3] = m->m.min_len; info[4] = m->m.n_bac; info[5] = m->m.n_arc;
+    return MGC_OK;
+}
+
+int mgc_engine_create(int device, const mgc_model *const *models, int n_models, mgc_engine **out) {
+    if (!models || !out || n_models < 1 || n_models > MGC_MAX_MODELS) return mgc::set_error(MGC_E_ARG, "bad model list");
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return mgc::set_error(MGC_E_CUDA, std::string("no CUDA device available (") + cudaGetErrorString(ce) +
+                                              "); this engine has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) return mgc::set_error(MGC_E_ARG, "device index out of range");
+    mgc_engine *e = nullptr;
+    try {
+        CUDA_TRY(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+        if (prop.major < 10) throw std::runtime_error("CUDA: device is not sm_100 class (built for sm_100a only)");
+        e = new mgc_engine();
+        e->device = device;
+        e->n_sm = prop.multiProcessorCount;
+        CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+        for (auto &ev : e->ev) CUDA_TRY(cudaEventCreate(&ev));
+        e->n_models = n_models;
+        e->pm.resize(n_models);
+        for (int i = 0; i < n_models; i++) {
+            if (!models[i]) throw std::invalid_argument("null model");
+            e->models.push_back(models[i]->m);
+        }
+        upload_models(e);
+        *out = e;
+        return MGC_OK;
+    } catch (const std::invalid_argument &ex) {
+        delete e;
+        return mgc::set_error(MGC_E_ARG, ex.what());
+    } catch (const std::exception &ex) {
+        delete e;
+        return mgc::set_error(MGC_E_CUDA, ex.what());
+    }
+}
+
+void mgc_engine_destroy(mgc_engine *e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaDeviceSynchronize();
+    for (auto &p : e->pm) {
+        for (DevBuf *b : {&p.lc_full, &p.ln_full, &p.lc_ramp, &p.ln_ramp, &p.sc, &p.orfs, &p.starts, &p.surv, &p.sorted, &p.bcount,
+                          &p.cum, &p.prev, &p.gptr, &p.av_right, &p.av_left, &p.av_ls, &p.av_idx, &p.av_cum, &p.av_pmax, &p.av_parg,
+                          &p.chain, &p.gene_count, &p.gene_off, &p.contig_total, &p.genes})
+            b->release();
+    }
+    for (DevBuf *b : {&e->d_models, &e->ascii, &e->aoff, &e->cwoff, &e->clen, &e->grp2contig, &e->order, &e->lo, &e->hi, &e->gc,
+                      &e->tile_sums, &e->flags, &e->t_orfs, &e->t_starts, &e->t_surv, &e->t_sorted, &e->t_bcount, &e->t_gene_off,
+                      &e->t_genes, &e->t_chainbufs, &e->counters, &e->surv_counters, &e->work_counters, &e->model_cents,
+                      &e->gene_totals, &e->win_stride, &e->win_off, &e->win_labels, &e->win_cents})
+        b->release();
+    for (auto &ev : e->ev) cudaEventDestroy(ev);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+static int guarded(const std::function<void()> &fn) {
+    try {
+        fn();
+        return MGC_OK;
+    } catch (const mgc::AlphabetError &ex) {
+        return mgc::set_error(MGC_E_ALPHABET, ex.what());
+    } catch (const std::invalid_argument &ex) {
+        return mgc::set_error(MGC_E_ARG, ex.what());
+    } catch (const std::bad_alloc &) {
+        return mgc::set_error(MGC_E_NOMEM, "host allocation failed");
+    } catch (const std::exception &ex) {
+        std::string m = ex.what();
+        cudaGetLastError();
+        return mgc::set_error(m.find("scratch exhausted") != std::string::npos || m.find("out of device memory") != std::string::npos
+                                  ? MGC_E_NOMEM
+                                  : MGC_E_CUDA,
+                              m);
+    }
+}
+
+int mgc_upload_batch(mgc_engine *e, const char *seq, const int64_t *offsets, int32_t n_contigs) {
+    if (!e || !seq || !offsets) return mgc::set_error(MGC_E_ARG, "null argument");
+    return guarded([&] { do_upload(e, seq, offsets, n_contigs); });
+}
+
+int mgc_decode_resident(mgc_engine *e, mgc_result **out) {
+    if (!e || !out) return mgc::set_error(MGC_E_ARG, "null argument");
+    return guarded([&] { *out = do_decode(e); });
+}
+
+int mgc_decode_batch(mgc_engine *e, const char *seq, const int64_t *offsets, int32_t n_contigs, mgc_result **out) {
+    if (!e || !seq || !offsets || !out) return mgc::set_error(MGC_E_ARG, "null argument");
+    return guarded([&] {
+        do_upload(e, seq, offsets, n_contigs);
+        *out = do_decode(e);
+    });
+}
+
+int64_t mgc_debug_candidates(mgc_engine *e, int model, mgc_candidate *out, int64_t cap) {
+    if (!e || model < 0 || model >= e->n_models || !e->have_genes) return mgc::set_error(MGC_E_ARG, "bad argument");
+    int64_t n = -1;
+    int rc = guarded([&] {
+        CUDA_TRY(cudaSetDevice(e->device));
+        unsigned long long ns = 0;
+        CUDA_TRY(cudaMemcpy(&ns, e->surv_counters.as<unsigned long long>() + model, 8, cudaMemcpyDeviceToHost));
+        std::vector<Cand> c(ns);
+        std::vector<double> cum(ns);
+        if (ns) {
+            CUDA_TRY(cudaMemcpy(c.data(), e->pm[model].sorted.p, ns * sizeof(Cand), cudaMemcpyDeviceToHost));
+            CUDA_TRY(cudaMemcpy(cum.data(), e->pm[model].cum.p, ns * 8, cudaMemcpyDeviceToHost));
+        }
+        n = (int64_t)ns;
+        for (int64_t i = 0; i < n && i < cap && out; i++) {
+            mgc_candidate &o = out[i];
+            o.contig = c[i].contig; o.left = c[i].left; o.right = c[i].right; o.strand = c[i].strand; o.gc = c[i].gc;
+            o.domain = c[i].flags & 1; o.partial_start = (c[i].flags >> 1) & 1; o.partial_stop = (c[i].flags >> 2) & 1;
+            o.total = c[i].total; o.cum = cum[i];
+        }
+    });
+    return rc == MGC_OK ? n : rc;
+}
+
+int mgc_engine_stats(const mgc_engine *e, mgc_stats *out) {
+    if (!e || !out) return mgc::set_error(MGC_E_ARG, "null argument");
+    *out = e->stats;
+    return MGC_OK;
+}
+
+int64_t mgc_result_num_genes(const mgc_result *r, int model) {
+    if (!r || model < 0 || model >= r->n_models) return -1;
+    return (int64_t)r->genes[model].size();
+}
+
+const mgc_gene *mgc_result_genes(const mgc_result *r, int model) {
+    if (!r || model < 0 || model >= r->n_models) return nullptr;
+    return r->genes[model].data();
+}
+
+const double *mgc_result_contig_totals(const mgc_result *r, int model) {
+    if (!r || model < 0 || model >= r->n_models) return nullptr;
+    return r->contig_totals[model].data();
+}
+
+int mgc_result_model_cents(const mgc_result *r, int64_t *cents) {
+    if (!r || !cents) return mgc::set_error(MGC_E_ARG, "null argument");
+    for (int i = 0; i < r->n_models; i++) cents[i] = r->cents[i];
+    return MGC_OK;
+}
+
+void mgc_result_free(mgc_result *r) { delete r; }
+
+int mgc_window_counts(const int64_t *contig_len, const int32_t *stride, int32_t n_contigs, int32_t window, int32_t consecutive,
+                      int short_contigs, int64_t *win_offsets) {
+    if (!contig_len || !stride || !win_offsets || window <= 0) return mgc::set_error(MGC_E_ARG, "bad argument");
+    int64_t acc = 0;
+    for (int32_t c = 0; c < n_contigs; c++) {
+        win_offsets[c] = acc;
+        const int64_t L = contig_len[c], st = stride[c];
+        if (st <= 0) return mgc::set_error(MGC_E_ARG, "stride must be positive");
+        int64_t nw;
+        if (L <= 0) nw = 0;
+        else if (L <= 5000 && !short_contigs) nw = 1;                         // bin/pipeline.py:196-225
+        else if (L <= (int64_t)window + (int64_t)(consecutive - 1) * st)      // bin/pipeline.py:227-275
+            nw = L > window ? (L - window + st - 1) / st + 1 : 1;
+        else nw = (L + st - 1) / st;                                          // bin/pipeline.py:194,329
+        acc += nw;
+    }
+    win_offsets[n_contigs] = acc;
+    return MGC_OK;
+}
+
+int mgc_window_labels(mgc_engine *e, const int32_t *stride, int32_t window, int32_t consecutive, int short_contigs,
+                      const int64_t *win_offsets, int32_t *labels, int64_t *cents) {
+    if (!e || !stride || !win_offsets || !labels || !cents) return mgc::set_error(MGC_E_ARG, "null argument");
+    if (!e->have_genes) return mgc::set_error(MGC_E_ARG, "decode a batch before asking for window labels");
+    return guarded([&] {
+        CUDA_TRY(cudaSetDevice(e->device));
+        const int32_t n = e->n_contigs;
+        const int M = e->n_models;
+        const int64_t nw = win_offsets[n];
+        cudaStream_t st = e->stream;
+        e->win_stride.ensure((size_t)n * 4);
+        e->win_off.ensure((size_t)(n + 1) * 8);
+        e->win_labels.ensure((size_t)std::max<int64_t>(nw, 1) * 4);
+        e->win_cents.ensure((size_t)std::max<int64_t>(nw, 1) * M * 8);
+        CUDA_TRY(cudaMemcpyAsync(e->win_stride.p, stride, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(e->win_off.p, win_offsets, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
+        launch_windows(e->t_genes.as<const mgc_gene *>(), e->t_gene_off.as<const uint32_t *>(), M, e->clen.as<int32_t>(),
+                       e->win_stride.as<int32_t>(), e->win_off.as<int64_t>(), n, window, consecutive, short_contigs,
+                       e->win_labels.as<int32_t>(), e->win_cents.as<long long>(), st);
+        if (nw) {
+            CUDA_TRY(cudaMemcpyAsync(labels, e->win_labels.p, (size_t)nw * 4, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(cents, e->win_cents.p, (size_t)nw * M * 8, cudaMemcpyDeviceToHost, st));
+        }
+        CUDA_TRY(cudaStreamSynchronize(st));
+        CUDA_TRY(cudaGetLastError());
+    });
+}
+
+}  // extern "C"

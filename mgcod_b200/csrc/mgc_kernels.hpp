@@ -1,0 +1,39 @@
+// mgc_kernels.hpp — launch wrappers implemented in mgc_kernels.cu
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/mgcod_b200.h"
+
+namespace mgc {
+
+struct DevModel;
+struct OrfRec;
+struct Cand;
+struct Planes;
+struct ChainBufs;
+
+int launch_exclusive_scan(const uint32_t *in, uint32_t *out, uint32_t *tile_sums, int64_t n, uint32_t *grand_total,
+                          cudaStream_t st);
+void launch_groups(const int64_t *cwoff, int32_t n_contigs, int64_t n_groups, int32_t *grp2contig, cudaStream_t st);
+void launch_pack(const char *ascii, const int64_t *aoff, const int64_t *cwoff, const int32_t *clen, const int32_t *grp2contig,
+                 int64_t W, uint32_t *lo, uint32_t *hi, uint32_t *gccount, int *bad_letter, cudaStream_t st);
+void launch_orf_find(Planes pl, const int64_t *cwoff, const int32_t *clen, const int32_t *grp2contig, const DevModel *models,
+                     int n_models, OrfRec *const *orfs_m, uint32_t *const *starts_m, unsigned long long *counters_m,
+                     uint32_t cap_orf, uint32_t cap_starts, cudaStream_t st);
+void launch_orf_score(Planes pl, const uint32_t *gcpre, const int64_t *cwoff, const int32_t *clen, const DevModel *models,
+                      int n_models, OrfRec *const *orfs_m, uint32_t *const *starts_m, const unsigned long long *counters_m,
+                      Cand *const *surv_m, uint32_t *const *bcount_m, unsigned long long *surv_counters, uint32_t cap_orf,
+                      uint32_t cap_surv, const ChainBufs *bufs_m, int n_sm, cudaStream_t st);
+void launch_scatter(const Cand *const *surv_m, Cand *const *sorted_m, uint32_t *const *boff_m,
+                    const unsigned long long *surv_counters, const int64_t *cwoff, uint32_t cap_surv, int n_models, int n_sm,
+                    cudaStream_t st);
+void launch_chain(const ChainBufs *bufs_m, const int64_t *cwoff, const int32_t *clen, const int32_t *order, int32_t n_contigs,
+                  int *work_counters, int n_models, int n_sm, cudaStream_t st);
+void launch_gather(const ChainBufs *bufs_m, const uint32_t *const *gene_off_m, mgc_gene *const *genes_m, const int64_t *cwoff,
+                   const int32_t *clen, int32_t n_contigs, long long *model_cents, int n_models, int n_sm, cudaStream_t st);
+void launch_windows(const mgc_gene *const *genes_m, const uint32_t *const *gene_off_m, int n_models, const int32_t *clen,
+                    const int32_t *stride, const int64_t *win_off, int32_t n_contigs, int32_t window, int32_t consecutive,
+                    int short_contigs, int32_t *labels, long long *cents, cudaStream_t st);
+
+}  // namespace mgc

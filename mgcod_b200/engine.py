@@ -1,0 +1,211 @@
+"""Python face of the C-ABI (include/mgcod_b200.h): model files, the per-GPU engine and decode results.
+
+This is the in-process replacement for the reference's process boundary
+``subprocess.check_call([gmhmmp2, '-M', mgm_<code>.mod, '-s', fasta, '-f', 'gff', '-o', ...])``
+(reference bin/data.py:39-54): one :class:`Engine` holds the four parameter files on the GPU and decodes
+whole batches of contigs under all of them in one call.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import Candidate, Gene, Stats
+
+GENE_DTYPE = np.dtype([("contig", "<i4"), ("left", "<i4"), ("right", "<i4"), ("strand", "i1"), ("domain", "i1"),
+                       ("partial_left", "i1"), ("partial_right", "i1"), ("gc", "<i4"), ("_pad", "<i4"), ("logodd", "<f8")])
+assert GENE_DTYPE.itemsize == C.sizeof(Gene) == 32
+CAND_DTYPE = np.dtype([("contig", "<i4"), ("left", "<i4"), ("right", "<i4"), ("strand", "<i4"), ("gc", "<i4"),
+                       ("domain", "<i4"), ("partial_start", "<i4"), ("partial_stop", "<i4"), ("total", "<f8"), ("cum", "<f8")])
+assert CAND_DTYPE.itemsize == C.sizeof(Candidate)
+
+#: label order used everywhere in Mgcod (reference bin/pipeline.py:53-54)
+MGCOD_CODES = (11, 4, 15, 101)
+
+
+class MgcodError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"[{code}] {msg}")
+        self.code = code
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise MgcodError(rc, _lib.last_error())
+
+
+class ModelFile:
+    """A parsed ``.mod`` parameter file (host side; no GPU needed)."""
+
+    def __init__(self, path: str):
+        self.path = str(path)
+        self._h = C.c_void_p()
+        _check(_lib.lib().mgc_model_load(self.path.encode(), C.byref(self._h)))
+        info = (C.c_int32 * 6)()
+        _check(_lib.lib().mgc_model_info(self._h, info))
+        self.gcode, self.cod_order, self.non_order, self.gene_min_length, self.n_bacterial, self.n_archaeal = list(info)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            _lib.lib().mgc_model_free(self._h)
+            self._h = None
+
+
+def pack_sequences(seqs: Sequence[bytes | str]) -> tuple[np.ndarray, np.ndarray]:
+    """Concatenate sequences into one uint8 buffer + int64 offsets (the layout mgc_decode_batch takes)."""
+    bs = [s.encode() if isinstance(s, str) else bytes(s) for s in seqs]
+    offs = np.zeros(len(bs) + 1, dtype=np.int64)
+    np.cumsum([len(b) for b in bs], out=offs[1:])
+    buf = np.frombuffer(b"".join(bs), dtype=np.uint8) if offs[-1] else np.zeros(0, np.uint8)
+    return buf, offs
+
+
+class Result:
+    """Genes of one decoded batch for every model of the engine."""
+
+    def __init__(self, handle: C.c_void_p, n_models: int, n_contigs: int):
+        self._h = handle
+        self.n_models = n_models
+        self.n_contigs = n_contigs
+
+    def genes(self, model: int) -> np.ndarray:
+        """Structured array (GENE_DTYPE), ordered by (contig, left); 1-based inclusive coordinates."""
+        L = _lib.lib()
+        n = L.mgc_result_num_genes(self._h, model)
+        if n < 0:
+            raise IndexError(model)
+        if n == 0:
+            return np.zeros(0, GENE_DTYPE)
+        p = L.mgc_result_genes(self._h, model)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(n * 32,)).view(GENE_DTYPE).copy()
+
+    def contig_totals(self, model: int) -> np.ndarray:
+        p = _lib.lib().mgc_result_contig_totals(self._h, model)
+        return np.ctypeslib.as_array(p, shape=(self.n_contigs,)).copy()
+
+    def model_cents(self) -> np.ndarray:
+        out = np.zeros(self.n_models, dtype=np.int64)
+        _check(_lib.lib().mgc_result_model_cents(self._h, out.ctypes.data_as(C.POINTER(C.c_int64))))
+        return out
+
+    def write(self, model: int, contig_ids: Sequence[str], contig_len: Sequence[int], seq_file: str, mod_file: str,
+              gcode: int, out_path: str, fmt: str = "gff") -> None:
+        ids = (C.c_char_p * len(contig_ids))(*[s.encode() for s in contig_ids])
+        lens = np.asarray(contig_len, dtype=np.int64)
+        _check(_lib.lib().mgc_write_gff(self._h, model, ids, lens.ctypes.data_as(C.POINTER(C.c_int64)), len(contig_ids),
+                                        seq_file.encode(), mod_file.encode(), gcode, out_path.encode(), fmt.encode()))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            _lib.lib().mgc_result_free(self._h)
+            self._h = None
+
+
+class Engine:
+    """One per process per GPU.  ``models`` in label order (Mgcod: codes 11, 4, 15, 101)."""
+
+    def __init__(self, models: Sequence[ModelFile | str], device: int = 0):
+        self.models = [m if isinstance(m, ModelFile) else ModelFile(m) for m in models]
+        arr = (C.c_void_p * len(self.models))(*[m._h for m in self.models])
+        self._h = C.c_void_p()
+        _check(_lib.lib().mgc_engine_create(device, arr, len(self.models), C.byref(self._h)))
+        self.device = device
+        self.n_contigs = 0
+        self._keep = None
+
+    @property
+    def n_models(self) -> int:
+        return len(self.models)
+
+    def upload(self, buf: np.ndarray, offsets: np.ndarray) -> None:
+        """Host→device copy of a batch (``buf`` may be a pinned torch tensor's numpy view)."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        self._keep = (buf, offsets)
+        self.n_contigs = len(offsets) - 1
+        _check(_lib.lib().mgc_upload_batch(self._h, C.c_void_p(buf.ctypes.data), offsets.ctypes.data_as(C.POINTER(C.c_int64)),
+                                           self.n_contigs))
+
+    def decode_resident(self) -> Result:
+        r = C.c_void_p()
+        _check(_lib.lib().mgc_decode_resident(self._h, C.byref(r)))
+        return Result(r, self.n_models, self.n_contigs)
+
+    def decode(self, seqs: Sequence[bytes | str]) -> Result:
+        buf, offs = pack_sequences(seqs)
+        return self.decode_buffer(buf, offs)
+
+    def decode_buffer(self, buf: np.ndarray, offsets: np.ndarray) -> Result:
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        self.n_contigs = len(offsets) - 1
+        r = C.c_void_p()
+        _check(_lib.lib().mgc_decode_batch(self._h, C.c_void_p(buf.ctypes.data), offsets.ctypes.data_as(C.POINTER(C.c_int64)),
+                                           self.n_contigs, C.byref(r)))
+        return Result(r, self.n_models, self.n_contigs)
+
+    def stats(self) -> dict:
+        s = Stats()
+        _check(_lib.lib().mgc_engine_stats(self._h, C.byref(s)))
+        return {n: getattr(s, n) for n, _ in Stats._fields_}
+
+    def candidates(self, model: int) -> np.ndarray:
+        """Testing hook: pruned candidates (total > 0) of the last decode with their chain scores."""
+        L = _lib.lib()
+        n = L.mgc_debug_candidates(self._h, model, None, 0)
+        if n < 0:
+            raise MgcodError(int(n), _lib.last_error())
+        out = np.zeros(n, CAND_DTYPE)
+        if n:
+            L.mgc_debug_candidates(self._h, model, out.ctypes.data_as(C.POINTER(Candidate)), n)
+        return out
+
+    def window_labels(self, contig_len: Sequence[int], stride: Sequence[int], window: int, consecutive: int,
+                      short_contigs: bool) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """→ (win_offsets[n+1], labels[nwin], cents[nwin, n_models]) for the last decoded batch
+        (reference bin/pipeline.py:157-385)."""
+        L = _lib.lib()
+        lens = np.asarray(contig_len, dtype=np.int64)
+        st = np.asarray(stride, dtype=np.int32)
+        offs = np.zeros(len(lens) + 1, dtype=np.int64)
+        _check(L.mgc_window_counts(lens.ctypes.data_as(C.POINTER(C.c_int64)), st.ctypes.data_as(C.POINTER(C.c_int32)), len(lens),
+                                   window, consecutive, int(short_contigs), offs.ctypes.data_as(C.POINTER(C.c_int64))))
+        nw = int(offs[-1])
+        labels = np.zeros(max(nw, 1), dtype=np.int32)
+        cents = np.zeros((max(nw, 1), self.n_models), dtype=np.int64)
+        _check(L.mgc_window_labels(self._h, st.ctypes.data_as(C.POINTER(C.c_int32)), window, consecutive, int(short_contigs),
+                                   offs.ctypes.data_as(C.POINTER(C.c_int64)), labels.ctypes.data_as(C.POINTER(C.c_int32)),
+                                   cents.ctypes.data_as(C.POINTER(C.c_int64))))
+        return offs, labels[:nw], cents[:nw]
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            _lib.lib().mgc_engine_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+
+def synth_metagenome(seed: int, total_bp: int, min_len: int = 5000, max_len: int = 500000, threads: int = 8,
+                     out: np.ndarray | None = None) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """Synthetic contigs of BASELINE.json config 5: lengths ~ L^-2 on [min_len, max_len] until
+    ``total_bp``; gene-like content with a per-contig GC regime and true genetic code.
+    → (ascii buffer uint8, offsets int64[n+1], truth_code int32[n])."""
+    L = _lib.lib()
+    cap = total_bp // min_len + 16
+    lens = np.zeros(cap, dtype=np.int64)
+    n = L.mgc_synth_lengths(seed, total_bp, min_len, max_len, lens.ctypes.data_as(C.POINTER(C.c_int64)), cap)
+    if n < 0:
+        raise MgcodError(int(n), _lib.last_error())
+    lens = lens[:n].copy()
+    offs = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(lens, out=offs[1:])
+    buf = out if out is not None else np.empty(int(offs[-1]), dtype=np.uint8)
+    if buf.size < offs[-1]:
+        raise ValueError("output buffer too small")
+    truth = np.zeros(n, dtype=np.int32)
+    _check(L.mgc_synth_contigs(seed, lens.ctypes.data_as(C.POINTER(C.c_int64)), n, C.c_void_p(buf.ctypes.data),
+                               truth.ctypes.data_as(C.POINTER(C.c_int32)), threads))
+    return buf[:int(offs[-1])], offs, truth

@@ -1,0 +1,30 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+
+
+@pytest.fixture(scope="session")
+def model_dir(tmp_path_factory):
+    """Parametric 82-section model set (41 bacterial + 41 archaeal GC bins) for codes 11/4/15/101."""
+    from mgcod_b200 import synth
+    d = tmp_path_factory.mktemp("models")
+    synth.write_model_set(str(d), kind="parametric")
+    return str(d)
+
+
+@pytest.fixture(scope="session")
+def small_model_dir(tmp_path_factory):
+    """Few-section variants with odd orders to exercise ramp / gap-fill rules."""
+    from mgcod_b200 import synth
+    d = tmp_path_factory.mktemp("models_small")
+    synth.write_model_set(str(d), kind="parametric", cod_order=3, non_order=1, bins=(28, 35, 44, 57), domains=("B", "A"))
+    return str(d)
