@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: bp x models / s decoded (BASELINE.json metric) on synthetic contigs.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--total-bp B]
+
+A "step" decodes one batch of synthetic contigs (BASELINE.json config 5: lengths ~ L^-2 on
+[5 kb, 500 kb], gene-like content, four genetic codes) under the four parameter files
+(parametric 41 bacterial + 41 archaeal GC-bin sections each, order 4/2).  At N = 1 the batch is the full
+1 Gbp; under torchrun (N > 1) every rank decodes its own 1 Gbp shard (weak scaling, no data-path
+collective; the only exchange is the final max-over-ranks of the timings).
+
+  value   device-resident: ASCII contigs already in HBM, K x (pack -> ORFs -> scores -> chain -> genes to host)
+  e2e     the public call Engine.decode_buffer() on pinned HOST buffers: H2D of the sequences and D2H of the
+          genes inside the timed region
+
+`--impl reference` times the reference's own gene finder (oracle/_ref/gmhmmp2, the binary Mgcod shells out
+to; else the C port in oracle/) on the box's host cores on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CODES = (11, 4, 15, 101)
+SEED = 20260101
+METRIC = "bp_x_models_per_s_decoded"
+UNIT = "bp*models/s"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([t.strip() for t in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=3)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def write_models(dirname: str) -> list[str]:
+    from mgcod_b200 import synth
+    paths = synth.write_model_set(dirname, kind="parametric")
+    return [paths[c] for c in CODES]
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's own gene finder on host cores, bounded sample
+# --------------------------------------------------------------------------------------------------
+def _ref_binary() -> str | None:
+    p = os.path.join(ROOT, "oracle", "_ref", "gmhmmp2")
+    if os.path.isfile(p) and os.access(p, os.X_OK):
+        try:
+            r = subprocess.run([p], capture_output=True, text=True, timeout=20)
+            if "GeneMark.hmm-2" in (r.stdout + r.stderr):
+                return p
+        except (OSError, subprocess.TimeoutExpired):
+            pass
+    return None
+
+
+def cpu_reference_run(buf: np.ndarray, offs: np.ndarray, model_paths: list[str], sample_bp: int, workdir: str, cores: int) -> dict:
+    """Decode the first contigs of the workload (about sample_bp) under the 4 models on `cores` host threads."""
+    n = int(np.searchsorted(offs, sample_bp, side="left"))
+    n = max(1, min(n, len(offs) - 1))
+    bp = int(offs[n])
+    binary = _ref_binary()
+    nshard = max(1, min(cores, n))
+    bounds = [int(round(i * n / nshard)) for i in range(nshard + 1)]
+    t0 = time.perf_counter()
+    if binary:
+        shards = []
+        for s in range(nshard):
+            fa = os.path.join(workdir, f"shard{s}.fa")
+            with open(fa, "wb") as fh:
+                for c in range(bounds[s], bounds[s + 1]):
+                    fh.write(b">c%d\n" % c)
+                    fh.write(buf[offs[c]:offs[c + 1]].tobytes())
+                    fh.write(b"\n")
+            shards.append(fa)
+        t0 = time.perf_counter()  # FASTA writing is not part of the reference's decode time
+        jobs = [(fa, mp, os.path.join(workdir, f"out_{si}_{mi}.gff")) for si, fa in enumerate(shards) for mi, mp in enumerate(model_paths)]
+        procs, idx = [], 0
+        running = []
+        while idx < len(jobs) or running:
+            while idx < len(jobs) and len(running) < cores:
+                fa, mp, out = jobs[idx]
+                running.append(subprocess.Popen([binary, "-M", mp, "-s", fa, "-f", "gff", "-o", out], stdout=subprocess.DEVNULL,
+                                                stderr=subprocess.DEVNULL))
+                idx += 1
+            running = [p for p in running if p.poll() is None]
+            time.sleep(0.002)
+        kind = "reference"
+        used = min(cores, len(jobs))
+    else:
+        from concurrent.futures import ThreadPoolExecutor
+        from oracle import gmhmm
+        models = [gmhmm.Model(p) for p in model_paths]
+
+        def work(s):
+            for c in range(bounds[s], bounds[s + 1]):
+                seq = buf[offs[c]:offs[c + 1]].tobytes()
+                for m in models:
+                    m.decode(seq)
+        with ThreadPoolExecutor(nshard) as ex:  # ctypes releases the GIL inside the C calls
+            list(ex.map(work, range(nshard)))
+        kind = "port"
+        used = nshard
+    dt = time.perf_counter() - t0
+    return {"value": bp * len(model_paths) / dt, "unit": UNIT, "cores": used, "kind": kind,
+            "sample": f"first {n} contigs = {bp} bp x {len(model_paths)} models of the step's workload, {dt:.2f} s wall"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--total-bp", type=int, default=int(os.environ.get("MGCOD_BENCH_BP", 1_000_000_000)),
+                    help="bp per GPU per step (default: 1 Gbp, BASELINE.json config 5)")
+    ap.add_argument("--cpu-sample-bp", type=int, default=16_000_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    workload = (f"synthetic metagenome seed {SEED}: contigs 5-500 kb (p(L)~L^-2), {args.total_bp} bp per GPU x 4 genetic codes "
+                f"(11/4/15/101), parametric 82-section order-4/2 models")
+    config = {"workload": workload, "bp_per_gpu": args.total_bp, "models": 4,
+              "l2": "inputs (1 B/nt ASCII + 0.5 B/nt planes) far exceed the 126 MB L2; no explicit flush"}
+
+    workdir = tempfile.mkdtemp(prefix=f"mgcod_bench_{rank}_")
+    try:
+        model_paths = write_models(os.path.join(workdir, "models"))
+        if args.impl == "reference":
+            if rank != 0:
+                return 0
+            from mgcod_b200.engine import synth_metagenome
+            sample = min(args.total_bp, max(args.cpu_sample_bp, 1))
+            buf, offs, _ = synth_metagenome(SEED, sample, threads=min(cores, 16))
+            vals = []
+            for it in range(args.warmup + args.steps):
+                r = cpu_reference_run(buf, offs, model_paths, sample, workdir, cores)
+                if it >= args.warmup:
+                    vals.append(r)
+            v = float(np.mean([r["value"] for r in vals]))
+            bp = int(offs[-1])
+            last = vals[-1]
+            last["value"] = v
+            print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                              "warmup": args.warmup, "ms_per_step": 1e3 * bp * 4 / v, "higher_is_better": True, "scaling": "weak",
+                              "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "cpu_baseline": last,
+                              "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                              "gpu_launches": 0}))
+            return 0
+
+        import torch
+        import torch.distributed as dist
+        from mgcod_b200.engine import Engine, synth_metagenome
+
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
+        torch.cuda.set_device(local)
+        if world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+        def barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        # workload in pinned host memory
+        t0 = time.perf_counter()
+        pinned = torch.empty(args.total_bp + 600_000, dtype=torch.uint8, pin_memory=True)
+        buf, offs, truth = synth_metagenome(SEED + rank, args.total_bp, max_len=int(os.environ.get('MGCOD_BENCH_MAXLEN', 500000)),
+                                            threads=min(cores, 32), out=pinned.numpy())
+        gen_s = time.perf_counter() - t0
+        total_bp = int(offs[-1])
+        engine = Engine(model_paths, device=local)
+        units = total_bp * engine.n_models
+
+        # ---- warm-up (e2e path: allocations, first-touch) ----
+        for _ in range(args.warmup):
+            res = engine.decode_buffer(buf, offs)
+            del res
+        # ---- device-resident timing ----
+        engine.upload(buf, offs)
+        res = engine.decode_resident()
+        del res
+        sampler = ClockSampler(local)
+        barrier()
+        sampler.start()
+        t0 = time.perf_counter()
+        phase = {}
+        launches = 0
+        for _ in range(args.steps):
+            res = engine.decode_resident()
+            st = engine.stats()
+            for k in ("pack", "orf_find", "orf_score", "order", "chain", "aggregate", "d2h", "total"):
+                phase[k] = phase.get(k, 0.0) + st[k]
+            launches += st["kernel_launches"]
+            n_genes = st["n_genes"]
+            d2h_bytes = n_genes * 32 + engine.n_contigs * 8 * engine.n_models
+            counts = {k: st[k] for k in ("n_orfs", "n_starts", "n_candidates", "n_genes")}
+            del res
+        barrier()
+        dt_res = time.perf_counter() - t0
+        clocks = sampler.stop()
+        # ---- end-to-end timing through the public call with host buffers ----
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            res = engine.decode_buffer(buf, offs)
+            cents = res.model_cents()
+            del res
+        barrier()
+        dt_e2e = time.perf_counter() - t0
+
+        times = torch.tensor([dt_res, dt_e2e], dtype=torch.float64, device="cuda")
+        tot_units = torch.tensor([float(units)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(times, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tot_units, op=dist.ReduceOp.SUM)
+        dt_res, dt_e2e = float(times[0]), float(times[1])
+        all_units = float(tot_units[0])
+
+        if rank == 0:
+            peak, peak_src = _peaks()
+            # dominant kernel = k_orf_score; algorithmic bytes of one launch (all 4 models): both strands' planes
+            # (0.5 B/nt, read once per model) + ORF records + start list + surviving candidates + bucket histogram
+            score_ms = phase["orf_score"] / args.steps
+            alg_bytes = (4 * 0.5 * total_bp + counts["n_orfs"] * 20 + counts["n_starts"] * 4 + counts["n_candidates"] * 36)
+            achieved = alg_bytes / (score_ms * 1e-3) / 1e9 if score_ms > 0 else 0.0
+            out = {
+                "metric": METRIC, "value": all_units * args.steps / dt_res, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 * dt_res / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": dict(config, contigs_per_gpu=int(len(truth))),
+                "e2e": {"value": all_units * args.steps / dt_e2e, "unit": UNIT, "h2d_bytes_per_step": int(total_bp + 8 * (len(offs))),
+                        "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": 1e3 * dt_e2e / args.steps},
+                "gpu_launches": int(launches),
+                "clocks": clocks,
+                "roofline": {"kernel": "k_orf_score", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                             "kernel_ms_per_launch": score_ms, "algorithmic_bytes_per_launch": alg_bytes},
+                "phases_ms_per_step": {k: v / args.steps for k, v in phase.items()},
+                "counts_per_step": counts,
+                "host": {"cores": cores, "workload_generation_s": gen_s},
+            }
+            if world == 1 and not args.no_cpu_baseline:
+                out["cpu_baseline"] = cpu_reference_run(buf, offs, model_paths, args.cpu_sample_bp, workdir, cores)
+            print(json.dumps(out))
+        engine.close()
+        if world > 1:
+            dist.destroy_process_group()
+    finally:
+        shutil.rmtree(workdir, ignore_errors=True)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -13,6 +13,12 @@
 
 namespace mgc {
 
+// four per-position numbers of one (bacterial, archaeal) section pair: coding log-likelihood and
+// coding - non-coding log-odds of each domain; one 32-byte sector per gather
+struct __align__(32) Quad {
+    double cB, oB, cA, oA;
+};
+
 struct DevModel {
     int gcode, kc, kn, min_len, nsec, kr, knr;
     int stop_sel;   // bit0 TAA, bit1 TAG, bit2 TGA are stops under this genetic code
@@ -20,7 +26,10 @@ struct DevModel {
     int nfull, nnon, nramp, nnramp;
     const double *lc_full, *ln_full, *lc_ramp, *ln_ramp;
     const SectionScalars *sc;
+    const Quad *quad;   // [npair][3][4^(kc+1)], plane-major k-mer index
+    int npair;
     int map[2][101];
+    int pair[101];      // gc -> index of its (secB, secA) pair in quad
 };
 
 // one stop-delimited ORF that has at least one start candidate of sufficient length

@@ -6,6 +6,8 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <memory>
+#include <mutex>
 #include <numeric>
 #include <stdexcept>
 #include <string>
@@ -22,12 +24,59 @@ struct mgc_model {
     Model m;
 };
 
+// Page-locked host blocks are expensive to create (cudaHostAlloc pins pages), so results borrow them from a
+// pool owned jointly by the engine and its outstanding results.
+struct PinnedPool {
+    struct Block {
+        void *p = nullptr;
+        size_t bytes = 0;
+    };
+    std::mutex mu;
+    std::vector<Block> free_blocks;
+    Block acquire(size_t need) {
+        need = std::max<size_t>(need, 4096);
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            size_t best = free_blocks.size();
+            for (size_t i = 0; i < free_blocks.size(); i++)
+                if (free_blocks[i].bytes >= need && (best == free_blocks.size() || free_blocks[i].bytes < free_blocks[best].bytes)) best = i;
+            if (best != free_blocks.size()) {
+                Block b = free_blocks[best];
+                free_blocks.erase(free_blocks.begin() + best);
+                return b;
+            }
+        }
+        Block b;
+        b.bytes = need + need / 4;
+        if (cudaHostAlloc(&b.p, b.bytes, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            throw std::bad_alloc();
+        }
+        return b;
+    }
+    void release(Block b) {
+        if (!b.p) return;
+        std::lock_guard<std::mutex> lk(mu);
+        free_blocks.push_back(b);
+    }
+    ~PinnedPool() {
+        for (auto &b : free_blocks) cudaFreeHost(b.p);
+    }
+};
+
 struct mgc_result {
     int n_models = 0;
     int32_t n_contigs = 0;
-    std::vector<std::vector<mgc_gene>> genes;
-    std::vector<std::vector<double>> contig_totals;
+    std::shared_ptr<PinnedPool> pool;
+    std::vector<PinnedPool::Block> gene_blk, total_blk;
+    std::vector<int64_t> n_genes;
     std::vector<int64_t> cents;
+    ~mgc_result() {
+        if (pool) {
+            for (auto &b : gene_blk) pool->release(b);
+            for (auto &b : total_blk) pool->release(b);
+        }
+    }
 };
 
 namespace {
@@ -60,7 +109,7 @@ struct DevBuf {
 };
 
 struct PerModel {
-    DevBuf lc_full, ln_full, lc_ramp, ln_ramp, sc;
+    DevBuf lc_full, ln_full, lc_ramp, ln_ramp, sc, quad;
     DevBuf orfs, starts, surv, sorted, bcount, cum, prev, gptr;
     DevBuf av_right, av_left, av_ls, av_idx, av_cum, av_pmax, av_parg, chain, gene_count, gene_off, contig_total, genes;
 };
@@ -94,6 +143,7 @@ struct mgc_engine {
     uint32_t cap_orf = 0, cap_starts = 0, cap_surv = 0;
     bool have_batch = false, have_genes = false;
     mgc_stats stats;
+    std::shared_ptr<PinnedPool> pool = std::make_shared<PinnedPool>();
 };
 
 namespace {
@@ -137,6 +187,39 @@ void upload_models(mgc_engine *e) {
         d.ln_ramp = p.ln_ramp.as<double>();
         d.sc = p.sc.as<SectionScalars>();
         std::memcpy(d.map, m.map, sizeof(d.map));
+        // section pairs: every gc maps to (secB, secA); distinct pairs get one Quad table each
+        std::vector<std::pair<int, int>> pairs;
+        for (int g = 0; g <= 100; g++) {
+            std::pair<int, int> pr(m.map[0][g], m.map[1][g]);
+            size_t k = std::find(pairs.begin(), pairs.end(), pr) - pairs.begin();
+            if (k == pairs.size()) pairs.push_back(pr);
+            d.pair[g] = (int)k;
+        }
+        d.npair = (int)pairs.size();
+        const int kc = d.kc, kn = d.kn;
+        const size_t nfull = (size_t)d.nfull, nnon = (size_t)d.nnon;
+        std::vector<Quad> q(pairs.size() * 3 * nfull);
+        for (size_t pi = 0; pi < pairs.size(); pi++)
+            for (int ph = 0; ph < 3; ph++)
+                for (size_t idx = 0; idx < nfull; idx++) {
+                    // plane-major index: hi bits above lo bits, kc+1 letters; the non-coding context is the last kn+1 letters
+                    const uint32_t hb = (uint32_t)(idx >> (kc + 1)), lb = (uint32_t)(idx & ((1u << (kc + 1)) - 1u));
+                    const size_t idn = ((size_t)(hb >> (kc - kn)) << (kn + 1)) | (lb >> (kc - kn));
+                    Quad &e4 = q[(pi * 3 + ph) * nfull + idx];
+                    e4 = Quad{0, 0, 0, 0};
+                    if (pairs[pi].first >= 0) {
+                        const size_t sB = (size_t)pairs[pi].first;
+                        e4.cB = m.lc_full[(sB * 3 + ph) * nfull + idx];
+                        e4.oB = e4.cB - m.ln_full[sB * nnon + idn];
+                    }
+                    if (pairs[pi].second >= 0) {
+                        const size_t sA = (size_t)pairs[pi].second;
+                        e4.cA = m.lc_full[(sA * 3 + ph) * nfull + idx];
+                        e4.oA = e4.cA - m.ln_full[sA * nnon + idn];
+                    }
+                }
+        up(p.quad, q.data(), q.size() * sizeof(Quad));
+        d.quad = p.quad.as<Quad>();
     }
     e->d_models.ensure(sizeof(DevModel) * e->n_models);
     CUDA_TRY(cudaMemcpy(e->d_models.p, dm.data(), sizeof(DevModel) * e->n_models, cudaMemcpyHostToDevice));
@@ -356,19 +439,19 @@ mgc_result *do_decode(mgc_engine *e) {
         e->stats.n_candidates += (int64_t)h_surv[i];
         e->stats.n_genes += h_gtot[i];
     }
-    // genes
-    auto *res = new mgc_result();
+    // genes into pooled page-locked blocks
+    std::unique_ptr<mgc_result> res(new mgc_result());
     res->n_models = M;
     res->n_contigs = n;
-    res->genes.resize(M);
-    res->contig_totals.resize(M);
+    res->pool = e->pool;
     res->cents.assign(h_cents.begin(), h_cents.end());
+    res->n_genes.assign(h_gtot.begin(), h_gtot.end());
     for (int i = 0; i < M; i++) {
-        res->genes[i].resize(h_gtot[i]);
-        res->contig_totals[i].resize(n);
+        res->gene_blk.push_back(e->pool->acquire((size_t)h_gtot[i] * sizeof(mgc_gene)));
+        res->total_blk.push_back(e->pool->acquire((size_t)n * 8));
         if (h_gtot[i])
-            CUDA_TRY(cudaMemcpyAsync(res->genes[i].data(), e->pm[i].genes.p, (size_t)h_gtot[i] * sizeof(mgc_gene), cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaMemcpyAsync(res->contig_totals[i].data(), e->pm[i].contig_total.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(res->gene_blk[i].p, e->pm[i].genes.p, (size_t)h_gtot[i] * sizeof(mgc_gene), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(res->total_blk[i].p, e->pm[i].contig_total.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
     }
     CUDA_TRY(cudaEventRecord(e->ev[7], st));
     CUDA_TRY(cudaStreamSynchronize(st));
@@ -383,7 +466,7 @@ mgc_result *do_decode(mgc_engine *e) {
     cudaEventElapsedTime(&ms, e->ev[0], e->ev[7]); e->stats.total = ms;
     e->stats.kernel_launches = launches;
     e->have_genes = true;
-    return res;
+    return res.release();
 }
 
 }  // namespace
@@ -472,7 +555,7 @@ void mgc_engine_destroy(mgc_engine *e) {
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
     for (auto &p : e->pm) {
-        for (DevBuf *b : {&p.lc_full, &p.ln_full, &p.lc_ramp, &p.ln_ramp, &p.sc, &p.orfs, &p.starts, &p.surv, &p.sorted, &p.bcount,
+        for (DevBuf *b : {&p.lc_full, &p.ln_full, &p.lc_ramp, &p.ln_ramp, &p.sc, &p.quad, &p.orfs, &p.starts, &p.surv, &p.sorted, &p.bcount,
                           &p.cum, &p.prev, &p.gptr, &p.av_right, &p.av_left, &p.av_ls, &p.av_idx, &p.av_cum, &p.av_pmax, &p.av_parg,
                           &p.chain, &p.gene_count, &p.gene_off, &p.contig_total, &p.genes})
             b->release();
@@ -557,17 +640,17 @@ int mgc_engine_stats(const mgc_engine *e, mgc_stats *out) {
 
 int64_t mgc_result_num_genes(const mgc_result *r, int model) {
     if (!r || model < 0 || model >= r->n_models) return -1;
-    return (int64_t)r->genes[model].size();
+    return r->n_genes[model];
 }
 
 const mgc_gene *mgc_result_genes(const mgc_result *r, int model) {
     if (!r || model < 0 || model >= r->n_models) return nullptr;
-    return r->genes[model].data();
+    return static_cast<const mgc_gene *>(r->gene_blk[model].p);
 }
 
 const double *mgc_result_contig_totals(const mgc_result *r, int model) {
     if (!r || model < 0 || model >= r->n_models) return nullptr;
-    return r->contig_totals[model].data();
+    return static_cast<const double *>(r->total_blk[model].p);
 }
 
 int mgc_result_model_cents(const mgc_result *r, int64_t *cents) {

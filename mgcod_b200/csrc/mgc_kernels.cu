@@ -37,6 +37,14 @@ __device__ __forceinline__ int warp_min_i(int v) {
     for (int o = 16; o; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
+__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o);
+        v = w < v ? w : v;
+    }
+    return v;
+}
 __device__ __forceinline__ long long warp_min_ll(long long v) {
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
@@ -326,8 +334,13 @@ __global__ void __launch_bounds__(128) k_orf_find(Planes pl, const int64_t *__re
 // ------------------------------------------------------------------------------------------------
 // ORF scoring: one warp per ORF record
 // ------------------------------------------------------------------------------------------------
+// Per position the kernel needs four numbers under the (bacterial, archaeal) section pair of a GC bin:
+// coding log-likelihood and coding-minus-non-coding log-odds for each domain.  They sit in ONE 32-byte
+// table entry (Quad), so a position costs one sector-sized gather.  Lanes own positions (stride 32 down
+// from the stop) and accumulate privately; a warp reduction happens once per start codon, when the walk
+// reaches the position where that start's full-order region begins.
 struct Acc4 {
-    double cB, nB, cA, nA;  // coding / non-coding log-likelihood under the bacterial / archaeal section
+    double cB, oB, cA, oA;
 };
 
 __device__ __forceinline__ void window_bits(const uint32_t *lo, const uint32_t *hi, int first, int n, uint32_t &hb,
@@ -338,12 +351,23 @@ __device__ __forceinline__ void window_bits(const uint32_t *lo, const uint32_t *
     hb = __funnelshift_r(hi[w], hi[w + 1], sh) & mask;
 }
 
-__global__ void __launch_bounds__(256) k_orf_score(Planes pl, const uint32_t *__restrict__ gcpre, const int64_t *__restrict__ cwoff,
-                                                   const int32_t *__restrict__ clen, const DevModel *__restrict__ models,
-                                                   OrfRec *const *orfs_m, uint32_t *const *starts_m,
-                                                   const unsigned long long *counters_m, Cand *const *surv_m,
-                                                   uint32_t *const *bcount_m, unsigned long long *surv_counters, uint32_t cap_orf,
-                                                   uint32_t cap_surv, const ChainBufs *bufs_m) {
+__device__ __forceinline__ Acc4 warp_sum4(Acc4 v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        v.cB += __shfl_xor_sync(0xffffffffu, v.cB, o);
+        v.oB += __shfl_xor_sync(0xffffffffu, v.oB, o);
+        v.cA += __shfl_xor_sync(0xffffffffu, v.cA, o);
+        v.oA += __shfl_xor_sync(0xffffffffu, v.oA, o);
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(256, 3) k_orf_score(Planes pl, const uint32_t *__restrict__ gcpre, const int64_t *__restrict__ cwoff,
+                                                      const int32_t *__restrict__ clen, const DevModel *__restrict__ models,
+                                                      OrfRec *const *orfs_m, uint32_t *const *starts_m,
+                                                      const unsigned long long *counters_m, Cand *const *surv_m,
+                                                      uint32_t *const *bcount_m, unsigned long long *surv_counters, uint32_t cap_orf,
+                                                      uint32_t cap_surv, const ChainBufs *bufs_m) {
     const int mi = blockIdx.y;
     const DevModel &dm = models[mi];
     const int lane = lane_id();
@@ -358,6 +382,8 @@ __global__ void __launch_bounds__(256) k_orf_score(Planes pl, const uint32_t *__
     int32_t *gptr = bufs_m[mi].gptr;
     const int kc = dm.kc, kn = dm.kn;
     const int nfull = dm.nfull, nnon = dm.nnon, nramp = dm.nramp, nnramp = dm.nnramp;
+    const Quad *quad = dm.quad;
+    const int ph_lane0 = (((-1 - lane - kc) % 3) + 3) % 3;  // phase of the window's first letter at i = t-1-lane
 
     for (int64_t oi = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); oi < (int64_t)n_orfs; oi += nwarps) {
         const OrfRec rec = orfs[oi];
@@ -384,13 +410,14 @@ __global__ void __launch_bounds__(256) k_orf_score(Planes pl, const uint32_t *__
             const bool virt = (sraw >> 31) != 0;
             const int s = (int)(sraw & 0x7fffffffu);
             const int len = t + 3 - s;
-            int gc = 0, secB = -1, secA = -1;
+            int gc = 0, secB = -1, secA = -1, pair = 0x7fffffff;
             if (has) {
                 int a = strand ? (L - 1 - (t + 2)) : s, b = strand ? (L - 1 - s) : (t + 2);
                 int gcn = gc_count_fwd(pl.lo, pl.hi, gcpre, w0, a, b);
                 gc = (200 * gcn + len) / (2 * len);
                 secB = dm.map[0][gc];
                 secA = dm.map[1][gc];
+                pair = dm.pair[gc];
             }
             // forward-strand candidates whose start lies beyond the left edge are summed from their first letter
             const int first = s + ((virt && strand == 0) ? 0 : 3);
@@ -414,76 +441,69 @@ __global__ void __launch_bounds__(256) k_orf_score(Planes pl, const uint32_t *__
                         lnA = dm.ln_full + (size_t)max(secA, 0) * nnon;
                     }
                     if (secB >= 0) {
-                        acc.cB += dm.lc_ramp[(((size_t)secB * dm.kr + j) * 3 + 0) * nramp + idx];
-                        acc.nB += lnB[idn];
+                        double cv = dm.lc_ramp[(((size_t)secB * dm.kr + j) * 3 + 0) * nramp + idx];
+                        acc.cB += cv;
+                        acc.oB += cv - lnB[idn];
                     }
                     if (secA >= 0) {
-                        acc.cA += dm.lc_ramp[(((size_t)secA * dm.kr + j) * 3 + 0) * nramp + idx];
-                        acc.nA += lnA[idn];
+                        double cv = dm.lc_ramp[(((size_t)secA * dm.kr + j) * 3 + 0) * nramp + idx];
+                        acc.cA += cv;
+                        acc.oA += cv - lnA[idn];
                     }
                 }
             }
-            // full-order part: suffix sums from t-1 down to fullstart, one pass per distinct GC value
+            // full-order part: one walk from t-1 down per distinct section pair among this batch's starts
             bool done = !has || fullstart > t - 1;
             while (true) {
-                int gsel = warp_min_i(done ? 0x7fffffff : gc);
-                if (gsel == 0x7fffffff) break;
-                const bool mine = !done && gc == gsel;
-                const uint32_t mm = __ballot_sync(0xffffffffu, mine);
-                const int src = __ffs(mm) - 1;
-                const int sB = __shfl_sync(0xffffffffu, secB, src), sA = __shfl_sync(0xffffffffu, secA, src);
+                const int psel = warp_min_i(done ? 0x7fffffff : pair);
+                if (psel == 0x7fffffff) break;
+                const bool mine = !done && pair == psel;
                 const int lo_pos = warp_min_i(mine ? fullstart : 0x7fffffff);
-                const double *tcB = dm.lc_full + (size_t)max(sB, 0) * 3 * nfull;
-                const double *tcA = dm.lc_full + (size_t)max(sA, 0) * 3 * nfull;
-                const double *tnB = dm.ln_full + (size_t)max(sB, 0) * nnon;
-                const double *tnA = dm.ln_full + (size_t)max(sA, 0) * nnon;
-                Acc4 carry = {0, 0, 0, 0};
+                const Quad *tq = quad + (size_t)psel * 3 * nfull;
+                Acc4 run = {0, 0, 0, 0};  // lane-private sum over this lane's positions visited so far
                 Acc4 res = {0, 0, 0, 0};
+                int ph = ph_lane0;
                 for (int hiPos = t - 1; hiPos >= lo_pos; hiPos -= 32) {
                     const int i = hiPos - lane;
                     Acc4 v = {0, 0, 0, 0};
                     if (i >= lo_pos) {
                         uint32_t hb, lb;
                         window_bits(lo, hi, i - kc, kc + 1, hb, lb);
-                        uint32_t idx = (hb << (kc + 1)) | lb;
-                        uint32_t idn = ((hb >> (kc - kn)) << (kn + 1)) | (lb >> (kc - kn));
-                        int ph = ((i - kc - t) % 3 + 3) % 3;
-                        if (sB >= 0) { v.cB = tcB[(size_t)ph * nfull + idx]; v.nB = tnB[idn]; }
-                        if (sA >= 0) { v.cA = tcA[(size_t)ph * nfull + idx]; v.nA = tnA[idn]; }
+                        const Quad *q = tq + (size_t)ph * nfull + ((hb << (kc + 1)) | lb);
+                        const double2 x = __ldg(reinterpret_cast<const double2 *>(q));
+                        const double2 y = __ldg(reinterpret_cast<const double2 *>(q) + 1);
+                        v.cB = x.x; v.oB = x.y; v.cA = y.x; v.oA = y.y;
                     }
-                    // inclusive scan over lanes (lane 0 = position closest to the stop)
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        double a0 = shfl_up_d(v.cB, o), a1 = shfl_up_d(v.nB, o), a2 = shfl_up_d(v.cA, o), a3 = shfl_up_d(v.nA, o);
-                        if (lane >= o) { v.cB += a0; v.nB += a1; v.cA += a2; v.nA += a3; }
+                    // starts whose full-order region begins inside this chunk take their suffix sum now
+                    uint32_t hits = __ballot_sync(0xffffffffu, mine && fullstart <= hiPos && fullstart > hiPos - 32);
+                    while (hits) {
+                        const int o = __ffs(hits) - 1;
+                        hits &= hits - 1;
+                        const int tl = hiPos - __shfl_sync(0xffffffffu, fullstart, o);
+                        Acc4 part = run;
+                        if (lane <= tl) { part.cB += v.cB; part.oB += v.oB; part.cA += v.cA; part.oA += v.oA; }
+                        part = warp_sum4(part);
+                        if (lane == o) res = part;
                     }
-                    const int tl = hiPos - fullstart;  // lane holding the suffix that starts at my fullstart
-                    const bool hit = mine && tl >= 0 && tl < 32;
-                    const int sl = hit ? tl : 0;
-                    double r0 = shfl_d(v.cB, sl), r1 = shfl_d(v.nB, sl), r2 = shfl_d(v.cA, sl), r3 = shfl_d(v.nA, sl);
-                    if (hit) { res.cB = carry.cB + r0; res.nB = carry.nB + r1; res.cA = carry.cA + r2; res.nA = carry.nA + r3; }
-                    carry.cB += shfl_d(v.cB, 31); carry.nB += shfl_d(v.nB, 31);
-                    carry.cA += shfl_d(v.cA, 31); carry.nA += shfl_d(v.nA, 31);
+                    run.cB += v.cB; run.oB += v.oB; run.cA += v.cA; run.oA += v.oA;
+                    ph = ph == 2 ? 0 : ph + 1;
                 }
-                if (mine) { acc.cB += res.cB; acc.nB += res.nB; acc.cA += res.cA; acc.nA += res.nA; done = true; }
+                if (mine) { acc.cB += res.cB; acc.oB += res.oB; acc.cA += res.cA; acc.oA += res.oA; done = true; }
             }
             // totals
             bool keep = false;
             Cand cd;
             if (has && (secB >= 0 || secA >= 0)) {
                 const bool arc = secB < 0 || (secA >= 0 && acc.cA > acc.cB);
-                const int sec = arc ? secA : secB;
-                const SectionScalars sc = dm.sc[sec];
-                double orf = arc ? (acc.cA - acc.nA) : (acc.cB - acc.nB);
+                const SectionScalars *sc = dm.sc + (arc ? secA : secB);
                 double dl = (double)len;
-                double total = orf + 2.0 * log(dl) + dl * sc.dur_slope + sc.dur_const - 1.3862943611198906;
+                double total = (arc ? acc.oA : acc.oB) + 2.0 * log(dl) + dl * sc->dur_slope + sc->dur_const - 1.3862943611198906;
                 if (!virt) {
                     uint32_t hb, lb;
                     window_bits(lo, hi, s, 1, hb, lb);
-                    int st = hb ? (lb ? 2 : 1) : 0;  // A -> ATG, G -> GTG, T -> TTG
-                    total += sc.start_lo[st];
+                    total += sc->start_lo[hb ? (lb ? 2 : 1) : 0];  // A -> ATG, G -> GTG, T -> TTG
                 }
-                if (!pstop) total += sc.stop_lo[stop_type];
+                if (!pstop) total += sc->stop_lo[stop_type];
                 keep = total > 0.0;
                 cd.contig = c;
                 cd.left = strand ? (L - 1 - (t + 2)) : s;
@@ -496,6 +516,13 @@ __global__ void __launch_bounds__(256) k_orf_score(Planes pl, const uint32_t *__
                 cd.len = len;
             }
             const uint32_t km = __ballot_sync(0xffffffffu, keep);
+            if (km && strand && rec.n <= 32) {
+                // reverse strand: the survivor with the largest s has the smallest forward right end, so the chain meets it
+                // first among the starts of this ORF and can skip the lookup of the ORF's shared back-pointer
+                const int smax = -warp_min_i(keep ? -s : 0x7fffffff);
+                const bool any_virt = __any_sync(0xffffffffu, keep && virt);
+                if (keep && s == smax && !any_virt) cd.flags |= 8;
+            }
             if (km) {
                 unsigned long long base = 0;
                 if (lane == 0) base = atomicAdd(&surv_counters[mi], (unsigned long long)__popc(km));
@@ -545,12 +572,161 @@ __device__ __forceinline__ double overlap_penalty(int left_g, int len_g, int str
 }
 
 
+// The most recent CHAIN_RING predecessor states of the warp's contig live in shared memory; older ones
+// (rarely needed: only genes spanning more than CHAIN_RING states) are read back from global memory.
+// Candidates of one 128-nt bucket sit in registers (one per lane); all members of a group (same right
+// end) are evaluated in parallel, each lane walking the predecessor window of its own member.
+constexpr int CHAIN_RING = 64;
+constexpr int GP_CACHE = 8;
+struct ChainRing {
+    int right[CHAIN_RING], left[CHAIN_RING], ls[CHAIN_RING], idx[CHAIN_RING], parg[CHAIN_RING];
+    double cum[CHAIN_RING], pmax[CHAIN_RING];
+    uint32_t gp_orf[GP_CACHE];  // small cache of the shared back-pointers of the reverse-strand ORFs in flight
+    int gp_val[GP_CACHE];
+};
+
+struct ChainState {
+    int na;          // states visible as predecessors (all have right < current group's right end)
+    int head;        // states written
+    double pm_val;   // running prefix maximum over written states
+    int pm_arg;
+    int gp_next;     // round-robin slot of the pointer cache
+};
+
+__device__ __forceinline__ void chain_append(const ChainBufs &B, ChainRing &R, uint32_t cs, ChainState &S, int gi, double cum,
+                                             int right, int left, int ls) {
+    // all lanes hold identical arguments; lane 0 writes
+    if (S.head == 0 || cum > S.pm_val) { S.pm_val = cum; S.pm_arg = gi; }
+    if (lane_id() == 0) {
+        const int k = S.head, r = k & (CHAIN_RING - 1);
+        R.right[r] = right; R.left[r] = left; R.ls[r] = ls; R.idx[r] = gi; R.cum[r] = cum; R.pmax[r] = S.pm_val; R.parg[r] = S.pm_arg;
+        B.av_right[cs + k] = right; B.av_left[cs + k] = left; B.av_ls[cs + k] = ls; B.av_idx[cs + k] = gi;
+        B.av_cum[cs + k] = cum; B.av_pmax[cs + k] = S.pm_val; B.av_parg[cs + k] = S.pm_arg;
+    }
+    S.head++;
+}
+
+// Per-lane evaluation of one candidate against the visible predecessor states (k < S.na).
+//   bp_non : best non-overlapping predecessor (sorted index, -1 none)     b_non : its chain score (0 if none)
+//   bp_ov  : best overlapping predecessor that beats it strictly, else -1  b_ov  : its value
+__device__ __forceinline__ void chain_eval_lane(const ChainBufs &B, const ChainRing &R, uint32_t cs, const ChainState &S, int gl,
+                                                int glen, int gstrand, double &b_non, int &bp_non, double &b_ov, int &bp_ov) {
+    const int ring_lo = S.head - CHAIN_RING;  // states k >= ring_lo are in shared memory
+    double best_v = 0.0;
+    int best_p = -1;
+    int k = S.na - 1;
+    for (; k >= 0; k--) {
+        const bool inr = k >= ring_lo;
+        const int r = k & (CHAIN_RING - 1);
+        const int rh = inr ? R.right[r] : B.av_right[cs + k];
+        if (rh < gl) break;
+        const int lh = inr ? R.left[r] : B.av_left[cs + k];
+        if (lh < gl) {
+            const int ls = inr ? R.ls[r] : B.av_ls[cs + k];
+            const double ch = inr ? R.cum[r] : B.av_cum[cs + k];
+            const double v = ch - overlap_penalty(gl, glen, gstrand, rh, ls >> 1, (ls & 1) ? -1 : 1);
+            if (v >= best_v && v > 0.0) { best_v = v; best_p = k; }  // descending k: ties go to the earliest state
+        }
+    }
+    b_non = 0.0;
+    bp_non = -1;
+    if (k >= 0) {
+        const bool inr = k >= ring_lo;
+        const double pm = inr ? R.pmax[k & (CHAIN_RING - 1)] : B.av_pmax[cs + k];
+        if (pm > 0.0) { b_non = pm; bp_non = inr ? R.parg[k & (CHAIN_RING - 1)] : B.av_parg[cs + k]; }
+    }
+    b_ov = 0.0;
+    bp_ov = -1;
+    if (best_p >= 0 && best_v > b_non) {  // an overlap wins only if strictly better
+        b_ov = best_v;
+        bp_ov = best_p >= ring_lo ? R.idx[best_p & (CHAIN_RING - 1)] : B.av_idx[cs + best_p];
+    }
+}
+
+// current shared pointer of a reverse-strand ORF (warp-uniform call)
+__device__ __forceinline__ int gp_lookup(const ChainBufs &B, const ChainRing &R, uint32_t orf, int flags) {
+    if (flags & 8) return GPTR_UNSET;  // first surviving start of its ORF in chain order: nothing stored yet
+    const int lane = lane_id();
+    const uint32_t hit = __ballot_sync(0xffffffffu, lane < GP_CACHE && R.gp_orf[lane & (GP_CACHE - 1)] == orf);
+    if (hit) return R.gp_val[__ffs(hit) - 1];
+    return B.gptr[orf];
+}
+
+__device__ __forceinline__ void gp_store(const ChainBufs &B, ChainRing &R, ChainState &S, uint32_t orf, int val) {
+    const int lane = lane_id();
+    const uint32_t hit = __ballot_sync(0xffffffffu, lane < GP_CACHE && R.gp_orf[lane & (GP_CACHE - 1)] == orf);
+    int slot;
+    if (hit) slot = __ffs(hit) - 1;
+    else { slot = S.gp_next; S.gp_next = (S.gp_next + 1) & (GP_CACHE - 1); }
+    if (lane == 0) {
+        R.gp_orf[slot] = orf;
+        R.gp_val[slot] = val;
+        B.gptr[orf] = val;
+    }
+    __syncwarp();
+}
+
+// Processes the candidates held one per lane (valid lanes: `pending`) in chain order.
+__device__ __forceinline__ void chain_bucket(const ChainBufs &B, ChainRing &R, uint32_t cs, ChainState &S, uint32_t bs, const Cand &me,
+                                             bool pending) {
+    const int lane = lane_id();
+    while (true) {
+        const int rmin = warp_min_i(pending ? me.right : 0x7fffffff);
+        if (rmin == 0x7fffffff) break;
+        const bool ing = pending && me.right == rmin;
+        pending = pending && !ing;
+        double b_non = 0, b_ov = 0;
+        int bp_non = -1, bp_ov = -1;
+        if (ing) chain_eval_lane(B, R, cs, S, me.left, me.len, me.strand, b_non, bp_non, b_ov, bp_ov);
+        double cumg = me.total + (bp_ov >= 0 ? b_ov : b_non);
+        int prevg = bp_ov >= 0 ? bp_ov : bp_non;
+        if (ing) {
+            B.cum[bs + lane] = cumg;
+            B.prev[bs + lane] = prevg;
+        }
+        // reverse-strand members: shared pointer of their ORF, then append (ascending left)
+        uint32_t rev = __ballot_sync(0xffffffffu, ing && me.strand < 0);
+        while (rev) {
+            // smallest left first
+            const int lmin = warp_min_i(((rev >> lane) & 1u) ? me.left : 0x7fffffff);
+            const int o = __ffs(__ballot_sync(0xffffffffu, ((rev >> lane) & 1u) && me.left == lmin)) - 1;
+            rev &= ~(1u << o);
+            const uint32_t gorf = __shfl_sync(0xffffffffu, me.orf, o);
+            const int gfl = __shfl_sync(0xffffffffu, (int)me.flags, o);
+            const int o_non = __shfl_sync(0xffffffffu, bp_non, o), o_ov = __shfl_sync(0xffffffffu, bp_ov, o);
+            int gp = gp_lookup(B, R, gorf, gfl);
+            if (gp == GPTR_UNSET) gp = o_non;
+            if (o_ov >= 0) gp = o_ov;
+            gp_store(B, R, S, gorf, gp);
+            chain_append(B, R, cs, S, (int)(bs + o), __shfl_sync(0xffffffffu, cumg, o), rmin, lmin,
+                         __shfl_sync(0xffffffffu, me.len, o) * 2 + 1);
+        }
+        // direct-strand members: the stop keeps one state, its best start (ties: smallest left)
+        const bool dirm = ing && me.strand > 0;
+        if (__any_sync(0xffffffffu, dirm)) {
+            double bc = dirm ? cumg : -1e300;
+            int bl = dirm ? me.left : 0x7fffffff, bo = lane;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                const double oc = __shfl_xor_sync(0xffffffffu, bc, o);
+                const int ol = __shfl_xor_sync(0xffffffffu, bl, o), oo = __shfl_xor_sync(0xffffffffu, bo, o);
+                if (oc > bc || (oc == bc && ol < bl)) { bc = oc; bl = ol; bo = oo; }
+            }
+            chain_append(B, R, cs, S, (int)(bs + bo), bc, rmin, bl, __shfl_sync(0xffffffffu, me.len, bo) * 2);
+        }
+        S.na = S.head;
+        __syncwarp();
+    }
+}
+
 __global__ void __launch_bounds__(128) k_chain(const ChainBufs *bufs_m, const int64_t *__restrict__ cwoff,
                                                const int32_t *__restrict__ clen, const int32_t *__restrict__ order,
                                                int32_t n_contigs, int *work_counters) {
+    __shared__ ChainRing rings[4];
     const int mi = blockIdx.y;
     const ChainBufs B = bufs_m[mi];
     const int lane = lane_id();
+    ChainRing &R = rings[threadIdx.x >> 5];
     while (true) {
         int item = 0;
         if (lane == 0) item = atomicAdd(&work_counters[mi], 1);
@@ -562,148 +738,113 @@ __global__ void __launch_bounds__(128) k_chain(const ChainBufs *bufs_m, const in
         const int64_t b_first = g0 >> 7, b_last = (g0 + max(L - 1, 0)) >> 7;
         const uint32_t cs = b_first ? B.bend[b_first - 1] : 0u;
         const uint32_t ce = B.bend[b_last];
-        int na = 0;  // number of available states
-        for (int64_t b = b_first; b <= b_last; b++) {
-            const uint32_t bs = b ? B.bend[b - 1] : 0u, be = B.bend[b];
-            if (bs == be) continue;
-            int cur_right = -1;
-            while (true) {
-                // next group: smallest right end above cur_right
-                int r = 0x7fffffff;
-                for (uint32_t k = bs + lane; k < be; k += 32) {
-                    int rr = B.sorted[k].right;
-                    if (rr > cur_right) r = min(r, rr);
+        ChainState S;
+        S.na = 0; S.head = 0; S.pm_val = 0.0; S.pm_arg = -1; S.gp_next = 0;
+        if (lane < GP_CACHE) R.gp_orf[lane] = 0xffffffffu;
+        __syncwarp();
+        // the contig's candidates are contiguous in `sorted`; walk them in register-sized pieces that end on bucket boundaries
+        uint32_t prev_end = cs;
+        uint32_t nxt_end = b_first <= b_last ? (b_first + lane <= b_last ? B.bend[b_first + lane] : ce) : ce;
+        for (int64_t bb = b_first; bb <= b_last && prev_end < ce; bb += 32) {
+            const uint32_t my_end = nxt_end;
+            if (bb + 32 <= b_last) nxt_end = bb + 32 + lane <= b_last ? B.bend[bb + 32 + lane] : ce;  // prefetch next block of bucket ends
+            uint32_t my_start = __shfl_up_sync(0xffffffffu, my_end, 1);
+            if (lane == 0) my_start = prev_end;
+            prev_end = __shfl_sync(0xffffffffu, my_end, 31);
+            uint32_t nonempty = __ballot_sync(0xffffffffu, my_end > my_start);
+            // software pipeline: the next non-empty bucket is loaded while the current one is processed
+            Cand nxt;
+            nxt.right = 0;
+            uint32_t nbs = 0, nn = 0;
+            if (nonempty) {
+                const int bl = __ffs(nonempty) - 1;
+                nbs = __shfl_sync(0xffffffffu, my_start, bl);
+                nn = __shfl_sync(0xffffffffu, my_end, bl) - nbs;
+                if ((uint32_t)lane < nn && nn <= 32) nxt = B.sorted[nbs + lane];
+            }
+            while (nonempty) {
+                nonempty &= nonempty - 1;
+                const Cand me = nxt;
+                const uint32_t bs = nbs, n = nn;
+                if (nonempty) {
+                    const int bl = __ffs(nonempty) - 1;
+                    nbs = __shfl_sync(0xffffffffu, my_start, bl);
+                    nn = __shfl_sync(0xffffffffu, my_end, bl) - nbs;
+                    if ((uint32_t)lane < nn && nn <= 32) nxt = B.sorted[nbs + lane];
                 }
-                r = warp_min_i(r);
-                if (r == 0x7fffffff) break;
-                cur_right = r;
-                // members are evaluated in the order (+ strand first, left ascending, real start first)
-                long long last_key = -1;
-                int best_dir = -1;       // sorted index of the best direct-strand member so far
-                double best_dir_cum = 0;
-                const int na_group = na; // predecessors must have right < r: only states appended before this group
-                // reverse-strand members are appended after the group; remember them in a small list
-                int rev_count = 0;
-                while (true) {
-                    long long key = 0x7fffffffffffffffLL;
-                    uint32_t kidx = 0;
-                    for (uint32_t k = bs + lane; k < be; k += 32) {
-                        const Cand cd = B.sorted[k];
-                        if (cd.right != r) continue;
-                        long long kk = ((long long)(cd.strand < 0) << 40) | ((long long)cd.left << 1) | ((cd.flags >> 1) & 1);
-                        if (kk > last_key && kk < key) { key = kk; kidx = k; }
-                    }
-                    long long kmin = warp_min_ll(key);
-                    if (kmin == 0x7fffffffffffffffLL) break;
-                    last_key = kmin;
-                    const uint32_t owner = __ballot_sync(0xffffffffu, key == kmin);
-                    const uint32_t gi = __shfl_sync(0xffffffffu, kidx, __ffs(owner) - 1);
-                    const Cand g = B.sorted[gi];
-                    // scan the available states backwards: lane 0 = most recent
-                    double best_v = 0.0;
-                    int best_p = -1;
-                    int lo_idx = na_group;  // first state with right >= left(g)
-                    for (int khi = na_group; khi > 0; khi -= 32) {
-                        const int k = khi - 1 - lane;
-                        bool inwin = false;
-                        double v = -1e300;
-                        int p = -1;
-                        if (k >= 0) {
-                            const int rh = B.av_right[cs + k];
-                            inwin = rh >= g.left;
-                            if (inwin) {
-                                const int lh = B.av_left[cs + k];
-                                if (lh < g.left) {
-                                    const int ls = B.av_ls[cs + k];
-                                    v = B.av_cum[cs + k] - overlap_penalty(g.left, g.len, g.strand, rh, ls >> 1, (ls & 1) ? -1 : 1);
-                                    p = k;
-                                }
+                if (n <= 32) {
+                    chain_bucket(B, R, cs, S, bs, me, (uint32_t)lane < n);
+                } else {
+                    // rare: more than 32 candidates in one 128-nt bucket.  Their right ends are handled in ascending order,
+                    // 32 members of a group at a time (a group larger than 32 falls back to member-at-a-time semantics
+                    // only in the choice of the kept direct-strand state, which is re-resolved below).
+                    int cur = -1;
+                    while (true) {
+                        int r = 0x7fffffff;
+                        for (uint32_t k = bs + lane; k < bs + n; k += 32) {
+                            const int rr = B.sorted[k].right;
+                            if (rr > cur) r = min(r, rr);
+                        }
+                        r = warp_min_i(r);
+                        if (r == 0x7fffffff) break;
+                        cur = r;
+                        // evaluate all members of this group; append reverse members immediately, track the best direct one
+                        double bc = -1e300;
+                        int bleft = 0x7fffffff, bidx = -1, blen = 0;
+                        const ChainState S0 = S;  // members see the states before the group
+                        for (uint32_t k0 = bs; k0 < bs + n; k0 += 32) {
+                            const uint32_t k = k0 + lane;
+                            Cand g;
+                            g.right = -1;
+                            if (k < bs + n) g = B.sorted[k];
+                            const bool ing = g.right == r;
+                            double b_non = 0, b_ov = 0;
+                            int bp_non = -1, bp_ov = -1;
+                            ChainState Sv = S0;
+                            Sv.head = S.head;
+                            if (ing) chain_eval_lane(B, R, cs, Sv, g.left, g.len, g.strand, b_non, bp_non, b_ov, bp_ov);
+                            const double cumg = g.total + (bp_ov >= 0 ? b_ov : b_non);
+                            if (ing) { B.cum[k] = cumg; B.prev[k] = bp_ov >= 0 ? bp_ov : bp_non; }
+                            uint32_t rev = __ballot_sync(0xffffffffu, ing && g.strand < 0);
+                            while (rev) {
+                                const int o = __ffs(rev) - 1;
+                                rev &= rev - 1;
+                                const uint32_t gorf = __shfl_sync(0xffffffffu, g.orf, o);
+                                const int o_non = __shfl_sync(0xffffffffu, bp_non, o), o_ov = __shfl_sync(0xffffffffu, bp_ov, o);
+                                int gp = gp_lookup(B, R, gorf, 0);
+                                if (gp == GPTR_UNSET) gp = o_non;
+                                if (o_ov >= 0) gp = o_ov;
+                                gp_store(B, R, S, gorf, gp);
+                                chain_append(B, R, cs, S, (int)(k0 + o), __shfl_sync(0xffffffffu, cumg, o), r,
+                                             __shfl_sync(0xffffffffu, g.left, o), __shfl_sync(0xffffffffu, g.len, o) * 2 + 1);
+                            }
+                            const bool dirm = ing && g.strand > 0;
+                            double c2 = dirm ? cumg : -1e300;
+                            int l2 = dirm ? g.left : 0x7fffffff, o2 = lane;
+#pragma unroll
+                            for (int o = 16; o; o >>= 1) {
+                                const double oc = __shfl_xor_sync(0xffffffffu, c2, o);
+                                const int ol = __shfl_xor_sync(0xffffffffu, l2, o), oo = __shfl_xor_sync(0xffffffffu, o2, o);
+                                if (oc > c2 || (oc == c2 && ol < l2)) { c2 = oc; l2 = ol; o2 = oo; }
+                            }
+                            if (c2 > bc || (c2 == bc && l2 < bleft)) {
+                                bc = c2; bleft = l2; bidx = (int)(k0 + o2); blen = __shfl_sync(0xffffffffu, g.len, o2);
                             }
                         }
-                        const uint32_t wm = __ballot_sync(0xffffffffu, inwin);
-                        // best overlapping predecessor in this window: max v, ties -> smallest k
-#pragma unroll
-                        for (int o = 16; o; o >>= 1) {
-                            double ov = __shfl_xor_sync(0xffffffffu, v, o);
-                            int op = __shfl_xor_sync(0xffffffffu, p, o);
-                            if (ov > v || (ov == v && op >= 0 && (p < 0 || op < p))) { v = ov; p = op; }
-                        }
-                        if (p >= 0 && (v > best_v || (v == best_v && best_p >= 0 && p < best_p))) { best_v = v; best_p = p; }
-                        lo_idx = khi - __popc(wm);
-                        if (wm != 0xffffffffu) break;
+                        if (bidx >= 0 && bc > -1e299) chain_append(B, R, cs, S, bidx, bc, r, bleft, blen * 2);
+                        S.na = S.head;
+                        __syncwarp();
                     }
-                    if (lo_idx < 0) lo_idx = 0;
-                    // non-overlapping predecessors: prefix maximum
-                    double b = 0.0;
-                    int bp = -1;
-                    if (lo_idx > 0) {
-                        double pm = B.av_pmax[cs + lo_idx - 1];
-                        if (pm > 0.0) { b = pm; bp = B.av_parg[cs + lo_idx - 1]; }
-                    }
-                    const bool rev = g.strand < 0;
-                    int gp = GPTR_UNSET;
-                    if (rev) {
-                        gp = B.gptr[g.orf];
-                        if (gp == GPTR_UNSET) gp = bp;
-                    }
-                    // the overlap option wins only if strictly better (ties among overlaps: earliest state)
-                    if (best_p >= 0 && best_v > b) {
-                        b = best_v;
-                        bp = B.av_idx[cs + best_p];
-                        if (rev) gp = bp;
-                    }
-                    const double cumg = g.total + b;
-                    if (lane == 0) {
-                        B.cum[gi] = cumg;
-                        B.prev[gi] = bp;
-                        if (rev) B.gptr[g.orf] = gp;
-                    }
-                    if (!rev) {
-                        if (best_dir < 0 || cumg > best_dir_cum) { best_dir = (int)gi; best_dir_cum = cumg; }
-                    } else {
-                        // reverse members go straight to the tail of the state arrays (invisible until na advances)
-                        if (lane == 0) {
-                            const int slot = na_group + rev_count;
-                            B.av_idx[cs + slot] = (int)gi;
-                            B.av_cum[cs + slot] = cumg;
-                            B.av_right[cs + slot] = g.right;
-                            B.av_left[cs + slot] = g.left;
-                            B.av_ls[cs + slot] = g.len * 2 + 1;
-                        }
-                        rev_count++;
-                    }
-                    __syncwarp();
                 }
-                // append: every reverse-strand member (already in place), then the single kept direct-strand state
-                if (lane == 0) {
-                    int w = na_group + rev_count;
-                    if (best_dir >= 0) {
-                        const Cand g = B.sorted[best_dir];
-                        B.av_idx[cs + w] = best_dir;
-                        B.av_cum[cs + w] = best_dir_cum;
-                        B.av_right[cs + w] = g.right;
-                        B.av_left[cs + w] = g.left;
-                        B.av_ls[cs + w] = g.len * 2;
-                        w++;
-                    }
-                    for (int q = na_group; q < w; q++) {
-                        double pc = B.av_cum[cs + q];
-                        if (q == 0 || pc > B.av_pmax[cs + q - 1]) { B.av_pmax[cs + q] = pc; B.av_parg[cs + q] = B.av_idx[cs + q]; }
-                        else { B.av_pmax[cs + q] = B.av_pmax[cs + q - 1]; B.av_parg[cs + q] = B.av_parg[cs + q - 1]; }
-                    }
-                    na = w;
-                }
-                na = __shfl_sync(0xffffffffu, na, 0);
-                __syncwarp();
             }
         }
         // traceback (reverse-strand genes follow their ORF's shared pointer)
         if (lane == 0) {
             int ng = 0;
             double tot = 0.0;
-            if (na > 0) {
-                tot = B.av_pmax[cs + na - 1];
-                int g = B.av_parg[cs + na - 1];
+            if (S.head > 0) {
+                tot = S.pm_val;
+                int g = S.pm_arg;
                 const int limit = (int)(ce - cs);
                 int k = limit;
                 while (g >= 0 && k > 0) {
@@ -712,7 +853,6 @@ __global__ void __launch_bounds__(128) k_chain(const ChainBufs *bufs_m, const in
                     g = cd.strand < 0 ? B.gptr[cd.orf] : B.prev[g];
                     ng++;
                 }
-                // move to the front in ascending order
                 for (int q = 0; q < ng; q++) B.chain[cs + q] = B.chain[cs + k + q];
             }
             B.gene_count[c] = ng;
