@@ -94,6 +94,11 @@ const double *mgc_result_contig_totals(const mgc_result *r, int model);
 /* sum over all genes of round(logodd,2) in 1/100 units — Pipeline.classify_complete_sequence */
 int mgc_result_model_cents(const mgc_result *r, int64_t *cents /*[n_models]*/);
 void mgc_result_free(mgc_result *r);
+/* Host-side constructor (no GPU): wraps caller-provided genes, e.g. parsed back from cached GFF files
+ * (bin/data.py:39 skips gmhmmp2 when mgm_<code>_<species>.gff exists).  genes[m] holds counts[m] genes ordered
+ * by (contig, left); totals[m] holds n_contigs chain totals. */
+int mgc_result_create(int n_models, int32_t n_contigs, const mgc_gene *const *genes, const int64_t *counts,
+                      const double *const *totals, mgc_result **out);
 
 /*
  * Sliding-window labels (bin/pipeline.py:157-385) computed on the device from the genes of the

@@ -4,7 +4,9 @@
 // GC prefix), per-model scratch, one stream.  Nothing here falls back to a CPU path: without a usable
 // device mgc_engine_create fails with MGC_E_CUDA.
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -71,8 +73,12 @@ struct mgc_result {
     std::vector<PinnedPool::Block> gene_blk, total_blk;
     std::vector<int64_t> n_genes;
     std::vector<int64_t> cents;
+    bool host_owned = false;   // blocks came from malloc (mgc_result_create), not from the pinned pool
     ~mgc_result() {
-        if (pool) {
+        if (host_owned) {
+            for (auto &b : gene_blk) std::free(b.p);
+            for (auto &b : total_blk) std::free(b.p);
+        } else if (pool) {
             for (auto &b : gene_blk) pool->release(b);
             for (auto &b : total_blk) pool->release(b);
         }
@@ -660,6 +666,33 @@ int mgc_result_model_cents(const mgc_result *r, int64_t *cents) {
 }
 
 void mgc_result_free(mgc_result *r) { delete r; }
+
+int mgc_result_create(int n_models, int32_t n_contigs, const mgc_gene *const *genes, const int64_t *counts,
+                      const double *const *totals, mgc_result **out) {
+    if (n_models < 1 || n_models > MGC_MAX_MODELS || n_contigs < 0 || !genes || !counts || !totals || !out)
+        return mgc::set_error(MGC_E_ARG, "bad argument");
+    auto *r = new mgc_result();
+    r->n_models = n_models;
+    r->n_contigs = n_contigs;
+    for (int m = 0; m < n_models; m++) {
+        PinnedPool::Block g, t;   // plain heap blocks; no pool attached, freed below through host_owned
+        g.bytes = (size_t)std::max<int64_t>(counts[m], 1) * sizeof(mgc_gene);
+        g.p = std::malloc(g.bytes);
+        t.bytes = (size_t)std::max<int32_t>(n_contigs, 1) * 8;
+        t.p = std::malloc(t.bytes);
+        if (counts[m]) std::memcpy(g.p, genes[m], (size_t)counts[m] * sizeof(mgc_gene));
+        if (n_contigs) std::memcpy(t.p, totals[m], (size_t)n_contigs * 8);
+        r->gene_blk.push_back(g);
+        r->total_blk.push_back(t);
+        r->n_genes.push_back(counts[m]);
+        long long cents = 0;
+        for (int64_t k = 0; k < counts[m]; k++) cents += llrint(genes[m][k].logodd * 100.0);
+        r->cents.push_back(cents);
+    }
+    r->host_owned = true;
+    *out = r;
+    return MGC_OK;
+}
 
 int mgc_window_counts(const int64_t *contig_len, const int32_t *stride, int32_t n_contigs, int32_t window, int32_t consecutive,
                       int short_contigs, int64_t *win_offsets) {

@@ -208,7 +208,7 @@ int mgc_write_gff(const mgc_result *r, int model, const char *const *contig_ids,
         }
         const int64_t n = k - first;
         if (n > 0)
-            std::fprintf(f, "# %s\ttotal_logodd\t%g\taverage_length\t%lld\taverage_density\t%.2f\n", id, totals[c], len_sum / n,
+            std::fprintf(f, "# %s\ttotal_logodd\t%g\taverage_length\t%lld\taverage_density\t%.2f\n", id, totals[c], (long long)((double)len_sum / (double)n + 0.5),
                          (double)n / ((double)L / 1000.0));
     }
     if (lst) std::fprintf(f, "\n# output date end: %s\n# Done with file: %s\n", date.c_str(), seq_file_name ? seq_file_name : "");

@@ -1,0 +1,110 @@
+"""``Data`` — drop-in for the reference's boundary class (bin/data.py:16-124), backed by the CUDA engine.
+
+Same constructor, same three methods, same DataFrame schema; what changes is *how* ``run_mgm`` gets its
+genes: instead of ``subprocess.check_call([gmhmmp2, '-M', mgm_<code>.mod, '-s', fasta, '-f', 'gff', '-o', ...])``
+four times (bin/data.py:39-54) one :class:`mgcod_b200.engine.Engine` decodes every contig of the FASTA under
+the four parameter files in a single batch on the GPU.  The four ``mgm_<code>_<species>.gff`` files are still
+written in gmhmmp2's text format (they are documented output, README.md:65, and an on-disk cache: a model whose
+file already exists is not rewritten, bin/data.py:39,43,47,51).
+"""
+from __future__ import annotations
+
+import logging
+import os
+
+import numpy as np
+import pandas as pd
+
+from .engine import MGCOD_CODES, Engine, ModelFile, pack_sequences
+from .synth import read_fasta
+
+GFF_COLUMNS = ["sequence", "source", "feature", "start", "end", "logodd", "strand", "phase", "attributes"]
+
+
+class Record:
+    """The slice of Biopython's SeqRecord that Mgcod touches: ``id``, ``description``, ``seq``, ``len()``."""
+
+    def __init__(self, rid: str, description: str, seq: str):
+        self.id, self.description, self.seq = rid, description, seq
+
+    def __len__(self):
+        return len(self.seq)
+
+
+_ENGINES: dict = {}
+
+
+def shared_engine(model_dir: str, device: int = 0) -> Engine:
+    """One engine per (process, GPU, model directory): the parameter files are parsed and uploaded once,
+    not once per genome as in the reference (4 subprocesses per FASTA)."""
+    key = (os.path.abspath(model_dir), device)
+    if key not in _ENGINES:
+        _ENGINES[key] = Engine([ModelFile(os.path.join(model_dir, f"mgm_{c}.mod")) for c in MGCOD_CODES], device=device)
+    return _ENGINES[key]
+
+
+class Data:
+    def __init__(self, path_to_genome, path_to_predictions, verbose, cwd, species, model_dir=None, device=0):
+        """Same positional arguments as the reference.  ``model_dir`` defaults to ``<cwd>/dependencies``
+        (where the reference keeps mgm_11/4/15/101.mod) or ``$MGCOD_MODEL_DIR``."""
+        self.path_to_genome = path_to_genome
+        self.path_to_predictions = path_to_predictions
+        self.verbose = verbose
+        self.cwd = cwd
+        self.species = species
+        self.model_dir = model_dir or os.environ.get("MGCOD_MODEL_DIR") or os.path.join(cwd, "dependencies")
+        self.device = device
+        self.records = None
+        self.result = None          # engine.Result of the last run_mgm
+        self.engine = None
+
+    # -- bin/data.py:108-124
+    def read_dna_sequence(self):
+        logging.info(f"Reading {self.path_to_genome}")
+        if self.verbose:
+            print(f"Reading {self.path_to_genome}")
+        recs = [Record(i, d, s) for i, d, s in read_fasta(self.path_to_genome)]
+        self._file_order = recs
+        if len(recs) > 1:
+            recs = [recs[x] for x in np.argsort([r.id for r in recs])]
+        self.records = recs
+        return recs
+
+    def _gff_path(self, code):
+        return f"{self.path_to_predictions}mgm_{code}_{self.species}.gff"
+
+    # -- bin/data.py:31-54
+    def run_mgm(self):
+        logging.info(f"Running MGM models on {self.species}")
+        if self.verbose:
+            print(f"Running MGM models on {self.species}")
+        missing = [c for c in MGCOD_CODES if not os.path.isfile(self._gff_path(c))]
+        if not missing:
+            return
+        if self.records is None:
+            self.read_dna_sequence()
+        recs = self._file_order                       # gmhmmp2 writes records in file order
+        self.engine = shared_engine(self.model_dir, self.device)
+        buf, offs = pack_sequences([r.seq for r in recs])
+        self.result = self.engine.decode_buffer(buf, offs)
+        self._decoded_order = recs
+        ids = [r.id for r in recs]
+        lens = [len(r) for r in recs]
+        for mi, code in enumerate(MGCOD_CODES):
+            if code in missing:
+                self.result.write(mi, ids, lens, str(self.path_to_genome), os.path.join(self.model_dir, f"mgm_{code}.mod"), code,
+                                  self._gff_path(code), "gff")
+
+    # -- bin/data.py:56-106
+    def extract_gene_coords(self):
+        logging.info(f"Extracting gene coordinates predicted in {self.species}")
+        if self.verbose:
+            print(f"Extracting gene coordinates predicted in {self.species}")
+        frames = []
+        for code in MGCOD_CODES:
+            df = pd.read_csv(self._gff_path(code), sep="\t", header=None, comment="#", names=GFF_COLUMNS)
+            df["source"] = df["source"] + f"_{code}"
+            df["length"] = df["end"] - df["start"] + 1
+            df["sequence"] = df["sequence"].astype(str)
+            frames.append(df)
+        return tuple(frames)

@@ -71,6 +71,20 @@ class Result:
         self.n_models = n_models
         self.n_contigs = n_contigs
 
+    @classmethod
+    def from_genes(cls, genes_per_model: Sequence[np.ndarray], totals_per_model: Sequence[np.ndarray]) -> "Result":
+        """Host-only result (no GPU), e.g. from cached GFF files; arrays of GENE_DTYPE ordered by (contig, left)."""
+        M = len(genes_per_model)
+        gs = [np.ascontiguousarray(g, dtype=GENE_DTYPE) for g in genes_per_model]
+        ts = [np.ascontiguousarray(t, dtype=np.float64) for t in totals_per_model]
+        n_contigs = len(ts[0])
+        gp = (C.c_void_p * M)(*[g.ctypes.data for g in gs])
+        tp = (C.c_void_p * M)(*[t.ctypes.data for t in ts])
+        counts = (C.c_int64 * M)(*[len(g) for g in gs])
+        h = C.c_void_p()
+        _check(_lib.lib().mgc_result_create(M, n_contigs, gp, counts, tp, C.byref(h)))
+        return cls(h, M, n_contigs)
+
     def genes(self, model: int) -> np.ndarray:
         """Structured array (GENE_DTYPE), ordered by (contig, left); 1-based inclusive coordinates."""
         L = _lib.lib()

@@ -1,0 +1,105 @@
+"""GPU: edge cases and size-independent properties at sizes the oracle would not finish quickly."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+CODES = (11, 4, 15, 101)
+
+
+@pytest.fixture(scope="module")
+def engine(model_dir):
+    from mgcod_b200.engine import Engine
+    e = Engine([f"{model_dir}/mgm_{c}.mod" for c in CODES])
+    yield e
+    e.close()
+
+
+def test_ambiguous_letters_are_rejected_loudly(engine):
+    from mgcod_b200 import _lib
+    from mgcod_b200.engine import MgcodError
+    with pytest.raises(MgcodError) as e:
+        engine.decode(["ACGT" * 100 + "N" + "ACGT" * 100])
+    assert e.value.code == _lib.MGC_E_ALPHABET
+
+
+def test_tiny_and_empty_contigs(engine):
+    res = engine.decode(["", "A", "ACGTAC", "ATG" + "GCA" * 40 + "TAA", "ATGAAATAA"])
+    for mi in range(4):
+        g = res.genes(mi)
+        assert set(g["contig"].tolist()) <= {3}
+    assert engine.stats()["n_genes"] >= 0
+
+
+def test_small_orders_and_few_bins_match_oracle(small_model_dir):
+    """order 3/1 models with four GC bins per domain (gap filling above/below the provided bins)"""
+    from mgcod_b200.engine import Engine, synth_metagenome
+    from oracle import gmhmm
+    from tests import parity
+    buf, offs, truth = synth_metagenome(21, 80000, threads=2)
+    seqs = [buf[offs[i]:offs[i + 1]].tobytes() for i in range(len(truth))]
+    eng = Engine([f"{small_model_dir}/mgm_{c}.mod" for c in CODES])
+    res = eng.decode_buffer(buf, offs)
+    for mi, c in enumerate(CODES):
+        orc = gmhmm.Model(f"{small_model_dir}/mgm_{c}.mod")
+        assert not parity.compare_candidates(eng.candidates(mi), orc, seqs)
+        rows, _ = parity.oracle_genes(orc, seqs)
+        assert not parity.compare_genes(res.genes(mi), rows)
+    eng.close()
+
+
+def test_full_size_properties(engine):
+    """64 Mbp x 4 models: deterministic, genes ordered and inside their contigs, stop-codon/frame consistent,
+    chain totals consistent with the genes, window sums add up to the per-model sums, labels follow the planted code."""
+    from mgcod_b200.engine import synth_metagenome
+    buf, offs, truth = synth_metagenome(20260101, 64_000_000, threads=8)
+    lens = np.diff(offs)
+    r1 = engine.decode_buffer(buf, offs)
+    g1 = [r1.genes(m) for m in range(4)]
+    c1 = r1.model_cents().copy()
+    r2 = engine.decode_buffer(buf, offs)
+    for m in range(4):
+        g2 = r2.genes(m)
+        assert g1[m].tobytes() == g2.tobytes(), "decode is not deterministic"
+        g = g1[m]
+        assert (np.diff(g["contig"]) >= 0).all()
+        same = np.diff(g["contig"]) == 0
+        assert (np.diff(g["left"])[same] > 0).all() and (np.diff(g["right"])[same] > 0).all(), "chain order violated"
+        assert (g["left"] >= 1).all() and (g["right"] <= lens[g["contig"]]).all()
+        assert ((g["right"] - g["left"] + 1) % 3 == 0).all() and (g["logodd"] > 0).all()
+        assert (g["right"] - g["left"] + 1 >= 90).all()
+        # complete genes end in a stop codon of the model's genetic code on their strand
+        stops = {11: {b"TAA", b"TAG", b"TGA"}, 4: {b"TAA", b"TAG"}, 15: {b"TAA", b"TGA"}, 101: {b"TAG", b"TGA"}}[CODES[m]]
+        comp = bytes.maketrans(b"ACGT", b"TGCA")
+        for k in np.random.default_rng(m).choice(len(g), 3000, replace=False):
+            x = g[k]
+            base = offs[x["contig"]]
+            if x["strand"] > 0 and not x["partial_right"]:
+                assert buf[base + x["right"] - 3: base + x["right"]].tobytes() in stops
+            if x["strand"] < 0 and not x["partial_left"]:
+                assert buf[base + x["left"] - 1: base + x["left"] + 2].tobytes().translate(comp)[::-1] in stops
+        # chain totals: non-negative, and positive exactly where genes were found.  (They are NOT bounded by the sum of
+        # the traced genes' scores: the reference's shared back-pointer of reverse-strand ORFs can trace a path that
+        # differs from the one the total was computed on — DESIGN.md "chain".)
+        tot = r2.contig_totals(m)
+        has = np.bincount(g["contig"], minlength=len(lens)) > 0
+        assert (tot >= 0).all() and ((tot > 0) == has).all()
+        assert int(np.rint(g["logodd"] * 100).astype(np.int64).sum()) == int(c1[m])
+    # non-overlapping windows (stride == window) partition the genes by left coordinate
+    w = 5000
+    offs_w, labels, cents = engine.window_labels(lens, np.full(len(lens), w, np.int32), w, 1, True)
+    long_enough = lens > w
+    for m in range(4):
+        g = g1[m]
+        per_contig = np.bincount(g["contig"], weights=np.rint(g["logodd"] * 100), minlength=len(lens)).astype(np.int64)
+        wsum = np.add.reduceat(cents[:, m], offs_w[:-1])
+        # the spanning-gene fallback can only add to empty windows, so window sums are >= the gene sums
+        assert (wsum[long_enough] >= per_contig[long_enough]).all()
+        assert (wsum[long_enough] - per_contig[long_enough]).sum() <= 0.02 * per_contig.sum()
+    # per-contig majority label recovers the planted genetic code for the long contigs
+    code_of = np.array(CODES)
+    hit = tot_c = 0
+    for c in np.flatnonzero(lens > 20000):
+        lab = labels[offs_w[c]:offs_w[c + 1]]
+        hit += code_of[np.bincount(lab, minlength=4).argmax()] == truth[c]
+        tot_c += 1
+    assert hit / tot_c > 0.97
