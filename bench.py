@@ -252,7 +252,7 @@ def main():
         for _ in range(args.steps):
             res = engine.decode_resident()
             st = engine.stats()
-            for k in ("pack", "orf_find", "orf_score", "order", "chain", "aggregate", "d2h", "total"):
+            for k in ("pack", "orf_find", "orf_prep", "orf_score", "orf_final", "order", "chain", "aggregate", "d2h", "total"):
                 phase[k] = phase.get(k, 0.0) + st[k]
             launches += st["kernel_launches"]
             n_genes = st["n_genes"]

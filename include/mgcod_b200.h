@@ -50,7 +50,7 @@ typedef struct {
 
 /* Device-side timings of the last decode, milliseconds (CUDA events on the engine's stream). */
 typedef struct {
-    float h2d, pack, orf_find, orf_score, order, chain, aggregate, d2h, total;
+    float h2d, pack, orf_find, orf_prep, orf_score /* walk */, orf_final, order, chain, aggregate, d2h, total;
     int64_t n_orfs, n_starts, n_candidates, n_genes; /* summed over models */
     int32_t kernel_launches;
 } mgc_stats;

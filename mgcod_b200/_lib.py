@@ -30,7 +30,7 @@ class Candidate(C.Structure):
 
 
 class Stats(C.Structure):
-    _fields_ = [(n, C.c_float) for n in ("h2d", "pack", "orf_find", "orf_score", "order", "chain", "aggregate", "d2h", "total")] + \
+    _fields_ = [(n, C.c_float) for n in ("h2d", "pack", "orf_find", "orf_prep", "orf_score", "orf_final", "order", "chain", "aggregate", "d2h", "total")] + \
                [(n, C.c_int64) for n in ("n_orfs", "n_starts", "n_candidates", "n_genes")] + [("kernel_launches", C.c_int32)]
 
 

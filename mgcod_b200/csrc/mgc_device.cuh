@@ -27,19 +27,42 @@ struct DevModel {
     const double *lc_full, *ln_full, *lc_ramp, *ln_ramp;
     const SectionScalars *sc;
     const Quad *quad;   // [npair][3][4^(kc+1)], plane-major k-mer index
+    const Quad *rquad;  // [npair][kr][4^kr]: order ramp (window starts on a codon boundary, phase 0)
     int npair;
     int map[2][101];
     int pair[101];      // gc -> index of its (secB, secA) pair in quad
 };
 
-// one stop-delimited ORF that has at least one start candidate of sufficient length
+// one stop-delimited ORF that may have start candidates of sufficient length
 struct OrfRec {
     int32_t contig;
     int32_t t;          // strand-local position of the first nt of the (real or virtual) stop codon
-    uint32_t base;      // first entry in the starts array
-    uint32_t n;         // number of starts
-    uint32_t sf;        // bit0: strand (1 = reverse complement); bit8: stop codon missing (ORF runs into the right edge)
+    int32_t s_lo;       // first position a start codon may occupy (previous in-frame stop + 3, or the frame's first codon)
+    uint32_t base;      // first entry in the starts array (filled by k_orf_prep)
+    uint32_t n;         // number of starts              (filled by k_orf_prep)
+    uint32_t sf;        // bit0: strand (1 = reverse complement); bit1: open at the left edge (virtual start);
+                        // bit8: stop codon missing (ORF runs into the right edge)
 };
+
+// one start candidate of an ORF
+struct StartRec {
+    uint32_t sraw;      // strand-local position of the start codon; bit31: virtual start at the contig edge
+    uint32_t orf;       // index of its OrfRec
+    uint32_t pg;        // section pair (low 16 bits) | gc << 16
+    int32_t link;       // index (within the ORF) of the previous start of the same section pair that has a full-order region, -1 none
+};
+
+// one walk of an ORF under one section pair: serves every start of that pair
+struct ItemRec {
+    uint32_t orf;
+    int32_t lo_pos;     // lowest position of the walk (first full-order position of the farthest start of this pair)
+    uint32_t key;       // pair * WALK_CLASSES + length class (descending)
+    int32_t last;       // index (within the ORF) of the start of this pair closest to the stop
+};
+
+constexpr int WALK_CLASSES = 64;   // length classes of 32 nt; the last one collects everything longer
+constexpr int WALK_UNIT = 256;     // threads per CTA of k_walk
+constexpr int WALK_CHUNK = 2048;   // items per work unit (one section pair; warps take 32 at a time)
 
 // a start/stop pair with total > 0, forward coordinates, 0-based inclusive
 struct Cand {

@@ -115,12 +115,13 @@ struct DevBuf {
 };
 
 struct PerModel {
-    DevBuf lc_full, ln_full, lc_ramp, ln_ramp, sc, quad;
-    DevBuf orfs, starts, surv, sorted, bcount, cum, prev, gptr;
+    DevBuf lc_full, ln_full, lc_ramp, ln_ramp, sc, quad, rquad;
+    DevBuf ls, ls_tile, orfs, starts, items, items_sorted, hist, item_off, unit_off, sums;
+    DevBuf surv, sorted, bcount, cum, prev, gptr;
     DevBuf av_right, av_left, av_ls, av_idx, av_cum, av_pmax, av_parg, chain, gene_count, gene_off, contig_total, genes;
 };
 
-constexpr int N_EVENTS = 10;
+constexpr int N_EVENTS = 12;
 
 }  // namespace
 
@@ -140,6 +141,9 @@ struct mgc_engine {
     DevBuf ascii, aoff, cwoff, clen, grp2contig, order, lo, hi, gc, tile_sums, flags;
     // pointer tables + counters (device)
     DevBuf t_orfs, t_starts, t_surv, t_sorted, t_bcount, t_gene_off, t_genes, t_chainbufs;
+    DevBuf t_ls, t_ls_tile, t_items, t_items_sorted, t_hist, t_item_off, t_unit_off, t_sums, unit_totals, next_unit;
+    uint32_t cap_items = 0;
+    int max_cod_order = 0;
     DevBuf counters;     // [M][8] unsigned long long: 0 orfs, 1 starts
     DevBuf surv_counters;  // [M]
     DevBuf work_counters;  // [M] int
@@ -226,6 +230,29 @@ void upload_models(mgc_engine *e) {
                 }
         up(p.quad, q.data(), q.size() * sizeof(Quad));
         d.quad = p.quad.as<Quad>();
+        // order ramp: order j < kc, window of j+1 letters starting on a codon boundary (phase 0);
+        // non-coding order is min(j, kn): its context is the last min(j,kn)+1 letters of the window
+        const int kr = d.kr, knr = d.knr;
+        const size_t nramp = (size_t)d.nramp, nnramp = (size_t)d.nnramp;
+        std::vector<Quad> rq(pairs.size() * kr * nramp, Quad{0, 0, 0, 0});
+        for (size_t pi = 0; pi < pairs.size(); pi++)
+            for (int j = 0; j < kc; j++)
+                for (size_t idx = 0; idx < ((size_t)1 << (2 * (j + 1))); idx++) {
+                    const uint32_t hb = (uint32_t)(idx >> (j + 1)), lb = (uint32_t)(idx & ((1u << (j + 1)) - 1u));
+                    Quad &e4 = rq[(pi * kr + j) * nramp + idx];
+                    for (int dom = 0; dom < 2; dom++) {
+                        const int sec = dom ? pairs[pi].second : pairs[pi].first;
+                        if (sec < 0) continue;
+                        const double cv = m.lc_ramp[(((size_t)sec * kr + j) * 3 + 0) * nramp + idx];
+                        double nv;
+                        if (j < kn) nv = m.ln_ramp[((size_t)sec * knr + j) * nnramp + idx];
+                        else nv = m.ln_full[(size_t)sec * nnon + ((((size_t)(hb >> (j - kn))) << (kn + 1)) | (lb >> (j - kn)))];
+                        if (dom) { e4.cA = cv; e4.oA = cv - nv; } else { e4.cB = cv; e4.oB = cv - nv; }
+                    }
+                }
+        up(p.rquad, rq.data(), std::max<size_t>(rq.size(), 1) * sizeof(Quad));
+        d.rquad = p.rquad.as<Quad>();
+        e->max_cod_order = std::max(e->max_cod_order, kc);
     }
     e->d_models.ensure(sizeof(DevModel) * e->n_models);
     CUDA_TRY(cudaMemcpy(e->d_models.p, dm.data(), sizeof(DevModel) * e->n_models, cudaMemcpyHostToDevice));
@@ -242,15 +269,30 @@ void ensure_batch_buffers(mgc_engine *e) {
     e->tile_sums.ensure((size_t)(scan_n / 2048 + 8) * 4);
     e->grp2contig.ensure((size_t)(W / 4 + 8) * 4);
     e->flags.ensure(64);
-    e->cap_orf = (uint32_t)std::min<int64_t>(nt / 16 + 8192, 0x7fffff00);
-    e->cap_starts = (uint32_t)std::min<int64_t>(nt / 4 + 8192, 0x7fffff00);
-    e->cap_surv = (uint32_t)std::min<int64_t>(nt / 16 + 8192, 0x7fffff00);
+    // observed on gene-dense input per kb and model: ~11 ORFs, ~36 starts, ~18 walk items, ~10 surviving candidates
+    e->cap_orf = (uint32_t)std::min<int64_t>(nt / 24 + 8192, 0x7fffff00);
+    e->cap_starts = (uint32_t)std::min<int64_t>(nt / 8 + 8192, 0x7fffff00);
+    e->cap_items = (uint32_t)std::min<int64_t>(nt / 16 + 8192, 0x7fffff00);
+    e->cap_surv = (uint32_t)std::min<int64_t>(nt / 24 + 8192, 0x7fffff00);
     std::vector<void *> t_orfs(M), t_starts(M), t_surv(M), t_sorted(M), t_bcount(M), t_gene_off(M), t_genes(M);
+    std::vector<void *> t_ls(M), t_ls_tile(M), t_items(M), t_items_sorted(M), t_hist(M), t_item_off(M), t_unit_off(M), t_sums(M);
+    const int64_t ls_tiles = (2 * W + 255) / 256;
     std::vector<ChainBufs> cb(M);
     for (int i = 0; i < M; i++) {
         PerModel &p = e->pm[i];
         p.orfs.ensure((size_t)e->cap_orf * sizeof(OrfRec));
-        p.starts.ensure((size_t)e->cap_starts * 4);
+        p.starts.ensure((size_t)e->cap_starts * sizeof(StartRec));
+        p.sums.ensure((size_t)e->cap_starts * 32);
+        p.items.ensure((size_t)e->cap_items * sizeof(ItemRec));
+        p.items_sorted.ensure((size_t)e->cap_items * sizeof(ItemRec));
+        const size_t nkeys = (size_t)102 * WALK_CLASSES;   // at most 101 distinct section pairs
+        p.hist.ensure((nkeys + 8) * 4);
+        p.item_off.ensure((nkeys + 8) * 4);
+        p.unit_off.ensure((nkeys + 8) * 4);
+        p.ls.ensure((size_t)(2 * W + 8) * 3 * 4);
+        p.ls_tile.ensure((size_t)(ls_tiles + 8) * 3 * 4);
+        t_ls[i] = p.ls.p; t_ls_tile[i] = p.ls_tile.p; t_items[i] = p.items.p; t_items_sorted[i] = p.items_sorted.p;
+        t_hist[i] = p.hist.p; t_item_off[i] = p.item_off.p; t_unit_off[i] = p.unit_off.p; t_sums[i] = p.sums.p;
         p.surv.ensure((size_t)e->cap_surv * sizeof(Cand));
         p.sorted.ensure((size_t)e->cap_surv * sizeof(Cand));
         p.bcount.ensure((size_t)(nb + 8) * 4);
@@ -300,6 +342,16 @@ void ensure_batch_buffers(mgc_engine *e) {
     up(e->t_gene_off, t_gene_off.data(), M * sizeof(void *));
     up(e->t_genes, t_genes.data(), M * sizeof(void *));
     up(e->t_chainbufs, cb.data(), M * sizeof(ChainBufs));
+    up(e->t_ls, t_ls.data(), M * sizeof(void *));
+    up(e->t_ls_tile, t_ls_tile.data(), M * sizeof(void *));
+    up(e->t_items, t_items.data(), M * sizeof(void *));
+    up(e->t_items_sorted, t_items_sorted.data(), M * sizeof(void *));
+    up(e->t_hist, t_hist.data(), M * sizeof(void *));
+    up(e->t_item_off, t_item_off.data(), M * sizeof(void *));
+    up(e->t_unit_off, t_unit_off.data(), M * sizeof(void *));
+    up(e->t_sums, t_sums.data(), M * sizeof(void *));
+    e->unit_totals.ensure((size_t)M * 4 + 16);
+    e->next_unit.ensure(16);
     e->counters.ensure((size_t)M * 8 * 8);
     e->surv_counters.ensure((size_t)M * 8);
     e->work_counters.ensure((size_t)M * 4);
@@ -378,7 +430,11 @@ mgc_result *do_decode(mgc_engine *e) {
     CUDA_TRY(cudaMemsetAsync(e->surv_counters.p, 0, (size_t)M * 8, st));
     CUDA_TRY(cudaMemsetAsync(e->work_counters.p, 0, (size_t)M * 4, st));
     CUDA_TRY(cudaMemsetAsync(e->model_cents.p, 0, (size_t)M * 8, st));
-    for (int i = 0; i < M; i++) CUDA_TRY(cudaMemsetAsync(e->pm[i].bcount.p, 0, (size_t)(nb + 8) * 4, st));
+    CUDA_TRY(cudaMemsetAsync(e->next_unit.p, 0, 16, st));
+    for (int i = 0; i < M; i++) {
+        CUDA_TRY(cudaMemsetAsync(e->pm[i].bcount.p, 0, (size_t)(nb + 8) * 4, st));
+        CUDA_TRY(cudaMemsetAsync(e->pm[i].hist.p, 0, e->pm[i].hist.bytes, st));
+    }
     // pack + GC prefix
     launch_pack(e->ascii.as<char>(), e->aoff.as<int64_t>(), e->cwoff.as<int64_t>(), e->clen.as<int32_t>(),
                 e->grp2contig.as<int32_t>(), W, e->lo.as<uint32_t>(), e->hi.as<uint32_t>(), e->gc.as<uint32_t>(),
@@ -390,15 +446,29 @@ mgc_result *do_decode(mgc_engine *e) {
     pl.lo = e->lo.as<uint32_t>();
     pl.hi = e->hi.as<uint32_t>();
     pl.W = W;
+    launches += launch_laststop(pl, e->cwoff.as<int64_t>(), e->clen.as<int32_t>(), e->grp2contig.as<int32_t>(),
+                                e->d_models.as<DevModel>(), M, e->t_ls.as<uint32_t *>(), e->t_ls_tile.as<uint32_t *>(), st);
     launch_orf_find(pl, e->cwoff.as<int64_t>(), e->clen.as<int32_t>(), e->grp2contig.as<int32_t>(), e->d_models.as<DevModel>(), M,
-                    e->t_orfs.as<OrfRec *>(), e->t_starts.as<uint32_t *>(), e->counters.as<unsigned long long>(), e->cap_orf,
-                    e->cap_starts, st);
+                    e->t_ls.as<const uint32_t *>(), e->t_orfs.as<OrfRec *>(), e->counters.as<unsigned long long>(), e->cap_orf, st);
     launches += 1;
     CUDA_TRY(cudaEventRecord(e->ev[2], st));
-    launch_orf_score(pl, e->gc.as<uint32_t>(), e->cwoff.as<int64_t>(), e->clen.as<int32_t>(), e->d_models.as<DevModel>(), M,
-                     e->t_orfs.as<OrfRec *>(), e->t_starts.as<uint32_t *>(), e->counters.as<unsigned long long>(),
-                     e->t_surv.as<Cand *>(), e->t_bcount.as<uint32_t *>(), e->surv_counters.as<unsigned long long>(), e->cap_orf,
-                     e->cap_surv, e->t_chainbufs.as<ChainBufs>(), e->n_sm, st);
+    launch_orf_prep(pl, e->gc.as<uint32_t>(), e->cwoff.as<int64_t>(), e->clen.as<int32_t>(), e->d_models.as<DevModel>(), M,
+                    e->t_orfs.as<OrfRec *>(), e->t_starts.as<StartRec *>(), e->t_items.as<ItemRec *>(), e->t_hist.as<uint32_t *>(),
+                    e->counters.as<unsigned long long>(), e->t_chainbufs.as<ChainBufs>(), e->cap_orf, e->cap_starts, e->cap_items,
+                    e->n_sm, st);
+    launches += 1;
+    launches += launch_item_sort(e->t_items.as<const ItemRec *>(), e->t_items_sorted.as<ItemRec *>(), e->t_hist.as<uint32_t *>(),
+                                 e->t_item_off.as<uint32_t *>(), e->t_unit_off.as<uint32_t *>(), e->d_models.as<DevModel>(), M,
+                                 e->unit_totals.as<uint32_t>(), e->counters.as<unsigned long long>(), e->cap_items, e->n_sm, st);
+    CUDA_TRY(cudaEventRecord(e->ev[8], st));
+    launches += launch_walk(pl, e->cwoff.as<int64_t>(), e->d_models.as<DevModel>(), M, e->max_cod_order, e->t_orfs.as<const OrfRec *>(),
+                            e->t_starts.as<const StartRec *>(), e->t_items_sorted.as<const ItemRec *>(),
+                            e->t_item_off.as<const uint32_t *>(), e->t_unit_off.as<const uint32_t *>(), e->unit_totals.as<uint32_t>(),
+                            e->t_sums.as<void *>(), e->next_unit.as<unsigned int>(), e->n_sm, st);
+    CUDA_TRY(cudaEventRecord(e->ev[9], st));
+    launch_final(pl, e->cwoff.as<int64_t>(), e->clen.as<int32_t>(), e->d_models.as<DevModel>(), M, e->t_orfs.as<const OrfRec *>(),
+                 e->t_starts.as<const StartRec *>(), e->t_sums.as<void *>(), e->counters.as<unsigned long long>(), e->t_surv.as<Cand *>(),
+                 e->t_bcount.as<uint32_t *>(), e->surv_counters.as<unsigned long long>(), e->cap_starts, e->cap_surv, e->n_sm, st);
     launches += 1;
     CUDA_TRY(cudaEventRecord(e->ev[3], st));
     for (int i = 0; i < M; i++)
@@ -437,7 +507,8 @@ mgc_result *do_decode(mgc_engine *e) {
     CUDA_TRY(cudaGetLastError());
     if (h_flags[0]) throw AlphabetError("sequence contains letters outside ACGT; ambiguous letters are not supported by this build");
     for (int i = 0; i < M; i++) {
-        if (h_counters[(size_t)i * 8] > e->cap_orf || h_counters[(size_t)i * 8 + 1] > e->cap_starts || h_surv[i] > e->cap_surv)
+        if (h_counters[(size_t)i * 8] > e->cap_orf || h_counters[(size_t)i * 8 + 1] > e->cap_starts ||
+            h_counters[(size_t)i * 8 + 2] > e->cap_items || h_surv[i] > e->cap_surv)
             throw std::runtime_error("device scratch exhausted (ORFs " + std::to_string(h_counters[(size_t)i * 8]) + ", starts " +
                                      std::to_string(h_counters[(size_t)i * 8 + 1]) + ", candidates " + std::to_string(h_surv[i]) + ")");
         e->stats.n_orfs += (int64_t)h_counters[(size_t)i * 8];
@@ -464,7 +535,9 @@ mgc_result *do_decode(mgc_engine *e) {
     float ms;
     cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]); e->stats.pack = ms;
     cudaEventElapsedTime(&ms, e->ev[1], e->ev[2]); e->stats.orf_find = ms;
-    cudaEventElapsedTime(&ms, e->ev[2], e->ev[3]); e->stats.orf_score = ms;
+    cudaEventElapsedTime(&ms, e->ev[2], e->ev[8]); e->stats.orf_prep = ms;
+    cudaEventElapsedTime(&ms, e->ev[8], e->ev[9]); e->stats.orf_score = ms;
+    cudaEventElapsedTime(&ms, e->ev[9], e->ev[3]); e->stats.orf_final = ms;
     cudaEventElapsedTime(&ms, e->ev[3], e->ev[4]); e->stats.order = ms;
     cudaEventElapsedTime(&ms, e->ev[4], e->ev[5]); e->stats.chain = ms;
     cudaEventElapsedTime(&ms, e->ev[5], e->ev[6]); e->stats.aggregate = ms;
@@ -561,7 +634,8 @@ void mgc_engine_destroy(mgc_engine *e) {
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
     for (auto &p : e->pm) {
-        for (DevBuf *b : {&p.lc_full, &p.ln_full, &p.lc_ramp, &p.ln_ramp, &p.sc, &p.quad, &p.orfs, &p.starts, &p.surv, &p.sorted, &p.bcount,
+        for (DevBuf *b : {&p.lc_full, &p.ln_full, &p.lc_ramp, &p.ln_ramp, &p.sc, &p.quad, &p.rquad, &p.ls, &p.ls_tile, &p.items, &p.items_sorted, &p.hist,
+                          &p.item_off, &p.unit_off, &p.sums, &p.orfs, &p.starts, &p.surv, &p.sorted, &p.bcount,
                           &p.cum, &p.prev, &p.gptr, &p.av_right, &p.av_left, &p.av_ls, &p.av_idx, &p.av_cum, &p.av_pmax, &p.av_parg,
                           &p.chain, &p.gene_count, &p.gene_off, &p.contig_total, &p.genes})
             b->release();
@@ -569,7 +643,8 @@ void mgc_engine_destroy(mgc_engine *e) {
     for (DevBuf *b : {&e->d_models, &e->ascii, &e->aoff, &e->cwoff, &e->clen, &e->grp2contig, &e->order, &e->lo, &e->hi, &e->gc,
                       &e->tile_sums, &e->flags, &e->t_orfs, &e->t_starts, &e->t_surv, &e->t_sorted, &e->t_bcount, &e->t_gene_off,
                       &e->t_genes, &e->t_chainbufs, &e->counters, &e->surv_counters, &e->work_counters, &e->model_cents,
-                      &e->gene_totals, &e->win_stride, &e->win_off, &e->win_labels, &e->win_cents})
+                      &e->gene_totals, &e->t_ls, &e->t_ls_tile, &e->t_items, &e->t_items_sorted, &e->t_hist, &e->t_item_off,
+                      &e->t_unit_off, &e->t_sums, &e->unit_totals, &e->next_unit, &e->win_stride, &e->win_off, &e->win_labels, &e->win_cents})
         b->release();
     for (auto &ev : e->ev) cudaEventDestroy(ev);
     if (e->stream) cudaStreamDestroy(e->stream);

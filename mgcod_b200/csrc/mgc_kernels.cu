@@ -214,12 +214,13 @@ __global__ void __launch_bounds__(256) k_pack(const char *__restrict__ ascii, co
 }
 
 // ------------------------------------------------------------------------------------------------
-// ORF discovery
+// last in-frame stop table:  ls[w*3 + f] = 1 + position of the last stop codon at or before the end of
+// word w whose position is congruent to f mod 3 (positions count letters of the whole two-strand slot
+// space; 0 = none).  A plain max-scan over words; consumers compare with their contig's first position.
 // ------------------------------------------------------------------------------------------------
 struct FindCtx {
-    const uint32_t *lo, *hi;  // strand region base + contig slot
+    const uint32_t *lo, *hi;  // planes of the strand region, contig slot
     int L;                    // contig length
-    int nwords;               // ceil(L/32)
     int stop_sel, atg_only;
 };
 
@@ -232,117 +233,198 @@ __device__ __forceinline__ CodonMasks masks_at(const FindCtx &cx, int w) {
     return m;
 }
 
-// Handles the ORF that ends at stop position t (first nt of the stop codon, or of the last full codon
-// when `virt`): finds the previous in-frame stop, counts / writes the start candidates.
-__device__ void handle_stop(const FindCtx &cx, const DevModel &dm, int contig, int strand, int t, bool virt,
-                            OrfRec *orfs, uint32_t *starts, unsigned long long *counters, uint32_t cap_orf,
-                            uint32_t cap_starts) {
-    const int f = t % 3;
-    // latest start position that still gives len >= min_len and at least one codon between start and stop
-    int s_hi = min(t - 3, t + 3 - dm.min_len);
-    if (s_hi < f) return;
-    // previous in-frame stop
-    int p_prev = -1;
-    {
-        int w = t >> 5;
-        uint32_t below = (t & 31) ? ((1u << (t & 31)) - 1u) : 0u;
-        for (; w >= 0; w--) {
-            CodonMasks m = masks_at(cx, w);
-            int r = ((f - (w * 32) % 3) % 3 + 3) % 3;
-            uint32_t sm = stop_mask(m, cx.stop_sel) & frame_pattern(r) & below;
-            if (sm) { p_prev = w * 32 + 31 - __clz(sm); break; }
-            below = 0xffffffffu;
+struct U3 {
+    uint32_t v[3];
+};
+__device__ __forceinline__ U3 max3(U3 a, U3 b) {
+    U3 r;
+    r.v[0] = max(a.v[0], b.v[0]); r.v[1] = max(a.v[1], b.v[1]); r.v[2] = max(a.v[2], b.v[2]);
+    return r;
+}
+
+constexpr int LS_THREADS = 256;
+
+// grid.x = tiles of 256 words over the 2W words of both strands, grid.y = model
+__global__ void __launch_bounds__(LS_THREADS) k_laststop_tiles(Planes pl, const int64_t *__restrict__ cwoff, const int32_t *__restrict__ clen,
+                                                               const int32_t *__restrict__ grp2contig, const DevModel *__restrict__ models,
+                                                               uint32_t *const *ls_m, uint32_t *const *ls_tile_m) {
+    __shared__ U3 wsum[LS_THREADS / 32];
+    const int mi = blockIdx.y;
+    const int64_t w = (int64_t)blockIdx.x * LS_THREADS + threadIdx.x;  // word in [0, 2W)
+    const int lane = lane_id(), wid = threadIdx.x >> 5;
+    U3 x = {{0, 0, 0}};
+    if (w < 2 * pl.W) {
+        const int strand = w >= pl.W;
+        const int64_t ws = w - (strand ? pl.W : 0);
+        const int c = grp2contig[ws >> 2];
+        const int wl = (int)(ws - cwoff[c]);
+        const int L = clen[c];
+        if (L >= 3 && wl * 32 <= L - 3) {
+            FindCtx cx;
+            cx.lo = pl.lo + (int64_t)strand * pl.W + cwoff[c];
+            cx.hi = pl.hi + (int64_t)strand * pl.W + cwoff[c];
+            cx.L = L; cx.stop_sel = models[mi].stop_sel; cx.atg_only = models[mi].atg_only;
+            const uint32_t sm = stop_mask(masks_at(cx, wl), cx.stop_sel);
+            const uint32_t P0 = (uint32_t)(w * 32);
+            const int r0 = (int)(P0 % 3u);
+#pragma unroll
+            for (int f = 0; f < 3; f++) {
+                const uint32_t m = sm & frame_pattern((f - r0 + 3) % 3);
+                x.v[f] = m ? P0 + (31u - (uint32_t)__clz(m)) + 1u : 0u;
+            }
         }
     }
-    const bool open_left = p_prev < 0;
-    int s_lo = open_left ? f : p_prev + 3;
-    if (s_lo > s_hi) return;
-    // pass 1: count
-    uint32_t n = open_left ? 1u : 0u;
-    for (int w = s_lo >> 5; w <= (s_hi >> 5); w++) {
-        CodonMasks m = masks_at(cx, w);
-        int r = ((f - (w * 32) % 3) % 3 + 3) % 3;
-        uint32_t mm = m.start & frame_pattern(r) & bit_range(s_lo - 32 * w, s_hi - 32 * w);
-        n += __popc(mm);
+    // inclusive max-scan within the warp, then across warps
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        U3 y;
+        y.v[0] = __shfl_up_sync(0xffffffffu, x.v[0], o); y.v[1] = __shfl_up_sync(0xffffffffu, x.v[1], o);
+        y.v[2] = __shfl_up_sync(0xffffffffu, x.v[2], o);
+        if (lane >= o) x = max3(x, y);
     }
-    if (!n) return;
-    unsigned long long oid = atomicAdd(&counters[0], 1ull);
-    unsigned long long base = atomicAdd(&counters[1], (unsigned long long)n);
-    if (oid >= cap_orf || base + n > cap_starts) return;  // overflow is detected on the host from the counters
-    OrfRec rec;
-    rec.contig = contig;
-    rec.t = t;
-    rec.base = (uint32_t)base;
-    rec.n = n;
-    rec.sf = (uint32_t)strand | (virt ? 0x100u : 0u);
-    orfs[oid] = rec;
-    // pass 2: write (virtual start first; bit31 marks it)
-    uint32_t k = (uint32_t)base;
-    if (open_left) starts[k++] = 0x80000000u | (uint32_t)f;
-    for (int w = s_lo >> 5; w <= (s_hi >> 5); w++) {
-        CodonMasks m = masks_at(cx, w);
-        int r = ((f - (w * 32) % 3) % 3 + 3) % 3;
-        uint32_t mm = m.start & frame_pattern(r) & bit_range(s_lo - 32 * w, s_hi - 32 * w);
-        while (mm) {
-            int b = __ffs(mm) - 1;
-            mm &= mm - 1;
-            starts[k++] = (uint32_t)(w * 32 + b);
-        }
+    if (lane == 31) wsum[wid] = x;
+    __syncthreads();
+    U3 carry = {{0, 0, 0}};
+    for (int k = 0; k < wid; k++) carry = max3(carry, wsum[k]);
+    x = max3(x, carry);
+    uint32_t *ls = ls_m[mi];
+    if (w < 2 * pl.W) { ls[w * 3 + 0] = x.v[0]; ls[w * 3 + 1] = x.v[1]; ls[w * 3 + 2] = x.v[2]; }
+    if (threadIdx.x == LS_THREADS - 1) {
+        uint32_t *lt = ls_tile_m[mi];
+        lt[(int64_t)blockIdx.x * 3 + 0] = x.v[0]; lt[(int64_t)blockIdx.x * 3 + 1] = x.v[1]; lt[(int64_t)blockIdx.x * 3 + 2] = x.v[2];
     }
 }
 
-// thread per word of the slot space; grid.y = strand, grid.z = model
+// one block per model: running maximum over the tile results (exclusive: tile t receives the max of tiles < t)
+__global__ void __launch_bounds__(1024) k_laststop_sums(uint32_t *const *ls_tile_m, int64_t n_tiles) {
+    __shared__ U3 wsum[32];
+    __shared__ U3 carry_s;
+    uint32_t *lt = ls_tile_m[blockIdx.x];
+    const int lane = lane_id(), wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = U3{{0, 0, 0}};
+    __syncthreads();
+    for (int64_t b = 0; b < n_tiles; b += 1024) {
+        const int64_t i = b + threadIdx.x;
+        U3 own = {{0, 0, 0}};
+        if (i < n_tiles) { own.v[0] = lt[i * 3]; own.v[1] = lt[i * 3 + 1]; own.v[2] = lt[i * 3 + 2]; }
+        U3 x = own;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            U3 y;
+            y.v[0] = __shfl_up_sync(0xffffffffu, x.v[0], o); y.v[1] = __shfl_up_sync(0xffffffffu, x.v[1], o);
+            y.v[2] = __shfl_up_sync(0xffffffffu, x.v[2], o);
+            if (lane >= o) x = max3(x, y);
+        }
+        if (lane == 31) wsum[wid] = x;
+        __syncthreads();
+        U3 c = carry_s;
+        for (int k = 0; k < wid; k++) c = max3(c, wsum[k]);
+        // exclusive value = max over everything before me = (inclusive of previous lane) max carry
+        U3 prev;
+        prev.v[0] = __shfl_up_sync(0xffffffffu, x.v[0], 1); prev.v[1] = __shfl_up_sync(0xffffffffu, x.v[1], 1);
+        prev.v[2] = __shfl_up_sync(0xffffffffu, x.v[2], 1);
+        if (lane == 0) prev = U3{{0, 0, 0}};
+        const U3 excl = max3(prev, c);
+        if (i < n_tiles) { lt[i * 3] = excl.v[0]; lt[i * 3 + 1] = excl.v[1]; lt[i * 3 + 2] = excl.v[2]; }
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = max3(x, c);
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(LS_THREADS) k_laststop_apply(uint32_t *const *ls_m, uint32_t *const *ls_tile_m, int64_t n_words) {
+    const int mi = blockIdx.y;
+    const int64_t w = (int64_t)blockIdx.x * LS_THREADS + threadIdx.x;
+    if (w >= n_words) return;
+    const uint32_t *lt = ls_tile_m[mi] + (int64_t)blockIdx.x * 3;
+    uint32_t *ls = ls_m[mi] + w * 3;
+    ls[0] = max(ls[0], lt[0]); ls[1] = max(ls[1], lt[1]); ls[2] = max(ls[2], lt[2]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// ORF discovery: thread per word; the previous in-frame stop comes from the table in O(1)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void emit_orf(const FindCtx &cx, const DevModel &dm, int contig, int strand, int t, bool virt,
+                                         int p_prev /* local, < 0 = none in this contig */, OrfRec *orfs,
+                                         unsigned long long *counters, uint32_t cap_orf) {
+    const int f = t % 3;
+    const int s_hi = min(t - 3, t + 3 - dm.min_len);
+    const bool open_left = p_prev < 0;
+    const int s_lo = open_left ? f : p_prev + 3;
+    if (s_lo > s_hi) return;
+    if (!open_left) {
+        // cheap existence test for a start codon: look at up to four words of the admissible range
+        bool any = false;
+        const int w_end = min(s_hi >> 5, (s_lo >> 5) + 3);
+        for (int w = s_lo >> 5; w <= w_end && !any; w++) {
+            const CodonMasks m = masks_at(cx, w);
+            const int r = ((f - (w * 32) % 3) % 3 + 3) % 3;
+            any = (m.start & frame_pattern(r) & bit_range(s_lo - 32 * w, s_hi - 32 * w)) != 0;
+        }
+        if (!any && (s_hi >> 5) <= w_end) return;
+    }
+    const unsigned long long oid = atomicAdd(&counters[0], 1ull);
+    if (oid >= cap_orf) return;  // overflow is detected on the host from the counter
+    OrfRec rec;
+    rec.contig = contig; rec.t = t; rec.s_lo = s_lo; rec.base = 0; rec.n = 0;
+    rec.sf = (uint32_t)strand | (open_left ? 2u : 0u) | (virt ? 0x100u : 0u);
+    orfs[oid] = rec;
+}
+
+// grid.x over the 2W words of both strands, grid.y = model
 __global__ void __launch_bounds__(128) k_orf_find(Planes pl, const int64_t *__restrict__ cwoff, const int32_t *__restrict__ clen,
                                                   const int32_t *__restrict__ grp2contig, const DevModel *__restrict__ models,
-                                                  OrfRec *const *orfs_m, uint32_t *const *starts_m,
-                                                  unsigned long long *counters_m, uint32_t cap_orf, uint32_t cap_starts) {
-    int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= pl.W) return;
-    const int strand = blockIdx.y, mi = blockIdx.z;
+                                                  const uint32_t *const *ls_m, OrfRec *const *orfs_m, unsigned long long *counters_m,
+                                                  uint32_t cap_orf) {
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= 2 * pl.W) return;
+    const int mi = blockIdx.y;
     const DevModel &dm = models[mi];
-    int c = grp2contig[w >> 2];
-    int L = clen[c];
-    int wl = (int)(w - cwoff[c]);
+    const int strand = w >= pl.W;
+    const int64_t ws = w - (strand ? pl.W : 0);
+    const int c = grp2contig[ws >> 2];
+    const int L = clen[c];
+    const int wl = (int)(ws - cwoff[c]);
     if (L < 6 || wl * 32 > L - 3) return;  // no codon starts in this word (virtual stops sit at t <= L-3 too)
     FindCtx cx;
     cx.lo = pl.lo + (int64_t)strand * pl.W + cwoff[c];
     cx.hi = pl.hi + (int64_t)strand * pl.W + cwoff[c];
-    cx.L = L;
-    cx.nwords = (L + 31) >> 5;
-    cx.stop_sel = dm.stop_sel;
-    cx.atg_only = dm.atg_only;
+    cx.L = L; cx.stop_sel = dm.stop_sel; cx.atg_only = dm.atg_only;
     OrfRec *orfs = orfs_m[mi];
-    uint32_t *starts = starts_m[mi];
     unsigned long long *counters = counters_m + (size_t)mi * 8;
-    CodonMasks m = masks_at(cx, wl);
-    uint32_t sm = stop_mask(m, cx.stop_sel);
+    const uint32_t *ls = ls_m[mi];
+    const uint32_t P0 = (uint32_t)(w * 32);                      // slot-space position of bit 0
+    const uint32_t Pc = (uint32_t)(((int64_t)strand * pl.W + cwoff[c]) * 32);  // ... of the contig's first letter
+    const uint32_t all = stop_mask(masks_at(cx, wl), cx.stop_sel);
+    // previous stop per frame coming from the words before this one
+    uint32_t carry[3] = {0, 0, 0};
+    if (w > 0) { carry[0] = ls[(w - 1) * 3]; carry[1] = ls[(w - 1) * 3 + 1]; carry[2] = ls[(w - 1) * 3 + 2]; }
+    auto prev_local = [&](int b) {  // previous in-frame stop of the codon at bit b, contig-local, -1 if none
+        const uint32_t P = P0 + (uint32_t)b;
+        const int f = (int)(P % 3u);
+        const uint32_t below = b ? ((1u << b) - 1u) : 0u;
+        const uint32_t m = all & frame_pattern((f - (int)(P0 % 3u) + 3) % 3) & below;
+        uint32_t pp1 = m ? P0 + (31u - (uint32_t)__clz(m)) + 1u : carry[f];
+        return pp1 > Pc ? (int)(pp1 - 1u - Pc) : -1;
+    };
+    uint32_t sm = all;
     while (sm) {
-        int b = __ffs(sm) - 1;
+        const int b = __ffs(sm) - 1;
         sm &= sm - 1;
-        handle_stop(cx, dm, c, strand, wl * 32 + b, false, orfs, starts, counters, cap_orf, cap_starts);
+        emit_orf(cx, dm, c, strand, wl * 32 + b, false, prev_local(b), orfs, counters, cap_orf);
     }
     // right edge: in each frame the last full codon closes an open ORF unless it is a real stop
     for (int f = 0; f < 3; f++) {
-        int tv = L - 3 - ((L - 3 - f) % 3 + 3) % 3;  // largest t <= L-3 with t % 3 == f
+        const int tv = L - 3 - ((L - 3 - f) % 3 + 3) % 3;  // largest t <= L-3 with t % 3 == f
         if (tv < 0 || (tv >> 5) != wl) continue;
-        uint32_t all = stop_mask(m, cx.stop_sel);
         if ((all >> (tv & 31)) & 1u) continue;
-        handle_stop(cx, dm, c, strand, tv, true, orfs, starts, counters, cap_orf, cap_starts);
+        emit_orf(cx, dm, c, strand, tv, true, prev_local(tv & 31), orfs, counters, cap_orf);
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// ORF scoring: one warp per ORF record
+// ORF preparation: thread per ORF — start list with GC bin / section pair, walk items
 // ------------------------------------------------------------------------------------------------
-// Per position the kernel needs four numbers under the (bacterial, archaeal) section pair of a GC bin:
-// coding log-likelihood and coding-minus-non-coding log-odds for each domain.  They sit in ONE 32-byte
-// table entry (Quad), so a position costs one sector-sized gather.  Lanes own positions (stride 32 down
-// from the stop) and accumulate privately; a warp reduction happens once per start codon, when the walk
-// reaches the position where that start's full-order region begins.
-struct Acc4 {
-    double cB, oB, cA, oA;
-};
-
 __device__ __forceinline__ void window_bits(const uint32_t *lo, const uint32_t *hi, int first, int n, uint32_t &hb,
                                             uint32_t &lb) {
     int w = first >> 5, sh = first & 31;
@@ -351,188 +433,458 @@ __device__ __forceinline__ void window_bits(const uint32_t *lo, const uint32_t *
     hb = __funnelshift_r(hi[w], hi[w + 1], sh) & mask;
 }
 
-__device__ __forceinline__ Acc4 warp_sum4(Acc4 v) {
+__global__ void __launch_bounds__(128) k_orf_prep(Planes pl, const uint32_t *__restrict__ gcpre, const int64_t *__restrict__ cwoff,
+                                                  const int32_t *__restrict__ clen, const DevModel *__restrict__ models,
+                                                  OrfRec *const *orfs_m, StartRec *const *starts_m, ItemRec *const *items_m,
+                                                  uint32_t *const *hist_m, unsigned long long *counters_m, const ChainBufs *bufs_m,
+                                                  uint32_t cap_orf, uint32_t cap_starts, uint32_t cap_items) {
+    const int mi = blockIdx.y;
+    const DevModel &dm = models[mi];
+    unsigned long long *counters = counters_m + (size_t)mi * 8;
+    unsigned long long n_orfs = counters[0];
+    if (n_orfs > cap_orf) n_orfs = cap_orf;
+    OrfRec *orfs = orfs_m[mi];
+    StartRec *starts = starts_m[mi];
+    ItemRec *items = items_m[mi];
+    uint32_t *hist = hist_m[mi];
+    int32_t *gptr = bufs_m[mi].gptr;
+    const int kc = dm.kc;
+    const int lane = lane_id();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    // whole warps iterate together so that the two reservations below cost one atomic per warp
+    for (int64_t o0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~31LL; o0 < (int64_t)n_orfs; o0 += stride) {
+        const int64_t oi = o0 + lane;
+        const bool has = oi < (int64_t)n_orfs;
+        OrfRec rec;
+        rec.contig = 0; rec.t = 0; rec.s_lo = 1; rec.sf = 0;
+        if (has) {
+            rec = orfs[oi];
+            gptr[oi] = GPTR_UNSET;
+        }
+        const int c = rec.contig, t = rec.t, strand = rec.sf & 1;
+        const bool open_left = has && (rec.sf & 2u) != 0;
+        const int L = has ? clen[c] : 0;
+        const int64_t w0 = has ? cwoff[c] : 0;
+        FindCtx cx;
+        cx.lo = pl.lo + (int64_t)strand * pl.W + w0;
+        cx.hi = pl.hi + (int64_t)strand * pl.W + w0;
+        cx.L = L; cx.stop_sel = dm.stop_sel; cx.atg_only = dm.atg_only;
+        const int f = t % 3;
+        const int s_lo = rec.s_lo, s_hi = has ? min(t - 3, t + 3 - dm.min_len) : 0;
+        // pass 1: count
+        uint32_t n = open_left ? 1u : 0u;
+        if (has)
+            for (int w = s_lo >> 5; w <= (s_hi >> 5); w++) {
+                const CodonMasks m = masks_at(cx, w);
+                const int r = ((f - (w * 32) % 3) % 3 + 3) % 3;
+                n += __popc(m.start & frame_pattern(r) & bit_range(s_lo - 32 * w, s_hi - 32 * w));
+            }
+        // warp-aggregated reservation of the start records
+        uint32_t pre = n;
 #pragma unroll
-    for (int o = 16; o; o >>= 1) {
-        v.cB += __shfl_xor_sync(0xffffffffu, v.cB, o);
-        v.oB += __shfl_xor_sync(0xffffffffu, v.oB, o);
-        v.cA += __shfl_xor_sync(0xffffffffu, v.cA, o);
-        v.oA += __shfl_xor_sync(0xffffffffu, v.oA, o);
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, pre, o);
+            if (lane >= o) pre += y;
+        }
+        unsigned long long wbase = 0;
+        const uint32_t wtot = __shfl_sync(0xffffffffu, pre, 31);
+        if (lane == 31 && wtot) wbase = atomicAdd(&counters[1], (unsigned long long)wtot);
+        wbase = __shfl_sync(0xffffffffu, wbase, 31);
+        const unsigned long long base = wbase + pre - n;
+        const bool ok = has && n && base + n <= cap_starts;
+        if (ok) {
+            orfs[oi].base = (uint32_t)base;
+            orfs[oi].n = n;
+        }
+        // pass 2: starts in ascending position (virtual start first).  Starts of the same section pair are chained
+        // (StartRec.link = previous start of that pair) so that the walk can hop from one to the next.
+        uint32_t k = (uint32_t)base;
+        constexpr int NSLOT = 6, NPEND = 10;
+        int sl_pair[NSLOT], sl_lo[NSLOT], sl_last[NSLOT];
+#pragma unroll
+        for (int z = 0; z < NSLOT; z++) { sl_pair[z] = -1; sl_lo[z] = 0; sl_last[z] = -1; }
+        int nslot = 0;
+        ItemRec pend[NPEND];
+        int npend = 0;
+        auto flush_slot = [&](int q) {
+            const int ext = t - sl_lo[q];
+            const int cls = WALK_CLASSES - 1 - min(ext >> 5, WALK_CLASSES - 1);
+            ItemRec it;
+            it.orf = (uint32_t)oi;
+            it.lo_pos = sl_lo[q];
+            it.key = (uint32_t)(sl_pair[q] * WALK_CLASSES + cls);
+            it.last = sl_last[q];
+            if (npend < NPEND) pend[npend++] = it;
+            else {  // very many distinct GC bins among the starts of one ORF: emit directly
+                const unsigned long long ii = atomicAdd(&counters[2], 1ull);
+                if (ii < cap_items) {
+                    items[ii] = it;
+                    atomicAdd(&hist[it.key], 1u);
+                }
+            }
+        };
+        auto add_start = [&](int s, bool virt) {
+            const int len = t + 3 - s;
+            const int a = strand ? (L - 1 - (t + 2)) : s, b = strand ? (L - 1 - s) : (t + 2);
+            const int gcn = gc_count_fwd(pl.lo, pl.hi, gcpre, w0, a, b);
+            const int gc = (200 * gcn + len) / (2 * len);
+            const int pair = dm.pair[gc];
+            const int j = (int)(k - (uint32_t)base);
+            StartRec sr;
+            sr.sraw = (uint32_t)s | (virt ? 0x80000000u : 0u);
+            sr.orf = (uint32_t)oi;
+            sr.pg = (uint32_t)pair | ((uint32_t)gc << 16);
+            sr.link = -1;
+            const int fullstart = s + ((virt && strand == 0) ? 0 : 3) + kc;
+            if (fullstart <= t - 1) {  // has a full-order region: belongs to a walk
+                int q = -1;
+#pragma unroll
+                for (int z = 0; z < NSLOT; z++)
+                    if (sl_pair[z] == pair) q = z;
+                if (q < 0) {
+                    if (nslot < NSLOT) q = nslot++;
+                    else {           // more distinct pairs in flight than slots: retire the oldest slot into its own walk
+                        flush_slot(0);
+#pragma unroll
+                        for (int z = 0; z < NSLOT - 1; z++) { sl_pair[z] = sl_pair[z + 1]; sl_lo[z] = sl_lo[z + 1]; sl_last[z] = sl_last[z + 1]; }
+                        q = NSLOT - 1;
+                    }
+                    sl_pair[q] = pair;
+                    sl_lo[q] = fullstart;
+                    sl_last[q] = -1;
+                }
+                sr.link = sl_last[q];
+                sl_last[q] = j;
+            }
+            starts[k++] = sr;
+        };
+        if (ok) {
+            if (open_left) add_start(f, true);
+            for (int w = s_lo >> 5; w <= (s_hi >> 5); w++) {
+                const CodonMasks m = masks_at(cx, w);
+                const int r = ((f - (w * 32) % 3) % 3 + 3) % 3;
+                uint32_t mm = m.start & frame_pattern(r) & bit_range(s_lo - 32 * w, s_hi - 32 * w);
+                while (mm) {
+                    const int b = __ffs(mm) - 1;
+                    mm &= mm - 1;
+                    add_start(w * 32 + b, false);
+                }
+            }
+            for (int q = 0; q < nslot; q++) flush_slot(q);
+        }
+        // warp-aggregated reservation of the walk items
+        uint32_t ipre = (uint32_t)npend;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, ipre, o);
+            if (lane >= o) ipre += y;
+        }
+        unsigned long long ibase = 0;
+        const uint32_t itot = __shfl_sync(0xffffffffu, ipre, 31);
+        if (lane == 31 && itot) ibase = atomicAdd(&counters[2], (unsigned long long)itot);
+        ibase = __shfl_sync(0xffffffffu, ibase, 31) + ipre - (uint32_t)npend;
+        for (int q = 0; q < npend; q++)
+            if (ibase + q < cap_items) {
+                items[ibase + q] = pend[q];
+                atomicAdd(&hist[pend[q].key], 1u);
+            }
     }
-    return v;
 }
 
-__global__ void __launch_bounds__(256, 3) k_orf_score(Planes pl, const uint32_t *__restrict__ gcpre, const int64_t *__restrict__ cwoff,
-                                                      const int32_t *__restrict__ clen, const DevModel *__restrict__ models,
-                                                      OrfRec *const *orfs_m, uint32_t *const *starts_m,
-                                                      const unsigned long long *counters_m, Cand *const *surv_m,
-                                                      uint32_t *const *bcount_m, unsigned long long *surv_counters, uint32_t cap_orf,
-                                                      uint32_t cap_surv, const ChainBufs *bufs_m) {
+// one block per model: item offsets per key (exclusive scan of the histogram, which is turned into the scatter
+// cursor); work units = chunks of WALK_CHUNK items of one section pair, with their prefix over pairs
+__global__ void __launch_bounds__(1024) k_item_plan(uint32_t *const *hist_m, uint32_t *const *item_off_m, uint32_t *const *unit_off_m,
+                                                    const DevModel *__restrict__ models, uint32_t *unit_totals) {
+    __shared__ uint32_t carry_i;
+    const int mi = blockIdx.x;
+    const int npair = models[mi].npair, nkeys = npair * WALK_CLASSES;
+    uint32_t *hist = hist_m[mi], *ioff = item_off_m[mi], *uoff = unit_off_m[mi];
+    if (threadIdx.x == 0) carry_i = 0;
+    __syncthreads();
+    for (int b = 0; b < nkeys; b += 1024) {
+        const int i = b + threadIdx.x;
+        const uint32_t cnt = i < nkeys ? hist[i] : 0u;
+        uint32_t ti;
+        const uint32_t ei = block_exclusive_scan(cnt, &ti);
+        if (i < nkeys) {
+            ioff[i] = carry_i + ei;
+            hist[i] = carry_i + ei;  // scatter cursor
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) carry_i += ti;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        ioff[nkeys] = carry_i;
+        uint32_t acc = 0;
+        for (int p = 0; p < npair; p++) {
+            uoff[p] = acc;
+            const uint32_t cnt = ioff[(p + 1) * WALK_CLASSES] - ioff[p * WALK_CLASSES];
+            acc += (cnt + WALK_CHUNK - 1) / WALK_CHUNK;
+        }
+        uoff[npair] = acc;
+        unit_totals[mi] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_item_scatter(const ItemRec *const *items_m, ItemRec *const *sorted_m, uint32_t *const *cursor_m,
+                                                      const unsigned long long *counters_m, uint32_t cap_items) {
+    const int mi = blockIdx.y;
+    unsigned long long n = counters_m[(size_t)mi * 8 + 2];
+    if (n > cap_items) n = cap_items;
+    const ItemRec *items = items_m[mi];
+    ItemRec *sorted = sorted_m[mi];
+    uint32_t *cursor = cursor_m[mi];
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < (int64_t)n; k += (int64_t)gridDim.x * blockDim.x) {
+        const ItemRec it = items[k];
+        sorted[atomicAdd(&cursor[it.key], 1u)] = it;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the walk: thread per item, the section pair's table in shared memory
+// ------------------------------------------------------------------------------------------------
+// A work unit is a chunk of up to WALK_CHUNK items of one (model, section pair), ordered long to short.  Persistent
+// CTAs take units in order, so a CTA reloads its 96 KB table only when the pair changes; inside a unit the CTA's warps
+// take 32 items at a time from a shared counter and never wait for each other.  Each thread walks its item from the
+// letter before the stop codon down to lo_pos, keeping the (k+1)-letter window as two shift registers, adds one Quad
+// per position, and stores the running sums whenever it passes the first full-order position of a start codon of its
+// pair (the starts of a pair are chained, the next one is prefetched).  No shuffles.
+struct Acc4 {
+    double cB, oB, cA, oA;
+};
+
+template <bool SMEM_TABLE>
+__global__ void __launch_bounds__(WALK_UNIT, 2) k_walk(Planes pl, const int64_t *__restrict__ cwoff, const DevModel *__restrict__ models,
+                                                       int n_models, const OrfRec *const *orfs_m, const StartRec *const *starts_m,
+                                                       const ItemRec *const *items_m, const uint32_t *const *item_off_m,
+                                                       const uint32_t *const *unit_off_m, const uint32_t *__restrict__ unit_totals,
+                                                       Acc4 *const *sums_m, unsigned int *next_unit) {
+    extern __shared__ __align__(32) unsigned char smem_raw[];
+    Quad *tbl = reinterpret_cast<Quad *>(smem_raw);
+    __shared__ int s_model, s_pair;
+    __shared__ uint32_t s_first, s_end;
+    __shared__ unsigned int s_next;
+    const int lane = lane_id();
+    int loaded_model = -1, loaded_pair = -1;
+    while (true) {
+        if (threadIdx.x == 0) {
+            unsigned int u = atomicAdd(next_unit, 1u);
+            int m = 0;
+            while (m < n_models && u >= unit_totals[m]) { u -= unit_totals[m]; m++; }
+            s_model = m;
+            if (m < n_models) {
+                const uint32_t *uoff = unit_off_m[m];
+                int lo = 0, hi = models[m].npair;  // last pair with uoff[pair] <= u (uoff has npair + 1 entries)
+                while (lo + 1 < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (uoff[mid] <= u) lo = mid; else hi = mid;
+                }
+                s_pair = lo;
+                const uint32_t *ioff = item_off_m[m];
+                const uint32_t first = ioff[lo * WALK_CLASSES] + (u - uoff[lo]) * WALK_CHUNK;
+                s_first = first;
+                s_end = min(first + (uint32_t)WALK_CHUNK, ioff[(lo + 1) * WALK_CLASSES]);
+                s_next = first;
+            }
+        }
+        __syncthreads();
+        const int mi = s_model;
+        if (mi >= n_models) break;
+        const DevModel &dm = models[mi];
+        const int pair = s_pair;
+        const int kc = dm.kc, nfull = dm.nfull;
+        const Quad *gq = dm.quad + (size_t)pair * 3 * nfull;
+        if (SMEM_TABLE && (mi != loaded_model || pair != loaded_pair)) {
+            const int4 *src = reinterpret_cast<const int4 *>(gq);
+            int4 *dst = reinterpret_cast<int4 *>(tbl);
+            const int n16 = 3 * nfull * 2;
+            for (int i = threadIdx.x; i < n16; i += WALK_UNIT) dst[i] = __ldg(src + i);
+            loaded_model = mi;
+            loaded_pair = pair;
+            __syncthreads();
+        }
+        const Quad *tq = SMEM_TABLE ? tbl : gq;
+        const uint32_t wmask = (1u << (kc + 1)) - 1u;
+        const uint32_t end = s_end;
+        const ItemRec *items = items_m[mi];
+        while (true) {
+            uint32_t w_first = 0;
+            if (lane == 0) w_first = atomicAdd(&s_next, 32u);
+            w_first = __shfl_sync(0xffffffffu, w_first, 0);
+            if (w_first >= end) break;
+            if (w_first + lane < end) {
+                const ItemRec it = items[w_first + lane];
+                const OrfRec rec = orfs_m[mi][it.orf];
+                const int t = rec.t, strand = rec.sf & 1;
+                const uint32_t *lo = pl.lo + (int64_t)strand * pl.W + cwoff[rec.contig];
+                const uint32_t *hi = pl.hi + (int64_t)strand * pl.W + cwoff[rec.contig];
+                const StartRec *st = starts_m[mi] + rec.base;
+                Acc4 *sums = sums_m[mi] + rec.base;
+                // the starts of my pair, from the one closest to the stop outwards, one record prefetched ahead
+                int j = it.last;
+                StartRec cur = st[j];
+                auto full_of = [&](const StartRec &sr) {
+                    return (int)(sr.sraw & 0x7fffffffu) + (((sr.sraw >> 31) && strand == 0) ? 0 : 3) + kc;
+                };
+                int target = full_of(cur);
+                StartRec nxt = cur;
+                if (cur.link >= 0) nxt = st[cur.link];
+                Acc4 acc = {0, 0, 0, 0};
+                int i = t - 1;
+                uint32_t hb, lb;
+                window_bits(lo, hi, i - kc, kc + 1, hb, lb);
+                int ph = (((-1 - kc) % 3) + 3) % 3;   // codon position of the window's first letter at i = t-1
+                int p = i - kc - 1;                   // next letter to shift in
+                uint32_t cl = 0, ch = 0;
+                if (p >= 0) { cl = lo[p >> 5]; ch = hi[p >> 5]; }
+                const int lo_pos = it.lo_pos;
+                while (i >= lo_pos) {
+                    // a run ends at the next target, at lo_pos, or where the current plane word is used up
+                    int run = i - max(target, lo_pos) + 1;
+                    if (p >= 0) run = min(run, (p & 31) + 1);
+                    int bit = p & 31;
+                    for (int r = 0; r < run; r++) {
+                        const Quad *q = tq + ph * nfull + ((hb << (kc + 1)) | lb);
+                        const double2 x = *reinterpret_cast<const double2 *>(q);
+                        const double2 y = *(reinterpret_cast<const double2 *>(q) + 1);
+                        acc.cB += x.x; acc.oB += x.y; acc.cA += y.x; acc.oA += y.y;
+                        lb = ((lb << 1) & wmask) | ((cl >> bit) & 1u);
+                        hb = ((hb << 1) & wmask) | ((ch >> bit) & 1u);
+                        bit = (bit - 1) & 31;
+                        ph = ph == 0 ? 2 : ph - 1;
+                    }
+                    i -= run;
+                    p -= run;
+                    if (p >= 0 && (p & 31) == 31) { cl = lo[p >> 5]; ch = hi[p >> 5]; }
+                    if (p < 0) { cl = 0; ch = 0; }
+                    while (i + 1 == target) {   // a virtual and a real start may share their first full-order position
+                        sums[j] = acc;
+                        j = cur.link;
+                        if (j < 0) { target = -1; break; }
+                        cur = nxt;
+                        target = full_of(cur);
+                        if (cur.link >= 0) nxt = st[cur.link];
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-start totals: order ramp, domain choice, duration / start / stop terms, pruning, bucket histogram
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_final(Planes pl, const int64_t *__restrict__ cwoff, const int32_t *__restrict__ clen,
+                                               const DevModel *__restrict__ models, const OrfRec *const *orfs_m,
+                                               const StartRec *const *starts_m, const Acc4 *const *sums_m,
+                                               const unsigned long long *counters_m, Cand *const *surv_m, uint32_t *const *bcount_m,
+                                               unsigned long long *surv_counters, uint32_t cap_starts, uint32_t cap_surv) {
     const int mi = blockIdx.y;
     const DevModel &dm = models[mi];
     const int lane = lane_id();
-    const int warps_per_block = blockDim.x >> 5;
-    const int64_t nwarps = (int64_t)gridDim.x * warps_per_block;
-    unsigned long long n_orfs = counters_m[(size_t)mi * 8 + 0];
-    if (n_orfs > cap_orf) n_orfs = cap_orf;
+    unsigned long long n_starts = counters_m[(size_t)mi * 8 + 1];
+    if (n_starts > cap_starts) n_starts = cap_starts;
     const OrfRec *orfs = orfs_m[mi];
-    const uint32_t *starts = starts_m[mi];
+    const StartRec *starts = starts_m[mi];
+    const Acc4 *sums = sums_m[mi];
     Cand *surv = surv_m[mi];
     uint32_t *bcount = bcount_m[mi];
-    int32_t *gptr = bufs_m[mi].gptr;
-    const int kc = dm.kc, kn = dm.kn;
-    const int nfull = dm.nfull, nnon = dm.nnon, nramp = dm.nramp, nnramp = dm.nnramp;
-    const Quad *quad = dm.quad;
-    const int ph_lane0 = (((-1 - lane - kc) % 3) + 3) % 3;  // phase of the window's first letter at i = t-1-lane
-
-    for (int64_t oi = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); oi < (int64_t)n_orfs; oi += nwarps) {
-        const OrfRec rec = orfs[oi];
-        if (lane == 0) gptr[oi] = GPTR_UNSET;
-        const int c = rec.contig, t = rec.t, strand = rec.sf & 1;
-        const bool pstop = (rec.sf & 0x100u) != 0;
-        const int L = clen[c];
-        const int64_t w0 = cwoff[c];
-        const uint32_t *lo = pl.lo + (int64_t)strand * pl.W + w0;
-        const uint32_t *hi = pl.hi + (int64_t)strand * pl.W + w0;
-        // type of the stop codon (uniform)
-        int stop_type = 0;
-        if (!pstop) {
-            uint32_t hb, lb;
-            window_bits(lo, hi, t, 3, hb, lb);
-            // TAA: A at +1,+2 ; TAG: G at +2 ; TGA: G at +1
-            bool g1 = ((hb >> 1) & 1u) && !((lb >> 1) & 1u);
-            bool g2 = ((hb >> 2) & 1u) && !((lb >> 2) & 1u);
-            stop_type = g1 ? 2 : (g2 ? 1 : 0);
-        }
-        for (uint32_t b0 = 0; b0 < rec.n; b0 += 32) {
-            const bool has = b0 + lane < rec.n;
-            uint32_t sraw = has ? starts[rec.base + b0 + lane] : 0u;
-            const bool virt = (sraw >> 31) != 0;
-            const int s = (int)(sraw & 0x7fffffffu);
+    const int kc = dm.kc, nramp = dm.nramp;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    // whole warps iterate together (ballots below); the loop bound is rounded up to a multiple of 32
+    for (int64_t k0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~31LL; k0 < (int64_t)n_starts; k0 += stride) {
+        const int64_t k = k0 + lane;
+        const bool has = k < (int64_t)n_starts;
+        bool keep = false;
+        Cand cd;
+        cd.right = 0; cd.contig = 0;
+        uint32_t orf_id = 0xffffffffu;
+        int s = 0, strand = 0;
+        bool virt = false;
+        int64_t w0 = 0;
+        uint32_t orf_base = 0, orf_n = 0;
+        if (has) {
+            const StartRec sr = starts[k];
+            const OrfRec rec = orfs[sr.orf];
+            orf_id = sr.orf; orf_base = rec.base; orf_n = rec.n;
+            const int c = rec.contig, t = rec.t;
+            strand = rec.sf & 1;
+            const bool pstop = (rec.sf & 0x100u) != 0;
+            const int L = clen[c];
+            w0 = cwoff[c];
+            const uint32_t *lo = pl.lo + (int64_t)strand * pl.W + w0;
+            const uint32_t *hi = pl.hi + (int64_t)strand * pl.W + w0;
+            virt = (sr.sraw >> 31) != 0;
+            s = (int)(sr.sraw & 0x7fffffffu);
             const int len = t + 3 - s;
-            int gc = 0, secB = -1, secA = -1, pair = 0x7fffffff;
-            if (has) {
-                int a = strand ? (L - 1 - (t + 2)) : s, b = strand ? (L - 1 - s) : (t + 2);
-                int gcn = gc_count_fwd(pl.lo, pl.hi, gcpre, w0, a, b);
-                gc = (200 * gcn + len) / (2 * len);
-                secB = dm.map[0][gc];
-                secA = dm.map[1][gc];
-                pair = dm.pair[gc];
-            }
-            // forward-strand candidates whose start lies beyond the left edge are summed from their first letter
+            const int gc = (int)(sr.pg >> 16), pair = (int)(sr.pg & 0xffffu);
+            const int secB = dm.map[0][gc], secA = dm.map[1][gc];
             const int first = s + ((virt && strand == 0) ? 0 : 3);
             const int fullstart = first + kc;
             Acc4 acc = {0, 0, 0, 0};
-            // ramp: orders 0..kc-1 at positions first .. first+kc-1 (window always starts on a codon boundary)
-            if (has) {
-                for (int j = 0; j < kc && first + j <= t - 1; j++) {
-                    uint32_t hb, lb;
-                    window_bits(lo, hi, first, j + 1, hb, lb);
-                    uint32_t idx = (hb << (j + 1)) | lb;
-                    uint32_t idn;
-                    const double *lnB, *lnA;
-                    if (j < kn) {
-                        idn = idx;
-                        lnB = dm.ln_ramp + ((size_t)max(secB, 0) * dm.knr + j) * nnramp;
-                        lnA = dm.ln_ramp + ((size_t)max(secA, 0) * dm.knr + j) * nnramp;
-                    } else {
-                        idn = ((hb >> (j - kn)) << (kn + 1)) | (lb >> (j - kn));
-                        lnB = dm.ln_full + (size_t)max(secB, 0) * nnon;
-                        lnA = dm.ln_full + (size_t)max(secA, 0) * nnon;
-                    }
-                    if (secB >= 0) {
-                        double cv = dm.lc_ramp[(((size_t)secB * dm.kr + j) * 3 + 0) * nramp + idx];
-                        acc.cB += cv;
-                        acc.oB += cv - lnB[idn];
-                    }
-                    if (secA >= 0) {
-                        double cv = dm.lc_ramp[(((size_t)secA * dm.kr + j) * 3 + 0) * nramp + idx];
-                        acc.cA += cv;
-                        acc.oA += cv - lnA[idn];
-                    }
-                }
+            if (fullstart <= t - 1) acc = sums[k];
+            // order ramp: orders 0..kc-1 at positions first .. first+kc-1 (window starts on a codon boundary)
+            const Quad *rq = dm.rquad + (size_t)pair * dm.kr * nramp;
+            for (int j = 0; j < kc && first + j <= t - 1; j++) {
+                uint32_t hb, lb;
+                window_bits(lo, hi, first, j + 1, hb, lb);
+                const Quad *q = rq + (size_t)j * nramp + ((hb << (j + 1)) | lb);
+                const double2 x = __ldg(reinterpret_cast<const double2 *>(q));
+                const double2 y = __ldg(reinterpret_cast<const double2 *>(q) + 1);
+                acc.cB += x.x; acc.oB += x.y; acc.cA += y.x; acc.oA += y.y;
             }
-            // full-order part: one walk from t-1 down per distinct section pair among this batch's starts
-            bool done = !has || fullstart > t - 1;
-            while (true) {
-                const int psel = warp_min_i(done ? 0x7fffffff : pair);
-                if (psel == 0x7fffffff) break;
-                const bool mine = !done && pair == psel;
-                const int lo_pos = warp_min_i(mine ? fullstart : 0x7fffffff);
-                const Quad *tq = quad + (size_t)psel * 3 * nfull;
-                Acc4 run = {0, 0, 0, 0};  // lane-private sum over this lane's positions visited so far
-                Acc4 res = {0, 0, 0, 0};
-                int ph = ph_lane0;
-                for (int hiPos = t - 1; hiPos >= lo_pos; hiPos -= 32) {
-                    const int i = hiPos - lane;
-                    Acc4 v = {0, 0, 0, 0};
-                    if (i >= lo_pos) {
-                        uint32_t hb, lb;
-                        window_bits(lo, hi, i - kc, kc + 1, hb, lb);
-                        const Quad *q = tq + (size_t)ph * nfull + ((hb << (kc + 1)) | lb);
-                        const double2 x = __ldg(reinterpret_cast<const double2 *>(q));
-                        const double2 y = __ldg(reinterpret_cast<const double2 *>(q) + 1);
-                        v.cB = x.x; v.oB = x.y; v.cA = y.x; v.oA = y.y;
-                    }
-                    // starts whose full-order region begins inside this chunk take their suffix sum now
-                    uint32_t hits = __ballot_sync(0xffffffffu, mine && fullstart <= hiPos && fullstart > hiPos - 32);
-                    while (hits) {
-                        const int o = __ffs(hits) - 1;
-                        hits &= hits - 1;
-                        const int tl = hiPos - __shfl_sync(0xffffffffu, fullstart, o);
-                        Acc4 part = run;
-                        if (lane <= tl) { part.cB += v.cB; part.oB += v.oB; part.cA += v.cA; part.oA += v.oA; }
-                        part = warp_sum4(part);
-                        if (lane == o) res = part;
-                    }
-                    run.cB += v.cB; run.oB += v.oB; run.cA += v.cA; run.oA += v.oA;
-                    ph = ph == 2 ? 0 : ph + 1;
-                }
-                if (mine) { acc.cB += res.cB; acc.oB += res.oB; acc.cA += res.cA; acc.oA += res.oA; done = true; }
-            }
-            // totals
-            bool keep = false;
-            Cand cd;
-            if (has && (secB >= 0 || secA >= 0)) {
+            if (secB >= 0 || secA >= 0) {
                 const bool arc = secB < 0 || (secA >= 0 && acc.cA > acc.cB);
                 const SectionScalars *sc = dm.sc + (arc ? secA : secB);
-                double dl = (double)len;
+                const double dl = (double)len;
                 double total = (arc ? acc.oA : acc.oB) + 2.0 * log(dl) + dl * sc->dur_slope + sc->dur_const - 1.3862943611198906;
                 if (!virt) {
                     uint32_t hb, lb;
                     window_bits(lo, hi, s, 1, hb, lb);
                     total += sc->start_lo[hb ? (lb ? 2 : 1) : 0];  // A -> ATG, G -> GTG, T -> TTG
                 }
-                if (!pstop) total += sc->stop_lo[stop_type];
+                if (!pstop) {
+                    uint32_t hb, lb;
+                    window_bits(lo, hi, t, 3, hb, lb);
+                    // TAA: A at +1,+2 ; TAG: G at +2 ; TGA: G at +1
+                    const bool g1 = ((hb >> 1) & 1u) && !((lb >> 1) & 1u);
+                    const bool g2 = ((hb >> 2) & 1u) && !((lb >> 2) & 1u);
+                    total += sc->stop_lo[g1 ? 2 : (g2 ? 1 : 0)];
+                }
                 keep = total > 0.0;
                 cd.contig = c;
                 cd.left = strand ? (L - 1 - (t + 2)) : s;
                 cd.right = strand ? (L - 1 - s) : (t + 2);
-                cd.orf = (uint32_t)oi;
+                cd.orf = sr.orf;
                 cd.total = total;
                 cd.gc = (int16_t)gc;
                 cd.strand = strand ? -1 : 1;
                 cd.flags = (uint8_t)((arc ? 1 : 0) | (virt ? 2 : 0) | (pstop ? 4 : 0));
                 cd.len = len;
             }
-            const uint32_t km = __ballot_sync(0xffffffffu, keep);
-            if (km && strand && rec.n <= 32) {
-                // reverse strand: the survivor with the largest s has the smallest forward right end, so the chain meets it
-                // first among the starts of this ORF and can skip the lookup of the ORF's shared back-pointer
-                const int smax = -warp_min_i(keep ? -s : 0x7fffffff);
-                const bool any_virt = __any_sync(0xffffffffu, keep && virt);
-                if (keep && s == smax && !any_virt) cd.flags |= 8;
-            }
-            if (km) {
-                unsigned long long base = 0;
-                if (lane == 0) base = atomicAdd(&surv_counters[mi], (unsigned long long)__popc(km));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (keep) {
-                    unsigned long long k = base + __popc(km & ((1u << lane) - 1u));
-                    if (k < cap_surv) {
-                        surv[k] = cd;
-                        atomicAdd(&bcount[(w0 * 32 + cd.right) >> 7], 1u);
-                    }
+        }
+        // reverse strand: the survivor with the largest s has the smallest forward right end, so the chain meets it
+        // first among the starts of its ORF and may skip the lookup of the ORF's shared back-pointer.  Decidable here
+        // only when all starts of the ORF sit in this warp's 32 slots (starts of an ORF are contiguous, ascending in s).
+        const uint32_t km = __ballot_sync(0xffffffffu, keep);
+        const uint32_t same = __match_any_sync(0xffffffffu, orf_id);   // lanes holding starts of my ORF
+        const uint32_t vm = __ballot_sync(0xffffffffu, has && virt);
+        if (keep && strand) {
+            const bool whole = (int64_t)orf_base >= k0 && (int64_t)orf_base + orf_n <= k0 + 32;
+            const bool last = (((same & km) >> lane) >> 1) == 0;        // no kept start of this ORF in a higher lane
+            if (whole && last && !(vm & same & km)) cd.flags |= 8;
+        }
+        if (km) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(&surv_counters[mi], (unsigned long long)__popc(km));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (keep) {
+                const unsigned long long kk = base + __popc(km & ((1u << lane) - 1u));
+                if (kk < cap_surv) {
+                    surv[kk] = cd;
+                    atomicAdd(&bcount[(w0 * 32 + cd.right) >> 7], 1u);
                 }
             }
         }
@@ -970,20 +1322,68 @@ void launch_pack(const char *ascii, const int64_t *aoff, const int64_t *cwoff, c
     k_pack<<<grid, 256, 0, st>>>(ascii, aoff, cwoff, clen, grp2contig, W, lo, hi, gccount, bad_letter);
 }
 
-void launch_orf_find(Planes pl, const int64_t *cwoff, const int32_t *clen, const int32_t *grp2contig, const DevModel *models,
-                     int n_models, OrfRec *const *orfs_m, uint32_t *const *starts_m, unsigned long long *counters_m,
-                     uint32_t cap_orf, uint32_t cap_starts, cudaStream_t st) {
-    dim3 grid((unsigned)((pl.W + 127) / 128), 2, n_models);
-    k_orf_find<<<grid, 128, 0, st>>>(pl, cwoff, clen, grp2contig, models, orfs_m, starts_m, counters_m, cap_orf, cap_starts);
+int launch_laststop(Planes pl, const int64_t *cwoff, const int32_t *clen, const int32_t *grp2contig, const DevModel *models,
+                    int n_models, uint32_t *const *ls_m, uint32_t *const *ls_tile_m, cudaStream_t st) {
+    const int64_t nw = 2 * pl.W, nt = (nw + LS_THREADS - 1) / LS_THREADS;
+    dim3 grid((unsigned)nt, n_models);
+    k_laststop_tiles<<<grid, LS_THREADS, 0, st>>>(pl, cwoff, clen, grp2contig, models, ls_m, ls_tile_m);
+    k_laststop_sums<<<n_models, 1024, 0, st>>>(ls_tile_m, nt);
+    k_laststop_apply<<<grid, LS_THREADS, 0, st>>>(ls_m, ls_tile_m, nw);
+    return 3;
 }
 
-void launch_orf_score(Planes pl, const uint32_t *gcpre, const int64_t *cwoff, const int32_t *clen, const DevModel *models,
-                      int n_models, OrfRec *const *orfs_m, uint32_t *const *starts_m, const unsigned long long *counters_m,
-                      Cand *const *surv_m, uint32_t *const *bcount_m, unsigned long long *surv_counters, uint32_t cap_orf,
-                      uint32_t cap_surv, const ChainBufs *bufs_m, int n_sm, cudaStream_t st) {
+void launch_orf_find(Planes pl, const int64_t *cwoff, const int32_t *clen, const int32_t *grp2contig, const DevModel *models,
+                     int n_models, const uint32_t *const *ls_m, OrfRec *const *orfs_m, unsigned long long *counters_m,
+                     uint32_t cap_orf, cudaStream_t st) {
+    dim3 grid((unsigned)((2 * pl.W + 127) / 128), n_models);
+    k_orf_find<<<grid, 128, 0, st>>>(pl, cwoff, clen, grp2contig, models, ls_m, orfs_m, counters_m, cap_orf);
+}
+
+void launch_orf_prep(Planes pl, const uint32_t *gcpre, const int64_t *cwoff, const int32_t *clen, const DevModel *models, int n_models,
+                     OrfRec *const *orfs_m, StartRec *const *starts_m, ItemRec *const *items_m, uint32_t *const *hist_m,
+                     unsigned long long *counters_m, const ChainBufs *bufs_m, uint32_t cap_orf, uint32_t cap_starts, uint32_t cap_items,
+                     int n_sm, cudaStream_t st) {
+    dim3 grid(n_sm * 16, n_models);
+    k_orf_prep<<<grid, 128, 0, st>>>(pl, gcpre, cwoff, clen, models, orfs_m, starts_m, items_m, hist_m, counters_m, bufs_m, cap_orf,
+                                     cap_starts, cap_items);
+}
+
+int launch_item_sort(const ItemRec *const *items_m, ItemRec *const *sorted_m, uint32_t *const *hist_m, uint32_t *const *item_off_m,
+                     uint32_t *const *unit_off_m, const DevModel *models, int n_models, uint32_t *unit_totals,
+                     const unsigned long long *counters_m, uint32_t cap_items, int n_sm, cudaStream_t st) {
+    k_item_plan<<<n_models, 1024, 0, st>>>(hist_m, item_off_m, unit_off_m, models, unit_totals);
+    dim3 grid(n_sm * 4, n_models);
+    k_item_scatter<<<grid, 256, 0, st>>>(items_m, sorted_m, hist_m, counters_m, cap_items);
+    return 2;
+}
+
+int walk_smem_bytes(int cod_order) { return 3 * (1 << (2 * (cod_order + 1))) * (int)sizeof(Quad); }
+
+int launch_walk(Planes pl, const int64_t *cwoff, const DevModel *models, int n_models, int max_cod_order, const OrfRec *const *orfs_m,
+                const StartRec *const *starts_m, const ItemRec *const *items_m, const uint32_t *const *item_off_m,
+                const uint32_t *const *unit_off_m, const uint32_t *unit_totals, void *const *sums_m, unsigned int *next_unit, int n_sm,
+                cudaStream_t st) {
+    const int smem = walk_smem_bytes(max_cod_order);
+    Acc4 *const *sums = reinterpret_cast<Acc4 *const *>(sums_m);
+    if (smem <= 100 * 1024) {
+        cudaFuncSetAttribute(k_walk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        k_walk<true><<<n_sm * 2, WALK_UNIT, smem, st>>>(pl, cwoff, models, n_models, orfs_m, starts_m, items_m, item_off_m, unit_off_m,
+                                                        unit_totals, sums, next_unit);
+    } else {
+        // tables of order > 4 do not fit next to a second CTA: gather from global memory (L1/L2) instead
+        k_walk<false><<<n_sm * 4, WALK_UNIT, 0, st>>>(pl, cwoff, models, n_models, orfs_m, starts_m, items_m, item_off_m, unit_off_m,
+                                                      unit_totals, sums, next_unit);
+    }
+    return 1;
+}
+
+void launch_final(Planes pl, const int64_t *cwoff, const int32_t *clen, const DevModel *models, int n_models, const OrfRec *const *orfs_m,
+                  const StartRec *const *starts_m, void *const *sums_m, const unsigned long long *counters_m, Cand *const *surv_m,
+                  uint32_t *const *bcount_m, unsigned long long *surv_counters, uint32_t cap_starts, uint32_t cap_surv, int n_sm,
+                  cudaStream_t st) {
     dim3 grid(n_sm * 8, n_models);
-    k_orf_score<<<grid, 256, 0, st>>>(pl, gcpre, cwoff, clen, models, orfs_m, starts_m, counters_m, surv_m, bcount_m,
-                                      surv_counters, cap_orf, cap_surv, bufs_m);
+    k_final<<<grid, 256, 0, st>>>(pl, cwoff, clen, models, orfs_m, starts_m, reinterpret_cast<const Acc4 *const *>(sums_m), counters_m,
+                                  surv_m, bcount_m, surv_counters, cap_starts, cap_surv);
 }
 
 void launch_scatter(const Cand *const *surv_m, Cand *const *sorted_m, uint32_t *const *boff_m,

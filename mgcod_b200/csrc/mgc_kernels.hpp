@@ -9,6 +9,8 @@ namespace mgc {
 
 struct DevModel;
 struct OrfRec;
+struct StartRec;
+struct ItemRec;
 struct Cand;
 struct Planes;
 struct ChainBufs;
@@ -18,13 +20,26 @@ int launch_exclusive_scan(const uint32_t *in, uint32_t *out, uint32_t *tile_sums
 void launch_groups(const int64_t *cwoff, int32_t n_contigs, int64_t n_groups, int32_t *grp2contig, cudaStream_t st);
 void launch_pack(const char *ascii, const int64_t *aoff, const int64_t *cwoff, const int32_t *clen, const int32_t *grp2contig,
                  int64_t W, uint32_t *lo, uint32_t *hi, uint32_t *gccount, int *bad_letter, cudaStream_t st);
+int launch_laststop(Planes pl, const int64_t *cwoff, const int32_t *clen, const int32_t *grp2contig, const DevModel *models,
+                    int n_models, uint32_t *const *ls_m, uint32_t *const *ls_tile_m, cudaStream_t st);
 void launch_orf_find(Planes pl, const int64_t *cwoff, const int32_t *clen, const int32_t *grp2contig, const DevModel *models,
-                     int n_models, OrfRec *const *orfs_m, uint32_t *const *starts_m, unsigned long long *counters_m,
-                     uint32_t cap_orf, uint32_t cap_starts, cudaStream_t st);
-void launch_orf_score(Planes pl, const uint32_t *gcpre, const int64_t *cwoff, const int32_t *clen, const DevModel *models,
-                      int n_models, OrfRec *const *orfs_m, uint32_t *const *starts_m, const unsigned long long *counters_m,
-                      Cand *const *surv_m, uint32_t *const *bcount_m, unsigned long long *surv_counters, uint32_t cap_orf,
-                      uint32_t cap_surv, const ChainBufs *bufs_m, int n_sm, cudaStream_t st);
+                     int n_models, const uint32_t *const *ls_m, OrfRec *const *orfs_m, unsigned long long *counters_m,
+                     uint32_t cap_orf, cudaStream_t st);
+void launch_orf_prep(Planes pl, const uint32_t *gcpre, const int64_t *cwoff, const int32_t *clen, const DevModel *models, int n_models,
+                     OrfRec *const *orfs_m, StartRec *const *starts_m, ItemRec *const *items_m, uint32_t *const *hist_m,
+                     unsigned long long *counters_m, const ChainBufs *bufs_m, uint32_t cap_orf, uint32_t cap_starts, uint32_t cap_items,
+                     int n_sm, cudaStream_t st);
+int launch_item_sort(const ItemRec *const *items_m, ItemRec *const *sorted_m, uint32_t *const *hist_m, uint32_t *const *item_off_m,
+                     uint32_t *const *unit_off_m, const DevModel *models, int n_models, uint32_t *unit_totals,
+                     const unsigned long long *counters_m, uint32_t cap_items, int n_sm, cudaStream_t st);
+int launch_walk(Planes pl, const int64_t *cwoff, const DevModel *models, int n_models, int max_cod_order, const OrfRec *const *orfs_m,
+                const StartRec *const *starts_m, const ItemRec *const *items_m, const uint32_t *const *item_off_m,
+                const uint32_t *const *unit_off_m, const uint32_t *unit_totals, void *const *sums_m, unsigned int *next_unit, int n_sm,
+                cudaStream_t st);
+void launch_final(Planes pl, const int64_t *cwoff, const int32_t *clen, const DevModel *models, int n_models, const OrfRec *const *orfs_m,
+                  const StartRec *const *starts_m, void *const *sums_m, const unsigned long long *counters_m, Cand *const *surv_m,
+                  uint32_t *const *bcount_m, unsigned long long *surv_counters, uint32_t cap_starts, uint32_t cap_surv, int n_sm,
+                  cudaStream_t st);
 void launch_scatter(const Cand *const *surv_m, Cand *const *sorted_m, uint32_t *const *boff_m,
                     const unsigned long long *surv_counters, const int64_t *cwoff, uint32_t cap_surv, int n_models, int n_sm,
                     cudaStream_t st);
