@@ -52,6 +52,13 @@ struct StartRec {
     int32_t link;       // index (within the ORF) of the previous start of the same section pair that has a full-order region, -1 none
 };
 
+// one 32-letter word of an ORF's admissible start range
+struct WordItem {
+    uint32_t orf;
+    uint32_t pre;       // starts of the ORF before this word (incl. the virtual one)
+    uint32_t j;         // word index within the range
+};
+
 // one walk of an ORF under one section pair: serves every start of that pair
 struct ItemRec {
     uint32_t orf;

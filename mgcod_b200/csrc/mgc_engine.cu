@@ -116,7 +116,7 @@ struct DevBuf {
 
 struct PerModel {
     DevBuf lc_full, ln_full, lc_ramp, ln_ramp, sc, quad, rquad;
-    DevBuf ls, ls_tile, orfs, starts, items, items_sorted, hist, item_off, unit_off, sums;
+    DevBuf ls, ls_tile, orfs, starts, witems, items, items_sorted, hist, item_off, unit_off, sums;
     DevBuf surv, sorted, bcount, cum, prev, gptr;
     DevBuf av_right, av_left, av_ls, av_idx, av_cum, av_pmax, av_parg, chain, gene_count, gene_off, contig_total, genes;
 };
@@ -141,6 +141,8 @@ struct mgc_engine {
     DevBuf ascii, aoff, cwoff, clen, grp2contig, order, lo, hi, gc, tile_sums, flags;
     // pointer tables + counters (device)
     DevBuf t_orfs, t_starts, t_surv, t_sorted, t_bcount, t_gene_off, t_genes, t_chainbufs;
+    DevBuf t_witems;
+    uint32_t cap_witems = 0;
     DevBuf t_ls, t_ls_tile, t_items, t_items_sorted, t_hist, t_item_off, t_unit_off, t_sums, unit_totals, next_unit;
     uint32_t cap_items = 0;
     int max_cod_order = 0;
@@ -274,6 +276,8 @@ void ensure_batch_buffers(mgc_engine *e) {
     e->cap_starts = (uint32_t)std::min<int64_t>(nt / 8 + 8192, 0x7fffff00);
     e->cap_items = (uint32_t)std::min<int64_t>(nt / 16 + 8192, 0x7fffff00);
     e->cap_surv = (uint32_t)std::min<int64_t>(nt / 24 + 8192, 0x7fffff00);
+    e->cap_witems = (uint32_t)std::min<int64_t>(nt / 8 + 8192, 0x7fffff00);
+    std::vector<void *> t_witems(M);
     std::vector<void *> t_orfs(M), t_starts(M), t_surv(M), t_sorted(M), t_bcount(M), t_gene_off(M), t_genes(M);
     std::vector<void *> t_ls(M), t_ls_tile(M), t_items(M), t_items_sorted(M), t_hist(M), t_item_off(M), t_unit_off(M), t_sums(M);
     const int64_t ls_tiles = (2 * W + 255) / 256;
@@ -283,6 +287,8 @@ void ensure_batch_buffers(mgc_engine *e) {
         p.orfs.ensure((size_t)e->cap_orf * sizeof(OrfRec));
         p.starts.ensure((size_t)e->cap_starts * sizeof(StartRec));
         p.sums.ensure((size_t)e->cap_starts * 32);
+        p.witems.ensure((size_t)e->cap_witems * sizeof(WordItem));
+        t_witems[i] = p.witems.p;
         p.items.ensure((size_t)e->cap_items * sizeof(ItemRec));
         p.items_sorted.ensure((size_t)e->cap_items * sizeof(ItemRec));
         const size_t nkeys = (size_t)102 * WALK_CLASSES;   // at most 101 distinct section pairs
@@ -342,6 +348,7 @@ void ensure_batch_buffers(mgc_engine *e) {
     up(e->t_gene_off, t_gene_off.data(), M * sizeof(void *));
     up(e->t_genes, t_genes.data(), M * sizeof(void *));
     up(e->t_chainbufs, cb.data(), M * sizeof(ChainBufs));
+    up(e->t_witems, t_witems.data(), M * sizeof(void *));
     up(e->t_ls, t_ls.data(), M * sizeof(void *));
     up(e->t_ls_tile, t_ls_tile.data(), M * sizeof(void *));
     up(e->t_items, t_items.data(), M * sizeof(void *));
@@ -452,11 +459,10 @@ mgc_result *do_decode(mgc_engine *e) {
                     e->t_ls.as<const uint32_t *>(), e->t_orfs.as<OrfRec *>(), e->counters.as<unsigned long long>(), e->cap_orf, st);
     launches += 1;
     CUDA_TRY(cudaEventRecord(e->ev[2], st));
-    launch_orf_prep(pl, e->gc.as<uint32_t>(), e->cwoff.as<int64_t>(), e->clen.as<int32_t>(), e->d_models.as<DevModel>(), M,
-                    e->t_orfs.as<OrfRec *>(), e->t_starts.as<StartRec *>(), e->t_items.as<ItemRec *>(), e->t_hist.as<uint32_t *>(),
-                    e->counters.as<unsigned long long>(), e->t_chainbufs.as<ChainBufs>(), e->cap_orf, e->cap_starts, e->cap_items,
-                    e->n_sm, st);
-    launches += 1;
+    launches += launch_orf_prep(pl, e->gc.as<uint32_t>(), e->cwoff.as<int64_t>(), e->clen.as<int32_t>(), e->d_models.as<DevModel>(), M,
+                                e->t_orfs.as<OrfRec *>(), e->t_witems.as<WordItem *>(), e->t_starts.as<StartRec *>(),
+                                e->t_items.as<ItemRec *>(), e->t_hist.as<uint32_t *>(), e->counters.as<unsigned long long>(),
+                                e->t_chainbufs.as<ChainBufs>(), e->cap_orf, e->cap_starts, e->cap_items, e->cap_witems, e->n_sm, st);
     launches += launch_item_sort(e->t_items.as<const ItemRec *>(), e->t_items_sorted.as<ItemRec *>(), e->t_hist.as<uint32_t *>(),
                                  e->t_item_off.as<uint32_t *>(), e->t_unit_off.as<uint32_t *>(), e->d_models.as<DevModel>(), M,
                                  e->unit_totals.as<uint32_t>(), e->counters.as<unsigned long long>(), e->cap_items, e->n_sm, st);
@@ -508,7 +514,7 @@ mgc_result *do_decode(mgc_engine *e) {
     if (h_flags[0]) throw AlphabetError("sequence contains letters outside ACGT; ambiguous letters are not supported by this build");
     for (int i = 0; i < M; i++) {
         if (h_counters[(size_t)i * 8] > e->cap_orf || h_counters[(size_t)i * 8 + 1] > e->cap_starts ||
-            h_counters[(size_t)i * 8 + 2] > e->cap_items || h_surv[i] > e->cap_surv)
+            h_counters[(size_t)i * 8 + 2] > e->cap_items || h_counters[(size_t)i * 8 + 3] > e->cap_witems || h_surv[i] > e->cap_surv)
             throw std::runtime_error("device scratch exhausted (ORFs " + std::to_string(h_counters[(size_t)i * 8]) + ", starts " +
                                      std::to_string(h_counters[(size_t)i * 8 + 1]) + ", candidates " + std::to_string(h_surv[i]) + ")");
         e->stats.n_orfs += (int64_t)h_counters[(size_t)i * 8];
@@ -635,7 +641,7 @@ void mgc_engine_destroy(mgc_engine *e) {
     cudaDeviceSynchronize();
     for (auto &p : e->pm) {
         for (DevBuf *b : {&p.lc_full, &p.ln_full, &p.lc_ramp, &p.ln_ramp, &p.sc, &p.quad, &p.rquad, &p.ls, &p.ls_tile, &p.items, &p.items_sorted, &p.hist,
-                          &p.item_off, &p.unit_off, &p.sums, &p.orfs, &p.starts, &p.surv, &p.sorted, &p.bcount,
+                          &p.item_off, &p.unit_off, &p.sums, &p.witems, &p.orfs, &p.starts, &p.surv, &p.sorted, &p.bcount,
                           &p.cum, &p.prev, &p.gptr, &p.av_right, &p.av_left, &p.av_ls, &p.av_idx, &p.av_cum, &p.av_pmax, &p.av_parg,
                           &p.chain, &p.gene_count, &p.gene_off, &p.contig_total, &p.genes})
             b->release();
@@ -644,7 +650,7 @@ void mgc_engine_destroy(mgc_engine *e) {
                       &e->tile_sums, &e->flags, &e->t_orfs, &e->t_starts, &e->t_surv, &e->t_sorted, &e->t_bcount, &e->t_gene_off,
                       &e->t_genes, &e->t_chainbufs, &e->counters, &e->surv_counters, &e->work_counters, &e->model_cents,
                       &e->gene_totals, &e->t_ls, &e->t_ls_tile, &e->t_items, &e->t_items_sorted, &e->t_hist, &e->t_item_off,
-                      &e->t_unit_off, &e->t_sums, &e->unit_totals, &e->next_unit, &e->win_stride, &e->win_off, &e->win_labels, &e->win_cents})
+                      &e->t_unit_off, &e->t_sums, &e->t_witems, &e->unit_totals, &e->next_unit, &e->win_stride, &e->win_off, &e->win_labels, &e->win_cents})
         b->release();
     for (auto &ev : e->ev) cudaEventDestroy(ev);
     if (e->stream) cudaStreamDestroy(e->stream);

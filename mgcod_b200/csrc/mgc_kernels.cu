@@ -178,31 +178,61 @@ __global__ void __launch_bounds__(256) k_pack(const char *__restrict__ ascii, co
     if (w0 >= W) return;
     uint32_t mylo = 0, myhi = 0, mygc = 0;
     int bad = 0;
-    for (int r = 0; r < 32; r++) {
-        int64_t w = w0 + r;
-        uint32_t code = 0;
-        bool valid = false;
-        if (w < W) {
-            int c = grp2contig[w >> 2];
-            int L = clen[c];
-            int64_t i = (w - cwoff[c]) * 32 + lane;
-            if (i < L) {
-                valid = true;
-                unsigned char ch = (unsigned char)ascii[aoff[c] + (strand ? (L - 1 - i) : i)];
-                unsigned char up = ch & 0xDF;  // upper case
-                if (!(up == 'A' || up == 'C' || up == 'G' || up == 'T' || up == 'U')) bad = 1;
-                code = (ch >> 1) & 3u;         // A0 C1 G3 T2 (also U -> 2)
-                code ^= code >> 1;             // A0 C1 G2 T3
-                if (strand) code = 3u - code;
+    auto encode = [&](unsigned char ch, bool valid, uint32_t &code) {
+        const unsigned char up = ch & 0xDF;  // upper case
+        if (valid && !(up == 'A' || up == 'C' || up == 'G' || up == 'T' || up == 'U')) bad = 1;
+        code = (ch >> 1) & 3u;         // A0 C1 G3 T2 (also U -> 2)
+        code ^= code >> 1;             // A0 C1 G2 T3
+        if (strand) code = 3u - code;
+        if (!valid) code = 0;
+    };
+    const int c_first = grp2contig[w0 >> 2];
+    const int c_last = w0 + 31 < W ? grp2contig[(w0 + 31) >> 2] : -1;
+    if (c_first == c_last) {
+        // all 32 words belong to one contig: one set of contig parameters, 32 independent byte loads in flight
+        const int L = clen[c_first];
+        const int64_t i0 = (w0 - cwoff[c_first]) * 32 + lane;
+        const char *src = ascii + aoff[c_first];
+        for (int r0 = 0; r0 < 32; r0 += 8) {
+            unsigned char chs[8];
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                const int64_t i = i0 + (r0 + r) * 32;
+                chs[r] = i < L ? (unsigned char)__ldg(src + (strand ? (L - 1 - i) : i)) : (unsigned char)'A';
+            }
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                const bool valid = i0 + (r0 + r) * 32 < L;
+                uint32_t code;
+                encode(chs[r], valid, code);
+                const uint32_t bl = __ballot_sync(0xffffffffu, code & 1u);
+                const uint32_t bh = __ballot_sync(0xffffffffu, (code >> 1) & 1u);
+                const uint32_t bv = __ballot_sync(0xffffffffu, valid);
+                if (lane == r0 + r) { mylo = bl; myhi = bh; mygc = __popc((bl ^ bh) & bv); }
             }
         }
-        uint32_t bl = __ballot_sync(0xffffffffu, code & 1u);
-        uint32_t bh = __ballot_sync(0xffffffffu, (code >> 1) & 1u);
-        uint32_t bv = __ballot_sync(0xffffffffu, valid);
-        if (lane == r) {
-            mylo = bl;
-            myhi = bh;
-            mygc = __popc((bl ^ bh) & bv);
+    } else {
+        for (int r = 0; r < 32; r++) {
+            int64_t w = w0 + r;
+            uint32_t code = 0;
+            bool valid = false;
+            if (w < W) {
+                int c = grp2contig[w >> 2];
+                int L = clen[c];
+                int64_t i = (w - cwoff[c]) * 32 + lane;
+                if (i < L) {
+                    valid = true;
+                    encode((unsigned char)ascii[aoff[c] + (strand ? (L - 1 - i) : i)], true, code);
+                }
+            }
+            uint32_t bl = __ballot_sync(0xffffffffu, code & 1u);
+            uint32_t bh = __ballot_sync(0xffffffffu, (code >> 1) & 1u);
+            uint32_t bv = __ballot_sync(0xffffffffu, valid);
+            if (lane == r) {
+                mylo = bl;
+                myhi = bh;
+                mygc = __popc((bl ^ bh) & bv);
+            }
         }
     }
     if (w0 + lane < W) {
@@ -344,14 +374,14 @@ __global__ void __launch_bounds__(LS_THREADS) k_laststop_apply(uint32_t *const *
 // ------------------------------------------------------------------------------------------------
 // ORF discovery: thread per word; the previous in-frame stop comes from the table in O(1)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void emit_orf(const FindCtx &cx, const DevModel &dm, int contig, int strand, int t, bool virt,
-                                         int p_prev /* local, < 0 = none in this contig */, OrfRec *orfs,
-                                         unsigned long long *counters, uint32_t cap_orf) {
+// Builds the record of the ORF ending at stop position t if it can hold a start codon; false otherwise.
+__device__ __forceinline__ bool make_orf(const FindCtx &cx, const DevModel &dm, int contig, int strand, int t, bool virt,
+                                         int p_prev /* local, < 0 = none in this contig */, OrfRec &rec) {
     const int f = t % 3;
     const int s_hi = min(t - 3, t + 3 - dm.min_len);
     const bool open_left = p_prev < 0;
     const int s_lo = open_left ? f : p_prev + 3;
-    if (s_lo > s_hi) return;
+    if (s_lo > s_hi) return false;
     if (!open_left) {
         // cheap existence test for a start codon: look at up to four words of the admissible range
         bool any = false;
@@ -361,14 +391,11 @@ __device__ __forceinline__ void emit_orf(const FindCtx &cx, const DevModel &dm, 
             const int r = ((f - (w * 32) % 3) % 3 + 3) % 3;
             any = (m.start & frame_pattern(r) & bit_range(s_lo - 32 * w, s_hi - 32 * w)) != 0;
         }
-        if (!any && (s_hi >> 5) <= w_end) return;
+        if (!any && (s_hi >> 5) <= w_end) return false;
     }
-    const unsigned long long oid = atomicAdd(&counters[0], 1ull);
-    if (oid >= cap_orf) return;  // overflow is detected on the host from the counter
-    OrfRec rec;
     rec.contig = contig; rec.t = t; rec.s_lo = s_lo; rec.base = 0; rec.n = 0;
     rec.sf = (uint32_t)strand | (open_left ? 2u : 0u) | (virt ? 0x100u : 0u);
-    orfs[oid] = rec;
+    return true;
 }
 
 // grid.x over the 2W words of both strands, grid.y = model
@@ -377,49 +404,76 @@ __global__ void __launch_bounds__(128) k_orf_find(Planes pl, const int64_t *__re
                                                   const uint32_t *const *ls_m, OrfRec *const *orfs_m, unsigned long long *counters_m,
                                                   uint32_t cap_orf) {
     const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= 2 * pl.W) return;
     const int mi = blockIdx.y;
     const DevModel &dm = models[mi];
-    const int strand = w >= pl.W;
-    const int64_t ws = w - (strand ? pl.W : 0);
-    const int c = grp2contig[ws >> 2];
-    const int L = clen[c];
-    const int wl = (int)(ws - cwoff[c]);
-    if (L < 6 || wl * 32 > L - 3) return;  // no codon starts in this word (virtual stops sit at t <= L-3 too)
-    FindCtx cx;
-    cx.lo = pl.lo + (int64_t)strand * pl.W + cwoff[c];
-    cx.hi = pl.hi + (int64_t)strand * pl.W + cwoff[c];
-    cx.L = L; cx.stop_sel = dm.stop_sel; cx.atg_only = dm.atg_only;
+    const int lane = lane_id();
+    constexpr int NBUF = 6;
+    OrfRec buf[NBUF];
+    int nb = 0;
     OrfRec *orfs = orfs_m[mi];
     unsigned long long *counters = counters_m + (size_t)mi * 8;
-    const uint32_t *ls = ls_m[mi];
-    const uint32_t P0 = (uint32_t)(w * 32);                      // slot-space position of bit 0
-    const uint32_t Pc = (uint32_t)(((int64_t)strand * pl.W + cwoff[c]) * 32);  // ... of the contig's first letter
-    const uint32_t all = stop_mask(masks_at(cx, wl), cx.stop_sel);
-    // previous stop per frame coming from the words before this one
-    uint32_t carry[3] = {0, 0, 0};
-    if (w > 0) { carry[0] = ls[(w - 1) * 3]; carry[1] = ls[(w - 1) * 3 + 1]; carry[2] = ls[(w - 1) * 3 + 2]; }
-    auto prev_local = [&](int b) {  // previous in-frame stop of the codon at bit b, contig-local, -1 if none
-        const uint32_t P = P0 + (uint32_t)b;
-        const int f = (int)(P % 3u);
-        const uint32_t below = b ? ((1u << b) - 1u) : 0u;
-        const uint32_t m = all & frame_pattern((f - (int)(P0 % 3u) + 3) % 3) & below;
-        uint32_t pp1 = m ? P0 + (31u - (uint32_t)__clz(m)) + 1u : carry[f];
-        return pp1 > Pc ? (int)(pp1 - 1u - Pc) : -1;
+    auto push = [&](const OrfRec &r) {
+        if (nb < NBUF) buf[nb++] = r;
+        else {  // a word with more qualifying stops than the buffer holds: emit directly
+            const unsigned long long oid = atomicAdd(&counters[0], 1ull);
+            if (oid < cap_orf) orfs[oid] = r;
+        }
     };
-    uint32_t sm = all;
-    while (sm) {
-        const int b = __ffs(sm) - 1;
-        sm &= sm - 1;
-        emit_orf(cx, dm, c, strand, wl * 32 + b, false, prev_local(b), orfs, counters, cap_orf);
+    if (w < 2 * pl.W) {
+        const int strand = w >= pl.W;
+        const int64_t ws = w - (strand ? pl.W : 0);
+        const int c = grp2contig[ws >> 2];
+        const int L = clen[c];
+        const int wl = (int)(ws - cwoff[c]);
+        if (L >= 6 && wl * 32 <= L - 3) {  // the word holds codon starts (virtual stops sit at t <= L-3 too)
+            FindCtx cx;
+            cx.lo = pl.lo + (int64_t)strand * pl.W + cwoff[c];
+            cx.hi = pl.hi + (int64_t)strand * pl.W + cwoff[c];
+            cx.L = L; cx.stop_sel = dm.stop_sel; cx.atg_only = dm.atg_only;
+            const uint32_t *ls = ls_m[mi];
+            const uint32_t P0 = (uint32_t)(w * 32);                      // slot-space position of bit 0
+            const uint32_t Pc = (uint32_t)(((int64_t)strand * pl.W + cwoff[c]) * 32);  // ... of the contig's first letter
+            const uint32_t all = stop_mask(masks_at(cx, wl), cx.stop_sel);
+            // previous stop per frame coming from the words before this one
+            uint32_t carry[3] = {0, 0, 0};
+            if (w > 0) { carry[0] = ls[(w - 1) * 3]; carry[1] = ls[(w - 1) * 3 + 1]; carry[2] = ls[(w - 1) * 3 + 2]; }
+            auto prev_local = [&](int b) {  // previous in-frame stop of the codon at bit b, contig-local, -1 if none
+                const uint32_t P = P0 + (uint32_t)b;
+                const int f = (int)(P % 3u);
+                const uint32_t below = b ? ((1u << b) - 1u) : 0u;
+                const uint32_t m = all & frame_pattern((f - (int)(P0 % 3u) + 3) % 3) & below;
+                const uint32_t pp1 = m ? P0 + (31u - (uint32_t)__clz(m)) + 1u : carry[f];
+                return pp1 > Pc ? (int)(pp1 - 1u - Pc) : -1;
+            };
+            OrfRec r;
+            uint32_t sm = all;
+            while (sm) {
+                const int b = __ffs(sm) - 1;
+                sm &= sm - 1;
+                if (make_orf(cx, dm, c, strand, wl * 32 + b, false, prev_local(b), r)) push(r);
+            }
+            // right edge: in each frame the last full codon closes an open ORF unless it is a real stop
+            for (int f = 0; f < 3; f++) {
+                const int tv = L - 3 - ((L - 3 - f) % 3 + 3) % 3;  // largest t <= L-3 with t % 3 == f
+                if (tv < 0 || (tv >> 5) != wl) continue;
+                if ((all >> (tv & 31)) & 1u) continue;
+                if (make_orf(cx, dm, c, strand, tv, true, prev_local(tv & 31), r)) push(r);
+            }
+        }
     }
-    // right edge: in each frame the last full codon closes an open ORF unless it is a real stop
-    for (int f = 0; f < 3; f++) {
-        const int tv = L - 3 - ((L - 3 - f) % 3 + 3) % 3;  // largest t <= L-3 with t % 3 == f
-        if (tv < 0 || (tv >> 5) != wl) continue;
-        if ((all >> (tv & 31)) & 1u) continue;
-        emit_orf(cx, dm, c, strand, tv, true, prev_local(tv & 31), orfs, counters, cap_orf);
+    // one reservation per warp
+    uint32_t pre = (uint32_t)nb;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, pre, o);
+        if (lane >= o) pre += y;
     }
+    const uint32_t tot = __shfl_sync(0xffffffffu, pre, 31);
+    unsigned long long base = 0;
+    if (lane == 31 && tot) base = atomicAdd(&counters[0], (unsigned long long)tot);
+    base = __shfl_sync(0xffffffffu, base, 31) + pre - (uint32_t)nb;
+    for (int q = 0; q < nb; q++)
+        if (base + q < cap_orf) orfs[base + q] = buf[q];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -433,25 +487,37 @@ __device__ __forceinline__ void window_bits(const uint32_t *lo, const uint32_t *
     hb = __funnelshift_r(hi[w], hi[w + 1], sh) & mask;
 }
 
-__global__ void __launch_bounds__(128) k_orf_prep(Planes pl, const uint32_t *__restrict__ gcpre, const int64_t *__restrict__ cwoff,
-                                                  const int32_t *__restrict__ clen, const DevModel *__restrict__ models,
-                                                  OrfRec *const *orfs_m, StartRec *const *starts_m, ItemRec *const *items_m,
-                                                  uint32_t *const *hist_m, unsigned long long *counters_m, const ChainBufs *bufs_m,
-                                                  uint32_t cap_orf, uint32_t cap_starts, uint32_t cap_items) {
+// warp-wide exclusive prefix + one atomic reservation for the whole warp; returns this lane's first index
+__device__ __forceinline__ unsigned long long warp_reserve(unsigned long long *counter, uint32_t n) {
+    const int lane = lane_id();
+    uint32_t pre = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, pre, o);
+        if (lane >= o) pre += y;
+    }
+    const uint32_t tot = __shfl_sync(0xffffffffu, pre, 31);
+    unsigned long long base = 0;
+    if (lane == 31 && tot) base = atomicAdd(counter, (unsigned long long)tot);
+    return __shfl_sync(0xffffffffu, base, 31) + pre - n;
+}
+
+// prep 1: thread per ORF — number of start codons per 32-letter word of its admissible range (one WordItem per word,
+// carrying the running prefix) and in total; reserves the ORF's slice of the start array.
+__global__ void __launch_bounds__(128) k_orf_count(Planes pl, const int64_t *__restrict__ cwoff, const int32_t *__restrict__ clen,
+                                                   const DevModel *__restrict__ models, OrfRec *const *orfs_m, WordItem *const *witems_m,
+                                                   unsigned long long *counters_m, const ChainBufs *bufs_m, uint32_t cap_orf,
+                                                   uint32_t cap_starts, uint32_t cap_witems) {
     const int mi = blockIdx.y;
     const DevModel &dm = models[mi];
     unsigned long long *counters = counters_m + (size_t)mi * 8;
     unsigned long long n_orfs = counters[0];
     if (n_orfs > cap_orf) n_orfs = cap_orf;
     OrfRec *orfs = orfs_m[mi];
-    StartRec *starts = starts_m[mi];
-    ItemRec *items = items_m[mi];
-    uint32_t *hist = hist_m[mi];
+    WordItem *witems = witems_m[mi];
     int32_t *gptr = bufs_m[mi].gptr;
-    const int kc = dm.kc;
     const int lane = lane_id();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    // whole warps iterate together so that the two reservations below cost one atomic per warp
     for (int64_t o0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~31LL; o0 < (int64_t)n_orfs; o0 += stride) {
         const int64_t oi = o0 + lane;
         const bool has = oi < (int64_t)n_orfs;
@@ -461,44 +527,115 @@ __global__ void __launch_bounds__(128) k_orf_prep(Planes pl, const uint32_t *__r
             rec = orfs[oi];
             gptr[oi] = GPTR_UNSET;
         }
-        const int c = rec.contig, t = rec.t, strand = rec.sf & 1;
+        const int t = rec.t, strand = rec.sf & 1;
         const bool open_left = has && (rec.sf & 2u) != 0;
-        const int L = has ? clen[c] : 0;
-        const int64_t w0 = has ? cwoff[c] : 0;
+        const int64_t w0 = has ? cwoff[rec.contig] : 0;
+        FindCtx cx;
+        cx.lo = pl.lo + (int64_t)strand * pl.W + w0;
+        cx.hi = pl.hi + (int64_t)strand * pl.W + w0;
+        cx.L = has ? clen[rec.contig] : 0; cx.stop_sel = dm.stop_sel; cx.atg_only = dm.atg_only;
+        const int f = t % 3;
+        const int s_lo = rec.s_lo, s_hi = has ? min(t - 3, t + 3 - dm.min_len) : 0;
+        const uint32_t nwords = has ? (uint32_t)((s_hi >> 5) - (s_lo >> 5) + 1) : 0u;
+        const unsigned long long wbase = warp_reserve(&counters[3], nwords);
+        const bool wok = has && wbase + nwords <= cap_witems;
+        uint32_t n = open_left ? 1u : 0u;
+        if (wok)
+            for (uint32_t j = 0; j < nwords; j++) {
+                const int w = (s_lo >> 5) + (int)j;
+                const CodonMasks m = masks_at(cx, w);
+                const int r = ((f - (w * 32) % 3) % 3 + 3) % 3;
+                WordItem wi;
+                wi.orf = (uint32_t)oi; wi.pre = n; wi.j = j;
+                witems[wbase + j] = wi;
+                n += __popc(m.start & frame_pattern(r) & bit_range(s_lo - 32 * w, s_hi - 32 * w));
+            }
+        if (!wok) n = 0;
+        const unsigned long long base = warp_reserve(&counters[1], n);
+        if (has) {
+            const bool ok = n && base + n <= cap_starts;
+            orfs[oi].base = (uint32_t)base;
+            orfs[oi].n = ok ? n : 0u;
+        }
+    }
+}
+
+// prep 2: thread per (ORF, word) — the start records of that word: position, GC bin, section pair
+__global__ void __launch_bounds__(256) k_orf_starts(Planes pl, const uint32_t *__restrict__ gcpre, const int64_t *__restrict__ cwoff,
+                                                    const int32_t *__restrict__ clen, const DevModel *__restrict__ models,
+                                                    const OrfRec *const *orfs_m, const WordItem *const *witems_m, StartRec *const *starts_m,
+                                                    const unsigned long long *counters_m, uint32_t cap_witems) {
+    const int mi = blockIdx.y;
+    const DevModel &dm = models[mi];
+    unsigned long long nw = counters_m[(size_t)mi * 8 + 3];
+    if (nw > cap_witems) nw = cap_witems;
+    const OrfRec *orfs = orfs_m[mi];
+    const WordItem *witems = witems_m[mi];
+    StartRec *starts = starts_m[mi];
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < (int64_t)nw; k += (int64_t)gridDim.x * blockDim.x) {
+        const WordItem wi = witems[k];
+        const OrfRec rec = orfs[wi.orf];
+        if (!rec.n) continue;
+        const int c = rec.contig, t = rec.t, strand = rec.sf & 1;
+        const int L = clen[c];
+        const int64_t w0 = cwoff[c];
         FindCtx cx;
         cx.lo = pl.lo + (int64_t)strand * pl.W + w0;
         cx.hi = pl.hi + (int64_t)strand * pl.W + w0;
         cx.L = L; cx.stop_sel = dm.stop_sel; cx.atg_only = dm.atg_only;
         const int f = t % 3;
-        const int s_lo = rec.s_lo, s_hi = has ? min(t - 3, t + 3 - dm.min_len) : 0;
-        // pass 1: count
-        uint32_t n = open_left ? 1u : 0u;
-        if (has)
-            for (int w = s_lo >> 5; w <= (s_hi >> 5); w++) {
-                const CodonMasks m = masks_at(cx, w);
-                const int r = ((f - (w * 32) % 3) % 3 + 3) % 3;
-                n += __popc(m.start & frame_pattern(r) & bit_range(s_lo - 32 * w, s_hi - 32 * w));
-            }
-        // warp-aggregated reservation of the start records
-        uint32_t pre = n;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, pre, o);
-            if (lane >= o) pre += y;
+        const int s_lo = rec.s_lo, s_hi = min(t - 3, t + 3 - dm.min_len);
+        const int w = (s_lo >> 5) + (int)wi.j;
+        uint32_t kk = rec.base + wi.pre;
+        auto put = [&](int s, bool virt) {
+            const int len = t + 3 - s;
+            const int a = strand ? (L - 1 - (t + 2)) : s, b = strand ? (L - 1 - s) : (t + 2);
+            const int gcn = gc_count_fwd(pl.lo, pl.hi, gcpre, w0, a, b);
+            const int gc = (200 * gcn + len) / (2 * len);
+            StartRec sr;
+            sr.sraw = (uint32_t)s | (virt ? 0x80000000u : 0u);
+            sr.orf = wi.orf;
+            sr.pg = (uint32_t)dm.pair[gc] | ((uint32_t)gc << 16);
+            sr.link = -1;
+            starts[kk++] = sr;
+        };
+        if (wi.j == 0 && (rec.sf & 2u)) {   // the virtual start at the contig edge comes first
+            kk = rec.base;
+            put(f, true);
         }
-        unsigned long long wbase = 0;
-        const uint32_t wtot = __shfl_sync(0xffffffffu, pre, 31);
-        if (lane == 31 && wtot) wbase = atomicAdd(&counters[1], (unsigned long long)wtot);
-        wbase = __shfl_sync(0xffffffffu, wbase, 31);
-        const unsigned long long base = wbase + pre - n;
-        const bool ok = has && n && base + n <= cap_starts;
-        if (ok) {
-            orfs[oi].base = (uint32_t)base;
-            orfs[oi].n = n;
+        const CodonMasks m = masks_at(cx, w);
+        const int r = ((f - (w * 32) % 3) % 3 + 3) % 3;
+        uint32_t mm = m.start & frame_pattern(r) & bit_range(s_lo - 32 * w, s_hi - 32 * w);
+        while (mm) {
+            const int b = __ffs(mm) - 1;
+            mm &= mm - 1;
+            put(w * 32 + b, false);
         }
-        // pass 2: starts in ascending position (virtual start first).  Starts of the same section pair are chained
-        // (StartRec.link = previous start of that pair) so that the walk can hop from one to the next.
-        uint32_t k = (uint32_t)base;
+    }
+}
+
+// prep 3: thread per ORF — chains the starts of equal section pair (ascending position) and emits one walk item per chain
+__global__ void __launch_bounds__(128) k_orf_link(const DevModel *__restrict__ models, const OrfRec *const *orfs_m,
+                                                  StartRec *const *starts_m, ItemRec *const *items_m, uint32_t *const *hist_m,
+                                                  unsigned long long *counters_m, uint32_t cap_orf, uint32_t cap_items) {
+    const int mi = blockIdx.y;
+    const DevModel &dm = models[mi];
+    unsigned long long *counters = counters_m + (size_t)mi * 8;
+    unsigned long long n_orfs = counters[0];
+    if (n_orfs > cap_orf) n_orfs = cap_orf;
+    const OrfRec *orfs = orfs_m[mi];
+    StartRec *starts = starts_m[mi];
+    ItemRec *items = items_m[mi];
+    uint32_t *hist = hist_m[mi];
+    const int kc = dm.kc;
+    const int lane = lane_id();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t o0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~31LL; o0 < (int64_t)n_orfs; o0 += stride) {
+        const int64_t oi = o0 + lane;
+        OrfRec rec;
+        rec.n = 0; rec.t = 0; rec.sf = 0; rec.base = 0;
+        if (oi < (int64_t)n_orfs) rec = orfs[oi];
+        const int t = rec.t, strand = rec.sf & 1;
         constexpr int NSLOT = 6, NPEND = 10;
         int sl_pair[NSLOT], sl_lo[NSLOT], sl_last[NSLOT];
 #pragma unroll
@@ -508,11 +645,10 @@ __global__ void __launch_bounds__(128) k_orf_prep(Planes pl, const uint32_t *__r
         int npend = 0;
         auto flush_slot = [&](int q) {
             const int ext = t - sl_lo[q];
-            const int cls = WALK_CLASSES - 1 - min(ext >> 5, WALK_CLASSES - 1);
             ItemRec it;
             it.orf = (uint32_t)oi;
             it.lo_pos = sl_lo[q];
-            it.key = (uint32_t)(sl_pair[q] * WALK_CLASSES + cls);
+            it.key = (uint32_t)(sl_pair[q] * WALK_CLASSES + (WALK_CLASSES - 1 - min(ext >> 5, WALK_CLASSES - 1)));
             it.last = sl_last[q];
             if (npend < NPEND) pend[npend++] = it;
             else {  // very many distinct GC bins among the starts of one ORF: emit directly
@@ -523,66 +659,33 @@ __global__ void __launch_bounds__(128) k_orf_prep(Planes pl, const uint32_t *__r
                 }
             }
         };
-        auto add_start = [&](int s, bool virt) {
-            const int len = t + 3 - s;
-            const int a = strand ? (L - 1 - (t + 2)) : s, b = strand ? (L - 1 - s) : (t + 2);
-            const int gcn = gc_count_fwd(pl.lo, pl.hi, gcpre, w0, a, b);
-            const int gc = (200 * gcn + len) / (2 * len);
-            const int pair = dm.pair[gc];
-            const int j = (int)(k - (uint32_t)base);
-            StartRec sr;
-            sr.sraw = (uint32_t)s | (virt ? 0x80000000u : 0u);
-            sr.orf = (uint32_t)oi;
-            sr.pg = (uint32_t)pair | ((uint32_t)gc << 16);
-            sr.link = -1;
-            const int fullstart = s + ((virt && strand == 0) ? 0 : 3) + kc;
-            if (fullstart <= t - 1) {  // has a full-order region: belongs to a walk
-                int q = -1;
+        StartRec *st = starts + rec.base;
+        for (int j = 0; j < (int)rec.n; j++) {
+            const uint32_t sraw = st[j].sraw;
+            const int pair = (int)(st[j].pg & 0xffffu);
+            const int fullstart = (int)(sraw & 0x7fffffffu) + (((sraw >> 31) && strand == 0) ? 0 : 3) + kc;
+            if (fullstart > t - 1) continue;  // no full-order region: not part of any walk
+            int q = -1;
 #pragma unroll
-                for (int z = 0; z < NSLOT; z++)
-                    if (sl_pair[z] == pair) q = z;
-                if (q < 0) {
-                    if (nslot < NSLOT) q = nslot++;
-                    else {           // more distinct pairs in flight than slots: retire the oldest slot into its own walk
-                        flush_slot(0);
+            for (int z = 0; z < NSLOT; z++)
+                if (sl_pair[z] == pair) q = z;
+            if (q < 0) {
+                if (nslot < NSLOT) q = nslot++;
+                else {           // more distinct pairs in flight than slots: retire the oldest slot into its own walk
+                    flush_slot(0);
 #pragma unroll
-                        for (int z = 0; z < NSLOT - 1; z++) { sl_pair[z] = sl_pair[z + 1]; sl_lo[z] = sl_lo[z + 1]; sl_last[z] = sl_last[z + 1]; }
-                        q = NSLOT - 1;
-                    }
-                    sl_pair[q] = pair;
-                    sl_lo[q] = fullstart;
-                    sl_last[q] = -1;
+                    for (int z = 0; z < NSLOT - 1; z++) { sl_pair[z] = sl_pair[z + 1]; sl_lo[z] = sl_lo[z + 1]; sl_last[z] = sl_last[z + 1]; }
+                    q = NSLOT - 1;
                 }
-                sr.link = sl_last[q];
-                sl_last[q] = j;
+                sl_pair[q] = pair;
+                sl_lo[q] = fullstart;
+                sl_last[q] = -1;
             }
-            starts[k++] = sr;
-        };
-        if (ok) {
-            if (open_left) add_start(f, true);
-            for (int w = s_lo >> 5; w <= (s_hi >> 5); w++) {
-                const CodonMasks m = masks_at(cx, w);
-                const int r = ((f - (w * 32) % 3) % 3 + 3) % 3;
-                uint32_t mm = m.start & frame_pattern(r) & bit_range(s_lo - 32 * w, s_hi - 32 * w);
-                while (mm) {
-                    const int b = __ffs(mm) - 1;
-                    mm &= mm - 1;
-                    add_start(w * 32 + b, false);
-                }
-            }
-            for (int q = 0; q < nslot; q++) flush_slot(q);
+            if (sl_last[q] >= 0) st[j].link = sl_last[q];
+            sl_last[q] = j;
         }
-        // warp-aggregated reservation of the walk items
-        uint32_t ipre = (uint32_t)npend;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, ipre, o);
-            if (lane >= o) ipre += y;
-        }
-        unsigned long long ibase = 0;
-        const uint32_t itot = __shfl_sync(0xffffffffu, ipre, 31);
-        if (lane == 31 && itot) ibase = atomicAdd(&counters[2], (unsigned long long)itot);
-        ibase = __shfl_sync(0xffffffffu, ibase, 31) + ipre - (uint32_t)npend;
+        for (int q = 0; q < nslot; q++) flush_slot(q);
+        const unsigned long long ibase = warp_reserve(&counters[2], (uint32_t)npend);
         for (int q = 0; q < npend; q++)
             if (ibase + q < cap_items) {
                 items[ibase + q] = pend[q];
@@ -945,11 +1048,13 @@ struct ChainState {
     int gp_next;     // round-robin slot of the pointer cache
 };
 
-__device__ __forceinline__ void chain_append(const ChainBufs &B, ChainRing &R, uint32_t cs, ChainState &S, int gi, double cum,
-                                             int right, int left, int ls) {
-    // all lanes hold identical arguments; lane 0 writes
+// Appends one predecessor state.  `owner` holds the values; cum is broadcast so that every lane tracks the running
+// prefix maximum in registers.
+__device__ __forceinline__ void chain_append(const ChainBufs &B, ChainRing &R, uint32_t cs, ChainState &S, int owner, int gi,
+                                             double my_cum, int right, int left, int ls) {
+    const double cum = __shfl_sync(0xffffffffu, my_cum, owner);
     if (S.head == 0 || cum > S.pm_val) { S.pm_val = cum; S.pm_arg = gi; }
-    if (lane_id() == 0) {
+    if (lane_id() == owner) {
         const int k = S.head, r = k & (CHAIN_RING - 1);
         R.right[r] = right; R.left[r] = left; R.ls[r] = ls; R.idx[r] = gi; R.cum[r] = cum; R.pmax[r] = S.pm_val; R.parg[r] = S.pm_arg;
         B.av_right[cs + k] = right; B.av_left[cs + k] = left; B.av_ls[cs + k] = ls; B.av_idx[cs + k] = gi;
@@ -1018,53 +1123,62 @@ __device__ __forceinline__ void gp_store(const ChainBufs &B, ChainRing &R, Chain
     __syncwarp();
 }
 
-// Processes the candidates held one per lane (valid lanes: `pending`) in chain order.
+// Processes the candidates held one per lane (valid lanes: `pending`) in chain order.  All candidates of a bucket end
+// within the same 128 positions, so (right & 127) orders the groups; warp-wide minima are single redux instructions.
 __device__ __forceinline__ void chain_bucket(const ChainBufs &B, ChainRing &R, uint32_t cs, ChainState &S, uint32_t bs, const Cand &me,
                                              bool pending) {
     const int lane = lane_id();
+    const uint32_t rr = (uint32_t)me.right & 127u;
     while (true) {
-        const int rmin = warp_min_i(pending ? me.right : 0x7fffffff);
-        if (rmin == 0x7fffffff) break;
-        const bool ing = pending && me.right == rmin;
+        const uint32_t rmin = __reduce_min_sync(0xffffffffu, pending ? rr : 0xffffffffu);
+        if (rmin == 0xffffffffu) break;
+        const bool ing = pending && rr == rmin;
         pending = pending && !ing;
         double b_non = 0, b_ov = 0;
         int bp_non = -1, bp_ov = -1;
         if (ing) chain_eval_lane(B, R, cs, S, me.left, me.len, me.strand, b_non, bp_non, b_ov, bp_ov);
-        double cumg = me.total + (bp_ov >= 0 ? b_ov : b_non);
-        int prevg = bp_ov >= 0 ? bp_ov : bp_non;
+        const double cumg = me.total + (bp_ov >= 0 ? b_ov : b_non);
         if (ing) {
             B.cum[bs + lane] = cumg;
-            B.prev[bs + lane] = prevg;
+            B.prev[bs + lane] = bp_ov >= 0 ? bp_ov : bp_non;
         }
-        // reverse-strand members: shared pointer of their ORF, then append (ascending left)
+        // reverse-strand members: shared pointer of their ORF, then append (ascending left; a real start before a
+        // virtual one at the same position)
         uint32_t rev = __ballot_sync(0xffffffffu, ing && me.strand < 0);
+        const uint32_t dir = __ballot_sync(0xffffffffu, ing && me.strand > 0);
         while (rev) {
-            // smallest left first
-            const int lmin = warp_min_i(((rev >> lane) & 1u) ? me.left : 0x7fffffff);
-            const int o = __ffs(__ballot_sync(0xffffffffu, ((rev >> lane) & 1u) && me.left == lmin)) - 1;
+            int o = __ffs(rev) - 1;
+            if (rev & (rev - 1)) {
+                const bool in = (rev >> lane) & 1u;
+                const uint32_t key = in ? (((uint32_t)me.left << 1) | ((me.flags >> 1) & 1u)) : 0xffffffffu;
+                const uint32_t kmin = __reduce_min_sync(0xffffffffu, key);
+                o = __ffs(__ballot_sync(0xffffffffu, in && key == kmin)) - 1;
+            }
             rev &= ~(1u << o);
             const uint32_t gorf = __shfl_sync(0xffffffffu, me.orf, o);
             const int gfl = __shfl_sync(0xffffffffu, (int)me.flags, o);
-            const int o_non = __shfl_sync(0xffffffffu, bp_non, o), o_ov = __shfl_sync(0xffffffffu, bp_ov, o);
             int gp = gp_lookup(B, R, gorf, gfl);
-            if (gp == GPTR_UNSET) gp = o_non;
-            if (o_ov >= 0) gp = o_ov;
+            // the owner resolves the pointer, everybody learns it
+            if (gp == GPTR_UNSET) gp = bp_non;
+            if (bp_ov >= 0) gp = bp_ov;
+            gp = __shfl_sync(0xffffffffu, gp, o);
             gp_store(B, R, S, gorf, gp);
-            chain_append(B, R, cs, S, (int)(bs + o), __shfl_sync(0xffffffffu, cumg, o), rmin, lmin,
-                         __shfl_sync(0xffffffffu, me.len, o) * 2 + 1);
+            chain_append(B, R, cs, S, o, (int)(bs + o), cumg, me.right, me.left, me.len * 2 + 1);
         }
         // direct-strand members: the stop keeps one state, its best start (ties: smallest left)
-        const bool dirm = ing && me.strand > 0;
-        if (__any_sync(0xffffffffu, dirm)) {
-            double bc = dirm ? cumg : -1e300;
-            int bl = dirm ? me.left : 0x7fffffff, bo = lane;
-#pragma unroll
-            for (int o = 16; o; o >>= 1) {
-                const double oc = __shfl_xor_sync(0xffffffffu, bc, o);
-                const int ol = __shfl_xor_sync(0xffffffffu, bl, o), oo = __shfl_xor_sync(0xffffffffu, bo, o);
-                if (oc > bc || (oc == bc && ol < bl)) { bc = oc; bl = ol; bo = oo; }
+        if (dir) {
+            int o = __ffs(dir) - 1;
+            if (dir & (dir - 1)) {
+                const bool in = (dir >> lane) & 1u;
+                const unsigned long long bits = (unsigned long long)__double_as_longlong(cumg);  // cumg > 0: bit order = value order
+                const uint32_t hi = __reduce_max_sync(0xffffffffu, in ? (uint32_t)(bits >> 32) : 0u);
+                const bool in2 = in && (uint32_t)(bits >> 32) == hi;
+                const uint32_t lo = __reduce_max_sync(0xffffffffu, in2 ? (uint32_t)bits : 0u);
+                const bool in3 = in2 && (uint32_t)bits == lo;
+                const uint32_t lmin = __reduce_min_sync(0xffffffffu, in3 ? (uint32_t)me.left : 0xffffffffu);
+                o = __ffs(__ballot_sync(0xffffffffu, in3 && (uint32_t)me.left == lmin)) - 1;
             }
-            chain_append(B, R, cs, S, (int)(bs + bo), bc, rmin, bl, __shfl_sync(0xffffffffu, me.len, bo) * 2);
+            chain_append(B, R, cs, S, o, (int)(bs + o), cumg, me.right, me.left, me.len * 2);
         }
         S.na = S.head;
         __syncwarp();
@@ -1167,8 +1281,7 @@ __global__ void __launch_bounds__(128) k_chain(const ChainBufs *bufs_m, const in
                                 if (gp == GPTR_UNSET) gp = o_non;
                                 if (o_ov >= 0) gp = o_ov;
                                 gp_store(B, R, S, gorf, gp);
-                                chain_append(B, R, cs, S, (int)(k0 + o), __shfl_sync(0xffffffffu, cumg, o), r,
-                                             __shfl_sync(0xffffffffu, g.left, o), __shfl_sync(0xffffffffu, g.len, o) * 2 + 1);
+                                chain_append(B, R, cs, S, o, (int)(k0 + o), cumg, g.right, g.left, g.len * 2 + 1);
                             }
                             const bool dirm = ing && g.strand > 0;
                             double c2 = dirm ? cumg : -1e300;
@@ -1183,7 +1296,7 @@ __global__ void __launch_bounds__(128) k_chain(const ChainBufs *bufs_m, const in
                                 bc = c2; bleft = l2; bidx = (int)(k0 + o2); blen = __shfl_sync(0xffffffffu, g.len, o2);
                             }
                         }
-                        if (bidx >= 0 && bc > -1e299) chain_append(B, R, cs, S, bidx, bc, r, bleft, blen * 2);
+                        if (bidx >= 0 && bc > -1e299) chain_append(B, R, cs, S, 0, bidx, bc, r, bleft, blen * 2);
                         S.na = S.head;
                         __syncwarp();
                     }
@@ -1339,13 +1452,16 @@ void launch_orf_find(Planes pl, const int64_t *cwoff, const int32_t *clen, const
     k_orf_find<<<grid, 128, 0, st>>>(pl, cwoff, clen, grp2contig, models, ls_m, orfs_m, counters_m, cap_orf);
 }
 
-void launch_orf_prep(Planes pl, const uint32_t *gcpre, const int64_t *cwoff, const int32_t *clen, const DevModel *models, int n_models,
-                     OrfRec *const *orfs_m, StartRec *const *starts_m, ItemRec *const *items_m, uint32_t *const *hist_m,
-                     unsigned long long *counters_m, const ChainBufs *bufs_m, uint32_t cap_orf, uint32_t cap_starts, uint32_t cap_items,
-                     int n_sm, cudaStream_t st) {
+int launch_orf_prep(Planes pl, const uint32_t *gcpre, const int64_t *cwoff, const int32_t *clen, const DevModel *models, int n_models,
+                    OrfRec *const *orfs_m, WordItem *const *witems_m, StartRec *const *starts_m, ItemRec *const *items_m,
+                    uint32_t *const *hist_m, unsigned long long *counters_m, const ChainBufs *bufs_m, uint32_t cap_orf,
+                    uint32_t cap_starts, uint32_t cap_items, uint32_t cap_witems, int n_sm, cudaStream_t st) {
     dim3 grid(n_sm * 16, n_models);
-    k_orf_prep<<<grid, 128, 0, st>>>(pl, gcpre, cwoff, clen, models, orfs_m, starts_m, items_m, hist_m, counters_m, bufs_m, cap_orf,
-                                     cap_starts, cap_items);
+    k_orf_count<<<grid, 128, 0, st>>>(pl, cwoff, clen, models, orfs_m, witems_m, counters_m, bufs_m, cap_orf, cap_starts, cap_witems);
+    dim3 grid2(n_sm * 8, n_models);
+    k_orf_starts<<<grid2, 256, 0, st>>>(pl, gcpre, cwoff, clen, models, orfs_m, witems_m, starts_m, counters_m, cap_witems);
+    k_orf_link<<<grid, 128, 0, st>>>(models, orfs_m, starts_m, items_m, hist_m, counters_m, cap_orf, cap_items);
+    return 3;
 }
 
 int launch_item_sort(const ItemRec *const *items_m, ItemRec *const *sorted_m, uint32_t *const *hist_m, uint32_t *const *item_off_m,
