@@ -59,7 +59,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
@@ -171,7 +171,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--total-bp", type=int, default=int(os.environ.get("MGCOD_BENCH_BP", 1_000_000_000)),
                     help="bp per GPU per step (default: 1 Gbp, BASELINE.json config 5)")
-    ap.add_argument("--cpu-sample-bp", type=int, default=16_000_000)
+    ap.add_argument("--cpu-sample-bp", type=int, default=32_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -257,7 +257,7 @@ def main():
             launches += st["kernel_launches"]
             n_genes = st["n_genes"]
             d2h_bytes = n_genes * 32 + engine.n_contigs * 8 * engine.n_models
-            counts = {k: st[k] for k in ("n_orfs", "n_starts", "n_candidates", "n_genes")}
+            counts = {k: st[k] for k in ("n_orfs", "n_starts", "n_walks", "n_candidates", "n_genes")}
             del res
         barrier()
         dt_res = time.perf_counter() - t0
@@ -282,10 +282,11 @@ def main():
 
         if rank == 0:
             peak, peak_src = _peaks()
-            # dominant kernel = k_orf_score; algorithmic bytes of one launch (all 4 models): both strands' planes
-            # (0.5 B/nt, read once per model) + ORF records + start list + surviving candidates + bucket histogram
+            # dominant kernel = k_walk (phase "orf_score").  Algorithmic bytes of one launch (all 4 models): both strands'
+            # planes once per model (0.5 B/nt), per walk its item + ORF record (16 + 24 B), per start its record read and its
+            # four sums written (16 + 32 B).  The section-pair tables (104 KB each) live in shared memory and are not counted.
             score_ms = phase["orf_score"] / args.steps
-            alg_bytes = (4 * 0.5 * total_bp + counts["n_orfs"] * 20 + counts["n_starts"] * 4 + counts["n_candidates"] * 36)
+            alg_bytes = 4 * 0.5 * total_bp + counts["n_walks"] * 40 + counts["n_starts"] * 48
             achieved = alg_bytes / (score_ms * 1e-3) / 1e9 if score_ms > 0 else 0.0
             out = {
                 "metric": METRIC, "value": all_units * args.steps / dt_res, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -295,7 +296,7 @@ def main():
                         "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": 1e3 * dt_e2e / args.steps},
                 "gpu_launches": int(launches),
                 "clocks": clocks,
-                "roofline": {"kernel": "k_orf_score", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "roofline": {"kernel": "k_walk", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                              "kernel_ms_per_launch": score_ms, "algorithmic_bytes_per_launch": alg_bytes},
                 "phases_ms_per_step": {k: v / args.steps for k, v in phase.items()},

@@ -51,7 +51,7 @@ typedef struct {
 /* Device-side timings of the last decode, milliseconds (CUDA events on the engine's stream). */
 typedef struct {
     float h2d, pack, orf_find, orf_prep, orf_score /* walk */, orf_final, order, chain, aggregate, d2h, total;
-    int64_t n_orfs, n_starts, n_candidates, n_genes; /* summed over models */
+    int64_t n_orfs, n_starts, n_walks, n_candidates, n_genes; /* summed over models */
     int32_t kernel_launches;
 } mgc_stats;
 
@@ -112,6 +112,15 @@ int mgc_window_counts(const int64_t *contig_len, const int32_t *stride, int32_t 
                       int32_t consecutive, int short_contigs, int64_t *win_offsets);
 int mgc_window_labels(mgc_engine *e, const int32_t *stride, int32_t window, int32_t consecutive,
                       int short_contigs, const int64_t *win_offsets, int32_t *labels, int64_t *cents);
+
+/*
+ * Label smoothing on the device (Pipeline.find_best_sequence_of_labels, bin/pipeline.py:1064-1168) for every contig of
+ * a label array laid out by win_offsets.  Contigs with a single distinct label are copied.  noise_labels: bit l set =
+ * label l is treated as noise (the host passes all but the two most frequent labels of the whole input,
+ * pipeline.py:1084-1086).  status[c]: 0 ok, 1 = the reference raises IndexError on this input.
+ */
+int mgc_merge_labels(mgc_engine *e, const int32_t *labels, const int64_t *win_offsets, int32_t n_contigs,
+                     int32_t consecutive, uint32_t noise_labels, int32_t *merged, int32_t *status);
 
 /* ---- testing hook: the pruned candidate list (total > 0) of the last decode, in chain order ----
  * Mirrors what `gmhmmp2 --debug 1` prints per start point; used by the parity tests only. */

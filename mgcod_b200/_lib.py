@@ -31,7 +31,7 @@ class Candidate(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("h2d", "pack", "orf_find", "orf_prep", "orf_score", "orf_final", "order", "chain", "aggregate", "d2h", "total")] + \
-               [(n, C.c_int64) for n in ("n_orfs", "n_starts", "n_candidates", "n_genes")] + [("kernel_launches", C.c_int32)]
+               [(n, C.c_int64) for n in ("n_orfs", "n_starts", "n_walks", "n_candidates", "n_genes")] + [("kernel_launches", C.c_int32)]
 
 
 #: every symbol include/mgcod_b200.h declares
@@ -39,7 +39,7 @@ EXPORTS = (
     "mgc_version", "mgc_last_error", "mgc_device_count", "mgc_model_load", "mgc_model_free", "mgc_model_info",
     "mgc_engine_create", "mgc_engine_destroy", "mgc_decode_batch", "mgc_upload_batch", "mgc_decode_resident",
     "mgc_engine_stats", "mgc_result_num_genes", "mgc_result_genes", "mgc_result_contig_totals",
-    "mgc_result_model_cents", "mgc_result_free", "mgc_result_create", "mgc_window_counts", "mgc_window_labels", "mgc_debug_candidates",
+    "mgc_result_model_cents", "mgc_result_free", "mgc_result_create", "mgc_window_counts", "mgc_window_labels", "mgc_merge_labels", "mgc_debug_candidates",
     "mgc_write_gff", "mgc_synth_lengths", "mgc_synth_contigs",
 )
 
@@ -87,6 +87,7 @@ def lib():
     L.mgc_result_create.argtypes = [C.c_int, i32, C.POINTER(vp), C.POINTER(i64), C.POINTER(vp), C.POINTER(vp)]
     L.mgc_window_counts.argtypes = [C.POINTER(i64), C.POINTER(i32), i32, i32, i32, C.c_int, C.POINTER(i64)]
     L.mgc_window_labels.argtypes = [vp, C.POINTER(i32), i32, i32, C.c_int, C.POINTER(i64), C.POINTER(i32), C.POINTER(i64)]
+    L.mgc_merge_labels.argtypes = [vp, C.POINTER(i32), C.POINTER(i64), i32, i32, C.c_uint32, C.POINTER(i32), C.POINTER(i32)]
     L.mgc_debug_candidates.argtypes = [vp, C.c_int, C.POINTER(Candidate), i64]
     L.mgc_debug_candidates.restype = i64
     L.mgc_write_gff.argtypes = [vp, C.c_int, C.POINTER(cp), C.POINTER(i64), i32, cp, cp, C.c_int, cp, cp]

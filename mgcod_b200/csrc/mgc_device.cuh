@@ -27,6 +27,8 @@ struct DevModel {
     const double *lc_full, *ln_full, *lc_ramp, *ln_ramp;
     const SectionScalars *sc;
     const Quad *quad;   // [npair][3][4^(kc+1)], plane-major k-mer index
+    const double2 *wtab; // [npair][wtab_n16]: the walk's table image (coding part 2x replicated, non-coding part 8x replicated)
+    int wtab_n16;
     const Quad *rquad;  // [npair][kr][4^kr]: order ramp (window starts on a codon boundary, phase 0)
     int npair;
     int map[2][101];

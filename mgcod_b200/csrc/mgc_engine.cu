@@ -115,7 +115,7 @@ struct DevBuf {
 };
 
 struct PerModel {
-    DevBuf lc_full, ln_full, lc_ramp, ln_ramp, sc, quad, rquad;
+    DevBuf lc_full, ln_full, lc_ramp, ln_ramp, sc, quad, rquad, wtab;
     DevBuf ls, ls_tile, orfs, starts, witems, items, items_sorted, hist, item_off, unit_off, sums;
     DevBuf surv, sorted, bcount, cum, prev, gptr;
     DevBuf av_right, av_left, av_ls, av_idx, av_cum, av_pmax, av_parg, chain, gene_count, gene_off, contig_total, genes;
@@ -145,7 +145,7 @@ struct mgc_engine {
     uint32_t cap_witems = 0;
     DevBuf t_ls, t_ls_tile, t_items, t_items_sorted, t_hist, t_item_off, t_unit_off, t_sums, unit_totals, next_unit;
     uint32_t cap_items = 0;
-    int max_cod_order = 0;
+    int max_cod_order = 0, max_non_order = 0;
     DevBuf counters;     // [M][8] unsigned long long: 0 orfs, 1 starts
     DevBuf surv_counters;  // [M]
     DevBuf work_counters;  // [M] int
@@ -232,6 +232,33 @@ void upload_models(mgc_engine *e) {
                 }
         up(p.quad, q.data(), q.size() * sizeof(Quad));
         d.quad = p.quad.as<Quad>();
+        // image of the walk kernel's shared-memory table (see k_walk): per pair, coding {B, A} entries with rows of four
+        // entries stored twice (bank halves for even / odd lanes), then non-coding {B, A} entries stored eight times
+        {
+            const size_t n16 = 3 * nfull * 2 + nnon * 8;
+            std::vector<double> img(pairs.size() * n16 * 2, 0.0);
+            for (size_t pi = 0; pi < pairs.size(); pi++) {
+                double *base = img.data() + pi * n16 * 2;
+                for (size_t ent = 0; ent < 3 * nfull; ent++) {
+                    const Quad &e4 = q[pi * 3 * nfull + ent];
+                    for (int rep = 0; rep < 2; rep++) {
+                        const size_t o16 = ((ent & ~(size_t)3) << 1) | (ent & 3) | ((size_t)rep << 2);
+                        base[o16 * 2] = e4.cB;
+                        base[o16 * 2 + 1] = e4.cA;
+                    }
+                }
+                double *nb = base + 3 * nfull * 2 * 2;
+                for (size_t idn = 0; idn < nnon; idn++)
+                    for (int rep = 0; rep < 8; rep++) {
+                        const size_t o16 = (idn << 3) | (size_t)rep;
+                        nb[o16 * 2] = pairs[pi].first >= 0 ? m.ln_full[(size_t)pairs[pi].first * nnon + idn] : 0.0;
+                        nb[o16 * 2 + 1] = pairs[pi].second >= 0 ? m.ln_full[(size_t)pairs[pi].second * nnon + idn] : 0.0;
+                    }
+            }
+            up(p.wtab, img.data(), img.size() * sizeof(double));
+            d.wtab = p.wtab.as<double2>();
+            d.wtab_n16 = (int)n16;
+        }
         // order ramp: order j < kc, window of j+1 letters starting on a codon boundary (phase 0);
         // non-coding order is min(j, kn): its context is the last min(j,kn)+1 letters of the window
         const int kr = d.kr, knr = d.knr;
@@ -255,6 +282,7 @@ void upload_models(mgc_engine *e) {
         up(p.rquad, rq.data(), std::max<size_t>(rq.size(), 1) * sizeof(Quad));
         d.rquad = p.rquad.as<Quad>();
         e->max_cod_order = std::max(e->max_cod_order, kc);
+        e->max_non_order = std::max(e->max_non_order, kn);
     }
     e->d_models.ensure(sizeof(DevModel) * e->n_models);
     CUDA_TRY(cudaMemcpy(e->d_models.p, dm.data(), sizeof(DevModel) * e->n_models, cudaMemcpyHostToDevice));
@@ -456,7 +484,8 @@ mgc_result *do_decode(mgc_engine *e) {
     launches += launch_laststop(pl, e->cwoff.as<int64_t>(), e->clen.as<int32_t>(), e->grp2contig.as<int32_t>(),
                                 e->d_models.as<DevModel>(), M, e->t_ls.as<uint32_t *>(), e->t_ls_tile.as<uint32_t *>(), st);
     launch_orf_find(pl, e->cwoff.as<int64_t>(), e->clen.as<int32_t>(), e->grp2contig.as<int32_t>(), e->d_models.as<DevModel>(), M,
-                    e->t_ls.as<const uint32_t *>(), e->t_orfs.as<OrfRec *>(), e->counters.as<unsigned long long>(), e->cap_orf, st);
+                    e->t_ls.as<const uint32_t *>(), e->t_ls_tile.as<const uint32_t *>(), e->t_orfs.as<OrfRec *>(),
+                    e->counters.as<unsigned long long>(), e->cap_orf, st);
     launches += 1;
     CUDA_TRY(cudaEventRecord(e->ev[2], st));
     launches += launch_orf_prep(pl, e->gc.as<uint32_t>(), e->cwoff.as<int64_t>(), e->clen.as<int32_t>(), e->d_models.as<DevModel>(), M,
@@ -467,7 +496,8 @@ mgc_result *do_decode(mgc_engine *e) {
                                  e->t_item_off.as<uint32_t *>(), e->t_unit_off.as<uint32_t *>(), e->d_models.as<DevModel>(), M,
                                  e->unit_totals.as<uint32_t>(), e->counters.as<unsigned long long>(), e->cap_items, e->n_sm, st);
     CUDA_TRY(cudaEventRecord(e->ev[8], st));
-    launches += launch_walk(pl, e->cwoff.as<int64_t>(), e->d_models.as<DevModel>(), M, e->max_cod_order, e->t_orfs.as<const OrfRec *>(),
+    launches += launch_walk(pl, e->cwoff.as<int64_t>(), e->d_models.as<DevModel>(), M, e->max_cod_order, e->max_non_order,
+                            e->t_orfs.as<const OrfRec *>(),
                             e->t_starts.as<const StartRec *>(), e->t_items_sorted.as<const ItemRec *>(),
                             e->t_item_off.as<const uint32_t *>(), e->t_unit_off.as<const uint32_t *>(), e->unit_totals.as<uint32_t>(),
                             e->t_sums.as<void *>(), e->next_unit.as<unsigned int>(), e->n_sm, st);
@@ -519,6 +549,7 @@ mgc_result *do_decode(mgc_engine *e) {
                                      std::to_string(h_counters[(size_t)i * 8 + 1]) + ", candidates " + std::to_string(h_surv[i]) + ")");
         e->stats.n_orfs += (int64_t)h_counters[(size_t)i * 8];
         e->stats.n_starts += (int64_t)h_counters[(size_t)i * 8 + 1];
+        e->stats.n_walks += (int64_t)h_counters[(size_t)i * 8 + 2];
         e->stats.n_candidates += (int64_t)h_surv[i];
         e->stats.n_genes += h_gtot[i];
     }
@@ -640,7 +671,7 @@ void mgc_engine_destroy(mgc_engine *e) {
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
     for (auto &p : e->pm) {
-        for (DevBuf *b : {&p.lc_full, &p.ln_full, &p.lc_ramp, &p.ln_ramp, &p.sc, &p.quad, &p.rquad, &p.ls, &p.ls_tile, &p.items, &p.items_sorted, &p.hist,
+        for (DevBuf *b : {&p.lc_full, &p.ln_full, &p.lc_ramp, &p.ln_ramp, &p.sc, &p.quad, &p.rquad, &p.wtab, &p.ls, &p.ls_tile, &p.items, &p.items_sorted, &p.hist,
                           &p.item_off, &p.unit_off, &p.sums, &p.witems, &p.orfs, &p.starts, &p.surv, &p.sorted, &p.bcount,
                           &p.cum, &p.prev, &p.gptr, &p.av_right, &p.av_left, &p.av_ls, &p.av_idx, &p.av_cum, &p.av_pmax, &p.av_parg,
                           &p.chain, &p.gene_count, &p.gene_off, &p.contig_total, &p.genes})
@@ -692,6 +723,34 @@ int mgc_decode_batch(mgc_engine *e, const char *seq, const int64_t *offsets, int
     return guarded([&] {
         do_upload(e, seq, offsets, n_contigs);
         *out = do_decode(e);
+    });
+}
+
+int mgc_merge_labels(mgc_engine *e, const int32_t *labels, const int64_t *win_offsets, int32_t n_contigs, int32_t consecutive,
+                     uint32_t noise_labels, int32_t *merged, int32_t *status) {
+    if (!e || !labels || !win_offsets || !merged || !status || n_contigs < 0 || consecutive < 1)
+        return mgc::set_error(MGC_E_ARG, "bad argument");
+    return guarded([&] {
+        CUDA_TRY(cudaSetDevice(e->device));
+        const int64_t nw = win_offsets[n_contigs];
+        cudaStream_t st = e->stream;
+        DevBuf d_lab, d_off, d_out, d_run, d_status;
+        d_lab.ensure((size_t)std::max<int64_t>(nw, 1) * 4);
+        d_out.ensure((size_t)std::max<int64_t>(nw, 1) * 4);
+        d_run.ensure((size_t)std::max<int64_t>(nw, 1) * 4);
+        d_off.ensure((size_t)(n_contigs + 1) * 8);
+        d_status.ensure((size_t)std::max(n_contigs, 1) * 4);
+        CUDA_TRY(cudaMemcpyAsync(d_lab.p, labels, (size_t)nw * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_off.p, win_offsets, (size_t)(n_contigs + 1) * 8, cudaMemcpyHostToDevice, st));
+        if (n_contigs)
+            launch_merge_labels(d_lab.as<int32_t>(), d_off.as<int64_t>(), n_contigs, consecutive, noise_labels, d_out.as<int32_t>(),
+                                d_run.as<int32_t>(), d_status.as<int32_t>(), st);
+        if (nw) CUDA_TRY(cudaMemcpyAsync(merged, d_out.p, (size_t)nw * 4, cudaMemcpyDeviceToHost, st));
+        if (n_contigs) CUDA_TRY(cudaMemcpyAsync(status, d_status.p, (size_t)n_contigs * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        cudaError_t le = cudaGetLastError();
+        d_lab.release(); d_off.release(); d_out.release(); d_run.release(); d_status.release();
+        if (le != cudaSuccess) throw std::runtime_error(std::string("CUDA: ") + cudaGetErrorString(le));
     });
 }
 

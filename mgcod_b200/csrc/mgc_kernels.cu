@@ -362,15 +362,6 @@ __global__ void __launch_bounds__(1024) k_laststop_sums(uint32_t *const *ls_tile
     }
 }
 
-__global__ void __launch_bounds__(LS_THREADS) k_laststop_apply(uint32_t *const *ls_m, uint32_t *const *ls_tile_m, int64_t n_words) {
-    const int mi = blockIdx.y;
-    const int64_t w = (int64_t)blockIdx.x * LS_THREADS + threadIdx.x;
-    if (w >= n_words) return;
-    const uint32_t *lt = ls_tile_m[mi] + (int64_t)blockIdx.x * 3;
-    uint32_t *ls = ls_m[mi] + w * 3;
-    ls[0] = max(ls[0], lt[0]); ls[1] = max(ls[1], lt[1]); ls[2] = max(ls[2], lt[2]);
-}
-
 // ------------------------------------------------------------------------------------------------
 // ORF discovery: thread per word; the previous in-frame stop comes from the table in O(1)
 // ------------------------------------------------------------------------------------------------
@@ -401,8 +392,8 @@ __device__ __forceinline__ bool make_orf(const FindCtx &cx, const DevModel &dm, 
 // grid.x over the 2W words of both strands, grid.y = model
 __global__ void __launch_bounds__(128) k_orf_find(Planes pl, const int64_t *__restrict__ cwoff, const int32_t *__restrict__ clen,
                                                   const int32_t *__restrict__ grp2contig, const DevModel *__restrict__ models,
-                                                  const uint32_t *const *ls_m, OrfRec *const *orfs_m, unsigned long long *counters_m,
-                                                  uint32_t cap_orf) {
+                                                  const uint32_t *const *ls_m, const uint32_t *const *ls_tile_m, OrfRec *const *orfs_m,
+                                                  unsigned long long *counters_m, uint32_t cap_orf) {
     const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int mi = blockIdx.y;
     const DevModel &dm = models[mi];
@@ -436,7 +427,10 @@ __global__ void __launch_bounds__(128) k_orf_find(Planes pl, const int64_t *__re
             const uint32_t all = stop_mask(masks_at(cx, wl), cx.stop_sel);
             // previous stop per frame coming from the words before this one
             uint32_t carry[3] = {0, 0, 0};
-            if (w > 0) { carry[0] = ls[(w - 1) * 3]; carry[1] = ls[(w - 1) * 3 + 1]; carry[2] = ls[(w - 1) * 3 + 2]; }
+            if (w > 0) {  // within-tile scan value of the previous word, topped up with the carry into its tile
+                const uint32_t *lt = ls_tile_m[mi] + ((w - 1) / LS_THREADS) * 3;
+                carry[0] = max(ls[(w - 1) * 3], lt[0]); carry[1] = max(ls[(w - 1) * 3 + 1], lt[1]); carry[2] = max(ls[(w - 1) * 3 + 2], lt[2]);
+            }
             auto prev_local = [&](int b) {  // previous in-frame stop of the codon at bit b, contig-local, -1 if none
                 const uint32_t P = P0 + (uint32_t)b;
                 const int f = (int)(P % 3u);
@@ -763,8 +757,8 @@ __global__ void __launch_bounds__(WALK_UNIT, 2) k_walk(Planes pl, const int64_t 
                                                        const ItemRec *const *items_m, const uint32_t *const *item_off_m,
                                                        const uint32_t *const *unit_off_m, const uint32_t *__restrict__ unit_totals,
                                                        Acc4 *const *sums_m, unsigned int *next_unit) {
-    extern __shared__ __align__(32) unsigned char smem_raw[];
-    Quad *tbl = reinterpret_cast<Quad *>(smem_raw);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double2 *tbl = reinterpret_cast<double2 *>(smem_raw);
     __shared__ int s_model, s_pair;
     __shared__ uint32_t s_first, s_end;
     __shared__ unsigned int s_next;
@@ -796,18 +790,24 @@ __global__ void __launch_bounds__(WALK_UNIT, 2) k_walk(Planes pl, const int64_t 
         if (mi >= n_models) break;
         const DevModel &dm = models[mi];
         const int pair = s_pair;
-        const int kc = dm.kc, nfull = dm.nfull;
-        const Quad *gq = dm.quad + (size_t)pair * 3 * nfull;
+        const int kc = dm.kc, kn = dm.kn, nfull = dm.nfull;
+        const double2 *gq = dm.wtab + (size_t)pair * dm.wtab_n16;
         if (SMEM_TABLE && (mi != loaded_model || pair != loaded_pair)) {
             const int4 *src = reinterpret_cast<const int4 *>(gq);
             int4 *dst = reinterpret_cast<int4 *>(tbl);
-            const int n16 = 3 * nfull * 2;
+            const int n16 = dm.wtab_n16;
             for (int i = threadIdx.x; i < n16; i += WALK_UNIT) dst[i] = __ldg(src + i);
             loaded_model = mi;
             loaded_pair = pair;
             __syncthreads();
         }
-        const Quad *tq = SMEM_TABLE ? tbl : gq;
+        // coding part: {ln P_cod^B, ln P_cod^A} per (phase, k-mer), two replicas interleaved so that even and odd lanes
+        // use disjoint halves of the banks; non-coding part: {ln P_non^B, ln P_non^A} per (kn+1)-mer, eight replicas so
+        // that the eight lanes of a quarter-warp never collide
+        const double2 *tc = SMEM_TABLE ? tbl : gq;
+        const double2 *tn = tc + (size_t)3 * nfull * 2;
+        const uint32_t rep2 = (uint32_t)(lane & 1) << 2, rep8 = (uint32_t)(lane & 7);
+        const int nsh = kc - kn;
         const uint32_t wmask = (1u << (kc + 1)) - 1u;
         const uint32_t end = s_end;
         const ItemRec *items = items_m[mi];
@@ -848,10 +848,11 @@ __global__ void __launch_bounds__(WALK_UNIT, 2) k_walk(Planes pl, const int64_t 
                     if (p >= 0) run = min(run, (p & 31) + 1);
                     int bit = p & 31;
                     for (int r = 0; r < run; r++) {
-                        const Quad *q = tq + ph * nfull + ((hb << (kc + 1)) | lb);
-                        const double2 x = *reinterpret_cast<const double2 *>(q);
-                        const double2 y = *(reinterpret_cast<const double2 *>(q) + 1);
-                        acc.cB += x.x; acc.oB += x.y; acc.cA += y.x; acc.oA += y.y;
+                        const uint32_t e = (uint32_t)(ph * nfull) + ((hb << (kc + 1)) | lb);
+                        const uint32_t idn = ((hb >> nsh) << (kn + 1)) | (lb >> nsh);
+                        const double2 c2 = tc[((e & ~3u) << 1) | (e & 3u) | rep2];
+                        const double2 n2 = tn[(idn << 3) | rep8];
+                        acc.cB += c2.x; acc.cA += c2.y; acc.oB += n2.x; acc.oA += n2.y;   // oB/oA hold the non-coding sums here
                         lb = ((lb << 1) & wmask) | ((cl >> bit) & 1u);
                         hb = ((hb << 1) & wmask) | ((ch >> bit) & 1u);
                         bit = (bit - 1) & 31;
@@ -862,7 +863,9 @@ __global__ void __launch_bounds__(WALK_UNIT, 2) k_walk(Planes pl, const int64_t 
                     if (p >= 0 && (p & 31) == 31) { cl = lo[p >> 5]; ch = hi[p >> 5]; }
                     if (p < 0) { cl = 0; ch = 0; }
                     while (i + 1 == target) {   // a virtual and a real start may share their first full-order position
-                        sums[j] = acc;
+                        Acc4 out;
+                        out.cB = acc.cB; out.oB = acc.cB - acc.oB; out.cA = acc.cA; out.oA = acc.cA - acc.oA;
+                        sums[j] = out;
                         j = cur.link;
                         if (j < 0) { target = -1; break; }
                         cur = nxt;
@@ -1422,6 +1425,75 @@ __global__ void __launch_bounds__(128) k_windows(const mgc_gene *const *genes_m,
 }
 
 // ------------------------------------------------------------------------------------------------
+// label smoothing (reference Pipeline.find_best_sequence_of_labels, bin/pipeline.py:1064-1168): thread per contig.
+// Sequential per contig and tiny (one label per window); runs on the device so that labels never leave HBM between
+// the window kernel and the segmentation inputs.  status[c] = 1 where the reference would raise IndexError (it walks
+// off the array when a contig starts with a noise label).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64) k_merge_labels(const int32_t *__restrict__ labels, const int64_t *__restrict__ win_off,
+                                                     int32_t n_contigs, int32_t consecutive, uint32_t noise_mask,
+                                                     int32_t *out, int32_t *run, int32_t *status) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_contigs) return;
+    const int64_t a = win_off[c];
+    const int n = (int)(win_off[c + 1] - a);
+    const int32_t *lab = labels + a;
+    int32_t *o = out + a, *r = run + a;
+    status[c] = 0;
+    bool uniform = true;
+    for (int i = 0; i < n; i++) {
+        o[i] = lab[i];
+        uniform &= lab[i] == lab[0];
+    }
+    if (n == 0 || uniform) return;
+    auto noise = [&](int l) { return l >= 0 && l < 32 && ((noise_mask >> l) & 1u); };
+    r[0] = 1;
+    for (int i = 1; i < n; i++) r[i] = (lab[i] == lab[i - 1] || noise(lab[i])) ? r[i - 1] + 1 : 1;
+    const int k = consecutive;
+    while (true) {
+        int seed = -1, best = 0;
+        for (int i = 0; i < n; i++)
+            if (r[i] > best) { best = r[i]; seed = i; }   // first maximum, as np.argmax
+        if (seed < 0) break;
+        int lo = seed - best, hi = seed + 1;
+        int ref_pos = seed;
+        int ref = o[ref_pos];
+        while (noise(ref)) {               // a noise label never names a block
+            ref_pos--;
+            if (ref_pos < -n) { status[c] = 1; return; }
+            ref = o[ref_pos < 0 ? ref_pos + n : ref_pos];   // negative indices wrap, as in numpy
+        }
+        int miss = 0;
+        while (lo >= 0 && miss < k) { miss = o[lo] != ref ? miss + 1 : 0; lo--; }
+        const bool left_exhausted = lo < 0;
+        miss = 0;
+        while (hi <= n - 1 && miss < k) { miss = o[hi] != ref ? miss + 1 : 0; hi++; }
+        lo = left_exhausted ? 0 : lo + k + 1;
+        hi = hi > n - 1 ? n : hi - k;
+        if (hi - lo < k) {
+            const int li = lo - 1;
+            const int left_label = o[li < 0 ? li + n : li];
+            const int right_label = hi < n ? o[hi] : left_label;
+            if (left_label == right_label) ref = left_label;
+            else {
+                int i = lo - 1, left_len = 0;
+                while (i >= 0 && o[i] == left_label) { i--; left_len++; }
+                int j = hi, right_len = 0;
+                while (j < n && o[j] == right_label) { j++; right_len++; }
+                ref = left_len > right_len ? left_label : right_label;
+            }
+        }
+        for (int i = max(lo, 0); i < hi; i++) { r[i] = 0; o[i] = ref; }
+        if (hi <= lo) { status[c] = 2; return; }  // no progress (cannot happen for well-formed input)
+    }
+}
+
+void launch_merge_labels(const int32_t *labels, const int64_t *win_off, int32_t n_contigs, int32_t consecutive, uint32_t noise_mask,
+                         int32_t *out, int32_t *run, int32_t *status, cudaStream_t st) {
+    k_merge_labels<<<(unsigned)((n_contigs + 63) / 64), 64, 0, st>>>(labels, win_off, n_contigs, consecutive, noise_mask, out, run, status);
+}
+
+// ------------------------------------------------------------------------------------------------
 // host-callable launch wrappers (keep <<< >>> in this translation unit)
 // ------------------------------------------------------------------------------------------------
 void launch_groups(const int64_t *cwoff, int32_t n_contigs, int64_t n_groups, int32_t *grp2contig, cudaStream_t st) {
@@ -1437,19 +1509,18 @@ void launch_pack(const char *ascii, const int64_t *aoff, const int64_t *cwoff, c
 
 int launch_laststop(Planes pl, const int64_t *cwoff, const int32_t *clen, const int32_t *grp2contig, const DevModel *models,
                     int n_models, uint32_t *const *ls_m, uint32_t *const *ls_tile_m, cudaStream_t st) {
-    const int64_t nw = 2 * pl.W, nt = (nw + LS_THREADS - 1) / LS_THREADS;
+    const int64_t nt = (2 * pl.W + LS_THREADS - 1) / LS_THREADS;
     dim3 grid((unsigned)nt, n_models);
     k_laststop_tiles<<<grid, LS_THREADS, 0, st>>>(pl, cwoff, clen, grp2contig, models, ls_m, ls_tile_m);
     k_laststop_sums<<<n_models, 1024, 0, st>>>(ls_tile_m, nt);
-    k_laststop_apply<<<grid, LS_THREADS, 0, st>>>(ls_m, ls_tile_m, nw);
-    return 3;
+    return 2;  // the carry into each tile is applied by the consumer (k_orf_find)
 }
 
 void launch_orf_find(Planes pl, const int64_t *cwoff, const int32_t *clen, const int32_t *grp2contig, const DevModel *models,
-                     int n_models, const uint32_t *const *ls_m, OrfRec *const *orfs_m, unsigned long long *counters_m,
-                     uint32_t cap_orf, cudaStream_t st) {
+                     int n_models, const uint32_t *const *ls_m, const uint32_t *const *ls_tile_m, OrfRec *const *orfs_m,
+                     unsigned long long *counters_m, uint32_t cap_orf, cudaStream_t st) {
     dim3 grid((unsigned)((2 * pl.W + 127) / 128), n_models);
-    k_orf_find<<<grid, 128, 0, st>>>(pl, cwoff, clen, grp2contig, models, ls_m, orfs_m, counters_m, cap_orf);
+    k_orf_find<<<grid, 128, 0, st>>>(pl, cwoff, clen, grp2contig, models, ls_m, ls_tile_m, orfs_m, counters_m, cap_orf);
 }
 
 int launch_orf_prep(Planes pl, const uint32_t *gcpre, const int64_t *cwoff, const int32_t *clen, const DevModel *models, int n_models,
@@ -1473,16 +1544,17 @@ int launch_item_sort(const ItemRec *const *items_m, ItemRec *const *sorted_m, ui
     return 2;
 }
 
-int walk_smem_bytes(int cod_order) { return 3 * (1 << (2 * (cod_order + 1))) * (int)sizeof(Quad); }
+int walk_smem_bytes(int cod_order, int non_order) { return (3 * (1 << (2 * (cod_order + 1))) * 2 + (1 << (2 * (non_order + 1))) * 8) * 16; }
 
-int launch_walk(Planes pl, const int64_t *cwoff, const DevModel *models, int n_models, int max_cod_order, const OrfRec *const *orfs_m,
+int launch_walk(Planes pl, const int64_t *cwoff, const DevModel *models, int n_models, int max_cod_order, int max_non_order,
+                const OrfRec *const *orfs_m,
                 const StartRec *const *starts_m, const ItemRec *const *items_m, const uint32_t *const *item_off_m,
                 const uint32_t *const *unit_off_m, const uint32_t *unit_totals, void *const *sums_m, unsigned int *next_unit, int n_sm,
                 cudaStream_t st) {
-    const int smem = walk_smem_bytes(max_cod_order);
+    const int smem = walk_smem_bytes(max_cod_order, max_non_order);
     Acc4 *const *sums = reinterpret_cast<Acc4 *const *>(sums_m);
-    if (smem <= 100 * 1024) {
-        cudaFuncSetAttribute(k_walk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (smem <= 110 * 1024) {
+        cudaFuncSetAttribute(k_walk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
         k_walk<true><<<n_sm * 2, WALK_UNIT, smem, st>>>(pl, cwoff, models, n_models, orfs_m, starts_m, items_m, item_off_m, unit_off_m,
                                                         unit_totals, sums, next_unit);
     } else {

@@ -24,8 +24,8 @@ void launch_pack(const char *ascii, const int64_t *aoff, const int64_t *cwoff, c
 int launch_laststop(Planes pl, const int64_t *cwoff, const int32_t *clen, const int32_t *grp2contig, const DevModel *models,
                     int n_models, uint32_t *const *ls_m, uint32_t *const *ls_tile_m, cudaStream_t st);
 void launch_orf_find(Planes pl, const int64_t *cwoff, const int32_t *clen, const int32_t *grp2contig, const DevModel *models,
-                     int n_models, const uint32_t *const *ls_m, OrfRec *const *orfs_m, unsigned long long *counters_m,
-                     uint32_t cap_orf, cudaStream_t st);
+                     int n_models, const uint32_t *const *ls_m, const uint32_t *const *ls_tile_m, OrfRec *const *orfs_m,
+                     unsigned long long *counters_m, uint32_t cap_orf, cudaStream_t st);
 int launch_orf_prep(Planes pl, const uint32_t *gcpre, const int64_t *cwoff, const int32_t *clen, const DevModel *models, int n_models,
                     OrfRec *const *orfs_m, WordItem *const *witems_m, StartRec *const *starts_m, ItemRec *const *items_m,
                     uint32_t *const *hist_m, unsigned long long *counters_m, const ChainBufs *bufs_m, uint32_t cap_orf,
@@ -33,7 +33,8 @@ int launch_orf_prep(Planes pl, const uint32_t *gcpre, const int64_t *cwoff, cons
 int launch_item_sort(const ItemRec *const *items_m, ItemRec *const *sorted_m, uint32_t *const *hist_m, uint32_t *const *item_off_m,
                      uint32_t *const *unit_off_m, const DevModel *models, int n_models, uint32_t *unit_totals,
                      const unsigned long long *counters_m, uint32_t cap_items, int n_sm, cudaStream_t st);
-int launch_walk(Planes pl, const int64_t *cwoff, const DevModel *models, int n_models, int max_cod_order, const OrfRec *const *orfs_m,
+int launch_walk(Planes pl, const int64_t *cwoff, const DevModel *models, int n_models, int max_cod_order, int max_non_order,
+                const OrfRec *const *orfs_m,
                 const StartRec *const *starts_m, const ItemRec *const *items_m, const uint32_t *const *item_off_m,
                 const uint32_t *const *unit_off_m, const uint32_t *unit_totals, void *const *sums_m, unsigned int *next_unit, int n_sm,
                 cudaStream_t st);
@@ -51,5 +52,8 @@ void launch_gather(const ChainBufs *bufs_m, const uint32_t *const *gene_off_m, m
 void launch_windows(const mgc_gene *const *genes_m, const uint32_t *const *gene_off_m, int n_models, const int32_t *clen,
                     const int32_t *stride, const int64_t *win_off, int32_t n_contigs, int32_t window, int32_t consecutive,
                     int short_contigs, int32_t *labels, long long *cents, cudaStream_t st);
+
+void launch_merge_labels(const int32_t *labels, const int64_t *win_off, int32_t n_contigs, int32_t consecutive, uint32_t noise_mask,
+                         int32_t *out, int32_t *run, int32_t *status, cudaStream_t st);
 
 }  // namespace mgc

@@ -193,6 +193,26 @@ class Engine:
                                    cents.ctypes.data_as(C.POINTER(C.c_int64))))
         return offs, labels[:nw], cents[:nw]
 
+    def merge_labels(self, labels_per_contig: Sequence[np.ndarray], consecutive: int) -> list[np.ndarray]:
+        """Device-side label smoothing (reference bin/pipeline.py:1064-1168) of every contig's window labels; noise labels =
+        all but the two most frequent labels over the whole input.  Raises IndexError where the reference does."""
+        from .labels import noise_labels
+        labs = [np.ascontiguousarray(l, dtype=np.int32) for l in labels_per_contig]
+        offs = np.zeros(len(labs) + 1, dtype=np.int64)
+        np.cumsum([len(l) for l in labs], out=offs[1:])
+        flat = np.concatenate(labs) if labs else np.zeros(0, np.int32)
+        mask = 0
+        for l in noise_labels(flat) if flat.size else []:
+            mask |= 1 << int(l)
+        out = np.zeros(max(int(offs[-1]), 1), dtype=np.int32)
+        status = np.zeros(max(len(labs), 1), dtype=np.int32)
+        _check(_lib.lib().mgc_merge_labels(self._h, flat.ctypes.data_as(C.POINTER(C.c_int32)), offs.ctypes.data_as(C.POINTER(C.c_int64)),
+                                           len(labs), consecutive, mask, out.ctypes.data_as(C.POINTER(C.c_int32)),
+                                           status.ctypes.data_as(C.POINTER(C.c_int32))))
+        if (status[:len(labs)] != 0).any():
+            raise IndexError(f"label smoothing walks off the array for contig index {int(np.flatnonzero(status)[0])} (as the reference does)")
+        return [out[offs[i]:offs[i + 1]].astype(np.int64) for i in range(len(labs))]
+
     def close(self) -> None:
         if getattr(self, "_h", None):
             _lib.lib().mgc_engine_destroy(self._h)

@@ -7,8 +7,9 @@ Same constructor arguments and result attributes (``genome_label``, ``logodd_sco
 * gene finding under the four models ............ GPU (:class:`mgcod_b200.data.Data` → engine)
 * per-file sums and argmax (classify_complete_sequence, pipeline.py:139-155) ... GPU (integer 1/100 units)
 * per-window sums, spanning-gene fallback, argmax labels (identify_most_common_codes, :157-385) ... GPU
-* label smoothing (find_best_sequence_of_labels, :1064-1168) and switch coordinates
-  (segment_genome_based_on_window_labels, :387-492) ... host, :mod:`mgcod_b200.labels`
+* label smoothing (find_best_sequence_of_labels, :1064-1168) ... GPU (`k_merge_labels`, thread per contig); a host
+  restatement lives in :mod:`mgcod_b200.labels`
+* switch coordinates (segment_genome_based_on_window_labels, :387-492) ... host, :mod:`mgcod_b200.labels`
 
 Out of scope this round: ``compare_sets_of_predicted_genes`` — the pairwise
 isoform comparison that rewrites GFF attributes; ``coords_w_isoforms`` is therefore only set when a single
@@ -77,10 +78,8 @@ class Pipeline:
                 self.consecutive_windows = n = min(first.shape[0], last.shape[0])
                 warnings.warn(f"Setting consecutive windows to {n}")
             self.genome_label = [np.concatenate([last, self.genome_label[0].copy(), first])]
-        all_labels = np.concatenate(self.genome_label)
-        updated = []
-        for wl in self.genome_label:
-            updated.append(wl if np.unique(wl).shape[0] == 1 else L.find_best_sequence_of_labels(wl, all_labels, n))
+        # smoothing of every contig's labels in one device call (host restatement: labels.find_best_sequence_of_labels)
+        updated = self.data.engine.merge_labels(self.genome_label, n)
         if padded:
             updated = [updated[0][n:-n]]
             self.genome_label = [self.genome_label[0][n:-n]]
