@@ -835,33 +835,32 @@ __global__ void __launch_bounds__(WALK_UNIT, 2) k_walk(Planes pl, const int64_t 
                 if (cur.link >= 0) nxt = st[cur.link];
                 Acc4 acc = {0, 0, 0, 0};
                 int i = t - 1;
-                uint32_t hb, lb;
-                window_bits(lo, hi, i - kc, kc + 1, hb, lb);
                 int ph = (((-1 - kc) % 3) + 3) % 3;   // codon position of the window's first letter at i = t-1
-                int p = i - kc - 1;                   // next letter to shift in
-                uint32_t cl = 0, ch = 0;
-                if (p >= 0) { cl = lo[p >> 5]; ch = hi[p >> 5]; }
+                // the (kc+1)-letter window ending at i starts at bit `sh` of plane word `w`; the word pair (w, w+1) sits in registers
+                int w = (i - kc) >> 5, sh = (i - kc) & 31;
+                uint32_t l0 = lo[w], l1 = lo[w + 1], h0 = hi[w], h1 = hi[w + 1];
                 const int lo_pos = it.lo_pos;
                 while (i >= lo_pos) {
-                    // a run ends at the next target, at lo_pos, or where the current plane word is used up
-                    int run = i - max(target, lo_pos) + 1;
-                    if (p >= 0) run = min(run, (p & 31) + 1);
-                    int bit = p & 31;
+                    // a run ends at the next target, at lo_pos, or where the window start leaves the current plane word
+                    const int run = min(i - max(target, lo_pos) + 1, sh + 1);
                     for (int r = 0; r < run; r++) {
+                        const uint32_t lb = __funnelshift_r(l0, l1, sh) & wmask;
+                        const uint32_t hb = __funnelshift_r(h0, h1, sh) & wmask;
                         const uint32_t e = (uint32_t)(ph * nfull) + ((hb << (kc + 1)) | lb);
                         const uint32_t idn = ((hb >> nsh) << (kn + 1)) | (lb >> nsh);
                         const double2 c2 = tc[((e & ~3u) << 1) | (e & 3u) | rep2];
                         const double2 n2 = tn[(idn << 3) | rep8];
                         acc.cB += c2.x; acc.cA += c2.y; acc.oB += n2.x; acc.oA += n2.y;   // oB/oA hold the non-coding sums here
-                        lb = ((lb << 1) & wmask) | ((cl >> bit) & 1u);
-                        hb = ((hb << 1) & wmask) | ((ch >> bit) & 1u);
-                        bit = (bit - 1) & 31;
+                        sh--;
                         ph = ph == 0 ? 2 : ph - 1;
                     }
                     i -= run;
-                    p -= run;
-                    if (p >= 0 && (p & 31) == 31) { cl = lo[p >> 5]; ch = hi[p >> 5]; }
-                    if (p < 0) { cl = 0; ch = 0; }
+                    if (sh < 0 && w > 0) {
+                        w--;
+                        sh = 31;
+                        l1 = l0; h1 = h0;
+                        l0 = lo[w]; h0 = hi[w];
+                    }
                     while (i + 1 == target) {   // a virtual and a real start may share their first full-order position
                         Acc4 out;
                         out.cB = acc.cB; out.oB = acc.cB - acc.oB; out.cA = acc.cA; out.oA = acc.cA - acc.oA;
