@@ -93,6 +93,10 @@ const mgc_gene *mgc_result_genes(const mgc_result *r, int model);
 const double *mgc_result_contig_totals(const mgc_result *r, int model);
 /* sum over all genes of round(logodd,2) in 1/100 units — Pipeline.classify_complete_sequence */
 int mgc_result_model_cents(const mgc_result *r, int64_t *cents /*[n_models]*/);
+/* $GENE_MIN_LENGTH of the model the genes came from (90 for results made by mgc_result_create until set): gmhmmp2
+ * skips records shorter than it, and mgc_write_gff then omits their summary line */
+int32_t mgc_result_min_gene_length(const mgc_result *r, int model);
+int mgc_result_set_min_gene_length(mgc_result *r, int model, int32_t min_len);
 void mgc_result_free(mgc_result *r);
 /* Host-side constructor (no GPU): wraps caller-provided genes, e.g. parsed back from cached GFF files
  * (bin/data.py:39 skips gmhmmp2 when mgm_<code>_<species>.gff exists).  genes[m] holds counts[m] genes ordered

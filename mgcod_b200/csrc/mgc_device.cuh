@@ -33,6 +33,7 @@ struct DevModel {
     int npair;
     int map[2][101];
     int pair[101];      // gc -> index of its (secB, secA) pair in quad
+    const double *pair_amb;  // [npair][4]: ln COD_P_N (B, A), ln NON_P_N (B, A) — terms of a window with an ambiguous letter
 };
 
 // one stop-delimited ORF that may have start candidates of sufficient length
@@ -43,7 +44,8 @@ struct OrfRec {
     uint32_t base;      // first entry in the starts array (filled by k_orf_prep)
     uint32_t n;         // number of starts              (filled by k_orf_prep)
     uint32_t sf;        // bit0: strand (1 = reverse complement); bit1: open at the left edge (virtual start);
-                        // bit8: stop codon missing (ORF runs into the right edge)
+                        // bit8: stop codon missing (ORF runs into the right edge); bit9: the virtual start is summed from
+                        // its first letter (every case except a reverse-strand ORF cut by the true end of the record)
 };
 
 // one start candidate of an ORF
@@ -106,6 +108,10 @@ struct ChainBufs {
 
 struct Planes {
     const uint32_t *lo, *hi;  // [2][W + 4]
+    const uint32_t *nm;       // [2][W + 4] ambiguity mask: bit set = letter outside ACGT (its code in lo/hi is 0)
+    const uint32_t *npre;     // [W + 4] exclusive prefix of ambiguous letters per word, forward region
+    const int *dflags;        // device flags written by k_pack: [0] letter outside the IUPAC alphabet, [1] any ambiguous letter
+    const uint8_t *cflags;    // per contig slot: bit0 = its right edge is the end of the record (not a gap)
     int64_t W;                // words per strand region
 };
 

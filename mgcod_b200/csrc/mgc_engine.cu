@@ -73,6 +73,7 @@ struct mgc_result {
     std::vector<PinnedPool::Block> gene_blk, total_blk;
     std::vector<int64_t> n_genes;
     std::vector<int64_t> cents;
+    std::vector<int32_t> min_len;   // $GENE_MIN_LENGTH of each model: records shorter than it get no summary line
     bool host_owned = false;   // blocks came from malloc (mgc_result_create), not from the pinned pool
     ~mgc_result() {
         if (host_owned) {
@@ -115,7 +116,7 @@ struct DevBuf {
 };
 
 struct PerModel {
-    DevBuf lc_full, ln_full, lc_ramp, ln_ramp, sc, quad, rquad, wtab;
+    DevBuf lc_full, ln_full, lc_ramp, ln_ramp, sc, quad, rquad, wtab, pair_amb;
     DevBuf ls, ls_tile, orfs, starts, witems, items, items_sorted, hist, item_off, unit_off, sums;
     DevBuf surv, sorted, bcount, cum, prev, gptr;
     DevBuf av_right, av_left, av_ls, av_idx, av_cum, av_pmax, av_parg, chain, gene_count, gene_off, contig_total, genes;
@@ -138,6 +139,21 @@ struct mgc_engine {
     int64_t total_nt = 0, W = 0;
     std::vector<int64_t> h_aoff, h_cwoff;
     std::vector<int32_t> h_clen, h_order;
+    // the caller's contigs ("parents") and the slots actually decoded: one slot per contig, or several when runs of
+    // >= 40 ambiguous letters split a contig (gmhmmp2 --incomplete_at_gaps 40)
+    struct Seg {
+        int32_t parent;
+        int64_t aoff;      // offset of its first letter in the device ASCII buffer
+        int32_t len;
+        int32_t poff;      // offset inside the parent
+        uint8_t right_end; // its right edge is the end of the record
+    };
+    std::vector<Seg> segs;
+    std::vector<int64_t> h_parent_aoff;
+    std::vector<int32_t> h_parent_len;
+    int32_t n_parents = 0;
+    bool segmented = false;
+    DevBuf nm, ncount, cflags, plen, gaps, gap_count;
     DevBuf ascii, aoff, cwoff, clen, grp2contig, order, lo, hi, gc, tile_sums, flags;
     // pointer tables + counters (device)
     DevBuf t_orfs, t_starts, t_surv, t_sorted, t_bcount, t_gene_off, t_genes, t_chainbufs;
@@ -279,6 +295,18 @@ void upload_models(mgc_engine *e) {
                         if (dom) { e4.cA = cv; e4.oA = cv - nv; } else { e4.cB = cv; e4.oB = cv - nv; }
                     }
                 }
+        {
+            std::vector<double> pa(pairs.size() * 4, 0.0);
+            for (size_t pi = 0; pi < pairs.size(); pi++)
+                for (int dom = 0; dom < 2; dom++) {
+                    const int sec = dom ? pairs[pi].second : pairs[pi].first;
+                    if (sec < 0) continue;
+                    pa[pi * 4 + dom] = m.sc[sec].ln_cpn;                          // ln COD_P_N
+                    pa[pi * 4 + 2 + dom] = m.sc[sec].ln_cpn - m.sc[sec].ln_pn;    // ln NON_P_N
+                }
+            up(p.pair_amb, pa.data(), pa.size() * sizeof(double));
+            d.pair_amb = p.pair_amb.as<double>();
+        }
         up(p.rquad, rq.data(), std::max<size_t>(rq.size(), 1) * sizeof(Quad));
         d.rquad = p.rquad.as<Quad>();
         e->max_cod_order = std::max(e->max_cod_order, kc);
@@ -294,6 +322,8 @@ void ensure_batch_buffers(mgc_engine *e) {
     e->lo.ensure((size_t)(2 * W + 8) * 4);
     e->hi.ensure((size_t)(2 * W + 8) * 4);
     e->gc.ensure((size_t)(W + 8) * 4);
+    e->nm.ensure((size_t)(2 * W + 8) * 4);
+    e->ncount.ensure((size_t)(W + 8) * 4);
     const int64_t nb = W / 4;
     const int64_t scan_n = std::max<int64_t>(std::max<int64_t>(W, nb), e->n_contigs + 1);
     e->tile_sums.ensure((size_t)(scan_n / 2048 + 8) * 4);
@@ -394,25 +424,27 @@ void ensure_batch_buffers(mgc_engine *e) {
     e->gene_totals.ensure((size_t)M * 4);
 }
 
-void do_upload(mgc_engine *e, const char *seq, const int64_t *offsets, int32_t n) {
-    if (n <= 0) throw std::invalid_argument("n_contigs must be positive");
-    CUDA_TRY(cudaSetDevice(e->device));
-    e->have_batch = e->have_genes = false;
+// (re)builds the slot table from e->segs and uploads it; the ASCII letters stay where they are
+void set_slots(mgc_engine *e) {
+    const int32_t n = (int32_t)e->segs.size();
     e->n_contigs = n;
-    e->h_aoff.assign(offsets, offsets + n + 1);
     e->h_clen.resize(n);
     e->h_cwoff.resize(n + 1);
+    e->h_aoff.resize(n + 1);
+    std::vector<uint8_t> cflags(n);
     int64_t w = 0, nt = 0;
     for (int32_t c = 0; c < n; c++) {
-        int64_t L = offsets[c + 1] - offsets[c];
-        if (L < 0 || L > 0x7ffffff0) throw std::invalid_argument("contig length out of range");
+        const int64_t L = e->segs[c].len;
         e->h_clen[c] = (int32_t)L;
         e->h_cwoff[c] = w;
-        int64_t words = (L + 31) / 32 + 1;
+        e->h_aoff[c] = e->segs[c].aoff;
+        cflags[c] = e->segs[c].right_end;
+        const int64_t words = (L + 31) / 32 + 1;
         w += (words + 3) / 4 * 4;
         nt += L;
     }
     e->h_cwoff[n] = w;
+    e->h_aoff[n] = 0;
     if (w * 64 >= 0xffffffffLL) throw std::invalid_argument("batch too large: at most ~2e9 nt per decode call");
     e->W = w;
     e->total_nt = nt;
@@ -420,25 +452,49 @@ void do_upload(mgc_engine *e, const char *seq, const int64_t *offsets, int32_t n
     std::iota(e->h_order.begin(), e->h_order.end(), 0);
     std::stable_sort(e->h_order.begin(), e->h_order.end(), [&](int a, int b) { return e->h_clen[a] > e->h_clen[b]; });
     ensure_batch_buffers(e);
-    const int64_t a0 = offsets[0], a1 = offsets[n];
-    e->ascii.ensure((size_t)(a1 - a0) + 64);
     e->aoff.ensure((size_t)(n + 1) * 8);
     e->cwoff.ensure((size_t)(n + 1) * 8);
     e->clen.ensure((size_t)n * 4);
     e->order.ensure((size_t)n * 4);
-    std::vector<int64_t> rel(n + 1);
-    for (int32_t c = 0; c <= n; c++) rel[c] = offsets[c] - a0;
+    e->cflags.ensure((size_t)n + 16);
     cudaStream_t st = e->stream;
-    CUDA_TRY(cudaEventRecord(e->ev[0], st));
-    CUDA_TRY(cudaMemcpyAsync(e->ascii.p, seq + a0, (size_t)(a1 - a0), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(e->aoff.p, rel.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(e->aoff.p, e->h_aoff.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(e->cwoff.p, e->h_cwoff.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(e->clen.p, e->h_clen.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(e->order.p, e->h_order.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(e->cflags.p, cflags.data(), (size_t)n, cudaMemcpyHostToDevice, st));
     launch_groups(e->cwoff.as<int64_t>(), n, e->W / 4, e->grp2contig.as<int32_t>(), st);
-    CUDA_TRY(cudaEventRecord(e->ev[1], st));
-    CUDA_TRY(cudaStreamSynchronize(st));  // rel[] is a stack-local staging buffer
+    CUDA_TRY(cudaStreamSynchronize(st));  // cflags is a local staging buffer
     CUDA_TRY(cudaGetLastError());
+}
+
+void do_upload(mgc_engine *e, const char *seq, const int64_t *offsets, int32_t n) {
+    if (n <= 0) throw std::invalid_argument("n_contigs must be positive");
+    CUDA_TRY(cudaSetDevice(e->device));
+    e->have_batch = e->have_genes = false;
+    e->segmented = false;
+    e->n_parents = n;
+    e->h_parent_len.resize(n);
+    e->h_parent_aoff.resize(n + 1);
+    e->segs.resize(n);
+    const int64_t a0 = offsets[0], a1 = offsets[n];
+    for (int32_t c = 0; c < n; c++) {
+        const int64_t L = offsets[c + 1] - offsets[c];
+        if (L < 0 || L > 0x7ffffff0) throw std::invalid_argument("contig length out of range");
+        e->h_parent_len[c] = (int32_t)L;
+        e->h_parent_aoff[c] = offsets[c] - a0;
+        e->segs[c] = mgc_engine::Seg{c, offsets[c] - a0, (int32_t)L, 0, 1};
+    }
+    e->h_parent_aoff[n] = a1 - a0;
+    cudaStream_t st = e->stream;
+    e->ascii.ensure((size_t)(a1 - a0) + 64);
+    e->plen.ensure((size_t)n * 4 + 16);
+    CUDA_TRY(cudaEventRecord(e->ev[0], st));
+    CUDA_TRY(cudaMemcpyAsync(e->ascii.p, seq + a0, (size_t)(a1 - a0), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(e->plen.p, e->h_parent_len.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    set_slots(e);
+    CUDA_TRY(cudaEventRecord(e->ev[1], st));
+    CUDA_TRY(cudaStreamSynchronize(st));
     float ms = 0;
     cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]);
     e->stats = mgc_stats();
@@ -446,7 +502,8 @@ void do_upload(mgc_engine *e, const char *seq, const int64_t *offsets, int32_t n
     e->have_batch = true;
 }
 
-mgc_result *do_decode(mgc_engine *e) {
+// one pass of the device pipeline over the current slots; *amb_out tells whether any letter was ambiguous
+mgc_result *run_pipeline(mgc_engine *e, bool *amb_out) {
     if (!e->have_batch) throw std::invalid_argument("no batch uploaded");
     CUDA_TRY(cudaSetDevice(e->device));
     const int M = e->n_models;
@@ -472,14 +529,19 @@ mgc_result *do_decode(mgc_engine *e) {
     }
     // pack + GC prefix
     launch_pack(e->ascii.as<char>(), e->aoff.as<int64_t>(), e->cwoff.as<int64_t>(), e->clen.as<int32_t>(),
-                e->grp2contig.as<int32_t>(), W, e->lo.as<uint32_t>(), e->hi.as<uint32_t>(), e->gc.as<uint32_t>(),
-                e->flags.as<int>(), st);
+                e->grp2contig.as<int32_t>(), W, e->lo.as<uint32_t>(), e->hi.as<uint32_t>(), e->nm.as<uint32_t>(), e->gc.as<uint32_t>(),
+                e->ncount.as<uint32_t>(), e->flags.as<int>(), st);
     launches += 1;
     launches += launch_exclusive_scan(e->gc.as<uint32_t>(), e->gc.as<uint32_t>(), e->tile_sums.as<uint32_t>(), W, nullptr, st);
+    launches += launch_exclusive_scan(e->ncount.as<uint32_t>(), e->ncount.as<uint32_t>(), e->tile_sums.as<uint32_t>(), W, nullptr, st);
     CUDA_TRY(cudaEventRecord(e->ev[1], st));
     Planes pl;
     pl.lo = e->lo.as<uint32_t>();
     pl.hi = e->hi.as<uint32_t>();
+    pl.nm = e->nm.as<uint32_t>();
+    pl.npre = e->ncount.as<uint32_t>();
+    pl.dflags = e->flags.as<int>();
+    pl.cflags = e->cflags.as<uint8_t>();
     pl.W = W;
     launches += launch_laststop(pl, e->cwoff.as<int64_t>(), e->clen.as<int32_t>(), e->grp2contig.as<int32_t>(),
                                 e->d_models.as<DevModel>(), M, e->t_ls.as<uint32_t *>(), e->t_ls_tile.as<uint32_t *>(), st);
@@ -541,7 +603,8 @@ mgc_result *do_decode(mgc_engine *e) {
     CUDA_TRY(cudaMemcpyAsync(h_flags, e->flags.p, 64, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaGetLastError());
-    if (h_flags[0]) throw AlphabetError("sequence contains letters outside ACGT; ambiguous letters are not supported by this build");
+    if (h_flags[0]) throw AlphabetError("error, unexpected letter found in FASTA sequence (accepted: ACGTU and the IUPAC codes RYSWKMBDHVN)");
+    *amb_out = h_flags[1] != 0;
     for (int i = 0; i < M; i++) {
         if (h_counters[(size_t)i * 8] > e->cap_orf || h_counters[(size_t)i * 8 + 1] > e->cap_starts ||
             h_counters[(size_t)i * 8 + 2] > e->cap_items || h_counters[(size_t)i * 8 + 3] > e->cap_witems || h_surv[i] > e->cap_surv)
@@ -560,6 +623,7 @@ mgc_result *do_decode(mgc_engine *e) {
     res->pool = e->pool;
     res->cents.assign(h_cents.begin(), h_cents.end());
     res->n_genes.assign(h_gtot.begin(), h_gtot.end());
+    for (int i = 0; i < M; i++) res->min_len.push_back(e->models[i].min_len);
     for (int i = 0; i < M; i++) {
         res->gene_blk.push_back(e->pool->acquire((size_t)h_gtot[i] * sizeof(mgc_gene)));
         res->total_blk.push_back(e->pool->acquire((size_t)n * 8));
@@ -582,6 +646,83 @@ mgc_result *do_decode(mgc_engine *e) {
     cudaEventElapsedTime(&ms, e->ev[0], e->ev[7]); e->stats.total = ms;
     e->stats.kernel_launches = launches;
     e->have_genes = true;
+    return res.release();
+}
+
+// slot-space result -> the caller's contigs: contig index, coordinates, per-contig totals; re-uploads the mapped genes so
+// that the window kernel sees parents
+void remap_to_parents(mgc_engine *e, mgc_result *res) {
+    const int M = e->n_models;
+    const int32_t np = e->n_parents;
+    cudaStream_t st = e->stream;
+    for (int i = 0; i < M; i++) {
+        mgc_gene *g = static_cast<mgc_gene *>(res->gene_blk[i].p);
+        const int64_t ng = res->n_genes[i];
+        std::vector<uint32_t> off(np + 1, 0);
+        for (int64_t k = 0; k < ng; k++) {
+            const mgc_engine::Seg &s = e->segs[g[k].contig];
+            g[k].contig = s.parent;
+            g[k].left += s.poff;
+            g[k].right += s.poff;
+            off[s.parent + 1]++;
+        }
+        for (int32_t c = 0; c < np; c++) off[c + 1] += off[c];
+        const double *tot = static_cast<const double *>(res->total_blk[i].p);
+        PinnedPool::Block nb = e->pool->acquire((size_t)std::max(np, 1) * 8);
+        double *pt = static_cast<double *>(nb.p);
+        for (int32_t c = 0; c < np; c++) pt[c] = 0.0;
+        for (size_t c = 0; c < e->segs.size(); c++) pt[e->segs[c].parent] += tot[c];
+        e->pool->release(res->total_blk[i]);
+        res->total_blk[i] = nb;
+        if (ng) CUDA_TRY(cudaMemcpyAsync(e->pm[i].genes.p, g, (size_t)ng * sizeof(mgc_gene), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(e->pm[i].gene_off.p, off.data(), (size_t)(np + 1) * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    res->n_contigs = np;
+}
+
+mgc_result *do_decode(mgc_engine *e) {
+    bool amb = false;
+    std::unique_ptr<mgc_result> res(run_pipeline(e, &amb));
+    if (amb && !e->segmented) {
+        // runs of >= 40 ambiguous letters split a record (gmhmmp2 --incomplete_at_gaps 40): find them on the device,
+        // re-slot the batch and decode again
+        cudaStream_t st = e->stream;
+        const uint32_t cap = 1u << 20;
+        e->gaps.ensure((size_t)cap * 12);
+        e->gap_count.ensure(16);
+        CUDA_TRY(cudaMemsetAsync(e->gap_count.p, 0, 16, st));
+        launch_find_gaps(e->nm.as<uint32_t>(), e->cwoff.as<int64_t>(), e->clen.as<int32_t>(), e->n_contigs, 40, e->gaps.as<int32_t>(),
+                         e->gap_count.as<unsigned int>(), cap, st);
+        unsigned int ngap = 0;
+        CUDA_TRY(cudaMemcpyAsync(&ngap, e->gap_count.p, 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (ngap > cap) throw std::runtime_error("too many gaps in one batch");
+        if (ngap) {
+            std::vector<int32_t> gaps((size_t)ngap * 3);
+            CUDA_TRY(cudaMemcpy(gaps.data(), e->gaps.p, (size_t)ngap * 12, cudaMemcpyDeviceToHost));
+            std::vector<std::vector<std::pair<int32_t, int32_t>>> per(e->n_parents);
+            for (unsigned int k = 0; k < ngap; k++) per[gaps[k * 3]].push_back({gaps[k * 3 + 1], gaps[k * 3 + 2]});
+            std::vector<mgc_engine::Seg> segs;
+            for (int32_t c = 0; c < e->n_parents; c++) {
+                auto &v = per[c];
+                std::sort(v.begin(), v.end());
+                int32_t pos = 0;
+                const int32_t L = e->h_parent_len[c];
+                for (auto &gp : v) {
+                    if (gp.first > pos) segs.push_back(mgc_engine::Seg{c, e->h_parent_aoff[c] + pos, gp.first - pos, pos, 0});
+                    pos = gp.first + gp.second;
+                }
+                if (L > pos || v.empty()) segs.push_back(mgc_engine::Seg{c, e->h_parent_aoff[c] + pos, L - pos, pos, 1});
+            }
+            if (segs.empty()) segs.push_back(mgc_engine::Seg{0, e->h_parent_aoff[0], 0, 0, 1});  // nothing but gaps
+            e->segs.swap(segs);
+            e->segmented = true;
+            set_slots(e);
+            res.reset(run_pipeline(e, &amb));
+        }
+    }
+    if (e->segmented) remap_to_parents(e, res.get());
     return res.release();
 }
 
@@ -671,7 +812,7 @@ void mgc_engine_destroy(mgc_engine *e) {
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
     for (auto &p : e->pm) {
-        for (DevBuf *b : {&p.lc_full, &p.ln_full, &p.lc_ramp, &p.ln_ramp, &p.sc, &p.quad, &p.rquad, &p.wtab, &p.ls, &p.ls_tile, &p.items, &p.items_sorted, &p.hist,
+        for (DevBuf *b : {&p.lc_full, &p.ln_full, &p.lc_ramp, &p.ln_ramp, &p.sc, &p.quad, &p.rquad, &p.wtab, &p.pair_amb, &p.ls, &p.ls_tile, &p.items, &p.items_sorted, &p.hist,
                           &p.item_off, &p.unit_off, &p.sums, &p.witems, &p.orfs, &p.starts, &p.surv, &p.sorted, &p.bcount,
                           &p.cum, &p.prev, &p.gptr, &p.av_right, &p.av_left, &p.av_ls, &p.av_idx, &p.av_cum, &p.av_pmax, &p.av_parg,
                           &p.chain, &p.gene_count, &p.gene_off, &p.contig_total, &p.genes})
@@ -681,7 +822,7 @@ void mgc_engine_destroy(mgc_engine *e) {
                       &e->tile_sums, &e->flags, &e->t_orfs, &e->t_starts, &e->t_surv, &e->t_sorted, &e->t_bcount, &e->t_gene_off,
                       &e->t_genes, &e->t_chainbufs, &e->counters, &e->surv_counters, &e->work_counters, &e->model_cents,
                       &e->gene_totals, &e->t_ls, &e->t_ls_tile, &e->t_items, &e->t_items_sorted, &e->t_hist, &e->t_item_off,
-                      &e->t_unit_off, &e->t_sums, &e->t_witems, &e->unit_totals, &e->next_unit, &e->win_stride, &e->win_off, &e->win_labels, &e->win_cents})
+                      &e->t_unit_off, &e->t_sums, &e->t_witems, &e->nm, &e->ncount, &e->cflags, &e->plen, &e->gaps, &e->gap_count, &e->unit_totals, &e->next_unit, &e->win_stride, &e->win_off, &e->win_labels, &e->win_cents})
         b->release();
     for (auto &ev : e->ev) cudaEventDestroy(ev);
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -805,6 +946,17 @@ int mgc_result_model_cents(const mgc_result *r, int64_t *cents) {
     return MGC_OK;
 }
 
+int32_t mgc_result_min_gene_length(const mgc_result *r, int model) {
+    if (!r || model < 0 || model >= r->n_models) return mgc::set_error(MGC_E_ARG, "model index out of range");
+    return r->min_len[model];
+}
+
+int mgc_result_set_min_gene_length(mgc_result *r, int model, int32_t min_len) {
+    if (!r || model < 0 || model >= r->n_models || min_len < 0) return mgc::set_error(MGC_E_ARG, "bad argument");
+    r->min_len[model] = min_len;
+    return MGC_OK;
+}
+
 void mgc_result_free(mgc_result *r) { delete r; }
 
 int mgc_result_create(int n_models, int32_t n_contigs, const mgc_gene *const *genes, const int64_t *counts,
@@ -825,6 +977,7 @@ int mgc_result_create(int n_models, int32_t n_contigs, const mgc_gene *const *ge
         r->gene_blk.push_back(g);
         r->total_blk.push_back(t);
         r->n_genes.push_back(counts[m]);
+        r->min_len.push_back(90);
         long long cents = 0;
         for (int64_t k = 0; k < counts[m]; k++) cents += llrint(genes[m][k].logodd * 100.0);
         r->cents.push_back(cents);
@@ -860,7 +1013,7 @@ int mgc_window_labels(mgc_engine *e, const int32_t *stride, int32_t window, int3
     if (!e->have_genes) return mgc::set_error(MGC_E_ARG, "decode a batch before asking for window labels");
     return guarded([&] {
         CUDA_TRY(cudaSetDevice(e->device));
-        const int32_t n = e->n_contigs;
+        const int32_t n = e->n_parents;
         const int M = e->n_models;
         const int64_t nw = win_offsets[n];
         cudaStream_t st = e->stream;
@@ -870,7 +1023,7 @@ int mgc_window_labels(mgc_engine *e, const int32_t *stride, int32_t window, int3
         e->win_cents.ensure((size_t)std::max<int64_t>(nw, 1) * M * 8);
         CUDA_TRY(cudaMemcpyAsync(e->win_stride.p, stride, (size_t)n * 4, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(e->win_off.p, win_offsets, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
-        launch_windows(e->t_genes.as<const mgc_gene *>(), e->t_gene_off.as<const uint32_t *>(), M, e->clen.as<int32_t>(),
+        launch_windows(e->t_genes.as<const mgc_gene *>(), e->t_gene_off.as<const uint32_t *>(), M, e->plen.as<int32_t>(),
                        e->win_stride.as<int32_t>(), e->win_off.as<int64_t>(), n, window, consecutive, short_contigs,
                        e->win_labels.as<int32_t>(), e->win_cents.as<long long>(), st);
         if (nw) {

@@ -169,6 +169,7 @@ int mgc_write_gff(const mgc_result *r, int model, const char *const *contig_ids,
     if (!lst && std::strcmp(format, "gff") != 0) return mgc::set_error(MGC_E_ARG, "format must be gff or lst");
     const mgc_gene *genes = mgc_result_genes(r, model);
     const double *totals = mgc_result_contig_totals(r, model);
+    const long long min_len = mgc_result_min_gene_length(r, model);
     FILE *f = std::fopen(out_path, "w");
     if (!f) return mgc::set_error(MGC_E_IO, std::string("cannot open output file: ") + out_path);
     const std::string date = now_string();
@@ -210,6 +211,8 @@ int mgc_write_gff(const mgc_result *r, int model, const char *const *contig_ids,
         if (n > 0)
             std::fprintf(f, "# %s\ttotal_logodd\t%g\taverage_length\t%lld\taverage_density\t%.2f\n", id, totals[c], (long long)((double)len_sum / (double)n + 0.5),
                          (double)n / ((double)L / 1000.0));
+        else if (L >= min_len)  // a record the binary decoded without finding a gene; shorter records are skipped outright
+            std::fprintf(f, "# %s\ttotal_logodd\t0\taverage_length\t0\taverage_density\t0.00\n", id);
     }
     if (lst) std::fprintf(f, "\n# output date end: %s\n# Done with file: %s\n", date.c_str(), seq_file_name ? seq_file_name : "");
     if (std::fclose(f) != 0) return mgc::set_error(MGC_E_IO, "write failed");

@@ -54,15 +54,25 @@ __device__ __forceinline__ long long warp_min_ll(long long v) {
     return v;
 }
 
-// number of G/C letters in strand-0 positions [a, b] of contig slot starting at word `w0`
-__device__ __forceinline__ int gc_count_fwd(const uint32_t *lo, const uint32_t *hi, const uint32_t *gcpre, int64_t w0,
-                                            int a, int b) {
-    // pre(x) = number of GC among positions < x
-    int64_t wa = w0 + (a >> 5), wb = w0 + ((b + 1) >> 5);
-    uint32_t ma = (1u << (a & 31)) - 1u, mb = (1u << ((b + 1) & 31)) - 1u;
-    int pa = (int)gcpre[wa] + __popc((lo[wa] ^ hi[wa]) & ma);
-    int pb = (int)gcpre[wb] + __popc((lo[wb] ^ hi[wb]) & mb);
+// 2*(G+C) + (ambiguous letters) over strand-0 positions [a, b] of the contig slot starting at word `w0`; `pre` is the
+// exclusive per-word prefix of the same quantity.  (An ambiguous letter counts as half a G/C in the reference's GC %.)
+__device__ __forceinline__ int gc2_count_fwd(const Planes &pl, const uint32_t *pre, int64_t w0, int a, int b) {
+    const int64_t wa = w0 + (a >> 5), wb = w0 + ((b + 1) >> 5);
+    const uint32_t ma = (1u << (a & 31)) - 1u, mb = (1u << ((b + 1) & 31)) - 1u;
+    int pa = (int)pre[wa] + 2 * __popc((pl.lo[wa] ^ pl.hi[wa]) & ma);
+    int pb = (int)pre[wb] + 2 * __popc((pl.lo[wb] ^ pl.hi[wb]) & mb);
+    if (pl.dflags[1]) {
+        pa += __popc(pl.nm[wa] & ma);
+        pb += __popc(pl.nm[wb] & mb);
+    }
     return pb - pa;
+}
+
+// number of ambiguous letters in strand-0 positions [a, b]
+__device__ __forceinline__ int amb_count_fwd(const Planes &pl, int64_t w0, int a, int b) {
+    const int64_t wa = w0 + (a >> 5), wb = w0 + ((b + 1) >> 5);
+    const uint32_t ma = (1u << (a & 31)) - 1u, mb = (1u << ((b + 1) & 31)) - 1u;
+    return (int)pl.npre[wb] + __popc(pl.nm[wb] & mb) - (int)pl.npre[wa] - __popc(pl.nm[wa] & ma);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -166,30 +176,46 @@ __global__ void k_groups(const int64_t *cwoff, int32_t n_contigs, int64_t n_grou
     grp2contig[g] = lo;
 }
 
-// one warp packs 32 words (1024 letters) of one strand: lane = bit position, ballot = plane word
+// one warp packs 32 words (1024 letters) of one strand: lane = bit position, ballot = plane word.
+// Letters outside ACGT set the ambiguity plane (U included: the reference scores it like N) (their code is 0); letters outside the IUPAC nucleotide alphabet
+// (which the reference rejects: "error, unexpected letter found in FASTA sequence") raise flag 0.
 __global__ void __launch_bounds__(256) k_pack(const char *__restrict__ ascii, const int64_t *__restrict__ aoff,
                                               const int64_t *__restrict__ cwoff, const int32_t *__restrict__ clen,
                                               const int32_t *__restrict__ grp2contig, int64_t W, uint32_t *lo,
-                                              uint32_t *hi, uint32_t *gccount, int *bad_letter) {
+                                              uint32_t *hi, uint32_t *nm, uint32_t *gccount, uint32_t *ncount, int *dflags) {
     int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = lane_id();
     int strand = blockIdx.y;
     int64_t w0 = warp * 32;
     if (w0 >= W) return;
-    uint32_t mylo = 0, myhi = 0, mygc = 0;
-    int bad = 0;
-    auto encode = [&](unsigned char ch, bool valid, uint32_t &code) {
+    uint32_t mylo = 0, myhi = 0, mynm = 0;
+    int bad = 0, amb_any = 0;
+    auto encode = [&](unsigned char ch, bool valid, uint32_t &code, bool &amb) {
         const unsigned char up = ch & 0xDF;  // upper case
-        if (valid && !(up == 'A' || up == 'C' || up == 'G' || up == 'T' || up == 'U')) bad = 1;
-        code = (ch >> 1) & 3u;         // A0 C1 G3 T2 (also U -> 2)
+        amb = false;
+        if (valid && !(up == 'A' || up == 'C' || up == 'G' || up == 'T')) {
+            amb = true;
+            amb_any = 1;
+            // IUPAC: R Y S W K M B D H V N, and U
+            if (!(up == 'N' || up == 'U' || up == 'R' || up == 'Y' || up == 'S' || up == 'W' || up == 'K' || up == 'M' || up == 'B' || up == 'D' ||
+                  up == 'H' || up == 'V'))
+                bad = 1;
+        }
+        code = (ch >> 1) & 3u;         // A0 C1 G3 T2
         code ^= code >> 1;             // A0 C1 G2 T3
         if (strand) code = 3u - code;
-        if (!valid) code = 0;
+        if (!valid || amb) code = 0;
+    };
+    auto emit = [&](int r, uint32_t code, bool valid, bool amb) {
+        const uint32_t bl = __ballot_sync(0xffffffffu, code & 1u);
+        const uint32_t bh = __ballot_sync(0xffffffffu, (code >> 1) & 1u);
+        const uint32_t bn = __ballot_sync(0xffffffffu, valid && amb);
+        if (lane == r) { mylo = bl; myhi = bh; mynm = bn; }
     };
     const int c_first = grp2contig[w0 >> 2];
     const int c_last = w0 + 31 < W ? grp2contig[(w0 + 31) >> 2] : -1;
     if (c_first == c_last) {
-        // all 32 words belong to one contig: one set of contig parameters, 32 independent byte loads in flight
+        // all 32 words belong to one contig: one set of contig parameters, eight independent byte loads in flight
         const int L = clen[c_first];
         const int64_t i0 = (w0 - cwoff[c_first]) * 32 + lane;
         const char *src = ascii + aoff[c_first];
@@ -204,43 +230,41 @@ __global__ void __launch_bounds__(256) k_pack(const char *__restrict__ ascii, co
             for (int r = 0; r < 8; r++) {
                 const bool valid = i0 + (r0 + r) * 32 < L;
                 uint32_t code;
-                encode(chs[r], valid, code);
-                const uint32_t bl = __ballot_sync(0xffffffffu, code & 1u);
-                const uint32_t bh = __ballot_sync(0xffffffffu, (code >> 1) & 1u);
-                const uint32_t bv = __ballot_sync(0xffffffffu, valid);
-                if (lane == r0 + r) { mylo = bl; myhi = bh; mygc = __popc((bl ^ bh) & bv); }
+                bool amb;
+                encode(chs[r], valid, code, amb);
+                emit(r0 + r, code, valid, amb);
             }
         }
     } else {
         for (int r = 0; r < 32; r++) {
             int64_t w = w0 + r;
             uint32_t code = 0;
-            bool valid = false;
+            bool valid = false, amb = false;
             if (w < W) {
                 int c = grp2contig[w >> 2];
                 int L = clen[c];
                 int64_t i = (w - cwoff[c]) * 32 + lane;
                 if (i < L) {
                     valid = true;
-                    encode((unsigned char)ascii[aoff[c] + (strand ? (L - 1 - i) : i)], true, code);
+                    encode((unsigned char)ascii[aoff[c] + (strand ? (L - 1 - i) : i)], true, code, amb);
                 }
             }
-            uint32_t bl = __ballot_sync(0xffffffffu, code & 1u);
-            uint32_t bh = __ballot_sync(0xffffffffu, (code >> 1) & 1u);
-            uint32_t bv = __ballot_sync(0xffffffffu, valid);
-            if (lane == r) {
-                mylo = bl;
-                myhi = bh;
-                mygc = __popc((bl ^ bh) & bv);
-            }
+            emit(r, code, valid, amb);
         }
     }
     if (w0 + lane < W) {
         lo[(int64_t)strand * W + w0 + lane] = mylo;
         hi[(int64_t)strand * W + w0 + lane] = myhi;
-        if (!strand) gccount[w0 + lane] = mygc;
+        nm[(int64_t)strand * W + w0 + lane] = mynm;
+        if (!strand) {
+            gccount[w0 + lane] = 2u * __popc(mylo ^ myhi) + __popc(mynm);  // padding letters are A (code 0): they count nothing
+            ncount[w0 + lane] = __popc(mynm);
+        }
     }
-    if (!strand && __any_sync(0xffffffffu, bad) && lane == 0) atomicOr(bad_letter, 1);
+    if (!strand) {
+        if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&dflags[0], 1);
+        if (__any_sync(0xffffffffu, amb_any) && lane == 0) atomicOr(&dflags[1], 1);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -250,6 +274,7 @@ __global__ void __launch_bounds__(256) k_pack(const char *__restrict__ ascii, co
 // ------------------------------------------------------------------------------------------------
 struct FindCtx {
     const uint32_t *lo, *hi;  // planes of the strand region, contig slot
+    const uint32_t *nm;       // ambiguity mask of the same slot, nullptr when the batch has no ambiguous letter
     int L;                    // contig length
     int stop_sel, atg_only;
 };
@@ -259,6 +284,10 @@ __device__ __forceinline__ CodonMasks masks_at(const FindCtx &cx, int w) {
     // codon start positions must satisfy i <= L-3
     int last = cx.L - 3 - 32 * w;
     uint32_t valid = last < 0 ? 0u : (last >= 31 ? 0xffffffffu : ((1u << (last + 1)) - 1u));
+    if (cx.nm) {  // a codon with an ambiguous letter is neither a start nor a stop
+        const uint32_t n0 = cx.nm[w], n1 = cx.nm[w + 1];
+        valid &= ~(n0 | __funnelshift_r(n0, n1, 1) | __funnelshift_r(n0, n1, 2));
+    }
     m.start &= valid; m.taa &= valid; m.tag &= valid; m.tga &= valid;
     return m;
 }
@@ -293,6 +322,7 @@ __global__ void __launch_bounds__(LS_THREADS) k_laststop_tiles(Planes pl, const 
             FindCtx cx;
             cx.lo = pl.lo + (int64_t)strand * pl.W + cwoff[c];
             cx.hi = pl.hi + (int64_t)strand * pl.W + cwoff[c];
+        cx.nm = pl.dflags[1] ? pl.nm + (int64_t)strand * pl.W + cwoff[c] : nullptr;
             cx.L = L; cx.stop_sel = models[mi].stop_sel; cx.atg_only = models[mi].atg_only;
             const uint32_t sm = stop_mask(masks_at(cx, wl), cx.stop_sel);
             const uint32_t P0 = (uint32_t)(w * 32);
@@ -367,7 +397,7 @@ __global__ void __launch_bounds__(1024) k_laststop_sums(uint32_t *const *ls_tile
 // ------------------------------------------------------------------------------------------------
 // Builds the record of the ORF ending at stop position t if it can hold a start codon; false otherwise.
 __device__ __forceinline__ bool make_orf(const FindCtx &cx, const DevModel &dm, int contig, int strand, int t, bool virt,
-                                         int p_prev /* local, < 0 = none in this contig */, OrfRec &rec) {
+                                         int p_prev /* local, < 0 = none in this contig */, bool right_is_record_end, OrfRec &rec) {
     const int f = t % 3;
     const int s_hi = min(t - 3, t + 3 - dm.min_len);
     const bool open_left = p_prev < 0;
@@ -385,7 +415,9 @@ __device__ __forceinline__ bool make_orf(const FindCtx &cx, const DevModel &dm, 
         if (!any && (s_hi >> 5) <= w_end) return false;
     }
     rec.contig = contig; rec.t = t; rec.s_lo = s_lo; rec.base = 0; rec.n = 0;
-    rec.sf = (uint32_t)strand | (open_left ? 2u : 0u) | (virt ? 0x100u : 0u);
+    // the strand's left edge is the forward right edge for the reverse strand
+    const bool from_first = open_left && !(strand == 1 && right_is_record_end);
+    rec.sf = (uint32_t)strand | (open_left ? 2u : 0u) | (virt ? 0x100u : 0u) | (from_first ? 0x200u : 0u);
     return true;
 }
 
@@ -420,8 +452,10 @@ __global__ void __launch_bounds__(128) k_orf_find(Planes pl, const int64_t *__re
             FindCtx cx;
             cx.lo = pl.lo + (int64_t)strand * pl.W + cwoff[c];
             cx.hi = pl.hi + (int64_t)strand * pl.W + cwoff[c];
+        cx.nm = pl.dflags[1] ? pl.nm + (int64_t)strand * pl.W + cwoff[c] : nullptr;
             cx.L = L; cx.stop_sel = dm.stop_sel; cx.atg_only = dm.atg_only;
             const uint32_t *ls = ls_m[mi];
+            const bool right_end = (pl.cflags[c] & 1) != 0;
             const uint32_t P0 = (uint32_t)(w * 32);                      // slot-space position of bit 0
             const uint32_t Pc = (uint32_t)(((int64_t)strand * pl.W + cwoff[c]) * 32);  // ... of the contig's first letter
             const uint32_t all = stop_mask(masks_at(cx, wl), cx.stop_sel);
@@ -444,14 +478,14 @@ __global__ void __launch_bounds__(128) k_orf_find(Planes pl, const int64_t *__re
             while (sm) {
                 const int b = __ffs(sm) - 1;
                 sm &= sm - 1;
-                if (make_orf(cx, dm, c, strand, wl * 32 + b, false, prev_local(b), r)) push(r);
+                if (make_orf(cx, dm, c, strand, wl * 32 + b, false, prev_local(b), right_end, r)) push(r);
             }
             // right edge: in each frame the last full codon closes an open ORF unless it is a real stop
             for (int f = 0; f < 3; f++) {
                 const int tv = L - 3 - ((L - 3 - f) % 3 + 3) % 3;  // largest t <= L-3 with t % 3 == f
                 if (tv < 0 || (tv >> 5) != wl) continue;
                 if ((all >> (tv & 31)) & 1u) continue;
-                if (make_orf(cx, dm, c, strand, tv, true, prev_local(tv & 31), r)) push(r);
+                if (make_orf(cx, dm, c, strand, tv, true, prev_local(tv & 31), right_end, r)) push(r);
             }
         }
     }
@@ -527,6 +561,7 @@ __global__ void __launch_bounds__(128) k_orf_count(Planes pl, const int64_t *__r
         FindCtx cx;
         cx.lo = pl.lo + (int64_t)strand * pl.W + w0;
         cx.hi = pl.hi + (int64_t)strand * pl.W + w0;
+        cx.nm = pl.dflags[1] ? pl.nm + (int64_t)strand * pl.W + w0 : nullptr;
         cx.L = has ? clen[rec.contig] : 0; cx.stop_sel = dm.stop_sel; cx.atg_only = dm.atg_only;
         const int f = t % 3;
         const int s_lo = rec.s_lo, s_hi = has ? min(t - 3, t + 3 - dm.min_len) : 0;
@@ -576,6 +611,7 @@ __global__ void __launch_bounds__(256) k_orf_starts(Planes pl, const uint32_t *_
         FindCtx cx;
         cx.lo = pl.lo + (int64_t)strand * pl.W + w0;
         cx.hi = pl.hi + (int64_t)strand * pl.W + w0;
+        cx.nm = pl.dflags[1] ? pl.nm + (int64_t)strand * pl.W + w0 : nullptr;
         cx.L = L; cx.stop_sel = dm.stop_sel; cx.atg_only = dm.atg_only;
         const int f = t % 3;
         const int s_lo = rec.s_lo, s_hi = min(t - 3, t + 3 - dm.min_len);
@@ -584,8 +620,8 @@ __global__ void __launch_bounds__(256) k_orf_starts(Planes pl, const uint32_t *_
         auto put = [&](int s, bool virt) {
             const int len = t + 3 - s;
             const int a = strand ? (L - 1 - (t + 2)) : s, b = strand ? (L - 1 - s) : (t + 2);
-            const int gcn = gc_count_fwd(pl.lo, pl.hi, gcpre, w0, a, b);
-            const int gc = (200 * gcn + len) / (2 * len);
+            const int gc2 = gc2_count_fwd(pl, gcpre, w0, a, b);
+            const int gc = (100 * gc2 + len) / (2 * len);   // round half up of 100 * (GC + N/2) / len
             StartRec sr;
             sr.sraw = (uint32_t)s | (virt ? 0x80000000u : 0u);
             sr.orf = wi.orf;
@@ -609,7 +645,8 @@ __global__ void __launch_bounds__(256) k_orf_starts(Planes pl, const uint32_t *_
 }
 
 // prep 3: thread per ORF — chains the starts of equal section pair (ascending position) and emits one walk item per chain
-__global__ void __launch_bounds__(128) k_orf_link(const DevModel *__restrict__ models, const OrfRec *const *orfs_m,
+__global__ void __launch_bounds__(128) k_orf_link(Planes pl, const int64_t *__restrict__ cwoff, const int32_t *__restrict__ clen,
+                                                  const DevModel *__restrict__ models, const OrfRec *const *orfs_m,
                                                   StartRec *const *starts_m, ItemRec *const *items_m, uint32_t *const *hist_m,
                                                   unsigned long long *counters_m, uint32_t cap_orf, uint32_t cap_items) {
     const int mi = blockIdx.y;
@@ -627,9 +664,13 @@ __global__ void __launch_bounds__(128) k_orf_link(const DevModel *__restrict__ m
     for (int64_t o0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~31LL; o0 < (int64_t)n_orfs; o0 += stride) {
         const int64_t oi = o0 + lane;
         OrfRec rec;
-        rec.n = 0; rec.t = 0; rec.sf = 0; rec.base = 0;
+        rec.n = 0; rec.t = 0; rec.sf = 0; rec.base = 0; rec.contig = 0;
         if (oi < (int64_t)n_orfs) rec = orfs[oi];
         const int t = rec.t, strand = rec.sf & 1;
+        const bool from_first = (rec.sf & 0x200u) != 0;
+        const bool amb = pl.dflags[1] != 0;
+        const int Lc = amb && oi < (int64_t)n_orfs ? clen[rec.contig] : 0;
+        const int64_t w0c = amb && oi < (int64_t)n_orfs ? cwoff[rec.contig] : 0;
         constexpr int NSLOT = 6, NPEND = 10;
         int sl_pair[NSLOT], sl_lo[NSLOT], sl_last[NSLOT];
 #pragma unroll
@@ -641,6 +682,11 @@ __global__ void __launch_bounds__(128) k_orf_link(const DevModel *__restrict__ m
             const int ext = t - sl_lo[q];
             ItemRec it;
             it.orf = (uint32_t)oi;
+            if (amb) {  // does the walk [lo_pos - kc, t - 1] touch an ambiguous letter?  (bit 31 of orf selects the careful loop)
+                const int a = sl_lo[q] - kc, b = t - 1;
+                const int na = strand ? amb_count_fwd(pl, w0c, Lc - 1 - b, Lc - 1 - a) : amb_count_fwd(pl, w0c, a, b);
+                if (na) it.orf |= 0x80000000u;
+            }
             it.lo_pos = sl_lo[q];
             it.key = (uint32_t)(sl_pair[q] * WALK_CLASSES + (WALK_CLASSES - 1 - min(ext >> 5, WALK_CLASSES - 1)));
             it.last = sl_last[q];
@@ -657,7 +703,7 @@ __global__ void __launch_bounds__(128) k_orf_link(const DevModel *__restrict__ m
         for (int j = 0; j < (int)rec.n; j++) {
             const uint32_t sraw = st[j].sraw;
             const int pair = (int)(st[j].pg & 0xffffu);
-            const int fullstart = (int)(sraw & 0x7fffffffu) + (((sraw >> 31) && strand == 0) ? 0 : 3) + kc;
+            const int fullstart = (int)(sraw & 0x7fffffffu) + (((sraw >> 31) && from_first) ? 0 : 3) + kc;
             if (fullstart > t - 1) continue;  // no full-order region: not part of any walk
             int q = -1;
 #pragma unroll
@@ -807,6 +853,9 @@ __global__ void __launch_bounds__(WALK_UNIT, 2) k_walk(Planes pl, const int64_t 
         const double2 *tc = SMEM_TABLE ? tbl : gq;
         const double2 *tn = tc + (size_t)3 * nfull * 2;
         const uint32_t rep2 = (uint32_t)(lane & 1) << 2, rep8 = (uint32_t)(lane & 7);
+        // constant terms of windows with an ambiguous letter, per domain of this pair
+        const double2 amb_c = make_double2(dm.pair_amb[pair * 4 + 0], dm.pair_amb[pair * 4 + 1]);
+        const double2 amb_n = make_double2(dm.pair_amb[pair * 4 + 2], dm.pair_amb[pair * 4 + 3]);
         const int nsh = kc - kn;
         const uint32_t wmask = (1u << (kc + 1)) - 1u;
         const uint32_t end = s_end;
@@ -818,8 +867,10 @@ __global__ void __launch_bounds__(WALK_UNIT, 2) k_walk(Planes pl, const int64_t 
             if (w_first >= end) break;
             if (w_first + lane < end) {
                 const ItemRec it = items[w_first + lane];
-                const OrfRec rec = orfs_m[mi][it.orf];
+                const bool careful = (it.orf >> 31) != 0;   // the walk touches an ambiguous letter
+                const OrfRec rec = orfs_m[mi][it.orf & 0x7fffffffu];
                 const int t = rec.t, strand = rec.sf & 1;
+                const bool from_first = (rec.sf & 0x200u) != 0;
                 const uint32_t *lo = pl.lo + (int64_t)strand * pl.W + cwoff[rec.contig];
                 const uint32_t *hi = pl.hi + (int64_t)strand * pl.W + cwoff[rec.contig];
                 const StartRec *st = starts_m[mi] + rec.base;
@@ -828,7 +879,7 @@ __global__ void __launch_bounds__(WALK_UNIT, 2) k_walk(Planes pl, const int64_t 
                 int j = it.last;
                 StartRec cur = st[j];
                 auto full_of = [&](const StartRec &sr) {
-                    return (int)(sr.sraw & 0x7fffffffu) + (((sr.sraw >> 31) && strand == 0) ? 0 : 3) + kc;
+                    return (int)(sr.sraw & 0x7fffffffu) + (((sr.sraw >> 31) && from_first) ? 0 : 3) + kc;
                 };
                 int target = full_of(cur);
                 StartRec nxt = cur;
@@ -843,16 +894,35 @@ __global__ void __launch_bounds__(WALK_UNIT, 2) k_walk(Planes pl, const int64_t 
                 while (i >= lo_pos) {
                     // a run ends at the next target, at lo_pos, or where the window start leaves the current plane word
                     const int run = min(i - max(target, lo_pos) + 1, sh + 1);
-                    for (int r = 0; r < run; r++) {
-                        const uint32_t lb = __funnelshift_r(l0, l1, sh) & wmask;
-                        const uint32_t hb = __funnelshift_r(h0, h1, sh) & wmask;
-                        const uint32_t e = (uint32_t)(ph * nfull) + ((hb << (kc + 1)) | lb);
-                        const uint32_t idn = ((hb >> nsh) << (kn + 1)) | (lb >> nsh);
-                        const double2 c2 = tc[((e & ~3u) << 1) | (e & 3u) | rep2];
-                        const double2 n2 = tn[(idn << 3) | rep8];
-                        acc.cB += c2.x; acc.cA += c2.y; acc.oB += n2.x; acc.oA += n2.y;   // oB/oA hold the non-coding sums here
-                        sh--;
-                        ph = ph == 0 ? 2 : ph - 1;
+                    if (!careful) {
+                        for (int r = 0; r < run; r++) {
+                            const uint32_t lb = __funnelshift_r(l0, l1, sh) & wmask;
+                            const uint32_t hb = __funnelshift_r(h0, h1, sh) & wmask;
+                            const uint32_t e = (uint32_t)(ph * nfull) + ((hb << (kc + 1)) | lb);
+                            const uint32_t idn = ((hb >> nsh) << (kn + 1)) | (lb >> nsh);
+                            const double2 c2 = tc[((e & ~3u) << 1) | (e & 3u) | rep2];
+                            const double2 n2 = tn[(idn << 3) | rep8];
+                            acc.cB += c2.x; acc.cA += c2.y; acc.oB += n2.x; acc.oA += n2.y;   // oB/oA hold the non-coding sums here
+                            sh--;
+                            ph = ph == 0 ? 2 : ph - 1;
+                        }
+                    } else {
+                        // a window with an ambiguous letter contributes ln COD_P_N to the coding side and ln NON_P_N to the
+                        // non-coding side of each domain (so ln(COD_P_N / NON_P_N) to the log-odds)
+                        const uint32_t *nmp = pl.nm + (int64_t)strand * pl.W + cwoff[rec.contig];
+                        const uint32_t a0 = nmp[w], a1 = nmp[w + 1];
+                        for (int r = 0; r < run; r++) {
+                            const uint32_t lb = __funnelshift_r(l0, l1, sh) & wmask;
+                            const uint32_t hb = __funnelshift_r(h0, h1, sh) & wmask;
+                            const uint32_t e = (uint32_t)(ph * nfull) + ((hb << (kc + 1)) | lb);
+                            const uint32_t idn = ((hb >> nsh) << (kn + 1)) | (lb >> nsh);
+                            double2 c2 = tc[((e & ~3u) << 1) | (e & 3u) | rep2];
+                            double2 n2 = tn[(idn << 3) | rep8];
+                            if (__funnelshift_r(a0, a1, sh) & wmask) { c2 = amb_c; n2 = amb_n; }
+                            acc.cB += c2.x; acc.cA += c2.y; acc.oB += n2.x; acc.oA += n2.y;
+                            sh--;
+                            ph = ph == 0 ? 2 : ph - 1;
+                        }
                     }
                     i -= run;
                     if (sh < 0 && w > 0) {
@@ -926,18 +996,27 @@ __global__ void __launch_bounds__(256) k_final(Planes pl, const int64_t *__restr
             const int len = t + 3 - s;
             const int gc = (int)(sr.pg >> 16), pair = (int)(sr.pg & 0xffffu);
             const int secB = dm.map[0][gc], secA = dm.map[1][gc];
-            const int first = s + ((virt && strand == 0) ? 0 : 3);
+            const int first = s + ((virt && (rec.sf & 0x200u)) ? 0 : 3);
             const int fullstart = first + kc;
             Acc4 acc = {0, 0, 0, 0};
             if (fullstart <= t - 1) acc = sums[k];
+            const uint32_t *nmp = pl.dflags[1] ? pl.nm + (int64_t)strand * pl.W + w0 : nullptr;
             // order ramp: orders 0..kc-1 at positions first .. first+kc-1 (window starts on a codon boundary)
             const Quad *rq = dm.rquad + (size_t)pair * dm.kr * nramp;
             for (int j = 0; j < kc && first + j <= t - 1; j++) {
                 uint32_t hb, lb;
                 window_bits(lo, hi, first, j + 1, hb, lb);
                 const Quad *q = rq + (size_t)j * nramp + ((hb << (j + 1)) | lb);
-                const double2 x = __ldg(reinterpret_cast<const double2 *>(q));
-                const double2 y = __ldg(reinterpret_cast<const double2 *>(q) + 1);
+                double2 x = __ldg(reinterpret_cast<const double2 *>(q));
+                double2 y = __ldg(reinterpret_cast<const double2 *>(q) + 1);
+                if (nmp) {
+                    uint32_t nb_, dummy;
+                    window_bits(nmp, nmp, first, j + 1, nb_, dummy);
+                    if (nb_) {   // ambiguous letter in the ramp window: constant terms
+                        x = make_double2(dm.pair_amb[pair * 4 + 0], dm.pair_amb[pair * 4 + 0] - dm.pair_amb[pair * 4 + 2]);
+                        y = make_double2(dm.pair_amb[pair * 4 + 1], dm.pair_amb[pair * 4 + 1] - dm.pair_amb[pair * 4 + 3]);
+                    }
+                }
                 acc.cB += x.x; acc.oB += x.y; acc.cA += y.x; acc.oA += y.y;
             }
             if (secB >= 0 || secA >= 0) {
@@ -1493,6 +1572,43 @@ void launch_merge_labels(const int32_t *labels, const int64_t *win_off, int32_t 
 }
 
 // ------------------------------------------------------------------------------------------------
+// runs of >= min_run ambiguous letters per contig (only launched when the batch has ambiguous letters)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_find_gaps(const uint32_t *__restrict__ nm, const int64_t *__restrict__ cwoff,
+                                                   const int32_t *__restrict__ clen, int32_t n_contigs, int min_run, int32_t *gaps,
+                                                   unsigned int *gap_count, unsigned int cap) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_contigs) return;
+    const uint32_t *m = nm + cwoff[c];
+    const int L = clen[c];
+    int run = 0;
+    auto close = [&](int end) {  // a run of `run` letters ended just before position `end`
+        if (run >= min_run) {
+            const unsigned int k = atomicAdd(gap_count, 1u);
+            if (k < cap) { gaps[k * 3] = c; gaps[k * 3 + 1] = end - run; gaps[k * 3 + 2] = run; }
+        }
+        run = 0;
+    };
+    const int nwords = (L + 31) >> 5;
+    for (int w = 0; w < nwords; w++) {
+        const uint32_t x = m[w];
+        const int nb = min(32, L - 32 * w);
+        if (x == 0u) { if (run) close(32 * w); continue; }
+        if (nb == 32 && x == 0xffffffffu) { run += 32; continue; }
+        for (int b = 0; b < nb; b++) {
+            if ((x >> b) & 1u) run++;
+            else if (run) close(32 * w + b);
+        }
+    }
+    if (run) close(L);
+}
+
+void launch_find_gaps(const uint32_t *nm, const int64_t *cwoff, const int32_t *clen, int32_t n_contigs, int min_run, int32_t *gaps,
+                      unsigned int *gap_count, unsigned int cap, cudaStream_t st) {
+    k_find_gaps<<<(unsigned)((n_contigs + 127) / 128), 128, 0, st>>>(nm, cwoff, clen, n_contigs, min_run, gaps, gap_count, cap);
+}
+
+// ------------------------------------------------------------------------------------------------
 // host-callable launch wrappers (keep <<< >>> in this translation unit)
 // ------------------------------------------------------------------------------------------------
 void launch_groups(const int64_t *cwoff, int32_t n_contigs, int64_t n_groups, int32_t *grp2contig, cudaStream_t st) {
@@ -1500,10 +1616,11 @@ void launch_groups(const int64_t *cwoff, int32_t n_contigs, int64_t n_groups, in
 }
 
 void launch_pack(const char *ascii, const int64_t *aoff, const int64_t *cwoff, const int32_t *clen, const int32_t *grp2contig,
-                 int64_t W, uint32_t *lo, uint32_t *hi, uint32_t *gccount, int *bad_letter, cudaStream_t st) {
+                 int64_t W, uint32_t *lo, uint32_t *hi, uint32_t *nm, uint32_t *gccount, uint32_t *ncount, int *dflags,
+                 cudaStream_t st) {
     int64_t warps = (W + 31) / 32;
     dim3 grid((unsigned)((warps + 7) / 8), 2);
-    k_pack<<<grid, 256, 0, st>>>(ascii, aoff, cwoff, clen, grp2contig, W, lo, hi, gccount, bad_letter);
+    k_pack<<<grid, 256, 0, st>>>(ascii, aoff, cwoff, clen, grp2contig, W, lo, hi, nm, gccount, ncount, dflags);
 }
 
 int launch_laststop(Planes pl, const int64_t *cwoff, const int32_t *clen, const int32_t *grp2contig, const DevModel *models,
@@ -1530,7 +1647,7 @@ int launch_orf_prep(Planes pl, const uint32_t *gcpre, const int64_t *cwoff, cons
     k_orf_count<<<grid, 128, 0, st>>>(pl, cwoff, clen, models, orfs_m, witems_m, counters_m, bufs_m, cap_orf, cap_starts, cap_witems);
     dim3 grid2(n_sm * 8, n_models);
     k_orf_starts<<<grid2, 256, 0, st>>>(pl, gcpre, cwoff, clen, models, orfs_m, witems_m, starts_m, counters_m, cap_witems);
-    k_orf_link<<<grid, 128, 0, st>>>(models, orfs_m, starts_m, items_m, hist_m, counters_m, cap_orf, cap_items);
+    k_orf_link<<<grid, 128, 0, st>>>(pl, cwoff, clen, models, orfs_m, starts_m, items_m, hist_m, counters_m, cap_orf, cap_items);
     return 3;
 }
 

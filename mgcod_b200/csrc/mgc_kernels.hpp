@@ -20,7 +20,10 @@ int launch_exclusive_scan(const uint32_t *in, uint32_t *out, uint32_t *tile_sums
                           cudaStream_t st);
 void launch_groups(const int64_t *cwoff, int32_t n_contigs, int64_t n_groups, int32_t *grp2contig, cudaStream_t st);
 void launch_pack(const char *ascii, const int64_t *aoff, const int64_t *cwoff, const int32_t *clen, const int32_t *grp2contig,
-                 int64_t W, uint32_t *lo, uint32_t *hi, uint32_t *gccount, int *bad_letter, cudaStream_t st);
+                 int64_t W, uint32_t *lo, uint32_t *hi, uint32_t *nm, uint32_t *gccount, uint32_t *ncount, int *dflags,
+                 cudaStream_t st);
+void launch_find_gaps(const uint32_t *nm, const int64_t *cwoff, const int32_t *clen, int32_t n_contigs, int min_run, int32_t *gaps,
+                      unsigned int *gap_count, unsigned int cap, cudaStream_t st);
 int launch_laststop(Planes pl, const int64_t *cwoff, const int32_t *clen, const int32_t *grp2contig, const DevModel *models,
                     int n_models, uint32_t *const *ls_m, uint32_t *const *ls_tile_m, cudaStream_t st);
 void launch_orf_find(Planes pl, const int64_t *cwoff, const int32_t *clen, const int32_t *grp2contig, const DevModel *models,

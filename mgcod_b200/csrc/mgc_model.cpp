@@ -241,7 +241,7 @@ Model parse_model_file(const std::string &path) {
             sc.stop_lo[t] = std::log(opt(s, stop_key[t], 0.0) / non_codon(stop_codon[t]));
         }
         sc.ln_pn = std::log(need(s, "COD_P_N") / need(s, "NON_P_N"));
-        sc.pad = 0;
+        sc.ln_cpn = std::log(need(s, "COD_P_N"));
     }
     // a section serves the GC values up to its label: missing bin -> next higher provided; above all -> highest
     for (int d = 0; d < 2; d++) {

@@ -19,7 +19,7 @@ struct SectionScalars {
     double start_lo[3];     // ln(P(ATG|GTG|TTG) / Pnon(codon))
     double stop_lo[3];      // ln(P(TAA|TAG|TGA) / Pnon(codon))
     double ln_pn;           // ln($COD_P_N / $NON_P_N)
-    double pad;
+    double ln_cpn;          // ln($COD_P_N)
 };
 
 // One parsed file.  Section slots are numbered 0..nsec-1 in the order (domain, gc).

@@ -8,7 +8,7 @@ whole batches of contigs under all of them in one call.
 from __future__ import annotations
 
 import ctypes as C
-from typing import Sequence
+from typing import Optional, Sequence
 
 import numpy as np
 
@@ -72,8 +72,10 @@ class Result:
         self.n_contigs = n_contigs
 
     @classmethod
-    def from_genes(cls, genes_per_model: Sequence[np.ndarray], totals_per_model: Sequence[np.ndarray]) -> "Result":
-        """Host-only result (no GPU), e.g. from cached GFF files; arrays of GENE_DTYPE ordered by (contig, left)."""
+    def from_genes(cls, genes_per_model: Sequence[np.ndarray], totals_per_model: Sequence[np.ndarray],
+                   min_gene_length: Optional[Sequence[int]] = None) -> "Result":
+        """Host-only result (no GPU), e.g. from cached GFF files; arrays of GENE_DTYPE ordered by (contig, left).
+        min_gene_length: $GENE_MIN_LENGTH per model (default 90), only used by write() for gene-less records."""
         M = len(genes_per_model)
         gs = [np.ascontiguousarray(g, dtype=GENE_DTYPE) for g in genes_per_model]
         ts = [np.ascontiguousarray(t, dtype=np.float64) for t in totals_per_model]
@@ -83,6 +85,8 @@ class Result:
         counts = (C.c_int64 * M)(*[len(g) for g in gs])
         h = C.c_void_p()
         _check(_lib.lib().mgc_result_create(M, n_contigs, gp, counts, tp, C.byref(h)))
+        for m, v in enumerate(min_gene_length or ()):
+            _check(_lib.lib().mgc_result_set_min_gene_length(h, m, int(v)))
         return cls(h, M, n_contigs)
 
     def genes(self, model: int) -> np.ndarray:

@@ -46,3 +46,55 @@ def test_genes_match_oracle(engine, oracles):
         np.testing.assert_allclose(res.contig_totals(mi), totals, rtol=1e-9, atol=1e-9)
         cents = sum(int(round(r[4] * 100)) for r in rows)
         assert res.model_cents()[mi] == cents
+
+
+def _sprinkle(seqs, seed):
+    """ambiguous letters into clean contigs: singles, short runs, and runs of 39..300 (>= 40 splits the record)"""
+    import random
+    rng = random.Random(seed)
+    out = []
+    for s in seqs:
+        s = bytearray(s)
+        L = len(s)
+        for _ in range(rng.choice([0, 1, 3, 10, 30])):
+            a = rng.randrange(0, L)
+            n = rng.choice([1, 1, 1, 2, 5, 20, 39, 40, 41, 100, 300])
+            for i in range(a, min(L, a + n)):
+                s[i] = rng.choice(b"NNNNRYKMSWBDHVnU")
+        if rng.random() < 0.15:
+            s[:50] = b"N" * min(50, L)
+        if rng.random() < 0.15:
+            s[-45:] = b"N" * min(45, L)
+        out.append(bytes(s))
+    return out
+
+
+@pytest.mark.parametrize("seed", [3, 4])
+def test_ambiguous_letters_and_gaps_match_oracle(engine, oracles, seed):
+    buf, offs, seqs = _synthetic(30 + seed, 250000)
+    seqs = _sprinkle(seqs, seed)
+    res = engine.decode(seqs)
+    assert res.n_contigs == len(seqs)
+    for mi, orc in enumerate(oracles):
+        rows, totals = parity.oracle_genes(orc, seqs)
+        diffs = parity.compare_genes(res.genes(mi), rows)
+        assert not diffs, f"model {CODES[mi]}: " + "; ".join(diffs[:6])
+        np.testing.assert_allclose(res.contig_totals(mi), totals, rtol=1e-9, atol=1e-9)
+        assert res.model_cents()[mi] == sum(int(round(r[4] * 100)) for r in rows)
+    # the window kernel sees the caller's records, not the gap-free pieces
+    lens = np.array([len(s) for s in seqs], np.int64)
+    w = 5000
+    offs_w, labels, cents = engine.window_labels(lens, np.full(len(lens), w, np.int32), w, 1, True)
+    assert len(offs_w) == len(seqs) + 1
+    for mi in range(len(CODES)):
+        g = res.genes(mi)
+        per_contig = np.bincount(g["contig"], weights=np.rint(g["logodd"] * 100), minlength=len(lens)).astype(np.int64)
+        wsum = np.add.reduceat(cents[:, mi], offs_w[:-1])
+        long_enough = lens > w
+        # non-overlapping windows partition a record's genes (the spanning-gene fallback can only add to empty windows)
+        assert (wsum[long_enough] >= per_contig[long_enough]).all()
+        assert (wsum[long_enough] - per_contig[long_enough]).sum() <= 0.05 * max(per_contig.sum(), 1)
+    # a second decode of the resident (re-slotted) batch gives the same genes
+    res2 = engine.decode_resident()
+    for mi in range(len(CODES)):
+        assert np.array_equal(res.genes(mi), res2.genes(mi))

@@ -14,12 +14,16 @@ def engine(model_dir):
     e.close()
 
 
-def test_ambiguous_letters_are_rejected_loudly(engine):
+def test_letters_outside_the_iupac_alphabet_are_rejected_loudly(engine):
+    """gmhmmp2: "error, unexpected letter found in FASTA sequence" for anything but ACGTU + RYSWKMBDHVN"""
     from mgcod_b200 import _lib
     from mgcod_b200.engine import MgcodError
-    with pytest.raises(MgcodError) as e:
-        engine.decode(["ACGT" * 100 + "N" + "ACGT" * 100])
-    assert e.value.code == _lib.MGC_E_ALPHABET
+    for bad in ("X", "-", "*", "1", "E"):
+        with pytest.raises(MgcodError) as e:
+            engine.decode(["ACGT" * 100 + bad + "ACGT" * 100])
+        assert e.value.code == _lib.MGC_E_ALPHABET
+        assert "unexpected letter" in str(e.value)
+    engine.decode(["ACGT" * 100 + "NRYSWKMBDHVUnryswkmbdhvu" + "ACGT" * 100])   # accepted
 
 
 def test_tiny_and_empty_contigs(engine):

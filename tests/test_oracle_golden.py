@@ -68,3 +68,23 @@ def test_odd_records(tmpdir):
         golden = fx.xz_text(f"odd_code4.{fmt}.xz")
         sf, mf = _golden_header_names(golden)
         assert _written(res, 0, [i for i, _ in recs], [len(s) for _, s in recs], sf, mf, 4, tmpdir, fmt) == golden
+
+
+AMB_MODELS = {"code4": ("odd_model_code4.mod.xz", 4), "trained11": ("trained/mgm_11.mod.xz", 11),
+              "trained101": ("trained/mgm_101.mod.xz", 101)}
+
+
+@pytest.mark.parametrize("tag", sorted(AMB_MODELS))
+def test_ambiguous_letters_and_gaps(tag, tmpdir):
+    """IUPAC letters, U, lower-case n, runs of 39/40/41/700 ambiguous letters, gaps at either record end and a record
+    of nothing but N (tests/golden/make_golden_amb.py): constant window terms, half-GC counting, record splitting."""
+    from mgcod_b200.engine import Result
+    from oracle import gmhmm
+    rel, code = AMB_MODELS[tag]
+    recs = fx.parse_fasta_text(fx.xz_text("amb_input.fa.xz"))
+    mp = fx.write_xz(rel, os.path.join(tmpdir, f"amb_{tag}.mod"))
+    genes, totals = fx.genes_array_from_oracle(gmhmm.Model(mp), [s for _, s in recs])
+    res = Result.from_genes([genes], [totals])
+    golden = fx.xz_text(f"amb_{tag}.gff.xz")
+    sf, mf = _golden_header_names(golden)
+    assert _written(res, 0, [i for i, _ in recs], [len(s) for _, s in recs], sf, mf, code, tmpdir, "gff") == golden
