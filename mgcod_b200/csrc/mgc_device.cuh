@@ -101,10 +101,18 @@ struct ChainBufs {
     int32_t *av_idx;
     double *av_cum, *av_pmax;
     int32_t *av_parg;
-    int32_t *chain;         // traceback output, contig-local, stored at the contig's sorted range
-    int32_t *gene_count;    // per contig
-    double *contig_total;   // per contig
+    int32_t *chain;         // traceback output, piece-local, stored at the piece's sorted range
+    // chain pieces: a contig is cut where no candidate spans a bucket boundary; pieces are independent chains.
+    // Slot of the piece starting at relative bucket rb of contig c: slotbase[c] + rb / PIECE_BUCKETS.
+    int32_t *piece_b0, *piece_b1;   // per slot: first / last bucket (absolute index)
+    int32_t *work;                  // slots in processing order (k_chain_plan)
+    int32_t *gene_count;            // per slot (+1 terminator for the scan)
+    double *piece_total;            // per slot
+    const uint32_t *slot_gene_off;  // exclusive scan of gene_count
+    uint32_t *gene_off;             // per contig (+1)
+    double *contig_total;           // per contig
 };
+constexpr int PIECE_BUCKETS = 64;   // cuts are at least this many 128-nt buckets apart
 
 struct Planes {
     const uint32_t *lo, *hi;  // [2][W + 4]

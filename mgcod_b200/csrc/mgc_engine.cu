@@ -120,6 +120,7 @@ struct PerModel {
     DevBuf ls, ls_tile, orfs, starts, witems, items, items_sorted, hist, item_off, unit_off, sums;
     DevBuf surv, sorted, bcount, cum, prev, gptr;
     DevBuf av_right, av_left, av_ls, av_idx, av_cum, av_pmax, av_parg, chain, gene_count, gene_off, contig_total, genes;
+    DevBuf piece_b0, piece_b1, work, piece_total, slot_gene_off;
 };
 
 constexpr int N_EVENTS = 12;
@@ -136,6 +137,8 @@ struct mgc_engine {
     DevBuf d_models;
     // resident batch
     int32_t n_contigs = 0;
+    int32_t n_slots = 0;   // chain piece slots (ChainBufs)
+    DevBuf slotbase, slot_contig;
     int64_t total_nt = 0, W = 0;
     std::vector<int64_t> h_aoff, h_cwoff;
     std::vector<int32_t> h_clen, h_order;
@@ -371,7 +374,12 @@ void ensure_batch_buffers(mgc_engine *e) {
         p.av_pmax.ensure((size_t)e->cap_surv * 8);
         p.av_parg.ensure((size_t)e->cap_surv * 4);
         p.chain.ensure((size_t)e->cap_surv * 4);
-        p.gene_count.ensure((size_t)(e->n_contigs + 8) * 4);
+        p.gene_count.ensure((size_t)(e->n_slots + 8) * 4);
+        p.slot_gene_off.ensure((size_t)(e->n_slots + 8) * 4);
+        p.piece_b0.ensure((size_t)(e->n_slots + 8) * 4);
+        p.piece_b1.ensure((size_t)(e->n_slots + 8) * 4);
+        p.work.ensure((size_t)(e->n_slots + 8) * 4);
+        p.piece_total.ensure((size_t)(e->n_slots + 8) * 8);
         p.gene_off.ensure((size_t)(e->n_contigs + 8) * 4);
         p.contig_total.ensure((size_t)(e->n_contigs + 8) * 8);
         p.genes.ensure((size_t)e->cap_surv * sizeof(mgc_gene));
@@ -391,7 +399,13 @@ void ensure_batch_buffers(mgc_engine *e) {
         c.av_pmax = p.av_pmax.as<double>();
         c.av_parg = p.av_parg.as<int32_t>();
         c.chain = p.chain.as<int32_t>();
+        c.piece_b0 = p.piece_b0.as<int32_t>();
+        c.piece_b1 = p.piece_b1.as<int32_t>();
+        c.work = p.work.as<int32_t>();
         c.gene_count = p.gene_count.as<int32_t>();
+        c.piece_total = p.piece_total.as<double>();
+        c.slot_gene_off = p.slot_gene_off.as<uint32_t>();
+        c.gene_off = p.gene_off.as<uint32_t>();
         c.contig_total = p.contig_total.as<double>();
     }
     auto up = [&](DevBuf &b, const void *src, size_t bytes) {
@@ -419,7 +433,7 @@ void ensure_batch_buffers(mgc_engine *e) {
     e->next_unit.ensure(16);
     e->counters.ensure((size_t)M * 8 * 8);
     e->surv_counters.ensure((size_t)M * 8);
-    e->work_counters.ensure((size_t)M * 4);
+    e->work_counters.ensure((size_t)M * 8);
     e->model_cents.ensure((size_t)M * 8);
     e->gene_totals.ensure((size_t)M * 4);
 }
@@ -432,9 +446,13 @@ void set_slots(mgc_engine *e) {
     e->h_cwoff.resize(n + 1);
     e->h_aoff.resize(n + 1);
     std::vector<uint8_t> cflags(n);
+    std::vector<int32_t> slotbase(n + 1), slot_contig;
     int64_t w = 0, nt = 0;
     for (int32_t c = 0; c < n; c++) {
         const int64_t L = e->segs[c].len;
+        slotbase[c] = (int32_t)slot_contig.size();
+        const int64_t nbk = ((L > 0 ? L - 1 : 0) >> 7) + 1;
+        slot_contig.insert(slot_contig.end(), (size_t)((nbk + PIECE_BUCKETS - 1) / PIECE_BUCKETS), c);
         e->h_clen[c] = (int32_t)L;
         e->h_cwoff[c] = w;
         e->h_aoff[c] = e->segs[c].aoff;
@@ -443,6 +461,8 @@ void set_slots(mgc_engine *e) {
         w += (words + 3) / 4 * 4;
         nt += L;
     }
+    slotbase[n] = (int32_t)slot_contig.size();
+    e->n_slots = slotbase[n];
     e->h_cwoff[n] = w;
     e->h_aoff[n] = 0;
     if (w * 64 >= 0xffffffffLL) throw std::invalid_argument("batch too large: at most ~2e9 nt per decode call");
@@ -457,14 +477,18 @@ void set_slots(mgc_engine *e) {
     e->clen.ensure((size_t)n * 4);
     e->order.ensure((size_t)n * 4);
     e->cflags.ensure((size_t)n + 16);
+    e->slotbase.ensure((size_t)(n + 1) * 4);
+    e->slot_contig.ensure((size_t)e->n_slots * 4 + 16);
     cudaStream_t st = e->stream;
+    CUDA_TRY(cudaMemcpyAsync(e->slotbase.p, slotbase.data(), (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(e->slot_contig.p, slot_contig.data(), (size_t)e->n_slots * 4, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(e->aoff.p, e->h_aoff.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(e->cwoff.p, e->h_cwoff.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(e->clen.p, e->h_clen.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(e->order.p, e->h_order.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(e->cflags.p, cflags.data(), (size_t)n, cudaMemcpyHostToDevice, st));
     launch_groups(e->cwoff.as<int64_t>(), n, e->W / 4, e->grp2contig.as<int32_t>(), st);
-    CUDA_TRY(cudaStreamSynchronize(st));  // cflags is a local staging buffer
+    CUDA_TRY(cudaStreamSynchronize(st));  // cflags and the slot tables are local staging buffers
     CUDA_TRY(cudaGetLastError());
 }
 
@@ -520,10 +544,13 @@ mgc_result *run_pipeline(mgc_engine *e, bool *amb_out) {
     CUDA_TRY(cudaMemsetAsync(e->flags.p, 0, 64, st));
     CUDA_TRY(cudaMemsetAsync(e->counters.p, 0, (size_t)M * 64, st));
     CUDA_TRY(cudaMemsetAsync(e->surv_counters.p, 0, (size_t)M * 8, st));
-    CUDA_TRY(cudaMemsetAsync(e->work_counters.p, 0, (size_t)M * 4, st));
+    CUDA_TRY(cudaMemsetAsync(e->work_counters.p, 0, (size_t)M * 8, st));
     CUDA_TRY(cudaMemsetAsync(e->model_cents.p, 0, (size_t)M * 8, st));
     CUDA_TRY(cudaMemsetAsync(e->next_unit.p, 0, 16, st));
     for (int i = 0; i < M; i++) {
+        CUDA_TRY(cudaMemsetAsync(e->pm[i].gene_count.p, 0, (size_t)(e->n_slots + 1) * 4, st));
+        CUDA_TRY(cudaMemsetAsync(e->pm[i].piece_total.p, 0, (size_t)(e->n_slots + 1) * 8, st));
+        CUDA_TRY(cudaMemsetAsync(e->pm[i].piece_b1.p, 0xff, (size_t)(e->n_slots + 1) * 4, st));  // -1 = slot not used
         CUDA_TRY(cudaMemsetAsync(e->pm[i].bcount.p, 0, (size_t)(nb + 8) * 4, st));
         CUDA_TRY(cudaMemsetAsync(e->pm[i].hist.p, 0, e->pm[i].hist.bytes, st));
     }
@@ -576,19 +603,16 @@ mgc_result *run_pipeline(mgc_engine *e, bool *amb_out) {
                    e->surv_counters.as<unsigned long long>(), e->cwoff.as<int64_t>(), e->cap_surv, M, e->n_sm, st);
     launches += 1;
     CUDA_TRY(cudaEventRecord(e->ev[4], st));
-    launch_chain(e->t_chainbufs.as<ChainBufs>(), e->cwoff.as<int64_t>(), e->clen.as<int32_t>(), e->order.as<int32_t>(), n,
-                 e->work_counters.as<int>(), M, e->n_sm, st);
-    launches += 1;
+    launches += launch_chain(e->t_chainbufs.as<ChainBufs>(), e->cwoff.as<int64_t>(), e->clen.as<int32_t>(), e->order.as<int32_t>(), n,
+                             e->slotbase.as<int32_t>(), e->work_counters.as<int>(), M, e->n_sm, st);
     CUDA_TRY(cudaEventRecord(e->ev[5], st));
     for (int i = 0; i < M; i++) {
-        // gene_count[n] = 0 so that the exclusive scan yields the total at gene_off[n]
-        CUDA_TRY(cudaMemsetAsync(e->pm[i].gene_count.as<int32_t>() + n, 0, 4, st));
-        launches += launch_exclusive_scan(e->pm[i].gene_count.as<uint32_t>(), e->pm[i].gene_off.as<uint32_t>(),
-                                          e->tile_sums.as<uint32_t>(), (int64_t)n + 1, e->gene_totals.as<uint32_t>() + i, st);
+        // gene_count[n_slots] stays 0 so that the exclusive scan yields the total at slot_gene_off[n_slots]
+        launches += launch_exclusive_scan(e->pm[i].gene_count.as<uint32_t>(), e->pm[i].slot_gene_off.as<uint32_t>(),
+                                          e->tile_sums.as<uint32_t>(), (int64_t)e->n_slots + 1, e->gene_totals.as<uint32_t>() + i, st);
     }
-    launch_gather(e->t_chainbufs.as<ChainBufs>(), e->t_gene_off.as<const uint32_t *>(), e->t_genes.as<mgc_gene *>(),
-                  e->cwoff.as<int64_t>(), e->clen.as<int32_t>(), n, e->model_cents.as<long long>(), M, e->n_sm, st);
-    launches += 1;
+    launches += launch_gather(e->t_chainbufs.as<ChainBufs>(), e->t_genes.as<mgc_gene *>(), e->slot_contig.as<int32_t>(), e->n_slots,
+                              e->slotbase.as<int32_t>(), n, e->model_cents.as<long long>(), M, e->n_sm, st);
     CUDA_TRY(cudaEventRecord(e->ev[6], st));
 
     // small read-backs
@@ -815,14 +839,15 @@ void mgc_engine_destroy(mgc_engine *e) {
         for (DevBuf *b : {&p.lc_full, &p.ln_full, &p.lc_ramp, &p.ln_ramp, &p.sc, &p.quad, &p.rquad, &p.wtab, &p.pair_amb, &p.ls, &p.ls_tile, &p.items, &p.items_sorted, &p.hist,
                           &p.item_off, &p.unit_off, &p.sums, &p.witems, &p.orfs, &p.starts, &p.surv, &p.sorted, &p.bcount,
                           &p.cum, &p.prev, &p.gptr, &p.av_right, &p.av_left, &p.av_ls, &p.av_idx, &p.av_cum, &p.av_pmax, &p.av_parg,
-                          &p.chain, &p.gene_count, &p.gene_off, &p.contig_total, &p.genes})
+                          &p.chain, &p.gene_count, &p.gene_off, &p.contig_total, &p.genes, &p.piece_b0, &p.piece_b1, &p.work,
+                          &p.piece_total, &p.slot_gene_off})
             b->release();
     }
     for (DevBuf *b : {&e->d_models, &e->ascii, &e->aoff, &e->cwoff, &e->clen, &e->grp2contig, &e->order, &e->lo, &e->hi, &e->gc,
                       &e->tile_sums, &e->flags, &e->t_orfs, &e->t_starts, &e->t_surv, &e->t_sorted, &e->t_bcount, &e->t_gene_off,
                       &e->t_genes, &e->t_chainbufs, &e->counters, &e->surv_counters, &e->work_counters, &e->model_cents,
                       &e->gene_totals, &e->t_ls, &e->t_ls_tile, &e->t_items, &e->t_items_sorted, &e->t_hist, &e->t_item_off,
-                      &e->t_unit_off, &e->t_sums, &e->t_witems, &e->nm, &e->ncount, &e->cflags, &e->plen, &e->gaps, &e->gap_count, &e->unit_totals, &e->next_unit, &e->win_stride, &e->win_off, &e->win_labels, &e->win_cents})
+                      &e->t_unit_off, &e->t_sums, &e->t_witems, &e->slotbase, &e->slot_contig, &e->nm, &e->ncount, &e->cflags, &e->plen, &e->gaps, &e->gap_count, &e->unit_totals, &e->next_unit, &e->win_stride, &e->win_off, &e->win_labels, &e->win_cents})
         b->release();
     for (auto &ev : e->ev) cudaEventDestroy(ev);
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -909,11 +934,30 @@ int64_t mgc_debug_candidates(mgc_engine *e, int model, mgc_candidate *out, int64
             CUDA_TRY(cudaMemcpy(cum.data(), e->pm[model].cum.p, ns * 8, cudaMemcpyDeviceToHost));
         }
         n = (int64_t)ns;
+        // chain scores are stored relative to the candidate's piece; add the best score of everything before the piece
+        const int32_t nsl = e->n_slots;
+        std::vector<int32_t> b0(nsl), b1(nsl);
+        std::vector<double> pt(nsl), before(nsl, 0.0);
+        if (nsl) {
+            CUDA_TRY(cudaMemcpy(b0.data(), e->pm[model].piece_b0.p, (size_t)nsl * 4, cudaMemcpyDeviceToHost));
+            CUDA_TRY(cudaMemcpy(b1.data(), e->pm[model].piece_b1.p, (size_t)nsl * 4, cudaMemcpyDeviceToHost));
+            CUDA_TRY(cudaMemcpy(pt.data(), e->pm[model].piece_total.p, (size_t)nsl * 8, cudaMemcpyDeviceToHost));
+        }
+        std::vector<int32_t> sbase(e->n_contigs + 1, 0);
+        for (int32_t ci = 0; ci < e->n_contigs; ci++) {
+            const int64_t nbk = ((e->h_clen[ci] > 0 ? e->h_clen[ci] - 1 : 0) >> 7) + 1;
+            sbase[ci + 1] = sbase[ci] + (int32_t)((nbk + PIECE_BUCKETS - 1) / PIECE_BUCKETS);
+            double acc = 0.0;
+            for (int32_t s = sbase[ci]; s < sbase[ci + 1]; s++) { before[s] = acc; if (b1[s] >= 0) acc += pt[s]; }
+        }
         for (int64_t i = 0; i < n && i < cap && out; i++) {
             mgc_candidate &o = out[i];
             o.contig = c[i].contig; o.left = c[i].left; o.right = c[i].right; o.strand = c[i].strand; o.gc = c[i].gc;
             o.domain = c[i].flags & 1; o.partial_start = (c[i].flags >> 1) & 1; o.partial_stop = (c[i].flags >> 2) & 1;
             o.total = c[i].total; o.cum = cum[i];
+            const int64_t b = e->h_cwoff[o.contig] / 4 + (o.right >> 7);
+            for (int32_t s = sbase[o.contig]; s < sbase[o.contig + 1]; s++)
+                if (b1[s] >= 0 && b >= b0[s] && b <= b1[s]) { o.cum += before[s]; break; }
         }
     });
     return rc == MGC_OK ? n : rc;

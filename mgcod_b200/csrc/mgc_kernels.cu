@@ -1266,30 +1266,87 @@ __device__ __forceinline__ void chain_bucket(const ChainBufs &B, ChainRing &R, u
     }
 }
 
-__global__ void __launch_bounds__(128) k_chain(const ChainBufs *bufs_m, const int64_t *__restrict__ cwoff,
-                                               const int32_t *__restrict__ clen, const int32_t *__restrict__ order,
-                                               int32_t n_contigs, int *work_counters) {
+// Cut points.  Candidates are bucketed by right end; the boundary in front of relative bucket rb is safe when every
+// candidate ending at or after it also starts at or after it: nothing on its right can overlap, or share a
+// reverse-strand ORF with, anything on its left, and the only coupling left is the additive best score of the prefix.
+// One warp per (contig, model) walks the buckets from the end with a suffix minimum of the left ends and cuts at the
+// first safe boundary at least PIECE_BUCKETS below the previous cut.
+__global__ void __launch_bounds__(128) k_chain_plan(const ChainBufs *bufs_m, const int64_t *__restrict__ cwoff,
+                                                    const int32_t *__restrict__ clen, const int32_t *__restrict__ order,
+                                                    int32_t n_contigs, const int32_t *__restrict__ slotbase, int *work_counters) {
+    const int mi = blockIdx.y;
+    const ChainBufs B = bufs_m[mi];
+    const int lane = lane_id();
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t it = warp; it < n_contigs; it += nw) {
+        const int c = order[it];
+        const int L = clen[c];
+        const int64_t b_first = cwoff[c] >> 2;  // slots start on 128-nt boundaries
+        const int nbk = (max(L - 1, 0) >> 7) + 1;
+        const uint32_t cs = b_first ? B.bend[b_first - 1] : 0u, ce = B.bend[b_first + nbk - 1];
+        if (ce == cs) continue;
+        const int sb = slotbase[c];
+        int last_cut = nbk;  // the piece being grown ends at relative bucket last_cut - 1
+        if (nbk >= 2 * PIECE_BUCKETS) {
+            int carry = 0x7fffffff;  // minimum left end over all buckets above the current block
+            for (int top = nbk - 1; top >= PIECE_BUCKETS; top -= 32) {
+                const int rb = top - lane;
+                int m = 0x7fffffff;
+                if (rb >= PIECE_BUCKETS) {
+                    const uint32_t s0 = B.bend[b_first + rb - 1], e0 = B.bend[b_first + rb];
+                    for (uint32_t k = s0; k < e0; k++) m = min(m, B.sorted[k].left);
+                }
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, m, o);
+                    if (lane >= o) m = min(m, t);
+                }
+                m = min(m, carry);
+                carry = __shfl_sync(0xffffffffu, m, 31);
+                const bool ok = rb >= PIECE_BUCKETS && rb <= last_cut - PIECE_BUCKETS && m >= rb * 128;
+                const uint32_t mask = __ballot_sync(0xffffffffu, ok);
+                if (mask) {
+                    const int cut = top - (__ffs(mask) - 1);
+                    if (lane == 0) {
+                        const int slot = sb + cut / PIECE_BUCKETS;
+                        B.piece_b0[slot] = (int32_t)(b_first + cut);
+                        B.piece_b1[slot] = (int32_t)(b_first + last_cut - 1);
+                        B.work[atomicAdd(&work_counters[2 * mi], 1)] = slot;
+                    }
+                    last_cut = cut;
+                }
+            }
+        }
+        if (lane == 0) {
+            B.piece_b0[sb] = (int32_t)b_first;
+            B.piece_b1[sb] = (int32_t)(b_first + last_cut - 1);
+            B.work[atomicAdd(&work_counters[2 * mi], 1)] = sb;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_chain(const ChainBufs *bufs_m, int *work_counters) {
     __shared__ ChainRing rings[4];
     const int mi = blockIdx.y;
     const ChainBufs B = bufs_m[mi];
     const int lane = lane_id();
     ChainRing &R = rings[threadIdx.x >> 5];
+    const int n_work = work_counters[2 * mi];
     while (true) {
         int item = 0;
-        if (lane == 0) item = atomicAdd(&work_counters[mi], 1);
+        if (lane == 0) item = atomicAdd(&work_counters[2 * mi + 1], 1);
         item = __shfl_sync(0xffffffffu, item, 0);
-        if (item >= n_contigs) break;
-        const int c = order[item];
-        const int L = clen[c];
-        const int64_t g0 = cwoff[c] * 32;
-        const int64_t b_first = g0 >> 7, b_last = (g0 + max(L - 1, 0)) >> 7;
+        if (item >= n_work) break;
+        const int slot = B.work[item];
+        const int64_t b_first = B.piece_b0[slot], b_last = B.piece_b1[slot];
         const uint32_t cs = b_first ? B.bend[b_first - 1] : 0u;
         const uint32_t ce = B.bend[b_last];
         ChainState S;
         S.na = 0; S.head = 0; S.pm_val = 0.0; S.pm_arg = -1; S.gp_next = 0;
         if (lane < GP_CACHE) R.gp_orf[lane] = 0xffffffffu;
         __syncwarp();
-        // the contig's candidates are contiguous in `sorted`; walk them in register-sized pieces that end on bucket boundaries
+        // the piece's candidates are contiguous in `sorted`; walk them in register-sized blocks that end on bucket boundaries
         uint32_t prev_end = cs;
         uint32_t nxt_end = b_first <= b_last ? (b_first + lane <= b_last ? B.bend[b_first + lane] : ce) : ce;
         for (int64_t bb = b_first; bb <= b_last && prev_end < ce; bb += 32) {
@@ -1401,35 +1458,34 @@ __global__ void __launch_bounds__(128) k_chain(const ChainBufs *bufs_m, const in
                 }
                 for (int q = 0; q < ng; q++) B.chain[cs + q] = B.chain[cs + k + q];
             }
-            B.gene_count[c] = ng;
-            B.contig_total[c] = tot;
+            B.gene_count[slot] = ng;
+            B.piece_total[slot] = tot;
         }
         __syncwarp();
     }
 }
 
 // genes of all contigs, contiguous, ordered by (contig, left); per-model sum of round(logodd, 2) in cents
-__global__ void __launch_bounds__(128) k_gather(const ChainBufs *bufs_m, const uint32_t *const *gene_off_m, mgc_gene *const *genes_m,
-                                                const int64_t *__restrict__ cwoff, const int32_t *__restrict__ clen,
-                                                int32_t n_contigs, long long *model_cents) {
+__global__ void __launch_bounds__(128) k_gather(const ChainBufs *bufs_m, mgc_gene *const *genes_m, const int32_t *__restrict__ slot_contig,
+                                                int32_t n_slots, long long *model_cents) {
     const int mi = blockIdx.y;
     const ChainBufs B = bufs_m[mi];
-    const uint32_t *goff = gene_off_m[mi];
     mgc_gene *genes = genes_m[mi];
     const int lane = lane_id();
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
     long long cents = 0;
-    for (int64_t c = warp; c < n_contigs; c += nw) {
-        const int ng = B.gene_count[c];
+    for (int64_t slot = warp; slot < n_slots; slot += nw) {
+        const int ng = B.gene_count[slot];
         if (!ng) continue;
-        const int64_t g0 = cwoff[c] * 32;
-        const int64_t b_first = g0 >> 7;
+        const int64_t b_first = B.piece_b0[slot];
         const uint32_t cs = b_first ? B.bend[b_first - 1] : 0u;
+        const uint32_t off = B.slot_gene_off[slot];
+        const int32_t c = slot_contig[slot];
         for (int q = lane; q < ng; q += 32) {
             const Cand cd = B.sorted[B.chain[cs + q]];
             mgc_gene g;
-            g.contig = (int32_t)c;
+            g.contig = c;
             g.left = cd.left + 1;
             g.right = cd.right + 1;
             g.strand = cd.strand;
@@ -1439,13 +1495,27 @@ __global__ void __launch_bounds__(128) k_gather(const ChainBufs *bufs_m, const u
             g.partial_right = cd.strand > 0 ? pe : ps;
             g.gc = cd.gc;
             g.logodd = cd.total;
-            genes[goff[c] + q] = g;
+            genes[off + q] = g;
             cents += llrint(cd.total * 100.0);
         }
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) cents += __shfl_xor_sync(0xffffffffu, cents, o);
     if (lane == 0 && cents) atomicAdd((unsigned long long *)&model_cents[mi], (unsigned long long)cents);
+}
+
+// per contig: offset of its first gene and the chain total = sum of its pieces' totals, in order
+__global__ void __launch_bounds__(256) k_contig_finish(const ChainBufs *bufs_m, const int32_t *__restrict__ slotbase, int32_t n_contigs) {
+    const ChainBufs B = bufs_m[blockIdx.y];
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > n_contigs) return;
+    const int s0 = slotbase[c];
+    B.gene_off[c] = B.slot_gene_off[s0];
+    if (c == n_contigs) return;
+    const int s1 = slotbase[c + 1];
+    double t = 0.0;
+    for (int s = s0; s < s1; s++) t += B.piece_total[s];
+    B.contig_total[c] = t;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1697,21 +1767,22 @@ void launch_scatter(const Cand *const *surv_m, Cand *const *sorted_m, uint32_t *
     k_scatter<<<grid, 256, 0, st>>>(surv_m, sorted_m, boff_m, surv_counters, cwoff, cap_surv);
 }
 
-void launch_chain(const ChainBufs *bufs_m, const int64_t *cwoff, const int32_t *clen, const int32_t *order, int32_t n_contigs,
-                  int *work_counters, int n_models, int n_sm, cudaStream_t st) {
-    int64_t warps = n_contigs;
-    int64_t blocks = (warps + 3) / 4;
-    if (blocks > (int64_t)n_sm * 16) blocks = (int64_t)n_sm * 16;
-    dim3 grid((unsigned)blocks, n_models);
-    k_chain<<<grid, 128, 0, st>>>(bufs_m, cwoff, clen, order, n_contigs, work_counters);
-}
-
-void launch_gather(const ChainBufs *bufs_m, const uint32_t *const *gene_off_m, mgc_gene *const *genes_m, const int64_t *cwoff,
-                   const int32_t *clen, int32_t n_contigs, long long *model_cents, int n_models, int n_sm, cudaStream_t st) {
+int launch_chain(const ChainBufs *bufs_m, const int64_t *cwoff, const int32_t *clen, const int32_t *order, int32_t n_contigs,
+                 const int32_t *slotbase, int *work_counters, int n_models, int n_sm, cudaStream_t st) {
     int64_t blocks = ((int64_t)n_contigs + 3) / 4;
     if (blocks > (int64_t)n_sm * 16) blocks = (int64_t)n_sm * 16;
-    dim3 grid((unsigned)blocks, n_models);
-    k_gather<<<grid, 128, 0, st>>>(bufs_m, gene_off_m, genes_m, cwoff, clen, n_contigs, model_cents);
+    k_chain_plan<<<dim3((unsigned)blocks, n_models), 128, 0, st>>>(bufs_m, cwoff, clen, order, n_contigs, slotbase, work_counters);
+    k_chain<<<dim3((unsigned)n_sm * 16, n_models), 128, 0, st>>>(bufs_m, work_counters);
+    return 2;
+}
+
+int launch_gather(const ChainBufs *bufs_m, mgc_gene *const *genes_m, const int32_t *slot_contig, int32_t n_slots, const int32_t *slotbase,
+                  int32_t n_contigs, long long *model_cents, int n_models, int n_sm, cudaStream_t st) {
+    int64_t blocks = ((int64_t)n_slots + 3) / 4;
+    if (blocks > (int64_t)n_sm * 16) blocks = (int64_t)n_sm * 16;
+    k_gather<<<dim3((unsigned)blocks, n_models), 128, 0, st>>>(bufs_m, genes_m, slot_contig, n_slots, model_cents);
+    k_contig_finish<<<dim3((unsigned)(n_contigs / 256 + 1), n_models), 256, 0, st>>>(bufs_m, slotbase, n_contigs);
+    return 2;
 }
 
 void launch_windows(const mgc_gene *const *genes_m, const uint32_t *const *gene_off_m, int n_models, const int32_t *clen,
