@@ -10,8 +10,11 @@ A "step" decodes one batch of synthetic contigs (BASELINE.json config 5: lengths
 collective; the only exchange is the final max-over-ranks of the timings).
 
   value   device-resident: ASCII contigs already in HBM, K x (pack -> ORFs -> scores -> chain -> genes to host)
-  e2e     the public call Engine.decode_buffer() on pinned HOST buffers: H2D of the sequences and D2H of the
-          genes inside the timed region
+  e2e     the public call Engine.decode_stream() on pinned HOST buffers: every step copies its sequences H2D (on the
+          copy stream, overlapping the previous batch's decode) and reads its genes back, all inside the timed
+          region; e2e.single_call_* is Engine.decode_buffer() per step, nothing overlapped
+  isoforms        windows/s of the --isoforms labelling (window sums + labels + label merging) on the resident result
+  other_shapes    the "200k contigs x 5 kb" shape of SURVEY.md 8(d), device-resident
 
 `--impl reference` times the reference's own gene finder (oracle/_ref/gmhmmp2, the binary Mgcod shells out
 to; else the C port in oracle/) on the box's host cores on a bounded sample of the same workload.
@@ -270,14 +273,56 @@ def main():
             cents = res.model_cents()
             del res
         barrier()
+        dt_single = time.perf_counter() - t0
+        # the same through Engine.decode_stream(): a stream of host batches, batch i+1 copied while batch i is decoded.
+        # Every step still moves its own H2D bytes (adopted from the copy stream) and reads its genes back.
+        barrier()
+        t0 = time.perf_counter()
+        for res in engine.decode_stream((buf, offs) for _ in range(args.steps)):
+            cents = res.model_cents()
+            del res
+        barrier()
         dt_e2e = time.perf_counter() - t0
 
-        times = torch.tensor([dt_res, dt_e2e], dtype=torch.float64, device="cuda")
+        # ---- --isoforms labelling of the resident result (BASELINE.json configs[1] parameters: -w 5000 -st 2500 -n 3) ----
+        engine.upload(buf, offs)
+        res = engine.decode_resident()
+        lens = np.diff(offs)
+        strides = np.full(len(lens), 2500, np.int32)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            woffs, wlab, wcents = engine.window_labels(lens, strides, 5000, 3, False)
+            merged = engine.merge_labels([wlab[woffs[i]:woffs[i + 1]] for i in range(len(lens))], 3)
+        torch.cuda.synchronize()
+        dt_win = (time.perf_counter() - t0) / args.steps
+        n_windows = int(woffs[-1])
+        del res
+
+        # ---- second shape of SURVEY.md 8(d): 200k contigs of 5 kb (launch/overhead behaviour) ----
+        shape2 = None
+        if world == 1 and not os.environ.get("MGCOD_BENCH_SKIP_SHAPE2"):
+            buf2, offs2, _ = synth_metagenome(SEED + 1000, args.total_bp, min_len=5000, max_len=5000, threads=min(cores, 32),
+                                              out=pinned.numpy())
+            engine.upload(buf2, offs2)
+            for _ in range(2):
+                del_me = engine.decode_resident()
+                del del_me
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                del_me = engine.decode_resident()
+                del del_me
+            torch.cuda.synchronize()
+            dt2 = (time.perf_counter() - t0) / args.steps
+            shape2 = {"workload": f"{len(offs2) - 1} contigs x 5 kb, same generator", "ms_per_step": 1e3 * dt2,
+                      "value": int(offs2[-1]) * engine.n_models / dt2, "unit": UNIT, "resident": True}
+
+        times = torch.tensor([dt_res, dt_e2e, dt_single, dt_win], dtype=torch.float64, device="cuda")
         tot_units = torch.tensor([float(units)], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(times, op=dist.ReduceOp.MAX)
             dist.all_reduce(tot_units, op=dist.ReduceOp.SUM)
-        dt_res, dt_e2e = float(times[0]), float(times[1])
+        dt_res, dt_e2e, dt_single, dt_win = (float(x) for x in times)
         all_units = float(tot_units[0])
 
         if rank == 0:
@@ -293,7 +338,13 @@ def main():
                 "warmup": args.warmup, "ms_per_step": 1e3 * dt_res / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": dict(config, contigs_per_gpu=int(len(truth))),
                 "e2e": {"value": all_units * args.steps / dt_e2e, "unit": UNIT, "h2d_bytes_per_step": int(total_bp + 8 * (len(offs))),
-                        "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": 1e3 * dt_e2e / args.steps},
+                        "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": 1e3 * dt_e2e / args.steps,
+                        "api": "Engine.decode_stream (H2D of batch i+1 overlaps the decode of batch i)",
+                        "single_call_ms_per_step": 1e3 * dt_single / args.steps,
+                        "single_call_value": all_units * args.steps / dt_single},
+                "isoforms": {"metric": "windows_per_s_labelled", "windows_per_gpu": n_windows, "w": 5000, "stride": 2500, "n": 3,
+                             "labelling_ms": 1e3 * dt_win, "value_labelling_only": world * n_windows / dt_win,
+                             "value_with_decode": world * n_windows / (dt_win + dt_res / args.steps), "unit": "windows/s"},
                 "gpu_launches": int(launches),
                 "clocks": clocks,
                 "roofline": {"kernel": "k_walk", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -303,6 +354,8 @@ def main():
                 "counts_per_step": counts,
                 "host": {"cores": cores, "workload_generation_s": gen_s},
             }
+            if shape2:
+                out["other_shapes"] = [shape2]
             if world == 1 and not args.no_cpu_baseline:
                 out["cpu_baseline"] = cpu_reference_run(buf, offs, model_paths, args.cpu_sample_bp, workdir, cores)
             print(json.dumps(out))

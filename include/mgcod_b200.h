@@ -82,6 +82,12 @@ int mgc_decode_batch(mgc_engine *e, const char *seq, const int64_t *offsets, int
 /* Two-step form used by the benchmark: copy + pack once, decode many times with inputs resident in HBM. */
 int mgc_upload_batch(mgc_engine *e, const char *seq, const int64_t *offsets, int32_t n_contigs);
 int mgc_decode_resident(mgc_engine *e, mgc_result **out);
+/* Streams of batches: starts the host->device copy of the NEXT batch on a second stream and returns at once; the copy
+ * runs while mgc_decode_resident works on the current batch.  The next mgc_upload_batch / mgc_decode_batch with the same
+ * seq pointer and offsets adopts the copied letters instead of copying again.  seq must stay valid and unchanged until
+ * then, and must be page-locked for the copy to overlap (pageable memory works but is staged synchronously).
+ * Replaces the process-level overlap of bin/multiprocess_mgcod.py:140-145 (one genome loading while another decodes). */
+int mgc_prefetch_batch(mgc_engine *e, const char *seq, const int64_t *offsets, int32_t n_contigs);
 
 int mgc_engine_stats(const mgc_engine *e, mgc_stats *out);
 

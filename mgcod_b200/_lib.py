@@ -37,7 +37,7 @@ class Stats(C.Structure):
 #: every symbol include/mgcod_b200.h declares
 EXPORTS = (
     "mgc_version", "mgc_last_error", "mgc_device_count", "mgc_model_load", "mgc_model_free", "mgc_model_info",
-    "mgc_engine_create", "mgc_engine_destroy", "mgc_decode_batch", "mgc_upload_batch", "mgc_decode_resident",
+    "mgc_engine_create", "mgc_engine_destroy", "mgc_decode_batch", "mgc_upload_batch", "mgc_prefetch_batch", "mgc_decode_resident",
     "mgc_engine_stats", "mgc_result_num_genes", "mgc_result_genes", "mgc_result_contig_totals",
     "mgc_result_model_cents", "mgc_result_min_gene_length", "mgc_result_set_min_gene_length", "mgc_result_free", "mgc_result_create", "mgc_window_counts", "mgc_window_labels", "mgc_merge_labels", "mgc_debug_candidates",
     "mgc_write_gff", "mgc_synth_lengths", "mgc_synth_contigs",
@@ -74,6 +74,7 @@ def lib():
     L.mgc_engine_destroy.argtypes = [vp]
     L.mgc_decode_batch.argtypes = [vp, vp, C.POINTER(i64), i32, C.POINTER(vp)]
     L.mgc_upload_batch.argtypes = [vp, vp, C.POINTER(i64), i32]
+    L.mgc_prefetch_batch.argtypes = [vp, vp, C.POINTER(i64), i32]
     L.mgc_decode_resident.argtypes = [vp, C.POINTER(vp)]
     L.mgc_engine_stats.argtypes = [vp, C.POINTER(Stats)]
     L.mgc_result_num_genes.argtypes = [vp, C.c_int]

@@ -158,6 +158,15 @@ struct mgc_engine {
     bool segmented = false;
     DevBuf nm, ncount, cflags, plen, gaps, gap_count;
     DevBuf ascii, aoff, cwoff, clen, grp2contig, order, lo, hi, gc, tile_sums, flags;
+    // next batch on its way to the device while the current one is decoded (mgc_prefetch_batch)
+    DevBuf ascii_next;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t copy_done = nullptr;
+    struct {
+        bool valid = false;
+        const char *seq = nullptr;
+        std::vector<int64_t> offsets;
+    } pending;
     // pointer tables + counters (device)
     DevBuf t_orfs, t_starts, t_surv, t_sorted, t_bcount, t_gene_off, t_genes, t_chainbufs;
     DevBuf t_witems;
@@ -511,10 +520,19 @@ void do_upload(mgc_engine *e, const char *seq, const int64_t *offsets, int32_t n
     }
     e->h_parent_aoff[n] = a1 - a0;
     cudaStream_t st = e->stream;
-    e->ascii.ensure((size_t)(a1 - a0) + 64);
     e->plen.ensure((size_t)n * 4 + 16);
     CUDA_TRY(cudaEventRecord(e->ev[0], st));
-    CUDA_TRY(cudaMemcpyAsync(e->ascii.p, seq + a0, (size_t)(a1 - a0), cudaMemcpyHostToDevice, st));
+    const bool adopted = e->pending.valid && e->pending.seq == seq && (int32_t)e->pending.offsets.size() == n + 1 &&
+                         std::memcmp(e->pending.offsets.data(), offsets, (size_t)(n + 1) * 8) == 0;
+    e->pending.valid = false;
+    if (adopted) {  // the letters are already on their way (or there): take the buffer over
+        std::swap(e->ascii, e->ascii_next);
+        CUDA_TRY(cudaStreamWaitEvent(st, e->copy_done, 0));
+    } else {
+        CUDA_TRY(cudaStreamSynchronize(e->copy_stream));  // a prefetch nobody adopted must not outlive its host buffer
+        e->ascii.ensure((size_t)(a1 - a0) + 64);
+        CUDA_TRY(cudaMemcpyAsync(e->ascii.p, seq + a0, (size_t)(a1 - a0), cudaMemcpyHostToDevice, st));
+    }
     CUDA_TRY(cudaMemcpyAsync(e->plen.p, e->h_parent_len.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
     set_slots(e);
     CUDA_TRY(cudaEventRecord(e->ev[1], st));
@@ -813,6 +831,8 @@ int mgc_engine_create(int device, const mgc_model *const *models, int n_models, 
         e->n_sm = prop.multiProcessorCount;
         CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
         for (auto &ev : e->ev) CUDA_TRY(cudaEventCreate(&ev));
+        CUDA_TRY(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&e->copy_done, cudaEventDisableTiming));
         e->n_models = n_models;
         e->pm.resize(n_models);
         for (int i = 0; i < n_models; i++) {
@@ -847,9 +867,11 @@ void mgc_engine_destroy(mgc_engine *e) {
                       &e->tile_sums, &e->flags, &e->t_orfs, &e->t_starts, &e->t_surv, &e->t_sorted, &e->t_bcount, &e->t_gene_off,
                       &e->t_genes, &e->t_chainbufs, &e->counters, &e->surv_counters, &e->work_counters, &e->model_cents,
                       &e->gene_totals, &e->t_ls, &e->t_ls_tile, &e->t_items, &e->t_items_sorted, &e->t_hist, &e->t_item_off,
-                      &e->t_unit_off, &e->t_sums, &e->t_witems, &e->slotbase, &e->slot_contig, &e->nm, &e->ncount, &e->cflags, &e->plen, &e->gaps, &e->gap_count, &e->unit_totals, &e->next_unit, &e->win_stride, &e->win_off, &e->win_labels, &e->win_cents})
+                      &e->t_unit_off, &e->t_sums, &e->t_witems, &e->ascii_next, &e->slotbase, &e->slot_contig, &e->nm, &e->ncount, &e->cflags, &e->plen, &e->gaps, &e->gap_count, &e->unit_totals, &e->next_unit, &e->win_stride, &e->win_off, &e->win_labels, &e->win_cents})
         b->release();
     for (auto &ev : e->ev) cudaEventDestroy(ev);
+    if (e->copy_done) cudaEventDestroy(e->copy_done);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -877,6 +899,22 @@ static int guarded(const std::function<void()> &fn) {
 int mgc_upload_batch(mgc_engine *e, const char *seq, const int64_t *offsets, int32_t n_contigs) {
     if (!e || !seq || !offsets) return mgc::set_error(MGC_E_ARG, "null argument");
     return guarded([&] { do_upload(e, seq, offsets, n_contigs); });
+}
+
+int mgc_prefetch_batch(mgc_engine *e, const char *seq, const int64_t *offsets, int32_t n_contigs) {
+    if (!e || !seq || !offsets || n_contigs <= 0) return mgc::set_error(MGC_E_ARG, "bad argument");
+    return guarded([&] {
+        CUDA_TRY(cudaSetDevice(e->device));
+        CUDA_TRY(cudaStreamSynchronize(e->copy_stream));
+        const int64_t a0 = offsets[0], a1 = offsets[n_contigs];
+        if (a1 < a0) throw std::invalid_argument("offsets must ascend");
+        e->ascii_next.ensure((size_t)(a1 - a0) + 64);
+        CUDA_TRY(cudaMemcpyAsync(e->ascii_next.p, seq + a0, (size_t)(a1 - a0), cudaMemcpyHostToDevice, e->copy_stream));
+        CUDA_TRY(cudaEventRecord(e->copy_done, e->copy_stream));
+        e->pending.valid = true;
+        e->pending.seq = seq;
+        e->pending.offsets.assign(offsets, offsets + n_contigs + 1);
+    });
 }
 
 int mgc_decode_resident(mgc_engine *e, mgc_result **out) {

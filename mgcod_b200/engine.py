@@ -8,7 +8,7 @@ whole batches of contigs under all of them in one call.
 from __future__ import annotations
 
 import ctypes as C
-from typing import Optional, Sequence
+from typing import Iterable, Iterator, Optional, Sequence
 
 import numpy as np
 
@@ -145,6 +145,32 @@ class Engine:
         self.n_contigs = len(offsets) - 1
         _check(_lib.lib().mgc_upload_batch(self._h, C.c_void_p(buf.ctypes.data), offsets.ctypes.data_as(C.POINTER(C.c_int64)),
                                            self.n_contigs))
+
+    def prefetch(self, buf: np.ndarray, offsets: np.ndarray) -> None:
+        """Starts copying the NEXT batch to the device on a second stream (returns at once); the following ``upload`` /
+        ``decode_buffer`` of the same arrays adopts it.  ``buf`` should be page-locked and must not change until then."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        self._keep_next = (buf, offsets)
+        _check(_lib.lib().mgc_prefetch_batch(self._h, C.c_void_p(buf.ctypes.data), offsets.ctypes.data_as(C.POINTER(C.c_int64)),
+                                             len(offsets) - 1))
+
+    def decode_stream(self, batches: Iterable[tuple[np.ndarray, np.ndarray]]) -> Iterator[Result]:
+        """Decodes a sequence of (buf, offsets) batches, copying batch i+1 to the device while batch i is decoded —
+        what bin/multiprocess_mgcod.py:140-145 gets from running several genomes' processes side by side."""
+        it = iter(batches)
+        cur = next(it, None)
+        if cur is None:
+            return
+        self.upload(*cur)
+        while cur is not None:
+            nxt = next(it, None)
+            if nxt is not None:
+                nxt = (nxt[0], np.ascontiguousarray(nxt[1], dtype=np.int64))
+                self.prefetch(*nxt)
+            yield self.decode_resident()
+            if nxt is not None:
+                self.upload(*nxt)
+            cur = nxt
 
     def decode_resident(self) -> Result:
         r = C.c_void_p()

@@ -98,3 +98,20 @@ def test_ambiguous_letters_and_gaps_match_oracle(engine, oracles, seed):
     res2 = engine.decode_resident()
     for mi in range(len(CODES)):
         assert np.array_equal(res.genes(mi), res2.genes(mi))
+
+
+def test_long_contigs_chained_in_pieces_match_oracle(engine, oracles):
+    """contigs far longer than one chain piece (8 kb): cut points, slot order and stitched totals.  The candidate dump
+    re-adds the prefix score, so chain scores compare with the sequential oracle too."""
+    from mgcod_b200.engine import synth_metagenome
+    buf, offs, truth = synth_metagenome(77, 1_300_000, min_len=600_000, max_len=700_000, threads=4)
+    seqs = [buf[offs[i]:offs[i + 1]].tobytes() for i in range(len(truth))]
+    assert len(seqs) >= 2
+    res = engine.decode_buffer(buf, offs)
+    for mi in (0, 2):
+        rows, totals = parity.oracle_genes(oracles[mi], seqs)
+        diffs = parity.compare_genes(res.genes(mi), rows)
+        assert not diffs, f"model {CODES[mi]}: " + "; ".join(diffs[:6])
+        np.testing.assert_allclose(res.contig_totals(mi), totals, rtol=1e-9, atol=1e-9)
+    diffs = parity.compare_candidates(engine.candidates(1), oracles[1], seqs)
+    assert not diffs, "; ".join(diffs[:6])

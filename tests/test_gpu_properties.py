@@ -107,3 +107,24 @@ def test_full_size_properties(engine):
         hit += code_of[np.bincount(lab, minlength=4).argmax()] == truth[c]
         tot_c += 1
     assert hit / tot_c > 0.97
+
+
+def test_decode_stream_equals_batch_by_batch(engine):
+    """batch i+1 travels on the copy stream while batch i is decoded; results equal those of separate calls, a
+    prefetch that is never adopted is harmless"""
+    from mgcod_b200.engine import synth_metagenome
+    batches = []
+    for seed in (5, 6, 7):
+        buf, offs, _ = synth_metagenome(seed, 60000 + 20000 * seed, threads=2)
+        batches.append((buf, offs))
+    want = [[engine.decode_buffer(b, o).genes(m) for m in range(4)] for b, o in batches]
+    got = [[r.genes(m) for m in range(4)] for r in engine.decode_stream(iter(batches))]
+    assert len(got) == 3
+    for w, g in zip(want, got):
+        for a, b in zip(w, g):
+            assert np.array_equal(a, b)
+    engine.prefetch(*batches[0])
+    r = engine.decode_buffer(*batches[1])      # different batch: the prefetched letters are dropped
+    assert np.array_equal(r.genes(0), want[1][0])
+    r = engine.decode_buffer(*batches[0])
+    assert np.array_equal(r.genes(2), want[0][2])
