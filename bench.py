@@ -242,6 +242,8 @@ def main():
         for _ in range(args.warmup):
             res = engine.decode_buffer(buf, offs)
             del res
+        for res in engine.decode_stream((buf, offs) for _ in range(max(2, args.warmup))):   # the timed e2e path
+            del res
         # ---- device-resident timing ----
         engine.upload(buf, offs)
         res = engine.decode_resident()
@@ -292,7 +294,7 @@ def main():
         t0 = time.perf_counter()
         for _ in range(args.steps):
             woffs, wlab, wcents = engine.window_labels(lens, strides, 5000, 3, False)
-            merged = engine.merge_labels([wlab[woffs[i]:woffs[i + 1]] for i in range(len(lens))], 3)
+            merged = engine.merge_labels([wlab[woffs[i]:woffs[i + 1]] for i in range(len(lens))], 3, strict=False)
         torch.cuda.synchronize()
         dt_win = (time.perf_counter() - t0) / args.steps
         n_windows = int(woffs[-1])

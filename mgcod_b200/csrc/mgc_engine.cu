@@ -181,6 +181,7 @@ struct mgc_engine {
     DevBuf gene_totals;    // [M] uint32 grand totals of the gene scans
     DevBuf win_stride, win_off, win_labels, win_cents;
     uint32_t cap_orf = 0, cap_starts = 0, cap_surv = 0;
+    std::vector<unsigned char> table_sig;   // contents of the device pointer tables as last uploaded
     bool have_batch = false, have_genes = false;
     mgc_stats stats;
     std::shared_ptr<PinnedPool> pool = std::make_shared<PinnedPool>();
@@ -417,7 +418,18 @@ void ensure_batch_buffers(mgc_engine *e) {
         c.gene_off = p.gene_off.as<uint32_t>();
         c.contig_total = p.contig_total.as<double>();
     }
+    // the pointer tables only change when a buffer was reallocated: skip their upload for a batch that fits
+    std::vector<unsigned char> sig;
+    auto add_sig = [&](const void *src, size_t bytes) {
+        sig.insert(sig.end(), static_cast<const unsigned char *>(src), static_cast<const unsigned char *>(src) + bytes);
+    };
+    for (auto *v : {&t_orfs, &t_starts, &t_surv, &t_sorted, &t_bcount, &t_gene_off, &t_genes, &t_witems, &t_ls, &t_ls_tile, &t_items,
+                    &t_items_sorted, &t_hist, &t_item_off, &t_unit_off, &t_sums})
+        add_sig(v->data(), M * sizeof(void *));
+    add_sig(cb.data(), M * sizeof(ChainBufs));
+    const bool tables_current = sig == e->table_sig;
     auto up = [&](DevBuf &b, const void *src, size_t bytes) {
+        if (tables_current) return;
         b.ensure(bytes);
         CUDA_TRY(cudaMemcpy(b.p, src, bytes, cudaMemcpyHostToDevice));
     };
@@ -438,6 +450,7 @@ void ensure_batch_buffers(mgc_engine *e) {
     up(e->t_item_off, t_item_off.data(), M * sizeof(void *));
     up(e->t_unit_off, t_unit_off.data(), M * sizeof(void *));
     up(e->t_sums, t_sums.data(), M * sizeof(void *));
+    e->table_sig.swap(sig);
     e->unit_totals.ensure((size_t)M * 4 + 16);
     e->next_unit.ensure(16);
     e->counters.ensure((size_t)M * 8 * 8);
@@ -477,9 +490,12 @@ void set_slots(mgc_engine *e) {
     if (w * 64 >= 0xffffffffLL) throw std::invalid_argument("batch too large: at most ~2e9 nt per decode call");
     e->W = w;
     e->total_nt = nt;
+    // longest first, ties in input order: one sort of packed (inverted length, index) keys
+    std::vector<uint64_t> keys(n);
+    for (int32_t c = 0; c < n; c++) keys[c] = ((uint64_t)(0x7fffffffu - (uint32_t)e->h_clen[c]) << 32) | (uint32_t)c;
+    std::sort(keys.begin(), keys.end());
     e->h_order.resize(n);
-    std::iota(e->h_order.begin(), e->h_order.end(), 0);
-    std::stable_sort(e->h_order.begin(), e->h_order.end(), [&](int a, int b) { return e->h_clen[a] > e->h_clen[b]; });
+    for (int32_t c = 0; c < n; c++) e->h_order[c] = (int32_t)(keys[c] & 0xffffffffu);
     ensure_batch_buffers(e);
     e->aoff.ensure((size_t)(n + 1) * 8);
     e->cwoff.ensure((size_t)(n + 1) * 8);

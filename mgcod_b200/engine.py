@@ -49,7 +49,7 @@ class ModelFile:
         self.gcode, self.cod_order, self.non_order, self.gene_min_length, self.n_bacterial, self.n_archaeal = list(info)
 
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and _lib is not None and getattr(_lib, "lib", None):   # None during interpreter shutdown
             _lib.lib().mgc_model_free(self._h)
             self._h = None
 
@@ -117,7 +117,7 @@ class Result:
                                         seq_file.encode(), mod_file.encode(), gcode, out_path.encode(), fmt.encode()))
 
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and _lib is not None and getattr(_lib, "lib", None):   # None during interpreter shutdown
             _lib.lib().mgc_result_free(self._h)
             self._h = None
 
@@ -223,9 +223,10 @@ class Engine:
                                    cents.ctypes.data_as(C.POINTER(C.c_int64))))
         return offs, labels[:nw], cents[:nw]
 
-    def merge_labels(self, labels_per_contig: Sequence[np.ndarray], consecutive: int) -> list[np.ndarray]:
+    def merge_labels(self, labels_per_contig: Sequence[np.ndarray], consecutive: int, strict: bool = True) -> list[np.ndarray]:
         """Device-side label smoothing (reference bin/pipeline.py:1064-1168) of every contig's window labels; noise labels =
-        all but the two most frequent labels over the whole input.  Raises IndexError where the reference does."""
+        all but the two most frequent labels over the whole input.  Raises IndexError where the reference does
+        (``strict=False``: such contigs keep their input labels, for bulk runs)."""
         from .labels import noise_labels
         labs = [np.ascontiguousarray(l, dtype=np.int32) for l in labels_per_contig]
         offs = np.zeros(len(labs) + 1, dtype=np.int64)
@@ -239,12 +240,12 @@ class Engine:
         _check(_lib.lib().mgc_merge_labels(self._h, flat.ctypes.data_as(C.POINTER(C.c_int32)), offs.ctypes.data_as(C.POINTER(C.c_int64)),
                                            len(labs), consecutive, mask, out.ctypes.data_as(C.POINTER(C.c_int32)),
                                            status.ctypes.data_as(C.POINTER(C.c_int32))))
-        if (status[:len(labs)] != 0).any():
+        if strict and (status[:len(labs)] != 0).any():
             raise IndexError(f"label smoothing walks off the array for contig index {int(np.flatnonzero(status)[0])} (as the reference does)")
-        return [out[offs[i]:offs[i + 1]].astype(np.int64) for i in range(len(labs))]
+        return [(labs[i] if status[i] else out[offs[i]:offs[i + 1]]).astype(np.int64) for i in range(len(labs))]
 
     def close(self) -> None:
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and _lib is not None and getattr(_lib, "lib", None):   # None during interpreter shutdown
             _lib.lib().mgc_engine_destroy(self._h)
             self._h = None
 
