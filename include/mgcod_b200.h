@@ -111,6 +111,19 @@ int mgc_result_create(int n_models, int32_t n_contigs, const mgc_gene *const *ge
                       const double *const *totals, mgc_result **out);
 
 /*
+ * In-frame stop codons inside genes (bin/results.py:253-294, Results.find_recoded_stops via make_seqrecord): for each
+ * gene (contig, left, right, strand as in mgc_gene, coordinates of the last uploaded batch) the codon indices
+ * k = 0 .. ncodons-2 whose codon, read on the gene's strand, is TAA / TAG / TGA.  Runs on the packed sequence resident
+ * on the device after a decode.
+ *   counts[n_genes*3]     per gene: number of TAA, TAG, TGA codons found (in that order)
+ *   pos_off[n_genes*3+1]  exclusive prefix of counts
+ *   positions[pos_cap]    codon indices, ascending per (gene, stop); filled only if pos_cap >= the total
+ * Returns the total number of positions (call once with positions = NULL to size the array), negative on error.
+ */
+int64_t mgc_recoded_stops(mgc_engine *e, const mgc_gene *genes, int64_t n_genes, int32_t *counts, int64_t *pos_off,
+                          int32_t *positions, int64_t pos_cap);
+
+/*
  * Sliding-window labels (bin/pipeline.py:157-385) computed on the device from the genes of the
  * last decode.  For contig c: windows start at 0, stride, ... < len; window [start, start+w).
  *   stride[c]      per-contig stride (the host resolves the 2500/5000 default, pipeline.py:172-183)

@@ -112,6 +112,10 @@ struct ChainBufs {
     uint32_t *gene_off;             // per contig (+1)
     double *contig_total;           // per contig
 };
+// a gene located in the packed planes: slot, strand region (0 forward, 1 reverse complement), first letter and length there
+struct GeneRef {
+    int32_t slot, strand, start, n;
+};
 constexpr int PIECE_BUCKETS = 64;   // cuts are at least this many 128-nt buckets apart
 
 struct Planes {

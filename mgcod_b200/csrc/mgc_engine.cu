@@ -1105,6 +1105,62 @@ int mgc_window_counts(const int64_t *contig_len, const int32_t *stride, int32_t 
     return MGC_OK;
 }
 
+int64_t mgc_recoded_stops(mgc_engine *e, const mgc_gene *genes, int64_t n_genes, int32_t *counts, int64_t *pos_off, int32_t *positions,
+                          int64_t pos_cap) {
+    if (!e || (!genes && n_genes > 0) || n_genes < 0 || !counts || !pos_off) return mgc::set_error(MGC_E_ARG, "bad argument");
+    if (!e->have_genes) return mgc::set_error(MGC_E_ARG, "decode a batch before asking for recoded stops");
+    int64_t total = 0;
+    int rc = guarded([&] {
+        CUDA_TRY(cudaSetDevice(e->device));
+        cudaStream_t st = e->stream;
+        // genes are in the caller's record coordinates; locate each in its slot (a record split at gaps has several)
+        std::vector<int32_t> first_seg(e->n_parents + 1, 0);
+        for (size_t s = 0; s < e->segs.size(); s++) first_seg[e->segs[s].parent + 1] = (int32_t)s + 1;
+        for (int32_t c = 0; c < e->n_parents; c++) first_seg[c + 1] = std::max(first_seg[c + 1], first_seg[c]);
+        std::vector<GeneRef> refs((size_t)n_genes);
+        for (int64_t i = 0; i < n_genes; i++) {
+            const mgc_gene &g = genes[i];
+            if (g.contig < 0 || g.contig >= e->n_parents || g.left < 1 || g.right < g.left || g.right > e->h_parent_len[g.contig])
+                throw std::invalid_argument("gene " + std::to_string(i) + " lies outside its contig");
+            int32_t lo = first_seg[g.contig], hi = first_seg[g.contig + 1] - 1, slot = -1;
+            while (lo <= hi) {  // last segment starting at or before the gene
+                const int32_t mid = (lo + hi) / 2;
+                if (e->segs[mid].poff <= g.left - 1) { slot = mid; lo = mid + 1; } else hi = mid - 1;
+            }
+            if (slot < 0 || g.right - e->segs[slot].poff > e->segs[slot].len)
+                throw std::invalid_argument("gene " + std::to_string(i) + " crosses a gap");
+            const int32_t l0 = g.left - 1 - e->segs[slot].poff, r0 = g.right - 1 - e->segs[slot].poff, L = e->segs[slot].len;
+            refs[i] = GeneRef{slot, g.strand < 0 ? 1 : 0, g.strand < 0 ? L - 1 - r0 : l0, r0 - l0 + 1};
+        }
+        DevBuf d_refs, d_counts, d_off, d_pos;
+        d_refs.ensure(std::max<size_t>((size_t)n_genes * sizeof(GeneRef), 16));
+        d_counts.ensure(std::max<size_t>((size_t)n_genes * 12, 16));
+        Planes pl;
+        pl.lo = e->lo.as<uint32_t>(); pl.hi = e->hi.as<uint32_t>(); pl.nm = e->nm.as<uint32_t>(); pl.npre = e->ncount.as<uint32_t>();
+        pl.dflags = e->flags.as<int>(); pl.cflags = e->cflags.as<uint8_t>(); pl.W = e->W;
+        if (n_genes) CUDA_TRY(cudaMemcpyAsync(d_refs.p, refs.data(), (size_t)n_genes * sizeof(GeneRef), cudaMemcpyHostToDevice, st));
+        launch_recoded_stops(pl, e->cwoff.as<int64_t>(), e->clen.as<int32_t>(), d_refs.as<GeneRef>(), n_genes, d_counts.as<int32_t>(), nullptr,
+                             nullptr, false, e->n_sm, st);
+        if (n_genes) CUDA_TRY(cudaMemcpyAsync(counts, d_counts.p, (size_t)n_genes * 12, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        pos_off[0] = 0;
+        for (int64_t i = 0; i < n_genes * 3; i++) pos_off[i + 1] = pos_off[i] + counts[i];
+        total = pos_off[n_genes * 3];
+        if (positions && total > 0 && pos_cap >= total) {
+            d_off.ensure((size_t)(n_genes * 3 + 1) * 8);
+            d_pos.ensure((size_t)total * 4);
+            CUDA_TRY(cudaMemcpyAsync(d_off.p, pos_off, (size_t)(n_genes * 3 + 1) * 8, cudaMemcpyHostToDevice, st));
+            launch_recoded_stops(pl, e->cwoff.as<int64_t>(), e->clen.as<int32_t>(), d_refs.as<GeneRef>(), n_genes, nullptr, d_off.as<int64_t>(),
+                                 d_pos.as<int32_t>(), true, e->n_sm, st);
+            CUDA_TRY(cudaMemcpyAsync(positions, d_pos.p, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+        }
+        CUDA_TRY(cudaGetLastError());
+        d_refs.release(); d_counts.release(); d_off.release(); d_pos.release();
+    });
+    return rc == MGC_OK ? total : rc;
+}
+
 int mgc_window_labels(mgc_engine *e, const int32_t *stride, int32_t window, int32_t consecutive, int short_contigs,
                       const int64_t *win_offsets, int32_t *labels, int64_t *cents) {
     if (!e || !stride || !win_offsets || !labels || !cents) return mgc::set_error(MGC_E_ARG, "null argument");

@@ -1642,6 +1642,76 @@ void launch_merge_labels(const int32_t *labels, const int64_t *win_off, int32_t 
 }
 
 // ------------------------------------------------------------------------------------------------
+// in-frame stop codons inside genes (reference bin/results.py:253-294, Results.find_recoded_stops / make_seqrecord):
+// codon indices k < ncodons - 1 whose codon is TAA / TAG / TGA, per gene, ascending.  One warp per gene over the
+// packed planes of the resident batch.  FILL = false counts, FILL = true writes the indices at pos_off[g*3 + t].
+// ------------------------------------------------------------------------------------------------
+template <bool FILL>
+__global__ void __launch_bounds__(128) k_recoded_stops(Planes pl, const int64_t *__restrict__ cwoff, const int32_t *__restrict__ clen,
+                                                       const GeneRef *__restrict__ genes, int64_t n_genes, int32_t *counts,
+                                                       const int64_t *__restrict__ pos_off, int32_t *pos_out) {
+    const int lane = lane_id();
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t g = warp; g < n_genes; g += nw) {
+        const GeneRef gr = genes[g];
+        FindCtx cx;
+        const int64_t w0s = cwoff[gr.slot];
+        cx.lo = pl.lo + (int64_t)gr.strand * pl.W + w0s;
+        cx.hi = pl.hi + (int64_t)gr.strand * pl.W + w0s;
+        cx.nm = pl.dflags[1] ? pl.nm + (int64_t)gr.strand * pl.W + w0s : nullptr;
+        cx.L = clen[gr.slot];
+        cx.stop_sel = 7;
+        cx.atg_only = 0;
+        const int s = gr.start, last = gr.start + gr.n - 4;  // codon starts p with s <= p <= last, p = s mod 3: all but the final codon
+        int base[3] = {0, 0, 0};
+        if (last >= s) {
+            const int wa = s >> 5, wb = last >> 5;
+            for (int wblk = wa; wblk <= wb; wblk += 32) {
+                const int w = wblk + lane;
+                uint32_t bits[3] = {0u, 0u, 0u};
+                if (w <= wb) {
+                    const CodonMasks m = masks_at(cx, w);
+                    const int r = ((s - 32 * w) % 3 + 3) % 3;
+                    const uint32_t sel = frame_pattern(r) & bit_range(s - 32 * w, last - 32 * w);
+                    bits[0] = m.taa & sel; bits[1] = m.tag & sel; bits[2] = m.tga & sel;
+                }
+#pragma unroll
+                for (int t = 0; t < 3; t++) {
+                    const int c = __popc(bits[t]);
+                    int inc = c;  // inclusive scan over lanes
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int v = __shfl_up_sync(0xffffffffu, inc, o);
+                        if (lane >= o) inc += v;
+                    }
+                    if (FILL) {
+                        int64_t at = pos_off[g * 3 + t] + base[t] + inc - c;
+                        uint32_t b = bits[t];
+                        while (b) {
+                            const int bit = __ffs(b) - 1;
+                            b &= b - 1;
+                            pos_out[at++] = (32 * w + bit - s) / 3;
+                        }
+                    }
+                    base[t] += __shfl_sync(0xffffffffu, inc, 31);
+                }
+            }
+        }
+        if (!FILL && lane == 0) { counts[g * 3] = base[0]; counts[g * 3 + 1] = base[1]; counts[g * 3 + 2] = base[2]; }
+    }
+}
+
+void launch_recoded_stops(Planes pl, const int64_t *cwoff, const int32_t *clen, const GeneRef *genes, int64_t n_genes, int32_t *counts,
+                          const int64_t *pos_off, int32_t *pos_out, bool fill, int n_sm, cudaStream_t st) {
+    int64_t blocks = (n_genes + 3) / 4;
+    if (blocks > (int64_t)n_sm * 16) blocks = (int64_t)n_sm * 16;
+    if (blocks < 1) blocks = 1;
+    if (fill) k_recoded_stops<true><<<(unsigned)blocks, 128, 0, st>>>(pl, cwoff, clen, genes, n_genes, counts, pos_off, pos_out);
+    else k_recoded_stops<false><<<(unsigned)blocks, 128, 0, st>>>(pl, cwoff, clen, genes, n_genes, counts, pos_off, pos_out);
+}
+
+// ------------------------------------------------------------------------------------------------
 // runs of >= min_run ambiguous letters per contig (only launched when the batch has ambiguous letters)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_find_gaps(const uint32_t *__restrict__ nm, const int64_t *__restrict__ cwoff,

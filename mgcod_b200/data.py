@@ -87,6 +87,7 @@ class Data:
         self.engine = shared_engine(self.model_dir, self.device)
         buf, offs = pack_sequences([r.seq for r in recs])
         self.result = self.engine.decode_buffer(buf, offs)
+        self.engine._resident_owner = self
         self._decoded_order = recs
         ids = [r.id for r in recs]
         lens = [len(r) for r in recs]
@@ -94,6 +95,21 @@ class Data:
             if code in missing:
                 self.result.write(mi, ids, lens, str(self.path_to_genome), os.path.join(self.model_dir, f"mgm_{code}.mod"), code,
                                   self._gff_path(code), "gff")
+
+    def ensure_resident(self):
+        """→ (engine, record ids in batch order) with this genome's packed sequence resident on the device — what
+        :class:`mgcod_b200.results.Results` scans for recoded stops.  Decodes again when run_mgm was served from the
+        on-disk cache (or another genome has been decoded since)."""
+        if self.records is None:
+            self.read_dna_sequence()
+        recs = self._file_order
+        if self.engine is None:
+            self.engine = shared_engine(self.model_dir, self.device)
+        if self.result is None or getattr(self.engine, "_resident_owner", None) is not self:
+            buf, offs = pack_sequences([r.seq for r in recs])
+            self.result = self.engine.decode_buffer(buf, offs)
+        self.engine._resident_owner = self
+        return self.engine, [r.id for r in recs]
 
     # -- bin/data.py:56-106
     def extract_gene_coords(self):

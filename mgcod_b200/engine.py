@@ -205,6 +205,25 @@ class Engine:
             L.mgc_debug_candidates(self._h, model, out.ctypes.data_as(C.POINTER(Candidate)), n)
         return out
 
+    def recoded_stops(self, genes: np.ndarray) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """In-frame stop codons inside ``genes`` (GENE_DTYPE rows of the last decoded batch), on the device
+        (reference bin/results.py:253-294).  → (counts[n, 3] for TAA/TAG/TGA, offsets[n*3+1], codon indices)."""
+        L = _lib.lib()
+        g = np.ascontiguousarray(genes, dtype=GENE_DTYPE)
+        n = len(g)
+        counts = np.zeros((max(n, 1), 3), dtype=np.int32)
+        offs = np.zeros(n * 3 + 1, dtype=np.int64)
+        args = (self._h, C.c_void_p(g.ctypes.data), n, counts.ctypes.data_as(C.POINTER(C.c_int32)), offs.ctypes.data_as(C.POINTER(C.c_int64)))
+        total = L.mgc_recoded_stops(*args, None, 0)
+        if total < 0:
+            raise MgcodError(int(total), _lib.last_error())
+        pos = np.zeros(max(int(total), 1), dtype=np.int32)
+        if total:
+            total = L.mgc_recoded_stops(*args, pos.ctypes.data_as(C.POINTER(C.c_int32)), int(total))
+            if total < 0:
+                raise MgcodError(int(total), _lib.last_error())
+        return counts[:n], offs, pos[:int(total)]
+
     def window_labels(self, contig_len: Sequence[int], stride: Sequence[int], window: int, consecutive: int,
                       short_contigs: bool) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
         """→ (win_offsets[n+1], labels[nwin], cents[nwin, n_models]) for the last decoded batch

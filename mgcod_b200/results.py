@@ -1,0 +1,253 @@
+"""``Results`` — the reference's output class (bin/results.py:19-385) on top of the CUDA engine.
+
+Same constructor arguments, same files: ``<out><species>.gff`` (final annotation with a ``number of recodings``
+attribute per gene), ``<out><species>.tab`` (classification summary), ``<out><species>_stats.tab`` (codon indices
+of in-frame recoded stops), optional ``proteins_nt_/proteins_aa_<species>.fasta``.
+
+What runs where: the per-gene in-frame stop scan (``find_recoded_stops`` through ``make_seqrecord``,
+bin/results.py:253-294) runs on the GPU over the packed sequence left resident by the decode
+(``mgc_recoded_stops``); slicing/formatting the text files stays on the host.
+
+The reference attaches recodings to rows by *position*: ``stop_recodings`` is built contig by contig in sorted-id
+order (bin/results.py:362-372) but indexed with the row number of ``coords_w_isoforms``, which is in FASTA order
+(bin/results.py:58-72, 175); for a multi-FASTA whose records are not sorted the counts land on other genes.  The
+mirror reproduces that, so its files are byte-identical to the reference's (tests/golden/results_*).
+
+Supported: every run that ends with ONE genetic code (default mode, or ``--isoforms`` with uniform labels).
+Runs with a switch need ``compare_sets_of_predicted_genes`` (not built yet) and raise
+``NotImplementedError``.
+"""
+from __future__ import annotations
+
+import logging
+import os
+import warnings
+
+import numpy as np
+import pandas as pd
+
+from .engine import GENE_DTYPE, MGCOD_CODES, pack_sequences
+
+VERSION_BANNER = "GeneMark.hmm-2 version 1.17"   # line 2 of the binary's usage text (bin/results.py:185)
+STOPS = ("TAA", "TAG", "TGA")                      # order of mgc_recoded_stops' counts
+_COMP = str.maketrans("ACGTacgtNn", "TGCAtgcaNn")
+
+# standard table (bin/results.py:307-325); per genetic code one stop becomes a sense codon (:328-345)
+_BASES = "TCAG"
+_AAS = "FFLLSSSSYY**CC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG"
+_TABLE = {a + b + c: _AAS[16 * i + 4 * j + k] for i, a in enumerate(_BASES) for j, b in enumerate(_BASES)
+          for k, c in enumerate(_BASES) if _AAS[16 * i + 4 * j + k] != "*"}
+_RECODED = {"4": ("TGA", "W"), "15": ("TAG", "Q"), "101": ("TAA", "Y")}
+
+
+class Results:
+    def __init__(self, pipeline, species, path_to_predictions, path_to_genome, path_to_output, date, delete, amino_acids,
+                 nucleotides, verbosity, working_dir):
+        self.verbose = verbosity
+        self.cwd = working_dir
+        self.results = pipeline
+        self.species = species
+        self.path_to_predictions = path_to_predictions
+        self.path_to_final_annotations = path_to_output + species + ".gff"
+        self.path_to_nt_seqs = "{}proteins_nt_{}.fasta".format(path_to_output, species)
+        self.path_to_aa_seqs = "{}proteins_aa_{}.fasta".format(path_to_output, species)
+        self.path_to_genome = path_to_genome
+        self.path_to_output = path_to_output + species + ".tab"
+        self.date = date
+        self.delete = delete
+        self.amino_acids = amino_acids
+        self.nucleotides = nucleotides
+        if self.results.coords_w_isoforms is None or not isinstance(self.results.genome_label, (int, np.integer)):
+            raise NotImplementedError("results of a run with a genetic-code switch need the isoform comparison "
+                                      "(bin/pipeline.py:559-951), which this build does not have yet")
+        self.stop_recodings = self.extract_sequences()
+        logging.info(f"Writing results for {self.species}")
+        if self.verbose:
+            print(f"Writing results for {self.species}")
+        self.save_results()
+        # number of recodings into the GFF attributes, row i <- stop_recodings[i] (bin/results.py:57-75)
+        coords = self.results.coords_w_isoforms
+        attributes = coords.attributes.values.copy()
+        coords["gene_id"] = [float(a.split(";")[0].split(" ")[1]) for a in attributes]
+        for i in range(len(attributes)):
+            if not attributes[i].endswith(";"):
+                attributes[i] += ";"
+            r = self.stop_recodings[i]
+            attributes[i] = (attributes[i] + " number of recodings: "
+                             + f"total {len(r['TAA']) + len(r['TGA']) + len(r['TAG'])}, TAA {len(r['TAA'])}, "
+                             + f"TGA {len(r['TGA'])}, TAG {len(r['TAG'])};")
+        coords["attributes"] = attributes
+
+    def __call__(self):
+        self.write_stats()
+        self.write_final_results()
+        if self.delete:
+            for c in MGCOD_CODES:
+                os.remove(f"{self.path_to_predictions}mgm_{c}_{self.species}.gff")
+
+    # ---- bin/results.py:358-385 + 269-294 --------------------------------------------------------------------
+    def extract_sequences(self):
+        P = self.results
+        coords = P.coords_w_isoforms
+        engine, file_ids = P.data.ensure_resident()
+        index_of = {rid: i for i, rid in enumerate(file_ids)}
+        per_contig = []          # rows of each contig in the order the reference visits them
+        for n in range(P.nr_contigs):
+            cur = coords[coords.contig == P.sequence[n].id]
+            cur = cur[cur.logodd != "."].reset_index(drop=True)
+            per_contig.append(cur)
+        genes = np.zeros(sum(len(c) for c in per_contig), dtype=GENE_DTYPE)
+        k = 0
+        for n, cur in enumerate(per_contig):
+            m = len(cur)
+            genes["contig"][k:k + m] = index_of[P.sequence[n].id]
+            genes["left"][k:k + m] = cur.start.values
+            genes["right"][k:k + m] = cur.end.values
+            genes["strand"][k:k + m] = np.where(cur.strand.values == "-", -1, 1)
+            k += m
+        counts, offs, pos = engine.recoded_stops(genes)      # GPU: in-frame stops of every gene
+        stop_recodings = []
+        for g in range(len(genes)):
+            # dict order of the reference: TAG, TGA, TAA (bin/results.py:285-288)
+            d = {}
+            for name in ("TAG", "TGA", "TAA"):
+                t = STOPS.index(name)
+                d[name] = pos[offs[3 * g + t]:offs[3 * g + t + 1]].tolist()
+            stop_recodings.append(d)
+        if self.nucleotides or self.amino_acids:
+            nt = self._nucleotide_records(per_contig, stop_recodings)
+            if self.nucleotides:
+                _write_fasta(nt, self.path_to_nt_seqs)
+            if self.amino_acids:
+                # as in the reference, the loop bound is the gene count of the LAST contig (bin/results.py:378)
+                last = per_contig[-1] if per_contig else []
+                aa = [self.translate_seq(last.iloc[i], nt[i], stop_recodings[i]) for i in range(len(last))]
+                _write_fasta(aa, self.path_to_aa_seqs)
+        return stop_recodings
+
+    def _nucleotide_records(self, per_contig, stop_recodings):
+        """[(id, description, sequence)]: lower case, recoded in-frame stop codons upper case (bin/results.py:269-294)"""
+        out = []
+        g = 0
+        for n, cur in enumerate(per_contig):
+            rec = self.results.sequence[n]
+            for i in range(len(cur)):
+                p = cur.iloc[i]
+                s = rec.seq[p.start - 1:p.end]
+                if p.strand == "-":
+                    s = s[::-1].translate(_COMP)
+                s = list(s.lower())
+                r = stop_recodings[g]
+                for name in STOPS:
+                    for k in r[name]:
+                        s[3 * k:3 * k + 3] = [c.upper() for c in s[3 * k:3 * k + 3]]
+                desc = (f"{p.start}..{p.end},{p.source}, {p.attributes} number recodings: TAA {len(r['TAA'])},"
+                        f"TGA {len(r['TGA'])},TAG {len(r['TAG'])}")
+                out.append((f"{i + 1} {rec.id}", desc, "".join(s)))
+                g += 1
+        return out
+
+    @staticmethod
+    def find_recoded_stops(seq, stop):
+        """Host restatement (bin/results.py:253-267) for callers that have a string, not a resident batch: codon indices
+        of in-frame ``stop`` codons except the last codon, and the sequence with those codons upper-cased."""
+        seq = str(seq)
+        hits = [p for p in range(0, len(seq) - 3, 3) if seq[p:p + 3] == stop]
+        for p in hits:
+            seq = seq[:p] + seq[p:p + 3].upper() + seq[p + 3:]
+        return [p // 3 for p in hits], seq
+
+    @staticmethod
+    def translate_seq(prediction, nucleotide_seq, start_recodings):
+        """bin/results.py:296-356: translation under the gene's genetic code (stop codons dropped), lower case, amino
+        acids of recoded stops upper case."""
+        rid, desc, s = nucleotide_seq
+        table = dict(_TABLE)
+        for key, (codon, aa) in _RECODED.items():     # same substring tests as the reference: '4' in source, ...
+            if key in prediction.source:
+                table[codon] = aa
+                break
+        s = s.upper()
+        aa = []
+        for p in range(0, len(s) - len(s) % 3, 3):
+            codon = s[p:p + 3]
+            if codon in table:
+                aa.append(table[codon])
+            elif codon in STOPS:
+                continue
+            else:
+                aa.append("X")
+        aa = list("".join(aa).lower())
+        for positions in start_recodings.values():
+            for k in positions:
+                aa[k] = aa[k].upper()
+        return rid, desc, "".join(aa)
+
+    # ---- bin/results.py:86-157 (single genetic code branch) ---------------------------------------------------
+    def save_results(self):
+        first = self.results.sequence[0].id
+        with open(self.path_to_output, "w") as fh:
+            fh.write("\t\tSequence\n")
+            fh.write(f"{first}\tMajor genetic code\t{float(self.results.genome_label)}\n")
+            fh.write(f"{first}\tTotal gene count\t{float(self.results.coords_w_isoforms.shape[0])}\n")
+
+    # ---- bin/results.py:159-181 --------------------------------------------------------------------------------
+    def write_stats(self):
+        coords = self.results.coords_w_isoforms
+        with open(self.path_to_output.replace(".tab", "_stats.tab"), "w+") as stat:
+            for n, recodings in enumerate(self.stop_recodings):
+                positions, stops = [], []
+                for name, where in recodings.items():
+                    positions.extend(where)
+                    stops.extend([name] * len(where))
+                if len(set(stops)) != 1:
+                    order = np.argsort(positions)
+                    positions = [positions[i] for i in order]
+                    stops = [stops[i] for i in order]
+                line = f"{coords.loc[n, 'attributes'].split(';')[0]} recodings {len(positions)} codon_index_values"
+                for p, s in zip(positions, stops):
+                    line += f" {p} {s}"
+                stat.write(line.replace(" ", "\t") + "\n")
+
+    # ---- bin/results.py:181-251 --------------------------------------------------------------------------------
+    def write_final_results(self):
+        P = self.results
+        tables = [str(P.genome_label)]
+        parameters = ", ".join(f"{self.cwd}/dependencies/mgm_{x}.mod" for x in tables)
+        coords = P.coords_w_isoforms
+        if coords.shape[0] == 0:
+            warnings.warn("No genes were predicted, automatically assign genetic code 11")
+        columns = [c for c in P.label_to_gene_coords[0].columns.values if c in coords.columns]
+        with open(self.path_to_final_annotations, "w+") as out:
+            out.write("##gff-version 2\n")
+            out.write("#" + VERSION_BANNER + "\n")
+            out.write(f"# File with sequence: {self.path_to_genome}\n")
+            out.write(f"# File with MetaGeneMark parameters: {parameters}\n")
+            out.write(f"# translation table: {', '.join(tables)}\n")
+            out.write(f"# output date start: {self.date.strftime('%a %b %d %Y %H:%M:%S')}\n")
+            for n in range(P.nr_contigs):
+                size = len(P.sequence[n].seq)
+                cur = coords[coords.contig == P.sequence[n].id].copy()
+                cur = cur.loc[:, columns]
+                if cur.shape[0] == 0:
+                    continue
+                cur.reset_index(drop=True, inplace=True)
+                accession = cur.iloc[0, 0]
+                out.write("\n")
+                out.write(f"##sequence-region {accession} 1 {size}\n")
+                average_gene_length = int(np.round(cur.length.values.mean()))
+                total_logodd_score = np.round(cur.logodd.sum(), decimals=1)
+                average_gene_density = np.round(cur.shape[0] / (size / 1000), decimals=2)
+                cur.drop(["length", "contig"], axis=1, inplace=True)
+                cur.to_csv(out, header=False, sep="\t", index=False)
+                out.write(f"# {accession}\ttotal_logodd\t{total_logodd_score}\taverage_length\t"
+                          f"{average_gene_length}\taverage_density\t{average_gene_density}\n")
+
+
+def _write_fasta(records, path):
+    """Biopython's FASTA writer: ``>id description`` and 60 letters per line."""
+    with open(path, "w") as fh:
+        for rid, desc, s in records:
+            fh.write(f">{rid} {desc}\n")
+            for i in range(0, len(s), 60):
+                fh.write(s[i:i + 60] + "\n")
