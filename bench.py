@@ -294,7 +294,7 @@ def main():
         t0 = time.perf_counter()
         for _ in range(args.steps):
             woffs, wlab, wcents = engine.window_labels(lens, strides, 5000, 3, False)
-            merged = engine.merge_labels([wlab[woffs[i]:woffs[i + 1]] for i in range(len(lens))], 3, strict=False)
+            merged, mstatus = engine.merge_labels_flat(wlab, woffs, 3)
         torch.cuda.synchronize()
         dt_win = (time.perf_counter() - t0) / args.steps
         n_windows = int(woffs[-1])

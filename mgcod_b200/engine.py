@@ -242,26 +242,39 @@ class Engine:
                                    cents.ctypes.data_as(C.POINTER(C.c_int64))))
         return offs, labels[:nw], cents[:nw]
 
-    def merge_labels(self, labels_per_contig: Sequence[np.ndarray], consecutive: int, strict: bool = True) -> list[np.ndarray]:
-        """Device-side label smoothing (reference bin/pipeline.py:1064-1168) of every contig's window labels; noise labels =
-        all but the two most frequent labels over the whole input.  Raises IndexError where the reference does
-        (``strict=False``: such contigs keep their input labels, for bulk runs)."""
+    def merge_labels_flat(self, flat: np.ndarray, offs: np.ndarray, consecutive: int) -> tuple[np.ndarray, np.ndarray]:
+        """Label smoothing of all contigs in one device call on the flat layout ``window_labels`` returns.
+        → (merged labels, status per contig: 0 ok, 1 = the reference raises IndexError there; those keep their input)."""
         from .labels import noise_labels
-        labs = [np.ascontiguousarray(l, dtype=np.int32) for l in labels_per_contig]
-        offs = np.zeros(len(labs) + 1, dtype=np.int64)
-        np.cumsum([len(l) for l in labs], out=offs[1:])
-        flat = np.concatenate(labs) if labs else np.zeros(0, np.int32)
+        flat = np.ascontiguousarray(flat, dtype=np.int32)
+        offs = np.ascontiguousarray(offs, dtype=np.int64)
+        n = len(offs) - 1
         mask = 0
         for l in noise_labels(flat) if flat.size else []:
             mask |= 1 << int(l)
         out = np.zeros(max(int(offs[-1]), 1), dtype=np.int32)
-        status = np.zeros(max(len(labs), 1), dtype=np.int32)
+        status = np.zeros(max(n, 1), dtype=np.int32)
         _check(_lib.lib().mgc_merge_labels(self._h, flat.ctypes.data_as(C.POINTER(C.c_int32)), offs.ctypes.data_as(C.POINTER(C.c_int64)),
-                                           len(labs), consecutive, mask, out.ctypes.data_as(C.POINTER(C.c_int32)),
+                                           n, consecutive, mask, out.ctypes.data_as(C.POINTER(C.c_int32)),
                                            status.ctypes.data_as(C.POINTER(C.c_int32))))
-        if strict and (status[:len(labs)] != 0).any():
+        out = out[:int(offs[-1])]
+        status = status[:n]
+        for c in np.flatnonzero(status):
+            out[offs[c]:offs[c + 1]] = flat[offs[c]:offs[c + 1]]
+        return out, status
+
+    def merge_labels(self, labels_per_contig: Sequence[np.ndarray], consecutive: int, strict: bool = True) -> list[np.ndarray]:
+        """Device-side label smoothing (reference bin/pipeline.py:1064-1168) of every contig's window labels; noise labels =
+        all but the two most frequent labels over the whole input.  Raises IndexError where the reference does
+        (``strict=False``: such contigs keep their input labels, for bulk runs)."""
+        labs = [np.ascontiguousarray(l, dtype=np.int32) for l in labels_per_contig]
+        offs = np.zeros(len(labs) + 1, dtype=np.int64)
+        np.cumsum([len(l) for l in labs], out=offs[1:])
+        flat = np.concatenate(labs) if labs else np.zeros(0, np.int32)
+        out, status = self.merge_labels_flat(flat, offs, consecutive)
+        if strict and (status != 0).any():
             raise IndexError(f"label smoothing walks off the array for contig index {int(np.flatnonzero(status)[0])} (as the reference does)")
-        return [(labs[i] if status[i] else out[offs[i]:offs[i + 1]]).astype(np.int64) for i in range(len(labs))]
+        return [out[offs[i]:offs[i + 1]].astype(np.int64) for i in range(len(labs))]
 
     def close(self) -> None:
         if getattr(self, "_h", None) and _lib is not None and getattr(_lib, "lib", None):   # None during interpreter shutdown
