@@ -116,7 +116,8 @@ struct ChainBufs {
 struct GeneRef {
     int32_t slot, strand, start, n;
 };
-constexpr int PIECE_BUCKETS = 64;   // cuts are at least this many 128-nt buckets apart
+constexpr int PIECE_BUCKETS = 64;
+constexpr int PACK_SLACK = 64;      // bytes of slack before and after the letters in the device ASCII buffer (k_pack)   // cuts are at least this many 128-nt buckets apart
 
 struct Planes {
     const uint32_t *lo, *hi;  // [2][W + 4]

@@ -546,8 +546,8 @@ void do_upload(mgc_engine *e, const char *seq, const int64_t *offsets, int32_t n
         CUDA_TRY(cudaStreamWaitEvent(st, e->copy_done, 0));
     } else {
         CUDA_TRY(cudaStreamSynchronize(e->copy_stream));  // a prefetch nobody adopted must not outlive its host buffer
-        e->ascii.ensure((size_t)(a1 - a0) + 64);
-        CUDA_TRY(cudaMemcpyAsync(e->ascii.p, seq + a0, (size_t)(a1 - a0), cudaMemcpyHostToDevice, st));
+        e->ascii.ensure((size_t)(a1 - a0) + 2 * PACK_SLACK);
+        CUDA_TRY(cudaMemcpyAsync(e->ascii.as<char>() + PACK_SLACK, seq + a0, (size_t)(a1 - a0), cudaMemcpyHostToDevice, st));
     }
     CUDA_TRY(cudaMemcpyAsync(e->plen.p, e->h_parent_len.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
     set_slots(e);
@@ -589,7 +589,7 @@ mgc_result *run_pipeline(mgc_engine *e, bool *amb_out) {
         CUDA_TRY(cudaMemsetAsync(e->pm[i].hist.p, 0, e->pm[i].hist.bytes, st));
     }
     // pack + GC prefix
-    launch_pack(e->ascii.as<char>(), e->aoff.as<int64_t>(), e->cwoff.as<int64_t>(), e->clen.as<int32_t>(),
+    launch_pack(e->ascii.as<char>() + PACK_SLACK, e->aoff.as<int64_t>(), e->cwoff.as<int64_t>(), e->clen.as<int32_t>(),
                 e->grp2contig.as<int32_t>(), W, e->lo.as<uint32_t>(), e->hi.as<uint32_t>(), e->nm.as<uint32_t>(), e->gc.as<uint32_t>(),
                 e->ncount.as<uint32_t>(), e->flags.as<int>(), st);
     launches += 1;
@@ -924,8 +924,8 @@ int mgc_prefetch_batch(mgc_engine *e, const char *seq, const int64_t *offsets, i
         CUDA_TRY(cudaStreamSynchronize(e->copy_stream));
         const int64_t a0 = offsets[0], a1 = offsets[n_contigs];
         if (a1 < a0) throw std::invalid_argument("offsets must ascend");
-        e->ascii_next.ensure((size_t)(a1 - a0) + 64);
-        CUDA_TRY(cudaMemcpyAsync(e->ascii_next.p, seq + a0, (size_t)(a1 - a0), cudaMemcpyHostToDevice, e->copy_stream));
+        e->ascii_next.ensure((size_t)(a1 - a0) + 2 * PACK_SLACK);
+        CUDA_TRY(cudaMemcpyAsync(e->ascii_next.as<char>() + PACK_SLACK, seq + a0, (size_t)(a1 - a0), cudaMemcpyHostToDevice, e->copy_stream));
         CUDA_TRY(cudaEventRecord(e->copy_done, e->copy_stream));
         e->pending.valid = true;
         e->pending.seq = seq;

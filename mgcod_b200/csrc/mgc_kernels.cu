@@ -177,93 +177,86 @@ __global__ void k_groups(const int64_t *cwoff, int32_t n_contigs, int64_t n_grou
 }
 
 // one warp packs 32 words (1024 letters) of one strand: lane = bit position, ballot = plane word.
-// Letters outside ACGT set the ambiguity plane (U included: the reference scores it like N) (their code is 0); letters outside the IUPAC nucleotide alphabet
-// (which the reference rejects: "error, unexpected letter found in FASTA sequence") raise flag 0.
+// Letters outside ACGT set the ambiguity plane (U included: the reference scores it like N); their code is 0.  Letters
+// outside the IUPAC nucleotide alphabet (which the reference rejects: "error, unexpected letter found in FASTA sequence")
+// raise flag 0.
+//
+// Thread per (strand, plane word).  The 32 letters of a word are handled four at a time inside 32-bit registers: the
+// code bits are bits 1 and 2 of the ASCII letter (A 0x41, C 0x43, G 0x47, T 0x54: hi = b2, lo = b1 ^ b2), the ACGT test
+// is a bit formula on the upper-cased letter, and a multiply gathers one bit per byte into a nibble.  A reverse-strand
+// word is the bit-reversed complement of the forward window that mirrors it.  The ASCII buffer has PACK_SLACK bytes of
+// slack on both sides so that the aligned 36-byte read of a window may start before / end after the contig.
+__device__ __forceinline__ uint32_t nibble_of(uint32_t v) {  // v has one bit per byte (bit 0 of each): -> bit j = byte j
+    return (v * 0x01020408u) >> 24;
+}
+
+__device__ __forceinline__ bool iupac_letter(unsigned char up) {
+    return up == 'N' || up == 'U' || up == 'R' || up == 'Y' || up == 'S' || up == 'W' || up == 'K' || up == 'M' || up == 'B' ||
+           up == 'D' || up == 'H' || up == 'V';
+}
+
 __global__ void __launch_bounds__(256) k_pack(const char *__restrict__ ascii, const int64_t *__restrict__ aoff,
                                               const int64_t *__restrict__ cwoff, const int32_t *__restrict__ clen,
                                               const int32_t *__restrict__ grp2contig, int64_t W, uint32_t *lo,
                                               uint32_t *hi, uint32_t *nm, uint32_t *gccount, uint32_t *ncount, int *dflags) {
-    int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    int lane = lane_id();
-    int strand = blockIdx.y;
-    int64_t w0 = warp * 32;
-    if (w0 >= W) return;
-    uint32_t mylo = 0, myhi = 0, mynm = 0;
-    int bad = 0, amb_any = 0;
-    auto encode = [&](unsigned char ch, bool valid, uint32_t &code, bool &amb) {
-        const unsigned char up = ch & 0xDF;  // upper case
-        amb = false;
-        if (valid && !(up == 'A' || up == 'C' || up == 'G' || up == 'T')) {
-            amb = true;
-            amb_any = 1;
-            // IUPAC: R Y S W K M B D H V N, and U
-            if (!(up == 'N' || up == 'U' || up == 'R' || up == 'Y' || up == 'S' || up == 'W' || up == 'K' || up == 'M' || up == 'B' || up == 'D' ||
-                  up == 'H' || up == 'V'))
-                bad = 1;
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int strand = blockIdx.y;
+    if (w >= W) return;
+    const int c = grp2contig[w >> 2];
+    const int L = clen[c];
+    const int64_t wl = w - cwoff[c];
+    // forward window [p, p + 32) of the contig that this word shows (mirrored for the reverse strand)
+    const int64_t p = strand ? (int64_t)L - 32 * (wl + 1) : 32 * wl;
+    uint32_t f_lo = 0, f_hi = 0, f_nm = 0, valid = 0;
+    if (p < L && p > -32) {
+        const int from = p < 0 ? (int)-p : 0, to = p + 31 >= L ? (int)(L - 1 - p) : 31;
+        valid = bit_range(from, to);
+        const char *a = ascii + aoff[c] + p;
+        const uintptr_t ua = reinterpret_cast<uintptr_t>(a);
+        const uint32_t *q = reinterpret_cast<const uint32_t *>(ua & ~(uintptr_t)3);
+        const int sh8 = (int)(ua & 3) * 8;
+        uint32_t wv[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) wv[k] = __ldg(q + k);
+        uint32_t notacgt = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const uint32_t x = __funnelshift_r(wv[k], wv[k + 1], sh8);   // letters 4k .. 4k+3, first letter in the low byte
+            const uint32_t b0 = x, b1 = x >> 1, b2 = x >> 2, b3 = x >> 3, b4 = x >> 4, b6 = x >> 6, b7 = x >> 7;   // bit 5 = case
+            const uint32_t acg = ~b4 & b0 & ~(b2 & ~b1), t = b4 & b2 & ~b1 & ~b0;
+            const uint32_t ok = ~b7 & b6 & ~b3 & (acg | t) & 0x01010101u;
+            f_hi |= nibble_of(b2 & 0x01010101u) << (4 * k);
+            f_lo |= nibble_of((b1 ^ b2) & 0x01010101u) << (4 * k);
+            notacgt |= nibble_of(ok ^ 0x01010101u) << (4 * k);
         }
-        code = (ch >> 1) & 3u;         // A0 C1 G3 T2
-        code ^= code >> 1;             // A0 C1 G2 T3
-        if (strand) code = 3u - code;
-        if (!valid || amb) code = 0;
-    };
-    auto emit = [&](int r, uint32_t code, bool valid, bool amb) {
-        const uint32_t bl = __ballot_sync(0xffffffffu, code & 1u);
-        const uint32_t bh = __ballot_sync(0xffffffffu, (code >> 1) & 1u);
-        const uint32_t bn = __ballot_sync(0xffffffffu, valid && amb);
-        if (lane == r) { mylo = bl; myhi = bh; mynm = bn; }
-    };
-    const int c_first = grp2contig[w0 >> 2];
-    const int c_last = w0 + 31 < W ? grp2contig[(w0 + 31) >> 2] : -1;
-    if (c_first == c_last) {
-        // all 32 words belong to one contig: one set of contig parameters, eight independent byte loads in flight
-        const int L = clen[c_first];
-        const int64_t i0 = (w0 - cwoff[c_first]) * 32 + lane;
-        const char *src = ascii + aoff[c_first];
-        for (int r0 = 0; r0 < 32; r0 += 8) {
-            unsigned char chs[8];
-#pragma unroll
-            for (int r = 0; r < 8; r++) {
-                const int64_t i = i0 + (r0 + r) * 32;
-                chs[r] = i < L ? (unsigned char)__ldg(src + (strand ? (L - 1 - i) : i)) : (unsigned char)'A';
+        f_nm = notacgt & valid;
+        if (f_nm) {   // rare: tell IUPAC codes from letters the reference rejects
+            bool bad = false;
+            uint32_t m = f_nm;
+            while (m) {
+                const int bpos = __ffs(m) - 1;
+                m &= m - 1;
+                if (!iupac_letter((unsigned char)a[bpos] & 0xDF)) bad = true;
             }
-#pragma unroll
-            for (int r = 0; r < 8; r++) {
-                const bool valid = i0 + (r0 + r) * 32 < L;
-                uint32_t code;
-                bool amb;
-                encode(chs[r], valid, code, amb);
-                emit(r0 + r, code, valid, amb);
+            if (!strand) {
+                atomicOr(&dflags[1], 1);
+                if (bad) atomicOr(&dflags[0], 1);
             }
         }
+    }
+    const uint32_t keep = valid & ~f_nm;
+    uint32_t o_lo, o_hi, o_nm;
+    if (strand) {
+        o_lo = __brev(~f_lo & keep); o_hi = __brev(~f_hi & keep); o_nm = __brev(f_nm);
     } else {
-        for (int r = 0; r < 32; r++) {
-            int64_t w = w0 + r;
-            uint32_t code = 0;
-            bool valid = false, amb = false;
-            if (w < W) {
-                int c = grp2contig[w >> 2];
-                int L = clen[c];
-                int64_t i = (w - cwoff[c]) * 32 + lane;
-                if (i < L) {
-                    valid = true;
-                    encode((unsigned char)ascii[aoff[c] + (strand ? (L - 1 - i) : i)], true, code, amb);
-                }
-            }
-            emit(r, code, valid, amb);
-        }
+        o_lo = f_lo & keep; o_hi = f_hi & keep; o_nm = f_nm;
     }
-    if (w0 + lane < W) {
-        lo[(int64_t)strand * W + w0 + lane] = mylo;
-        hi[(int64_t)strand * W + w0 + lane] = myhi;
-        nm[(int64_t)strand * W + w0 + lane] = mynm;
-        if (!strand) {
-            gccount[w0 + lane] = 2u * __popc(mylo ^ myhi) + __popc(mynm);  // padding letters are A (code 0): they count nothing
-            ncount[w0 + lane] = __popc(mynm);
-        }
-    }
+    lo[(int64_t)strand * W + w] = o_lo;
+    hi[(int64_t)strand * W + w] = o_hi;
+    nm[(int64_t)strand * W + w] = o_nm;
     if (!strand) {
-        if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&dflags[0], 1);
-        if (__any_sync(0xffffffffu, amb_any) && lane == 0) atomicOr(&dflags[1], 1);
+        gccount[w] = 2u * __popc(o_lo ^ o_hi) + __popc(o_nm);   // padding letters are A (code 0): they count nothing
+        ncount[w] = __popc(o_nm);
     }
 }
 
@@ -895,17 +888,26 @@ __global__ void __launch_bounds__(WALK_UNIT, 2) k_walk(Planes pl, const int64_t 
                     // a run ends at the next target, at lo_pos, or where the window start leaves the current plane word
                     const int run = min(i - max(target, lo_pos) + 1, sh + 1);
                     if (!careful) {
-                        for (int r = 0; r < run; r++) {
+                        // software pipeline: the two lookups of position r+1 are in flight while position r is accumulated
+                        auto lookup = [&](double2 &c2, double2 &n2) {
                             const uint32_t lb = __funnelshift_r(l0, l1, sh) & wmask;
                             const uint32_t hb = __funnelshift_r(h0, h1, sh) & wmask;
                             const uint32_t e = (uint32_t)(ph * nfull) + ((hb << (kc + 1)) | lb);
                             const uint32_t idn = ((hb >> nsh) << (kn + 1)) | (lb >> nsh);
-                            const double2 c2 = tc[((e & ~3u) << 1) | (e & 3u) | rep2];
-                            const double2 n2 = tn[(idn << 3) | rep8];
-                            acc.cB += c2.x; acc.cA += c2.y; acc.oB += n2.x; acc.oA += n2.y;   // oB/oA hold the non-coding sums here
+                            c2 = tc[((e & ~3u) << 1) | (e & 3u) | rep2];
+                            n2 = tn[(idn << 3) | rep8];
                             sh--;
                             ph = ph == 0 ? 2 : ph - 1;
+                        };
+                        double2 c2, n2;
+                        lookup(c2, n2);
+                        for (int r = 1; r < run; r++) {
+                            double2 c3, n3;
+                            lookup(c3, n3);
+                            acc.cB += c2.x; acc.cA += c2.y; acc.oB += n2.x; acc.oA += n2.y;   // oB/oA hold the non-coding sums here
+                            c2 = c3; n2 = n3;
                         }
+                        acc.cB += c2.x; acc.cA += c2.y; acc.oB += n2.x; acc.oA += n2.y;
                     } else {
                         // a window with an ambiguous letter contributes ln COD_P_N to the coding side and ln NON_P_N to the
                         // non-coding side of each domain (so ln(COD_P_N / NON_P_N) to the log-odds)
@@ -1758,8 +1760,7 @@ void launch_groups(const int64_t *cwoff, int32_t n_contigs, int64_t n_groups, in
 void launch_pack(const char *ascii, const int64_t *aoff, const int64_t *cwoff, const int32_t *clen, const int32_t *grp2contig,
                  int64_t W, uint32_t *lo, uint32_t *hi, uint32_t *nm, uint32_t *gccount, uint32_t *ncount, int *dflags,
                  cudaStream_t st) {
-    int64_t warps = (W + 31) / 32;
-    dim3 grid((unsigned)((warps + 7) / 8), 2);
+    dim3 grid((unsigned)((W + 255) / 256), 2);
     k_pack<<<grid, 256, 0, st>>>(ascii, aoff, cwoff, clen, grp2contig, W, lo, hi, nm, gccount, ncount, dflags);
 }
 
