@@ -414,41 +414,43 @@ __device__ __forceinline__ bool make_orf(const FindCtx &cx, const DevModel &dm, 
     return true;
 }
 
-// grid.x over the 2W words of both strands, grid.y = model
+// grid.x over the 2W words of both strands, grid.y = model.
+// Phase A, lane = word: stop mask, previous in-frame stops, and the cheap length test (distance to the previous in-frame
+// stop >= GENE_MIN_LENGTH; with a minimum length above one word only the first stop of each frame in the word can pass).
+// Survivors go to a per-warp queue.  Phase B, lane = queued stop: the start-codon existence test and the record — dense
+// lanes instead of a divergent per-word loop.
+constexpr int FIND_Q = 6;   // queued stops per word: 3 frames + 3 virtual stops at the right edge
 __global__ void __launch_bounds__(128) k_orf_find(Planes pl, const int64_t *__restrict__ cwoff, const int32_t *__restrict__ clen,
                                                   const int32_t *__restrict__ grp2contig, const DevModel *__restrict__ models,
                                                   const uint32_t *const *ls_m, const uint32_t *const *ls_tile_m, OrfRec *const *orfs_m,
                                                   unsigned long long *counters_m, uint32_t cap_orf) {
+    __shared__ int q_t[4][32 * FIND_Q], q_prev[4][32 * FIND_Q];   // contig-local stop position (bit 31 = virtual), previous stop
+    __shared__ unsigned char q_src[4][32 * FIND_Q];
     const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int mi = blockIdx.y;
     const DevModel &dm = models[mi];
-    const int lane = lane_id();
-    constexpr int NBUF = 6;
-    OrfRec buf[NBUF];
-    int nb = 0;
+    const int lane = lane_id(), wib = threadIdx.x >> 5;
     OrfRec *orfs = orfs_m[mi];
     unsigned long long *counters = counters_m + (size_t)mi * 8;
-    auto push = [&](const OrfRec &r) {
-        if (nb < NBUF) buf[nb++] = r;
-        else {  // a word with more qualifying stops than the buffer holds: emit directly
-            const unsigned long long oid = atomicAdd(&counters[0], 1ull);
-            if (oid < cap_orf) orfs[oid] = r;
-        }
-    };
+    // ---- phase A ----
+    int my_t[FIND_Q], my_prev[FIND_Q];
+    int nq = 0;
+    int c = 0, L = 0, strand = 0;
+    bool right_end = false;
     if (w < 2 * pl.W) {
-        const int strand = w >= pl.W;
+        strand = w >= pl.W;
         const int64_t ws = w - (strand ? pl.W : 0);
-        const int c = grp2contig[ws >> 2];
-        const int L = clen[c];
+        c = grp2contig[ws >> 2];
+        L = clen[c];
         const int wl = (int)(ws - cwoff[c]);
         if (L >= 6 && wl * 32 <= L - 3) {  // the word holds codon starts (virtual stops sit at t <= L-3 too)
             FindCtx cx;
             cx.lo = pl.lo + (int64_t)strand * pl.W + cwoff[c];
             cx.hi = pl.hi + (int64_t)strand * pl.W + cwoff[c];
-        cx.nm = pl.dflags[1] ? pl.nm + (int64_t)strand * pl.W + cwoff[c] : nullptr;
+            cx.nm = pl.dflags[1] ? pl.nm + (int64_t)strand * pl.W + cwoff[c] : nullptr;
             cx.L = L; cx.stop_sel = dm.stop_sel; cx.atg_only = dm.atg_only;
             const uint32_t *ls = ls_m[mi];
-            const bool right_end = (pl.cflags[c] & 1) != 0;
+            right_end = (pl.cflags[c] & 1) != 0;
             const uint32_t P0 = (uint32_t)(w * 32);                      // slot-space position of bit 0
             const uint32_t Pc = (uint32_t)(((int64_t)strand * pl.W + cwoff[c]) * 32);  // ... of the contig's first letter
             const uint32_t all = stop_mask(masks_at(cx, wl), cx.stop_sel);
@@ -466,35 +468,89 @@ __global__ void __launch_bounds__(128) k_orf_find(Planes pl, const int64_t *__re
                 const uint32_t pp1 = m ? P0 + (31u - (uint32_t)__clz(m)) + 1u : carry[f];
                 return pp1 > Pc ? (int)(pp1 - 1u - Pc) : -1;
             };
-            OrfRec r;
-            uint32_t sm = all;
-            while (sm) {
-                const int b = __ffs(sm) - 1;
-                sm &= sm - 1;
-                if (make_orf(cx, dm, c, strand, wl * 32 + b, false, prev_local(b), right_end, r)) push(r);
+            auto consider = [&](int b, bool virt) {
+                const int t = wl * 32 + b, pp = prev_local(b);
+                const int s_lo = pp < 0 ? t % 3 : pp + 3, s_hi = min(t - 3, t + 3 - dm.min_len);
+                if (s_lo > s_hi) return;
+                if (nq < FIND_Q) { my_t[nq] = t | (virt ? (int)0x80000000 : 0); my_prev[nq] = pp; nq++; }
+                else {  // only with a minimum length below one word: finish this one here
+                    OrfRec r;
+                    if (make_orf(cx, dm, c, strand, t, virt, pp, right_end, r)) {
+                        const unsigned long long oid = atomicAdd(&counters[0], 1ull);
+                        if (oid < cap_orf) orfs[oid] = r;
+                    }
+                }
+            };
+            if (dm.min_len > 34) {
+                // a stop with an earlier in-frame stop in the same word is closer than GENE_MIN_LENGTH to it
+#pragma unroll
+                for (int r = 0; r < 3; r++) {
+                    const uint32_t m = all & frame_pattern(r);
+                    if (m) consider(__ffs(m) - 1, false);
+                }
+            } else {
+                uint32_t sm = all;
+                while (sm) {
+                    const int b = __ffs(sm) - 1;
+                    sm &= sm - 1;
+                    consider(b, false);
+                }
             }
             // right edge: in each frame the last full codon closes an open ORF unless it is a real stop
-            for (int f = 0; f < 3; f++) {
-                const int tv = L - 3 - ((L - 3 - f) % 3 + 3) % 3;  // largest t <= L-3 with t % 3 == f
-                if (tv < 0 || (tv >> 5) != wl) continue;
-                if ((all >> (tv & 31)) & 1u) continue;
-                if (make_orf(cx, dm, c, strand, tv, true, prev_local(tv & 31), right_end, r)) push(r);
-            }
+            if (wl * 32 + 34 >= L - 3)
+                for (int f = 0; f < 3; f++) {
+                    const int tv = L - 3 - ((L - 3 - f) % 3 + 3) % 3;  // largest t <= L-3 with t % 3 == f
+                    if (tv < 0 || (tv >> 5) != wl) continue;
+                    if ((all >> (tv & 31)) & 1u) continue;
+                    consider(tv & 31, true);
+                }
         }
     }
-    // one reservation per warp
-    uint32_t pre = (uint32_t)nb;
+    // ---- queue ----
+    uint32_t pre = (uint32_t)nq;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const uint32_t y = __shfl_up_sync(0xffffffffu, pre, o);
         if (lane >= o) pre += y;
     }
-    const uint32_t tot = __shfl_sync(0xffffffffu, pre, 31);
-    unsigned long long base = 0;
-    if (lane == 31 && tot) base = atomicAdd(&counters[0], (unsigned long long)tot);
-    base = __shfl_sync(0xffffffffu, base, 31) + pre - (uint32_t)nb;
-    for (int q = 0; q < nb; q++)
-        if (base + q < cap_orf) orfs[base + q] = buf[q];
+    const int K = (int)__shfl_sync(0xffffffffu, pre, 31);
+    if (K == 0) return;
+    pre -= (uint32_t)nq;
+    for (int q = 0; q < nq; q++) {
+        q_t[wib][pre + q] = my_t[q];
+        q_prev[wib][pre + q] = my_prev[q];
+        q_src[wib][pre + q] = (unsigned char)lane;
+    }
+    __syncwarp();
+    // ---- phase B ----
+    for (int q0 = 0; q0 < K; q0 += 32) {
+        const int q = q0 + lane;
+        OrfRec r;
+        bool ok = false;
+        // context of the source word, fetched by all lanes (a warp may span two contigs or the strand boundary)
+        const int src = q < K ? q_src[wib][q] : 0;
+        const int cs = __shfl_sync(0xffffffffu, c, src);
+        const int Ls = __shfl_sync(0xffffffffu, L, src);
+        const int ss = __shfl_sync(0xffffffffu, strand, src);
+        const int re = __shfl_sync(0xffffffffu, (int)right_end, src);
+        if (q < K) {
+            const int tq = q_t[wib][q], pp = q_prev[wib][q];
+            FindCtx cx;
+            cx.lo = pl.lo + (int64_t)ss * pl.W + cwoff[cs];
+            cx.hi = pl.hi + (int64_t)ss * pl.W + cwoff[cs];
+            cx.nm = pl.dflags[1] ? pl.nm + (int64_t)ss * pl.W + cwoff[cs] : nullptr;
+            cx.L = Ls; cx.stop_sel = dm.stop_sel; cx.atg_only = dm.atg_only;
+            ok = make_orf(cx, dm, cs, ss, tq & 0x7fffffff, tq < 0, pp, re != 0, r);
+        }
+        const uint32_t okm = __ballot_sync(0xffffffffu, ok);
+        if (okm) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(&counters[0], (unsigned long long)__popc(okm));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const unsigned long long at = base + __popc(okm & ((1u << lane) - 1u));
+            if (ok && at < cap_orf) orfs[at] = r;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
