@@ -1061,20 +1061,20 @@ __global__ void __launch_bounds__(256) k_final(Planes pl, const int64_t *__restr
             const uint32_t *nmp = pl.dflags[1] ? pl.nm + (int64_t)strand * pl.W + w0 : nullptr;
             // order ramp: orders 0..kc-1 at positions first .. first+kc-1 (window starts on a codon boundary)
             const Quad *rq = dm.rquad + (size_t)pair * dm.kr * nramp;
-            for (int j = 0; j < kc && first + j <= t - 1; j++) {
+            // The ramp shares one ambiguity test: an ambiguous letter anywhere in the first full-order window (the kc+1
+            // letters the sum starts with) silences all kc reduced-order positions (probed against the reference).
+            bool ramp_bad = false;
+            if (nmp) {
+                uint32_t nb_, dummy;
+                window_bits(nmp, nmp, first, min(kc + 1, t + 3 - first), nb_, dummy);
+                ramp_bad = nb_ != 0;
+            }
+            for (int j = 0; j < kc && first + j <= t - 1 && !ramp_bad; j++) {
                 uint32_t hb, lb;
                 window_bits(lo, hi, first, j + 1, hb, lb);
                 const Quad *q = rq + (size_t)j * nramp + ((hb << (j + 1)) | lb);
-                double2 x = __ldg(reinterpret_cast<const double2 *>(q));
-                double2 y = __ldg(reinterpret_cast<const double2 *>(q) + 1);
-                if (nmp) {
-                    uint32_t nb_, dummy;
-                    window_bits(nmp, nmp, first, j + 1, nb_, dummy);
-                    if (nb_) {   // ambiguous letter in the ramp window: constant terms
-                        x = make_double2(dm.pair_amb[pair * 4 + 0], dm.pair_amb[pair * 4 + 0] - dm.pair_amb[pair * 4 + 2]);
-                        y = make_double2(dm.pair_amb[pair * 4 + 1], dm.pair_amb[pair * 4 + 1] - dm.pair_amb[pair * 4 + 3]);
-                    }
-                }
+                const double2 x = __ldg(reinterpret_cast<const double2 *>(q));
+                const double2 y = __ldg(reinterpret_cast<const double2 *>(q) + 1);
                 acc.cB += x.x; acc.oB += x.y; acc.cA += y.x; acc.oA += y.y;
             }
             if (secB >= 0 || secA >= 0) {

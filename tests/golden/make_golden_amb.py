@@ -42,6 +42,21 @@ def build_records():
     recs.append(("gap_at_end", mutate(base, [(11900, 100, "N"), (2000, 45, "N")])))
     recs.append(("two_gaps_close", mutate(base, [(4000, 60, "N"), (4100, 60, "N")])))
     recs.append(("all_gap", "N" * 300))
+    # ambiguous letters right behind start codons (the order-ramp positions) of the genes gmhmmp2 finds in the clean slice
+    import subprocess
+    with tempfile.TemporaryDirectory() as tmp:
+        mod = os.path.join(tmp, "m.mod")
+        open(mod, "wb").write(lzma.open(f"{HERE}/trained/mgm_11.mod.xz").read())
+        fa = os.path.join(tmp, "b.fa")
+        open(fa, "w").write(">b\n" + base + "\n")
+        ramp = list(base)
+        for line in run_gm(mod, fa).split("\n"):
+            f = line.split("\t")
+            if len(f) > 8 and f[2] == "CDS" and rng.random() < 0.7:
+                left, right = int(f[3]), int(f[4])
+                for o in rng.sample(range(3, 11), rng.choice([1, 2, 3])):
+                    ramp[left - 1 + o if f[6] == "+" else right - 1 - o] = rng.choice("NNRY")
+    recs.append(("ramp_ns", "".join(ramp)))
     recs.append(("clean", seq[60000:66000]))
     return recs
 
