@@ -938,7 +938,13 @@ __global__ void __launch_bounds__(WALK_UNIT, 2) k_walk(Planes pl, const int64_t 
                 int ph = (((-1 - kc) % 3) + 3) % 3;   // codon position of the window's first letter at i = t-1
                 // the (kc+1)-letter window ending at i starts at bit `sh` of plane word `w`; the word pair (w, w+1) sits in registers
                 int w = (i - kc) >> 5, sh = (i - kc) & 31;
-                uint32_t l0 = lo[w], l1 = lo[w + 1], h0 = hi[w], h1 = hi[w + 1];
+                // plane words come in 16-byte groups (4 words = 128 letters) held in registers: one sector request per
+                // group instead of one per word (the L1 is too small for 512 concurrent item streams per SM)
+                const uint4 *lo4 = reinterpret_cast<const uint4 *>(lo), *hi4 = reinterpret_cast<const uint4 *>(hi);
+                uint4 gl = lo4[w >> 2], gh = hi4[w >> 2];
+                auto pick = [](const uint4 &v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : v.w)); };
+                uint32_t l0 = pick(gl, w & 3), h0 = pick(gh, w & 3);
+                uint32_t l1 = (w & 3) == 3 ? lo[w + 1] : pick(gl, (w & 3) + 1), h1 = (w & 3) == 3 ? hi[w + 1] : pick(gh, (w & 3) + 1);
                 const int lo_pos = it.lo_pos;
                 while (i >= lo_pos) {
                     // a run ends at the next target, at lo_pos, or where the window start leaves the current plane word
@@ -987,7 +993,8 @@ __global__ void __launch_bounds__(WALK_UNIT, 2) k_walk(Planes pl, const int64_t 
                         w--;
                         sh = 31;
                         l1 = l0; h1 = h0;
-                        l0 = lo[w]; h0 = hi[w];
+                        if ((w & 3) == 3) { gl = lo4[w >> 2]; gh = hi4[w >> 2]; }
+                        l0 = pick(gl, w & 3); h0 = pick(gh, w & 3);
                     }
                     while (i + 1 == target) {   // a virtual and a real start may share their first full-order position
                         Acc4 out;
@@ -1069,9 +1076,10 @@ __global__ void __launch_bounds__(256) k_final(Planes pl, const int64_t *__restr
                 window_bits(nmp, nmp, first, min(kc + 1, t + 3 - first), nb_, dummy);
                 ramp_bad = nb_ != 0;
             }
+            uint32_t rhb = 0, rlb = 0;   // the kc letters at `first`, read once; order j uses the first j+1 of them
+            if (kc > 0 && !ramp_bad) window_bits(lo, hi, first, kc, rhb, rlb);
             for (int j = 0; j < kc && first + j <= t - 1 && !ramp_bad; j++) {
-                uint32_t hb, lb;
-                window_bits(lo, hi, first, j + 1, hb, lb);
+                const uint32_t jm = (2u << j) - 1u, hb = rhb & jm, lb = rlb & jm;
                 const Quad *q = rq + (size_t)j * nramp + ((hb << (j + 1)) | lb);
                 const double2 x = __ldg(reinterpret_cast<const double2 *>(q));
                 const double2 y = __ldg(reinterpret_cast<const double2 *>(q) + 1);
