@@ -1247,6 +1247,58 @@ __device__ __forceinline__ void chain_eval_lane(const ChainBufs &B, const ChainR
     }
 }
 
+// The same evaluation for ONE candidate with the whole warp: lane l looks at predecessor state top - l.  The states
+// are ordered by right end, so the overlapping ones (right >= gl) are the last few; the first state below them gives
+// the best non-overlapping predecessor through its prefix maximum.  All arguments and results are warp-uniform.
+__device__ __forceinline__ void chain_eval_warp(const ChainBufs &B, const ChainRing &R, uint32_t cs, const ChainState &S, int gl,
+                                                int glen, int gstrand, double &b_non, int &bp_non, double &b_ov, int &bp_ov) {
+    const int lane = lane_id();
+    const int ring_lo = S.head - CHAIN_RING;  // states k >= ring_lo are in shared memory
+    double best_v = 0.0;
+    int best_k = 0x7fffffff;
+    int k_non = -1;
+    for (int top = S.na - 1; top >= 0; top -= 32) {
+        const int k = top - lane;
+        const bool valid = k >= 0;
+        const bool inr = k >= ring_lo;
+        const int r = k & (CHAIN_RING - 1);
+        int rh = 0x7fffffff, lh = 0x7fffffff;
+        if (valid) {
+            rh = inr ? R.right[r] : B.av_right[cs + k];
+            lh = inr ? R.left[r] : B.av_left[cs + k];
+        }
+        if (valid && rh >= gl && lh < gl) {
+            const int ls = inr ? R.ls[r] : B.av_ls[cs + k];
+            const double ch = inr ? R.cum[r] : B.av_cum[cs + k];
+            const double v = ch - overlap_penalty(gl, glen, gstrand, rh, ls >> 1, (ls & 1) ? -1 : 1);
+            if (v >= best_v && v > 0.0) { best_v = v; best_k = k; }  // a lane meets its states in descending k: ties go to the earliest
+        }
+        const uint32_t below = __ballot_sync(0xffffffffu, valid && rh < gl);
+        if (below) { k_non = top - (__ffs(below) - 1); break; }
+    }
+    // best overlapping predecessor over the lanes: largest v, ties to the smallest k (v > 0: bit order = value order)
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(best_v);
+    const uint32_t hi = __reduce_max_sync(0xffffffffu, (uint32_t)(bits >> 32));
+    const bool in2 = (uint32_t)(bits >> 32) == hi;
+    const uint32_t lo = __reduce_max_sync(0xffffffffu, in2 ? (uint32_t)bits : 0u);
+    const bool in3 = in2 && (uint32_t)bits == lo;
+    const uint32_t kmin = __reduce_min_sync(0xffffffffu, in3 ? (uint32_t)best_k : 0xffffffffu);
+    const double vmax = __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+    b_non = 0.0;
+    bp_non = -1;
+    if (k_non >= 0) {
+        const bool inr = k_non >= ring_lo;
+        const double pm = inr ? R.pmax[k_non & (CHAIN_RING - 1)] : B.av_pmax[cs + k_non];
+        if (pm > 0.0) { b_non = pm; bp_non = inr ? R.parg[k_non & (CHAIN_RING - 1)] : B.av_parg[cs + k_non]; }
+    }
+    b_ov = 0.0;
+    bp_ov = -1;
+    if (vmax > 0.0 && kmin != 0x7fffffffu && vmax > b_non) {  // an overlap wins only if strictly better
+        b_ov = vmax;
+        bp_ov = (int)kmin >= ring_lo ? R.idx[kmin & (CHAIN_RING - 1)] : B.av_idx[cs + kmin];
+    }
+}
+
 // current shared pointer of a reverse-strand ORF (warp-uniform call)
 __device__ __forceinline__ int gp_lookup(const ChainBufs &B, const ChainRing &R, uint32_t orf, int flags) {
     if (flags & 8) return GPTR_UNSET;  // first surviving start of its ORF in chain order: nothing stored yet
@@ -1283,7 +1335,14 @@ __device__ __forceinline__ void chain_bucket(const ChainBufs &B, ChainRing &R, u
         pending = pending && !ing;
         double b_non = 0, b_ov = 0;
         int bp_non = -1, bp_ov = -1;
-        if (ing) chain_eval_lane(B, R, cs, S, me.left, me.len, me.strand, b_non, bp_non, b_ov, bp_ov);
+        for (uint32_t gm = __ballot_sync(0xffffffffu, ing); gm; gm &= gm - 1) {  // the members one by one, 32 states at a time
+            const int o = __ffs(gm) - 1;
+            double r_bn, r_bo;
+            int r_pn, r_po;
+            chain_eval_warp(B, R, cs, S, __shfl_sync(0xffffffffu, me.left, o), __shfl_sync(0xffffffffu, me.len, o),
+                            __shfl_sync(0xffffffffu, (int)me.strand, o), r_bn, r_pn, r_bo, r_po);
+            if (lane == o) { b_non = r_bn; bp_non = r_pn; b_ov = r_bo; bp_ov = r_po; }
+        }
         const double cumg = me.total + (bp_ov >= 0 ? b_ov : b_non);
         if (ing) {
             B.cum[bs + lane] = cumg;
