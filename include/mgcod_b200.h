@@ -159,6 +159,19 @@ int mgc_write_gff(const mgc_result *r, int model, const char *const *contig_ids,
                   int32_t n_contigs, const char *seq_file_name, const char *mod_file_name, int gcode,
                   const char *out_path, const char *format /* "gff" | "lst" */);
 
+/* ---- FASTA ingest (bin/data.py:108-124, Biopython SeqIO.parse) — host only ----
+ * Reads a (multi-)FASTA file into ONE contiguous letter buffer + offsets, the layout mgc_decode_batch takes.  Record id =
+ * first whitespace-delimited token of the defline (Biopython's rec.id); records keep file order (gmhmmp2's output order).
+ * page_locked != 0 asks for page-locked memory so that the H2D copy can overlap (falls back to ordinary pages). */
+typedef struct mgc_fasta mgc_fasta;
+int mgc_fasta_read(const char *path, int page_locked, mgc_fasta **out);
+int32_t mgc_fasta_num_records(const mgc_fasta *f);
+const char *mgc_fasta_id(const mgc_fasta *f, int32_t i);
+const char *mgc_fasta_defline(const mgc_fasta *f, int32_t i);
+const char *mgc_fasta_sequence(const mgc_fasta *f);      /* concatenated letters, no separators */
+const int64_t *mgc_fasta_offsets(const mgc_fasta *f);    /* n + 1 entries */
+void mgc_fasta_free(mgc_fasta *f);
+
 /* ---- synthetic workload (BASELINE.json config 5) — host only ---- */
 /* Draws contig lengths ~ L^-2 on [min_len,max_len] until total >= total_bp; returns count. */
 int64_t mgc_synth_lengths(uint64_t seed, int64_t total_bp, int32_t min_len, int32_t max_len, int64_t *lens,

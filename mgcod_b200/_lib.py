@@ -41,6 +41,7 @@ EXPORTS = (
     "mgc_engine_stats", "mgc_result_num_genes", "mgc_result_genes", "mgc_result_contig_totals",
     "mgc_result_model_cents", "mgc_result_min_gene_length", "mgc_result_set_min_gene_length", "mgc_result_free", "mgc_result_create", "mgc_recoded_stops", "mgc_window_counts", "mgc_window_labels", "mgc_merge_labels", "mgc_debug_candidates",
     "mgc_write_gff", "mgc_synth_lengths", "mgc_synth_contigs",
+    "mgc_fasta_read", "mgc_fasta_num_records", "mgc_fasta_id", "mgc_fasta_defline", "mgc_fasta_sequence", "mgc_fasta_offsets", "mgc_fasta_free",
 )
 
 _LIB = None
@@ -100,6 +101,18 @@ def lib():
     L.mgc_synth_lengths.argtypes = [C.c_uint64, i64, i32, i32, C.POINTER(i64), i64]
     L.mgc_synth_lengths.restype = i64
     L.mgc_synth_contigs.argtypes = [C.c_uint64, C.POINTER(i64), i64, vp, C.POINTER(i32), C.c_int]
+    L.mgc_fasta_read.argtypes = [cp, C.c_int, C.POINTER(vp)]
+    L.mgc_fasta_num_records.argtypes = [vp]
+    L.mgc_fasta_num_records.restype = i32
+    L.mgc_fasta_id.argtypes = [vp, i32]
+    L.mgc_fasta_id.restype = cp
+    L.mgc_fasta_defline.argtypes = [vp, i32]
+    L.mgc_fasta_defline.restype = cp
+    L.mgc_fasta_sequence.argtypes = [vp]
+    L.mgc_fasta_sequence.restype = vp
+    L.mgc_fasta_offsets.argtypes = [vp]
+    L.mgc_fasta_offsets.restype = C.POINTER(i64)
+    L.mgc_fasta_free.argtypes = [vp]
     _LIB = L
     return L
 

@@ -5,8 +5,10 @@
 // back with pandas (bin/data.py:66-96) and caches it on disk (bin/data.py:39).
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <ctime>
+#include <memory>
 #include <string>
 #include <thread>
 #include <vector>
@@ -253,3 +255,91 @@ int mgc_synth_contigs(uint64_t seed, const int64_t *lens, int64_t n, char *seq, 
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// FASTA ingest (replaces Biopython's SeqIO.parse at bin/data.py:108-124 for large inputs): the file is mapped, header
+// lines are located with memchr, sequence lines are copied without their line ends into ONE buffer, which can be
+// page-locked so that mgc_decode_batch / mgc_prefetch_batch copy from it asynchronously.
+// ------------------------------------------------------------------------------------------------
+#include <cuda_runtime.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+struct mgc_fasta {
+    std::vector<std::string> ids, deflines;
+    std::vector<int64_t> offsets;
+    char *seq = nullptr;
+    bool pinned = false;
+    ~mgc_fasta() {
+        if (seq) {
+            if (pinned) cudaFreeHost(seq);
+            else std::free(seq);
+        }
+    }
+};
+
+int mgc_fasta_read(const char *path, int page_locked, mgc_fasta **out) {
+    if (!path || !out) return mgc::set_error(MGC_E_ARG, "null argument");
+    const int fd = ::open(path, O_RDONLY);
+    if (fd < 0) return mgc::set_error(MGC_E_IO, std::string("error, cannot open file: ") + path);
+    struct stat sb;
+    if (::fstat(fd, &sb) != 0) { ::close(fd); return mgc::set_error(MGC_E_IO, std::string("cannot stat ") + path); }
+    const size_t size = (size_t)sb.st_size;
+    const char *map = nullptr;
+    if (size) {
+        map = static_cast<const char *>(::mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0));
+        if (map == MAP_FAILED) { ::close(fd); return mgc::set_error(MGC_E_IO, std::string("cannot map ") + path); }
+        ::madvise(const_cast<char *>(map), size, MADV_SEQUENTIAL);
+    }
+    std::unique_ptr<mgc_fasta> f(new mgc_fasta());
+    if (page_locked && cudaHostAlloc(reinterpret_cast<void **>(&f->seq), size + 64, cudaHostAllocDefault) == cudaSuccess) f->pinned = true;
+    else {
+        cudaGetLastError();  // no device / no memory: ordinary pages still work, copies are then staged by the driver
+        f->seq = static_cast<char *>(std::malloc(size + 64));
+    }
+    if (!f->seq) {
+        if (map) ::munmap(const_cast<char *>(map), size);
+        ::close(fd);
+        return mgc::set_error(MGC_E_NOMEM, "out of host memory");
+    }
+    int64_t n = 0;
+    const char *p = map, *end = map + size;
+    bool in_record = false;
+    while (p < end) {
+        const char *nl = static_cast<const char *>(std::memchr(p, '\n', (size_t)(end - p)));
+        const char *le = nl ? nl : end;
+        const char *a = p, *b = le;
+        while (b > a && (b[-1] == '\r' || b[-1] == ' ' || b[-1] == '\t')) b--;
+        if (a < b && *a == '>') {
+            f->offsets.push_back(n);   // start of this record; the end of the last one is appended after the loop
+            std::string def(a + 1, b);
+            size_t k = 0;
+            while (k < def.size() && def[k] != ' ' && def[k] != '\t') k++;
+            f->ids.emplace_back(def.substr(0, k));
+            f->deflines.emplace_back(std::move(def));
+            in_record = true;
+        } else if (in_record) {
+            while (a < b && (*a == ' ' || *a == '\t')) a++;
+            std::memcpy(f->seq + n, a, (size_t)(b - a));
+            n += b - a;
+        }
+        p = nl ? nl + 1 : end;
+    }
+    f->offsets.push_back(n);
+    if (f->ids.empty()) f->offsets.assign(1, 0);
+    if (map) ::munmap(const_cast<char *>(map), size);
+    ::close(fd);
+    *out = f.release();
+    return MGC_OK;
+}
+
+int32_t mgc_fasta_num_records(const mgc_fasta *f) { return f ? (int32_t)f->ids.size() : -1; }
+const char *mgc_fasta_id(const mgc_fasta *f, int32_t i) { return f && i >= 0 && i < (int32_t)f->ids.size() ? f->ids[i].c_str() : nullptr; }
+const char *mgc_fasta_defline(const mgc_fasta *f, int32_t i) {
+    return f && i >= 0 && i < (int32_t)f->deflines.size() ? f->deflines[i].c_str() : nullptr;
+}
+const char *mgc_fasta_sequence(const mgc_fasta *f) { return f ? f->seq : nullptr; }
+const int64_t *mgc_fasta_offsets(const mgc_fasta *f) { return f ? f->offsets.data() : nullptr; }
+void mgc_fasta_free(mgc_fasta *f) { delete f; }

@@ -87,3 +87,27 @@ def test_plane_index_layout():
         hi |= (code >> 1) << r
         lo |= (code & 1) << r
     assert (hi, lo) == (0b101, 0b100)
+
+
+def test_native_fasta_reader_matches_python_reader(tmp_path):
+    """mgc_fasta_read vs the plain Python reader: ids, deflines, sequences; CRLF, blank lines, spaces, lower case, an empty
+    record, no trailing newline"""
+    from mgcod_b200.data import Fasta
+    from mgcod_b200.synth import read_fasta
+    text = (">one first record\r\nACGTAC\r\nGGTT \r\n\r\n>two\n\nacgtnn\n  TTAA\n>empty\n>four|x  y\tz\nAC\nG")
+    p = tmp_path / "x.fa"
+    p.write_bytes(text.encode())
+    f = Fasta(str(p), page_locked=False)
+    want = read_fasta(str(p))
+    assert f.ids == [w[0] for w in want] == ["one", "two", "empty", "four|x"]
+    assert f.deflines == [w[1] for w in want]
+    recs = f.records()
+    assert [r.seq for r in recs] == [w[2] for w in want] == ["ACGTACGGTT", "acgtnnTTAA", "", "ACG"]
+    assert [len(r) for r in recs] == [10, 10, 0, 3]
+    assert f.offsets.tolist() == [0, 10, 20, 20, 23]
+    f.close()
+    empty = tmp_path / "e.fa"
+    empty.write_bytes(b"")
+    assert Fasta(str(empty), page_locked=False).ids == []
+    with pytest.raises(OSError):
+        Fasta(str(tmp_path / "missing.fa"))
