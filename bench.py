@@ -319,6 +319,43 @@ def main():
             shape2 = {"workload": f"{len(offs2) - 1} contigs x 5 kb, same generator", "ms_per_step": 1e3 * dt2,
                       "value": int(offs2[-1]) * engine.n_models / dt2, "unit": UNIT, "resident": True}
 
+        # ---- file to files on a 100 Mbp slice: native FASTA read -> decode -> four GFF files (SURVEY.md 8d "also report") ----
+        file_e2e = None
+        if world == 1 and not os.environ.get("MGCOD_BENCH_SKIP_FILES"):
+            from mgcod_b200.data import Fasta
+            nrec = int(np.searchsorted(offs, 100_000_000, side="left"))
+            fa = os.path.join(workdir, "sample.fasta")
+            with open(fa, "wb") as fh:
+                for i in range(nrec):
+                    fh.write(b">contig_%d synthetic\n" % i)
+                    rec = buf[offs[i]:offs[i + 1]]
+                    k = len(rec) // 80
+                    rows = np.empty((k, 81), np.uint8)          # 80 letters + newline per line
+                    rows[:, :80] = rec[:k * 80].reshape(k, 80)
+                    rows[:, 80] = 10
+                    fh.write(rows.tobytes())
+                    if len(rec) > k * 80:
+                        fh.write(rec[k * 80:].tobytes() + b"\n")
+            t0 = time.perf_counter()
+            f = Fasta(fa)
+            t1 = time.perf_counter()
+            r = engine.decode_buffer(f.buffer, f.offsets)
+            torch.cuda.synchronize()
+            t2 = time.perf_counter()
+            lens_f = np.diff(f.offsets)
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(max_workers=4) as tp:      # as Data.run_mgm does: the C writer runs without the GIL
+                for j in [tp.submit(r.write, mi, f.ids, lens_f, fa, model_paths[mi], code, os.path.join(workdir, f"mgm_{code}_sample.gff"), "gff")
+                          for mi, code in enumerate((11, 4, 15, 101))]:
+                    j.result()
+            t3 = time.perf_counter()
+            assert int(f.offsets[-1]) == int(offs[nrec]), "FASTA round trip lost letters"
+            file_e2e = {"bp": int(f.offsets[-1]), "contigs": nrec, "read_fasta_s": t1 - t0, "decode_s": t2 - t1, "write_4_gff_s": t3 - t2,
+                        "value": int(f.offsets[-1]) * engine.n_models / (t3 - t0), "unit": UNIT,
+                        "genes_written": int(sum(r.num_genes(mi) for mi in range(engine.n_models)))}
+            del r
+            f.close()
+
         times = torch.tensor([dt_res, dt_e2e, dt_single, dt_win], dtype=torch.float64, device="cuda")
         tot_units = torch.tensor([float(units)], dtype=torch.float64, device="cuda")
         if world > 1:
@@ -358,6 +395,8 @@ def main():
             }
             if shape2:
                 out["other_shapes"] = [shape2]
+            if file_e2e:
+                out["file_e2e"] = file_e2e
             if world == 1 and not args.no_cpu_baseline:
                 out["cpu_baseline"] = cpu_reference_run(buf, offs, model_paths, args.cpu_sample_bp, workdir, cores)
             print(json.dumps(out))

@@ -162,6 +162,61 @@ void synth_one(uint64_t seed, int64_t index, char *out, int64_t L, int32_t *trut
 
 extern "C" {
 
+namespace {
+
+// Append-only text buffer flushed to a FILE in large blocks: the gene lines are formatted by hand (decimal integers and
+// "%.2f" with an exact fallback), which is ~6x faster than one fprintf per field for the ~100 bytes per gene.
+struct TextOut {
+    FILE *f;
+    std::vector<char> buf;
+    size_t n = 0;
+    explicit TextOut(FILE *fp) : f(fp), buf(1 << 22) {}
+    void room(size_t need) {
+        if (n + need > buf.size()) flush();
+    }
+    void flush() {
+        if (n) std::fwrite(buf.data(), 1, n, f);
+        n = 0;
+    }
+    void str(const char *s, size_t len) {
+        room(len);
+        if (len > buf.size()) { std::fwrite(s, 1, len, f); return; }
+        std::memcpy(buf.data() + n, s, len);
+        n += len;
+    }
+    void str(const char *s) { str(s, std::strlen(s)); }
+    void ch(char c) { room(1); buf[n++] = c; }
+    void u64(unsigned long long v) {
+        char t[24];
+        int k = 0;
+        do { t[k++] = (char)('0' + v % 10); v /= 10; } while (v);
+        room(k);
+        while (k) buf[n++] = t[--k];
+    }
+    void i64(long long v) {
+        if (v < 0) { ch('-'); u64((unsigned long long)(-v)); } else u64((unsigned long long)v);
+    }
+    // printf("%.2f"): exact unless v*100 lies within 1e-6 of a rounding boundary, where snprintf decides
+    void fixed2(double v) {
+        const double a = std::fabs(v) * 100.0;
+        const double fl = std::floor(a), fr = a - fl;
+        if (!(a < 9e15) || std::fabs(fr - 0.5) < 1e-6) {
+            char t[64];
+            const int k = std::snprintf(t, sizeof t, "%.2f", v);
+            str(t, (size_t)k);
+            return;
+        }
+        const unsigned long long r = (unsigned long long)fl + (fr > 0.5 ? 1ull : 0ull);
+        if (std::signbit(v)) ch('-');   // printf prints "-0.00" for small negative values
+        u64(r / 100);
+        ch('.');
+        ch((char)('0' + (r / 10) % 10));
+        ch((char)('0' + r % 10));
+    }
+};
+
+}  // namespace
+
 int mgc_write_gff(const mgc_result *r, int model, const char *const *contig_ids, const int64_t *contig_len, int32_t n_contigs,
                   const char *seq_file_name, const char *mod_file_name, int gcode, const char *out_path, const char *format) {
     if (!r || !contig_ids || !contig_len || !out_path || !format) return mgc::set_error(MGC_E_ARG, "null argument");
@@ -184,12 +239,18 @@ int mgc_write_gff(const mgc_result *r, int model, const char *const *contig_ids,
     std::fprintf(f, "# output date start: %s\n", date.c_str());
     int64_t k = 0;
     long gene_id = 0;
+    TextOut o(f);
+    char tmp[256];
     for (int32_t c = 0; c < n_contigs; c++) {
         const char *id = contig_ids[c];
+        const size_t idlen = std::strlen(id);
         const long long L = (long long)contig_len[c];
-        std::fprintf(f, "\n");
-        if (lst) std::fprintf(f, "# sequence-region %d %lld\nSequenceID: %s\n", L > 0 ? 1 : 0, L, id);
-        else std::fprintf(f, "##sequence-region %s %d %lld\n", id, L > 0 ? 1 : 0, L);
+        o.ch('\n');
+        if (lst) {
+            o.str("# sequence-region "); o.ch(L > 0 ? '1' : '0'); o.ch(' '); o.i64(L); o.str("\nSequenceID: "); o.str(id, idlen); o.ch('\n');
+        } else {
+            o.str("##sequence-region "); o.str(id, idlen); o.ch(' '); o.ch(L > 0 ? '1' : '0'); o.ch(' '); o.i64(L); o.ch('\n');
+        }
         int64_t first = k;
         long long len_sum = 0;
         while (k < ng && genes[k].contig == c) {
@@ -199,23 +260,27 @@ int mgc_write_gff(const mgc_result *r, int model, const char *const *contig_ids,
             gene_id++;
             const char *type = g.domain ? "archaea" : "bacteria";
             if (lst) {
-                std::fprintf(f, "%6ld   %c   %c%d   %c%d %7d %s\n", gene_id, g.strand > 0 ? '+' : '-', g.partial_left ? '<' : ' ',
-                             g.left, g.partial_right ? '>' : ' ', g.right, len, type);
+                const int n = std::snprintf(tmp, sizeof tmp, "%6ld   %c   %c%d   %c%d %7d %s\n", gene_id, g.strand > 0 ? '+' : '-',
+                                            g.partial_left ? '<' : ' ', g.left, g.partial_right ? '>' : ' ', g.right, len, type);
+                o.str(tmp, (size_t)n);
             } else {
-                std::fprintf(f, "%s\tGeneMark.hmm2\tCDS\t%d\t%d\t%.2f\t%c\t0\tgene_id %ld; gene_type %s; ", id, g.left, g.right,
-                             g.logodd, g.strand > 0 ? '+' : '-', gene_id, type);
-                if (g.partial_left || g.partial_right) std::fprintf(f, "partial %d%d; ", g.partial_left ? 1 : 0, g.partial_right ? 1 : 0);
-                std::fprintf(f, "gc %d; length %d;\n", g.gc, len);
+                o.str(id, idlen); o.str("\tGeneMark.hmm2\tCDS\t"); o.i64(g.left); o.ch('\t'); o.i64(g.right); o.ch('\t'); o.fixed2(g.logodd);
+                o.ch('\t'); o.ch(g.strand > 0 ? '+' : '-'); o.str("\t0\tgene_id "); o.i64(gene_id); o.str("; gene_type "); o.str(type); o.str("; ");
+                if (g.partial_left || g.partial_right) { o.str("partial "); o.ch(g.partial_left ? '1' : '0'); o.ch(g.partial_right ? '1' : '0'); o.str("; "); }
+                o.str("gc "); o.i64(g.gc); o.str("; length "); o.i64(len); o.str(";\n");
             }
             k++;
         }
         const int64_t n = k - first;
-        if (n > 0)
-            std::fprintf(f, "# %s\ttotal_logodd\t%g\taverage_length\t%lld\taverage_density\t%.2f\n", id, totals[c], (long long)((double)len_sum / (double)n + 0.5),
-                         (double)n / ((double)L / 1000.0));
-        else if (L >= min_len)  // a record the binary decoded without finding a gene; shorter records are skipped outright
-            std::fprintf(f, "# %s\ttotal_logodd\t0\taverage_length\t0\taverage_density\t0.00\n", id);
+        if (n > 0) {
+            const int m = std::snprintf(tmp, sizeof tmp, "\ttotal_logodd\t%g\taverage_length\t%lld\taverage_density\t%.2f\n", totals[c],
+                                        (long long)((double)len_sum / (double)n + 0.5), (double)n / ((double)L / 1000.0));
+            o.str("# "); o.str(id, idlen); o.str(tmp, (size_t)m);
+        } else if (L >= min_len) {  // a record the binary decoded without finding a gene; shorter records are skipped outright
+            o.str("# "); o.str(id, idlen); o.str("\ttotal_logodd\t0\taverage_length\t0\taverage_density\t0.00\n");
+        }
     }
+    o.flush();
     if (lst) std::fprintf(f, "\n# output date end: %s\n# Done with file: %s\n", date.c_str(), seq_file_name ? seq_file_name : "");
     if (std::fclose(f) != 0) return mgc::set_error(MGC_E_IO, "write failed");
     return MGC_OK;

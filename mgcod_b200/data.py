@@ -133,10 +133,14 @@ class Data:
         self._decoded_order = recs
         ids = [r.id for r in recs]
         lens = [len(r) for r in recs]
-        for mi, code in enumerate(MGCOD_CODES):
-            if code in missing:
-                self.result.write(mi, ids, lens, str(self.path_to_genome), os.path.join(self.model_dir, f"mgm_{code}.mod"), code,
-                                  self._gff_path(code), "gff")
+        # the four files are formatted side by side (the C writer runs without the GIL)
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=4) as pool:
+            jobs = [pool.submit(self.result.write, mi, ids, lens, str(self.path_to_genome),
+                                os.path.join(self.model_dir, f"mgm_{code}.mod"), code, self._gff_path(code), "gff")
+                    for mi, code in enumerate(MGCOD_CODES) if code in missing]
+            for j in jobs:
+                j.result()
 
     def ensure_resident(self):
         """→ (engine, record ids in batch order) with this genome's packed sequence resident on the device — what

@@ -89,6 +89,9 @@ class Result:
             _check(_lib.lib().mgc_result_set_min_gene_length(h, m, int(v)))
         return cls(h, M, n_contigs)
 
+    def num_genes(self, model: int) -> int:
+        return int(_lib.lib().mgc_result_num_genes(self._h, model))
+
     def genes(self, model: int) -> np.ndarray:
         """Structured array (GENE_DTYPE), ordered by (contig, left); 1-based inclusive coordinates."""
         L = _lib.lib()

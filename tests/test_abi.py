@@ -111,3 +111,24 @@ def test_native_fasta_reader_matches_python_reader(tmp_path):
     assert Fasta(str(empty), page_locked=False).ids == []
     with pytest.raises(OSError):
         Fasta(str(tmp_path / "missing.fa"))
+
+
+def test_gff_writer_formats_scores_like_printf(tmp_path):
+    """the hand-rolled "%.2f" of the writer equals C printf on random and on boundary values (x.xx5, tiny, negative, huge)"""
+    from mgcod_b200.engine import GENE_DTYPE, Result
+    rng = np.random.default_rng(5)
+    vals = np.concatenate([rng.uniform(0, 500, 60000), rng.integers(0, 100000, 20000) / 1000.0, rng.integers(0, 2000, 5000) / 200.0 + 0.005,
+                           [0.0, 0.004999, 0.005, 0.015, 0.025, 1e-9, -0.001, -1.005, 1e15, 123456789.125, 2.675, 1.0049999999999999]])
+    n = len(vals)
+    g = np.zeros(n, dtype=GENE_DTYPE)
+    g["contig"] = 0
+    g["left"] = np.arange(n) * 3 + 1
+    g["right"] = g["left"] + 299
+    g["strand"] = 1
+    g["logodd"] = vals
+    g["gc"] = 40
+    res = Result.from_genes([g], [np.array([1.5])])
+    out = str(tmp_path / "f.gff")
+    res.write(0, ["c"], [int(g["right"][-1]) + 10], "s", "m", 11, out, "gff")
+    got = [l.split("\t")[5] for l in open(out) if "\tCDS\t" in l]
+    assert got == ["%.2f" % v for v in vals]
