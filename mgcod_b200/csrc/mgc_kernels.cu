@@ -579,6 +579,18 @@ __device__ __forceinline__ unsigned long long warp_reserve(unsigned long long *c
     return __shfl_sync(0xffffffffu, base, 31) + pre - n;
 }
 
+// One atomic per distinct key in the warp instead of one per lane: lanes holding the same key elect a leader that adds
+// the group size; returns this lane's slot.  `active` lanes only (all 32 lanes must call).
+__device__ __forceinline__ uint32_t warp_key_reserve(uint32_t *counters, uint32_t key, bool active) {
+    const int lane = lane_id();
+    const uint32_t peers = __match_any_sync(0xffffffffu, active ? key : 0xffffffffu);
+    uint32_t base = 0;
+    const int leader = __ffs(peers) - 1;
+    if (active && lane == leader) base = atomicAdd(&counters[key], (uint32_t)__popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+}
+
 // prep 1: thread per ORF — number of start codons per 32-letter word of its admissible range (one WordItem per word,
 // carrying the running prefix) and in total; reserves the ORF's slice of the start array.
 __global__ void __launch_bounds__(128) k_orf_count(Planes pl, const int64_t *__restrict__ cwoff, const int32_t *__restrict__ clen,
@@ -775,11 +787,12 @@ __global__ void __launch_bounds__(128) k_orf_link(Planes pl, const int64_t *__re
         }
         for (int q = 0; q < nslot; q++) flush_slot(q);
         const unsigned long long ibase = warp_reserve(&counters[2], (uint32_t)npend);
-        for (int q = 0; q < npend; q++)
-            if (ibase + q < cap_items) {
-                items[ibase + q] = pend[q];
-                atomicAdd(&hist[pend[q].key], 1u);
-            }
+        const int maxp = __reduce_max_sync(0xffffffffu, npend);
+        for (int q = 0; q < maxp; q++) {  // uniform trip count: the histogram update is aggregated over the warp
+            const bool has = q < npend && ibase + q < cap_items;
+            if (has) items[ibase + q] = pend[q];
+            warp_key_reserve(hist, has ? pend[q].key : 0u, has);
+        }
     }
 }
 
@@ -827,9 +840,15 @@ __global__ void __launch_bounds__(256) k_item_scatter(const ItemRec *const *item
     const ItemRec *items = items_m[mi];
     ItemRec *sorted = sorted_m[mi];
     uint32_t *cursor = cursor_m[mi];
-    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < (int64_t)n; k += (int64_t)gridDim.x * blockDim.x) {
-        const ItemRec it = items[k];
-        sorted[atomicAdd(&cursor[it.key], 1u)] = it;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t k0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~31LL; k0 < (int64_t)n; k0 += stride) {
+        const int64_t k = k0 + lane_id();
+        const bool has = k < (int64_t)n;
+        ItemRec it;
+        it.key = 0;
+        if (has) it = items[k];
+        const uint32_t at = warp_key_reserve(cursor, it.key, has);
+        if (has) sorted[at] = it;
     }
 }
 
