@@ -38,6 +38,10 @@ sys.path.insert(0, ROOT)
 
 CODES = (11, 4, 15, 101)
 SEED = 20260101
+# DRAM bytes of ONE k_walk launch on the default 1 Gbp x 4 models workload, from the committed ncu capture (43.66 GB read + 4.65 GB
+# written; the algorithmic bytes are 12.4 GB: items of one section pair are scattered over the genome, so plane and record
+# sectors are fetched several times -- DESIGN.md section 4).
+WALK_DRAM_BYTES_1GBP = 48.31e9
 METRIC = "bp_x_models_per_s_decoded"
 UNIT = "bp*models/s"
 
@@ -366,6 +370,7 @@ def main():
 
         if rank == 0:
             peak, peak_src = _peaks()
+            default_workload = args.total_bp == 1_000_000_000 and "MGCOD_BENCH_MAXLEN" not in os.environ
             # dominant kernel = k_walk (phase "orf_score").  Algorithmic bytes of one launch (all 4 models): both strands'
             # planes once per model (0.5 B/nt), per walk its item + ORF record (16 + 24 B), per start its record read and its
             # four sums written (16 + 32 B).  The section-pair tables (104 KB each) live in shared memory and are not counted.
@@ -387,7 +392,10 @@ def main():
                 "gpu_launches": int(launches),
                 "clocks": clocks,
                 "roofline": {"kernel": "k_walk", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                             "frac": achieved / peak, "traffic": WALK_DRAM_BYTES_1GBP if default_workload else None,
+                             "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one k_walk launch on this "
+                                               "workload (profiles/r1d_top_kernels_1Gbp.txt)" if default_workload else None,
+                             "peak_source": peak_src,
                              "kernel_ms_per_launch": score_ms, "algorithmic_bytes_per_launch": alg_bytes},
                 "phases_ms_per_step": {k: v / args.steps for k, v in phase.items()},
                 "counts_per_step": counts,
