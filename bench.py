@@ -118,6 +118,27 @@ def _ref_binary() -> str | None:
     return None
 
 
+def bind_to_gpu_numa_node(device: int):
+    """Pins this rank to the CPUs next to its GPU (sysfs local_cpulist), so that the page-locked staging buffers it
+    allocates afterwards are on the GPU's NUMA node.  Best effort: returns the cpu list used, or None."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(device)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        text = open(f"/sys/bus/pci/devices/{bdf}/local_cpulist").read().strip()
+        cpus = set()
+        for part in text.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return text
+    except Exception:
+        pass
+    return None
+
+
 def cpu_reference_run(buf: np.ndarray, offs: np.ndarray, model_paths: list[str], sample_bp: int, workdir: str, cores: int) -> dict:
     """Decode the first contigs of the workload (about sample_bp) under the 4 models on `cores` host threads."""
     n = int(np.searchsorted(offs, sample_bp, side="left"))
@@ -224,6 +245,7 @@ def main():
         if not torch.cuda.is_available():
             raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
         torch.cuda.set_device(local)
+        numa = bind_to_gpu_numa_node(local) if world > 1 else None   # before any page-locked allocation (first touch)
         if world > 1:
             dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -399,7 +421,7 @@ def main():
                              "kernel_ms_per_launch": score_ms, "algorithmic_bytes_per_launch": alg_bytes},
                 "phases_ms_per_step": {k: v / args.steps for k, v in phase.items()},
                 "counts_per_step": counts,
-                "host": {"cores": cores, "workload_generation_s": gen_s},
+                "host": {"cores": cores, "workload_generation_s": gen_s, "numa_cpus": numa},
             }
             if shape2:
                 out["other_shapes"] = [shape2]
