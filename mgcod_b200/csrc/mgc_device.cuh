@@ -93,6 +93,8 @@ constexpr int32_t GPTR_UNSET = (int32_t)0x80808080;
 struct ChainBufs {
     const Cand *sorted;
     const uint32_t *bend;   // bucket ends (bucket b spans [b ? bend[b-1] : 0, bend[b]))
+    const uint32_t *cover;  // exclusive prefix of the boundary difference array: cover[k + 1] = LONG candidates spanning the boundary in front of bucket k
+    uint32_t *minleft;      // per bucket: smallest left end among the candidates ending in it (0xffffffff if none)
     double *cum;            // per sorted entry
     int32_t *prev;          // per sorted entry (index into sorted, -1 none)
     int32_t *gptr;          // per ORF record: shared back-pointer of reverse-strand ORFs (GPTR_UNSET until first use)

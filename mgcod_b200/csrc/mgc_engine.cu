@@ -121,7 +121,7 @@ struct PerModel {
     DevBuf ls, ls_tile, orfs, starts, witems, items, items_sorted, hist, item_off, unit_off, sums;
     DevBuf surv, sorted, bcount, cum, prev, gptr;
     DevBuf av_right, av_left, av_ls, av_idx, av_cum, av_pmax, av_parg, chain, gene_count, gene_off, contig_total, genes;
-    DevBuf piece_b0, piece_b1, work, piece_total, slot_gene_off;
+    DevBuf piece_b0, piece_b1, work, piece_total, slot_gene_off, cover, minleft;
 };
 
 constexpr int N_EVENTS = 12;
@@ -169,7 +169,7 @@ struct mgc_engine {
         std::vector<int64_t> offsets;
     } pending;
     // pointer tables + counters (device)
-    DevBuf t_orfs, t_starts, t_surv, t_sorted, t_bcount, t_gene_off, t_genes, t_chainbufs;
+    DevBuf t_orfs, t_starts, t_surv, t_sorted, t_bcount, t_cover, t_gene_off, t_genes, t_chainbufs;
     DevBuf t_witems;
     uint32_t cap_witems = 0;
     DevBuf t_ls, t_ls_tile, t_items, t_items_sorted, t_hist, t_item_off, t_unit_off, t_sums, unit_totals, next_unit;
@@ -350,7 +350,7 @@ void ensure_batch_buffers(mgc_engine *e) {
     e->cap_surv = (uint32_t)std::min<int64_t>(nt / 24 + 8192, 0x7fffff00);
     e->cap_witems = (uint32_t)std::min<int64_t>(nt / 8 + 8192, 0x7fffff00);
     std::vector<void *> t_witems(M);
-    std::vector<void *> t_orfs(M), t_starts(M), t_surv(M), t_sorted(M), t_bcount(M), t_gene_off(M), t_genes(M);
+    std::vector<void *> t_orfs(M), t_starts(M), t_surv(M), t_sorted(M), t_bcount(M), t_cover(M), t_gene_off(M), t_genes(M);
     std::vector<void *> t_ls(M), t_ls_tile(M), t_items(M), t_items_sorted(M), t_hist(M), t_item_off(M), t_unit_off(M), t_sums(M);
     const int64_t ls_tiles = (2 * W + 255) / 256;
     std::vector<ChainBufs> cb(M);
@@ -374,6 +374,8 @@ void ensure_batch_buffers(mgc_engine *e) {
         p.surv.ensure((size_t)e->cap_surv * sizeof(Cand));
         p.sorted.ensure((size_t)e->cap_surv * sizeof(Cand));
         p.bcount.ensure((size_t)(nb + 8) * 4);
+        p.cover.ensure((size_t)(nb + 8) * 4);
+        p.minleft.ensure((size_t)(nb + 8) * 4);
         p.cum.ensure((size_t)e->cap_surv * 8);
         p.prev.ensure((size_t)e->cap_surv * 4);
         p.gptr.ensure((size_t)e->cap_orf * 4);
@@ -395,10 +397,12 @@ void ensure_batch_buffers(mgc_engine *e) {
         p.contig_total.ensure((size_t)(e->n_contigs + 8) * 8);
         p.genes.ensure((size_t)e->cap_surv * sizeof(mgc_gene));
         t_orfs[i] = p.orfs.p; t_starts[i] = p.starts.p; t_surv[i] = p.surv.p; t_sorted[i] = p.sorted.p;
-        t_bcount[i] = p.bcount.p; t_gene_off[i] = p.gene_off.p; t_genes[i] = p.genes.p;
+        t_bcount[i] = p.bcount.p; t_cover[i] = p.cover.p; t_gene_off[i] = p.gene_off.p; t_genes[i] = p.genes.p;
         ChainBufs &c = cb[i];
         c.sorted = p.sorted.as<Cand>();
         c.bend = p.bcount.as<uint32_t>();
+        c.cover = p.cover.as<uint32_t>();
+        c.minleft = p.minleft.as<uint32_t>();
         c.cum = p.cum.as<double>();
         c.prev = p.prev.as<int32_t>();
         c.gptr = p.gptr.as<int32_t>();
@@ -424,7 +428,7 @@ void ensure_batch_buffers(mgc_engine *e) {
     auto add_sig = [&](const void *src, size_t bytes) {
         sig.insert(sig.end(), static_cast<const unsigned char *>(src), static_cast<const unsigned char *>(src) + bytes);
     };
-    for (auto *v : {&t_orfs, &t_starts, &t_surv, &t_sorted, &t_bcount, &t_gene_off, &t_genes, &t_witems, &t_ls, &t_ls_tile, &t_items,
+    for (auto *v : {&t_orfs, &t_starts, &t_surv, &t_sorted, &t_bcount, &t_cover, &t_gene_off, &t_genes, &t_witems, &t_ls, &t_ls_tile, &t_items,
                     &t_items_sorted, &t_hist, &t_item_off, &t_unit_off, &t_sums})
         add_sig(v->data(), M * sizeof(void *));
     add_sig(cb.data(), M * sizeof(ChainBufs));
@@ -439,6 +443,7 @@ void ensure_batch_buffers(mgc_engine *e) {
     up(e->t_surv, t_surv.data(), M * sizeof(void *));
     up(e->t_sorted, t_sorted.data(), M * sizeof(void *));
     up(e->t_bcount, t_bcount.data(), M * sizeof(void *));
+    up(e->t_cover, t_cover.data(), M * sizeof(void *));
     up(e->t_gene_off, t_gene_off.data(), M * sizeof(void *));
     up(e->t_genes, t_genes.data(), M * sizeof(void *));
     up(e->t_chainbufs, cb.data(), M * sizeof(ChainBufs));
@@ -603,6 +608,7 @@ mgc_result *run_pipeline(mgc_engine *e, bool *amb_out) {
         CUDA_TRY(cudaMemsetAsync(e->pm[i].piece_total.p, 0, (size_t)(e->n_slots + 1) * 8, st));
         CUDA_TRY(cudaMemsetAsync(e->pm[i].piece_b1.p, 0xff, (size_t)(e->n_slots + 1) * 4, st));  // -1 = slot not used
         CUDA_TRY(cudaMemsetAsync(e->pm[i].bcount.p, 0, (size_t)(nb + 8) * 4, st));
+        CUDA_TRY(cudaMemsetAsync(e->pm[i].cover.p, 0, (size_t)(nb + 8) * 4, st));
         CUDA_TRY(cudaMemsetAsync(e->pm[i].hist.p, 0, e->pm[i].hist.bytes, st));
     }
     // pack + GC prefix
@@ -644,18 +650,22 @@ mgc_result *run_pipeline(mgc_engine *e, bool *amb_out) {
     CUDA_TRY(cudaEventRecord(e->ev[9], st));
     launch_final(pl, e->cwoff.as<int64_t>(), e->clen.as<int32_t>(), e->d_models.as<DevModel>(), M, e->t_orfs.as<const OrfRec *>(),
                  e->t_starts.as<const StartRec *>(), e->t_sums.as<void *>(), e->counters.as<unsigned long long>(), e->t_surv.as<Cand *>(),
-                 e->t_bcount.as<uint32_t *>(), e->surv_counters.as<unsigned long long>(), e->cap_starts, e->cap_surv, e->n_sm, st);
+                 e->t_bcount.as<uint32_t *>(), e->t_cover.as<uint32_t *>(), e->surv_counters.as<unsigned long long>(), e->cap_starts, e->cap_surv,
+                 e->n_sm, st);
     launches += 1;
     CUDA_TRY(cudaEventRecord(e->ev[3], st));
-    for (int i = 0; i < M; i++)
+    for (int i = 0; i < M; i++) {
         launches += launch_exclusive_scan(e->pm[i].bcount.as<uint32_t>(), e->pm[i].bcount.as<uint32_t>(), e->tile_sums.as<uint32_t>(),
                                           nb, nullptr, st);
+        launches += launch_exclusive_scan(e->pm[i].cover.as<uint32_t>(), e->pm[i].cover.as<uint32_t>(), e->tile_sums.as<uint32_t>(),
+                                          nb + 2, nullptr, st);
+    }
     launch_scatter(e->t_surv.as<const Cand *>(), e->t_sorted.as<Cand *>(), e->t_bcount.as<uint32_t *>(),
                    e->surv_counters.as<unsigned long long>(), e->cwoff.as<int64_t>(), e->cap_surv, M, e->n_sm, st);
     launches += 1;
     CUDA_TRY(cudaEventRecord(e->ev[4], st));
-    launches += launch_chain(e->t_chainbufs.as<ChainBufs>(), e->cwoff.as<int64_t>(), e->clen.as<int32_t>(), e->order.as<int32_t>(), n,
-                             e->slotbase.as<int32_t>(), e->work_counters.as<int>(), M, e->n_sm, st);
+    launches += launch_chain(e->t_chainbufs.as<ChainBufs>(), e->cwoff.as<int64_t>(), e->clen.as<int32_t>(), e->slotbase.as<int32_t>(),
+                             e->slot_contig.as<int32_t>(), e->n_slots, nb, e->work_counters.as<int>(), M, e->n_sm, st);
     CUDA_TRY(cudaEventRecord(e->ev[5], st));
     for (int i = 0; i < M; i++) {
         // gene_count[n_slots] stays 0 so that the exclusive scan yields the total at slot_gene_off[n_slots]
@@ -893,11 +903,11 @@ void mgc_engine_destroy(mgc_engine *e) {
                           &p.item_off, &p.unit_off, &p.sums, &p.witems, &p.orfs, &p.starts, &p.surv, &p.sorted, &p.bcount,
                           &p.cum, &p.prev, &p.gptr, &p.av_right, &p.av_left, &p.av_ls, &p.av_idx, &p.av_cum, &p.av_pmax, &p.av_parg,
                           &p.chain, &p.gene_count, &p.gene_off, &p.contig_total, &p.genes, &p.piece_b0, &p.piece_b1, &p.work,
-                          &p.piece_total, &p.slot_gene_off})
+                          &p.piece_total, &p.slot_gene_off, &p.cover, &p.minleft})
             b->release();
     }
     for (DevBuf *b : {&e->d_models, &e->ascii, &e->aoff, &e->cwoff, &e->clen, &e->grp2contig, &e->order, &e->lo, &e->hi, &e->gc,
-                      &e->tile_sums, &e->flags, &e->t_orfs, &e->t_starts, &e->t_surv, &e->t_sorted, &e->t_bcount, &e->t_gene_off,
+                      &e->tile_sums, &e->flags, &e->t_orfs, &e->t_starts, &e->t_surv, &e->t_sorted, &e->t_bcount, &e->t_cover, &e->t_gene_off,
                       &e->t_genes, &e->t_chainbufs, &e->counters, &e->surv_counters, &e->work_counters, &e->model_cents,
                       &e->gene_totals, &e->t_ls, &e->t_ls_tile, &e->t_items, &e->t_items_sorted, &e->t_hist, &e->t_item_off,
                       &e->t_unit_off, &e->t_sums, &e->t_witems, &e->ascii_next, &e->slotbase, &e->slot_contig, &e->nm, &e->ncount, &e->cflags, &e->plen, &e->gaps, &e->gap_count, &e->unit_totals, &e->next_unit, &e->win_stride, &e->win_off, &e->win_labels, &e->win_cents})

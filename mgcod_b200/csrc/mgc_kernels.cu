@@ -1039,7 +1039,8 @@ __global__ void __launch_bounds__(256) k_final(Planes pl, const int64_t *__restr
                                                const DevModel *__restrict__ models, const OrfRec *const *orfs_m,
                                                const StartRec *const *starts_m, const Acc4 *const *sums_m,
                                                const unsigned long long *counters_m, Cand *const *surv_m, uint32_t *const *bcount_m,
-                                               unsigned long long *surv_counters, uint32_t cap_starts, uint32_t cap_surv) {
+                                               uint32_t *const *cover_m, unsigned long long *surv_counters, uint32_t cap_starts,
+                                               uint32_t cap_surv) {
     const int mi = blockIdx.y;
     const DevModel &dm = models[mi];
     const int lane = lane_id();
@@ -1050,6 +1051,7 @@ __global__ void __launch_bounds__(256) k_final(Planes pl, const int64_t *__restr
     const Acc4 *sums = sums_m[mi];
     Cand *surv = surv_m[mi];
     uint32_t *bcount = bcount_m[mi];
+    uint32_t *cover = cover_m[mi];
     const int kc = dm.kc, nramp = dm.nramp;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     // whole warps iterate together (ballots below); the loop bound is rounded up to a multiple of 32
@@ -1153,7 +1155,11 @@ __global__ void __launch_bounds__(256) k_final(Planes pl, const int64_t *__restr
                 const unsigned long long kk = base + __popc(km & ((1u << lane) - 1u));
                 if (kk < cap_surv) {
                     surv[kk] = cd;
-                    atomicAdd(&bcount[(w0 * 32 + cd.right) >> 7], 1u);
+                    const uint32_t br = (uint32_t)((w0 * 32 + cd.right) >> 7), bl = (uint32_t)((w0 * 32 + cd.left) >> 7);
+                    atomicAdd(&bcount[br], 1u);
+                    // a LONG candidate (spanning >= PIECE_BUCKETS bucket boundaries, > 8 kb: rare) marks the boundaries it spans
+                    // in a difference array; the plan kernel finds all shorter ones by looking PIECE_BUCKETS buckets ahead
+                    if (br >= bl + PIECE_BUCKETS) { atomicAdd(&cover[bl + 1], 1u); atomicAdd(&cover[br + 1], 0xffffffffu); }
                 }
             }
         }
@@ -1410,64 +1416,64 @@ __device__ __forceinline__ void chain_bucket(const ChainBufs &B, ChainRing &R, u
     }
 }
 
-// Cut points.  Candidates are bucketed by right end; the boundary in front of relative bucket rb is safe when every
-// candidate ending at or after it also starts at or after it: nothing on its right can overlap, or share a
-// reverse-strand ORF with, anything on its left, and the only coupling left is the additive best score of the prefix.
-// One warp per (contig, model) walks the buckets from the end with a suffix minimum of the left ends and cuts at the
-// first safe boundary at least PIECE_BUCKETS below the previous cut.
+// Cut points.  Candidates are bucketed by right end; the boundary in front of a bucket is safe when no candidate spans
+// it: nothing on its right can then overlap, or share a reverse-strand ORF with, anything on its left, and the only
+// coupling left is the additive best score of the prefix.  A candidate ending in bucket b spans boundary k <= b iff its
+// left end lies before the boundary, so with minleft[b] = smallest left end among the candidates ending in b,
+//   boundary k is safe  <=>  min(minleft[k .. k+H)) >= position of k   and no LONG candidate (>= H boundaries) spans k,
+// the long ones being counted by k_final in a prefix-summed difference array (ChainBufs::cover).  H = PIECE_BUCKETS.
+__global__ void __launch_bounds__(256) k_chain_minleft(const ChainBufs *bufs_m, int64_t n_buckets) {
+    const ChainBufs B = bufs_m[blockIdx.y];
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_buckets) return;
+    uint32_t m = 0xffffffffu;
+    for (uint32_t k = b ? B.bend[b - 1] : 0u, e = B.bend[b]; k < e; k++) m = min(m, (uint32_t)B.sorted[k].left);
+    B.minleft[b] = m;
+}
+
+// Thread per piece slot = aligned window of PIECE_BUCKETS buckets of a contig; a window contributes its first safe
+// boundary as a cut (window 0: the contig start), and the piece runs up to the next window's cut.  Fully parallel, also
+// inside one long contig.
 __global__ void __launch_bounds__(128) k_chain_plan(const ChainBufs *bufs_m, const int64_t *__restrict__ cwoff,
-                                                    const int32_t *__restrict__ clen, const int32_t *__restrict__ order,
-                                                    int32_t n_contigs, const int32_t *__restrict__ slotbase, int *work_counters) {
+                                                    const int32_t *__restrict__ clen, const int32_t *__restrict__ slotbase,
+                                                    const int32_t *__restrict__ slot_contig, int32_t n_slots, int *work_counters) {
     const int mi = blockIdx.y;
     const ChainBufs B = bufs_m[mi];
-    const int lane = lane_id();
-    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t it = warp; it < n_contigs; it += nw) {
-        const int c = order[it];
-        const int L = clen[c];
-        const int64_t b_first = cwoff[c] >> 2;  // slots start on 128-nt boundaries
-        const int nbk = (max(L - 1, 0) >> 7) + 1;
-        const uint32_t cs = b_first ? B.bend[b_first - 1] : 0u, ce = B.bend[b_first + nbk - 1];
-        if (ce == cs) continue;
-        const int sb = slotbase[c];
-        int last_cut = nbk;  // the piece being grown ends at relative bucket last_cut - 1
-        if (nbk >= 2 * PIECE_BUCKETS) {
-            int carry = 0x7fffffff;  // minimum left end over all buckets above the current block
-            for (int top = nbk - 1; top >= PIECE_BUCKETS; top -= 32) {
-                const int rb = top - lane;
-                int m = 0x7fffffff;
-                if (rb >= PIECE_BUCKETS) {
-                    const uint32_t s0 = B.bend[b_first + rb - 1], e0 = B.bend[b_first + rb];
-                    for (uint32_t k = s0; k < e0; k++) m = min(m, B.sorted[k].left);
-                }
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int t = __shfl_up_sync(0xffffffffu, m, o);
-                    if (lane >= o) m = min(m, t);
-                }
-                m = min(m, carry);
-                carry = __shfl_sync(0xffffffffu, m, 31);
-                const bool ok = rb >= PIECE_BUCKETS && rb <= last_cut - PIECE_BUCKETS && m >= rb * 128;
-                const uint32_t mask = __ballot_sync(0xffffffffu, ok);
-                if (mask) {
-                    const int cut = top - (__ffs(mask) - 1);
-                    if (lane == 0) {
-                        const int slot = sb + cut / PIECE_BUCKETS;
-                        B.piece_b0[slot] = (int32_t)(b_first + cut);
-                        B.piece_b1[slot] = (int32_t)(b_first + last_cut - 1);
-                        B.work[atomicAdd(&work_counters[2 * mi], 1)] = slot;
-                    }
-                    last_cut = cut;
-                }
-            }
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_slots) return;
+    const int c = slot_contig[s];
+    const int sb = slotbase[c], m = s - sb, nwin = slotbase[c + 1] - sb;
+    const int L = clen[c];
+    const int64_t b_first = cwoff[c] >> 2;  // slots start on 128-nt boundaries
+    const int nbk = (max(L - 1, 0) >> 7) + 1;
+    const uint32_t cs = b_first ? B.bend[b_first - 1] : 0u, ce = B.bend[b_first + nbk - 1];
+    if (ce == cs) return;
+    const uint32_t *cov = B.cover + b_first + 1;  // cov[rb]: LONG candidates spanning the boundary in front of relative bucket rb
+    const uint32_t *ml = B.minleft + b_first;     // ml[rb]: smallest (contig-relative) left end among the candidates ending in rb
+    auto cut_of = [&](int win) {  // first safe boundary of the window, -1 if none
+        if (win == 0) return 0;
+        const int lo = win * PIECE_BUCKETS, hi = min(lo + PIECE_BUCKETS - 1, nbk - 1);
+        uint32_t run = 0xffffffffu;  // min(minleft[rb .. hi + H)), built from the far end
+        for (int rb = min(hi + PIECE_BUCKETS - 1, nbk - 1); rb > hi; rb--) run = min(run, ml[rb]);
+        int best = -1;
+        for (int rb = hi; rb >= lo; rb--) {
+            run = min(run, ml[rb]);
+            if (run >= (uint32_t)rb * 128u && cov[rb] == 0u) best = rb;
         }
-        if (lane == 0) {
-            B.piece_b0[sb] = (int32_t)b_first;
-            B.piece_b1[sb] = (int32_t)(b_first + last_cut - 1);
-            B.work[atomicAdd(&work_counters[2 * mi], 1)] = sb;
-        }
+        return best;
+    };
+    const int mine = cut_of(m);
+    if (mine < 0) return;
+    int last = nbk - 1;
+    for (int win = m + 1; win < nwin; win++) {
+        const int nx = cut_of(win);
+        if (nx >= 0) { last = nx - 1; break; }
     }
+    const uint32_t ps = (b_first + mine) ? B.bend[b_first + mine - 1] : 0u, pe = B.bend[b_first + last];
+    if (pe == ps) return;  // nothing ends inside this piece
+    B.piece_b0[s] = (int32_t)(b_first + mine);
+    B.piece_b1[s] = (int32_t)(b_first + last);
+    B.work[atomicAdd(&work_counters[2 * mi], 1)] = s;
 }
 
 __global__ void __launch_bounds__(128) k_chain(const ChainBufs *bufs_m, int *work_counters) {
@@ -1966,11 +1972,11 @@ int launch_walk(Planes pl, const int64_t *cwoff, const DevModel *models, int n_m
 
 void launch_final(Planes pl, const int64_t *cwoff, const int32_t *clen, const DevModel *models, int n_models, const OrfRec *const *orfs_m,
                   const StartRec *const *starts_m, void *const *sums_m, const unsigned long long *counters_m, Cand *const *surv_m,
-                  uint32_t *const *bcount_m, unsigned long long *surv_counters, uint32_t cap_starts, uint32_t cap_surv, int n_sm,
+                  uint32_t *const *bcount_m, uint32_t *const *cover_m, unsigned long long *surv_counters, uint32_t cap_starts, uint32_t cap_surv, int n_sm,
                   cudaStream_t st) {
     dim3 grid(n_sm * 8, n_models);
     k_final<<<grid, 256, 0, st>>>(pl, cwoff, clen, models, orfs_m, starts_m, reinterpret_cast<const Acc4 *const *>(sums_m), counters_m,
-                                  surv_m, bcount_m, surv_counters, cap_starts, cap_surv);
+                                  surv_m, bcount_m, cover_m, surv_counters, cap_starts, cap_surv);
 }
 
 void launch_scatter(const Cand *const *surv_m, Cand *const *sorted_m, uint32_t *const *boff_m,
@@ -1980,13 +1986,13 @@ void launch_scatter(const Cand *const *surv_m, Cand *const *sorted_m, uint32_t *
     k_scatter<<<grid, 256, 0, st>>>(surv_m, sorted_m, boff_m, surv_counters, cwoff, cap_surv);
 }
 
-int launch_chain(const ChainBufs *bufs_m, const int64_t *cwoff, const int32_t *clen, const int32_t *order, int32_t n_contigs,
-                 const int32_t *slotbase, int *work_counters, int n_models, int n_sm, cudaStream_t st) {
-    int64_t blocks = ((int64_t)n_contigs + 3) / 4;
-    if (blocks > (int64_t)n_sm * 16) blocks = (int64_t)n_sm * 16;
-    k_chain_plan<<<dim3((unsigned)blocks, n_models), 128, 0, st>>>(bufs_m, cwoff, clen, order, n_contigs, slotbase, work_counters);
+int launch_chain(const ChainBufs *bufs_m, const int64_t *cwoff, const int32_t *clen, const int32_t *slotbase, const int32_t *slot_contig,
+                 int32_t n_slots, int64_t n_buckets, int *work_counters, int n_models, int n_sm, cudaStream_t st) {
+    k_chain_minleft<<<dim3((unsigned)((n_buckets + 255) / 256), n_models), 256, 0, st>>>(bufs_m, n_buckets);
+    k_chain_plan<<<dim3((unsigned)((n_slots + 127) / 128), n_models), 128, 0, st>>>(bufs_m, cwoff, clen, slotbase, slot_contig, n_slots,
+                                                                                     work_counters);
     k_chain<<<dim3((unsigned)n_sm * 16, n_models), 128, 0, st>>>(bufs_m, work_counters);
-    return 2;
+    return 3;
 }
 
 int launch_gather(const ChainBufs *bufs_m, mgc_gene *const *genes_m, const int32_t *slot_contig, int32_t n_slots, const int32_t *slotbase,

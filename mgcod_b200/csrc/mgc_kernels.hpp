@@ -45,13 +45,13 @@ int launch_walk(Planes pl, const int64_t *cwoff, const DevModel *models, int n_m
                 cudaStream_t st);
 void launch_final(Planes pl, const int64_t *cwoff, const int32_t *clen, const DevModel *models, int n_models, const OrfRec *const *orfs_m,
                   const StartRec *const *starts_m, void *const *sums_m, const unsigned long long *counters_m, Cand *const *surv_m,
-                  uint32_t *const *bcount_m, unsigned long long *surv_counters, uint32_t cap_starts, uint32_t cap_surv, int n_sm,
+                  uint32_t *const *bcount_m, uint32_t *const *cover_m, unsigned long long *surv_counters, uint32_t cap_starts, uint32_t cap_surv, int n_sm,
                   cudaStream_t st);
 void launch_scatter(const Cand *const *surv_m, Cand *const *sorted_m, uint32_t *const *boff_m,
                     const unsigned long long *surv_counters, const int64_t *cwoff, uint32_t cap_surv, int n_models, int n_sm,
                     cudaStream_t st);
-int launch_chain(const ChainBufs *bufs_m, const int64_t *cwoff, const int32_t *clen, const int32_t *order, int32_t n_contigs,
-                 const int32_t *slotbase, int *work_counters, int n_models, int n_sm, cudaStream_t st);
+int launch_chain(const ChainBufs *bufs_m, const int64_t *cwoff, const int32_t *clen, const int32_t *slotbase, const int32_t *slot_contig,
+                 int32_t n_slots, int64_t n_buckets, int *work_counters, int n_models, int n_sm, cudaStream_t st);
 int launch_gather(const ChainBufs *bufs_m, mgc_gene *const *genes_m, const int32_t *slot_contig, int32_t n_slots, const int32_t *slotbase,
                   int32_t n_contigs, long long *model_cents, int n_models, int n_sm, cudaStream_t st);
 void launch_windows(const mgc_gene *const *genes_m, const uint32_t *const *gene_off_m, int n_models, const int32_t *clen,
