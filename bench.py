@@ -382,6 +382,44 @@ def main():
             del r
             f.close()
 
+        # ---- latency of the reference's own example (BASELINE.json configs[0]/[1]: phage2, 173 747 bp, one contig) ----
+        small = None
+        golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests", "golden")
+        if world == 1 and os.path.exists(os.path.join(golden, "phage2.fa.xz")):
+            import lzma
+            text = lzma.open(os.path.join(golden, "phage2.fa.xz"), "rt").read()
+            pseq = np.frombuffer("".join(l.strip() for l in text.split("\n") if not l.startswith(">")).encode(), dtype=np.uint8)
+            ppin = torch.empty(len(pseq), dtype=torch.uint8, pin_memory=True)
+            ppin.numpy()[:] = pseq
+            poffs = np.array([0, len(pseq)], dtype=np.int64)
+            tdir = os.path.join(workdir, "trained")
+            os.makedirs(tdir, exist_ok=True)
+            tpaths = []
+            for c in (11, 4, 15, 101):
+                tp = os.path.join(tdir, f"mgm_{c}.mod")
+                open(tp, "wb").write(lzma.open(os.path.join(golden, "trained", f"mgm_{c}.mod.xz")).read())
+                tpaths.append(tp)
+            eng2 = Engine(tpaths, device=local)
+            plens, pstr = np.array([len(pseq)], np.int64), np.array([2500], np.int32)
+            for _ in range(5):
+                r = eng2.decode_buffer(ppin.numpy(), poffs)
+                eng2.window_labels(plens, pstr, 5000, 3, False)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(20):
+                r = eng2.decode_buffer(ppin.numpy(), poffs)
+                label = int(np.argmax(r.model_cents()))
+            t1 = time.perf_counter()
+            for _ in range(20):
+                r = eng2.decode_buffer(ppin.numpy(), poffs)
+                wo, wl, wc = eng2.window_labels(plens, pstr, 5000, 3, False)
+                wm, _ = eng2.merge_labels_flat(wl, wo, 3)
+            t2 = time.perf_counter()
+            small = {"input": "phage2 (173747 bp, 1 contig) x 4 trained order-4/2 models, host buffers in, genes/labels out",
+                     "default_mode_ms": 1e3 * (t1 - t0) / 20, "isoforms_w5000_st2500_n3_ms": 1e3 * (t2 - t1) / 20,
+                     "windows": int(wo[-1]), "genetic_code": (11, 4, 15, 101)[label]}
+            eng2.close()
+
         times = torch.tensor([dt_res, dt_e2e, dt_single, dt_win], dtype=torch.float64, device="cuda")
         tot_units = torch.tensor([float(units)], dtype=torch.float64, device="cuda")
         if world > 1:
@@ -427,6 +465,8 @@ def main():
                 out["other_shapes"] = [shape2]
             if file_e2e:
                 out["file_e2e"] = file_e2e
+            if small:
+                out["small_input_latency"] = small
             if world == 1 and not args.no_cpu_baseline:
                 out["cpu_baseline"] = cpu_reference_run(buf, offs, model_paths, args.cpu_sample_bp, workdir, cores)
             print(json.dumps(out))
