@@ -142,7 +142,7 @@ struct mgc_engine {
     DevBuf slotbase, slot_contig;
     int64_t total_nt = 0, W = 0;
     std::vector<int64_t> h_aoff, h_cwoff;
-    std::vector<int32_t> h_clen, h_order;
+    std::vector<int32_t> h_clen;
     // the caller's contigs ("parents") and the slots actually decoded: one slot per contig, or several when runs of
     // >= 40 ambiguous letters split a contig (gmhmmp2 --incomplete_at_gaps 40)
     struct Seg {
@@ -158,7 +158,7 @@ struct mgc_engine {
     int32_t n_parents = 0;
     bool segmented = false;
     DevBuf nm, ncount, cflags, plen, gaps, gap_count;
-    DevBuf ascii, aoff, cwoff, clen, grp2contig, order, lo, hi, gc, tile_sums, flags;
+    DevBuf ascii, aoff, cwoff, clen, grp2contig, lo, hi, gc, tile_sums, flags;
     // next batch on its way to the device while the current one is decoded (mgc_prefetch_batch)
     DevBuf ascii_next;
     cudaStream_t copy_stream = nullptr;
@@ -174,7 +174,7 @@ struct mgc_engine {
     uint32_t cap_witems = 0;
     DevBuf t_ls, t_ls_tile, t_items, t_items_sorted, t_hist, t_item_off, t_unit_off, t_sums, unit_totals, next_unit;
     uint32_t cap_items = 0;
-    int max_cod_order = 0, max_non_order = 0;
+    int max_cod_order = 0, max_non_order = 0, max_pairs = 1;
     DevBuf counters;     // [M][8] unsigned long long: 0 orfs, 1 starts
     DevBuf surv_counters;  // [M]
     DevBuf work_counters;  // [M] int
@@ -324,6 +324,7 @@ void upload_models(mgc_engine *e) {
         up(p.rquad, rq.data(), std::max<size_t>(rq.size(), 1) * sizeof(Quad));
         d.rquad = p.rquad.as<Quad>();
         e->max_cod_order = std::max(e->max_cod_order, kc);
+        e->max_pairs = std::max(e->max_pairs, d.npair);
         e->max_non_order = std::max(e->max_non_order, kn);
     }
     e->d_models.ensure(sizeof(DevModel) * e->n_models);
@@ -499,28 +500,12 @@ void set_slots(mgc_engine *e) {
     if (w * 64 >= 0xffffffffLL) throw std::invalid_argument("batch too large: at most ~2e9 nt per decode call");
     e->W = w;
     e->total_nt = nt;
-    // roughly longest first (load balance of the plan kernel; the chain itself works on equal-sized pieces): a stable
-    // counting sort on a log-linear length class (3 mantissa bits) instead of a comparison sort
-    {
-        auto cls = [](int32_t L) {
-            const uint32_t v = (uint32_t)L + 1u;
-            const int lg = 31 - __builtin_clz(v);
-            const uint32_t mant = lg >= 3 ? (v >> (lg - 3)) & 7u : 0u;
-            return 255 - (int)((uint32_t)lg * 8u + mant);
-        };
-        uint32_t hist[257] = {0};
-        for (int32_t c = 0; c < n; c++) hist[cls(e->h_clen[c]) + 1]++;
-        for (int k = 0; k < 256; k++) hist[k + 1] += hist[k];
-        e->h_order.resize(n);
-        for (int32_t c = 0; c < n; c++) e->h_order[hist[cls(e->h_clen[c])]++] = c;
-    }
     const double t1 = now_ms();
     ensure_batch_buffers(e);
     const double t2 = now_ms();
     e->aoff.ensure((size_t)(n + 1) * 8);
     e->cwoff.ensure((size_t)(n + 1) * 8);
     e->clen.ensure((size_t)n * 4);
-    e->order.ensure((size_t)n * 4);
     e->cflags.ensure((size_t)n + 16);
     e->slotbase.ensure((size_t)(n + 1) * 4);
     e->slot_contig.ensure((size_t)e->n_slots * 4 + 16);
@@ -530,7 +515,6 @@ void set_slots(mgc_engine *e) {
     CUDA_TRY(cudaMemcpyAsync(e->aoff.p, e->h_aoff.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(e->cwoff.p, e->h_cwoff.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(e->clen.p, e->h_clen.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(e->order.p, e->h_order.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(e->cflags.p, cflags.data(), (size_t)n, cudaMemcpyHostToDevice, st));
     launch_groups(e->cwoff.as<int64_t>(), n, e->W / 4, e->grp2contig.as<int32_t>(), st);
     const double t3 = now_ms();
@@ -618,6 +602,7 @@ mgc_result *run_pipeline(mgc_engine *e, bool *amb_out) {
     launches += 1;
     launches += launch_exclusive_scan(e->gc.as<uint32_t>(), e->gc.as<uint32_t>(), e->tile_sums.as<uint32_t>(), W, nullptr, st);
     launches += launch_exclusive_scan(e->ncount.as<uint32_t>(), e->ncount.as<uint32_t>(), e->tile_sums.as<uint32_t>(), W, nullptr, st);
+    CUDA_TRY(cudaPeekAtLastError());   // a failed launch must not go unnoticed until the end
     CUDA_TRY(cudaEventRecord(e->ev[1], st));
     Planes pl;
     pl.lo = e->lo.as<uint32_t>();
@@ -633,6 +618,7 @@ mgc_result *run_pipeline(mgc_engine *e, bool *amb_out) {
                     e->t_ls.as<const uint32_t *>(), e->t_ls_tile.as<const uint32_t *>(), e->t_orfs.as<OrfRec *>(),
                     e->counters.as<unsigned long long>(), e->cap_orf, st);
     launches += 1;
+    CUDA_TRY(cudaPeekAtLastError());   // a failed launch must not go unnoticed until the end
     CUDA_TRY(cudaEventRecord(e->ev[2], st));
     launches += launch_orf_prep(pl, e->gc.as<uint32_t>(), e->cwoff.as<int64_t>(), e->clen.as<int32_t>(), e->d_models.as<DevModel>(), M,
                                 e->t_orfs.as<OrfRec *>(), e->t_witems.as<WordItem *>(), e->t_starts.as<StartRec *>(),
@@ -641,18 +627,22 @@ mgc_result *run_pipeline(mgc_engine *e, bool *amb_out) {
     launches += launch_item_sort(e->t_items.as<const ItemRec *>(), e->t_items_sorted.as<ItemRec *>(), e->t_hist.as<uint32_t *>(),
                                  e->t_item_off.as<uint32_t *>(), e->t_unit_off.as<uint32_t *>(), e->d_models.as<DevModel>(), M,
                                  e->unit_totals.as<uint32_t>(), e->counters.as<unsigned long long>(), e->cap_items, e->n_sm, st);
+    CUDA_TRY(cudaPeekAtLastError());
+    CUDA_TRY(cudaPeekAtLastError());   // a failed launch must not go unnoticed until the end
     CUDA_TRY(cudaEventRecord(e->ev[8], st));
     launches += launch_walk(pl, e->cwoff.as<int64_t>(), e->d_models.as<DevModel>(), M, e->max_cod_order, e->max_non_order,
                             e->t_orfs.as<const OrfRec *>(),
                             e->t_starts.as<const StartRec *>(), e->t_items_sorted.as<const ItemRec *>(),
                             e->t_item_off.as<const uint32_t *>(), e->t_unit_off.as<const uint32_t *>(), e->unit_totals.as<uint32_t>(),
                             e->t_sums.as<void *>(), e->next_unit.as<unsigned int>(), e->n_sm, st);
+    CUDA_TRY(cudaPeekAtLastError());   // a failed launch must not go unnoticed until the end
     CUDA_TRY(cudaEventRecord(e->ev[9], st));
     launch_final(pl, e->cwoff.as<int64_t>(), e->clen.as<int32_t>(), e->d_models.as<DevModel>(), M, e->t_orfs.as<const OrfRec *>(),
                  e->t_starts.as<const StartRec *>(), e->t_sums.as<void *>(), e->counters.as<unsigned long long>(), e->t_surv.as<Cand *>(),
                  e->t_bcount.as<uint32_t *>(), e->t_cover.as<uint32_t *>(), e->surv_counters.as<unsigned long long>(), e->cap_starts, e->cap_surv,
                  e->n_sm, st);
     launches += 1;
+    CUDA_TRY(cudaPeekAtLastError());   // a failed launch must not go unnoticed until the end
     CUDA_TRY(cudaEventRecord(e->ev[3], st));
     for (int i = 0; i < M; i++) {
         launches += launch_exclusive_scan(e->pm[i].bcount.as<uint32_t>(), e->pm[i].bcount.as<uint32_t>(), e->tile_sums.as<uint32_t>(),
@@ -663,9 +653,11 @@ mgc_result *run_pipeline(mgc_engine *e, bool *amb_out) {
     launch_scatter(e->t_surv.as<const Cand *>(), e->t_sorted.as<Cand *>(), e->t_bcount.as<uint32_t *>(),
                    e->surv_counters.as<unsigned long long>(), e->cwoff.as<int64_t>(), e->cap_surv, M, e->n_sm, st);
     launches += 1;
+    CUDA_TRY(cudaPeekAtLastError());   // a failed launch must not go unnoticed until the end
     CUDA_TRY(cudaEventRecord(e->ev[4], st));
     launches += launch_chain(e->t_chainbufs.as<ChainBufs>(), e->cwoff.as<int64_t>(), e->clen.as<int32_t>(), e->slotbase.as<int32_t>(),
                              e->slot_contig.as<int32_t>(), e->n_slots, nb, e->work_counters.as<int>(), M, e->n_sm, st);
+    CUDA_TRY(cudaPeekAtLastError());   // a failed launch must not go unnoticed until the end
     CUDA_TRY(cudaEventRecord(e->ev[5], st));
     for (int i = 0; i < M; i++) {
         // gene_count[n_slots] stays 0 so that the exclusive scan yields the total at slot_gene_off[n_slots]
@@ -674,6 +666,7 @@ mgc_result *run_pipeline(mgc_engine *e, bool *amb_out) {
     }
     launches += launch_gather(e->t_chainbufs.as<ChainBufs>(), e->t_genes.as<mgc_gene *>(), e->slot_contig.as<int32_t>(), e->n_slots,
                               e->slotbase.as<int32_t>(), n, e->model_cents.as<long long>(), M, e->n_sm, st);
+    CUDA_TRY(cudaPeekAtLastError());   // a failed launch must not go unnoticed until the end
     CUDA_TRY(cudaEventRecord(e->ev[6], st));
 
     // small read-backs
@@ -906,7 +899,7 @@ void mgc_engine_destroy(mgc_engine *e) {
                           &p.piece_total, &p.slot_gene_off, &p.cover, &p.minleft})
             b->release();
     }
-    for (DevBuf *b : {&e->d_models, &e->ascii, &e->aoff, &e->cwoff, &e->clen, &e->grp2contig, &e->order, &e->lo, &e->hi, &e->gc,
+    for (DevBuf *b : {&e->d_models, &e->ascii, &e->aoff, &e->cwoff, &e->clen, &e->grp2contig, &e->lo, &e->hi, &e->gc,
                       &e->tile_sums, &e->flags, &e->t_orfs, &e->t_starts, &e->t_surv, &e->t_sorted, &e->t_bcount, &e->t_cover, &e->t_gene_off,
                       &e->t_genes, &e->t_chainbufs, &e->counters, &e->surv_counters, &e->work_counters, &e->model_cents,
                       &e->gene_totals, &e->t_ls, &e->t_ls_tile, &e->t_items, &e->t_items_sorted, &e->t_hist, &e->t_item_off,
