@@ -270,6 +270,8 @@ def main():
             del res
         for res in engine.decode_stream((buf, offs) for _ in range(max(2, args.warmup))):   # the timed e2e path
             del res
+        free_b, total_b = torch.cuda.mem_get_info()
+        hbm_used_gb = (total_b - free_b) / 1e9       # buffers of one 1 Gbp x 4 models batch incl. the prefetch buffer
         # ---- device-resident timing ----
         engine.upload(buf, offs)
         res = engine.decode_resident()
@@ -460,6 +462,7 @@ def main():
                 "phases_ms_per_step": {k: v / args.steps for k, v in phase.items()},
                 "counts_per_step": counts,
                 "host": {"cores": cores, "workload_generation_s": gen_s, "numa_cpus": numa},
+                "hbm_used_gb": hbm_used_gb,
             }
             if shape2:
                 out["other_shapes"] = [shape2]
