@@ -125,6 +125,7 @@ struct Planes {
     const uint32_t *lo, *hi;  // [2][W + 4]
     const uint32_t *nm;       // [2][W + 4] ambiguity mask: bit set = letter outside ACGT (its code in lo/hi is 0)
     const uint32_t *npre;     // [W + 4] exclusive prefix of ambiguous letters per word, forward region
+    const uint32_t *codon;    // [5][2W] codon planes: start (ATG|GTG|TTG), ATG, TAA, TAG, TGA (k_codon_planes)
     const int *dflags;        // device flags written by k_pack: [0] letter outside the IUPAC alphabet, [1] any ambiguous letter
     const uint8_t *cflags;    // per contig slot: bit0 = its right edge is the end of the record (not a gap)
     int64_t W;                // words per strand region

@@ -157,7 +157,7 @@ struct mgc_engine {
     std::vector<int32_t> h_parent_len;
     int32_t n_parents = 0;
     bool segmented = false;
-    DevBuf nm, ncount, cflags, plen, gaps, gap_count;
+    DevBuf nm, ncount, cflags, plen, gaps, gap_count, codon;
     DevBuf ascii, aoff, cwoff, clen, grp2contig, lo, hi, gc, tile_sums, flags;
     // next batch on its way to the device while the current one is decoded (mgc_prefetch_batch)
     DevBuf ascii_next;
@@ -338,6 +338,7 @@ void ensure_batch_buffers(mgc_engine *e) {
     e->hi.ensure((size_t)(2 * W + 8) * 4);
     e->gc.ensure((size_t)(W + 8) * 4);
     e->nm.ensure((size_t)(2 * W + 8) * 4);
+    e->codon.ensure((size_t)(10 * W + 8) * 4);
     e->ncount.ensure((size_t)(W + 8) * 4);
     const int64_t nb = W / 4;
     const int64_t scan_n = std::max<int64_t>(std::max<int64_t>(W, nb), e->n_contigs + 1);
@@ -611,7 +612,10 @@ mgc_result *run_pipeline(mgc_engine *e, bool *amb_out) {
     pl.npre = e->ncount.as<uint32_t>();
     pl.dflags = e->flags.as<int>();
     pl.cflags = e->cflags.as<uint8_t>();
+    pl.codon = e->codon.as<uint32_t>();
     pl.W = W;
+    launch_codon_planes(pl, e->cwoff.as<int64_t>(), e->clen.as<int32_t>(), e->grp2contig.as<int32_t>(), e->codon.as<uint32_t>(), st);
+    launches += 1;
     launches += launch_laststop(pl, e->cwoff.as<int64_t>(), e->clen.as<int32_t>(), e->grp2contig.as<int32_t>(),
                                 e->d_models.as<DevModel>(), M, e->t_ls.as<uint32_t *>(), e->t_ls_tile.as<uint32_t *>(), st);
     launch_orf_find(pl, e->cwoff.as<int64_t>(), e->clen.as<int32_t>(), e->grp2contig.as<int32_t>(), e->d_models.as<DevModel>(), M,
@@ -903,7 +907,7 @@ void mgc_engine_destroy(mgc_engine *e) {
                       &e->tile_sums, &e->flags, &e->t_orfs, &e->t_starts, &e->t_surv, &e->t_sorted, &e->t_bcount, &e->t_cover, &e->t_gene_off,
                       &e->t_genes, &e->t_chainbufs, &e->counters, &e->surv_counters, &e->work_counters, &e->model_cents,
                       &e->gene_totals, &e->t_ls, &e->t_ls_tile, &e->t_items, &e->t_items_sorted, &e->t_hist, &e->t_item_off,
-                      &e->t_unit_off, &e->t_sums, &e->t_witems, &e->ascii_next, &e->slotbase, &e->slot_contig, &e->nm, &e->ncount, &e->cflags, &e->plen, &e->gaps, &e->gap_count, &e->unit_totals, &e->next_unit, &e->win_stride, &e->win_off, &e->win_labels, &e->win_cents})
+                      &e->t_unit_off, &e->t_sums, &e->t_witems, &e->ascii_next, &e->slotbase, &e->slot_contig, &e->nm, &e->ncount, &e->codon, &e->cflags, &e->plen, &e->gaps, &e->gap_count, &e->unit_totals, &e->next_unit, &e->win_stride, &e->win_off, &e->win_labels, &e->win_cents})
         b->release();
     for (auto &ev : e->ev) cudaEventDestroy(ev);
     if (e->copy_done) cudaEventDestroy(e->copy_done);
@@ -1157,7 +1161,7 @@ int64_t mgc_recoded_stops(mgc_engine *e, const mgc_gene *genes, int64_t n_genes,
         d_counts.ensure(std::max<size_t>((size_t)n_genes * 12, 16));
         Planes pl;
         pl.lo = e->lo.as<uint32_t>(); pl.hi = e->hi.as<uint32_t>(); pl.nm = e->nm.as<uint32_t>(); pl.npre = e->ncount.as<uint32_t>();
-        pl.dflags = e->flags.as<int>(); pl.cflags = e->cflags.as<uint8_t>(); pl.W = e->W;
+        pl.dflags = e->flags.as<int>(); pl.cflags = e->cflags.as<uint8_t>(); pl.codon = e->codon.as<uint32_t>(); pl.W = e->W;
         if (n_genes) CUDA_TRY(cudaMemcpyAsync(d_refs.p, refs.data(), (size_t)n_genes * sizeof(GeneRef), cudaMemcpyHostToDevice, st));
         launch_recoded_stops(pl, e->cwoff.as<int64_t>(), e->clen.as<int32_t>(), d_refs.as<GeneRef>(), n_genes, d_counts.as<int32_t>(), nullptr,
                              nullptr, false, e->n_sm, st);

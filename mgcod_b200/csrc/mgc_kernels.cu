@@ -266,23 +266,67 @@ __global__ void __launch_bounds__(256) k_pack(const char *__restrict__ ascii, co
 // space; 0 = none).  A plain max-scan over words; consumers compare with their contig's first position.
 // ------------------------------------------------------------------------------------------------
 struct FindCtx {
-    const uint32_t *lo, *hi;  // planes of the strand region, contig slot
-    const uint32_t *nm;       // ambiguity mask of the same slot, nullptr when the batch has no ambiguous letter
+    const uint32_t *cp;       // codon planes of the strand region at the contig slot (plane p at cp + p * cstride)
+    int64_t cstride;
     int L;                    // contig length
     int stop_sel, atg_only;
 };
 
+// Codon planes (k_codon_planes): bit b of word w = "a codon of that kind starts at letter 32w + b".  Codon starts beyond
+// L - 3 and codons holding an ambiguous letter are already masked out.
+enum { CP_START3 = 0, CP_ATG = 1, CP_TAA = 2, CP_TAG = 3, CP_TGA = 4, CP_PLANES = 5 };
+
+__device__ __forceinline__ FindCtx make_ctx(const Planes &pl, int strand, int64_t w0, int L, int stop_sel, int atg_only) {
+    FindCtx cx;
+    cx.cp = pl.codon + (int64_t)strand * pl.W + w0;
+    cx.cstride = 2 * pl.W;
+    cx.L = L; cx.stop_sel = stop_sel; cx.atg_only = atg_only;
+    return cx;
+}
+
+__device__ __forceinline__ uint32_t starts_at(const FindCtx &cx, int w) { return cx.cp[(cx.atg_only ? CP_ATG : CP_START3) * cx.cstride + w]; }
+
+__device__ __forceinline__ uint32_t stops_at(const FindCtx &cx, int w) {   // the stop codons of the model's genetic code
+    uint32_t m = 0;
+    if (cx.stop_sel & 1) m |= cx.cp[CP_TAA * cx.cstride + w];
+    if (cx.stop_sel & 2) m |= cx.cp[CP_TAG * cx.cstride + w];
+    if (cx.stop_sel & 4) m |= cx.cp[CP_TGA * cx.cstride + w];
+    return m;
+}
+
 __device__ __forceinline__ CodonMasks masks_at(const FindCtx &cx, int w) {
-    CodonMasks m = codon_masks(cx.lo[w], cx.hi[w], cx.lo[w + 1], cx.hi[w + 1], cx.atg_only);
+    CodonMasks m;
+    m.start = starts_at(cx, w);
+    m.taa = cx.cp[CP_TAA * cx.cstride + w]; m.tag = cx.cp[CP_TAG * cx.cstride + w]; m.tga = cx.cp[CP_TGA * cx.cstride + w];
+    return m;
+}
+
+// thread per (strand, plane word): the five codon planes from the letter planes, once for all models
+__global__ void __launch_bounds__(256) k_codon_planes(Planes pl, const int64_t *__restrict__ cwoff, const int32_t *__restrict__ clen,
+                                                      const int32_t *__restrict__ grp2contig, uint32_t *codon) {
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int strand = blockIdx.y;
+    if (w >= pl.W) return;
+    const int c = grp2contig[w >> 2];
+    const int L = clen[c];
+    const int wl = (int)(w - cwoff[c]);
+    const int64_t at = (int64_t)strand * pl.W + w;
+    const uint32_t l0 = pl.lo[at], h0 = pl.hi[at], l1 = pl.lo[at + 1], h1 = pl.hi[at + 1];
+    CodonMasks m = codon_masks(l0, h0, l1, h1, 0);
+    const uint32_t atg = codon_masks(l0, h0, l1, h1, 1).start;
     // codon start positions must satisfy i <= L-3
-    int last = cx.L - 3 - 32 * w;
+    const int last = L - 3 - 32 * wl;
     uint32_t valid = last < 0 ? 0u : (last >= 31 ? 0xffffffffu : ((1u << (last + 1)) - 1u));
-    if (cx.nm) {  // a codon with an ambiguous letter is neither a start nor a stop
-        const uint32_t n0 = cx.nm[w], n1 = cx.nm[w + 1];
+    if (pl.dflags[1]) {  // a codon with an ambiguous letter is neither a start nor a stop
+        const uint32_t n0 = pl.nm[at], n1 = pl.nm[at + 1];
         valid &= ~(n0 | __funnelshift_r(n0, n1, 1) | __funnelshift_r(n0, n1, 2));
     }
-    m.start &= valid; m.taa &= valid; m.tag &= valid; m.tga &= valid;
-    return m;
+    const int64_t cs = 2 * pl.W;
+    codon[CP_START3 * cs + at] = m.start & valid;
+    codon[CP_ATG * cs + at] = atg & valid;
+    codon[CP_TAA * cs + at] = m.taa & valid;
+    codon[CP_TAG * cs + at] = m.tag & valid;
+    codon[CP_TGA * cs + at] = m.tga & valid;
 }
 
 struct U3 {
@@ -312,12 +356,8 @@ __global__ void __launch_bounds__(LS_THREADS) k_laststop_tiles(Planes pl, const 
         const int wl = (int)(ws - cwoff[c]);
         const int L = clen[c];
         if (L >= 3 && wl * 32 <= L - 3) {
-            FindCtx cx;
-            cx.lo = pl.lo + (int64_t)strand * pl.W + cwoff[c];
-            cx.hi = pl.hi + (int64_t)strand * pl.W + cwoff[c];
-        cx.nm = pl.dflags[1] ? pl.nm + (int64_t)strand * pl.W + cwoff[c] : nullptr;
-            cx.L = L; cx.stop_sel = models[mi].stop_sel; cx.atg_only = models[mi].atg_only;
-            const uint32_t sm = stop_mask(masks_at(cx, wl), cx.stop_sel);
+            const FindCtx cx = make_ctx(pl, strand, cwoff[c], L, models[mi].stop_sel, models[mi].atg_only);
+            const uint32_t sm = stops_at(cx, wl);
             const uint32_t P0 = (uint32_t)(w * 32);
             const int r0 = (int)(P0 % 3u);
 #pragma unroll
@@ -401,9 +441,8 @@ __device__ __forceinline__ bool make_orf(const FindCtx &cx, const DevModel &dm, 
         bool any = false;
         const int w_end = min(s_hi >> 5, (s_lo >> 5) + 3);
         for (int w = s_lo >> 5; w <= w_end && !any; w++) {
-            const CodonMasks m = masks_at(cx, w);
             const int r = ((f - (w * 32) % 3) % 3 + 3) % 3;
-            any = (m.start & frame_pattern(r) & bit_range(s_lo - 32 * w, s_hi - 32 * w)) != 0;
+            any = (starts_at(cx, w) & frame_pattern(r) & bit_range(s_lo - 32 * w, s_hi - 32 * w)) != 0;
         }
         if (!any && (s_hi >> 5) <= w_end) return false;
     }
@@ -444,16 +483,12 @@ __global__ void __launch_bounds__(128) k_orf_find(Planes pl, const int64_t *__re
         L = clen[c];
         const int wl = (int)(ws - cwoff[c]);
         if (L >= 6 && wl * 32 <= L - 3) {  // the word holds codon starts (virtual stops sit at t <= L-3 too)
-            FindCtx cx;
-            cx.lo = pl.lo + (int64_t)strand * pl.W + cwoff[c];
-            cx.hi = pl.hi + (int64_t)strand * pl.W + cwoff[c];
-            cx.nm = pl.dflags[1] ? pl.nm + (int64_t)strand * pl.W + cwoff[c] : nullptr;
-            cx.L = L; cx.stop_sel = dm.stop_sel; cx.atg_only = dm.atg_only;
+            const FindCtx cx = make_ctx(pl, strand, cwoff[c], L, dm.stop_sel, dm.atg_only);
             const uint32_t *ls = ls_m[mi];
             right_end = (pl.cflags[c] & 1) != 0;
             const uint32_t P0 = (uint32_t)(w * 32);                      // slot-space position of bit 0
             const uint32_t Pc = (uint32_t)(((int64_t)strand * pl.W + cwoff[c]) * 32);  // ... of the contig's first letter
-            const uint32_t all = stop_mask(masks_at(cx, wl), cx.stop_sel);
+            const uint32_t all = stops_at(cx, wl);
             // previous stop per frame coming from the words before this one
             uint32_t carry[3] = {0, 0, 0};
             if (w > 0) {  // within-tile scan value of the previous word, topped up with the carry into its tile
@@ -535,11 +570,7 @@ __global__ void __launch_bounds__(128) k_orf_find(Planes pl, const int64_t *__re
         const int re = __shfl_sync(0xffffffffu, (int)right_end, src);
         if (q < K) {
             const int tq = q_t[wib][q], pp = q_prev[wib][q];
-            FindCtx cx;
-            cx.lo = pl.lo + (int64_t)ss * pl.W + cwoff[cs];
-            cx.hi = pl.hi + (int64_t)ss * pl.W + cwoff[cs];
-            cx.nm = pl.dflags[1] ? pl.nm + (int64_t)ss * pl.W + cwoff[cs] : nullptr;
-            cx.L = Ls; cx.stop_sel = dm.stop_sel; cx.atg_only = dm.atg_only;
+            const FindCtx cx = make_ctx(pl, ss, cwoff[cs], Ls, dm.stop_sel, dm.atg_only);
             ok = make_orf(cx, dm, cs, ss, tq & 0x7fffffff, tq < 0, pp, re != 0, r);
         }
         const uint32_t okm = __ballot_sync(0xffffffffu, ok);
@@ -619,11 +650,7 @@ __global__ void __launch_bounds__(128) k_orf_count(Planes pl, const int64_t *__r
         const int t = rec.t, strand = rec.sf & 1;
         const bool open_left = has && (rec.sf & 2u) != 0;
         const int64_t w0 = has ? cwoff[rec.contig] : 0;
-        FindCtx cx;
-        cx.lo = pl.lo + (int64_t)strand * pl.W + w0;
-        cx.hi = pl.hi + (int64_t)strand * pl.W + w0;
-        cx.nm = pl.dflags[1] ? pl.nm + (int64_t)strand * pl.W + w0 : nullptr;
-        cx.L = has ? clen[rec.contig] : 0; cx.stop_sel = dm.stop_sel; cx.atg_only = dm.atg_only;
+        const FindCtx cx = make_ctx(pl, strand, w0, has ? clen[rec.contig] : 0, dm.stop_sel, dm.atg_only);
         const int f = t % 3;
         const int s_lo = rec.s_lo, s_hi = has ? min(t - 3, t + 3 - dm.min_len) : 0;
         const uint32_t nwords = has ? (uint32_t)((s_hi >> 5) - (s_lo >> 5) + 1) : 0u;
@@ -633,12 +660,11 @@ __global__ void __launch_bounds__(128) k_orf_count(Planes pl, const int64_t *__r
         if (wok)
             for (uint32_t j = 0; j < nwords; j++) {
                 const int w = (s_lo >> 5) + (int)j;
-                const CodonMasks m = masks_at(cx, w);
                 const int r = ((f - (w * 32) % 3) % 3 + 3) % 3;
                 WordItem wi;
                 wi.orf = (uint32_t)oi; wi.pre = n; wi.j = j;
                 witems[wbase + j] = wi;
-                n += __popc(m.start & frame_pattern(r) & bit_range(s_lo - 32 * w, s_hi - 32 * w));
+                n += __popc(starts_at(cx, w) & frame_pattern(r) & bit_range(s_lo - 32 * w, s_hi - 32 * w));
             }
         if (!wok) n = 0;
         const unsigned long long base = warp_reserve(&counters[1], n);
@@ -669,11 +695,7 @@ __global__ void __launch_bounds__(256) k_orf_starts(Planes pl, const uint32_t *_
         const int c = rec.contig, t = rec.t, strand = rec.sf & 1;
         const int L = clen[c];
         const int64_t w0 = cwoff[c];
-        FindCtx cx;
-        cx.lo = pl.lo + (int64_t)strand * pl.W + w0;
-        cx.hi = pl.hi + (int64_t)strand * pl.W + w0;
-        cx.nm = pl.dflags[1] ? pl.nm + (int64_t)strand * pl.W + w0 : nullptr;
-        cx.L = L; cx.stop_sel = dm.stop_sel; cx.atg_only = dm.atg_only;
+        const FindCtx cx = make_ctx(pl, strand, w0, L, dm.stop_sel, dm.atg_only);
         const int f = t % 3;
         const int s_lo = rec.s_lo, s_hi = min(t - 3, t + 3 - dm.min_len);
         const int w = (s_lo >> 5) + (int)wi.j;
@@ -694,9 +716,8 @@ __global__ void __launch_bounds__(256) k_orf_starts(Planes pl, const uint32_t *_
             kk = rec.base;
             put(f, true);
         }
-        const CodonMasks m = masks_at(cx, w);
         const int r = ((f - (w * 32) % 3) % 3 + 3) % 3;
-        uint32_t mm = m.start & frame_pattern(r) & bit_range(s_lo - 32 * w, s_hi - 32 * w);
+        uint32_t mm = starts_at(cx, w) & frame_pattern(r) & bit_range(s_lo - 32 * w, s_hi - 32 * w);
         while (mm) {
             const int b = __ffs(mm) - 1;
             mm &= mm - 1;
@@ -1805,14 +1826,7 @@ __global__ void __launch_bounds__(128) k_recoded_stops(Planes pl, const int64_t 
     const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t g = warp; g < n_genes; g += nw) {
         const GeneRef gr = genes[g];
-        FindCtx cx;
-        const int64_t w0s = cwoff[gr.slot];
-        cx.lo = pl.lo + (int64_t)gr.strand * pl.W + w0s;
-        cx.hi = pl.hi + (int64_t)gr.strand * pl.W + w0s;
-        cx.nm = pl.dflags[1] ? pl.nm + (int64_t)gr.strand * pl.W + w0s : nullptr;
-        cx.L = clen[gr.slot];
-        cx.stop_sel = 7;
-        cx.atg_only = 0;
+        const FindCtx cx = make_ctx(pl, gr.strand, cwoff[gr.slot], clen[gr.slot], 7, 0);
         const int s = gr.start, last = gr.start + gr.n - 4;  // codon starts p with s <= p <= last, p = s mod 3: all but the final codon
         int base[3] = {0, 0, 0};
         if (last >= s) {
@@ -1910,6 +1924,10 @@ void launch_pack(const char *ascii, const int64_t *aoff, const int64_t *cwoff, c
                  cudaStream_t st) {
     dim3 grid((unsigned)((W + 255) / 256), 2);
     k_pack<<<grid, 256, 0, st>>>(ascii, aoff, cwoff, clen, grp2contig, W, lo, hi, nm, gccount, ncount, dflags);
+}
+
+void launch_codon_planes(Planes pl, const int64_t *cwoff, const int32_t *clen, const int32_t *grp2contig, uint32_t *codon, cudaStream_t st) {
+    k_codon_planes<<<dim3((unsigned)((pl.W + 255) / 256), 2), 256, 0, st>>>(pl, cwoff, clen, grp2contig, codon);
 }
 
 int launch_laststop(Planes pl, const int64_t *cwoff, const int32_t *clen, const int32_t *grp2contig, const DevModel *models,

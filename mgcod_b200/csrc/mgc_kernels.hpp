@@ -24,6 +24,7 @@ void launch_pack(const char *ascii, const int64_t *aoff, const int64_t *cwoff, c
                  cudaStream_t st);
 void launch_recoded_stops(Planes pl, const int64_t *cwoff, const int32_t *clen, const GeneRef *genes, int64_t n_genes, int32_t *counts,
                           const int64_t *pos_off, int32_t *pos_out, bool fill, int n_sm, cudaStream_t st);
+void launch_codon_planes(Planes pl, const int64_t *cwoff, const int32_t *clen, const int32_t *grp2contig, uint32_t *codon, cudaStream_t st);
 void launch_find_gaps(const uint32_t *nm, const int64_t *cwoff, const int32_t *clen, int32_t n_contigs, int min_run, int32_t *gaps,
                       unsigned int *gap_count, unsigned int cap, cudaStream_t st);
 int launch_laststop(Planes pl, const int64_t *cwoff, const int32_t *clen, const int32_t *grp2contig, const DevModel *models,
