@@ -148,3 +148,31 @@ def test_genes_longer_than_a_chain_piece(engine, oracles):
         diffs = parity.compare_candidates(engine.candidates(mi), orc, test_seqs)
         assert not diffs, f"model {CODES[mi]}: " + "; ".join(diffs[:6])
     assert found_long >= 4          # the long gene is predicted, so candidates spanning > 128 boundaries existed
+
+
+def test_many_short_and_odd_length_contigs_match_oracle(engine, oracles):
+    """hundreds of contigs of 0..700 nt (lengths around the word, bucket and minimum-gene-length boundaries), cut from
+    gene-dense sequence at random offsets, plus their reverse complements: slot, bucket, piece and edge-partial logic"""
+    import random
+    rng = random.Random(20260222)
+    buf, offs, seqs = _synthetic(123, 150000)
+    src = b"".join(seqs)
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    lens = [0, 1, 2, 3, 5, 6, 31, 32, 33, 63, 64, 65, 89, 90, 91, 92, 93, 95, 96, 97, 127, 128, 129, 130, 191, 192, 255, 256, 257]
+    test_seqs = []
+    for L in lens * 4 + [rng.randrange(90, 700) for _ in range(250)]:
+        a = rng.randrange(0, len(src) - L - 1)
+        s = src[a:a + L]
+        test_seqs.append(s if rng.random() < 0.5 else s.translate(comp)[::-1])
+    rng.shuffle(test_seqs)
+    res = engine.decode(test_seqs)
+    total = 0
+    for mi, orc in enumerate(oracles):
+        rows, totals = parity.oracle_genes(orc, test_seqs)
+        total += len(rows)
+        diffs = parity.compare_genes(res.genes(mi), rows)
+        assert not diffs, f"model {CODES[mi]}: " + "; ".join(diffs[:6])
+        np.testing.assert_allclose(res.contig_totals(mi), totals, rtol=1e-9, atol=1e-9)
+    assert total > 500
+    diffs = parity.compare_candidates(engine.candidates(3), oracles[3], test_seqs)
+    assert not diffs, "; ".join(diffs[:6])
