@@ -128,3 +128,39 @@ def test_decode_stream_equals_batch_by_batch(engine):
     assert np.array_equal(r.genes(0), want[1][0])
     r = engine.decode_buffer(*batches[0])
     assert np.array_equal(r.genes(2), want[0][2])
+
+
+@pytest.mark.parametrize("kc,kn,gcode,domains,bins", [
+    (0, 0, 11, ("B",), [40]),
+    (1, 0, 4, ("B", "A"), [35, 45]),
+    (2, 1, 25, ("B",), [30, 38, 46]),
+    (2, 2, 1, ("B", "A"), [40]),            # genetic code 1: ATG is the only start codon
+    (4, 0, 15, ("B",), [33, 44]),
+    (5, 2, 101, ("B", "A"), [36, 42]),      # order 5: tables too large for shared memory, gathered from global memory
+    (5, 3, 11, ("B",), [41]),
+])
+def test_model_orders_codes_and_domains_match_oracle(kc, kn, gcode, domains, bins, tmp_path):
+    """every Markov order the parser accepts (0..5 coding, 0..3 non-coding), the genetic codes outside Mgcod's four (25, 1),
+    bacterial-only and two-domain files, one to three GC bins — genes and chain totals against the oracle"""
+    import lzma, os
+    from mgcod_b200 import synth
+    from mgcod_b200.engine import Engine, synth_metagenome
+    from oracle import gmhmm
+    from tests import parity
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "phage2.fa.xz")
+    template = "".join(l.strip() for l in lzma.open(golden, "rt") if not l.startswith(">")).upper()
+    mod = str(tmp_path / "m.mod")
+    synth.write_mod(mod, synth.trained_sections(synth.encode(template), gcode, kc, kn, bins=bins, domains=domains))
+    buf, offs, truth = synth_metagenome(300 + kc * 10 + kn, 90000, threads=2)
+    seqs = [buf[offs[i]:offs[i + 1]].tobytes() for i in range(len(truth))] + [template[20000:50000].encode()]
+    eng = Engine([mod])
+    res = eng.decode(seqs)
+    orc = gmhmm.Model(mod)
+    rows, totals = parity.oracle_genes(orc, seqs)
+    assert len(rows) > 20
+    diffs = parity.compare_genes(res.genes(0), rows)
+    assert not diffs, "; ".join(diffs[:6])
+    np.testing.assert_allclose(res.contig_totals(0), totals, rtol=1e-9, atol=1e-9)
+    diffs = parity.compare_candidates(eng.candidates(0), orc, seqs)
+    assert not diffs, "; ".join(diffs[:6])
+    eng.close()
