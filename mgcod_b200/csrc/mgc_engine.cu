@@ -182,6 +182,7 @@ struct mgc_engine {
     DevBuf gene_totals;    // [M] uint32 grand totals of the gene scans
     DevBuf win_stride, win_off, win_labels, win_cents;
     uint32_t cap_orf = 0, cap_starts = 0, cap_surv = 0;
+    int cap_scale = 1;     // multiplier of the scratch capacities, raised on overflow
     std::vector<unsigned char> table_sig;   // contents of the device pointer tables as last uploaded
     bool have_batch = false, have_genes = false;
     mgc_stats stats;
@@ -346,11 +347,13 @@ void ensure_batch_buffers(mgc_engine *e) {
     e->grp2contig.ensure((size_t)(W / 4 + 8) * 4);
     e->flags.ensure(64);
     // observed on gene-dense input per kb and model: ~11 ORFs, ~36 starts, ~18 walk items, ~10 surviving candidates
-    e->cap_orf = (uint32_t)std::min<int64_t>(nt / 24 + 8192, 0x7fffff00);
-    e->cap_starts = (uint32_t)std::min<int64_t>(nt / 8 + 8192, 0x7fffff00);
-    e->cap_items = (uint32_t)std::min<int64_t>(nt / 16 + 8192, 0x7fffff00);
-    e->cap_surv = (uint32_t)std::min<int64_t>(nt / 24 + 8192, 0x7fffff00);
-    e->cap_witems = (uint32_t)std::min<int64_t>(nt / 8 + 8192, 0x7fffff00);
+    // cap_scale doubles when a batch turns out denser than that (low-complexity sequence such as ATG repeats): do_decode retries
+    const int64_t sc = e->cap_scale;
+    e->cap_orf = (uint32_t)std::min<int64_t>(nt / 24 * sc + 8192, 0x7fffff00);
+    e->cap_starts = (uint32_t)std::min<int64_t>(nt / 8 * sc + 8192, 0x7fffff00);
+    e->cap_items = (uint32_t)std::min<int64_t>(nt / 16 * sc + 8192, 0x7fffff00);
+    e->cap_surv = (uint32_t)std::min<int64_t>(nt / 24 * sc + 8192, 0x7fffff00);
+    e->cap_witems = (uint32_t)std::min<int64_t>(nt / 8 * sc + 8192, 0x7fffff00);
     std::vector<void *> t_witems(M);
     std::vector<void *> t_orfs(M), t_starts(M), t_surv(M), t_sorted(M), t_bcount(M), t_cover(M), t_gene_off(M), t_genes(M);
     std::vector<void *> t_ls(M), t_ls_tile(M), t_items(M), t_items_sorted(M), t_hist(M), t_item_off(M), t_unit_off(M), t_sums(M);
@@ -690,7 +693,7 @@ mgc_result *run_pipeline(mgc_engine *e, bool *amb_out) {
     for (int i = 0; i < M; i++) {
         if (h_counters[(size_t)i * 8] > e->cap_orf || h_counters[(size_t)i * 8 + 1] > e->cap_starts ||
             h_counters[(size_t)i * 8 + 2] > e->cap_items || h_counters[(size_t)i * 8 + 3] > e->cap_witems || h_surv[i] > e->cap_surv)
-            throw std::runtime_error("device scratch exhausted (ORFs " + std::to_string(h_counters[(size_t)i * 8]) + ", starts " +
+            throw mgc::ScratchExhausted("device scratch exhausted (ORFs " + std::to_string(h_counters[(size_t)i * 8]) + ", starts " +
                                      std::to_string(h_counters[(size_t)i * 8 + 1]) + ", candidates " + std::to_string(h_surv[i]) + ")");
         e->stats.n_orfs += (int64_t)h_counters[(size_t)i * 8];
         e->stats.n_starts += (int64_t)h_counters[(size_t)i * 8 + 1];
@@ -763,9 +766,23 @@ void remap_to_parents(mgc_engine *e, mgc_result *res) {
     res->n_contigs = np;
 }
 
+// run_pipeline with the scratch capacities doubled (up to 32x) when the batch holds more ORFs / starts / candidates per
+// letter than the defaults provide for
+mgc_result *run_pipeline_growing(mgc_engine *e, bool *amb_out) {
+    while (true) {
+        try {
+            return run_pipeline(e, amb_out);
+        } catch (const mgc::ScratchExhausted &) {
+            if (e->cap_scale >= 32) throw;
+            e->cap_scale *= 2;
+            ensure_batch_buffers(e);
+        }
+    }
+}
+
 mgc_result *do_decode(mgc_engine *e) {
     bool amb = false;
-    std::unique_ptr<mgc_result> res(run_pipeline(e, &amb));
+    std::unique_ptr<mgc_result> res(run_pipeline_growing(e, &amb));
     if (amb && !e->segmented) {
         // runs of >= 40 ambiguous letters split a record (gmhmmp2 --incomplete_at_gaps 40): find them on the device,
         // re-slot the batch and decode again
@@ -801,7 +818,7 @@ mgc_result *do_decode(mgc_engine *e) {
             e->segs.swap(segs);
             e->segmented = true;
             set_slots(e);
-            res.reset(run_pipeline(e, &amb));
+            res.reset(run_pipeline_growing(e, &amb));
         }
     }
     if (e->segmented) remap_to_parents(e, res.get());

@@ -6,6 +6,10 @@
 
 namespace mgc {
 
+struct ScratchExhausted : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
 struct AlphabetError : std::runtime_error {
     using std::runtime_error::runtime_error;
 };

@@ -164,3 +164,31 @@ def test_model_orders_codes_and_domains_match_oracle(kc, kn, gcode, domains, bin
     diffs = parity.compare_candidates(eng.candidates(0), orc, seqs)
     assert not diffs, "; ".join(diffs[:6])
     eng.close()
+
+
+def test_low_complexity_repeats_grow_the_scratch_buffers(engine):
+    """(ATG)n / (CAT)n repeats hold a start codon every three letters — far more starts per letter than the scratch
+    capacities assume; the engine must notice, grow and still agree with the oracle"""
+    from mgcod_b200.engine import synth_metagenome
+    from oracle import gmhmm
+    from tests import parity
+    import tempfile
+    from mgcod_b200 import synth
+    buf, offs, _ = synth_metagenome(55, 30000, threads=2)
+    flank = buf[offs[0]:offs[1]].tobytes()[:6000]
+    a = flank[:3000] + b"ATG" * 14000 + b"TAA" + flank[3000:]
+    b = flank[:2001] + b"TTA" + b"CAT" * 14000 + flank[2001:]
+    seqs = [a, b, flank]
+    res = engine.decode(seqs)
+    st = engine.stats()
+    assert st["n_starts"] > 4 * 2 * 14000 * 0.9
+    d = tempfile.mkdtemp()
+    paths = synth.write_model_set(d, kind="parametric")
+    for mi, code in ((0, 11), (3, 101)):
+        rows, totals = parity.oracle_genes(gmhmm.Model(paths[code]), seqs)
+        diffs = parity.compare_genes(res.genes(mi), rows)
+        assert not diffs, f"model {code}: " + "; ".join(diffs[:6])
+        np.testing.assert_allclose(res.contig_totals(mi), totals, rtol=1e-9, atol=1e-9)
+    # the engine keeps working at normal sizes afterwards
+    res2 = engine.decode([flank])
+    assert np.array_equal(res2.genes(0)[["left", "right"]], res.genes(0)[res.genes(0)["contig"] == 2][["left", "right"]])
