@@ -11,7 +11,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmgcod_b200.so")
+LIB_PATH = os.environ.get("MGCOD_B200_LIB") or os.path.join(_HERE, "libmgcod_b200.so")   # override: A/B runs of two builds
 
 MGC_MAX_MODELS = 8
 MGC_E_ARG, MGC_E_IO, MGC_E_PARSE, MGC_E_CUDA, MGC_E_ALPHABET, MGC_E_NOMEM = -1, -2, -3, -4, -5, -6

@@ -34,6 +34,7 @@ struct DevModel {
     int map[2][101];
     int pair[101];      // gc -> index of its (secB, secA) pair in quad
     const double *pair_amb;  // [npair][4]: ln COD_P_N (B, A), ln NON_P_N (B, A) — terms of a window with an ambiguous letter
+    const double *pair_ub;   // [npair][2][3]: upper bounds of the ramp, start and stop terms per domain (early pruning in k_final)
 };
 
 // one stop-delimited ORF that may have start candidates of sufficient length

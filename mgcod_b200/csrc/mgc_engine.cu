@@ -117,7 +117,7 @@ struct DevBuf {
 };
 
 struct PerModel {
-    DevBuf lc_full, ln_full, lc_ramp, ln_ramp, sc, quad, rquad, wtab, pair_amb;
+    DevBuf lc_full, ln_full, lc_ramp, ln_ramp, sc, quad, rquad, wtab, pair_amb, pair_ub;
     DevBuf ls, ls_tile, orfs, starts, witems, items, items_sorted, hist, item_off, unit_off, sums;
     DevBuf surv, sorted, bcount, cum, prev, gptr;
     DevBuf av_right, av_left, av_ls, av_idx, av_cum, av_pmax, av_parg, chain, gene_count, gene_off, contig_total, genes;
@@ -321,6 +321,30 @@ void upload_models(mgc_engine *e) {
                 }
             up(p.pair_amb, pa.data(), pa.size() * sizeof(double));
             d.pair_amb = p.pair_amb.as<double>();
+        }
+        {
+            // upper bounds of what k_final adds to a start's walk sum, per pair and domain: order ramp (0 if ambiguous letters
+            // silence it), start term, stop term.  A start whose bound stays <= 0 is pruned without touching the planes.
+            std::vector<double> ub(pairs.size() * 6, 0.0);
+            for (size_t pi = 0; pi < pairs.size(); pi++)
+                for (int dom = 0; dom < 2; dom++) {
+                    const int sec = dom ? pairs[pi].second : pairs[pi].first;
+                    if (sec < 0) continue;
+                    double ramp = 0.0;
+                    for (int j = 0; j < kc; j++) {
+                        double best = -1e300;
+                        for (size_t idx = 0; idx < ((size_t)1 << (2 * (j + 1))); idx++) {
+                            const Quad &e4 = rq[(pi * kr + j) * nramp + idx];
+                            best = std::max(best, dom ? e4.oA : e4.oB);
+                        }
+                        ramp += std::max(best, 0.0);   // a short candidate may stop before position j
+                    }
+                    ub[pi * 6 + dom * 3 + 0] = ramp;
+                    ub[pi * 6 + dom * 3 + 1] = std::max({m.sc[sec].start_lo[0], m.sc[sec].start_lo[1], m.sc[sec].start_lo[2]});
+                    ub[pi * 6 + dom * 3 + 2] = std::max({m.sc[sec].stop_lo[0], m.sc[sec].stop_lo[1], m.sc[sec].stop_lo[2]});
+                }
+            up(p.pair_ub, ub.data(), ub.size() * sizeof(double));
+            d.pair_ub = p.pair_ub.as<double>();
         }
         up(p.rquad, rq.data(), std::max<size_t>(rq.size(), 1) * sizeof(Quad));
         d.rquad = p.rquad.as<Quad>();
@@ -913,7 +937,7 @@ void mgc_engine_destroy(mgc_engine *e) {
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
     for (auto &p : e->pm) {
-        for (DevBuf *b : {&p.lc_full, &p.ln_full, &p.lc_ramp, &p.ln_ramp, &p.sc, &p.quad, &p.rquad, &p.wtab, &p.pair_amb, &p.ls, &p.ls_tile, &p.items, &p.items_sorted, &p.hist,
+        for (DevBuf *b : {&p.lc_full, &p.ln_full, &p.lc_ramp, &p.ln_ramp, &p.sc, &p.quad, &p.rquad, &p.wtab, &p.pair_amb, &p.pair_ub, &p.ls, &p.ls_tile, &p.items, &p.items_sorted, &p.hist,
                           &p.item_off, &p.unit_off, &p.sums, &p.witems, &p.orfs, &p.starts, &p.surv, &p.sorted, &p.bcount,
                           &p.cum, &p.prev, &p.gptr, &p.av_right, &p.av_left, &p.av_ls, &p.av_idx, &p.av_cum, &p.av_pmax, &p.av_parg,
                           &p.chain, &p.gene_count, &p.gene_off, &p.contig_total, &p.genes, &p.piece_b0, &p.piece_b1, &p.work,

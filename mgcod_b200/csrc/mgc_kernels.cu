@@ -1107,6 +1107,24 @@ __global__ void __launch_bounds__(256) k_final(Planes pl, const int64_t *__restr
             const int fullstart = first + kc;
             Acc4 acc = {0, 0, 0, 0};
             if (fullstart <= t - 1) acc = sums[k];
+            // Early pruning: with the largest possible ramp / start / stop terms of either domain the total stays <= 0 for most
+            // starts of spurious ORFs; those never touch the planes or the ramp tables.  (Exact otherwise: only candidates
+            // that the full computation would prune as well are dropped, with a 1e-6 guard band.)
+            const double dl = (double)len;
+            const double lgt = 2.0 * log(dl) - 1.3862943611198906;
+            bool maybe = false;
+            {
+                const double *ub = dm.pair_ub + pair * 6;
+                if (secB >= 0) {
+                    const SectionScalars *sb = dm.sc + secB;
+                    maybe |= acc.oB + ub[0] + lgt + dl * sb->dur_slope + sb->dur_const + (virt ? 0.0 : ub[1]) + (pstop ? 0.0 : ub[2]) > -1e-6;
+                }
+                if (secA >= 0) {
+                    const SectionScalars *sa = dm.sc + secA;
+                    maybe |= acc.oA + ub[3] + lgt + dl * sa->dur_slope + sa->dur_const + (virt ? 0.0 : ub[4]) + (pstop ? 0.0 : ub[5]) > -1e-6;
+                }
+            }
+            if (maybe) {
             const uint32_t *nmp = pl.dflags[1] ? pl.nm + (int64_t)strand * pl.W + w0 : nullptr;
             // order ramp: orders 0..kc-1 at positions first .. first+kc-1 (window starts on a codon boundary)
             const Quad *rq = dm.rquad + (size_t)pair * dm.kr * nramp;
@@ -1130,7 +1148,6 @@ __global__ void __launch_bounds__(256) k_final(Planes pl, const int64_t *__restr
             if (secB >= 0 || secA >= 0) {
                 const bool arc = secB < 0 || (secA >= 0 && acc.cA > acc.cB);
                 const SectionScalars *sc = dm.sc + (arc ? secA : secB);
-                const double dl = (double)len;
                 double total = (arc ? acc.oA : acc.oB) + 2.0 * log(dl) + dl * sc->dur_slope + sc->dur_const - 1.3862943611198906;
                 if (!virt) {
                     uint32_t hb, lb;
@@ -1155,6 +1172,7 @@ __global__ void __launch_bounds__(256) k_final(Planes pl, const int64_t *__restr
                 cd.strand = strand ? -1 : 1;
                 cd.flags = (uint8_t)((arc ? 1 : 0) | (virt ? 2 : 0) | (pstop ? 4 : 0));
                 cd.len = len;
+            }
             }
         }
         // reverse strand: the survivor with the largest s has the smallest forward right end, so the chain meets it
