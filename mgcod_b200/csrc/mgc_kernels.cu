@@ -17,6 +17,7 @@
 //
 // Arithmetic follows SURVEY.md §A.4-A.6 as pinned by oracle/ (never linked here).
 #include <cstdint>
+#include <cstdlib>
 #include <cstdio>
 
 #include "mgc_device.cuh"
@@ -723,6 +724,130 @@ __global__ void __launch_bounds__(256) k_orf_starts(Planes pl, const uint32_t *_
             mm &= mm - 1;
             put(w * 32 + b, false);
         }
+    }
+}
+
+// prep 1+2 fused, load-balanced: a block takes EXPAND_ORFS ORFs, expands them into their 32-letter words (exclusive scan of
+// the word counts, binary search per word), counts the start codons of every word with dense lanes, reserves the tile's
+// slice of the start array with one atomic, and writes the start records (position, GC bin, section pair) word by word.
+// The flat prefix of the per-word counts in expansion order is at the same time the offset of the word's first start.
+constexpr int EXPAND_ORFS = 256;
+__global__ void __launch_bounds__(EXPAND_ORFS) k_orf_expand(Planes pl, const uint32_t *__restrict__ gcpre, const int64_t *__restrict__ cwoff,
+                                                            const int32_t *__restrict__ clen, const DevModel *__restrict__ models,
+                                                            OrfRec *const *orfs_m, StartRec *const *starts_m, unsigned long long *counters_m,
+                                                            const ChainBufs *bufs_m, uint32_t cap_orf, uint32_t cap_starts) {
+    __shared__ uint32_t o_woff[EXPAND_ORFS + 1];     // first expanded word of each ORF
+    __shared__ int o_wfirst[EXPAND_ORFS], o_t[EXPAND_ORFS], o_slo[EXPAND_ORFS], o_shi[EXPAND_ORFS], o_contig[EXPAND_ORFS];
+    __shared__ uint32_t o_sf[EXPAND_ORFS], o_ok[EXPAND_ORFS];
+    __shared__ unsigned long long s_tile_base;
+    const int mi = blockIdx.y;
+    const DevModel &dm = models[mi];
+    unsigned long long *counters = counters_m + (size_t)mi * 8;
+    unsigned long long n_orfs = counters[0];
+    if (n_orfs > cap_orf) n_orfs = cap_orf;
+    OrfRec *orfs = orfs_m[mi];
+    StartRec *starts = starts_m[mi];
+    int32_t *gptr = bufs_m[mi].gptr;
+    const int tid = threadIdx.x;
+    for (int64_t tile0 = (int64_t)blockIdx.x * EXPAND_ORFS; tile0 < (int64_t)n_orfs; tile0 += (int64_t)gridDim.x * EXPAND_ORFS) {
+        // ---- the tile's ORFs ----
+        const int64_t oi = tile0 + tid;
+        const bool has = oi < (int64_t)n_orfs;
+        uint32_t nwords = 0;
+        if (has) {
+            const OrfRec rec = orfs[oi];
+            gptr[oi] = GPTR_UNSET;
+            const int s_hi = min(rec.t - 3, rec.t + 3 - dm.min_len);
+            o_wfirst[tid] = rec.s_lo >> 5;
+            o_t[tid] = rec.t; o_slo[tid] = rec.s_lo; o_shi[tid] = s_hi; o_contig[tid] = rec.contig; o_sf[tid] = rec.sf;
+            nwords = (uint32_t)((s_hi >> 5) - (rec.s_lo >> 5) + 1);
+        }
+        uint32_t tw;
+        const uint32_t wo = block_exclusive_scan(nwords, &tw);
+        o_woff[tid] = wo;
+        if (tid == 0) o_woff[EXPAND_ORFS] = tw;
+        __syncthreads();
+        // the word an expansion index stands for, and its start-codon mask (plus the virtual start in an ORF's first word)
+        auto word_of = [&](uint32_t k, int &i, int &w, uint32_t &mask, bool &virt_here) {
+            int lo = 0, hi = EXPAND_ORFS;   // last ORF with o_woff <= k
+            while (lo + 1 < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (o_woff[mid] <= k) lo = mid; else hi = mid;
+            }
+            i = lo;
+            const int j = (int)(k - o_woff[i]);
+            w = o_wfirst[i] + j;
+            const int c = o_contig[i], strand = (int)(o_sf[i] & 1u);
+            const FindCtx cx = make_ctx(pl, strand, cwoff[c], clen[c], dm.stop_sel, dm.atg_only);
+            const int f = o_t[i] % 3;
+            const int r = ((f - (w * 32) % 3) % 3 + 3) % 3;
+            mask = starts_at(cx, w) & frame_pattern(r) & bit_range(o_slo[i] - 32 * w, o_shi[i] - 32 * w);
+            virt_here = j == 0 && (o_sf[i] & 2u) != 0;
+        };
+        // ---- pass 1: starts of the tile ----
+        uint32_t mine = 0;
+        for (uint32_t k = tid; k < tw; k += EXPAND_ORFS) {
+            int i, w;
+            uint32_t mask;
+            bool vh;
+            word_of(k, i, w, mask, vh);
+            mine += (uint32_t)__popc(mask) + (vh ? 1u : 0u);
+        }
+        uint32_t tile_total;
+        block_exclusive_scan(mine, &tile_total);
+        if (tid == 0) s_tile_base = tile_total ? atomicAdd(&counters[1], (unsigned long long)tile_total) : 0ull;
+        __syncthreads();
+        const unsigned long long tile_base = s_tile_base;
+        const bool tile_ok = tile_base + tile_total <= cap_starts;
+        // ---- pass 2: flat prefix in expansion order = offset of each word's first start; write the records ----
+        uint32_t carry = 0;
+        for (uint32_t k0 = 0; k0 < tw; k0 += EXPAND_ORFS) {
+            const uint32_t k = k0 + tid;
+            int i = 0, w = 0;
+            uint32_t mask = 0;
+            bool vh = false;
+            if (k < tw) word_of(k, i, w, mask, vh);
+            const uint32_t cnt = (uint32_t)__popc(mask) + (vh ? 1u : 0u);
+            uint32_t chunk_total;
+            const uint32_t pre = carry + block_exclusive_scan(cnt, &chunk_total);
+            carry += chunk_total;
+            if (k < tw) {
+                if (k == o_woff[i]) o_ok[i] = pre;   // offset of the ORF's first start inside the tile
+                if (tile_ok && cnt) {
+                    const int c = o_contig[i], t = o_t[i], strand = (int)(o_sf[i] & 1u);
+                    const int L = clen[c];
+                    const int64_t w0 = cwoff[c];
+                    unsigned long long kk = tile_base + pre;
+                    auto put = [&](int sp, bool virt) {
+                        const int len = t + 3 - sp;
+                        const int a = strand ? (L - 1 - (t + 2)) : sp, b = strand ? (L - 1 - sp) : (t + 2);
+                        const int gc2 = gc2_count_fwd(pl, gcpre, w0, a, b);
+                        const int gc = (100 * gc2 + len) / (2 * len);   // round half up of 100 * (GC + N/2) / len
+                        StartRec sr;
+                        sr.sraw = (uint32_t)sp | (virt ? 0x80000000u : 0u);
+                        sr.orf = (uint32_t)(tile0 + i);
+                        sr.pg = (uint32_t)dm.pair[gc] | ((uint32_t)gc << 16);
+                        sr.link = -1;
+                        starts[kk++] = sr;
+                    };
+                    if (vh) put(t % 3, true);   // the virtual start at the contig edge comes first
+                    while (mask) {
+                        const int bpos = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        put(w * 32 + bpos, false);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // ---- the ORFs' slices ----
+        if (has) {
+            const uint32_t first = o_ok[tid];
+            const uint32_t next = tid + 1 < EXPAND_ORFS && tile0 + tid + 1 < (int64_t)n_orfs ? o_ok[tid + 1] : tile_total;
+            orfs[oi].base = (uint32_t)(tile_base + first);
+            orfs[oi].n = tile_ok ? next - first : 0u;
+        }
+        __syncthreads();
     }
 }
 
@@ -1969,9 +2094,14 @@ int launch_orf_prep(Planes pl, const uint32_t *gcpre, const int64_t *cwoff, cons
                     uint32_t *const *hist_m, unsigned long long *counters_m, const ChainBufs *bufs_m, uint32_t cap_orf,
                     uint32_t cap_starts, uint32_t cap_items, uint32_t cap_witems, int n_sm, cudaStream_t st) {
     dim3 grid(n_sm * 16, n_models);
-    k_orf_count<<<grid, 128, 0, st>>>(pl, cwoff, clen, models, orfs_m, witems_m, counters_m, bufs_m, cap_orf, cap_starts, cap_witems);
-    dim3 grid2(n_sm * 8, n_models);
-    k_orf_starts<<<grid2, 256, 0, st>>>(pl, gcpre, cwoff, clen, models, orfs_m, witems_m, starts_m, counters_m, cap_witems);
+    if (std::getenv("MGCOD_OLD_PREP")) {
+        k_orf_count<<<grid, 128, 0, st>>>(pl, cwoff, clen, models, orfs_m, witems_m, counters_m, bufs_m, cap_orf, cap_starts, cap_witems);
+        dim3 grid2(n_sm * 8, n_models);
+        k_orf_starts<<<grid2, 256, 0, st>>>(pl, gcpre, cwoff, clen, models, orfs_m, witems_m, starts_m, counters_m, cap_witems);
+    } else {
+        k_orf_expand<<<dim3(n_sm * 8, n_models), EXPAND_ORFS, 0, st>>>(pl, gcpre, cwoff, clen, models, orfs_m, starts_m, counters_m, bufs_m,
+                                                                     cap_orf, cap_starts);
+    }
     k_orf_link<<<grid, 128, 0, st>>>(pl, cwoff, clen, models, orfs_m, starts_m, items_m, hist_m, counters_m, cap_orf, cap_items);
     return 3;
 }
