@@ -58,11 +58,6 @@ struct StartRec {
 };
 
 // one 32-letter word of an ORF's admissible start range
-struct WordItem {
-    uint32_t orf;
-    uint32_t pre;       // starts of the ORF before this word (incl. the virtual one)
-    uint32_t j;         // word index within the range
-};
 
 // one walk of an ORF under one section pair: serves every start of that pair
 struct ItemRec {

@@ -118,7 +118,7 @@ struct DevBuf {
 
 struct PerModel {
     DevBuf lc_full, ln_full, lc_ramp, ln_ramp, sc, quad, rquad, wtab, pair_amb, pair_ub;
-    DevBuf ls, ls_tile, orfs, starts, witems, items, items_sorted, hist, item_off, unit_off, sums;
+    DevBuf ls, ls_tile, orfs, starts, items, items_sorted, hist, item_off, unit_off, sums;
     DevBuf surv, sorted, bcount, cum, prev, gptr;
     DevBuf av_right, av_left, av_ls, av_idx, av_cum, av_pmax, av_parg, chain, gene_count, gene_off, contig_total, genes;
     DevBuf piece_b0, piece_b1, work, piece_total, slot_gene_off, cover, minleft;
@@ -170,8 +170,6 @@ struct mgc_engine {
     } pending;
     // pointer tables + counters (device)
     DevBuf t_orfs, t_starts, t_surv, t_sorted, t_bcount, t_cover, t_gene_off, t_genes, t_chainbufs;
-    DevBuf t_witems;
-    uint32_t cap_witems = 0;
     DevBuf t_ls, t_ls_tile, t_items, t_items_sorted, t_hist, t_item_off, t_unit_off, t_sums, unit_totals, next_unit;
     uint32_t cap_items = 0;
     int max_cod_order = 0, max_non_order = 0, max_pairs = 1;
@@ -377,8 +375,6 @@ void ensure_batch_buffers(mgc_engine *e) {
     e->cap_starts = (uint32_t)std::min<int64_t>(nt / 8 * sc + 8192, 0x7fffff00);
     e->cap_items = (uint32_t)std::min<int64_t>(nt / 16 * sc + 8192, 0x7fffff00);
     e->cap_surv = (uint32_t)std::min<int64_t>(nt / 24 * sc + 8192, 0x7fffff00);
-    e->cap_witems = (uint32_t)std::min<int64_t>(nt / 8 * sc + 8192, 0x7fffff00);
-    std::vector<void *> t_witems(M);
     std::vector<void *> t_orfs(M), t_starts(M), t_surv(M), t_sorted(M), t_bcount(M), t_cover(M), t_gene_off(M), t_genes(M);
     std::vector<void *> t_ls(M), t_ls_tile(M), t_items(M), t_items_sorted(M), t_hist(M), t_item_off(M), t_unit_off(M), t_sums(M);
     const int64_t ls_tiles = (2 * W + 255) / 256;
@@ -388,8 +384,6 @@ void ensure_batch_buffers(mgc_engine *e) {
         p.orfs.ensure((size_t)e->cap_orf * sizeof(OrfRec));
         p.starts.ensure((size_t)e->cap_starts * sizeof(StartRec));
         p.sums.ensure((size_t)e->cap_starts * 32);
-        p.witems.ensure((size_t)e->cap_witems * sizeof(WordItem));
-        t_witems[i] = p.witems.p;
         p.items.ensure((size_t)e->cap_items * sizeof(ItemRec));
         p.items_sorted.ensure((size_t)e->cap_items * sizeof(ItemRec));
         const size_t nkeys = (size_t)102 * WALK_CLASSES;   // at most 101 distinct section pairs
@@ -457,7 +451,7 @@ void ensure_batch_buffers(mgc_engine *e) {
     auto add_sig = [&](const void *src, size_t bytes) {
         sig.insert(sig.end(), static_cast<const unsigned char *>(src), static_cast<const unsigned char *>(src) + bytes);
     };
-    for (auto *v : {&t_orfs, &t_starts, &t_surv, &t_sorted, &t_bcount, &t_cover, &t_gene_off, &t_genes, &t_witems, &t_ls, &t_ls_tile, &t_items,
+    for (auto *v : {&t_orfs, &t_starts, &t_surv, &t_sorted, &t_bcount, &t_cover, &t_gene_off, &t_genes, &t_ls, &t_ls_tile, &t_items,
                     &t_items_sorted, &t_hist, &t_item_off, &t_unit_off, &t_sums})
         add_sig(v->data(), M * sizeof(void *));
     add_sig(cb.data(), M * sizeof(ChainBufs));
@@ -476,7 +470,6 @@ void ensure_batch_buffers(mgc_engine *e) {
     up(e->t_gene_off, t_gene_off.data(), M * sizeof(void *));
     up(e->t_genes, t_genes.data(), M * sizeof(void *));
     up(e->t_chainbufs, cb.data(), M * sizeof(ChainBufs));
-    up(e->t_witems, t_witems.data(), M * sizeof(void *));
     up(e->t_ls, t_ls.data(), M * sizeof(void *));
     up(e->t_ls_tile, t_ls_tile.data(), M * sizeof(void *));
     up(e->t_items, t_items.data(), M * sizeof(void *));
@@ -652,9 +645,9 @@ mgc_result *run_pipeline(mgc_engine *e, bool *amb_out) {
     CUDA_TRY(cudaPeekAtLastError());   // a failed launch must not go unnoticed until the end
     CUDA_TRY(cudaEventRecord(e->ev[2], st));
     launches += launch_orf_prep(pl, e->gc.as<uint32_t>(), e->cwoff.as<int64_t>(), e->clen.as<int32_t>(), e->d_models.as<DevModel>(), M,
-                                e->t_orfs.as<OrfRec *>(), e->t_witems.as<WordItem *>(), e->t_starts.as<StartRec *>(),
-                                e->t_items.as<ItemRec *>(), e->t_hist.as<uint32_t *>(), e->counters.as<unsigned long long>(),
-                                e->t_chainbufs.as<ChainBufs>(), e->cap_orf, e->cap_starts, e->cap_items, e->cap_witems, e->n_sm, st);
+                                e->t_orfs.as<OrfRec *>(), e->t_starts.as<StartRec *>(), e->t_items.as<ItemRec *>(), e->t_hist.as<uint32_t *>(),
+                                e->counters.as<unsigned long long>(), e->t_chainbufs.as<ChainBufs>(), e->cap_orf, e->cap_starts, e->cap_items,
+                                e->n_sm, st);
     launches += launch_item_sort(e->t_items.as<const ItemRec *>(), e->t_items_sorted.as<ItemRec *>(), e->t_hist.as<uint32_t *>(),
                                  e->t_item_off.as<uint32_t *>(), e->t_unit_off.as<uint32_t *>(), e->d_models.as<DevModel>(), M,
                                  e->unit_totals.as<uint32_t>(), e->counters.as<unsigned long long>(), e->cap_items, e->n_sm, st);
@@ -716,7 +709,7 @@ mgc_result *run_pipeline(mgc_engine *e, bool *amb_out) {
     *amb_out = h_flags[1] != 0;
     for (int i = 0; i < M; i++) {
         if (h_counters[(size_t)i * 8] > e->cap_orf || h_counters[(size_t)i * 8 + 1] > e->cap_starts ||
-            h_counters[(size_t)i * 8 + 2] > e->cap_items || h_counters[(size_t)i * 8 + 3] > e->cap_witems || h_surv[i] > e->cap_surv)
+            h_counters[(size_t)i * 8 + 2] > e->cap_items || h_surv[i] > e->cap_surv)
             throw mgc::ScratchExhausted("device scratch exhausted (ORFs " + std::to_string(h_counters[(size_t)i * 8]) + ", starts " +
                                      std::to_string(h_counters[(size_t)i * 8 + 1]) + ", candidates " + std::to_string(h_surv[i]) + ")");
         e->stats.n_orfs += (int64_t)h_counters[(size_t)i * 8];
@@ -938,7 +931,7 @@ void mgc_engine_destroy(mgc_engine *e) {
     cudaDeviceSynchronize();
     for (auto &p : e->pm) {
         for (DevBuf *b : {&p.lc_full, &p.ln_full, &p.lc_ramp, &p.ln_ramp, &p.sc, &p.quad, &p.rquad, &p.wtab, &p.pair_amb, &p.pair_ub, &p.ls, &p.ls_tile, &p.items, &p.items_sorted, &p.hist,
-                          &p.item_off, &p.unit_off, &p.sums, &p.witems, &p.orfs, &p.starts, &p.surv, &p.sorted, &p.bcount,
+                          &p.item_off, &p.unit_off, &p.sums, &p.orfs, &p.starts, &p.surv, &p.sorted, &p.bcount,
                           &p.cum, &p.prev, &p.gptr, &p.av_right, &p.av_left, &p.av_ls, &p.av_idx, &p.av_cum, &p.av_pmax, &p.av_parg,
                           &p.chain, &p.gene_count, &p.gene_off, &p.contig_total, &p.genes, &p.piece_b0, &p.piece_b1, &p.work,
                           &p.piece_total, &p.slot_gene_off, &p.cover, &p.minleft})
@@ -948,7 +941,7 @@ void mgc_engine_destroy(mgc_engine *e) {
                       &e->tile_sums, &e->flags, &e->t_orfs, &e->t_starts, &e->t_surv, &e->t_sorted, &e->t_bcount, &e->t_cover, &e->t_gene_off,
                       &e->t_genes, &e->t_chainbufs, &e->counters, &e->surv_counters, &e->work_counters, &e->model_cents,
                       &e->gene_totals, &e->t_ls, &e->t_ls_tile, &e->t_items, &e->t_items_sorted, &e->t_hist, &e->t_item_off,
-                      &e->t_unit_off, &e->t_sums, &e->t_witems, &e->ascii_next, &e->slotbase, &e->slot_contig, &e->nm, &e->ncount, &e->codon, &e->cflags, &e->plen, &e->gaps, &e->gap_count, &e->unit_totals, &e->next_unit, &e->win_stride, &e->win_off, &e->win_labels, &e->win_cents})
+                      &e->t_unit_off, &e->t_sums, &e->ascii_next, &e->slotbase, &e->slot_contig, &e->nm, &e->ncount, &e->codon, &e->cflags, &e->plen, &e->gaps, &e->gap_count, &e->unit_totals, &e->next_unit, &e->win_stride, &e->win_off, &e->win_labels, &e->win_cents})
         b->release();
     for (auto &ev : e->ev) cudaEventDestroy(ev);
     if (e->copy_done) cudaEventDestroy(e->copy_done);

@@ -623,115 +623,12 @@ __device__ __forceinline__ uint32_t warp_key_reserve(uint32_t *counters, uint32_
     return base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
 }
 
-// prep 1: thread per ORF — number of start codons per 32-letter word of its admissible range (one WordItem per word,
-// carrying the running prefix) and in total; reserves the ORF's slice of the start array.
-__global__ void __launch_bounds__(128) k_orf_count(Planes pl, const int64_t *__restrict__ cwoff, const int32_t *__restrict__ clen,
-                                                   const DevModel *__restrict__ models, OrfRec *const *orfs_m, WordItem *const *witems_m,
-                                                   unsigned long long *counters_m, const ChainBufs *bufs_m, uint32_t cap_orf,
-                                                   uint32_t cap_starts, uint32_t cap_witems) {
-    const int mi = blockIdx.y;
-    const DevModel &dm = models[mi];
-    unsigned long long *counters = counters_m + (size_t)mi * 8;
-    unsigned long long n_orfs = counters[0];
-    if (n_orfs > cap_orf) n_orfs = cap_orf;
-    OrfRec *orfs = orfs_m[mi];
-    WordItem *witems = witems_m[mi];
-    int32_t *gptr = bufs_m[mi].gptr;
-    const int lane = lane_id();
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t o0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~31LL; o0 < (int64_t)n_orfs; o0 += stride) {
-        const int64_t oi = o0 + lane;
-        const bool has = oi < (int64_t)n_orfs;
-        OrfRec rec;
-        rec.contig = 0; rec.t = 0; rec.s_lo = 1; rec.sf = 0;
-        if (has) {
-            rec = orfs[oi];
-            gptr[oi] = GPTR_UNSET;
-        }
-        const int t = rec.t, strand = rec.sf & 1;
-        const bool open_left = has && (rec.sf & 2u) != 0;
-        const int64_t w0 = has ? cwoff[rec.contig] : 0;
-        const FindCtx cx = make_ctx(pl, strand, w0, has ? clen[rec.contig] : 0, dm.stop_sel, dm.atg_only);
-        const int f = t % 3;
-        const int s_lo = rec.s_lo, s_hi = has ? min(t - 3, t + 3 - dm.min_len) : 0;
-        const uint32_t nwords = has ? (uint32_t)((s_hi >> 5) - (s_lo >> 5) + 1) : 0u;
-        const unsigned long long wbase = warp_reserve(&counters[3], nwords);
-        const bool wok = has && wbase + nwords <= cap_witems;
-        uint32_t n = open_left ? 1u : 0u;
-        if (wok)
-            for (uint32_t j = 0; j < nwords; j++) {
-                const int w = (s_lo >> 5) + (int)j;
-                const int r = ((f - (w * 32) % 3) % 3 + 3) % 3;
-                WordItem wi;
-                wi.orf = (uint32_t)oi; wi.pre = n; wi.j = j;
-                witems[wbase + j] = wi;
-                n += __popc(starts_at(cx, w) & frame_pattern(r) & bit_range(s_lo - 32 * w, s_hi - 32 * w));
-            }
-        if (!wok) n = 0;
-        const unsigned long long base = warp_reserve(&counters[1], n);
-        if (has) {
-            const bool ok = n && base + n <= cap_starts;
-            orfs[oi].base = (uint32_t)base;
-            orfs[oi].n = ok ? n : 0u;
-        }
-    }
-}
-
-// prep 2: thread per (ORF, word) — the start records of that word: position, GC bin, section pair
-__global__ void __launch_bounds__(256) k_orf_starts(Planes pl, const uint32_t *__restrict__ gcpre, const int64_t *__restrict__ cwoff,
-                                                    const int32_t *__restrict__ clen, const DevModel *__restrict__ models,
-                                                    const OrfRec *const *orfs_m, const WordItem *const *witems_m, StartRec *const *starts_m,
-                                                    const unsigned long long *counters_m, uint32_t cap_witems) {
-    const int mi = blockIdx.y;
-    const DevModel &dm = models[mi];
-    unsigned long long nw = counters_m[(size_t)mi * 8 + 3];
-    if (nw > cap_witems) nw = cap_witems;
-    const OrfRec *orfs = orfs_m[mi];
-    const WordItem *witems = witems_m[mi];
-    StartRec *starts = starts_m[mi];
-    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < (int64_t)nw; k += (int64_t)gridDim.x * blockDim.x) {
-        const WordItem wi = witems[k];
-        const OrfRec rec = orfs[wi.orf];
-        if (!rec.n) continue;
-        const int c = rec.contig, t = rec.t, strand = rec.sf & 1;
-        const int L = clen[c];
-        const int64_t w0 = cwoff[c];
-        const FindCtx cx = make_ctx(pl, strand, w0, L, dm.stop_sel, dm.atg_only);
-        const int f = t % 3;
-        const int s_lo = rec.s_lo, s_hi = min(t - 3, t + 3 - dm.min_len);
-        const int w = (s_lo >> 5) + (int)wi.j;
-        uint32_t kk = rec.base + wi.pre;
-        auto put = [&](int s, bool virt) {
-            const int len = t + 3 - s;
-            const int a = strand ? (L - 1 - (t + 2)) : s, b = strand ? (L - 1 - s) : (t + 2);
-            const int gc2 = gc2_count_fwd(pl, gcpre, w0, a, b);
-            const int gc = (100 * gc2 + len) / (2 * len);   // round half up of 100 * (GC + N/2) / len
-            StartRec sr;
-            sr.sraw = (uint32_t)s | (virt ? 0x80000000u : 0u);
-            sr.orf = wi.orf;
-            sr.pg = (uint32_t)dm.pair[gc] | ((uint32_t)gc << 16);
-            sr.link = -1;
-            starts[kk++] = sr;
-        };
-        if (wi.j == 0 && (rec.sf & 2u)) {   // the virtual start at the contig edge comes first
-            kk = rec.base;
-            put(f, true);
-        }
-        const int r = ((f - (w * 32) % 3) % 3 + 3) % 3;
-        uint32_t mm = starts_at(cx, w) & frame_pattern(r) & bit_range(s_lo - 32 * w, s_hi - 32 * w);
-        while (mm) {
-            const int b = __ffs(mm) - 1;
-            mm &= mm - 1;
-            put(w * 32 + b, false);
-        }
-    }
-}
-
-// prep 1+2 fused, load-balanced: a block takes EXPAND_ORFS ORFs, expands them into their 32-letter words (exclusive scan of
+// prep 1+2, load-balanced: a block takes EXPAND_ORFS ORFs, expands them into their 32-letter words (exclusive scan of
 // the word counts, binary search per word), counts the start codons of every word with dense lanes, reserves the tile's
 // slice of the start array with one atomic, and writes the start records (position, GC bin, section pair) word by word.
 // The flat prefix of the per-word counts in expansion order is at the same time the offset of the word's first start.
 constexpr int EXPAND_ORFS = 256;
+constexpr int EXPAND_CACHE = 7168;   // expanded words cached between the passes (a tile has ~3300 on gene-dense input)
 __global__ void __launch_bounds__(EXPAND_ORFS) k_orf_expand(Planes pl, const uint32_t *__restrict__ gcpre, const int64_t *__restrict__ cwoff,
                                                             const int32_t *__restrict__ clen, const DevModel *__restrict__ models,
                                                             OrfRec *const *orfs_m, StartRec *const *starts_m, unsigned long long *counters_m,
@@ -740,6 +637,8 @@ __global__ void __launch_bounds__(EXPAND_ORFS) k_orf_expand(Planes pl, const uin
     __shared__ int o_wfirst[EXPAND_ORFS], o_t[EXPAND_ORFS], o_slo[EXPAND_ORFS], o_shi[EXPAND_ORFS], o_contig[EXPAND_ORFS];
     __shared__ uint32_t o_sf[EXPAND_ORFS], o_ok[EXPAND_ORFS];
     __shared__ unsigned long long s_tile_base;
+    __shared__ uint32_t c_mask[EXPAND_CACHE];        // pass 1 -> pass 2: start mask and ORF of each expanded word
+    __shared__ unsigned char c_orf[EXPAND_CACHE];
     const int mi = blockIdx.y;
     const DevModel &dm = models[mi];
     unsigned long long *counters = counters_m + (size_t)mi * 8;
@@ -784,13 +683,14 @@ __global__ void __launch_bounds__(EXPAND_ORFS) k_orf_expand(Planes pl, const uin
             mask = starts_at(cx, w) & frame_pattern(r) & bit_range(o_slo[i] - 32 * w, o_shi[i] - 32 * w);
             virt_here = j == 0 && (o_sf[i] & 2u) != 0;
         };
-        // ---- pass 1: starts of the tile ----
+        // ---- pass 1: starts of the tile; (ORF, mask) of the first EXPAND_CACHE words are kept for pass 2 ----
         uint32_t mine = 0;
         for (uint32_t k = tid; k < tw; k += EXPAND_ORFS) {
             int i, w;
             uint32_t mask;
             bool vh;
             word_of(k, i, w, mask, vh);
+            if (k < EXPAND_CACHE) { c_mask[k] = mask; c_orf[k] = (unsigned char)i; }
             mine += (uint32_t)__popc(mask) + (vh ? 1u : 0u);
         }
         uint32_t tile_total;
@@ -806,7 +706,14 @@ __global__ void __launch_bounds__(EXPAND_ORFS) k_orf_expand(Planes pl, const uin
             int i = 0, w = 0;
             uint32_t mask = 0;
             bool vh = false;
-            if (k < tw) word_of(k, i, w, mask, vh);
+            if (k < tw) {
+                if (k < EXPAND_CACHE) {
+                    i = c_orf[k];
+                    mask = c_mask[k];
+                    w = o_wfirst[i] + (int)(k - o_woff[i]);
+                    vh = k == o_woff[i] && (o_sf[i] & 2u) != 0;
+                } else word_of(k, i, w, mask, vh);
+            }
             const uint32_t cnt = (uint32_t)__popc(mask) + (vh ? 1u : 0u);
             uint32_t chunk_total;
             const uint32_t pre = carry + block_exclusive_scan(cnt, &chunk_total);
@@ -2090,20 +1997,14 @@ void launch_orf_find(Planes pl, const int64_t *cwoff, const int32_t *clen, const
 }
 
 int launch_orf_prep(Planes pl, const uint32_t *gcpre, const int64_t *cwoff, const int32_t *clen, const DevModel *models, int n_models,
-                    OrfRec *const *orfs_m, WordItem *const *witems_m, StartRec *const *starts_m, ItemRec *const *items_m,
-                    uint32_t *const *hist_m, unsigned long long *counters_m, const ChainBufs *bufs_m, uint32_t cap_orf,
-                    uint32_t cap_starts, uint32_t cap_items, uint32_t cap_witems, int n_sm, cudaStream_t st) {
-    dim3 grid(n_sm * 16, n_models);
-    if (std::getenv("MGCOD_OLD_PREP")) {
-        k_orf_count<<<grid, 128, 0, st>>>(pl, cwoff, clen, models, orfs_m, witems_m, counters_m, bufs_m, cap_orf, cap_starts, cap_witems);
-        dim3 grid2(n_sm * 8, n_models);
-        k_orf_starts<<<grid2, 256, 0, st>>>(pl, gcpre, cwoff, clen, models, orfs_m, witems_m, starts_m, counters_m, cap_witems);
-    } else {
-        k_orf_expand<<<dim3(n_sm * 8, n_models), EXPAND_ORFS, 0, st>>>(pl, gcpre, cwoff, clen, models, orfs_m, starts_m, counters_m, bufs_m,
-                                                                     cap_orf, cap_starts);
-    }
-    k_orf_link<<<grid, 128, 0, st>>>(pl, cwoff, clen, models, orfs_m, starts_m, items_m, hist_m, counters_m, cap_orf, cap_items);
-    return 3;
+                    OrfRec *const *orfs_m, StartRec *const *starts_m, ItemRec *const *items_m, uint32_t *const *hist_m,
+                    unsigned long long *counters_m, const ChainBufs *bufs_m, uint32_t cap_orf, uint32_t cap_starts, uint32_t cap_items,
+                    int n_sm, cudaStream_t st) {
+    k_orf_expand<<<dim3(n_sm * 8, n_models), EXPAND_ORFS, 0, st>>>(pl, gcpre, cwoff, clen, models, orfs_m, starts_m, counters_m, bufs_m,
+                                                                 cap_orf, cap_starts);
+    k_orf_link<<<dim3(n_sm * 16, n_models), 128, 0, st>>>(pl, cwoff, clen, models, orfs_m, starts_m, items_m, hist_m, counters_m, cap_orf,
+                                                        cap_items);
+    return 2;
 }
 
 int launch_item_sort(const ItemRec *const *items_m, ItemRec *const *sorted_m, uint32_t *const *hist_m, uint32_t *const *item_off_m,

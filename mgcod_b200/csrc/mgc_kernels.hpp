@@ -11,7 +11,6 @@ struct DevModel;
 struct OrfRec;
 struct StartRec;
 struct ItemRec;
-struct WordItem;
 struct Cand;
 struct Planes;
 struct ChainBufs;
@@ -33,9 +32,9 @@ void launch_orf_find(Planes pl, const int64_t *cwoff, const int32_t *clen, const
                      int n_models, const uint32_t *const *ls_m, const uint32_t *const *ls_tile_m, OrfRec *const *orfs_m,
                      unsigned long long *counters_m, uint32_t cap_orf, cudaStream_t st);
 int launch_orf_prep(Planes pl, const uint32_t *gcpre, const int64_t *cwoff, const int32_t *clen, const DevModel *models, int n_models,
-                    OrfRec *const *orfs_m, WordItem *const *witems_m, StartRec *const *starts_m, ItemRec *const *items_m,
-                    uint32_t *const *hist_m, unsigned long long *counters_m, const ChainBufs *bufs_m, uint32_t cap_orf,
-                    uint32_t cap_starts, uint32_t cap_items, uint32_t cap_witems, int n_sm, cudaStream_t st);
+                    OrfRec *const *orfs_m, StartRec *const *starts_m, ItemRec *const *items_m, uint32_t *const *hist_m,
+                    unsigned long long *counters_m, const ChainBufs *bufs_m, uint32_t cap_orf, uint32_t cap_starts, uint32_t cap_items,
+                    int n_sm, cudaStream_t st);
 int launch_item_sort(const ItemRec *const *items_m, ItemRec *const *sorted_m, uint32_t *const *hist_m, uint32_t *const *item_off_m,
                      uint32_t *const *unit_off_m, const DevModel *models, int n_models, uint32_t *unit_totals,
                      const unsigned long long *counters_m, uint32_t cap_items, int n_sm, cudaStream_t st);
