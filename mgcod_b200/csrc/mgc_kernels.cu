@@ -758,93 +758,88 @@ __global__ void __launch_bounds__(EXPAND_ORFS) k_orf_expand(Planes pl, const uin
     }
 }
 
-// prep 3: thread per ORF — chains the starts of equal section pair (ascending position) and emits one walk item per chain
-__global__ void __launch_bounds__(128) k_orf_link(Planes pl, const int64_t *__restrict__ cwoff, const int32_t *__restrict__ clen,
-                                                  const DevModel *__restrict__ models, const OrfRec *const *orfs_m,
-                                                  StartRec *const *starts_m, ItemRec *const *items_m, uint32_t *const *hist_m,
-                                                  unsigned long long *counters_m, uint32_t cap_orf, uint32_t cap_items) {
+// prep 3, thread per START: links every start to the nearest earlier start of its ORF with the same section pair (looking
+// back at most LINK_WIN starts), and the start that has no such later neighbour emits the walk item of its chain.  The
+// relation "nearest same-pair neighbour within LINK_WIN" is symmetric, so chains are well defined without communication;
+// a pair that reappears further away simply starts a new chain (one more item, same sums).
+constexpr int LINK_WIN = 24;
+__global__ void __launch_bounds__(256) k_start_link(Planes pl, const int64_t *__restrict__ cwoff, const int32_t *__restrict__ clen,
+                                                    const DevModel *__restrict__ models, const OrfRec *const *orfs_m,
+                                                    StartRec *const *starts_m, ItemRec *const *items_m, uint32_t *const *hist_m,
+                                                    unsigned long long *counters_m, uint32_t cap_starts, uint32_t cap_items) {
     const int mi = blockIdx.y;
     const DevModel &dm = models[mi];
     unsigned long long *counters = counters_m + (size_t)mi * 8;
-    unsigned long long n_orfs = counters[0];
-    if (n_orfs > cap_orf) n_orfs = cap_orf;
+    unsigned long long n_starts = counters[1];
+    if (n_starts > cap_starts) n_starts = cap_starts;
     const OrfRec *orfs = orfs_m[mi];
     StartRec *starts = starts_m[mi];
     ItemRec *items = items_m[mi];
     uint32_t *hist = hist_m[mi];
     const int kc = dm.kc;
     const int lane = lane_id();
+    const bool amb = pl.dflags[1] != 0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t o0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~31LL; o0 < (int64_t)n_orfs; o0 += stride) {
-        const int64_t oi = o0 + lane;
-        OrfRec rec;
-        rec.n = 0; rec.t = 0; rec.sf = 0; rec.base = 0; rec.contig = 0;
-        if (oi < (int64_t)n_orfs) rec = orfs[oi];
-        const int t = rec.t, strand = rec.sf & 1;
-        const bool from_first = (rec.sf & 0x200u) != 0;
-        const bool amb = pl.dflags[1] != 0;
-        const int Lc = amb && oi < (int64_t)n_orfs ? clen[rec.contig] : 0;
-        const int64_t w0c = amb && oi < (int64_t)n_orfs ? cwoff[rec.contig] : 0;
-        constexpr int NSLOT = 6, NPEND = 10;
-        int sl_pair[NSLOT], sl_lo[NSLOT], sl_last[NSLOT];
-#pragma unroll
-        for (int z = 0; z < NSLOT; z++) { sl_pair[z] = -1; sl_lo[z] = 0; sl_last[z] = -1; }
-        int nslot = 0;
-        ItemRec pend[NPEND];
-        int npend = 0;
-        auto flush_slot = [&](int q) {
-            const int ext = t - sl_lo[q];
-            ItemRec it;
-            it.orf = (uint32_t)oi;
-            if (amb) {  // does the walk [lo_pos - kc, t - 1] touch an ambiguous letter?  (bit 31 of orf selects the careful loop)
-                const int a = sl_lo[q] - kc, b = t - 1;
-                const int na = strand ? amb_count_fwd(pl, w0c, Lc - 1 - b, Lc - 1 - a) : amb_count_fwd(pl, w0c, a, b);
-                if (na) it.orf |= 0x80000000u;
-            }
-            it.lo_pos = sl_lo[q];
-            it.key = (uint32_t)(sl_pair[q] * WALK_CLASSES + (WALK_CLASSES - 1 - min(ext >> 5, WALK_CLASSES - 1)));
-            it.last = sl_last[q];
-            if (npend < NPEND) pend[npend++] = it;
-            else {  // very many distinct GC bins among the starts of one ORF: emit directly
-                const unsigned long long ii = atomicAdd(&counters[2], 1ull);
-                if (ii < cap_items) {
-                    items[ii] = it;
-                    atomicAdd(&hist[it.key], 1u);
+    for (int64_t k0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~31LL; k0 < (int64_t)n_starts; k0 += stride) {
+        const int64_t k = k0 + lane;
+        bool emit = false;
+        ItemRec it;
+        it.key = 0;
+        if (k < (int64_t)n_starts) {
+            const StartRec me = starts[k];
+            const OrfRec rec = orfs[me.orf];
+            const int j = (int)(k - rec.base), n = (int)rec.n, t = rec.t;
+            const bool from_first = (rec.sf & 0x200u) != 0;
+            const StartRec *st = starts + rec.base;
+            auto full_of = [&](uint32_t sraw) { return (int)(sraw & 0x7fffffffu) + (((sraw >> 31) && from_first) ? 0 : 3) + kc; };
+            const uint32_t pair = me.pg & 0xffffu;
+            const int my_full = full_of(me.sraw);
+            if (j < n && my_full <= t - 1) {     // starts without a full-order region are not part of any walk
+                auto prev_of = [&](int from) {   // nearest earlier start of the same pair with a full-order region, -1 if none near
+                    for (int d = 1; d <= LINK_WIN && from - d >= 0; d++) {
+                        const StartRec q = st[from - d];
+                        if ((q.pg & 0xffffu) == pair && full_of(q.sraw) <= t - 1) return from - d;
+                    }
+                    return -1;
+                };
+                const int prev = prev_of(j);
+                if (prev >= 0) starts[k].link = prev;
+                bool has_next = false;
+                for (int d = 1; d <= LINK_WIN && j + d < n && !has_next; d++) {
+                    const StartRec q = st[j + d];
+                    has_next = (q.pg & 0xffffu) == pair && full_of(q.sraw) <= t - 1;
+                }
+                if (!has_next) {   // the chain ends here (closest to the stop): find where it begins and emit its item
+                    int lo_pos = my_full, cur = prev;
+                    while (cur >= 0) {
+                        lo_pos = full_of(st[cur].sraw);
+                        cur = prev_of(cur);
+                    }
+                    const int ext = t - lo_pos;
+                    it.orf = me.orf;
+                    if (amb) {  // does the walk [lo_pos - kc, t - 1] touch an ambiguous letter?  (bit 31 of orf selects the careful loop)
+                        const int strand = rec.sf & 1, Lc = clen[rec.contig];
+                        const int64_t w0c = cwoff[rec.contig];
+                        const int a = lo_pos - kc, b = t - 1;
+                        const int na = strand ? amb_count_fwd(pl, w0c, Lc - 1 - b, Lc - 1 - a) : amb_count_fwd(pl, w0c, a, b);
+                        if (na) it.orf |= 0x80000000u;
+                    }
+                    it.lo_pos = lo_pos;
+                    it.key = (uint32_t)((int)pair * WALK_CLASSES + (WALK_CLASSES - 1 - min(ext >> 5, WALK_CLASSES - 1)));
+                    it.last = j;
+                    emit = true;
                 }
             }
-        };
-        StartRec *st = starts + rec.base;
-        for (int j = 0; j < (int)rec.n; j++) {
-            const uint32_t sraw = st[j].sraw;
-            const int pair = (int)(st[j].pg & 0xffffu);
-            const int fullstart = (int)(sraw & 0x7fffffffu) + (((sraw >> 31) && from_first) ? 0 : 3) + kc;
-            if (fullstart > t - 1) continue;  // no full-order region: not part of any walk
-            int q = -1;
-#pragma unroll
-            for (int z = 0; z < NSLOT; z++)
-                if (sl_pair[z] == pair) q = z;
-            if (q < 0) {
-                if (nslot < NSLOT) q = nslot++;
-                else {           // more distinct pairs in flight than slots: retire the oldest slot into its own walk
-                    flush_slot(0);
-#pragma unroll
-                    for (int z = 0; z < NSLOT - 1; z++) { sl_pair[z] = sl_pair[z + 1]; sl_lo[z] = sl_lo[z + 1]; sl_last[z] = sl_last[z + 1]; }
-                    q = NSLOT - 1;
-                }
-                sl_pair[q] = pair;
-                sl_lo[q] = fullstart;
-                sl_last[q] = -1;
-            }
-            if (sl_last[q] >= 0) st[j].link = sl_last[q];
-            sl_last[q] = j;
         }
-        for (int q = 0; q < nslot; q++) flush_slot(q);
-        const unsigned long long ibase = warp_reserve(&counters[2], (uint32_t)npend);
-        const int maxp = __reduce_max_sync(0xffffffffu, npend);
-        for (int q = 0; q < maxp; q++) {  // uniform trip count: the histogram update is aggregated over the warp
-            const bool has = q < npend && ibase + q < cap_items;
-            if (has) items[ibase + q] = pend[q];
-            warp_key_reserve(hist, has ? pend[q].key : 0u, has);
+        const uint32_t em = __ballot_sync(0xffffffffu, emit);
+        if (em) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(&counters[2], (unsigned long long)__popc(em));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const unsigned long long at = base + __popc(em & ((1u << lane) - 1u));
+            const bool ok = emit && at < cap_items;
+            if (ok) items[at] = it;
+            warp_key_reserve(hist, it.key, ok);
         }
     }
 }
@@ -2002,8 +1997,8 @@ int launch_orf_prep(Planes pl, const uint32_t *gcpre, const int64_t *cwoff, cons
                     int n_sm, cudaStream_t st) {
     k_orf_expand<<<dim3(n_sm * 8, n_models), EXPAND_ORFS, 0, st>>>(pl, gcpre, cwoff, clen, models, orfs_m, starts_m, counters_m, bufs_m,
                                                                  cap_orf, cap_starts);
-    k_orf_link<<<dim3(n_sm * 16, n_models), 128, 0, st>>>(pl, cwoff, clen, models, orfs_m, starts_m, items_m, hist_m, counters_m, cap_orf,
-                                                        cap_items);
+    k_start_link<<<dim3(n_sm * 8, n_models), 256, 0, st>>>(pl, cwoff, clen, models, orfs_m, starts_m, items_m, hist_m, counters_m, cap_starts,
+                                                         cap_items);
     return 2;
 }
 
