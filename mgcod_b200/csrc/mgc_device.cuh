@@ -38,7 +38,7 @@ struct DevModel {
 };
 
 // one stop-delimited ORF that may have start candidates of sufficient length
-struct OrfRec {
+struct __align__(8) OrfRec {
     int32_t contig;
     int32_t t;          // strand-local position of the first nt of the (real or virtual) stop codon
     int32_t s_lo;       // first position a start codon may occupy (previous in-frame stop + 3, or the frame's first codon)
@@ -50,7 +50,7 @@ struct OrfRec {
 };
 
 // one start candidate of an ORF
-struct StartRec {
+struct __align__(16) StartRec {
     uint32_t sraw;      // strand-local position of the start codon; bit31: virtual start at the contig edge
     uint32_t orf;       // index of its OrfRec
     uint32_t pg;        // section pair (low 16 bits) | gc << 16
@@ -60,7 +60,7 @@ struct StartRec {
 // one 32-letter word of an ORF's admissible start range
 
 // one walk of an ORF under one section pair: serves every start of that pair
-struct ItemRec {
+struct __align__(16) ItemRec {
     uint32_t orf;
     int32_t lo_pos;     // lowest position of the walk (first full-order position of the farthest start of this pair)
     uint32_t key;       // pair * WALK_CLASSES + length class (descending)
@@ -72,7 +72,7 @@ constexpr int WALK_UNIT = 256;     // threads per CTA of k_walk
 constexpr int WALK_CHUNK = 2048;   // items per work unit (one section pair; warps take 32 at a time)
 
 // a start/stop pair with total > 0, forward coordinates, 0-based inclusive
-struct Cand {
+struct __align__(16) Cand {
     int32_t contig;
     int32_t left, right;
     uint32_t orf;       // id of the ORF record (groups reverse-strand starts sharing a stop)
@@ -111,7 +111,7 @@ struct ChainBufs {
     double *contig_total;           // per contig
 };
 // a gene located in the packed planes: slot, strand region (0 forward, 1 reverse complement), first letter and length there
-struct GeneRef {
+struct __align__(16) GeneRef {
     int32_t slot, strand, start, n;
 };
 constexpr int PIECE_BUCKETS = 64;

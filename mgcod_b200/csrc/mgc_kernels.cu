@@ -909,7 +909,7 @@ __global__ void __launch_bounds__(256) k_item_scatter(const ItemRec *const *item
 // letter before the stop codon down to lo_pos, keeping the (k+1)-letter window as two shift registers, adds one Quad
 // per position, and stores the running sums whenever it passes the first full-order position of a start codon of its
 // pair (the starts of a pair are chained, the next one is prefetched).  No shuffles.
-struct Acc4 {
+struct __align__(16) Acc4 {
     double cB, oB, cA, oA;
 };
 
