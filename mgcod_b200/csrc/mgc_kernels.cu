@@ -1542,7 +1542,7 @@ __global__ void __launch_bounds__(128) k_chain_plan(const ChainBufs *bufs_m, con
     B.work[atomicAdd(&work_counters[2 * mi], 1)] = s;
 }
 
-__global__ void __launch_bounds__(128) k_chain(const ChainBufs *bufs_m, int *work_counters) {
+__global__ void __launch_bounds__(128, 8) k_chain(const ChainBufs *bufs_m, int *work_counters) {
     __shared__ ChainRing rings[4];
     const int mi = blockIdx.y;
     const ChainBufs B = bufs_m[mi];
