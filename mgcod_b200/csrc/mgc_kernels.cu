@@ -1083,7 +1083,7 @@ __global__ void __launch_bounds__(WALK_UNIT, 2) k_walk(Planes pl, const int64_t 
 // ------------------------------------------------------------------------------------------------
 // per-start totals: order ramp, domain choice, duration / start / stop terms, pruning, bucket histogram
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_final(Planes pl, const int64_t *__restrict__ cwoff, const int32_t *__restrict__ clen,
+__global__ void __launch_bounds__(256, 4) k_final(Planes pl, const int64_t *__restrict__ cwoff, const int32_t *__restrict__ clen,
                                                const DevModel *__restrict__ models, const OrfRec *const *orfs_m,
                                                const StartRec *const *starts_m, const Acc4 *const *sums_m,
                                                const unsigned long long *counters_m, Cand *const *surv_m, uint32_t *const *bcount_m,
