@@ -758,9 +758,11 @@ __global__ void __launch_bounds__(EXPAND_ORFS) k_orf_expand(Planes pl, const uin
     }
 }
 
-// prep 3, thread per START: links every start to the nearest earlier start of its ORF with the same section pair (looking
-// back at most LINK_WIN starts), and the start that has no such later neighbour emits the walk item of its chain.  The
-// relation "nearest same-pair neighbour within LINK_WIN" is symmetric, so chains are well defined without communication;
+// prep 3, thread per START: links every start to the nearest earlier start of its ORF with the same section pair, and
+// the start that has no such later neighbour emits the walk item of its chain.  The starts of an ORF are contiguous, so
+// within a warp's 32 consecutive starts the neighbours are found with one __match_any_sync on (ORF, pair) and the head of
+// a chain by hopping over lanes with shuffles; only chains that cross the warp's edge look at memory, at most LINK_WIN
+// starts away.  "Nearest same-pair neighbour" is a symmetric relation, so both ends of a link agree without talking;
 // a pair that reappears further away simply starts a new chain (one more item, same sums).
 constexpr int LINK_WIN = 24;
 __global__ void __launch_bounds__(256) k_start_link(Planes pl, const int64_t *__restrict__ cwoff, const int32_t *__restrict__ clen,
@@ -770,8 +772,8 @@ __global__ void __launch_bounds__(256) k_start_link(Planes pl, const int64_t *__
     const int mi = blockIdx.y;
     const DevModel &dm = models[mi];
     unsigned long long *counters = counters_m + (size_t)mi * 8;
-    unsigned long long n_starts = counters[1];
-    if (n_starts > cap_starts) n_starts = cap_starts;
+    const unsigned long long n_starts = counters[1];
+    if (n_starts > cap_starts) return;   // the start array overflowed and is only partly written: the host grows it and decodes again
     const OrfRec *orfs = orfs_m[mi];
     StartRec *starts = starts_m[mi];
     ItemRec *items = items_m[mi];
@@ -782,54 +784,85 @@ __global__ void __launch_bounds__(256) k_start_link(Planes pl, const int64_t *__
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t k0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~31LL; k0 < (int64_t)n_starts; k0 += stride) {
         const int64_t k = k0 + lane;
-        bool emit = false;
-        ItemRec it;
-        it.key = 0;
+        StartRec me;
+        OrfRec rec;
+        me.sraw = 0; me.orf = 0xffffffffu; me.pg = 0; me.link = -1;
+        rec.base = 0; rec.n = 0; rec.t = 0; rec.sf = 0; rec.contig = 0;
+        bool valid = false;
+        int j = 0, my_full = 0;
         if (k < (int64_t)n_starts) {
-            const StartRec me = starts[k];
-            const OrfRec rec = orfs[me.orf];
-            const int j = (int)(k - rec.base), n = (int)rec.n, t = rec.t;
-            const bool from_first = (rec.sf & 0x200u) != 0;
-            const StartRec *st = starts + rec.base;
-            auto full_of = [&](uint32_t sraw) { return (int)(sraw & 0x7fffffffu) + (((sraw >> 31) && from_first) ? 0 : 3) + kc; };
-            const uint32_t pair = me.pg & 0xffffu;
-            const int my_full = full_of(me.sraw);
-            if (j < n && my_full <= t - 1) {     // starts without a full-order region are not part of any walk
-                auto prev_of = [&](int from) {   // nearest earlier start of the same pair with a full-order region, -1 if none near
-                    for (int d = 1; d <= LINK_WIN && from - d >= 0; d++) {
-                        const StartRec q = st[from - d];
-                        if ((q.pg & 0xffffu) == pair && full_of(q.sraw) <= t - 1) return from - d;
-                    }
-                    return -1;
-                };
-                const int prev = prev_of(j);
-                if (prev >= 0) starts[k].link = prev;
-                bool has_next = false;
-                for (int d = 1; d <= LINK_WIN && j + d < n && !has_next; d++) {
+            me = starts[k];
+            rec = orfs[me.orf];
+            j = (int)(k - rec.base);
+        }
+        const int t = rec.t, n = (int)rec.n;
+        const bool from_first = (rec.sf & 0x200u) != 0;
+        auto full_of = [&](uint32_t sraw) { return (int)(sraw & 0x7fffffffu) + (((sraw >> 31) && from_first) ? 0 : 3) + kc; };
+        const uint32_t pair = me.pg & 0xffffu;
+        if (k < (int64_t)n_starts) {
+            my_full = full_of(me.sraw);
+            valid = j < n && my_full <= t - 1;   // starts without a full-order region are not part of any walk
+        }
+        const StartRec *st = starts + rec.base;
+        auto prev_in_memory = [&](int from) {   // nearest earlier start of the same pair with a full-order region, -1 if none near
+            for (int d = 1; d <= LINK_WIN && from - d >= 0; d++) {
+                const StartRec q = st[from - d];
+                if ((q.pg & 0xffffu) == pair && full_of(q.sraw) <= t - 1) return from - d;
+            }
+            return -1;
+        };
+        // neighbours inside the warp
+        const unsigned long long key = valid ? (((unsigned long long)me.orf << 16) | pair) : (0xffffffff00000000ull | (unsigned)lane);
+        const uint32_t peers = __match_any_sync(0xffffffffu, key);
+        const uint32_t below = peers & ((1u << lane) - 1u), above = peers & ~((2u << lane) - 1u);
+        int prev = -1;              // index inside the ORF
+        int prev_lane = -1;         // its lane if it sits in this warp
+        bool has_next = false;
+        if (valid) {
+            // the same rule everywhere: the nearest same-pair neighbour counts only if it is at most LINK_WIN starts away
+            if (below) {
+                const int pl_ = 31 - __clz(below);
+                if (lane - pl_ <= LINK_WIN) { prev_lane = pl_; prev = j - (lane - pl_); }
+            } else if (j > lane) prev = prev_in_memory(j);         // my ORF began before this warp's first start
+            if (above) has_next = (__ffs(above) - 1) - lane <= LINK_WIN;
+            else if (j + (31 - lane) < n - 1)                      // my ORF continues after this warp's last start
+                for (int d = 32 - lane; d <= LINK_WIN && j + d < n && !has_next; d++) {
                     const StartRec q = st[j + d];
                     has_next = (q.pg & 0xffffu) == pair && full_of(q.sraw) <= t - 1;
                 }
-                if (!has_next) {   // the chain ends here (closest to the stop): find where it begins and emit its item
-                    int lo_pos = my_full, cur = prev;
-                    while (cur >= 0) {
-                        lo_pos = full_of(st[cur].sraw);
-                        cur = prev_of(cur);
-                    }
-                    const int ext = t - lo_pos;
-                    it.orf = me.orf;
-                    if (amb) {  // does the walk [lo_pos - kc, t - 1] touch an ambiguous letter?  (bit 31 of orf selects the careful loop)
-                        const int strand = rec.sf & 1, Lc = clen[rec.contig];
-                        const int64_t w0c = cwoff[rec.contig];
-                        const int a = lo_pos - kc, b = t - 1;
-                        const int na = strand ? amb_count_fwd(pl, w0c, Lc - 1 - b, Lc - 1 - a) : amb_count_fwd(pl, w0c, a, b);
-                        if (na) it.orf |= 0x80000000u;
-                    }
-                    it.lo_pos = lo_pos;
-                    it.key = (uint32_t)((int)pair * WALK_CLASSES + (WALK_CLASSES - 1 - min(ext >> 5, WALK_CLASSES - 1)));
-                    it.last = j;
-                    emit = true;
-                }
+            if (prev >= 0) starts[k].link = prev;
+        }
+        // head of my chain: hop over lanes while the chain stays in the warp, then over memory
+        int lo_pos = my_full, hop = prev_lane, tail_prev = prev;
+        while (__any_sync(0xffffffffu, hop >= 0)) {
+            const int src = hop >= 0 ? hop : lane;
+            const int f_src = __shfl_sync(0xffffffffu, my_full, src);
+            const int p_src = __shfl_sync(0xffffffffu, prev_lane, src);
+            const int pm_src = __shfl_sync(0xffffffffu, prev, src);
+            if (hop >= 0) { lo_pos = f_src; hop = p_src; tail_prev = pm_src; }
+        }
+        bool emit = false;
+        ItemRec it;
+        it.key = 0;
+        if (valid && !has_next) {   // the chain ends here (closest to the stop): finish the way to its head and emit its item
+            int cur = tail_prev;    // first start of the chain that is not in this warp (or -1)
+            while (cur >= 0) {
+                lo_pos = full_of(st[cur].sraw);
+                cur = prev_in_memory(cur);
             }
+            const int ext = t - lo_pos;
+            it.orf = me.orf;
+            if (amb) {  // does the walk [lo_pos - kc, t - 1] touch an ambiguous letter?  (bit 31 of orf selects the careful loop)
+                const int strand = rec.sf & 1, Lc = clen[rec.contig];
+                const int64_t w0c = cwoff[rec.contig];
+                const int a = lo_pos - kc, b = t - 1;
+                const int na = strand ? amb_count_fwd(pl, w0c, Lc - 1 - b, Lc - 1 - a) : amb_count_fwd(pl, w0c, a, b);
+                if (na) it.orf |= 0x80000000u;
+            }
+            it.lo_pos = lo_pos;
+            it.key = (uint32_t)((int)pair * WALK_CLASSES + (WALK_CLASSES - 1 - min(ext >> 5, WALK_CLASSES - 1)));
+            it.last = j;
+            emit = true;
         }
         const uint32_t em = __ballot_sync(0xffffffffu, emit);
         if (em) {
@@ -1092,8 +1125,8 @@ __global__ void __launch_bounds__(256, 4) k_final(Planes pl, const int64_t *__re
     const int mi = blockIdx.y;
     const DevModel &dm = models[mi];
     const int lane = lane_id();
-    unsigned long long n_starts = counters_m[(size_t)mi * 8 + 1];
-    if (n_starts > cap_starts) n_starts = cap_starts;
+    const unsigned long long n_starts = counters_m[(size_t)mi * 8 + 1];
+    if (n_starts > cap_starts) return;   // overflowed, partly written start array: nothing to score, the host grows it and decodes again
     const OrfRec *orfs = orfs_m[mi];
     const StartRec *starts = starts_m[mi];
     const Acc4 *sums = sums_m[mi];
