@@ -91,7 +91,10 @@ int mgc_prefetch_batch(mgc_engine *e, const char *seq, const int64_t *offsets, i
 
 int mgc_engine_stats(const mgc_engine *e, mgc_stats *out);
 
-/* ---- results ---- */
+/* ---- results ----
+ * A result is returned as soon as the decode has finished on the device; its gene tables and totals travel to page-locked host
+ * memory on a copy-out stream while the caller may already start the next decode.  mgc_result_genes / _contig_totals /
+ * mgc_write_gff wait for that copy; gene counts and mgc_result_model_cents are available at once. */
 int64_t mgc_result_num_genes(const mgc_result *r, int model);
 /* genes of one model ordered by (contig, left); pointer valid until mgc_result_free */
 const mgc_gene *mgc_result_genes(const mgc_result *r, int model);

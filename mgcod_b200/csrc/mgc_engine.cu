@@ -29,6 +29,15 @@ struct mgc_model {
 
 // Page-locked host blocks are expensive to create (cudaHostAlloc pins pages), so results borrow them from a
 // pool owned jointly by the engine and its outstanding results.
+// completion of a result's device->host copy (shared by the result, the pool's deferred releases and the engine)
+struct Ready {
+    cudaEvent_t ev = nullptr;
+    Ready() { cudaEventCreateWithFlags(&ev, cudaEventDisableTiming); }
+    ~Ready() { if (ev) cudaEventDestroy(ev); }
+    bool done() const { return cudaEventQuery(ev) == cudaSuccess; }
+    void wait() const { cudaEventSynchronize(ev); }
+};
+
 struct PinnedPool {
     struct Block {
         void *p = nullptr;
@@ -36,10 +45,20 @@ struct PinnedPool {
     };
     std::mutex mu;
     std::vector<Block> free_blocks;
+    std::vector<std::pair<Block, std::shared_ptr<Ready>>> deferred;   // released while their copy was still in flight
+    void sweep_locked() {
+        for (size_t i = 0; i < deferred.size();)
+            if (deferred[i].second->done()) {
+                free_blocks.push_back(deferred[i].first);
+                deferred[i] = deferred.back();
+                deferred.pop_back();
+            } else i++;
+    }
     Block acquire(size_t need) {
         need = std::max<size_t>(need, 4096);
         {
             std::lock_guard<std::mutex> lk(mu);
+            sweep_locked();
             size_t best = free_blocks.size();
             for (size_t i = 0; i < free_blocks.size(); i++)
                 if (free_blocks[i].bytes >= need && (best == free_blocks.size() || free_blocks[i].bytes < free_blocks[best].bytes)) best = i;
@@ -57,12 +76,14 @@ struct PinnedPool {
         }
         return b;
     }
-    void release(Block b) {
+    void release(Block b, const std::shared_ptr<Ready> &ready = nullptr) {
         if (!b.p) return;
         std::lock_guard<std::mutex> lk(mu);
-        free_blocks.push_back(b);
+        if (ready && !ready->done()) deferred.emplace_back(b, ready);
+        else free_blocks.push_back(b);
     }
     ~PinnedPool() {
+        for (auto &d : deferred) { d.second->wait(); cudaFreeHost(d.first.p); }
         for (auto &b : free_blocks) cudaFreeHost(b.p);
     }
 };
@@ -76,13 +97,15 @@ struct mgc_result {
     std::vector<int64_t> cents;
     std::vector<int32_t> min_len;   // $GENE_MIN_LENGTH of each model: records shorter than it get no summary line
     bool host_owned = false;   // blocks came from malloc (mgc_result_create), not from the pinned pool
+    std::shared_ptr<Ready> ready;   // the genes / totals travel on a copy stream while the engine goes on; readers wait here
+    void wait() const { if (ready) ready->wait(); }
     ~mgc_result() {
         if (host_owned) {
             for (auto &b : gene_blk) std::free(b.p);
             for (auto &b : total_blk) std::free(b.p);
         } else if (pool) {
-            for (auto &b : gene_blk) pool->release(b);
-            for (auto &b : total_blk) pool->release(b);
+            for (auto &b : gene_blk) pool->release(b, ready);
+            for (auto &b : total_blk) pool->release(b, ready);
         }
     }
 };
@@ -161,8 +184,10 @@ struct mgc_engine {
     DevBuf ascii, aoff, cwoff, clen, grp2contig, lo, hi, gc, tile_sums, flags;
     // next batch on its way to the device while the current one is decoded (mgc_prefetch_batch)
     DevBuf ascii_next;
-    cudaStream_t copy_stream = nullptr;
-    cudaEvent_t copy_done = nullptr;
+    cudaStream_t copy_stream = nullptr, d2h_stream = nullptr;
+    cudaEvent_t copy_done = nullptr, main_done = nullptr, d2h_begin = nullptr, d2h_end = nullptr;
+    std::shared_ptr<Ready> last_ready;   // copy of the previous result: the next gather must not overwrite its source
+    bool d2h_timed = true;
     struct {
         bool valid = false;
         const char *seq = nullptr;
@@ -688,6 +713,7 @@ mgc_result *run_pipeline(mgc_engine *e, bool *amb_out) {
         launches += launch_exclusive_scan(e->pm[i].gene_count.as<uint32_t>(), e->pm[i].slot_gene_off.as<uint32_t>(),
                                           e->tile_sums.as<uint32_t>(), (int64_t)e->n_slots + 1, e->gene_totals.as<uint32_t>() + i, st);
     }
+    if (e->last_ready) CUDA_TRY(cudaStreamWaitEvent(st, e->last_ready->ev, 0));   // the previous result still reads the gene buffers
     launches += launch_gather(e->t_chainbufs.as<ChainBufs>(), e->t_genes.as<mgc_gene *>(), e->slot_contig.as<int32_t>(), e->n_slots,
                               e->slotbase.as<int32_t>(), n, e->model_cents.as<long long>(), M, e->n_sm, st);
     CUDA_TRY(cudaPeekAtLastError());   // a failed launch must not go unnoticed until the end
@@ -726,15 +752,23 @@ mgc_result *run_pipeline(mgc_engine *e, bool *amb_out) {
     res->cents.assign(h_cents.begin(), h_cents.end());
     res->n_genes.assign(h_gtot.begin(), h_gtot.end());
     for (int i = 0; i < M; i++) res->min_len.push_back(e->models[i].min_len);
+    // genes and totals travel on the copy-out stream; the caller may start the next decode meanwhile (readers of the result wait)
+    CUDA_TRY(cudaEventRecord(e->main_done, st));
+    CUDA_TRY(cudaStreamWaitEvent(e->d2h_stream, e->main_done, 0));
+    CUDA_TRY(cudaEventRecord(e->d2h_begin, e->d2h_stream));
     for (int i = 0; i < M; i++) {
         res->gene_blk.push_back(e->pool->acquire((size_t)h_gtot[i] * sizeof(mgc_gene)));
         res->total_blk.push_back(e->pool->acquire((size_t)n * 8));
         if (h_gtot[i])
-            CUDA_TRY(cudaMemcpyAsync(res->gene_blk[i].p, e->pm[i].genes.p, (size_t)h_gtot[i] * sizeof(mgc_gene), cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaMemcpyAsync(res->total_blk[i].p, e->pm[i].contig_total.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(res->gene_blk[i].p, e->pm[i].genes.p, (size_t)h_gtot[i] * sizeof(mgc_gene), cudaMemcpyDeviceToHost,
+                                     e->d2h_stream));
+        CUDA_TRY(cudaMemcpyAsync(res->total_blk[i].p, e->pm[i].contig_total.p, (size_t)n * 8, cudaMemcpyDeviceToHost, e->d2h_stream));
     }
-    CUDA_TRY(cudaEventRecord(e->ev[7], st));
-    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaEventRecord(e->d2h_end, e->d2h_stream));
+    res->ready = std::make_shared<Ready>();
+    CUDA_TRY(cudaEventRecord(res->ready->ev, e->d2h_stream));
+    e->last_ready = res->ready;
+    e->d2h_timed = false;
     float ms;
     cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]); e->stats.pack = ms;
     cudaEventElapsedTime(&ms, e->ev[1], e->ev[2]); e->stats.orf_find = ms;
@@ -744,8 +778,8 @@ mgc_result *run_pipeline(mgc_engine *e, bool *amb_out) {
     cudaEventElapsedTime(&ms, e->ev[3], e->ev[4]); e->stats.order = ms;
     cudaEventElapsedTime(&ms, e->ev[4], e->ev[5]); e->stats.chain = ms;
     cudaEventElapsedTime(&ms, e->ev[5], e->ev[6]); e->stats.aggregate = ms;
-    cudaEventElapsedTime(&ms, e->ev[6], e->ev[7]); e->stats.d2h = ms;
-    cudaEventElapsedTime(&ms, e->ev[0], e->ev[7]); e->stats.total = ms;
+    cudaEventElapsedTime(&ms, e->ev[0], e->ev[6]); e->stats.total = ms;   // + d2h once it is known (mgc_engine_stats)
+    e->stats.d2h = 0;
     e->stats.kernel_launches = launches;
     e->have_genes = true;
     return res.release();
@@ -754,6 +788,7 @@ mgc_result *run_pipeline(mgc_engine *e, bool *amb_out) {
 // slot-space result -> the caller's contigs: contig index, coordinates, per-contig totals; re-uploads the mapped genes so
 // that the window kernel sees parents
 void remap_to_parents(mgc_engine *e, mgc_result *res) {
+    res->wait();
     const int M = e->n_models;
     const int32_t np = e->n_parents;
     cudaStream_t st = e->stream;
@@ -907,6 +942,10 @@ int mgc_engine_create(int device, const mgc_model *const *models, int n_models, 
         for (auto &ev : e->ev) CUDA_TRY(cudaEventCreate(&ev));
         CUDA_TRY(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
         CUDA_TRY(cudaEventCreateWithFlags(&e->copy_done, cudaEventDisableTiming));
+        CUDA_TRY(cudaStreamCreateWithFlags(&e->d2h_stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&e->main_done, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreate(&e->d2h_begin));
+        CUDA_TRY(cudaEventCreate(&e->d2h_end));
         e->n_models = n_models;
         e->pm.resize(n_models);
         for (int i = 0; i < n_models; i++) {
@@ -944,6 +983,10 @@ void mgc_engine_destroy(mgc_engine *e) {
                       &e->t_unit_off, &e->t_sums, &e->ascii_next, &e->slotbase, &e->slot_contig, &e->nm, &e->ncount, &e->codon, &e->cflags, &e->plen, &e->gaps, &e->gap_count, &e->unit_totals, &e->next_unit, &e->win_stride, &e->win_off, &e->win_labels, &e->win_cents})
         b->release();
     for (auto &ev : e->ev) cudaEventDestroy(ev);
+    if (e->last_ready) e->last_ready->wait();
+    e->last_ready.reset();
+    if (e->d2h_stream) { cudaStreamSynchronize(e->d2h_stream); cudaStreamDestroy(e->d2h_stream); }
+    for (cudaEvent_t ev : {e->main_done, e->d2h_begin, e->d2h_end}) if (ev) cudaEventDestroy(ev);
     if (e->copy_done) cudaEventDestroy(e->copy_done);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -1075,8 +1118,18 @@ int64_t mgc_debug_candidates(mgc_engine *e, int model, mgc_candidate *out, int64
     return rc == MGC_OK ? n : rc;
 }
 
-int mgc_engine_stats(const mgc_engine *e, mgc_stats *out) {
-    if (!e || !out) return mgc::set_error(MGC_E_ARG, "null argument");
+int mgc_engine_stats(const mgc_engine *ce, mgc_stats *out) {
+    if (!ce || !out) return mgc::set_error(MGC_E_ARG, "null argument");
+    mgc_engine *e = const_cast<mgc_engine *>(ce);
+    if (!e->d2h_timed && e->last_ready) {   // the copy-out of the last result is timed once it has finished
+        e->last_ready->wait();
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, e->d2h_begin, e->d2h_end) == cudaSuccess) {
+            e->stats.d2h = ms;
+            e->stats.total += ms;
+        }
+        e->d2h_timed = true;
+    }
     *out = e->stats;
     return MGC_OK;
 }
@@ -1088,11 +1141,13 @@ int64_t mgc_result_num_genes(const mgc_result *r, int model) {
 
 const mgc_gene *mgc_result_genes(const mgc_result *r, int model) {
     if (!r || model < 0 || model >= r->n_models) return nullptr;
+    r->wait();
     return static_cast<const mgc_gene *>(r->gene_blk[model].p);
 }
 
 const double *mgc_result_contig_totals(const mgc_result *r, int model) {
     if (!r || model < 0 || model >= r->n_models) return nullptr;
+    r->wait();
     return static_cast<const double *>(r->total_blk[model].p);
 }
 
