@@ -286,8 +286,8 @@ void upload_models(mgc_engine *e) {
                 }
         up(p.quad, q.data(), q.size() * sizeof(Quad));
         d.quad = p.quad.as<Quad>();
-        // image of the walk kernel's shared-memory table (see k_walk): per pair, coding {B, A} entries with rows of four
-        // entries stored twice (bank halves for even / odd lanes), then non-coding {B, A} entries stored eight times
+        // image of the walk kernel's shared-memory table (see k_walk): per pair, coding {B, A} entries, each stored twice
+        // side by side (even / odd 16-byte slots for even / odd lanes), then non-coding {B, A} entries stored eight times
         {
             const size_t n16 = 3 * nfull * 2 + nnon * 8;
             std::vector<double> img(pairs.size() * n16 * 2, 0.0);
@@ -296,7 +296,7 @@ void upload_models(mgc_engine *e) {
                 for (size_t ent = 0; ent < 3 * nfull; ent++) {
                     const Quad &e4 = q[pi * 3 * nfull + ent];
                     for (int rep = 0; rep < 2; rep++) {
-                        const size_t o16 = ((ent & ~(size_t)3) << 1) | (ent & 3) | ((size_t)rep << 2);
+                        const size_t o16 = (ent << 1) | (size_t)rep;
                         base[o16 * 2] = e4.cB;
                         base[o16 * 2 + 1] = e4.cA;
                     }

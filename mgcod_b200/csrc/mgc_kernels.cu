@@ -996,12 +996,13 @@ __global__ void __launch_bounds__(WALK_UNIT, 2) k_walk(Planes pl, const int64_t 
             loaded_pair = pair;
             __syncthreads();
         }
-        // coding part: {ln P_cod^B, ln P_cod^A} per (phase, k-mer), two replicas interleaved so that even and odd lanes
-        // use disjoint halves of the banks; non-coding part: {ln P_non^B, ln P_non^A} per (kn+1)-mer, eight replicas so
+        // coding part: {ln P_cod^B, ln P_cod^A} per (phase, k-mer), the two replicas of an entry side by side so that even and
+        // odd lanes use disjoint bank groups (even / odd 16-byte slots); non-coding part: {ln P_non^B, ln P_non^A} per (kn+1)-mer, eight replicas so
         // that the eight lanes of a quarter-warp never collide
         const double2 *tc = SMEM_TABLE ? tbl : gq;
         const double2 *tn = tc + (size_t)3 * nfull * 2;
-        const uint32_t rep2 = (uint32_t)(lane & 1) << 2, rep8 = (uint32_t)(lane & 7);
+        const double2 *tc0 = tc + (lane & 1), *tn8 = tn + (lane & 7);   // my replicas
+        const int pstep = 2 * nfull;                                     // slots per codon position
         // constant terms of windows with an ambiguous letter, per domain of this pair
         const double2 amb_c = make_double2(dm.pair_amb[pair * 4 + 0], dm.pair_amb[pair * 4 + 1]);
         const double2 amb_n = make_double2(dm.pair_amb[pair * 4 + 2], dm.pair_amb[pair * 4 + 3]);
@@ -1035,7 +1036,8 @@ __global__ void __launch_bounds__(WALK_UNIT, 2) k_walk(Planes pl, const int64_t 
                 if (cur.link >= 0) nxt = st[cur.link];
                 Acc4 acc = {0, 0, 0, 0};
                 int i = t - 1;
-                int ph = (((-1 - kc) % 3) + 3) % 3;   // codon position of the window's first letter at i = t-1
+                const int ph = (((-1 - kc) % 3) + 3) % 3;   // codon position of the window's first letter at i = t-1
+                const double2 *tcp = tc0 + ph * pstep;       // the coding table of that codon position (my replica)
                 // the (kc+1)-letter window ending at i starts at bit `sh` of plane word `w`; the word pair (w, w+1) sits in registers
                 int w = (i - kc) >> 5, sh = (i - kc) & 31;
                 // plane words come in 16-byte groups (4 words = 128 letters) held in registers: one sector request per
@@ -1054,12 +1056,11 @@ __global__ void __launch_bounds__(WALK_UNIT, 2) k_walk(Planes pl, const int64_t 
                         auto lookup = [&](double2 &c2, double2 &n2) {
                             const uint32_t lb = __funnelshift_r(l0, l1, sh) & wmask;
                             const uint32_t hb = __funnelshift_r(h0, h1, sh) & wmask;
-                            const uint32_t e = (uint32_t)(ph * nfull) + ((hb << (kc + 1)) | lb);
                             const uint32_t idn = ((hb >> nsh) << (kn + 1)) | (lb >> nsh);
-                            c2 = tc[((e & ~3u) << 1) | (e & 3u) | rep2];
-                            n2 = tn[(idn << 3) | rep8];
+                            c2 = tcp[((hb << (kc + 1)) | lb) << 1];
+                            n2 = tn8[idn << 3];
                             sh--;
-                            ph = ph == 0 ? 2 : ph - 1;
+                            tcp = tcp == tc0 ? tc0 + 2 * pstep : tcp - pstep;   // codon position of the window's first letter steps 0 -> 2 -> 1 -> 0
                         };
                         double2 c2, n2;
                         lookup(c2, n2);
@@ -1078,14 +1079,13 @@ __global__ void __launch_bounds__(WALK_UNIT, 2) k_walk(Planes pl, const int64_t 
                         for (int r = 0; r < run; r++) {
                             const uint32_t lb = __funnelshift_r(l0, l1, sh) & wmask;
                             const uint32_t hb = __funnelshift_r(h0, h1, sh) & wmask;
-                            const uint32_t e = (uint32_t)(ph * nfull) + ((hb << (kc + 1)) | lb);
                             const uint32_t idn = ((hb >> nsh) << (kn + 1)) | (lb >> nsh);
-                            double2 c2 = tc[((e & ~3u) << 1) | (e & 3u) | rep2];
-                            double2 n2 = tn[(idn << 3) | rep8];
+                            double2 c2 = tcp[((hb << (kc + 1)) | lb) << 1];
+                            double2 n2 = tn8[idn << 3];
                             if (__funnelshift_r(a0, a1, sh) & wmask) { c2 = amb_c; n2 = amb_n; }
                             acc.cB += c2.x; acc.cA += c2.y; acc.oB += n2.x; acc.oA += n2.y;
                             sh--;
-                            ph = ph == 0 ? 2 : ph - 1;
+                            tcp = tcp == tc0 ? tc0 + 2 * pstep : tcp - pstep;
                         }
                     }
                     i -= run;
