@@ -665,15 +665,20 @@ __global__ void __launch_bounds__(EXPAND_ORFS) k_orf_expand(Planes pl, const uin
         const uint32_t wo = block_exclusive_scan(nwords, &tw);
         o_woff[tid] = wo;
         if (tid == 0) o_woff[EXPAND_ORFS] = tw;
+        // each ORF stamps its number on its words (cheaper than a binary search per word; words beyond the cache search)
+        for (uint32_t q = 0; q < nwords && wo + q < EXPAND_CACHE; q++) c_orf[wo + q] = (unsigned char)tid;
         __syncthreads();
         // the word an expansion index stands for, and its start-codon mask (plus the virtual start in an ORF's first word)
         auto word_of = [&](uint32_t k, int &i, int &w, uint32_t &mask, bool &virt_here) {
-            int lo = 0, hi = EXPAND_ORFS;   // last ORF with o_woff <= k
-            while (lo + 1 < hi) {
-                const int mid = (lo + hi) >> 1;
-                if (o_woff[mid] <= k) lo = mid; else hi = mid;
+            if (k < EXPAND_CACHE) i = c_orf[k];
+            else {
+                int lo = 0, hi = EXPAND_ORFS;   // last ORF with o_woff <= k
+                while (lo + 1 < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (o_woff[mid] <= k) lo = mid; else hi = mid;
+                }
+                i = lo;
             }
-            i = lo;
             const int j = (int)(k - o_woff[i]);
             w = o_wfirst[i] + j;
             const int c = o_contig[i], strand = (int)(o_sf[i] & 1u);
@@ -690,7 +695,7 @@ __global__ void __launch_bounds__(EXPAND_ORFS) k_orf_expand(Planes pl, const uin
             uint32_t mask;
             bool vh;
             word_of(k, i, w, mask, vh);
-            if (k < EXPAND_CACHE) { c_mask[k] = mask; c_orf[k] = (unsigned char)i; }
+            if (k < EXPAND_CACHE) c_mask[k] = mask;
             mine += (uint32_t)__popc(mask) + (vh ? 1u : 0u);
         }
         uint32_t tile_total;
