@@ -3,17 +3,20 @@
 // Pipeline for one batch of contigs and M parameter files (all launches on one stream, no host
 // synchronisation until the final counters are read):
 //
-//   k_groups      word-group -> contig map                                     (once per upload)
-//   k_pack        ASCII -> 2-bit planes for both strands, GC count per word    (reads 1 B/nt twice)
-//   scan          exclusive prefix of GC counts
-//   k_orf_find    per model: stop-delimited ORFs and their start codons        (bit-parallel on planes)
-//   k_orf_score   per model: one warp per ORF; 3-periodic Markov log-likelihoods of every start as
-//                 warp suffix scans, GC-bin section choice, domain choice, duration/start/stop terms,
-//                 pruning (total > 0), bucket histogram of right ends
-//   scan + k_scatter   survivors into position buckets (128 nt)  -> right-end order per contig
-//   k_chain       per (contig, model): one warp; max-plus chain with overlap penalties, traceback
-//   scan + k_gather    genes ordered by (contig, left), per-model sums in 1/100 units
-//   k_windows     per (contig, window): sums, spanning-gene fallback, argmax label
+//   k_groups         word-group -> contig map                                  (once per upload)
+//   k_pack           ASCII -> 2-bit planes + ambiguity plane for both strands, GC / N counts per word; scan x2
+//   k_codon_planes   start / ATG / TAA / TAG / TGA bit per letter, shared by the models
+//   k_laststop_*     per model: last in-frame stop before every word (max-scan)
+//   k_orf_find       per model: stop-delimited ORFs long enough to hold a gene and with a start codon
+//   k_orf_expand     per model: start records (position, GC bin, section pair) of every ORF, load-balanced per block
+//   k_start_link     chains the starts of an ORF that share a section pair; one walk item per chain
+//   k_item_plan / k_item_scatter   counting sort of the items by (section pair, length class)
+//   k_walk           thread per item: 3-periodic Markov log-likelihood sums from the stop down, the pair's tables in shared memory
+//   k_final          per start: order ramp, duration / start / stop terms, domain choice, pruning (total > 0), bucket histogram
+//   scan + k_scatter survivors into position buckets (128 nt) -> right-end order per contig
+//   k_chain_minleft / k_chain_plan / k_chain   cut points, then one warp per piece: max-plus chain with overlap penalties, traceback
+//   scan + k_gather + k_contig_finish   genes ordered by (contig, left), per-model sums in 1/100 units, per-contig totals
+//   on request: k_windows, k_merge_labels (window labels), k_recoded_stops (in-frame stops per gene), k_find_gaps
 //
 // Arithmetic follows SURVEY.md §A.4-A.6 as pinned by oracle/ (never linked here).
 #include <cstdint>
@@ -942,7 +945,7 @@ __global__ void __launch_bounds__(256) k_item_scatter(const ItemRec *const *item
 // the walk: thread per item, the section pair's table in shared memory
 // ------------------------------------------------------------------------------------------------
 // A work unit is a chunk of up to WALK_CHUNK items of one (model, section pair), ordered long to short.  Persistent
-// CTAs take units in order, so a CTA reloads its 96 KB table only when the pair changes; inside a unit the CTA's warps
+// CTAs take units in order, so a CTA reloads its ~100 KB table only when the pair changes; inside a unit the CTA's warps
 // take 32 items at a time from a shared counter and never wait for each other.  Each thread walks its item from the
 // letter before the stop codon down to lo_pos, keeping the (k+1)-letter window as two shift registers, adds one Quad
 // per position, and stores the running sums whenever it passes the first full-order position of a start codon of its
