@@ -128,8 +128,10 @@ class Data:
             self.read_dna_sequence()
         recs = self._file_order                       # gmhmmp2 writes records in file order
         self.engine = shared_engine(self.model_dir, self.device)
-        self.result = self.engine.decode_buffer(self._fasta.buffer, self._fasta.offsets)
-        self.engine._resident_owner = self
+        # inputs larger than one device batch are streamed in pieces and merged on the host (GFF files only: the window
+        # labels of --isoforms and the recoded-stop scan need the whole input resident)
+        self.result = self.engine.decode_large(self._fasta.buffer, self._fasta.offsets)
+        self.engine._resident_owner = self if int(self._fasta.offsets[-1]) <= self.engine.MAX_BATCH_BP else None
         self._decoded_order = recs
         ids = [r.id for r in recs]
         lens = [len(r) for r in recs]

@@ -175,6 +175,37 @@ class Engine:
                 self.upload(*nxt)
             cur = nxt
 
+    MAX_BATCH_BP = 1_800_000_000     # one device batch (mgc_decode_batch accepts ~2e9 letters; 70 GB of scratch per Gbp x 4 models)
+
+    def decode_large(self, buf: np.ndarray, offsets: np.ndarray, max_bp: Optional[int] = None) -> Result:
+        """Decodes inputs of any size: contigs are cut into batches of at most ``max_bp`` letters (whole contigs), streamed
+        through the device with ``decode_stream``, and the gene tables are merged on the host.  The returned result is
+        host-only (its genes are not resident on the device: window labels / recoded stops need a single batch)."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = len(offsets) - 1
+        max_bp = int(max_bp or self.MAX_BATCH_BP)
+        cuts = [0]
+        while cuts[-1] < n:
+            a = cuts[-1]
+            b = int(np.searchsorted(offsets, offsets[a] + max_bp, side="right")) - 1
+            b = min(max(b, a + 1), n)
+            if offsets[b] - offsets[a] > 0x7ffffff0 * 0.93:
+                raise MgcodError(_lib.MGC_E_ARG, f"contig {a} alone exceeds the size of one device batch")
+            cuts.append(b)
+        if len(cuts) == 2:
+            return self.decode_buffer(buf, offsets)
+        genes = [[] for _ in range(self.n_models)]
+        totals = [[] for _ in range(self.n_models)]
+        batches = [(buf, offsets[cuts[i]:cuts[i + 1] + 1]) for i in range(len(cuts) - 1)]
+        for i, res in enumerate(self.decode_stream(batches)):
+            for m in range(self.n_models):
+                g = res.genes(m)
+                g["contig"] += cuts[i]
+                genes[m].append(g)
+                totals[m].append(res.contig_totals(m))
+        min_len = [int(_lib.lib().mgc_result_min_gene_length(res._h, m)) for m in range(self.n_models)]
+        return Result.from_genes([np.concatenate(g) for g in genes], [np.concatenate(t) for t in totals], min_len)
+
     def decode_resident(self) -> Result:
         r = C.c_void_p()
         _check(_lib.lib().mgc_decode_resident(self._h, C.byref(r)))

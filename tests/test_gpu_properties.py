@@ -192,3 +192,24 @@ def test_low_complexity_repeats_grow_the_scratch_buffers(engine):
     # the engine keeps working at normal sizes afterwards
     res2 = engine.decode([flank])
     assert np.array_equal(res2.genes(0)[["left", "right"]], res.genes(0)[res.genes(0)["contig"] == 2][["left", "right"]])
+
+
+def test_decode_large_streams_batches_and_merges(engine, tmp_path):
+    """inputs beyond one device batch: whole contigs per batch, merged gene tables equal the single-batch decode, and the
+    merged (host-only) result writes the same GFF"""
+    from mgcod_b200.engine import synth_metagenome
+    buf, offs, truth = synth_metagenome(41, 400000, threads=2)
+    one = engine.decode_buffer(buf, offs)
+    want = [one.genes(m) for m in range(4)]
+    want_tot = [one.contig_totals(m) for m in range(4)]
+    ids = [f"c{i}" for i in range(len(truth))]
+    lens = np.diff(offs)
+    one.write(2, ids, lens, "s.fa", "m.mod", 15, str(tmp_path / "one.gff"), "gff")
+    many = engine.decode_large(buf, offs, max_bp=90000)
+    for m in range(4):
+        assert np.array_equal(many.genes(m), want[m])
+        np.testing.assert_array_equal(many.contig_totals(m), want_tot[m])
+    assert (many.model_cents() == one.model_cents()).all()
+    many.write(2, ids, lens, "s.fa", "m.mod", 15, str(tmp_path / "many.gff"), "gff")
+    strip = lambda t: "\n".join(l for l in t.split("\n") if not l.startswith("# output date"))
+    assert strip(open(tmp_path / "one.gff").read()) == strip(open(tmp_path / "many.gff").read())
