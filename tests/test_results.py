@@ -106,3 +106,27 @@ def test_recoded_stops_kernel_matches_host_restatement(tmp_path):
                 got = pos[offs[3 * k + t]:offs[3 * k + t + 1]].tolist()
                 assert got == want and counts[k, t] == len(want), (mi, k, stop)
     eng.close()
+
+
+@pytest.mark.gpu
+def test_multi_genome_driver(tmp_path):
+    """bin/multiprocess_mgcod.py mirror: a list of genomes through one engine; outputs equal the single-genome CLI's goldens,
+    a missing file is skipped"""
+    from mgcod_b200 import multi
+    tmp = str(tmp_path)
+    paths = fx.trained_models(tmp)
+    mdir = os.path.dirname(paths[11])
+    files = []
+    for case, text in _inputs().items():
+        fa = os.path.join(tmp, f"{case}.fasta")
+        open(fa, "w").write(text)
+        files.append(fa)
+    lst = os.path.join(tmp, "genomes.txt")
+    open(lst, "w").write("\n".join(files + [os.path.join(tmp, "missing.fasta")]) + "\n")
+    out, pred = os.path.join(tmp, "out") + "/", os.path.join(tmp, "pred") + "/"
+    rc = multi.main(["--genomes", lst, "-o", out, "-p", pred, "-NT", "--model_dir", mdir, "--threads", "4",
+                     "--logfile", os.path.join(tmp, "log", "m.log")])
+    assert rc == 0
+    for case in _inputs():
+        assert open(f"{out}{case}.tab").read() == fx.xz_text(f"results_{case}.tab.xz")
+        assert open(f"{out}{case}_stats.tab").read() == fx.xz_text(f"results_{case}_stats.tab.xz")
