@@ -141,9 +141,19 @@ class Engine:
     def n_models(self) -> int:
         return len(self.models)
 
+    @staticmethod
+    def _checked(buf: np.ndarray, offsets: np.ndarray) -> np.ndarray:
+        """the letter buffer must be one C-contiguous run of bytes that covers the offsets (its address crosses the C-ABI)"""
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        if not isinstance(buf, np.ndarray) or buf.dtype.itemsize != 1 or not buf.flags.c_contiguous:
+            raise TypeError("sequence buffer must be a C-contiguous numpy array of bytes (uint8 / int8 / S1)")
+        if len(offsets) < 2 or offsets[0] < 0 or (np.diff(offsets) < 0).any() or offsets[-1] > buf.size:
+            raise ValueError("offsets must ascend, start at >= 0 and end inside the buffer")
+        return offsets
+
     def upload(self, buf: np.ndarray, offsets: np.ndarray) -> None:
         """Host→device copy of a batch (``buf`` may be a pinned torch tensor's numpy view)."""
-        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        offsets = self._checked(buf, offsets)
         self._keep = (buf, offsets)
         self.n_contigs = len(offsets) - 1
         _check(_lib.lib().mgc_upload_batch(self._h, C.c_void_p(buf.ctypes.data), offsets.ctypes.data_as(C.POINTER(C.c_int64)),
@@ -152,7 +162,7 @@ class Engine:
     def prefetch(self, buf: np.ndarray, offsets: np.ndarray) -> None:
         """Starts copying the NEXT batch to the device on a second stream (returns at once); the following ``upload`` /
         ``decode_buffer`` of the same arrays adopts it.  ``buf`` should be page-locked and must not change until then."""
-        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        offsets = self._checked(buf, offsets)
         self._keep_next = (buf, offsets)
         _check(_lib.lib().mgc_prefetch_batch(self._h, C.c_void_p(buf.ctypes.data), offsets.ctypes.data_as(C.POINTER(C.c_int64)),
                                              len(offsets) - 1))
@@ -216,7 +226,7 @@ class Engine:
         return self.decode_buffer(buf, offs)
 
     def decode_buffer(self, buf: np.ndarray, offsets: np.ndarray) -> Result:
-        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        offsets = self._checked(buf, offsets)
         self.n_contigs = len(offsets) - 1
         r = C.c_void_p()
         _check(_lib.lib().mgc_decode_batch(self._h, C.c_void_p(buf.ctypes.data), offsets.ctypes.data_as(C.POINTER(C.c_int64)),

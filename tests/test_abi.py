@@ -132,3 +132,20 @@ def test_gff_writer_formats_scores_like_printf(tmp_path):
     res.write(0, ["c"], [int(g["right"][-1]) + 10], "s", "m", 11, out, "gff")
     got = [l.split("\t")[5] for l in open(out) if "\tCDS\t" in l]
     assert got == ["%.2f" % v for v in vals]
+
+
+def test_buffer_arguments_are_validated_before_crossing_the_abi():
+    """wrong dtype, strided views and offsets that leave the buffer are refused in Python (no engine needed)"""
+    chk = Engine._checked
+    buf = np.frombuffer(b"ACGTACGTAC", dtype=np.uint8)
+    assert chk(buf, [0, 4, 10]).tolist() == [0, 4, 10]
+    with pytest.raises(TypeError):
+        chk(buf.astype(np.int32), [0, 10])
+    with pytest.raises(TypeError):
+        chk(buf[::2], [0, 5])
+    with pytest.raises(ValueError):
+        chk(buf, [0, 11])
+    with pytest.raises(ValueError):
+        chk(buf, [0, 6, 4])
+    with pytest.raises(ValueError):
+        chk(buf, [3])
