@@ -199,7 +199,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--total-bp", type=int, default=int(os.environ.get("MGCOD_BENCH_BP", 1_000_000_000)),
                     help="bp per GPU per step (default: 1 Gbp, BASELINE.json config 5)")
-    ap.add_argument("--cpu-sample-bp", type=int, default=32_000_000)
+    ap.add_argument("--cpu-sample-bp", type=int, default=128_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
