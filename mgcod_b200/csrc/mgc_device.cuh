@@ -114,6 +114,7 @@ struct ChainBufs {
 struct __align__(16) GeneRef {
     int32_t slot, strand, start, n;
 };
+constexpr int SURV_CHUNK = 256;     // survivor slots a warp of k_final reserves at a time
 constexpr int PIECE_BUCKETS = 64;
 constexpr int PACK_SLACK = 64;      // bytes of slack before and after the letters in the device ASCII buffer (k_pack)   // cuts are at least this many 128-nt buckets apart
 

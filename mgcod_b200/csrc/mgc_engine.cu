@@ -694,8 +694,9 @@ mgc_result *run_pipeline(mgc_engine *e, bool *amb_out) {
     CUDA_TRY(cudaPeekAtLastError());   // a failed launch must not go unnoticed until the end
     CUDA_TRY(cudaEventRecord(e->ev[3], st));
     for (int i = 0; i < M; i++) {
+        // the grand total = number of candidates (survivor slots may include unfilled ones): low half of counter 4
         launches += launch_exclusive_scan(e->pm[i].bcount.as<uint32_t>(), e->pm[i].bcount.as<uint32_t>(), e->tile_sums.as<uint32_t>(),
-                                          nb, nullptr, st);
+                                          nb, reinterpret_cast<uint32_t *>(e->counters.as<unsigned long long>() + (size_t)i * 8 + 4), st);
         launches += launch_exclusive_scan(e->pm[i].cover.as<uint32_t>(), e->pm[i].cover.as<uint32_t>(), e->tile_sums.as<uint32_t>(),
                                           nb + 2, nullptr, st);
     }
@@ -741,7 +742,7 @@ mgc_result *run_pipeline(mgc_engine *e, bool *amb_out) {
         e->stats.n_orfs += (int64_t)h_counters[(size_t)i * 8];
         e->stats.n_starts += (int64_t)h_counters[(size_t)i * 8 + 1];
         e->stats.n_walks += (int64_t)h_counters[(size_t)i * 8 + 2];
-        e->stats.n_candidates += (int64_t)h_surv[i];
+        e->stats.n_candidates += (int64_t)(h_counters[(size_t)i * 8 + 4] & 0xffffffffull);
         e->stats.n_genes += h_gtot[i];
     }
     // genes into pooled page-locked blocks
@@ -1081,7 +1082,8 @@ int64_t mgc_debug_candidates(mgc_engine *e, int model, mgc_candidate *out, int64
     int rc = guarded([&] {
         CUDA_TRY(cudaSetDevice(e->device));
         unsigned long long ns = 0;
-        CUDA_TRY(cudaMemcpy(&ns, e->surv_counters.as<unsigned long long>() + model, 8, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(&ns, e->counters.as<unsigned long long>() + (size_t)model * 8 + 4, 8, cudaMemcpyDeviceToHost));
+        ns &= 0xffffffffull;   // candidates in `sorted` (the bucket scan's total)
         std::vector<Cand> c(ns);
         std::vector<double> cum(ns);
         if (ns) {

@@ -1143,6 +1143,12 @@ __global__ void __launch_bounds__(256, 4) k_final(Planes pl, const int64_t *__re
     uint32_t *cover = cover_m[mi];
     const int kc = dm.kc, nramp = dm.nramp;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    // Survivor slots are reserved per warp in chunks of SURV_CHUNK (one atomic per ~30 rounds instead of one per round: the
+    // single hot counter otherwise decides the speed of this latency-bound kernel); slots a warp does not fill
+    // carry contig = -1 and are skipped by k_scatter.  Small inputs reserve exactly (the waste would not fit their buffers).
+    const int chunk = n_starts >= (1ull << 22) ? SURV_CHUNK : 0;
+    unsigned long long chunk_base = 0;
+    int chunk_left = 0;
     // whole warps iterate together (ballots below); the loop bound is rounded up to a multiple of 32
     for (int64_t k0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~31LL; k0 < (int64_t)n_starts; k0 += stride) {
         const int64_t k = k0 + lane;
@@ -1255,9 +1261,22 @@ __global__ void __launch_bounds__(256, 4) k_final(Planes pl, const int64_t *__re
             if (whole && last && !(vm & same & km)) cd.flags |= 8;
         }
         if (km) {
+            const int cnt = __popc(km);
             unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(&surv_counters[mi], (unsigned long long)__popc(km));
-            base = __shfl_sync(0xffffffffu, base, 0);
+            if (chunk) {
+                if (cnt > chunk_left) {   // retire what is left of the old chunk, take a new one
+                    if (lane < chunk_left && chunk_base + lane < cap_surv) surv[chunk_base + lane].contig = -1;
+                    if (lane == 0) chunk_base = atomicAdd(&surv_counters[mi], (unsigned long long)chunk);
+                    chunk_base = __shfl_sync(0xffffffffu, chunk_base, 0);
+                    chunk_left = chunk;
+                }
+                base = chunk_base;
+                chunk_base += cnt;
+                chunk_left -= cnt;
+            } else {
+                if (lane == 0) base = atomicAdd(&surv_counters[mi], (unsigned long long)cnt);
+                base = __shfl_sync(0xffffffffu, base, 0);
+            }
             if (keep) {
                 const unsigned long long kk = base + __popc(km & ((1u << lane) - 1u));
                 if (kk < cap_surv) {
@@ -1271,6 +1290,8 @@ __global__ void __launch_bounds__(256, 4) k_final(Planes pl, const int64_t *__re
             }
         }
     }
+    for (int i = lane; i < chunk_left; i += 32)   // unused tail of the warp's last chunk
+        if (chunk_base + i < cap_surv) surv[chunk_base + i].contig = -1;
 }
 
 // survivors -> position buckets; boff holds exclusive offsets and is advanced to the bucket ends
@@ -1285,6 +1306,7 @@ __global__ void __launch_bounds__(256) k_scatter(const Cand *const *surv_m, Cand
     uint32_t *boff = boff_m[mi];
     for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < (int64_t)n; k += (int64_t)gridDim.x * blockDim.x) {
         Cand cd = surv[k];
+        if (cd.contig < 0) continue;   // slot reserved but not filled (k_final)
         uint32_t pos = atomicAdd(&boff[(cwoff[cd.contig] * 32 + cd.right) >> 7], 1u);
         sorted[pos] = cd;
     }
