@@ -741,7 +741,7 @@ mgc_result *run_pipeline(mgc_engine *e, bool *amb_out) {
                                      std::to_string(h_counters[(size_t)i * 8 + 1]) + ", candidates " + std::to_string(h_surv[i]) + ")");
         e->stats.n_orfs += (int64_t)h_counters[(size_t)i * 8];
         e->stats.n_starts += (int64_t)h_counters[(size_t)i * 8 + 1];
-        e->stats.n_walks += (int64_t)h_counters[(size_t)i * 8 + 2];
+        e->stats.n_walks += (int64_t)h_counters[(size_t)i * 8 + 5];
         e->stats.n_candidates += (int64_t)(h_counters[(size_t)i * 8 + 4] & 0xffffffffull);
         e->stats.n_genes += h_gtot[i];
     }

@@ -790,6 +790,10 @@ __global__ void __launch_bounds__(256) k_start_link(Planes pl, const int64_t *__
     const int lane = lane_id();
     const bool amb = pl.dflags[1] != 0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    // item slots are reserved per warp in chunks (one hot counter, see k_final); unfilled slots get key 0xffffffff
+    const int chunk = n_starts >= (1ull << 22) ? SURV_CHUNK : 0;
+    unsigned long long chunk_base = 0;
+    int chunk_left = 0;
     for (int64_t k0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~31LL; k0 < (int64_t)n_starts; k0 += stride) {
         const int64_t k = k0 + lane;
         StartRec me;
@@ -874,21 +878,36 @@ __global__ void __launch_bounds__(256) k_start_link(Planes pl, const int64_t *__
         }
         const uint32_t em = __ballot_sync(0xffffffffu, emit);
         if (em) {
+            const int cnt = __popc(em);
             unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(&counters[2], (unsigned long long)__popc(em));
-            base = __shfl_sync(0xffffffffu, base, 0);
+            if (chunk) {
+                if (cnt > chunk_left) {   // retire what is left of the old chunk, take a new one
+                    if (lane < chunk_left && chunk_base + lane < cap_items) items[chunk_base + lane].key = 0xffffffffu;
+                    if (lane == 0) chunk_base = atomicAdd(&counters[2], (unsigned long long)chunk);
+                    chunk_base = __shfl_sync(0xffffffffu, chunk_base, 0);
+                    chunk_left = chunk;
+                }
+                base = chunk_base;
+                chunk_base += cnt;
+                chunk_left -= cnt;
+            } else {
+                if (lane == 0) base = atomicAdd(&counters[2], (unsigned long long)cnt);
+                base = __shfl_sync(0xffffffffu, base, 0);
+            }
             const unsigned long long at = base + __popc(em & ((1u << lane) - 1u));
             const bool ok = emit && at < cap_items;
             if (ok) items[at] = it;
             warp_key_reserve(hist, it.key, ok);
         }
     }
+    for (int i = lane; i < chunk_left; i += 32)   // unused tail of the warp's last chunk
+        if (chunk_base + i < cap_items) items[chunk_base + i].key = 0xffffffffu;
 }
 
 // one block per model: item offsets per key (exclusive scan of the histogram, which is turned into the scatter
 // cursor); work units = chunks of WALK_CHUNK items of one section pair, with their prefix over pairs
 __global__ void __launch_bounds__(1024) k_item_plan(uint32_t *const *hist_m, uint32_t *const *item_off_m, uint32_t *const *unit_off_m,
-                                                    const DevModel *__restrict__ models, uint32_t *unit_totals) {
+                                                    const DevModel *__restrict__ models, uint32_t *unit_totals, unsigned long long *counters_m) {
     __shared__ uint32_t carry_i;
     const int mi = blockIdx.x;
     const int npair = models[mi].npair, nkeys = npair * WALK_CLASSES;
@@ -910,6 +929,7 @@ __global__ void __launch_bounds__(1024) k_item_plan(uint32_t *const *hist_m, uin
     }
     if (threadIdx.x == 0) {
         ioff[nkeys] = carry_i;
+        counters_m[(size_t)mi * 8 + 5] = carry_i;   // walk items (the slot counter 2 includes unfilled slots)
         uint32_t acc = 0;
         for (int p = 0; p < npair; p++) {
             uoff[p] = acc;
@@ -936,8 +956,9 @@ __global__ void __launch_bounds__(256) k_item_scatter(const ItemRec *const *item
         ItemRec it;
         it.key = 0;
         if (has) it = items[k];
-        const uint32_t at = warp_key_reserve(cursor, it.key, has);
-        if (has) sorted[at] = it;
+        const bool real = has && it.key != 0xffffffffu;   // slots reserved but not filled by k_start_link are skipped
+        const uint32_t at = warp_key_reserve(cursor, it.key, real);
+        if (real) sorted[at] = it;
     }
 }
 
@@ -2068,7 +2089,7 @@ int launch_orf_prep(Planes pl, const uint32_t *gcpre, const int64_t *cwoff, cons
 int launch_item_sort(const ItemRec *const *items_m, ItemRec *const *sorted_m, uint32_t *const *hist_m, uint32_t *const *item_off_m,
                      uint32_t *const *unit_off_m, const DevModel *models, int n_models, uint32_t *unit_totals,
                      const unsigned long long *counters_m, uint32_t cap_items, int n_sm, cudaStream_t st) {
-    k_item_plan<<<n_models, 1024, 0, st>>>(hist_m, item_off_m, unit_off_m, models, unit_totals);
+    k_item_plan<<<n_models, 1024, 0, st>>>(hist_m, item_off_m, unit_off_m, models, unit_totals, const_cast<unsigned long long *>(counters_m));
     dim3 grid(n_sm * 4, n_models);
     k_item_scatter<<<grid, 256, 0, st>>>(items_m, sorted_m, hist_m, counters_m, cap_items);
     return 2;
