@@ -1,0 +1,372 @@
+"""Isoform comparison of the two gene sets of a contig with a genetic-code switch.
+
+Mirror of ``Pipeline.compare_sets_of_predicted_genes`` and its helpers (bin/pipeline.py:559-951; ``get_child_1`` /
+``format_child_2`` / ``format_parent`` :494-557; ``insert_unseen_genes`` / ``update_gene_ids`` :1170-1238).  Same
+results — the two tables ``coords`` and ``coords_w_isoforms`` and ``gene_labels_to_gcode`` — but not the same
+machinery: the reference evaluates five boolean masks over the whole second gene set for every gene of the first
+(O(genes²) DataFrame work, minutes for a large genome); here each set is indexed once (sorted starts, ends by value)
+and every case is a binary search plus a filter over a handful of rows, and rows are plain dicts until the end.
+
+The cases, in the order the reference tests them for a gene (s, e, strand) of set 1 (bin/pipeline.py:614-905):
+
+  A  set 2 has exactly one gene with the same s, e, strand ............ identical, label 3
+  B  exactly one with the same e and strand ............................ isoforms (parent = union), label 3
+  C  exactly one with the same s and strand, ends within ``tolerance`` .. isoforms, label 3
+  D  exactly one set-2 gene strictly over-spanning it .................. the higher score wins (sum over the set-1
+                                                                          genes inside), isoforms if both ends are
+                                                                          closer than ``tolerance``
+  E  set-2 genes strictly inside it .................................... likewise the other way round
+  F  otherwise ......................................................... label 1
+
+Quirks of the reference that change its output are kept and marked ``# ref:`` (strand-blind masks on set 1, the
+"first row's attributes for all rows" rewrite, ``previous_end`` only updated in some branches, gene ids renumbered by
+string replacement).  Pinned against the reference's own outputs: tests/golden/iso_* (make_golden_isoforms.py).
+"""
+from __future__ import annotations
+
+import logging
+
+import numpy as np
+import pandas as pd
+
+from . import labels as L
+
+
+def _rest(attributes: str) -> str:
+    return ";".join(attributes.split(";")[1:])
+
+
+def gc_percent(seq: str) -> float:
+    """Biopython's ``SeqUtils.GC``: G, C and S in either case over the length."""
+    if not seq:
+        return 0.0
+    return sum(seq.count(x) for x in "GCgcSs") * 100.0 / len(seq)
+
+
+class _GeneSet:
+    """One model's genes on one contig, in file order, indexed for the six lookups."""
+
+    def __init__(self, frame: pd.DataFrame):
+        self.rows = frame.to_dict("records")
+        self.start = frame.start.values.astype(np.int64)
+        self.end = frame.end.values.astype(np.int64)
+        self.strand = frame.strand.values.astype(object)
+        self.logodd = frame.logodd.values.astype(np.float64)
+        self.order = np.argsort(self.start, kind="stable")
+        self.sorted_start = self.start[self.order]
+        self.max_len = int((self.end - self.start).max()) if len(self.rows) else 0
+        self.by_end: dict[int, list[int]] = {}
+        for i, e in enumerate(self.end.tolist()):
+            self.by_end.setdefault(e, []).append(i)
+        self.seen = np.zeros(len(self.rows), dtype=bool)
+
+    def __len__(self):
+        return len(self.rows)
+
+    def _window(self, lo: int, hi: int) -> np.ndarray:
+        """rows with lo <= start < hi, in file order"""
+        a = np.searchsorted(self.sorted_start, lo, "left")
+        b = np.searchsorted(self.sorted_start, hi, "left")
+        return np.sort(self.order[a:b])
+
+    def identical(self, s, e, st):
+        i = self._window(s, s + 1)
+        return i[(self.end[i] == e) & (self.strand[i] == st)]
+
+    def same_end(self, e, st):
+        i = np.asarray(self.by_end.get(int(e), []), dtype=np.int64)
+        return i[self.strand[i] == st]
+
+    def same_start(self, s, st):
+        i = self._window(s, s + 1)
+        return i[self.strand[i] == st]
+
+    def overspanning(self, s, e, st):
+        i = self._window(s - self.max_len - 1, s)          # a gene reaching beyond e >= s starts no earlier than that
+        return i[(self.end[i] > e) & (self.strand[i] == st)]
+
+    def inside(self, s, e, st=None):
+        """start >= s and end < e (and the strand, if given)"""
+        i = self._window(s, e)
+        m = self.end[i] < e
+        if st is not None:
+            m &= self.strand[i] == st
+        return i[m]
+
+    def equal(self, s, e):
+        i = self._window(s, s + 1)
+        return i[self.end[i] == e]                          # ref: no strand test on set 1
+
+    def copies(self, idx) -> list[dict]:
+        return [dict(self.rows[int(i)]) for i in idx]
+
+
+def update_gene_ids(rows: list[dict]) -> list[dict]:
+    """bin/pipeline.py:1211-1238: every gene id of ``rows`` (already copies) + 1, children follow their parent."""
+    reference = rows[0]["attributes"].split(";")[0].split(" ")[1]
+    current = int(reference) + 1
+
+    def bump(r):
+        r["attributes"] = r["attributes"].replace(f"gene_id {reference}", f"gene_id {current}").replace(
+            f"Parent={reference}", f"Parent={current}")
+
+    bump(rows[0])
+    for r in rows[1:]:
+        head = r["attributes"].split(";")[0]
+        if not head.startswith(f"gene_id {reference}"):     # ref: a prefix test on the text
+            current += 1
+            reference = head.split(" ")[1]
+        bump(r)
+    return rows
+
+
+def insert_unseen_genes(rows: list[dict], unseen: list[dict]) -> list[dict]:
+    """bin/pipeline.py:1170-1209: set-2 genes that matched nothing go behind the last row starting at or before them
+    (behind that row's children), take the id of the row they displace, and every later id moves up by one."""
+    for g in unseen:
+        gene = dict(g)
+        ind = -1
+        for k in range(len(rows) - 1, -1, -1):
+            if rows[k]["start"] <= gene["start"]:
+                ind = k + 1
+                break
+        if ind < 0:
+            gene["attributes"] = "gene_id 0;" + _rest(gene["attributes"])
+            rows = [gene] + update_gene_ids([dict(r) for r in rows])
+            continue
+        while ind <= len(rows) - 1 and "Parent" in rows[ind]["attributes"]:
+            ind += 1
+        if ind >= len(rows):
+            last = int(rows[-1]["attributes"].split(";")[0].split(" ")[1].split(".")[0])
+            gene["attributes"] = f"gene_id {last + 1};" + _rest(gene["attributes"])
+            rows = rows + [gene]
+        else:
+            here = int(rows[ind]["attributes"].split(";")[0].split(" ")[1].split(".")[0])
+            gene["attributes"] = f"gene_id {here};" + _rest(gene["attributes"])
+            rows = rows[:ind] + [gene] + update_gene_ids([dict(r) for r in rows[ind:]])
+    return rows
+
+
+def compare_contig(S1: _GeneSet, S2: _GeneSet, code_1, code_2, tolerance: int, seq: str):
+    """One contig: returns (current_gene_set rows with gene_label/source set, rows with isoforms)."""
+    g3 = f"{code_1}_{code_2}"
+    source = {1: f"GeneMark.hmm2_{code_1}", 2: f"GeneMark.hmm2_{code_2}", 3: f"GeneMark.hmm2_{g3}"}
+    both = "_".join(sorted(map(str, [code_1, code_2])))
+    cur: list[dict] = []
+    iso: list[dict] = []
+    gene_labels: list[int] = []
+    sources: list[str] = []
+
+    def child_1(s, e, gid, attributes):
+        rows = S1.copies(S1.equal(s, e))
+        rows[0]["attributes"] = f"gene_id {gid}.{code_1}; Parent={gid};" + _rest(attributes)
+        rows[0]["gene_label"] = 1
+        return rows
+
+    def child_2(idx, gid):
+        rows = S2.copies(idx)
+        rows[0]["attributes"] = f"gene_id {gid}.{code_2}; Parent={gid};" + _rest(rows[0]["attributes"])
+        rows[0]["gene_label"] = 2
+        return rows
+
+    def format_parent(rows, gid, attributes, length=False):
+        p = rows[0]
+        p["source"] = p["source"].split("_")[0] + "_" + both
+        if not length:
+            p["attributes"] = f"gene_id {gid};" + _rest(attributes)
+        else:
+            n = p["end"] - p["start"] + 1
+            p["length"] = n
+            gc = int(round(gc_percent(seq[p["start"] - 1:p["end"]]), 0))
+            p["attributes"] = f"gene_id {gid}; gene_type bacteria; gc {gc}; length {n};"
+        p["gene_label"] = 3
+        return rows
+
+    def retagged(rows, gid, label, all_rows=False):
+        """plain (non-isoform) rows for the isoform table: id rewritten, label set"""
+        if rows:
+            head = f"gene_id {gid};" + _rest(rows[0]["attributes"])
+            for r in rows:                                   # ref: every row gets the first row's attributes
+                r["attributes"] = head
+                r["gene_label"] = label
+        return rows
+
+    previous_end = 0
+    gene_id = 1
+    for i in range(len(S1)):
+        s, e, st = int(S1.start[i]), int(S1.end[i]), S1.strand[i]
+        logodd, attributes = float(S1.logodd[i]), S1.rows[i]["attributes"]
+        if e <= previous_end:
+            continue
+        own = S1.equal(s, e)
+        hit = S2.identical(s, e, st)
+        same_e = S2.same_end(e, st) if hit.shape[0] != 1 else hit
+        same_s = S2.same_start(s, st)
+        if hit.shape[0] == 1:                                                        # ---- A
+            gene_labels.append(3)
+            sources.append(source[3])
+            S2.seen[hit] = True
+            logodd_2 = float(S2.logodd[hit[0]])
+            cur.extend(S1.copies(own) if logodd >= logodd_2 else S2.copies(hit))
+            c1, c2 = child_1(s, e, gene_id, attributes), child_2(hit, gene_id)
+            parent = format_parent(S1.copies(own), gene_id, attributes)
+            parent[0]["logodd"] = max(c1[0]["logodd"], c2[0]["logodd"])
+            iso.extend(parent)
+        elif same_e.shape[0] == 1:                                                   # ---- B
+            gene_labels.append(3)
+            sources.append(source[3])
+            S2.seen[same_e] = True
+            logodd_2 = float(S2.logodd[same_e[0]])
+            cur.extend(S1.copies(own) if logodd >= logodd_2 else S2.copies(same_e))
+            c1, c2 = child_1(s, e, gene_id, attributes), child_2(same_e, gene_id)
+            parent = S1.copies(own)
+            parent[0]["start"] = min(c1[0]["start"], c2[0]["start"])
+            parent = format_parent(parent, gene_id, attributes, length=True)
+            parent[0]["logodd"] = "."
+            iso.extend(parent + c1 + c2)
+        elif same_s.shape[0] == 1 and abs(int(S2.end[same_s[0]]) - e) <= tolerance:   # ---- C
+            gene_labels.append(3)
+            sources.append(source[3])
+            S2.seen[same_s] = True
+            logodd_2 = float(S2.logodd[same_s[0]])
+            if logodd >= logodd_2:
+                cur.extend(S1.copies(own))
+            else:
+                cur.extend(S2.copies(same_s))
+                previous_end = int(S2.end[same_s[0]])
+            c1, c2 = child_1(s, e, gene_id, attributes), child_2(same_s, gene_id)
+            parent = S1.copies(own)
+            parent[0]["end"] = max(c1[0]["end"], c2[0]["end"])
+            parent = format_parent(parent, gene_id, attributes, length=True)
+            parent[0]["logodd"] = "."
+            iso.extend(parent + c1 + c2)
+        elif (over := S2.overspanning(s, e, st)).shape[0] == 1:                     # ---- D
+            o = int(over[0])
+            o_start, o_end, o_logodd = int(S2.start[o]), int(S2.end[o]), float(S2.logodd[o])
+            S2.seen[over] = True
+            within = S1.inside(o_start, o_end)                                       # ref: either strand
+            logodd_1 = float(np.sum(S1.logodd[within]))
+            isoforms = s - o_start < tolerance and o_end - e < tolerance
+            if isoforms:
+                parent = S2.copies(over)
+                parent = format_parent(parent, gene_id, parent[0]["attributes"])
+                parent[0]["logodd"] = "."
+                iso.extend(parent + child_1(s, e, gene_id, attributes) + child_2(over, gene_id))
+            if o_logodd > logodd_1:
+                gene_labels.append(2)
+                sources.append(source[2])
+                previous_end = o_end
+                cur.extend(S2.copies(over))
+                if not isoforms:
+                    iso.extend(retagged(S2.copies(over), gene_id, 2))
+            elif o_logodd < logodd_1:
+                gene_labels.extend([1] * within.shape[0])
+                sources.extend([source[1]] * within.shape[0])
+                previous_end = int(S1.end[within].max()) if within.shape[0] else float("nan")
+                cur.extend(S1.copies(within))
+                if not isoforms:
+                    iso.extend(retagged(S1.copies(within), gene_id, 1))
+            else:
+                gene_labels.append(3)
+                sources.append(source[3])
+                cur.extend(S2.copies(over))
+                if not isoforms:
+                    iso.extend(retagged(S2.copies(over), gene_id, 3))
+        elif (inner := S2.inside(s, e, st)).shape[0] >= 1:                           # ---- E
+            logodd_2 = float(np.sum(S2.logodd[inner]))
+            S2.seen[inner] = True
+            isoforms = (inner.shape[0] == 1 and int(S2.start[inner[0]]) - s < tolerance
+                        and e - int(S2.end[inner[0]]) < tolerance)
+            if isoforms:
+                parent = S1.copies(own)
+                parent[0]["source"] = parent[0]["source"].split("_")[0] + "_" + both
+                parent[0]["logodd"] = "."                    # ref: the parent keeps the id the model gave the gene
+                iso.extend(parent + child_1(s, e, gene_id, attributes) + child_2(inner, gene_id))
+            if logodd > logodd_2:
+                gene_labels.append(1)
+                sources.append(source[1])
+                cur.extend(S1.copies(own))
+                if not isoforms:
+                    iso.extend(retagged(S1.copies(own), gene_id, 1))
+            elif logodd < logodd_2:
+                gene_labels.extend([2] * inner.shape[0])
+                sources.extend([source[2]] * inner.shape[0])
+                cur.extend(S2.copies(inner))
+                if not isoforms:
+                    iso.extend(retagged(S2.copies(inner), gene_id, 2))
+            else:
+                gene_labels.append(3)
+                sources.append(source[3])
+                cur.extend(S1.copies(own))
+                if not isoforms:
+                    iso.extend(retagged(S1.copies(own), gene_id, 1))
+        else:                                                                        # ---- F
+            gene_labels.append(1)
+            sources.append(source[1])
+            cur.extend(S1.copies(own))
+            iso.extend(retagged(S1.copies(own), gene_id, 1))
+        gene_id += 1
+
+    if len(gene_labels) != len(cur):
+        # the reference assigns the label list to the rows of the contig and fails the same way
+        raise ValueError(f"Must have equal len keys and value when setting with an iterable ({len(cur)} rows, "
+                         f"{len(gene_labels)} labels)")
+    for r, lab, src in zip(cur, gene_labels, sources):
+        r["gene_label"] = lab
+        r["source"] = src
+    unseen = [dict(S2.rows[int(i)], gene_label=2) for i in np.flatnonzero(~S2.seen)]
+    if unseen:
+        cur.extend(dict(r) for r in unseen)
+        iso = insert_unseen_genes(iso, unseen)
+    return cur, iso
+
+
+def compare_sets_of_predicted_genes(P):
+    """``P`` is a :class:`mgcod_b200.pipeline.Pipeline` after label smoothing.  Returns what the reference returns:
+    (coords, gene_labels_to_gcode, coords_w_isoforms)."""
+    logging.info(f"Comparing sets of predicted genes in {P.species}")
+    if P.verbose:
+        print(f"Comparing sets of predicted genes in {P.species}")
+    columns = list(P.label_to_gene_coords[0].columns.values)
+    by_contig = {lab: dict(tuple(df.groupby("contig", sort=False))) for lab, df in P.label_to_gene_coords.items()}
+    gene_labels_to_gcode = {}
+    compared: list[pd.DataFrame] = []
+    with_isoforms: list[dict] = []
+    for n, rec in enumerate(P.sequence):
+        labs = np.unique(P.updated_genome_labels[n])
+        if labs.shape[0] == 1:
+            # ref: every contig's genes of that model, not only this contig's; and nothing for the isoform table
+            coords = P.label_to_gene_coords[int(labs[0])].copy()
+            coords["updated_gene_label"] = 1
+            compared.append(coords)
+            gene_labels_to_gcode[rec.id] = {1: P.label_to_gcode[int(labs[0])]}
+            continue
+        label_1, label_2 = int(labs[0]), int(labs[1])
+        code_1, code_2 = P.label_to_gcode[label_1], P.label_to_gcode[label_2]
+        msg = f"Contig {rec.id} in {P.species} carries genetic code {code_1} and {code_2}"
+        logging.info(msg)
+        if P.verbose:
+            print(msg)
+        gene_labels_to_gcode[rec.id] = {1: str(code_1), 2: str(code_2), 3: f"{code_1}_{code_2}"}
+        empty = P.label_to_gene_coords[label_1].iloc[:0]
+        S1 = _GeneSet(by_contig[label_1].get(rec.id, empty))
+        S2 = _GeneSet(by_contig[label_2].get(rec.id, empty))
+        cur, iso = compare_contig(S1, S2, code_1, code_2, P.tolerance, rec.seq)
+        # ref: DataFrame.sort_values('start') on an object column = numpy's quicksort over Python ints; rows with equal
+        # starts (an isoform pair's two genes) come out in that sort's order, and the smoothing below sees them so
+        starts = np.empty(len(cur), dtype=object)
+        starts[:] = [r["start"] for r in cur]
+        cur = [cur[int(k)] for k in np.argsort(starts, kind="quicksort")]
+        updated = L.find_best_sequence_of_labels(np.array([r["gene_label"] for r in cur], dtype=np.int64), None,
+                                                 P.consecutive_gene_labels, allow_multiple_labels=True)
+        frame = pd.DataFrame(cur, columns=columns + ["gene_label"])
+        frame["updated_gene_label"] = updated
+        compared.append(frame)
+        with_isoforms.extend(iso)
+        msg = f"Identified {sum(1 for r in iso if r['logodd'] == '.')} possible isoforms in {rec.id} in {P.species}"
+        logging.info(msg)
+        if P.verbose:
+            print(msg)
+    coords = pd.concat(compared, sort=True) if compared else pd.DataFrame(columns=columns)
+    coords_w_isoforms = pd.DataFrame(with_isoforms, columns=columns + ["gene_label"])
+    return coords, gene_labels_to_gcode, coords_w_isoforms

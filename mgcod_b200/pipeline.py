@@ -11,9 +11,8 @@ Same constructor arguments and result attributes (``genome_label``, ``logodd_sco
   restatement lives in :mod:`mgcod_b200.labels`
 * switch coordinates (segment_genome_based_on_window_labels, :387-492) ... host, :mod:`mgcod_b200.labels`
 
-Out of scope this round: ``compare_sets_of_predicted_genes`` — the pairwise
-isoform comparison that rewrites GFF attributes; ``coords_w_isoforms`` is therefore only set when a single
-genetic code is predicted.
+* isoform comparison of the two gene sets of a contig with a switch (compare_sets_of_predicted_genes, :559-951)
+  ... host, :mod:`mgcod_b200.isoforms` (indexed lookups instead of the reference's per-gene DataFrame masks)
 """
 from __future__ import annotations
 
@@ -22,6 +21,7 @@ import warnings
 
 import numpy as np
 
+from . import isoforms as iso_compare
 from . import labels as L
 from .data import Data
 from .engine import MGCOD_CODES
@@ -93,6 +93,7 @@ class Pipeline:
             self.coords_w_isoforms = self.label_to_gene_coords[self.gcode_to_label[code]]
             self.predicted_switch_regions = {seq.id: None for seq in self.sequence}
             return
+        self.coords, self.gene_label_to_gcode, self.coords_w_isoforms = self.compare_sets_of_predicted_genes()
         self.confident_1, self.confident_2, self.segment_labels = self.segment_genome_based_on_window_labels()
         self.predicted_switch_regions = {}
         for k, seq in enumerate(self.sequence):
@@ -168,5 +169,9 @@ class Pipeline:
                 if self.verbose:
                     print(f"Contig {seq.id} in {self.species} has genetic code {code} from {a} to {b}")
         return conf_1, conf_2, seg_labels
+
+    # ---- bin/pipeline.py:559-951 -------------------------------------------------------------------------
+    def compare_sets_of_predicted_genes(self):
+        return iso_compare.compare_sets_of_predicted_genes(self)
 
     find_best_sequence_of_labels = staticmethod(L.find_best_sequence_of_labels)

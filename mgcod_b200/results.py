@@ -13,9 +13,9 @@ order (bin/results.py:362-372) but indexed with the row number of ``coords_w_iso
 (bin/results.py:58-72, 175); for a multi-FASTA whose records are not sorted the counts land on other genes.  The
 mirror reproduces that, so its files are byte-identical to the reference's (tests/golden/results_*).
 
-Supported: every run that ends with ONE genetic code (default mode, or ``--isoforms`` with uniform labels).
-Runs with a switch need ``compare_sets_of_predicted_genes`` (not built yet) and raise
-``NotImplementedError``.
+Runs with a genetic-code switch (``--isoforms``) take the other branches of the same reference methods: parents of
+isoform pairs (``logodd == '.'``) carry no recodings, the ``.tab`` file gets one column per segment, and the GFF
+summary lines average each isoform pair (bin/results.py:61-75, 101-157, 213-251).  Golden files: tests/golden/iso_*.
 """
 from __future__ import annotations
 
@@ -57,9 +57,8 @@ class Results:
         self.delete = delete
         self.amino_acids = amino_acids
         self.nucleotides = nucleotides
-        if self.results.coords_w_isoforms is None or not isinstance(self.results.genome_label, (int, np.integer)):
-            raise NotImplementedError("results of a run with a genetic-code switch need the isoform comparison "
-                                      "(bin/pipeline.py:559-951), which this build does not have yet")
+        if self.results.coords_w_isoforms is None:
+            raise RuntimeError("Results needs a Pipeline that has been run")
         self.stop_recodings = self.extract_sequences()
         logging.info(f"Writing results for {self.species}")
         if self.verbose:
@@ -69,9 +68,13 @@ class Results:
         coords = self.results.coords_w_isoforms
         attributes = coords.attributes.values.copy()
         coords["gene_id"] = [float(a.split(";")[0].split(" ")[1]) for a in attributes]
+        logodd = coords.logodd.values
         for i in range(len(attributes)):
             if not attributes[i].endswith(";"):
                 attributes[i] += ";"
+            if isinstance(logodd[i], str) and logodd[i] == ".":      # parent of an isoform pair: no sequence of its own
+                self.stop_recodings.insert(i, {"TAA": [], "TGA": [], "TAG": []})
+                continue
             r = self.stop_recodings[i]
             attributes[i] = (attributes[i] + " number of recodings: "
                              + f"total {len(r['TAA']) + len(r['TGA']) + len(r['TAG'])}, TAA {len(r['TAA'])}, "
@@ -183,13 +186,58 @@ class Results:
                 aa[k] = aa[k].upper()
         return rid, desc, "".join(aa)
 
-    # ---- bin/results.py:86-157 (single genetic code branch) ---------------------------------------------------
+    # ---- bin/results.py:86-157 --------------------------------------------------------------------------------
     def save_results(self):
-        first = self.results.sequence[0].id
-        with open(self.path_to_output, "w") as fh:
-            fh.write("\t\tSequence\n")
-            fh.write(f"{first}\tMajor genetic code\t{float(self.results.genome_label)}\n")
-            fh.write(f"{first}\tTotal gene count\t{float(self.results.coords_w_isoforms.shape[0])}\n")
+        P = self.results
+        if isinstance(P.genome_label, (int, np.integer)):
+            first = P.sequence[0].id
+            with open(self.path_to_output, "w") as fh:
+                fh.write("\t\tSequence\n")
+                fh.write(f"{first}\tMajor genetic code\t{float(P.genome_label)}\n")
+                fh.write(f"{first}\tTotal gene count\t{float(P.coords_w_isoforms.shape[0])}\n")
+            return
+        # a switch somewhere: one column per segment.  The reference fills a DataFrame cell by cell; _Table keeps what
+        # decides the bytes of its to_csv: row and column order of first use, and whether a column started numeric
+        # (floats, "22.0") or with text (values kept as they are, "22").
+        table = _Table()
+        level_1 = [seq.id for seq in P.sequence]
+        coords_all = P.coords_w_isoforms
+        for i, contig in enumerate(level_1):
+            g = P.gene_label_to_gcode[contig]
+            if i == 0:
+                for c in level_1:
+                    for key in ("Coordinates in bp", "Major genetic code", f"Nr genes with {g[1]}", "Nr identical genes",
+                                "Nr isoforms", "Total gene count"):
+                        table.add_row((c, key))
+            segments = sorted(P.confident_1[contig] + P.confident_2[contig])
+            coords = coords_all[coords_all.contig == contig]
+            if len(g) == 1:
+                table.set((contig, "Coordinates in bp"), "Sequence", str(segments[0]))
+                table.set((contig, "Major genetic code"), "Sequence", g[1])
+                table.set((contig, "Total gene count"), "Sequence", coords.shape[0])
+                continue
+            start = coords.start.values.astype(np.int64)
+            is_parent = np.array([isinstance(v, str) and v == "." for v in coords.logodd.values], dtype=bool)
+            source = coords.source.values
+            both = "GeneMark.hmm2_{}_{}".format(*sorted([g[1], g[2]]))
+            keys = (f"Nr genes with {g[1]}", f"Nr genes with {g[2]}", "Nr identical genes", "Nr isoforms", "Total gene count")
+            for n, segment in enumerate(segments, start=1):
+                col = f"Segment {n}"
+                table.set((contig, "Coordinates in bp"), col, str(segment))
+                if segment in P.confident_1[contig]:
+                    table.set((contig, "Major genetic code"), col, g[1])
+                elif segment in P.confident_2[contig]:
+                    table.set((contig, "Major genetic code"), col, g[2])
+                here = (start >= segment[0]) & (start <= segment[1])
+                nr_isoforms = int((here & is_parent).sum())
+                nr_1 = int((here & (source == f"GeneMark.hmm2_{g[1]}")).sum()) - nr_isoforms
+                nr_2 = int((here & (source == f"GeneMark.hmm2_{g[2]}")).sum()) - nr_isoforms
+                nr_identical = int((here & (source == both)).sum()) - nr_isoforms
+                for key, v in zip(keys, (nr_1, nr_2, nr_identical, nr_isoforms, nr_identical + nr_1 + nr_2 + nr_isoforms)):
+                    table.set((contig, key), col, v)
+            for key in keys:
+                table.set((contig, key), "Sequence", table.row_sum((contig, key)))
+        table.write(self.path_to_output)
 
     # ---- bin/results.py:159-181 --------------------------------------------------------------------------------
     def write_stats(self):
@@ -212,7 +260,10 @@ class Results:
     # ---- bin/results.py:181-251 --------------------------------------------------------------------------------
     def write_final_results(self):
         P = self.results
-        tables = [str(P.genome_label)]
+        if isinstance(P.genome_label, (int, np.integer)):
+            tables = [str(P.genome_label)]
+        else:   # every label a window ever got, not only the two that survive the smoothing
+            tables = sorted({str(P.label_to_gcode[int(x)]) for y in P.genome_label for x in y})
         parameters = ", ".join(f"{self.cwd}/dependencies/mgm_{x}.mod" for x in tables)
         coords = P.coords_w_isoforms
         if coords.shape[0] == 0:
@@ -235,13 +286,63 @@ class Results:
                 accession = cur.iloc[0, 0]
                 out.write("\n")
                 out.write(f"##sequence-region {accession} 1 {size}\n")
-                average_gene_length = int(np.round(cur.length.values.mean()))
-                total_logodd_score = np.round(cur.logodd.sum(), decimals=1)
-                average_gene_density = np.round(cur.shape[0] / (size / 1000), decimals=2)
+                # an isoform pair counts once, with the mean of its two genes (bin/results.py:221-245)
+                logodd = cur.logodd.values
+                parents = [i for i in range(len(logodd)) if isinstance(logodd[i], str) and logodd[i] == "."]
+                if parents:
+                    members = sorted([i + 1 for i in parents] + [i + 2 for i in parents])
+                    plain = [i for i in range(len(logodd)) if i not in set(members) and i not in set(parents)]
+                    length = cur.length.values
+                    mean_length = [(length[members[i]] + length[members[i + 1]]) / 2 for i in range(0, len(members), 2)]
+                    mean_logodd = [(logodd[members[i]] + logodd[members[i + 1]]) / 2 for i in range(0, len(members), 2)]
+                    lengths = [length[i] for i in plain] + mean_length
+                    average_gene_length = int(np.round(sum(lengths[1:], lengths[0]) / len(lengths)))
+                    # object column in the reference: added up one by one, left to right
+                    total = 0
+                    for i in plain:
+                        total = total + logodd[i]
+                    total_logodd_score = np.round(total + sum(mean_logodd), decimals=1)
+                    n_genes = cur.shape[0] - 2 * len(parents)
+                else:
+                    average_gene_length = int(np.round(cur.length.values.mean()))
+                    total_logodd_score = np.round(cur.logodd.sum(), decimals=1)
+                    n_genes = cur.shape[0]
+                average_gene_density = np.round(n_genes / (size / 1000), decimals=2)
                 cur.drop(["length", "contig"], axis=1, inplace=True)
                 cur.to_csv(out, header=False, sep="\t", index=False)
                 out.write(f"# {accession}\ttotal_logodd\t{total_logodd_score}\taverage_length\t"
                           f"{average_gene_length}\taverage_density\t{average_gene_density}\n")
+
+
+class _Table:
+    """The cells of the reference's classification DataFrame in the order it creates them (bin/results.py:101-157)."""
+
+    def __init__(self):
+        self.rows, self.cols, self.kind, self.cell = [], [], {}, {}
+
+    def add_row(self, key):
+        if key not in self.rows:
+            self.rows.append(key)
+
+    def set(self, row, col, value):
+        self.add_row(row)
+        text = isinstance(value, str)
+        if col not in self.cols:
+            self.cols.append(col)
+            self.kind[col] = "object" if text else "float"
+        elif text:
+            self.kind[col] = "object"
+        self.cell[(row, col)] = float(value) if self.kind[col] == "float" else value
+
+    def row_sum(self, row):
+        vals = [self.cell[(row, c)] for c in self.cols if (row, c) in self.cell]
+        return sum(vals) if vals else 0
+
+    def write(self, path):
+        with open(path, "w") as fh:
+            fh.write("\t\t" + "\t".join(self.cols) + "\n")
+            for row in self.rows:
+                fh.write("\t".join([str(row[0]), str(row[1])] + [str(self.cell.get((row, c), "-")) for c in self.cols]) + "\n")
 
 
 def _write_fasta(records, path):

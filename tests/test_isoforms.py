@@ -1,0 +1,198 @@
+"""Isoform comparison (mgcod_b200.isoforms) against the reference's own compare_sets_of_predicted_genes on the binary's
+predictions: tests/golden/iso_*.json.xz (make_golden_isoforms.py).  Host logic only — no GPU."""
+import io
+import json
+import os
+import types
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from tests import fixtures as fx
+from mgcod_b200 import isoforms
+from mgcod_b200.data import GFF_COLUMNS, Record
+
+CASES = {"phage2": ("phage2.fa.xz", "phage2_trained_{}.gff.xz"),
+         "phage2_t300": ("phage2.fa.xz", "phage2_trained_{}.gff.xz"),
+         "mixed": (None, "iso_mixed_mgm_{}.gff.xz")}
+
+
+def mixed_fasta():
+    seq = fx.phage2()[0][1]
+    return [("zeta", "zeta two codes", seq[80000:125000]), ("alpha", "alpha", seq[106000:131000]),
+            ("mid", "mid x", seq[0:50000]), ("beta", "beta back", seq[120000:173000])]
+
+
+def records_of(case):
+    if case == "mixed":
+        recs = [Record(i, d, s) for i, d, s in mixed_fasta()]
+    else:
+        recs = [Record(i, i, s) for i, s in fx.phage2()]
+    return sorted(recs, key=lambda r: r.id)
+
+
+def fake_pipeline(case):
+    """what Pipeline holds when it calls the comparison, with gmhmmp2's own GFFs as the gene sets"""
+    ref = json.loads(fx.xz_text(f"iso_{case}.json.xz"))
+    frames = {}
+    for lab, code in enumerate(fx.CODES):
+        df = pd.read_csv(io.StringIO(fx.xz_text(CASES[case][1].format(code))), sep="\t", header=None, comment="#", names=GFF_COLUMNS)
+        df["source"] = df["source"] + f"_{code}"
+        df["length"] = df["end"] - df["start"] + 1
+        df["sequence"] = df["sequence"].astype(str)
+        df["contig"] = list(df.sequence.values)
+        frames[lab] = df
+    a = ref["args"]
+    P = types.SimpleNamespace(species=case, verbose=False, label_to_gene_coords=frames, sequence=records_of(case),
+                              updated_genome_labels=[np.array(u) for u in ref["updated"]], tolerance=a["tol"],
+                              consecutive_gene_labels=a["genes"], label_to_gcode=dict(enumerate(fx.CODES)))
+    assert [r.id for r in P.sequence] == ref["contigs"]
+    return P, ref
+
+
+def column(df, c):
+    out = []
+    for v in df[c].values:
+        if isinstance(v, float) and v != v:
+            out.append(None)
+        elif isinstance(v, str):
+            out.append(v)
+        else:
+            out.append(float(v) if c == "logodd" else int(v))
+    return out
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_compare_sets_matches_reference(case):
+    P, ref = fake_pipeline(case)
+    coords, g2g, iso = isoforms.compare_sets_of_predicted_genes(P)
+    assert {k: {str(i): str(v) for i, v in d.items()} for k, d in g2g.items()} == ref["gene_label_to_gcode"]
+    want = ref["coords_w_isoforms"]
+    assert iso.shape[0] == len(want["start"])
+    for c in ("contig", "source", "start", "end", "strand", "logodd", "attributes"):
+        assert column(iso, c) == want[c], c
+    # gene_label: the reference leaves it unset (NaN) on some parents; where it is set it must agree
+    got = column(iso, "gene_label")
+    assert [g for g, w in zip(got, want["gene_label"]) if w is not None] == [w for w in want["gene_label"] if w is not None]
+    # the plain table: same genes in the same order (ties of the sort by start included), labels and smoothed labels
+    coords = coords.reset_index(drop=True)
+    for c in ("contig", "start", "end", "strand", "source", "gene_label", "updated_gene_label"):
+        assert column(coords, c) == ref["coords"][c], c
+
+
+def test_update_gene_ids_and_insert():
+    rows = [{"start": 10, "attributes": "gene_id 1; x"}, {"start": 50, "attributes": "gene_id 2; gene_type a;"},
+            {"start": 40, "attributes": "gene_id 2.11; Parent=2; y"}, {"start": 50, "attributes": "gene_id 2.15; Parent=2; z"},
+            {"start": 90, "attributes": "gene_id 3; w"}]
+    out = isoforms.insert_unseen_genes([dict(r) for r in rows], [{"start": 45, "attributes": "gene_id 77; u"}])
+    # last row starting at or before 45 is the child at 40 (index 2); its sibling is skipped; the gene takes id 3
+    assert [r["attributes"] for r in out] == ["gene_id 1; x", "gene_id 2; gene_type a;", "gene_id 2.11; Parent=2; y",
+                                              "gene_id 2.15; Parent=2; z", "gene_id 3; u", "gene_id 4; w"]
+    out = isoforms.insert_unseen_genes([dict(r) for r in rows], [{"start": 5, "attributes": "gene_id 9; u"}])
+    assert [r["attributes"].split(";")[0] for r in out] == ["gene_id 0", "gene_id 2", "gene_id 3", "gene_id 3.11", "gene_id 3.15",
+                                                            "gene_id 4"]
+    out = isoforms.insert_unseen_genes([dict(r) for r in rows], [{"start": 95, "attributes": "gene_id 9; u"}])
+    assert out[-1]["attributes"] == "gene_id 4; u"
+
+
+def test_gc_percent():
+    assert isoforms.gc_percent("") == 0.0
+    assert isoforms.gc_percent("GCgcSsATat") == 60.0
+
+
+class HostResults:
+    """Results with the in-frame stop scan done by the host restatement instead of the GPU kernel (test-only: the product
+    class always uses the engine)."""
+
+    @staticmethod
+    def make(P, case, outdir):
+        import datetime
+        from mgcod_b200.results import Results, _COMP
+
+        class R(Results):
+            def extract_sequences(self):
+                out = []
+                coords = self.results.coords_w_isoforms
+                for n in range(self.results.nr_contigs):
+                    rec = self.results.sequence[n]
+                    cur = coords[coords.contig == rec.id]
+                    cur = cur[cur.logodd != "."]
+                    for s, e, st in zip(cur.start.values, cur.end.values, cur.strand.values):
+                        seq = rec.seq[s - 1:e]
+                        if st == "-":
+                            seq = seq[::-1].translate(_COMP)
+                        seq = seq.lower()
+                        d = {}
+                        for name in ("TAG", "TGA", "TAA"):
+                            d[name], seq = Results.find_recoded_stops(seq, name.lower())
+                        out.append(d)
+                return out
+
+        return R(P, case, "PRED/", f"TMP/{case}.fasta", outdir, datetime.datetime(2026, 1, 1, 12, 0, 0), False, False, False, False,
+                 "TMP/mgcod")
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_results_files_of_a_switch_run(case, tmp_path):
+    """.gff / .tab / _stats.tab of a run with a switch, byte for byte (the output-date line aside)"""
+    P, ref = fake_pipeline(case)
+    P.coords, P.gene_label_to_gcode, P.coords_w_isoforms = isoforms.compare_sets_of_predicted_genes(P)
+    P.nr_contigs = len(P.sequence)
+    P.genome_label = [np.array(l) for l in ref["labels"]]
+    P.confident_1 = {k: [tuple(t) for t in v] for k, v in ref["confident_1"].items()}
+    P.confident_2 = {k: [tuple(t) for t in v] for k, v in ref["confident_2"].items()}
+    out = str(tmp_path) + "/"
+    R = HostResults.make(P, case, out)
+    R()
+    strip = lambda t: "\n".join(l for l in t.split("\n") if not l.startswith("# output date"))
+    assert open(f"{out}{case}.tab").read() == fx.xz_text(f"iso_{case}.tab.xz")
+    assert open(f"{out}{case}_stats.tab").read() == fx.xz_text(f"iso_{case}_stats.tab.xz")
+    assert strip(open(f"{out}{case}.gff").read()) == fx.xz_text(f"iso_{case}.gff.xz")
+
+
+def _case_text(case):
+    if case == "mixed":
+        return "".join(f">{d}\n{s}\n" for _, d, s in mixed_fasta())
+    return fx.xz_text("phage2.fa.xz")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", list(CASES))
+@pytest.mark.parametrize("via_cli", [False, True])
+def test_switch_run_end_to_end_on_the_gpu(case, via_cli, tmp_path):
+    """FASTA -> CUDA decode under four models -> window labels -> isoform comparison -> Results files, equal to the
+    reference's files for the same command line (--isoforms -w .. -st .. -n .. -g .. -t ..)"""
+    import datetime
+    from mgcod_b200.pipeline import Pipeline
+    from mgcod_b200.results import Results
+    tmp = str(tmp_path)
+    ref = json.loads(fx.xz_text(f"iso_{case}.json.xz"))
+    a = ref["args"]
+    mdir = os.path.dirname(fx.trained_models(tmp)[11])
+    fa = os.path.join(tmp, f"{case}.fasta")
+    open(fa, "w").write(_case_text(case))
+    pred, out = os.path.join(tmp, "pred") + "/", os.path.join(tmp, "out") + "/"
+    if via_cli:
+        from mgcod_b200 import cli
+        assert cli.main(["-i", fa, "-p", pred, "-o", out, "--isoforms", "-w", str(a["window"]), "-st", str(a["stride"]), "-n", str(a["n"]),
+                         "-g", str(a["genes"]), "-t", str(a["tol"]), "--model_dir", mdir]) == 0
+    else:
+        os.makedirs(pred)
+        os.makedirs(out)
+        P = Pipeline(fa, pred, case, True, False, a["n"], a["genes"], a["window"], a["stride"], a["tol"], False, False, "CWD",
+                     model_dir=mdir)
+        P()
+        assert [u.tolist() for u in P.updated_genome_labels] == ref["updated"]
+        assert {k: {str(i): str(v) for i, v in d.items()} for k, d in P.gene_label_to_gcode.items()} == ref["gene_label_to_gcode"]
+        Results(P, case, pred, fa, out, datetime.datetime(2026, 1, 1, 12, 0, 0), False, False, False, False, "CWD")()
+    golden = fx.xz_text(f"iso_{case}.gff.xz").split("\n")
+    mine = fx.strip_dates(open(f"{out}{case}.gff").read()).split("\n")
+    assert len(golden) == len(mine)
+    for g, m in zip(golden, mine):
+        if g.startswith("# File with"):     # paths differ (temp dirs); the rest of the header must agree
+            assert m.split(":")[0] == g.split(":")[0]
+            continue
+        assert g == m
+    assert open(f"{out}{case}.tab").read() == fx.xz_text(f"iso_{case}.tab.xz")
+    assert open(f"{out}{case}_stats.tab").read() == fx.xz_text(f"iso_{case}_stats.tab.xz")
