@@ -195,6 +195,7 @@ struct mgc_engine {
     } pending;
     // pointer tables + counters (device)
     DevBuf t_orfs, t_starts, t_surv, t_sorted, t_bcount, t_cover, t_gene_off, t_genes, t_chainbufs;
+    DevBuf t_scan_buckets, t_gene_count, t_slot_gene_off;   // pointer tables of the batched scans
     DevBuf t_ls, t_ls_tile, t_items, t_items_sorted, t_hist, t_item_off, t_unit_off, t_sums, unit_totals, next_unit;
     uint32_t cap_items = 0;
     int max_cod_order = 0, max_non_order = 0, max_pairs = 1;
@@ -390,7 +391,7 @@ void ensure_batch_buffers(mgc_engine *e) {
     e->ncount.ensure((size_t)(W + 8) * 4);
     const int64_t nb = W / 4;
     const int64_t scan_n = std::max<int64_t>(std::max<int64_t>(W, nb), e->n_contigs + 1);
-    e->tile_sums.ensure((size_t)(scan_n / 2048 + 8) * 4);
+    e->tile_sums.ensure((size_t)(scan_n / 2048 + 8) * 4 * 2 * std::max(M, 1));   // batched scans keep one row of tile sums per array
     e->grp2contig.ensure((size_t)(W / 4 + 8) * 4);
     e->flags.ensure(64);
     // observed on gene-dense input per kb and model: ~11 ORFs, ~36 starts, ~18 walk items, ~10 surviving candidates
@@ -401,6 +402,7 @@ void ensure_batch_buffers(mgc_engine *e) {
     e->cap_items = (uint32_t)std::min<int64_t>(nt / 16 * sc + 8192, 0x7fffff00);
     e->cap_surv = (uint32_t)std::min<int64_t>(nt / 24 * sc + 8192, 0x7fffff00);
     std::vector<void *> t_orfs(M), t_starts(M), t_surv(M), t_sorted(M), t_bcount(M), t_cover(M), t_gene_off(M), t_genes(M);
+    std::vector<void *> t_scan_buckets(2 * M), t_gene_count(M), t_slot_gene_off(M);
     std::vector<void *> t_ls(M), t_ls_tile(M), t_items(M), t_items_sorted(M), t_hist(M), t_item_off(M), t_unit_off(M), t_sums(M);
     const int64_t ls_tiles = (2 * W + 255) / 256;
     std::vector<ChainBufs> cb(M);
@@ -446,6 +448,7 @@ void ensure_batch_buffers(mgc_engine *e) {
         p.genes.ensure((size_t)e->cap_surv * sizeof(mgc_gene));
         t_orfs[i] = p.orfs.p; t_starts[i] = p.starts.p; t_surv[i] = p.surv.p; t_sorted[i] = p.sorted.p;
         t_bcount[i] = p.bcount.p; t_cover[i] = p.cover.p; t_gene_off[i] = p.gene_off.p; t_genes[i] = p.genes.p;
+        t_scan_buckets[i] = p.bcount.p; t_scan_buckets[M + i] = p.cover.p; t_gene_count[i] = p.gene_count.p; t_slot_gene_off[i] = p.slot_gene_off.p;
         ChainBufs &c = cb[i];
         c.sorted = p.sorted.as<Cand>();
         c.bend = p.bcount.as<uint32_t>();
@@ -476,10 +479,11 @@ void ensure_batch_buffers(mgc_engine *e) {
     auto add_sig = [&](const void *src, size_t bytes) {
         sig.insert(sig.end(), static_cast<const unsigned char *>(src), static_cast<const unsigned char *>(src) + bytes);
     };
-    for (auto *v : {&t_orfs, &t_starts, &t_surv, &t_sorted, &t_bcount, &t_cover, &t_gene_off, &t_genes, &t_ls, &t_ls_tile, &t_items,
+    for (auto *v : {&t_gene_count, &t_slot_gene_off, &t_orfs, &t_starts, &t_surv, &t_sorted, &t_bcount, &t_cover, &t_gene_off, &t_genes, &t_ls, &t_ls_tile, &t_items,
                     &t_items_sorted, &t_hist, &t_item_off, &t_unit_off, &t_sums})
         add_sig(v->data(), M * sizeof(void *));
     add_sig(cb.data(), M * sizeof(ChainBufs));
+    add_sig(t_scan_buckets.data(), 2 * M * sizeof(void *));
     const bool tables_current = sig == e->table_sig;
     auto up = [&](DevBuf &b, const void *src, size_t bytes) {
         if (tables_current) return;
@@ -492,6 +496,9 @@ void ensure_batch_buffers(mgc_engine *e) {
     up(e->t_sorted, t_sorted.data(), M * sizeof(void *));
     up(e->t_bcount, t_bcount.data(), M * sizeof(void *));
     up(e->t_cover, t_cover.data(), M * sizeof(void *));
+    up(e->t_scan_buckets, t_scan_buckets.data(), 2 * M * sizeof(void *));
+    up(e->t_gene_count, t_gene_count.data(), M * sizeof(void *));
+    up(e->t_slot_gene_off, t_slot_gene_off.data(), M * sizeof(void *));
     up(e->t_gene_off, t_gene_off.data(), M * sizeof(void *));
     up(e->t_genes, t_genes.data(), M * sizeof(void *));
     up(e->t_chainbufs, cb.data(), M * sizeof(ChainBufs));
@@ -693,13 +700,13 @@ mgc_result *run_pipeline(mgc_engine *e, bool *amb_out) {
     launches += 1;
     CUDA_TRY(cudaPeekAtLastError());   // a failed launch must not go unnoticed until the end
     CUDA_TRY(cudaEventRecord(e->ev[3], st));
-    for (int i = 0; i < M; i++) {
-        // the grand total = number of candidates (survivor slots may include unfilled ones): low half of counter 4
-        launches += launch_exclusive_scan(e->pm[i].bcount.as<uint32_t>(), e->pm[i].bcount.as<uint32_t>(), e->tile_sums.as<uint32_t>(),
-                                          nb, reinterpret_cast<uint32_t *>(e->counters.as<unsigned long long>() + (size_t)i * 8 + 4), st);
-        launches += launch_exclusive_scan(e->pm[i].cover.as<uint32_t>(), e->pm[i].cover.as<uint32_t>(), e->tile_sums.as<uint32_t>(),
-                                          nb + 2, nullptr, st);
-    }
+    // bucket offsets (M arrays) and boundary coverage (M arrays) of all models in one batched scan, in place; the two extra
+    // entries are zero.  Grand totals: the first M = candidates per model (survivor slots may include unfilled ones), written
+    // to the low half of counter 4; the coverage totals land in counter 6 and are not used.
+    launches += launch_exclusive_scan_multi(e->t_scan_buckets.as<const uint32_t *>(), e->t_scan_buckets.as<uint32_t *>(), 2 * M,
+                                            e->tile_sums.as<uint32_t>(), nb + 2, nullptr, 0, st);
+    launch_bucket_totals(e->t_bcount.as<const uint32_t *const>(), nb, e->counters.as<unsigned long long>(), M, st);
+    launches += 1;
     launch_scatter(e->t_surv.as<const Cand *>(), e->t_sorted.as<Cand *>(), e->t_bcount.as<uint32_t *>(),
                    e->surv_counters.as<unsigned long long>(), e->cwoff.as<int64_t>(), e->cap_surv, M, e->n_sm, st);
     launches += 1;
@@ -709,11 +716,9 @@ mgc_result *run_pipeline(mgc_engine *e, bool *amb_out) {
                              e->slot_contig.as<int32_t>(), e->n_slots, nb, e->work_counters.as<int>(), M, e->n_sm, st);
     CUDA_TRY(cudaPeekAtLastError());   // a failed launch must not go unnoticed until the end
     CUDA_TRY(cudaEventRecord(e->ev[5], st));
-    for (int i = 0; i < M; i++) {
-        // gene_count[n_slots] stays 0 so that the exclusive scan yields the total at slot_gene_off[n_slots]
-        launches += launch_exclusive_scan(e->pm[i].gene_count.as<uint32_t>(), e->pm[i].slot_gene_off.as<uint32_t>(),
-                                          e->tile_sums.as<uint32_t>(), (int64_t)e->n_slots + 1, e->gene_totals.as<uint32_t>() + i, st);
-    }
+    // gene_count[n_slots] stays 0 so that the exclusive scan yields the total at slot_gene_off[n_slots]
+    launches += launch_exclusive_scan_multi(e->t_gene_count.as<const uint32_t *>(), e->t_slot_gene_off.as<uint32_t *>(), M,
+                                            e->tile_sums.as<uint32_t>(), (int64_t)e->n_slots + 1, e->gene_totals.as<uint32_t>(), 1, st);
     if (e->last_ready) CUDA_TRY(cudaStreamWaitEvent(st, e->last_ready->ev, 0));   // the previous result still reads the gene buffers
     launches += launch_gather(e->t_chainbufs.as<ChainBufs>(), e->t_genes.as<mgc_gene *>(), e->slot_contig.as<int32_t>(), e->n_slots,
                               e->slotbase.as<int32_t>(), n, e->model_cents.as<long long>(), M, e->n_sm, st);
@@ -978,7 +983,7 @@ void mgc_engine_destroy(mgc_engine *e) {
             b->release();
     }
     for (DevBuf *b : {&e->d_models, &e->ascii, &e->aoff, &e->cwoff, &e->clen, &e->grp2contig, &e->lo, &e->hi, &e->gc,
-                      &e->tile_sums, &e->flags, &e->t_orfs, &e->t_starts, &e->t_surv, &e->t_sorted, &e->t_bcount, &e->t_cover, &e->t_gene_off,
+                      &e->tile_sums, &e->flags, &e->t_orfs, &e->t_starts, &e->t_surv, &e->t_sorted, &e->t_bcount, &e->t_cover, &e->t_scan_buckets, &e->t_gene_count, &e->t_slot_gene_off, &e->t_gene_off,
                       &e->t_genes, &e->t_chainbufs, &e->counters, &e->surv_counters, &e->work_counters, &e->model_cents,
                       &e->gene_totals, &e->t_ls, &e->t_ls_tile, &e->t_items, &e->t_items_sorted, &e->t_hist, &e->t_item_off,
                       &e->t_unit_off, &e->t_sums, &e->ascii_next, &e->slotbase, &e->slot_contig, &e->nm, &e->ncount, &e->codon, &e->cflags, &e->plen, &e->gaps, &e->gap_count, &e->unit_totals, &e->next_unit, &e->win_stride, &e->win_off, &e->win_labels, &e->win_cents})

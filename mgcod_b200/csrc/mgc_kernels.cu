@@ -154,6 +154,75 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(uint32_t *out, const 
         if (base + k < n) out[base + k] += add;
 }
 
+// the same for several arrays of equal length in one launch each (blockIdx.y = array): in_m / out_m are device tables of
+// pointers, tile_sums holds nt entries per array, grand_totals (optional) one per array with the given stride in uint32
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles_multi(const uint32_t *const *in_m, uint32_t *const *out_m, uint32_t *tile_sums,
+                                                                   int64_t n, int64_t nt) {
+    const uint32_t *in = in_m[blockIdx.y];
+    uint32_t *out = out_m[blockIdx.y];
+    int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS], s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        v[k] = base + k < n ? in[base + k] : 0;
+        s += v[k];
+    }
+    uint32_t total;
+    uint32_t ex = block_exclusive_scan(s, &total);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        if (base + k < n) out[base + k] = ex;
+        ex += v[k];
+    }
+    if (threadIdx.x == 0) tile_sums[(int64_t)blockIdx.y * nt + blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) k_scan_sums_multi(uint32_t *tile_sums, int64_t nt, uint32_t *grand_totals, int total_stride) {
+    __shared__ uint32_t carry;
+    uint32_t *ts = tile_sums + (int64_t)blockIdx.x * nt;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int64_t b = 0; b < nt; b += 1024) {
+        int64_t i = b + threadIdx.x;
+        uint32_t v = i < nt ? ts[i] : 0, total;
+        uint32_t ex = block_exclusive_scan(v, &total);
+        if (i < nt) ts[i] = carry + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && grand_totals) grand_totals[(int64_t)blockIdx.x * total_stride] = carry;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_add_multi(uint32_t *const *out_m, const uint32_t *tile_sums, int64_t n, int64_t nt) {
+    uint32_t *out = out_m[blockIdx.y];
+    int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+    uint32_t add = tile_sums[(int64_t)blockIdx.y * nt + blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++)
+        if (base + k < n) out[base + k] += add;
+}
+
+int launch_exclusive_scan_multi(const uint32_t *const *in_m, uint32_t *const *out_m, int n_arrays, uint32_t *tile_sums, int64_t n,
+                                uint32_t *grand_totals, int total_stride, cudaStream_t st) {
+    if (n <= 0 || n_arrays <= 0) return 0;
+    const int64_t nt = (n + SCAN_TILE - 1) / SCAN_TILE;
+    k_scan_tiles_multi<<<dim3((unsigned)nt, n_arrays), SCAN_THREADS, 0, st>>>(in_m, out_m, tile_sums, n, nt);
+    k_scan_sums_multi<<<n_arrays, 1024, 0, st>>>(tile_sums, nt, grand_totals, total_stride);
+    k_scan_add_multi<<<dim3((unsigned)nt, n_arrays), SCAN_THREADS, 0, st>>>(out_m, tile_sums, n, nt);
+    return 3;
+}
+
+// after the in-place exclusive scan over nb + 2 entries (the last two were zero) entry nb holds the number of candidates
+__global__ void k_bucket_totals(const uint32_t *const *bend_m, int64_t nb, unsigned long long *counters_m) {
+    const int mi = threadIdx.x;
+    counters_m[(size_t)mi * 8 + 4] = bend_m[mi][nb];
+}
+
+void launch_bucket_totals(const uint32_t *const *bend_m, int64_t nb, unsigned long long *counters_m, int n_models, cudaStream_t st) {
+    k_bucket_totals<<<1, n_models, 0, st>>>(bend_m, nb, counters_m);
+}
+
 int launch_exclusive_scan(const uint32_t *in, uint32_t *out, uint32_t *tile_sums, int64_t n, uint32_t *grand_total,
                           cudaStream_t st) {
     if (n <= 0) return 0;

@@ -17,6 +17,9 @@ struct ChainBufs;
 
 int launch_exclusive_scan(const uint32_t *in, uint32_t *out, uint32_t *tile_sums, int64_t n, uint32_t *grand_total,
                           cudaStream_t st);
+void launch_bucket_totals(const uint32_t *const *bend_m, int64_t nb, unsigned long long *counters_m, int n_models, cudaStream_t st);
+int launch_exclusive_scan_multi(const uint32_t *const *in_m, uint32_t *const *out_m, int n_arrays, uint32_t *tile_sums, int64_t n,
+                                uint32_t *grand_totals, int total_stride, cudaStream_t st);
 void launch_groups(const int64_t *cwoff, int32_t n_contigs, int64_t n_groups, int32_t *grp2contig, cudaStream_t st);
 void launch_pack(const char *ascii, const int64_t *aoff, const int64_t *cwoff, const int32_t *clen, const int32_t *grp2contig,
                  int64_t W, uint32_t *lo, uint32_t *hi, uint32_t *nm, uint32_t *gccount, uint32_t *ncount, int *dflags,

@@ -196,3 +196,35 @@ def test_switch_run_end_to_end_on_the_gpu(case, via_cli, tmp_path):
         assert g == m
     assert open(f"{out}{case}.tab").read() == fx.xz_text(f"iso_{case}.tab.xz")
     assert open(f"{out}{case}_stats.tab").read() == fx.xz_text(f"iso_{case}_stats.tab.xz")
+
+
+def test_comparison_against_reference_on_random_gene_sets():
+    """300 perturbed pairs of gene sets (tests/golden/make_golden_isoform_cases.py): both tables as the reference builds them"""
+    import sys
+    sys.path.insert(0, fx.GOLDEN)
+    from make_golden_isoform_cases import case_sequence, frame
+    cases = json.loads(fx.xz_text("iso_cases.json.xz"))
+    assert len(cases) >= 250
+    seen_parents = 0
+    for k, c in enumerate(cases):
+        l1, l2 = c["labels"]
+        frames = {lab: frame([], code) for lab, code in enumerate(fx.CODES)}
+        frames[l1] = frame([tuple(g) for g in c["genes_1"]], fx.CODES[l1])
+        frames[l2] = frame([tuple(g) for g in c["genes_2"]], fx.CODES[l2])
+        P = types.SimpleNamespace(species="fuzz", verbose=False, label_to_gene_coords=frames,
+                                  sequence=[Record("c1", "c1", case_sequence(c["seq_seed"], c["seq_len"]))],
+                                  updated_genome_labels=[np.array([l1, l1, l2, l2])], tolerance=c["tolerance"],
+                                  consecutive_gene_labels=c["consecutive_gene_labels"], label_to_gcode=dict(enumerate(fx.CODES)))
+        want = c["expected"]
+        if "error" in want:
+            with pytest.raises(Exception):
+                isoforms.compare_sets_of_predicted_genes(P)
+            continue
+        coords, _, iso = isoforms.compare_sets_of_predicted_genes(P)
+        for col in ("source", "start", "end", "strand", "logodd", "attributes"):
+            assert column(iso, col) == want["iso"][col], (k, col)
+        coords = coords.reset_index(drop=True)
+        for col in ("start", "end", "strand", "source", "gene_label", "updated_gene_label"):
+            assert column(coords, col) == want["coords"][col], (k, col)
+        seen_parents += sum(1 for v in want["iso"]["logodd"] if v == ".")
+    assert seen_parents > 100
