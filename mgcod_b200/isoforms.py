@@ -120,9 +120,8 @@ def update_gene_ids(rows: list[dict]) -> list[dict]:
     return rows
 
 
-def insert_unseen_genes(rows: list[dict], unseen: list[dict]) -> list[dict]:
-    """bin/pipeline.py:1170-1209: set-2 genes that matched nothing go behind the last row starting at or before them
-    (behind that row's children), take the id of the row they displace, and every later id moves up by one."""
+def _insert_unseen_stepwise(rows: list[dict], unseen: list[dict]) -> list[dict]:
+    """bin/pipeline.py:1170-1209 step by step: every insertion renumbers the rows behind it (O(unseen x rows) string work)."""
     for g in unseen:
         gene = dict(g)
         ind = -1
@@ -145,6 +144,66 @@ def insert_unseen_genes(rows: list[dict], unseen: list[dict]) -> list[dict]:
             gene["attributes"] = f"gene_id {here};" + _rest(gene["attributes"])
             rows = rows[:ind] + [gene] + update_gene_ids([dict(r) for r in rows[ind:]])
     return rows
+
+
+def _insert_unseen_renumbered(rows: list[dict], unseen: list[dict]):
+    """The same result in one pass, for a table in the shape the comparison normally produces: every id is a plain
+    integer used by one row (or by a parent and its ``Parent=`` children), ids go up by one from row group to row group,
+    and no gene lands in front of the first row.  Then "take the id of the displaced row, everything behind moves up by
+    one" keeps the numbering consecutive in list order, so it is enough to find the positions (they depend on the starts
+    and the Parent marks only) and number the groups once at the end.  Returns None when the table is not of that shape
+    (a parent that kept its model's id, several rows sharing an id): the caller then goes step by step."""
+    if not rows:
+        return None
+    token = [r["attributes"].split(";")[0].split(" ")[1] for r in rows]
+    is_child = ["Parent" in r["attributes"] for r in rows]
+    group = []                       # id of the group each row belongs to
+    for k, (t, ch) in enumerate(zip(token, is_child)):
+        if ch:
+            if k == 0 or not t.startswith(f"{group[-1]}.") or f"Parent={group[-1]};" not in rows[k]["attributes"]:
+                return None
+            group.append(group[-1])
+        else:
+            if not t.isdigit() or (k > 0 and int(t) != group[-1] + 1) or rows[k]["attributes"].count(f"gene_id {t}") != 1:
+                return None
+            group.append(int(t))
+    starts = np.array([r["start"] for r in rows], dtype=np.int64)
+    child = np.array(is_child, dtype=bool)
+    origin = np.arange(len(rows), dtype=np.int64)            # >= 0: original row; -1 - j: unseen gene j
+    for j, g in enumerate(unseen):
+        at = np.flatnonzero(starts <= g["start"])
+        if at.shape[0] == 0:
+            return None
+        ind = int(at[-1]) + 1
+        while ind < starts.shape[0] and child[ind]:
+            ind += 1
+        starts = np.insert(starts, ind, g["start"])
+        child = np.insert(child, ind, False)
+        origin = np.insert(origin, ind, -1 - j)
+    out = []
+    current = group[0] - 1
+    for k, o in enumerate(origin.tolist()):
+        if o < 0:
+            current += 1
+            gene = dict(unseen[-1 - o])
+            gene["attributes"] = f"gene_id {current};" + _rest(gene["attributes"])
+            out.append(gene)
+            continue
+        if not is_child[o]:
+            current += 1
+        r = dict(rows[o])
+        if current != group[o]:
+            r["attributes"] = r["attributes"].replace(f"gene_id {group[o]}", f"gene_id {current}").replace(
+                f"Parent={group[o]}", f"Parent={current}")
+        out.append(r)
+    return out
+
+
+def insert_unseen_genes(rows: list[dict], unseen: list[dict]) -> list[dict]:
+    """bin/pipeline.py:1170-1209: set-2 genes that matched nothing go behind the last row starting at or before them
+    (behind that row's children), take the id of the row they displace, and every later id moves up by one."""
+    out = _insert_unseen_renumbered(rows, unseen)
+    return out if out is not None else _insert_unseen_stepwise(rows, unseen)
 
 
 def compare_contig(S1: _GeneSet, S2: _GeneSet, code_1, code_2, tolerance: int, seq: str):

@@ -228,3 +228,40 @@ def test_comparison_against_reference_on_random_gene_sets():
             assert column(coords, col) == want["coords"][col], (k, col)
         seen_parents += sum(1 for v in want["iso"]["logodd"] if v == ".")
     assert seen_parents > 100
+
+
+def test_one_pass_renumbering_equals_stepwise_insertion():
+    """the one-pass form of insert_unseen_genes against the step-by-step restatement of the reference on random tables,
+    including shapes it must decline (shared ids, a parent with a foreign id, a gene in front of the first row)"""
+    import random
+    rng = random.Random(5)
+    used_fast = declined = 0
+    for it in range(400):
+        rows, gid, pos = [], rng.choice([1, 1, 7, 99]), rng.randint(1, 50)
+        for _ in range(rng.randint(1, 30)):
+            s = pos
+            kind = rng.random()
+            if kind < 0.25:       # isoform triple
+                pid = gid if rng.random() > 0.04 else gid + 40      # case-E parent keeps a foreign id
+                rows.append({"start": s, "attributes": f"gene_id {pid}; gene_type bacteria; gc 30; length 300;"})
+                rows.append({"start": s + rng.choice([0, 30]), "attributes": f"gene_id {gid}.11; Parent={gid}; gene_type bacteria;"})
+                rows.append({"start": s, "attributes": f"gene_id {gid}.15; Parent={gid}; gene_type bacteria;"})
+            elif kind < 0.29:     # several rows sharing one id
+                for k in range(rng.randint(2, 3)):
+                    rows.append({"start": s + 100 * k, "attributes": f"gene_id {gid}; gene_type bacteria; gc 31;"})
+            else:
+                rows.append({"start": s, "attributes": f"gene_id {gid}; gene_type bacteria; gc 3{gid % 10}; length 1{gid};"})
+            gid += 1
+            pos += rng.randint(50, 400)
+        unseen = sorted(({"start": rng.randint(1 if rng.random() < 0.05 else rows[0]["start"], pos + 200),
+                          "attributes": f"gene_id {900 + k}; gene_type bacteria; gc 50;"} for k in range(rng.randint(1, 8))),
+                        key=lambda g: g["start"])
+        want = isoforms._insert_unseen_stepwise([dict(r) for r in rows], unseen)
+        fast = isoforms._insert_unseen_renumbered([dict(r) for r in rows], unseen)
+        if fast is None:
+            declined += 1
+        else:
+            used_fast += 1
+            assert fast == want, it
+        assert isoforms.insert_unseen_genes([dict(r) for r in rows], unseen) == want
+    assert used_fast > 150 and declined > 20
