@@ -54,6 +54,16 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def _alu_roofline(units_per_launch, kernel_ms, clocks):
+    mhz = float((clocks or {}).get("sm_mhz") or 1965.0)
+    peak = 148 * 128 * mhz * 1e6 / 1e12
+    achieved = 26.0 * units_per_launch / (kernel_ms * 1e-3) / 1e12 if kernel_ms > 0 else 0.0
+    return {"kernel": "k_walk", "bound": "alu", "achieved": achieved, "peak": peak, "unit": "Top/s", "frac": achieved / peak,
+            "ops_per_unit": 26, "sm_mhz": mhz,
+            "note": "algorithmic op count of SURVEY.md 8(d); the kernel's measured limiter is the shared-memory data pipe "
+                    "(profiles/r1f_top_kernels_1Gbp.txt)"}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
 
@@ -469,6 +479,9 @@ def main():
                                                "workload (profiles/r1f_top_kernels_1Gbp.txt)" if default_workload else None,
                              "peak_source": peak_src,
                              "kernel_ms_per_launch": score_ms, "algorithmic_bytes_per_launch": alg_bytes},
+                # SURVEY.md section 8(d) asks for the second candidate roof as well: ~26 simple ops (k-mer index updates, table
+                # lookups' adds, prefix sums) per bp x model against 148 SMs x 128 lanes x the SM clock seen during the run
+                "roofline_alu": _alu_roofline(total_bp * engine.n_models, score_ms, clocks),
                 "phases_ms_per_step": {k: v / args.steps for k, v in phase.items()},
                 "counts_per_step": counts,
                 "host": {"cores": cores, "workload_generation_s": gen_s, "numa_cpus": numa},

@@ -265,3 +265,94 @@ def test_one_pass_renumbering_equals_stepwise_insertion():
             assert fast == want, it
         assert isoforms.insert_unseen_genes([dict(r) for r in rows], unseen) == want
     assert used_fast > 150 and declined > 20
+
+
+# ---- BASELINE.json configs[2] / configs[3]: the reference's other example inputs ---------------------------------------
+
+def _example_text(case):
+    gca, phage = fx.xz_text("gca.fa.xz"), fx.xz_text("phage2.fa.xz")
+    return gca if case == "gca" else phage + gca          # both.fasta: phage2 first
+
+
+def _both_gff(code):
+    """gmhmmp2's GFF for both.fasta = its GFFs for the two records, gene ids continuing across records"""
+    import re
+    first = [l for l in fx.xz_text(f"phage2_trained_{code}.gff.xz").split("\n") if l and not l.startswith("#")]
+    second = [l for l in fx.xz_text(f"gca_trained_{code}.gff.xz").split("\n") if l and not l.startswith("#")]
+    n = len(first)
+    second = [re.sub(r"gene_id (\d+);", lambda m: f"gene_id {int(m.group(1)) + n};", l) for l in second]
+    return "\n".join(first + second) + "\n"
+
+
+def test_both_fasta_isoforms_host_part():
+    """configs[3] with --isoforms: two contigs, both with switches between codes 15 and 101, five segments on one of them;
+    comparison + Results files from the binary's GFFs (no GPU)"""
+    ref = json.loads(fx.xz_text("ex_both_iso.json.xz"))
+    frames = {}
+    for lab, code in enumerate(fx.CODES):
+        df = pd.read_csv(io.StringIO(_both_gff(code)), sep="\t", header=None, comment="#", names=GFF_COLUMNS)
+        df["source"] = df["source"] + f"_{code}"
+        df["length"] = df["end"] - df["start"] + 1
+        df["sequence"] = df["sequence"].astype(str)
+        df["contig"] = list(df.sequence.values)
+        frames[lab] = df
+    recs = sorted((Record(i, i, s) for i, s in fx.parse_fasta_text(_example_text("both"))), key=lambda r: r.id)
+    assert [r.id for r in recs] == ref["contigs"] and [len(r) for r in recs] == ref["lengths"]
+    P = types.SimpleNamespace(species="both_iso", verbose=False, label_to_gene_coords=frames, sequence=recs, nr_contigs=2,
+                              updated_genome_labels=[np.array(u) for u in ref["updated"]], tolerance=30, consecutive_gene_labels=5,
+                              label_to_gcode=dict(enumerate(fx.CODES)), genome_label=[np.array(l) for l in ref["labels"]],
+                              confident_1={k: [tuple(t) for t in v] for k, v in ref["confident_1"].items()},
+                              confident_2={k: [tuple(t) for t in v] for k, v in ref["confident_2"].items()})
+    P.coords, P.gene_label_to_gcode, P.coords_w_isoforms = isoforms.compare_sets_of_predicted_genes(P)
+    assert {k: {str(i): str(v) for i, v in d.items()} for k, d in P.gene_label_to_gcode.items()} == ref["gene_label_to_gcode"]
+    import tempfile
+    out = tempfile.mkdtemp() + "/"
+    HostResults.make(P, "both_iso", out)()
+    strip = lambda t: "\n".join(l for l in t.split("\n") if not l.startswith("# output date"))
+    assert open(f"{out}both_iso.tab").read() == fx.xz_text("ex_both_iso.tab.xz")
+    assert open(f"{out}both_iso_stats.tab").read() == fx.xz_text("ex_both_iso_stats.tab.xz")
+    assert strip(open(f"{out}both_iso.gff").read()) == fx.xz_text("ex_both_iso.gff.xz")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["gca", "both", "both_iso"])
+def test_reference_examples_end_to_end_on_the_gpu(case, tmp_path):
+    """configs[2] (GCA_002924505.1, default mode) and configs[3] (both.fasta, default and --isoforms with the automatic
+    stride): predictions of the four models, labels, and the three Results files equal the reference's"""
+    import datetime
+    from mgcod_b200.pipeline import Pipeline
+    from mgcod_b200.results import Results
+    tmp = str(tmp_path)
+    ref = json.loads(fx.xz_text(f"ex_{case}.json.xz"))
+    mdir = os.path.dirname(fx.trained_models(tmp)[11])
+    fa = os.path.join(tmp, f"{case}.fasta")
+    open(fa, "w").write(_example_text("gca" if case == "gca" else "both"))
+    pred, out = os.path.join(tmp, "pred") + "/", os.path.join(tmp, "out") + "/"
+    os.makedirs(pred)
+    os.makedirs(out)
+    P = Pipeline(fa, pred, case, case == "both_iso", False, 3, 5, 5000, None, 30, False, False, "CWD", model_dir=mdir)
+    P()
+    assert [r.id for r in P.sequence] == ref["contigs"]
+    for c in fx.CODES:      # the engine's GFFs against gmhmmp2's
+        want = fx.xz_text(f"gca_trained_{c}.gff.xz") if case == "gca" else _both_gff(c)
+        assert fx.gff_gene_lines(open(f"{pred}mgm_{c}_{case}.gff").read()) == fx.gff_gene_lines(want)
+    if case == "both_iso":
+        assert [l.tolist() for l in P.genome_label] == ref["labels"]
+        assert [u.tolist() for u in P.updated_genome_labels] == ref["updated"]
+        assert [np.round(s, 2).tolist() for s in P.logodd_scores] == ref["scores"]
+        assert {k: [list(t) for t in v] for k, v in P.confident_1.items()} == ref["confident_1"]
+        assert {k: [list(t) for t in v] for k, v in P.confident_2.items()} == ref["confident_2"]
+    else:
+        assert P.genome_label == ref["file_label"]
+        assert [round(float(df["logodd"].sum()), 2) for df in P.label_to_gene_coords.values()] == ref["file_sums"]
+    Results(P, case, pred, fa, out, datetime.datetime(2026, 1, 1, 12, 0, 0), False, False, False, False, "CWD")()
+    golden = fx.xz_text(f"ex_{case}.gff.xz").split("\n")
+    mine = fx.strip_dates(open(f"{out}{case}.gff").read()).split("\n")
+    assert len(golden) == len(mine)
+    for g, m in zip(golden, mine):
+        if g.startswith("# File with"):
+            assert m.split(":")[0] == g.split(":")[0]
+            continue
+        assert g == m
+    assert open(f"{out}{case}.tab").read() == fx.xz_text(f"ex_{case}.tab.xz")
+    assert open(f"{out}{case}_stats.tab").read() == fx.xz_text(f"ex_{case}_stats.tab.xz")

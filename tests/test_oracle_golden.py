@@ -44,6 +44,20 @@ def test_phage2_trained_models(code, tmpdir):
 
 
 @pytest.mark.parametrize("code", fx.CODES)
+def test_gca_example_trained_models(code, tmpdir):
+    """BASELINE.json configs[2]: examples/GCA_002924505.1 (189 826 bp, AT-rich, poly-A ends) under the four trained models"""
+    from mgcod_b200.engine import Result
+    from oracle import gmhmm
+    (rid, seq), = fx.parse_fasta_text(fx.xz_text("gca.fa.xz"))
+    paths = fx.trained_models(tmpdir)
+    golden = fx.xz_text(f"gca_trained_{code}.gff.xz")
+    genes, totals = fx.genes_array_from_oracle(gmhmm.Model(paths[code]), [seq])
+    res = Result.from_genes([genes], [totals])
+    sf, mf = _golden_header_names(golden)
+    assert _written(res, 0, [rid], [len(seq)], sf, mf, code, tmpdir, "gff") == golden
+
+
+@pytest.mark.parametrize("code", fx.CODES)
 def test_synthetic_parametric_models(code, tmpdir):
     from mgcod_b200.engine import Result
     from oracle import gmhmm
