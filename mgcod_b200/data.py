@@ -22,6 +22,18 @@ from .synth import read_fasta
 GFF_COLUMNS = ["sequence", "source", "feature", "start", "end", "logodd", "strand", "phase", "attributes"]
 
 
+def rows_by_contig(df) -> dict:
+    """contig id -> positions of its rows in ``df`` (frame order), found in one pass: the reference filters the whole frame
+    with ``df[df.contig == id]`` once per contig, which is quadratic for a metagenome"""
+    return df.groupby("contig", sort=False).indices if len(df) else {}
+
+
+def contig_rows(df, index: dict, contig):
+    """the rows of one contig (what ``df[df.contig == contig]`` returns), through :func:`rows_by_contig`"""
+    pos = index.get(contig)
+    return df.iloc[:0] if pos is None else df.iloc[pos]
+
+
 class Record:
     """The slice of Biopython's SeqRecord that Mgcod touches: ``id``, ``description``, ``seq``, ``len()``.
     ``seq`` may be given as a uint8 view into a :class:`Fasta` buffer; it is decoded to ``str`` on first use."""

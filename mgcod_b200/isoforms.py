@@ -30,6 +30,7 @@ import numpy as np
 import pandas as pd
 
 from . import labels as L
+from .data import contig_rows, rows_by_contig
 
 
 def _rest(attributes: str) -> str:
@@ -387,17 +388,21 @@ def compare_sets_of_predicted_genes(P):
     if P.verbose:
         print(f"Comparing sets of predicted genes in {P.species}")
     columns = list(P.label_to_gene_coords[0].columns.values)
-    by_contig = {lab: dict(tuple(df.groupby("contig", sort=False))) for lab, df in P.label_to_gene_coords.items()}
+    index = {lab: rows_by_contig(df) for lab, df in P.label_to_gene_coords.items()}
     gene_labels_to_gcode = {}
     compared: list[pd.DataFrame] = []
+    single: dict[int, list] = {}
     with_isoforms: list[dict] = []
     for n, rec in enumerate(P.sequence):
         labs = np.unique(P.updated_genome_labels[n])
         if labs.shape[0] == 1:
-            # ref: every contig's genes of that model, not only this contig's; and nothing for the isoform table
-            coords = P.label_to_gene_coords[int(labs[0])].copy()
-            coords["updated_gene_label"] = 1
-            compared.append(coords)
+            # Nothing goes to the isoform table (the reference's append to it is commented out, bin/pipeline.py:577), so the
+            # final GFF of a mixed input lists only the contigs with a switch.  One deliberate difference in the plain
+            # table, which nothing downstream reads: the reference appends the model's genes of EVERY contig here
+            # (no contig filter, :574-576) — contigs x genes rows for a metagenome; this keeps the contig's own genes.
+            pos = index[int(labs[0])].get(rec.id)
+            if pos is not None:
+                single.setdefault(int(labs[0]), []).append((n, pos))     # taken from the model's table in one go below
             gene_labels_to_gcode[rec.id] = {1: P.label_to_gcode[int(labs[0])]}
             continue
         label_1, label_2 = int(labs[0]), int(labs[1])
@@ -407,9 +412,8 @@ def compare_sets_of_predicted_genes(P):
         if P.verbose:
             print(msg)
         gene_labels_to_gcode[rec.id] = {1: str(code_1), 2: str(code_2), 3: f"{code_1}_{code_2}"}
-        empty = P.label_to_gene_coords[label_1].iloc[:0]
-        S1 = _GeneSet(by_contig[label_1].get(rec.id, empty))
-        S2 = _GeneSet(by_contig[label_2].get(rec.id, empty))
+        S1 = _GeneSet(contig_rows(P.label_to_gene_coords[label_1], index[label_1], rec.id))
+        S2 = _GeneSet(contig_rows(P.label_to_gene_coords[label_2], index[label_2], rec.id))
         cur, iso = compare_contig(S1, S2, code_1, code_2, P.tolerance, rec.seq)
         # ref: DataFrame.sort_values('start') on an object column = numpy's quicksort over Python ints; rows with equal
         # starts (an isoform pair's two genes) come out in that sort's order, and the smoothing below sees them so
@@ -420,12 +424,22 @@ def compare_sets_of_predicted_genes(P):
                                                  P.consecutive_gene_labels, allow_multiple_labels=True)
         frame = pd.DataFrame(cur, columns=columns + ["gene_label"])
         frame["updated_gene_label"] = updated
+        frame["_block"] = n
         compared.append(frame)
         with_isoforms.extend(iso)
         msg = f"Identified {sum(1 for r in iso if r['logodd'] == '.')} possible isoforms in {rec.id} in {P.species}"
         logging.info(msg)
         if P.verbose:
             print(msg)
-    coords = pd.concat(compared, sort=True) if compared else pd.DataFrame(columns=columns)
+    for lab, pieces in single.items():
+        frame = P.label_to_gene_coords[lab].iloc[np.concatenate([pos for _, pos in pieces])].copy()
+        frame["updated_gene_label"] = 1
+        frame["_block"] = np.concatenate([np.full(len(pos), n, dtype=np.int64) for n, pos in pieces])
+        compared.append(frame)
+    if compared:       # one block per contig, in contig order
+        coords = pd.concat(compared, sort=True)
+        coords = coords.iloc[np.argsort(coords["_block"].values, kind="stable")].drop(columns="_block")
+    else:
+        coords = pd.DataFrame(columns=columns)
     coords_w_isoforms = pd.DataFrame(with_isoforms, columns=columns + ["gene_label"])
     return coords, gene_labels_to_gcode, coords_w_isoforms

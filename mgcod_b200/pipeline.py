@@ -23,7 +23,7 @@ import numpy as np
 
 from . import isoforms as iso_compare
 from . import labels as L
-from .data import Data
+from .data import Data, rows_by_contig
 from .engine import MGCOD_CODES
 
 
@@ -156,11 +156,16 @@ class Pipeline:
         if self.verbose:
             print(f"Segmenting genome of {self.species}")
         conf_1, conf_2, seg_labels = {}, {}, {}
+        index = {lab: rows_by_contig(df) for lab, df in self.label_to_gene_coords.items()}
+        cols = {lab: (df.start.values, df.end.values, np.where(df.strand.values == "+", 1, -1))
+                for lab, df in self.label_to_gene_coords.items()}
+        none = np.zeros(0, dtype=np.int64)
         for k, seq in enumerate(self.sequence):
             genes = {}
-            for lab, df in self.label_to_gene_coords.items():
-                d = df[df.contig == seq.id]
-                genes[lab] = (d.start.values, d.end.values, np.where(d.strand.values == "+", 1, -1))
+            if np.unique(self.updated_genome_labels[k]).shape[0] > 1:      # genes matter only where the label changes
+                for lab in self.label_to_gene_coords:
+                    pos = index[lab].get(seq.id, none)
+                    genes[lab] = tuple(c[pos] for c in cols[lab])
             c1, c2, codes = L.segment_contig(self.updated_genome_labels[k], len(seq), L.resolve_stride(self.stride, len(seq)),
                                              self.window_size, genes, self.label_to_gcode)
             conf_1[seq.id], conf_2[seq.id], seg_labels[seq.id] = c1, c2, codes

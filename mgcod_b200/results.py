@@ -26,6 +26,7 @@ import warnings
 import numpy as np
 import pandas as pd
 
+from .data import contig_rows, rows_by_contig
 from .engine import GENE_DTYPE, MGCOD_CODES, pack_sequences
 
 VERSION_BANNER = "GeneMark.hmm-2 version 1.17"   # line 2 of the binary's usage text (bin/results.py:185)
@@ -66,7 +67,7 @@ class Results:
         self.save_results()
         # number of recodings into the GFF attributes, row i <- stop_recodings[i] (bin/results.py:57-75)
         coords = self.results.coords_w_isoforms
-        attributes = coords.attributes.values.copy()
+        attributes = coords.attributes.to_numpy(dtype=object).copy()     # not the arrow-backed array: item assignment on it copies
         coords["gene_id"] = [float(a.split(";")[0].split(" ")[1]) for a in attributes]
         logodd = coords.logodd.values
         for i in range(len(attributes)):
@@ -95,8 +96,9 @@ class Results:
         engine, file_ids = P.data.ensure_resident()
         index_of = {rid: i for i, rid in enumerate(file_ids)}
         per_contig = []          # rows of each contig in the order the reference visits them
+        index = rows_by_contig(coords)
         for n in range(P.nr_contigs):
-            cur = coords[coords.contig == P.sequence[n].id]
+            cur = contig_rows(coords, index, P.sequence[n].id)
             cur = cur[cur.logodd != "."].reset_index(drop=True)
             per_contig.append(cur)
         genes = np.zeros(sum(len(c) for c in per_contig), dtype=GENE_DTYPE)
@@ -202,6 +204,7 @@ class Results:
         table = _Table()
         level_1 = [seq.id for seq in P.sequence]
         coords_all = P.coords_w_isoforms
+        index = rows_by_contig(coords_all)
         for i, contig in enumerate(level_1):
             g = P.gene_label_to_gcode[contig]
             if i == 0:
@@ -210,7 +213,7 @@ class Results:
                                 "Nr isoforms", "Total gene count"):
                         table.add_row((c, key))
             segments = sorted(P.confident_1[contig] + P.confident_2[contig])
-            coords = coords_all[coords_all.contig == contig]
+            coords = contig_rows(coords_all, index, contig)
             if len(g) == 1:
                 table.set((contig, "Coordinates in bp"), "Sequence", str(segments[0]))
                 table.set((contig, "Major genetic code"), "Sequence", g[1])
@@ -276,12 +279,13 @@ class Results:
             out.write(f"# File with MetaGeneMark parameters: {parameters}\n")
             out.write(f"# translation table: {', '.join(tables)}\n")
             out.write(f"# output date start: {self.date.strftime('%a %b %d %Y %H:%M:%S')}\n")
+            index = rows_by_contig(coords)
             for n in range(P.nr_contigs):
-                size = len(P.sequence[n].seq)
-                cur = coords[coords.contig == P.sequence[n].id].copy()
-                cur = cur.loc[:, columns]
-                if cur.shape[0] == 0:
+                size = len(P.sequence[n])
+                if P.sequence[n].id not in index:       # no genes on this contig: no block in the file
                     continue
+                cur = contig_rows(coords, index, P.sequence[n].id).copy()
+                cur = cur.loc[:, columns]
                 cur.reset_index(drop=True, inplace=True)
                 accession = cur.iloc[0, 0]
                 out.write("\n")
@@ -318,10 +322,11 @@ class _Table:
     """The cells of the reference's classification DataFrame in the order it creates them (bin/results.py:101-157)."""
 
     def __init__(self):
-        self.rows, self.cols, self.kind, self.cell = [], [], {}, {}
+        self.rows, self.cols, self.kind, self.cell, self._known = [], [], {}, {}, set()
 
     def add_row(self, key):
-        if key not in self.rows:
+        if key not in self._known:
+            self._known.add(key)
             self.rows.append(key)
 
     def set(self, row, col, value):
