@@ -403,6 +403,22 @@ def main():
                         "genes_written": int(sum(r.num_genes(mi) for mi in range(engine.n_models)))}
             del r
             f.close()
+            # the whole command line on the same file, isoform mode: FASTA -> decode -> four GFFs -> window labels -> label
+            # smoothing -> isoform comparison of contigs with a switch -> .gff / .tab / _stats.tab  (python -m mgcod_b200.cli)
+            try:
+                from mgcod_b200 import cli
+                cli_out = os.path.join(workdir, "cli_out") + "/"
+                t4 = time.perf_counter()
+                rc = cli.main(["-i", fa, "-p", os.path.join(workdir, "cli_pred") + "/", "-o", cli_out, "--isoforms",
+                               "--model_dir", os.path.dirname(model_paths[0]), "--device", str(local),
+                               "--logfile", os.path.join(workdir, "log", "cli.log")])
+                t5 = time.perf_counter()
+                tab = open(os.path.join(cli_out, "sample.tab")).read().split("\n") if rc == 0 else []
+                file_e2e["cli_isoforms"] = {"seconds": t5 - t4, "rc": rc, "tab_rows": len(tab),
+                                            "windows_per_s": float(np.sum(np.ceil(lens_f / np.where(lens_f > 100000, 5000, 2500)))) / (t5 - t4),
+                                            "genes_in_final_gff": sum(1 for l in open(os.path.join(cli_out, "sample.gff")) if not l.startswith("#") and l.strip()) if rc == 0 else 0}
+            except Exception as ex:      # a host-side failure here must not take the headline numbers down with it
+                file_e2e["cli_isoforms"] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
 
         # ---- latency of the reference's own example (BASELINE.json configs[0]/[1]: phage2, 173 747 bp, one contig) ----
         small = None
