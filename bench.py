@@ -41,7 +41,7 @@ SEED = 20260101
 # DRAM bytes of ONE k_walk launch on the default 1 Gbp x 4 models workload, from the committed ncu capture (43.82 GB read + 4.65 GB
 # written; the algorithmic bytes are 12.4 GB: items of one section pair are scattered over the genome, so plane and record
 # sectors are fetched several times -- DESIGN.md section 4).
-WALK_DRAM_BYTES_1GBP = 48.47e9
+WALK_DRAM_BYTES_1GBP = 19.83e9
 METRIC = "bp_x_models_per_s_decoded"
 UNIT = "bp*models/s"
 
@@ -505,7 +505,7 @@ def main():
                 "roofline": {"kernel": "k_walk", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": WALK_DRAM_BYTES_1GBP if default_workload else None,
                              "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one k_walk launch on this "
-                                               "workload (profiles/r1f_top_kernels_1Gbp.txt)" if default_workload else None,
+                                               "workload (profiles/r1j_k_walk_1Gbp.txt)" if default_workload else None,
                              "peak_source": peak_src,
                              "kernel_ms_per_launch": score_ms, "algorithmic_bytes_per_launch": alg_bytes},
                 # SURVEY.md section 8(d) asks for the second candidate roof as well: ~26 simple ops (k-mer index updates, table

@@ -67,6 +67,26 @@ struct __align__(16) ItemRec {
     int32_t last;       // index (within the ORF) of the start of this pair closest to the stop
 };
 
+// Walk items are ordered by (position tile, section pair, length class): all items of a tile are walked before the next
+// tile, so the plane words of a tile (both strands, lo + hi = 16 B per word) stay in the 126 MB L2 while every section
+// pair and length class passes over them.  A tile is WALK_TILE_WORDS words (32 MB of planes; 16 tiles for 1 Gbp) unless that would give more
+// than WALK_TILES_MAX tiles; a small input is one tile.
+constexpr int WALK_TILES_MAX = 32;
+constexpr long long WALK_TILE_WORDS = 2ll << 20;
+struct WalkTiles {
+    int n;              // tiles in this batch
+    long long words;    // words per tile
+};
+inline WalkTiles walk_tiles_for(long long W) {
+    WalkTiles t;
+    long long n = (W + WALK_TILE_WORDS - 1) / WALK_TILE_WORDS;
+    if (n < 1) n = 1;
+    if (n > WALK_TILES_MAX) n = WALK_TILES_MAX;
+    t.n = (int)n;
+    t.words = (W + n - 1) / n;
+    if (t.words < 1) t.words = 1;
+    return t;
+}
 constexpr int WALK_CLASSES = 64;   // length classes of 32 nt; the last one collects everything longer
 constexpr int WALK_UNIT = 256;     // threads per CTA of k_walk
 constexpr int WALK_CHUNK = 2048;   // items per work unit (one section pair; warps take 32 at a time)
@@ -126,6 +146,8 @@ struct Planes {
     const int *dflags;        // device flags written by k_pack: [0] letter outside the IUPAC alphabet, [1] any ambiguous letter
     const uint8_t *cflags;    // per contig slot: bit0 = its right edge is the end of the record (not a gap)
     int64_t W;                // words per strand region
+    int n_tiles;              // walk_tiles_for(W): position tiles of the walk-item order
+    long long tile_words;
 };
 
 __device__ __forceinline__ uint32_t frame_pattern(int r) {

@@ -413,7 +413,7 @@ void ensure_batch_buffers(mgc_engine *e) {
         p.sums.ensure((size_t)e->cap_starts * 32);
         p.items.ensure((size_t)e->cap_items * sizeof(ItemRec));
         p.items_sorted.ensure((size_t)e->cap_items * sizeof(ItemRec));
-        const size_t nkeys = (size_t)102 * WALK_CLASSES;   // at most 101 distinct section pairs
+        const size_t nkeys = (size_t)102 * WALK_CLASSES * WALK_TILES_MAX;   // at most 101 distinct section pairs, per position tile
         p.hist.ensure((nkeys + 8) * 4);
         p.item_off.ensure((nkeys + 8) * 4);
         p.unit_off.ensure((nkeys + 8) * 4);
@@ -666,6 +666,7 @@ mgc_result *run_pipeline(mgc_engine *e, bool *amb_out) {
     pl.cflags = e->cflags.as<uint8_t>();
     pl.codon = e->codon.as<uint32_t>();
     pl.W = W;
+    { const WalkTiles wt = walk_tiles_for(W); pl.n_tiles = wt.n; pl.tile_words = wt.words; }
     launch_codon_planes(pl, e->cwoff.as<int64_t>(), e->clen.as<int32_t>(), e->grp2contig.as<int32_t>(), e->codon.as<uint32_t>(), st);
     launches += 1;
     launches += launch_laststop(pl, e->cwoff.as<int64_t>(), e->clen.as<int32_t>(), e->grp2contig.as<int32_t>(),
@@ -682,7 +683,7 @@ mgc_result *run_pipeline(mgc_engine *e, bool *amb_out) {
                                 e->n_sm, st);
     launches += launch_item_sort(e->t_items.as<const ItemRec *>(), e->t_items_sorted.as<ItemRec *>(), e->t_hist.as<uint32_t *>(),
                                  e->t_item_off.as<uint32_t *>(), e->t_unit_off.as<uint32_t *>(), e->d_models.as<DevModel>(), M,
-                                 e->unit_totals.as<uint32_t>(), e->counters.as<unsigned long long>(), e->cap_items, e->n_sm, st);
+                                 e->unit_totals.as<uint32_t>(), e->counters.as<unsigned long long>(), e->cap_items, pl.n_tiles, e->n_sm, st);
     CUDA_TRY(cudaPeekAtLastError());
     CUDA_TRY(cudaPeekAtLastError());   // a failed launch must not go unnoticed until the end
     CUDA_TRY(cudaEventRecord(e->ev[8], st));
@@ -1258,6 +1259,7 @@ int64_t mgc_recoded_stops(mgc_engine *e, const mgc_gene *genes, int64_t n_genes,
         Planes pl;
         pl.lo = e->lo.as<uint32_t>(); pl.hi = e->hi.as<uint32_t>(); pl.nm = e->nm.as<uint32_t>(); pl.npre = e->ncount.as<uint32_t>();
         pl.dflags = e->flags.as<int>(); pl.cflags = e->cflags.as<uint8_t>(); pl.codon = e->codon.as<uint32_t>(); pl.W = e->W;
+        { const WalkTiles wt = walk_tiles_for(e->W); pl.n_tiles = wt.n; pl.tile_words = wt.words; }
         if (n_genes) CUDA_TRY(cudaMemcpyAsync(d_refs.p, refs.data(), (size_t)n_genes * sizeof(GeneRef), cudaMemcpyHostToDevice, st));
         launch_recoded_stops(pl, e->cwoff.as<int64_t>(), e->clen.as<int32_t>(), d_refs.as<GeneRef>(), n_genes, d_counts.as<int32_t>(), nullptr,
                              nullptr, false, e->n_sm, st);

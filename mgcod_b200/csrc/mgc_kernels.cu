@@ -880,6 +880,7 @@ __global__ void __launch_bounds__(256) k_start_link(Planes pl, const int64_t *__
         const bool from_first = (rec.sf & 0x200u) != 0;
         auto full_of = [&](uint32_t sraw) { return (int)(sraw & 0x7fffffffu) + (((sraw >> 31) && from_first) ? 0 : 3) + kc; };
         const uint32_t pair = me.pg & 0xffffu;
+        const int npair = dm.npair;
         if (k < (int64_t)n_starts) {
             my_full = full_of(me.sraw);
             valid = j < n && my_full <= t - 1;   // starts without a full-order region are not part of any walk
@@ -941,7 +942,10 @@ __global__ void __launch_bounds__(256) k_start_link(Planes pl, const int64_t *__
                 if (na) it.orf |= 0x80000000u;
             }
             it.lo_pos = lo_pos;
-            it.key = (uint32_t)((int)pair * WALK_CLASSES + (WALK_CLASSES - 1 - min(ext >> 5, WALK_CLASSES - 1)));
+            // position tile first (see WALK_TILES), then section pair, then length class
+            const long long tile_raw = (long long)(cwoff[rec.contig] + (t >> 5)) / pl.tile_words;
+            const int tile = tile_raw < pl.n_tiles - 1 ? (int)tile_raw : pl.n_tiles - 1;
+            it.key = (uint32_t)((tile * npair + (int)pair) * WALK_CLASSES + (WALK_CLASSES - 1 - min(ext >> 5, WALK_CLASSES - 1)));
             it.last = j;
             emit = true;
         }
@@ -976,10 +980,10 @@ __global__ void __launch_bounds__(256) k_start_link(Planes pl, const int64_t *__
 // one block per model: item offsets per key (exclusive scan of the histogram, which is turned into the scatter
 // cursor); work units = chunks of WALK_CHUNK items of one section pair, with their prefix over pairs
 __global__ void __launch_bounds__(1024) k_item_plan(uint32_t *const *hist_m, uint32_t *const *item_off_m, uint32_t *const *unit_off_m,
-                                                    const DevModel *__restrict__ models, uint32_t *unit_totals, unsigned long long *counters_m) {
+                                                    const DevModel *__restrict__ models, uint32_t *unit_totals, unsigned long long *counters_m, int n_tiles) {
     __shared__ uint32_t carry_i;
     const int mi = blockIdx.x;
-    const int npair = models[mi].npair, nkeys = npair * WALK_CLASSES;
+    const int npair = models[mi].npair * n_tiles, nkeys = npair * WALK_CLASSES;   // (tile, pair) combinations
     uint32_t *hist = hist_m[mi], *ioff = item_off_m[mi], *uoff = unit_off_m[mi];
     if (threadIdx.x == 0) carry_i = 0;
     __syncthreads();
@@ -1065,7 +1069,7 @@ __global__ void __launch_bounds__(WALK_UNIT, 2) k_walk(Planes pl, const int64_t 
             s_model = m;
             if (m < n_models) {
                 const uint32_t *uoff = unit_off_m[m];
-                int lo = 0, hi = models[m].npair;  // last pair with uoff[pair] <= u (uoff has npair + 1 entries)
+                int lo = 0, hi = models[m].npair * pl.n_tiles;  // last (tile, pair) with uoff[.] <= u (uoff has one more entry)
                 while (lo + 1 < hi) {
                     const int mid = (lo + hi) >> 1;
                     if (uoff[mid] <= u) lo = mid; else hi = mid;
@@ -1082,7 +1086,7 @@ __global__ void __launch_bounds__(WALK_UNIT, 2) k_walk(Planes pl, const int64_t 
         const int mi = s_model;
         if (mi >= n_models) break;
         const DevModel &dm = models[mi];
-        const int pair = s_pair;
+        const int pair = s_pair % dm.npair;   // s_pair counts (tile, pair) combinations, tile-major
         const int kc = dm.kc, kn = dm.kn, nfull = dm.nfull;
         const double2 *gq = dm.wtab + (size_t)pair * dm.wtab_n16;
         if (SMEM_TABLE && (mi != loaded_model || pair != loaded_pair)) {
@@ -2157,8 +2161,8 @@ int launch_orf_prep(Planes pl, const uint32_t *gcpre, const int64_t *cwoff, cons
 
 int launch_item_sort(const ItemRec *const *items_m, ItemRec *const *sorted_m, uint32_t *const *hist_m, uint32_t *const *item_off_m,
                      uint32_t *const *unit_off_m, const DevModel *models, int n_models, uint32_t *unit_totals,
-                     const unsigned long long *counters_m, uint32_t cap_items, int n_sm, cudaStream_t st) {
-    k_item_plan<<<n_models, 1024, 0, st>>>(hist_m, item_off_m, unit_off_m, models, unit_totals, const_cast<unsigned long long *>(counters_m));
+                     const unsigned long long *counters_m, uint32_t cap_items, int n_tiles, int n_sm, cudaStream_t st) {
+    k_item_plan<<<n_models, 1024, 0, st>>>(hist_m, item_off_m, unit_off_m, models, unit_totals, const_cast<unsigned long long *>(counters_m), n_tiles);
     dim3 grid(n_sm * 4, n_models);
     k_item_scatter<<<grid, 256, 0, st>>>(items_m, sorted_m, hist_m, counters_m, cap_items);
     return 2;

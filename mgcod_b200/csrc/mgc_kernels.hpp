@@ -40,7 +40,7 @@ int launch_orf_prep(Planes pl, const uint32_t *gcpre, const int64_t *cwoff, cons
                     int n_sm, cudaStream_t st);
 int launch_item_sort(const ItemRec *const *items_m, ItemRec *const *sorted_m, uint32_t *const *hist_m, uint32_t *const *item_off_m,
                      uint32_t *const *unit_off_m, const DevModel *models, int n_models, uint32_t *unit_totals,
-                     const unsigned long long *counters_m, uint32_t cap_items, int n_sm, cudaStream_t st);
+                     const unsigned long long *counters_m, uint32_t cap_items, int n_tiles, int n_sm, cudaStream_t st);
 int launch_walk(Planes pl, const int64_t *cwoff, const DevModel *models, int n_models, int max_cod_order, int max_non_order,
                 const OrfRec *const *orfs_m,
                 const StartRec *const *starts_m, const ItemRec *const *items_m, const uint32_t *const *item_off_m,
