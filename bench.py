@@ -38,9 +38,9 @@ sys.path.insert(0, ROOT)
 
 CODES = (11, 4, 15, 101)
 SEED = 20260101
-# DRAM bytes of ONE k_walk launch on the default 1 Gbp x 4 models workload, from the committed ncu capture (43.82 GB read + 4.65 GB
-# written; the algorithmic bytes are 12.4 GB: items of one section pair are scattered over the genome, so plane and record
-# sectors are fetched several times -- DESIGN.md section 4).
+# DRAM bytes of ONE k_walk launch on the default 1 Gbp x 4 models workload, from the committed ncu capture
+# profiles/r1j_k_walk_1Gbp.txt (15.19 GB read + 4.64 GB written; the algorithmic bytes are 12.4 GB, the rest is 32-byte
+# sector granularity on 16-byte records and plane groups -- DESIGN.md section 4; 48.5 GB before the tile-major item order).
 WALK_DRAM_BYTES_1GBP = 19.83e9
 METRIC = "bp_x_models_per_s_decoded"
 UNIT = "bp*models/s"
