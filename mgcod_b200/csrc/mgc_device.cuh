@@ -63,7 +63,7 @@ struct __align__(16) StartRec {
 struct __align__(16) ItemRec {
     uint32_t orf;
     int32_t lo_pos;     // lowest position of the walk (first full-order position of the farthest start of this pair)
-    uint32_t key;       // pair * WALK_CLASSES + length class (descending)
+    uint32_t key;       // (tile * npair + pair) * WALK_CLASSES + length class (descending)
     int32_t last;       // index (within the ORF) of the start of this pair closest to the stop
 };
 

@@ -10,7 +10,7 @@
 //   k_orf_find       per model: stop-delimited ORFs long enough to hold a gene and with a start codon
 //   k_orf_expand     per model: start records (position, GC bin, section pair) of every ORF, load-balanced per block
 //   k_start_link     chains the starts of an ORF that share a section pair; one walk item per chain
-//   k_item_plan / k_item_scatter   counting sort of the items by (section pair, length class)
+//   k_item_plan / k_item_scatter   counting sort of the items by (position tile, section pair, length class)
 //   k_walk           thread per item: 3-periodic Markov log-likelihood sums from the stop down, the pair's tables in shared memory
 //   k_final          per start: order ramp, duration / start / stop terms, domain choice, pruning (total > 0), bucket histogram
 //   scan + k_scatter survivors into position buckets (128 nt) -> right-end order per contig
@@ -942,7 +942,7 @@ __global__ void __launch_bounds__(256) k_start_link(Planes pl, const int64_t *__
                 if (na) it.orf |= 0x80000000u;
             }
             it.lo_pos = lo_pos;
-            // position tile first (see WALK_TILES), then section pair, then length class
+            // position tile first (see WALK_TILE_WORDS), then section pair, then length class
             const long long tile_raw = (long long)(cwoff[rec.contig] + (t >> 5)) / pl.tile_words;
             const int tile = tile_raw < pl.n_tiles - 1 ? (int)tile_raw : pl.n_tiles - 1;
             it.key = (uint32_t)((tile * npair + (int)pair) * WALK_CLASSES + (WALK_CLASSES - 1 - min(ext >> 5, WALK_CLASSES - 1)));
