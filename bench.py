@@ -351,8 +351,8 @@ def main():
         # ---- second shape of SURVEY.md 8(d): 200k contigs of 5 kb (launch/overhead behaviour) ----
         shape2 = None
         if world == 1 and not os.environ.get("MGCOD_BENCH_SKIP_SHAPE2"):
-            buf2, offs2, _ = synth_metagenome(SEED + 1000, args.total_bp, min_len=5000, max_len=5000, threads=min(cores, 32),
-                                              out=pinned.numpy())
+            # its own host buffer: `buf` (a view of the pinned block) is still needed by the file and CPU-baseline legs below
+            buf2, offs2, _ = synth_metagenome(SEED + 1000, args.total_bp, min_len=5000, max_len=5000, threads=min(cores, 32))
             engine.upload(buf2, offs2)
             for _ in range(2):
                 del_me = engine.decode_resident()
@@ -366,6 +366,7 @@ def main():
             dt2 = (time.perf_counter() - t0) / args.steps
             shape2 = {"workload": f"{len(offs2) - 1} contigs x 5 kb, same generator", "ms_per_step": 1e3 * dt2,
                       "value": int(offs2[-1]) * engine.n_models / dt2, "unit": UNIT, "resident": True}
+            del buf2
 
         # ---- file to files on a 100 Mbp slice: native FASTA read -> decode -> four GFF files (SURVEY.md 8d "also report") ----
         file_e2e = None
@@ -409,7 +410,6 @@ def main():
             # other than the two most frequent ones are noise, bin/pipeline.py:1084), and a contig made of noise labels only
             # stops the reference's smoothing (and this mirror) with an IndexError.
             try:
-                from mgcod_b200 import cli
                 cli_out = os.path.join(workdir, "cli_out") + "/"
                 fa = os.path.join(workdir, "sample2.fasta")
                 two = [i for i in range(nrec) if int(truth[i]) in (11, 15)]
@@ -421,17 +421,35 @@ def main():
                             fh.write(rec[k:k + (1 << 20)].tobytes())
                         fh.write(b"\n")
                 lens_f = np.array([offs[i + 1] - offs[i] for i in two], dtype=np.int64)
+                # what python -m mgcod_b200.cli does (mgcod_b200/cli.py main), kept in reach for the diagnostics below
+                import datetime
+                from mgcod_b200.pipeline import Pipeline
+                from mgcod_b200.results import Results
+                pred_dir = os.path.join(workdir, "cli_pred") + "/"
+                os.makedirs(pred_dir, exist_ok=True)
+                os.makedirs(cli_out, exist_ok=True)
                 t4 = time.perf_counter()
-                rc = cli.main(["-i", fa, "-p", os.path.join(workdir, "cli_pred") + "/", "-o", cli_out, "--isoforms",
-                               "--model_dir", os.path.dirname(model_paths[0]), "--device", str(local),
-                               "--logfile", os.path.join(workdir, "log", "cli.log")])
+                P = Pipeline(fa, pred_dir, "sample2", True, False, 3, 5, 5000, None, 30, False, False, workdir,
+                             model_dir=os.path.dirname(model_paths[0]), device=local)
+                try:
+                    P()
+                except IndexError as ex:
+                    labs = P.genome_label if isinstance(P.genome_label, list) else []
+                    allab = np.concatenate(labs) if labs else np.zeros(0, dtype=np.int64)
+                    hist_l = np.bincount(allab, minlength=4)
+                    noise = set(np.argsort(hist_l)[::-1][2:].tolist())
+                    bad = [(k, P.sequence[k].id, len(P.sequence[k]), l.tolist()) for k, l in enumerate(labs)
+                           if len(l) and all(int(x) in noise for x in l)]
+                    raise IndexError(f"{ex}; label histogram {hist_l.tolist()}, contigs of noise labels only: {bad[:3]}")
+                Results(P, "sample2", pred_dir, fa, cli_out, datetime.datetime.now(), False, False, False, False, workdir)()
+                rc = 0
                 t5 = time.perf_counter()
                 tab = open(os.path.join(cli_out, "sample2.tab")).read().split("\n") if rc == 0 else []
                 file_e2e["cli_isoforms"] = {"seconds": t5 - t4, "rc": rc, "tab_rows": len(tab), "contigs": len(two), "bp": int(lens_f.sum()),
                                             "windows_per_s": float(np.sum(np.ceil(lens_f / np.where(lens_f > 100000, 5000, 2500)))) / (t5 - t4),
-                                            "genes_in_final_gff": sum(1 for l in open(os.path.join(cli_out, "sample2.gff")) if not l.startswith("#") and l.strip()) if rc == 0 else 0}
+                                            "genes_in_final_gff": sum(1 for l in open(os.path.join(cli_out, "sample2.gff")) if not l.startswith("#") and l.strip())}
             except Exception as ex:      # a host-side failure here must not take the headline numbers down with it
-                file_e2e["cli_isoforms"] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
+                file_e2e["cli_isoforms"] = {"error": f"{type(ex).__name__}: {ex}"[:900]}
 
         # ---- latency of the reference's own example (BASELINE.json configs[0]/[1]: phage2, 173 747 bp, one contig) ----
         small = None

@@ -77,9 +77,10 @@ struct WalkTiles {
     int n;              // tiles in this batch
     long long words;    // words per tile
 };
-inline WalkTiles walk_tiles_for(long long W) {
+inline WalkTiles walk_tiles_for(long long W, long long tile_words = WALK_TILE_WORDS) {
     WalkTiles t;
-    long long n = (W + WALK_TILE_WORDS - 1) / WALK_TILE_WORDS;
+    if (tile_words < 1) tile_words = WALK_TILE_WORDS;
+    long long n = (W + tile_words - 1) / tile_words;
     if (n < 1) n = 1;
     if (n > WALK_TILES_MAX) n = WALK_TILES_MAX;
     t.n = (int)n;

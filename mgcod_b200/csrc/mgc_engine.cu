@@ -30,6 +30,13 @@ struct mgc_model {
 // Page-locked host blocks are expensive to create (cudaHostAlloc pins pages), so results borrow them from a
 // pool owned jointly by the engine and its outstanding results.
 // completion of a result's device->host copy (shared by the result, the pool's deferred releases and the engine)
+// Test knob: MGCOD_B200_WALK_TILE_WORDS=<words> shrinks the position tiles of the walk-item order so that a small input
+// runs through the multi-tile code (results do not depend on the tiling).
+static long long walk_tile_words_setting() {
+    const char *s = std::getenv("MGCOD_B200_WALK_TILE_WORDS");
+    return s ? std::atoll(s) : WALK_TILE_WORDS;
+}
+
 struct Ready {
     cudaEvent_t ev = nullptr;
     Ready() { cudaEventCreateWithFlags(&ev, cudaEventDisableTiming); }
@@ -666,7 +673,7 @@ mgc_result *run_pipeline(mgc_engine *e, bool *amb_out) {
     pl.cflags = e->cflags.as<uint8_t>();
     pl.codon = e->codon.as<uint32_t>();
     pl.W = W;
-    { const WalkTiles wt = walk_tiles_for(W); pl.n_tiles = wt.n; pl.tile_words = wt.words; }
+    { const WalkTiles wt = walk_tiles_for(W, walk_tile_words_setting()); pl.n_tiles = wt.n; pl.tile_words = wt.words; }
     launch_codon_planes(pl, e->cwoff.as<int64_t>(), e->clen.as<int32_t>(), e->grp2contig.as<int32_t>(), e->codon.as<uint32_t>(), st);
     launches += 1;
     launches += launch_laststop(pl, e->cwoff.as<int64_t>(), e->clen.as<int32_t>(), e->grp2contig.as<int32_t>(),
@@ -1259,7 +1266,7 @@ int64_t mgc_recoded_stops(mgc_engine *e, const mgc_gene *genes, int64_t n_genes,
         Planes pl;
         pl.lo = e->lo.as<uint32_t>(); pl.hi = e->hi.as<uint32_t>(); pl.nm = e->nm.as<uint32_t>(); pl.npre = e->ncount.as<uint32_t>();
         pl.dflags = e->flags.as<int>(); pl.cflags = e->cflags.as<uint8_t>(); pl.codon = e->codon.as<uint32_t>(); pl.W = e->W;
-        { const WalkTiles wt = walk_tiles_for(e->W); pl.n_tiles = wt.n; pl.tile_words = wt.words; }
+        { const WalkTiles wt = walk_tiles_for(e->W, walk_tile_words_setting()); pl.n_tiles = wt.n; pl.tile_words = wt.words; }
         if (n_genes) CUDA_TRY(cudaMemcpyAsync(d_refs.p, refs.data(), (size_t)n_genes * sizeof(GeneRef), cudaMemcpyHostToDevice, st));
         launch_recoded_stops(pl, e->cwoff.as<int64_t>(), e->clen.as<int32_t>(), d_refs.as<GeneRef>(), n_genes, d_counts.as<int32_t>(), nullptr,
                              nullptr, false, e->n_sm, st);

@@ -213,3 +213,25 @@ def test_decode_large_streams_batches_and_merges(engine, tmp_path):
     many.write(2, ids, lens, "s.fa", "m.mod", 15, str(tmp_path / "many.gff"), "gff")
     strip = lambda t: "\n".join(l for l in t.split("\n") if not l.startswith("# output date"))
     assert strip(open(tmp_path / "one.gff").read()) == strip(open(tmp_path / "many.gff").read())
+
+
+def test_results_do_not_depend_on_the_walk_tiling(engine, monkeypatch):
+    """k_walk's items are ordered by (position tile, section pair, length class); a 200 Mbp batch has 4 tiles of 2 M plane
+    words, its 40 Mbp slices one each.  The genes of a contig must not depend on the batch it was decoded in."""
+    from mgcod_b200.engine import synth_metagenome
+    buf, offs, truth = synth_metagenome(77, 200_000_000, threads=8)
+    whole = engine.decode_buffer(buf, offs)
+    want = [whole.genes(m).copy() for m in range(4)]
+    tot = [whole.contig_totals(m).copy() for m in range(4)]
+    parts = engine.decode_large(buf, offs, max_bp=40_000_000)
+    for m in range(4):
+        assert np.array_equal(parts.genes(m), want[m]), m
+        np.testing.assert_array_equal(parts.contig_totals(m), tot[m])
+    # and with tiles of 4096 words (32 tiles, the cap) on a small batch
+    small_buf, small_offs = buf[:offs[40]], offs[:41]
+    ref = engine.decode_buffer(small_buf, small_offs)
+    ref_genes = [ref.genes(m).copy() for m in range(4)]
+    monkeypatch.setenv("MGCOD_B200_WALK_TILE_WORDS", "4096")
+    tiled = engine.decode_buffer(small_buf, small_offs)
+    for m in range(4):
+        assert np.array_equal(tiled.genes(m), ref_genes[m]), m
