@@ -139,9 +139,11 @@ def main():
         }
         if case == "mixed":    # the binary's predictions, so that the comparison can be tested without a GPU
             for c in G.CODES:
-                G.xz_write(f"{HERE}/iso_{case}_mgm_{c}.gff.xz", open(f"{pred}mgm_{c}_{case}.gff", "rb").read())
-        R = refres.Results(P, case, pred, fa, outd, date, False, False, False, False, cwd)
+                G.xz_write(f"{HERE}/iso_{case}_mgm_{c}.gff.xz", G.strip_dates(open(f"{pred}mgm_{c}_{case}.gff").read().replace(tmp, "TMP")).encode())
+        R = refres.Results(P, case, pred, fa, outd, date, False, False, True, False, cwd)      # -NT
         R()
+        import hashlib
+        dump["nt_sha256"] = hashlib.sha256(open(f"{outd}proteins_nt_{case}.fasta", "rb").read()).hexdigest()
         gff = open(f"{outd}{case}.gff").read().replace(tmp, "TMP")
         G.xz_write(f"{HERE}/iso_{case}.gff.xz", G.strip_dates(gff).encode())
         G.xz_write(f"{HERE}/iso_{case}.tab.xz", open(f"{outd}{case}.tab", "rb").read())

@@ -371,3 +371,50 @@ def test_reference_examples_end_to_end_on_the_gpu(case, tmp_path):
         assert g == m
     assert open(f"{out}{case}.tab").read() == fx.xz_text(f"ex_{case}.tab.xz")
     assert open(f"{out}{case}_stats.tab").read() == fx.xz_text(f"ex_{case}_stats.tab.xz")
+
+
+class FakeEngine:
+    """stands in for the CUDA engine in Results.extract_sequences: the in-frame stop scan by the host restatement, with the
+    engine's return layout (counts[g, 3], offsets[3g + 1], positions; stop order TAA, TAG, TGA)"""
+
+    def __init__(self, seqs):
+        self.seqs = seqs
+
+    def recoded_stops(self, genes):
+        from mgcod_b200.results import Results, _COMP
+        counts, offs, pos = np.zeros((len(genes), 3), dtype=np.int32), [0], []
+        for g in range(len(genes)):
+            s = self.seqs[int(genes["contig"][g])][int(genes["left"][g]) - 1:int(genes["right"][g])]
+            if genes["strand"][g] < 0:
+                s = s[::-1].translate(_COMP)
+            s = s.lower()
+            for t, stop in enumerate(("taa", "tag", "tga")):
+                hits, _ = Results.find_recoded_stops(s, stop)
+                counts[g, t] = len(hits)
+                pos.extend(hits)
+                offs.append(len(pos))
+        return counts, np.array(offs, dtype=np.int64), np.array(pos, dtype=np.int32)
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_product_results_class_with_nt_output_on_a_switch_run(case, tmp_path):
+    """the product Results class itself (extract_sequences, -NT records, attribute rewriting, all three files) with only the
+    device call replaced: the nucleotide FASTA of a switch run has the reference's digest"""
+    import datetime
+    import hashlib
+    from mgcod_b200.results import Results
+    P, ref = fake_pipeline(case)
+    P.coords, P.gene_label_to_gcode, P.coords_w_isoforms = isoforms.compare_sets_of_predicted_genes(P)
+    P.nr_contigs = len(P.sequence)
+    P.genome_label = [np.array(l) for l in ref["labels"]]
+    P.confident_1 = {k: [tuple(t) for t in v] for k, v in ref["confident_1"].items()}
+    P.confident_2 = {k: [tuple(t) for t in v] for k, v in ref["confident_2"].items()}
+    ids = [r.id for r in P.sequence]
+    P.data = types.SimpleNamespace(ensure_resident=lambda: (FakeEngine([r.seq for r in P.sequence]), ids))
+    out = str(tmp_path) + "/"
+    Results(P, case, "PRED/", f"TMP/{case}.fasta", out, datetime.datetime(2026, 1, 1, 12, 0, 0), False, False, True, False, "TMP/mgcod")()
+    assert hashlib.sha256(open(f"{out}proteins_nt_{case}.fasta", "rb").read()).hexdigest() == ref["nt_sha256"]
+    strip = lambda t: "\n".join(l for l in t.split("\n") if not l.startswith("# output date"))
+    assert open(f"{out}{case}.tab").read() == fx.xz_text(f"iso_{case}.tab.xz")
+    assert open(f"{out}{case}_stats.tab").read() == fx.xz_text(f"iso_{case}_stats.tab.xz")
+    assert strip(open(f"{out}{case}.gff").read()) == fx.xz_text(f"iso_{case}.gff.xz")
