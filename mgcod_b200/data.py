@@ -16,8 +16,7 @@ import numpy as np
 import pandas as pd
 
 from . import _lib
-from .engine import MGCOD_CODES, Engine, ModelFile, pack_sequences
-from .synth import read_fasta
+from .engine import MGCOD_CODES, Engine, ModelFile
 
 GFF_COLUMNS = ["sequence", "source", "feature", "start", "end", "logodd", "strand", "phase", "attributes"]
 

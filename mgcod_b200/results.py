@@ -24,10 +24,9 @@ import os
 import warnings
 
 import numpy as np
-import pandas as pd
 
 from .data import contig_rows, rows_by_contig
-from .engine import GENE_DTYPE, MGCOD_CODES, pack_sequences
+from .engine import GENE_DTYPE, MGCOD_CODES
 
 VERSION_BANNER = "GeneMark.hmm-2 version 1.17"   # line 2 of the binary's usage text (bin/results.py:185)
 STOPS = ("TAA", "TAG", "TGA")                      # order of mgc_recoded_stops' counts
