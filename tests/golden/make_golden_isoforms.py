@@ -75,6 +75,8 @@ def cases():
         "phage2": (phage, dict(window=5000, stride=2500, n=3, genes=5, tol=30)),
         "mixed": (mixed, dict(window=5000, stride=2500, n=3, genes=5, tol=30)),
         "phage2_t300": (phage, dict(window=5000, stride=5000, n=2, genes=3, tol=300)),
+        # two codes in the input but no contig with a switch: the isoform table stays empty
+        "two_single": (f">a15\n{seq[0:50000]}\n>b11\n{seq[106000:131000]}\n", dict(window=5000, stride=2500, n=3, genes=5, tol=30)),
     }
 
 
@@ -137,7 +139,7 @@ def main():
             "coords_w_isoforms": frame_dump(P.coords_w_isoforms, ["contig", "source", "start", "end", "strand", "logodd", "attributes",
                                                                   "gene_label"]),
         }
-        if case == "mixed":    # the binary's predictions, so that the comparison can be tested without a GPU
+        if case in ("mixed", "two_single"):    # the binary's predictions, so that the comparison can be tested without a GPU
             for c in G.CODES:
                 G.xz_write(f"{HERE}/iso_{case}_mgm_{c}.gff.xz", G.strip_dates(open(f"{pred}mgm_{c}_{case}.gff").read().replace(tmp, "TMP")).encode())
         R = refres.Results(P, case, pred, fa, outd, date, False, False, True, False, cwd)      # -NT
