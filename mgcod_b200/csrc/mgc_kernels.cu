@@ -806,7 +806,9 @@ __global__ void __launch_bounds__(EXPAND_ORFS) k_orf_expand(Planes pl, const uin
                         const int len = t + 3 - sp;
                         const int a = strand ? (L - 1 - (t + 2)) : sp, b = strand ? (L - 1 - sp) : (t + 2);
                         const int gc2 = gc2_count_fwd(pl, gcpre, w0, a, b);
-                        const int gc = (100 * gc2 + len) / (2 * len);   // round half up of 100 * (GC + N/2) / len
+                        // the binary's own arithmetic, operation for operation (no fused multiply-add): the quotient is
+                        // rounded before it is scaled, so exact .5 ties mostly go down (DESIGN.md §2 rule 2)
+                        const int gc = (int)__dadd_rn(__dmul_rn(__ddiv_rn((double)gc2, (double)(2 * len)), 100.0), 0.5);
                         StartRec sr;
                         sr.sraw = (uint32_t)sp | (virt ? 0x80000000u : 0u);
                         sr.orf = (uint32_t)(tile0 + i);

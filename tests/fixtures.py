@@ -83,3 +83,38 @@ def genes_array_from_oracle(model, seqs):
             rows.append((ci, g["left"], g["right"], g["strand"], g["domain"], g["partial_left"], g["partial_right"], g["gc"], 0,
                          g["logodd"]))
     return np.array(rows, dtype=GENE_DTYPE), np.array(totals, dtype=np.float64)
+
+
+def big_case(tmpdir: str):
+    """The 24 Mbp / 82-section golden of tests/golden/make_golden_big.py: regenerates contigs + parameter files, checks their
+    hashes → (meta, buffer, offsets, model paths)."""
+    from mgcod_b200 import synth
+    from mgcod_b200.engine import synth_metagenome
+    with lzma.open(os.path.join(GOLDEN, "big_parametric.json.xz"), "rt") as fh:
+        meta = json.load(fh)
+    buf, offs, truth = synth_metagenome(meta["seed"], meta["total_bp"], threads=4)
+    assert len(truth) == meta["n_contigs"]
+    assert hashlib.sha256(buf.tobytes()).hexdigest() == meta["seq_sha256"], "synthetic generator drifted from the golden set"
+    paths = synth.write_model_set(os.path.join(tmpdir, "bigpar"), kind="parametric")
+    for c in CODES:
+        assert hashlib.sha256(open(paths[c], "rb").read()).hexdigest() == meta["model_sha256"][str(c)]
+    return meta, buf, offs, paths
+
+
+def gene_attr_text(domain, pl, pr, gc, length) -> str:
+    """attributes of a GFF gene line behind the gene_id (gmhmmp2 Output::PrintGenes_GFF)"""
+    s = f"gene_type {'archaea' if domain else 'bacteria'};"
+    if pl or pr:
+        s += f" partial {int(pl)}{int(pr)};"
+    return s + f" gc {int(gc)}; length {int(length)};"
+
+
+def contig_digests(genes: np.ndarray, n_contigs: int):
+    """per-contig digest of a GENE_DTYPE table in the form make_golden_big.py stores"""
+    out = [hashlib.sha256() for _ in range(n_contigs)]
+    for g in genes:
+        left, right = int(g["left"]), int(g["right"])
+        out[int(g["contig"])].update(("%d %d %s %s %s\n" % (
+            left, right, "+" if g["strand"] > 0 else "-", "%.2f" % g["logodd"],
+            gene_attr_text(g["domain"], g["partial_left"], g["partial_right"], g["gc"], right - left + 1))).encode())
+    return [h.hexdigest()[:16] for h in out]
