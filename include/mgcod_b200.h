@@ -27,7 +27,8 @@ extern "C" {
 #define MGC_E_IO (-2)      /* file cannot be read / written */
 #define MGC_E_PARSE (-3)   /* malformed .mod or FASTA (gmhmmp2 prints "error, ..." and exits non-zero) */
 #define MGC_E_CUDA (-4)    /* no usable device / CUDA failure */
-#define MGC_E_ALPHABET (-5)/* sequence contains letters outside ACGT (not supported by this build) */
+#define MGC_E_ALPHABET (-5)/* a letter outside the accepted alphabet (ACGTU + IUPAC RYSWKMBDHVN, either case); gmhmmp2:
+                                "error, unexpected letter found in FASTA sequence" */
 #define MGC_E_NOMEM (-6)
 
 #define MGC_MAX_MODELS 8
@@ -136,8 +137,23 @@ int64_t mgc_recoded_stops(mgc_engine *e, const mgc_gene *genes, int64_t n_genes,
  */
 int mgc_window_counts(const int64_t *contig_len, const int32_t *stride, int32_t n_contigs, int32_t window,
                       int32_t consecutive, int short_contigs, int64_t *win_offsets);
-int mgc_window_labels(mgc_engine *e, const int32_t *stride, int32_t window, int32_t consecutive,
+int mgc_window_labels(mgc_engine *e, const int32_t *stride, int32_t n_contigs, int32_t window, int32_t consecutive,
                       int short_contigs, const int64_t *win_offsets, int32_t *labels, int64_t *cents);
+/* n_contigs = entries of stride[] (win_offsets has one more); MGC_E_ARG when it differs from the batch resident on the device
+ * (e.g. an input that was streamed in several batches: only the last one is resident). */
+
+/*
+ * --isoforms labelling in ONE call on the device (bin/pipeline.py:157-385 followed by :98-110 and :1064-1168): window sums and
+ * argmax labels, the label histogram of the whole input (its two most frequent labels stay, the others are noise), and the
+ * smoothing of every contig's labels — the labels do not visit the host in between.
+ *   labels, merged   [total windows]      raw argmax labels / smoothed labels
+ *   cents            [total windows * n_models] window sums in 1/100 units; may be NULL (only plots read them)
+ *   status           [n_contigs]          as mgc_merge_labels (1 = the reference raises IndexError on that contig)
+ * Not for the circular single-contig case (-r), whose labels are padded on the host between the two steps.
+ */
+int mgc_isoform_labels(mgc_engine *e, const int32_t *stride, int32_t n_contigs, int32_t window, int32_t consecutive,
+                       int short_contigs, const int64_t *win_offsets, int32_t *labels, int64_t *cents, int32_t *merged,
+                       int32_t *status);
 
 /*
  * Label smoothing on the device (Pipeline.find_best_sequence_of_labels, bin/pipeline.py:1064-1168) for every contig of

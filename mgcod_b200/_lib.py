@@ -39,7 +39,7 @@ EXPORTS = (
     "mgc_version", "mgc_last_error", "mgc_device_count", "mgc_model_load", "mgc_model_free", "mgc_model_info",
     "mgc_engine_create", "mgc_engine_destroy", "mgc_decode_batch", "mgc_upload_batch", "mgc_prefetch_batch", "mgc_decode_resident",
     "mgc_engine_stats", "mgc_result_num_genes", "mgc_result_genes", "mgc_result_contig_totals",
-    "mgc_result_model_cents", "mgc_result_min_gene_length", "mgc_result_set_min_gene_length", "mgc_result_free", "mgc_result_create", "mgc_recoded_stops", "mgc_window_counts", "mgc_window_labels", "mgc_merge_labels", "mgc_debug_candidates",
+    "mgc_result_model_cents", "mgc_result_min_gene_length", "mgc_result_set_min_gene_length", "mgc_result_free", "mgc_result_create", "mgc_recoded_stops", "mgc_window_counts", "mgc_window_labels", "mgc_isoform_labels", "mgc_merge_labels", "mgc_debug_candidates",
     "mgc_write_gff", "mgc_synth_lengths", "mgc_synth_contigs",
     "mgc_fasta_read", "mgc_fasta_num_records", "mgc_fasta_id", "mgc_fasta_defline", "mgc_fasta_sequence", "mgc_fasta_offsets", "mgc_fasta_free",
 )
@@ -93,7 +93,9 @@ def lib():
     L.mgc_recoded_stops.argtypes = [vp, vp, i64, C.POINTER(i32), C.POINTER(i64), C.POINTER(i32), i64]
     L.mgc_recoded_stops.restype = i64
     L.mgc_window_counts.argtypes = [C.POINTER(i64), C.POINTER(i32), i32, i32, i32, C.c_int, C.POINTER(i64)]
-    L.mgc_window_labels.argtypes = [vp, C.POINTER(i32), i32, i32, C.c_int, C.POINTER(i64), C.POINTER(i32), C.POINTER(i64)]
+    L.mgc_window_labels.argtypes = [vp, C.POINTER(i32), i32, i32, i32, C.c_int, C.POINTER(i64), C.POINTER(i32), C.POINTER(i64)]
+    L.mgc_isoform_labels.argtypes = [vp, C.POINTER(i32), i32, i32, i32, C.c_int, C.POINTER(i64), C.POINTER(i32), C.POINTER(i64),
+                                     C.POINTER(i32), C.POINTER(i32)]
     L.mgc_merge_labels.argtypes = [vp, C.POINTER(i32), C.POINTER(i64), i32, i32, C.c_uint32, C.POINTER(i32), C.POINTER(i32)]
     L.mgc_debug_candidates.argtypes = [vp, C.c_int, C.POINTER(Candidate), i64]
     L.mgc_debug_candidates.restype = i64

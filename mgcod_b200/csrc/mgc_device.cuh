@@ -27,14 +27,19 @@ struct DevModel {
     const double *lc_full, *ln_full, *lc_ramp, *ln_ramp;
     const SectionScalars *sc;
     const Quad *quad;   // [npair][3][4^(kc+1)], plane-major k-mer index
-    const double2 *wtab; // [npair][wtab_n16]: the walk's table image (coding part 2x replicated, non-coding part 8x replicated)
+    const double2 *wtab; // [npair][wtab_n16]: the single-position walk table image (coding part 2x replicated, non-coding part 8x replicated)
     int wtab_n16;
+    const double2 *wtab2; // [npair][wtab2_n16]: the pair walk's table image: coding {B, A} sums of two consecutive positions per
+                          // (phase, (kc+2)-mer), rc2 replicas side by side; non-coding sums per (kn+2)-mer, 8 replicas (k_walk_pair)
+    int wtab2_n16;
+    int rc2;              // replicas of the coding part (power of two, 1 for order 4); 0 = the tables do not fit one SM
     const Quad *rquad;  // [npair][kr][4^kr]: order ramp (window starts on a codon boundary, phase 0)
     int npair;
     int map[2][101];
     int pair[101];      // gc -> index of its (secB, secA) pair in quad
     const double *pair_amb;  // [npair][4]: ln COD_P_N (B, A), ln NON_P_N (B, A) — terms of a window with an ambiguous letter
-    const double *pair_ub;   // [npair][2][3]: upper bounds of the ramp, start and stop terms per domain (early pruning in k_final)
+    const double *pair_ub;   // [npair][8]: upper bounds per domain of the ramp, start and stop terms ([dom*3 + 0..2]) and of one
+                             // full-order position ([6 + dom], pair walk only) — early pruning in k_final
 };
 
 // one stop-delimited ORF that may have start candidates of sufficient length
@@ -60,12 +65,19 @@ struct __align__(16) StartRec {
 // one 32-letter word of an ORF's admissible start range
 
 // one walk of an ORF under one section pair: serves every start of that pair
+// (32 bytes: the second half repeats what the walk needs of the ORF record, so that a walk starts with its planes and start
+// records one load after the coalesced item load instead of item -> ORF -> contig offset -> planes)
 struct __align__(16) ItemRec {
-    uint32_t orf;
+    uint32_t orf;       // bit 31: the walk touches an ambiguous letter
     int32_t lo_pos;     // lowest position of the walk (first full-order position of the farthest start of this pair)
     uint32_t key;       // (tile * npair + pair) * WALK_CLASSES + length class (descending)
     int32_t last;       // index (within the ORF) of the start of this pair closest to the stop
+    int32_t t;          // OrfRec.t
+    uint32_t base;      // OrfRec.base
+    uint32_t woff;      // word offset of the contig's slot inside the planes of the ORF's strand (strand * W + cwoff[contig])
+    uint32_t sf;        // OrfRec.sf
 };
+static_assert(sizeof(ItemRec) == 32, "ItemRec must be 32 bytes");
 
 // Walk items are ordered by (position tile, section pair, length class): all items of a tile are walked before the next
 // tile, so the plane words of a tile (both strands, lo + hi = 16 B per word) stay in the 126 MB L2 while every section
@@ -91,6 +103,10 @@ inline WalkTiles walk_tiles_for(long long W, long long tile_words = WALK_TILE_WO
 constexpr int WALK_CLASSES = 64;   // length classes of 32 nt; the last one collects everything longer
 constexpr int WALK_UNIT = 256;     // threads per CTA of k_walk
 constexpr int WALK_CHUNK = 2048;   // items per work unit (one section pair; warps take 32 at a time)
+// pair walk: one CTA per SM owns the whole shared memory (192 KB coding + 32 KB non-coding for orders 4/2)
+constexpr int WALK2_THREADS = 768;
+constexpr int WALK2_CHUNK = 8192;  // larger units: the tail of a unit (its shortest items) idles a smaller share of the CTA
+constexpr int WALK2_SMEM_MAX = 227 * 1024 - 256;
 
 // a start/stop pair with total > 0, forward coordinates, 0-based inclusive
 struct __align__(16) Cand {

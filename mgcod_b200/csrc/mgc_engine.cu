@@ -147,7 +147,7 @@ struct DevBuf {
 };
 
 struct PerModel {
-    DevBuf lc_full, ln_full, lc_ramp, ln_ramp, sc, quad, rquad, wtab, pair_amb, pair_ub;
+    DevBuf lc_full, ln_full, lc_ramp, ln_ramp, sc, quad, rquad, wtab, wtab2, pair_amb, pair_ub;
     DevBuf ls, ls_tile, orfs, starts, items, items_sorted, hist, item_off, unit_off, sums;
     DevBuf surv, sorted, bcount, cum, prev, gptr;
     DevBuf av_right, av_left, av_ls, av_idx, av_cum, av_pmax, av_parg, chain, gene_count, gene_off, contig_total, genes;
@@ -206,12 +206,15 @@ struct mgc_engine {
     DevBuf t_ls, t_ls_tile, t_items, t_items_sorted, t_hist, t_item_off, t_unit_off, t_sums, unit_totals, next_unit;
     uint32_t cap_items = 0;
     int max_cod_order = 0, max_non_order = 0, max_pairs = 1;
+    bool orders_uniform = false;   // all models share one (COD_ORDER, NON_ORDER)
+    int pair_smem = 0;     // bytes of the pair walk's shared-memory table; 0 = single-position walk (order 5, or MGCOD_B200_WALK=single)
     DevBuf counters;     // [M][8] unsigned long long: 0 orfs, 1 starts
     DevBuf surv_counters;  // [M]
     DevBuf work_counters;  // [M] int
     DevBuf model_cents;    // [M]
     DevBuf gene_totals;    // [M] uint32 grand totals of the gene scans
-    DevBuf win_stride, win_off, win_labels, win_cents;
+    DevBuf win_stride, win_off, win_labels, win_cents, win_merged, win_run, win_status, win_hist;   // labelling scratch, kept between calls
+    PinnedPool::Block win_host;   // page-locked staging of the labelling results
     uint32_t cap_orf = 0, cap_starts = 0, cap_surv = 0;
     int cap_scale = 1;     // multiplier of the scratch capacities, raised on overflow
     std::vector<unsigned char> table_sig;   // contents of the device pointer tables as last uploaded
@@ -321,6 +324,53 @@ void upload_models(mgc_engine *e) {
             d.wtab = p.wtab.as<double2>();
             d.wtab_n16 = (int)n16;
         }
+        // image of the pair walk's table (k_walk_pair): per pair and codon position p of the window's first letter, for every
+        // (kc+2)-mer a0..a(kc+1) the sum lnP(a_kc | a0.., p) + lnP(a_(kc+1) | a1.., p+1) of both domains, rc2 replicas side by
+        // side; then the non-coding sums of the (kn+2)-mers, eight replicas.  rc2 = the most replicas that fit one SM.
+        {
+            const size_t npc = pow4(kc + 2), npn = pow4(kn + 2);
+            int rc = 8;
+            while (rc >= 1 && (3 * npc * (size_t)rc + npn * 8) * 16 > (size_t)WALK2_SMEM_MAX) rc >>= 1;
+            d.rc2 = rc;
+            d.wtab2 = nullptr;
+            d.wtab2_n16 = 0;
+            if (rc >= 1) {
+                const size_t n16 = 3 * npc * rc + npn * 8;
+                std::vector<double> img(pairs.size() * n16 * 2, 0.0);
+                const uint32_t m1 = (1u << (kc + 1)) - 1u;
+                for (size_t pi = 0; pi < pairs.size(); pi++) {
+                    double *base = img.data() + pi * n16 * 2;
+                    for (int ph = 0; ph < 3; ph++)
+                        for (size_t idx = 0; idx < npc; idx++) {
+                            const uint32_t hb = (uint32_t)(idx >> (kc + 2)), lb = (uint32_t)(idx & ((1u << (kc + 2)) - 1u));
+                            // bit 0 = first letter: the lower position's window is letters 0..kc, the upper one's 1..kc+1
+                            const size_t i0 = ((size_t)(hb & m1) << (kc + 1)) | (lb & m1);
+                            const size_t i1 = ((size_t)(hb >> 1) << (kc + 1)) | (lb >> 1);
+                            const Quad &q0 = q[(pi * 3 + ph) * nfull + i0], &q1 = q[(pi * 3 + (ph + 1) % 3) * nfull + i1];
+                            for (int rep = 0; rep < rc; rep++) {
+                                const size_t o16 = ((size_t)ph * npc + idx) * rc + rep;
+                                base[o16 * 2] = q0.cB + q1.cB;
+                                base[o16 * 2 + 1] = q0.cA + q1.cA;
+                            }
+                        }
+                    double *nb = base + 3 * npc * rc * 2;
+                    const uint32_t n1 = (1u << (kn + 1)) - 1u;
+                    for (size_t idn = 0; idn < npn; idn++) {
+                        const uint32_t hb = (uint32_t)(idn >> (kn + 2)), lb = (uint32_t)(idn & ((1u << (kn + 2)) - 1u));
+                        const size_t i0 = ((size_t)(hb & n1) << (kn + 1)) | (lb & n1);
+                        const size_t i1 = ((size_t)(hb >> 1) << (kn + 1)) | (lb >> 1);
+                        for (int dom = 0; dom < 2; dom++) {
+                            const int sec = dom ? pairs[pi].second : pairs[pi].first;
+                            const double v = sec >= 0 ? m.ln_full[(size_t)sec * nnon + i0] + m.ln_full[(size_t)sec * nnon + i1] : 0.0;
+                            for (int rep = 0; rep < 8; rep++) nb[((idn << 3) | (size_t)rep) * 2 + dom] = v;
+                        }
+                    }
+                }
+                up(p.wtab2, img.data(), img.size() * sizeof(double));
+                d.wtab2 = p.wtab2.as<double2>();
+                d.wtab2_n16 = (int)n16;
+            }
+        }
         // order ramp: order j < kc, window of j+1 letters starting on a codon boundary (phase 0);
         // non-coding order is min(j, kn): its context is the last min(j,kn)+1 letters of the window
         const int kr = d.kr, knr = d.knr;
@@ -356,7 +406,7 @@ void upload_models(mgc_engine *e) {
         {
             // upper bounds of what k_final adds to a start's walk sum, per pair and domain: order ramp (0 if ambiguous letters
             // silence it), start term, stop term.  A start whose bound stays <= 0 is pruned without touching the planes.
-            std::vector<double> ub(pairs.size() * 6, 0.0);
+            std::vector<double> ub(pairs.size() * 8, 0.0);
             for (size_t pi = 0; pi < pairs.size(); pi++)
                 for (int dom = 0; dom < 2; dom++) {
                     const int sec = dom ? pairs[pi].second : pairs[pi].first;
@@ -370,9 +420,16 @@ void upload_models(mgc_engine *e) {
                         }
                         ramp += std::max(best, 0.0);   // a short candidate may stop before position j
                     }
-                    ub[pi * 6 + dom * 3 + 0] = ramp;
-                    ub[pi * 6 + dom * 3 + 1] = std::max({m.sc[sec].start_lo[0], m.sc[sec].start_lo[1], m.sc[sec].start_lo[2]});
-                    ub[pi * 6 + dom * 3 + 2] = std::max({m.sc[sec].stop_lo[0], m.sc[sec].stop_lo[1], m.sc[sec].stop_lo[2]});
+                    ub[pi * 8 + dom * 3 + 0] = ramp;
+                    ub[pi * 8 + dom * 3 + 1] = std::max({m.sc[sec].start_lo[0], m.sc[sec].start_lo[1], m.sc[sec].start_lo[2]});
+                    ub[pi * 8 + dom * 3 + 2] = std::max({m.sc[sec].stop_lo[0], m.sc[sec].stop_lo[1], m.sc[sec].stop_lo[2]});
+                    // one full-order position at codon position 0 (added by k_final behind the pair walk), or its ambiguous-letter constant
+                    double one = std::max(0.0, m.sc[sec].ln_pn);
+                    for (size_t idx = 0; idx < nfull; idx++) {
+                        const Quad &e4 = q[(pi * 3 + 0) * nfull + idx];
+                        one = std::max(one, dom ? e4.oA : e4.oB);
+                    }
+                    ub[pi * 8 + 6 + dom] = one;
                 }
             up(p.pair_ub, ub.data(), ub.size() * sizeof(double));
             d.pair_ub = p.pair_ub.as<double>();
@@ -382,6 +439,21 @@ void upload_models(mgc_engine *e) {
         e->max_cod_order = std::max(e->max_cod_order, kc);
         e->max_pairs = std::max(e->max_pairs, d.npair);
         e->max_non_order = std::max(e->max_non_order, kn);
+    }
+    // the pair walk needs every model's pair tables in one SM's shared memory (orders <= 4); otherwise, or with
+    // MGCOD_B200_WALK=single (A/B measurements, tests of the older kernel), the single-position walk runs
+    e->pair_smem = 0;
+    {
+        const char *mode = std::getenv("MGCOD_B200_WALK");
+        bool all = !(mode && std::strcmp(mode, "single") == 0);
+        int bytes = 0;
+        for (const DevModel &d : dm) {
+            all = all && d.rc2 >= 1;
+            bytes = std::max(bytes, d.wtab2_n16 * 16);
+        }
+        if (all) e->pair_smem = bytes;
+        e->orders_uniform = true;
+        for (const DevModel &d : dm) e->orders_uniform = e->orders_uniform && d.kc == e->max_cod_order && d.kn == e->max_non_order;
     }
     e->d_models.ensure(sizeof(DevModel) * e->n_models);
     CUDA_TRY(cudaMemcpy(e->d_models.p, dm.data(), sizeof(DevModel) * e->n_models, cudaMemcpyHostToDevice));
@@ -690,7 +762,8 @@ mgc_result *run_pipeline(mgc_engine *e, bool *amb_out) {
                                 e->n_sm, st);
     launches += launch_item_sort(e->t_items.as<const ItemRec *>(), e->t_items_sorted.as<ItemRec *>(), e->t_hist.as<uint32_t *>(),
                                  e->t_item_off.as<uint32_t *>(), e->t_unit_off.as<uint32_t *>(), e->d_models.as<DevModel>(), M,
-                                 e->unit_totals.as<uint32_t>(), e->counters.as<unsigned long long>(), e->cap_items, pl.n_tiles, e->n_sm, st);
+                                 e->unit_totals.as<uint32_t>(), e->counters.as<unsigned long long>(), e->cap_items, pl.n_tiles, e->n_sm,
+                                 e->pair_smem > 0, st);
     CUDA_TRY(cudaPeekAtLastError());
     CUDA_TRY(cudaPeekAtLastError());   // a failed launch must not go unnoticed until the end
     CUDA_TRY(cudaEventRecord(e->ev[8], st));
@@ -698,13 +771,13 @@ mgc_result *run_pipeline(mgc_engine *e, bool *amb_out) {
                             e->t_orfs.as<const OrfRec *>(),
                             e->t_starts.as<const StartRec *>(), e->t_items_sorted.as<const ItemRec *>(),
                             e->t_item_off.as<const uint32_t *>(), e->t_unit_off.as<const uint32_t *>(), e->unit_totals.as<uint32_t>(),
-                            e->t_sums.as<void *>(), e->next_unit.as<unsigned int>(), e->n_sm, st);
+                            e->t_sums.as<void *>(), e->next_unit.as<unsigned int>(), e->n_sm, e->pair_smem, e->orders_uniform, st);
     CUDA_TRY(cudaPeekAtLastError());   // a failed launch must not go unnoticed until the end
     CUDA_TRY(cudaEventRecord(e->ev[9], st));
     launch_final(pl, e->cwoff.as<int64_t>(), e->clen.as<int32_t>(), e->d_models.as<DevModel>(), M, e->t_orfs.as<const OrfRec *>(),
                  e->t_starts.as<const StartRec *>(), e->t_sums.as<void *>(), e->counters.as<unsigned long long>(), e->t_surv.as<Cand *>(),
                  e->t_bcount.as<uint32_t *>(), e->t_cover.as<uint32_t *>(), e->surv_counters.as<unsigned long long>(), e->cap_starts, e->cap_surv,
-                 e->n_sm, st);
+                 e->n_sm, e->pair_smem > 0, st);
     launches += 1;
     CUDA_TRY(cudaPeekAtLastError());   // a failed launch must not go unnoticed until the end
     CUDA_TRY(cudaEventRecord(e->ev[3], st));
@@ -983,7 +1056,7 @@ void mgc_engine_destroy(mgc_engine *e) {
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
     for (auto &p : e->pm) {
-        for (DevBuf *b : {&p.lc_full, &p.ln_full, &p.lc_ramp, &p.ln_ramp, &p.sc, &p.quad, &p.rquad, &p.wtab, &p.pair_amb, &p.pair_ub, &p.ls, &p.ls_tile, &p.items, &p.items_sorted, &p.hist,
+        for (DevBuf *b : {&p.lc_full, &p.ln_full, &p.lc_ramp, &p.ln_ramp, &p.sc, &p.quad, &p.rquad, &p.wtab, &p.wtab2, &p.pair_amb, &p.pair_ub, &p.ls, &p.ls_tile, &p.items, &p.items_sorted, &p.hist,
                           &p.item_off, &p.unit_off, &p.sums, &p.orfs, &p.starts, &p.surv, &p.sorted, &p.bcount,
                           &p.cum, &p.prev, &p.gptr, &p.av_right, &p.av_left, &p.av_ls, &p.av_idx, &p.av_cum, &p.av_pmax, &p.av_parg,
                           &p.chain, &p.gene_count, &p.gene_off, &p.contig_total, &p.genes, &p.piece_b0, &p.piece_b1, &p.work,
@@ -994,7 +1067,7 @@ void mgc_engine_destroy(mgc_engine *e) {
                       &e->tile_sums, &e->flags, &e->t_orfs, &e->t_starts, &e->t_surv, &e->t_sorted, &e->t_bcount, &e->t_cover, &e->t_scan_buckets, &e->t_gene_count, &e->t_slot_gene_off, &e->t_gene_off,
                       &e->t_genes, &e->t_chainbufs, &e->counters, &e->surv_counters, &e->work_counters, &e->model_cents,
                       &e->gene_totals, &e->t_ls, &e->t_ls_tile, &e->t_items, &e->t_items_sorted, &e->t_hist, &e->t_item_off,
-                      &e->t_unit_off, &e->t_sums, &e->ascii_next, &e->slotbase, &e->slot_contig, &e->nm, &e->ncount, &e->codon, &e->cflags, &e->plen, &e->gaps, &e->gap_count, &e->unit_totals, &e->next_unit, &e->win_stride, &e->win_off, &e->win_labels, &e->win_cents})
+                      &e->t_unit_off, &e->t_sums, &e->ascii_next, &e->slotbase, &e->slot_contig, &e->nm, &e->ncount, &e->codon, &e->cflags, &e->plen, &e->gaps, &e->gap_count, &e->unit_totals, &e->next_unit, &e->win_stride, &e->win_off, &e->win_labels, &e->win_cents, &e->win_merged, &e->win_run, &e->win_status, &e->win_hist})
         b->release();
     for (auto &ev : e->ev) cudaEventDestroy(ev);
     if (e->last_ready) e->last_ready->wait();
@@ -1069,23 +1142,21 @@ int mgc_merge_labels(mgc_engine *e, const int32_t *labels, const int64_t *win_of
         CUDA_TRY(cudaSetDevice(e->device));
         const int64_t nw = win_offsets[n_contigs];
         cudaStream_t st = e->stream;
-        DevBuf d_lab, d_off, d_out, d_run, d_status;
-        d_lab.ensure((size_t)std::max<int64_t>(nw, 1) * 4);
-        d_out.ensure((size_t)std::max<int64_t>(nw, 1) * 4);
-        d_run.ensure((size_t)std::max<int64_t>(nw, 1) * 4);
-        d_off.ensure((size_t)(n_contigs + 1) * 8);
-        d_status.ensure((size_t)std::max(n_contigs, 1) * 4);
-        CUDA_TRY(cudaMemcpyAsync(d_lab.p, labels, (size_t)nw * 4, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(d_off.p, win_offsets, (size_t)(n_contigs + 1) * 8, cudaMemcpyHostToDevice, st));
+        // scratch lives in the engine: no allocation per call once it has grown to the largest input seen
+        e->win_labels.ensure((size_t)std::max<int64_t>(nw, 1) * 4);
+        e->win_merged.ensure((size_t)std::max<int64_t>(nw, 1) * 4);
+        e->win_run.ensure((size_t)std::max<int64_t>(nw, 1) * 4);
+        e->win_off.ensure((size_t)(n_contigs + 1) * 8);
+        e->win_status.ensure((size_t)std::max(n_contigs, 1) * 4);
+        CUDA_TRY(cudaMemcpyAsync(e->win_labels.p, labels, (size_t)nw * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(e->win_off.p, win_offsets, (size_t)(n_contigs + 1) * 8, cudaMemcpyHostToDevice, st));
         if (n_contigs)
-            launch_merge_labels(d_lab.as<int32_t>(), d_off.as<int64_t>(), n_contigs, consecutive, noise_labels, d_out.as<int32_t>(),
-                                d_run.as<int32_t>(), d_status.as<int32_t>(), st);
-        if (nw) CUDA_TRY(cudaMemcpyAsync(merged, d_out.p, (size_t)nw * 4, cudaMemcpyDeviceToHost, st));
-        if (n_contigs) CUDA_TRY(cudaMemcpyAsync(status, d_status.p, (size_t)n_contigs * 4, cudaMemcpyDeviceToHost, st));
+            launch_merge_labels(e->win_labels.as<int32_t>(), e->win_off.as<int64_t>(), n_contigs, consecutive, noise_labels, nullptr,
+                                e->win_merged.as<int32_t>(), e->win_run.as<int32_t>(), e->win_status.as<int32_t>(), st);
+        if (nw) CUDA_TRY(cudaMemcpyAsync(merged, e->win_merged.p, (size_t)nw * 4, cudaMemcpyDeviceToHost, st));
+        if (n_contigs) CUDA_TRY(cudaMemcpyAsync(status, e->win_status.p, (size_t)n_contigs * 4, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
-        cudaError_t le = cudaGetLastError();
-        d_lab.release(); d_off.release(); d_out.release(); d_run.release(); d_status.release();
-        if (le != cudaSuccess) throw std::runtime_error(std::string("CUDA: ") + cudaGetErrorString(le));
+        CUDA_TRY(cudaGetLastError());
     });
 }
 
@@ -1290,10 +1361,12 @@ int64_t mgc_recoded_stops(mgc_engine *e, const mgc_gene *genes, int64_t n_genes,
     return rc == MGC_OK ? total : rc;
 }
 
-int mgc_window_labels(mgc_engine *e, const int32_t *stride, int32_t window, int32_t consecutive, int short_contigs,
+int mgc_window_labels(mgc_engine *e, const int32_t *stride, int32_t n_contigs, int32_t window, int32_t consecutive, int short_contigs,
                       const int64_t *win_offsets, int32_t *labels, int64_t *cents) {
-    if (!e || !stride || !win_offsets || !labels || !cents) return mgc::set_error(MGC_E_ARG, "null argument");
+    if (!e || !stride || !win_offsets || !labels || !cents || window <= 0 || consecutive < 1) return mgc::set_error(MGC_E_ARG, "bad argument");
     if (!e->have_genes) return mgc::set_error(MGC_E_ARG, "decode a batch before asking for window labels");
+    if (n_contigs != e->n_parents)
+        return mgc::set_error(MGC_E_ARG, "window labels: the caller's contig count differs from the batch resident on the device");
     return guarded([&] {
         CUDA_TRY(cudaSetDevice(e->device));
         const int32_t n = e->n_parents;
@@ -1308,13 +1381,74 @@ int mgc_window_labels(mgc_engine *e, const int32_t *stride, int32_t window, int3
         CUDA_TRY(cudaMemcpyAsync(e->win_off.p, win_offsets, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
         launch_windows(e->t_genes.as<const mgc_gene *>(), e->t_gene_off.as<const uint32_t *>(), M, e->plen.as<int32_t>(),
                        e->win_stride.as<int32_t>(), e->win_off.as<int64_t>(), n, window, consecutive, short_contigs,
-                       e->win_labels.as<int32_t>(), e->win_cents.as<long long>(), st);
+                       e->win_labels.as<int32_t>(), e->win_cents.as<long long>(), nullptr, st);
         if (nw) {
             CUDA_TRY(cudaMemcpyAsync(labels, e->win_labels.p, (size_t)nw * 4, cudaMemcpyDeviceToHost, st));
             CUDA_TRY(cudaMemcpyAsync(cents, e->win_cents.p, (size_t)nw * M * 8, cudaMemcpyDeviceToHost, st));
         }
         CUDA_TRY(cudaStreamSynchronize(st));
         CUDA_TRY(cudaGetLastError());
+    });
+}
+
+int mgc_isoform_labels(mgc_engine *e, const int32_t *stride, int32_t n_contigs, int32_t window, int32_t consecutive, int short_contigs,
+                       const int64_t *win_offsets, int32_t *labels, int64_t *cents, int32_t *merged, int32_t *status) {
+    if (!e || !stride || !win_offsets || !labels || !merged || !status || window <= 0 || consecutive < 1)
+        return mgc::set_error(MGC_E_ARG, "bad argument");
+    if (!e->have_genes) return mgc::set_error(MGC_E_ARG, "decode a batch before asking for window labels");
+    if (n_contigs != e->n_parents)
+        return mgc::set_error(MGC_E_ARG, "window labels: the caller's contig count differs from the batch resident on the device");
+    return guarded([&] {
+        CUDA_TRY(cudaSetDevice(e->device));
+        const int32_t n = e->n_parents;
+        const int M = e->n_models;
+        const int64_t nw = win_offsets[n], nw1 = std::max<int64_t>(nw, 1);
+        cudaStream_t st = e->stream;
+        e->win_stride.ensure((size_t)n * 4);
+        e->win_off.ensure((size_t)(n + 1) * 8);
+        e->win_labels.ensure((size_t)nw1 * 4);
+        e->win_cents.ensure((size_t)nw1 * M * 8);
+        e->win_merged.ensure((size_t)nw1 * 4);
+        e->win_run.ensure((size_t)nw1 * 4);
+        e->win_status.ensure((size_t)std::max(n, 1) * 4);
+        e->win_hist.ensure(MGC_MAX_MODELS * 8 + 16);
+        // one page-locked block receives labels | merged | status | cents: a single pass over PCIe, then plain copies
+        const size_t o_lab = 0, o_mer = (size_t)nw1 * 4, o_sta = o_mer + (size_t)nw1 * 4;
+        const size_t o_cen = (o_sta + (size_t)std::max(n, 1) * 4 + 15) & ~(size_t)15;
+        const size_t need = o_cen + (cents ? (size_t)nw1 * M * 8 : 0);
+        if (e->win_host.bytes < need) {
+            e->pool->release(e->win_host);
+            e->win_host = PinnedPool::Block();
+            e->win_host = e->pool->acquire(need);
+        }
+        char *hp = static_cast<char *>(e->win_host.p);
+        CUDA_TRY(cudaMemsetAsync(e->win_hist.p, 0, MGC_MAX_MODELS * 8 + 16, st));
+        CUDA_TRY(cudaMemcpyAsync(e->win_stride.p, stride, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(e->win_off.p, win_offsets, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
+        unsigned long long *hist = e->win_hist.as<unsigned long long>();
+        uint32_t *mask = reinterpret_cast<uint32_t *>(hist + MGC_MAX_MODELS);
+        // window sums + labels + label histogram -> noise labels -> smoothing; the labels never leave the device in between
+        launch_windows(e->t_genes.as<const mgc_gene *>(), e->t_gene_off.as<const uint32_t *>(), M, e->plen.as<int32_t>(),
+                       e->win_stride.as<int32_t>(), e->win_off.as<int64_t>(), n, window, consecutive, short_contigs,
+                       e->win_labels.as<int32_t>(), e->win_cents.as<long long>(), hist, st);
+        launch_noise_mask(hist, M, mask, st);
+        if (n)
+            launch_merge_labels(e->win_labels.as<int32_t>(), e->win_off.as<int64_t>(), n, consecutive, 0u, mask, e->win_merged.as<int32_t>(),
+                                e->win_run.as<int32_t>(), e->win_status.as<int32_t>(), st);
+        if (nw) {
+            CUDA_TRY(cudaMemcpyAsync(hp + o_lab, e->win_labels.p, (size_t)nw * 4, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(hp + o_mer, e->win_merged.p, (size_t)nw * 4, cudaMemcpyDeviceToHost, st));
+            if (cents) CUDA_TRY(cudaMemcpyAsync(hp + o_cen, e->win_cents.p, (size_t)nw * M * 8, cudaMemcpyDeviceToHost, st));
+        }
+        if (n) CUDA_TRY(cudaMemcpyAsync(hp + o_sta, e->win_status.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        CUDA_TRY(cudaGetLastError());
+        if (nw) {
+            std::memcpy(labels, hp + o_lab, (size_t)nw * 4);
+            std::memcpy(merged, hp + o_mer, (size_t)nw * 4);
+            if (cents) std::memcpy(cents, hp + o_cen, (size_t)nw * M * 8);
+        }
+        if (n) std::memcpy(status, hp + o_sta, (size_t)n * 4);
     });
 }
 

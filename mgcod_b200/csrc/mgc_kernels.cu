@@ -927,7 +927,7 @@ __global__ void __launch_bounds__(256) k_start_link(Planes pl, const int64_t *__
         }
         bool emit = false;
         ItemRec it;
-        it.key = 0;
+        it.key = 0; it.t = 0; it.base = 0; it.woff = 0; it.sf = 0;
         if (valid && !has_next) {   // the chain ends here (closest to the stop): finish the way to its head and emit its item
             int cur = tail_prev;    // first start of the chain that is not in this warp (or -1)
             while (cur >= 0) {
@@ -949,6 +949,10 @@ __global__ void __launch_bounds__(256) k_start_link(Planes pl, const int64_t *__
             const int tile = tile_raw < pl.n_tiles - 1 ? (int)tile_raw : pl.n_tiles - 1;
             it.key = (uint32_t)((tile * npair + (int)pair) * WALK_CLASSES + (WALK_CLASSES - 1 - min(ext >> 5, WALK_CLASSES - 1)));
             it.last = j;
+            it.t = t;
+            it.base = rec.base;
+            it.woff = (uint32_t)((int64_t)(rec.sf & 1u) * pl.W + cwoff[rec.contig]);
+            it.sf = rec.sf;
             emit = true;
         }
         const uint32_t em = __ballot_sync(0xffffffffu, emit);
@@ -980,9 +984,10 @@ __global__ void __launch_bounds__(256) k_start_link(Planes pl, const int64_t *__
 }
 
 // one block per model: item offsets per key (exclusive scan of the histogram, which is turned into the scatter
-// cursor); work units = chunks of WALK_CHUNK items of one section pair, with their prefix over pairs
+// cursor); work units = chunks of chunk_items (WALK_CHUNK or WALK2_CHUNK) items of one section pair, with their prefix over pairs
 __global__ void __launch_bounds__(1024) k_item_plan(uint32_t *const *hist_m, uint32_t *const *item_off_m, uint32_t *const *unit_off_m,
-                                                    const DevModel *__restrict__ models, uint32_t *unit_totals, unsigned long long *counters_m, int n_tiles) {
+                                                    const DevModel *__restrict__ models, uint32_t *unit_totals, unsigned long long *counters_m, int n_tiles,
+                                                    uint32_t chunk_items) {
     __shared__ uint32_t carry_i;
     const int mi = blockIdx.x;
     const int npair = models[mi].npair * n_tiles, nkeys = npair * WALK_CLASSES;   // (tile, pair) combinations
@@ -1009,7 +1014,7 @@ __global__ void __launch_bounds__(1024) k_item_plan(uint32_t *const *hist_m, uin
         for (int p = 0; p < npair; p++) {
             uoff[p] = acc;
             const uint32_t cnt = ioff[(p + 1) * WALK_CLASSES] - ioff[p * WALK_CLASSES];
-            acc += (cnt + WALK_CHUNK - 1) / WALK_CHUNK;
+            acc += (cnt + chunk_items - 1) / chunk_items;
         }
         uoff[npair] = acc;
         unit_totals[mi] = acc;
@@ -1218,6 +1223,260 @@ __global__ void __launch_bounds__(WALK_UNIT, 2) k_walk(Planes pl, const int64_t 
 }
 
 // ------------------------------------------------------------------------------------------------
+// the pair walk: two positions per table lookup
+// ------------------------------------------------------------------------------------------------
+// Same items, same sums as k_walk, but the shared-memory tables are indexed by the (kc+2)-mer and hold the SUM of the two
+// positions that window covers ({B, A} coding log-likelihoods of positions i-1 and i), the non-coding table likewise by
+// the (kn+2)-mer: one coding and one non-coding lookup per TWO positions.  That halves the shared-memory wavefronts,
+// which bound k_walk (profiles/r1j_k_walk_1Gbp.txt), and the instruction count with them.  Order 4/2: 3 x 4096 x 16 B =
+// 192 KB coding (one copy) + 256 x 16 B x 8 replicas = 32 KB non-coding: one CTA of 512 threads owns the SM.
+//
+// A walk therefore advances in steps of two from the letter before the stop codon.  The first full-order position F of a
+// start lies t - F positions below the stop; when that count is odd the walk delivers the sum down to F + 1 and k_final
+// adds position F itself from the single-position table (phase 0 by construction: F - kc is the first summed letter).
+// The loop is flat — one pair step per iteration for every lane, plane-word refills and sum deliveries as short
+// predicated blocks inside it — so the lanes of a warp stay together until their items (sorted by length) end.
+// Items whose range touches an ambiguous letter take walk_careful() (single positions, tables behind L1/L2).
+struct WalkItemCtx {
+    const uint32_t *lo, *hi, *nm;
+    const StartRec *st;
+    Acc4 *sums;
+    int t, kc, kn, lo2, j;
+    bool from_first;
+};
+
+__device__ __forceinline__ int pair_target(uint32_t sraw, bool from_first, int kc, int t) {
+    const int F = (int)(sraw & 0x7fffffffu) + (((sraw >> 31) && from_first) ? 0 : 3) + kc;
+    return F + ((t - F) & 1);
+}
+
+__device__ __noinline__ void walk_careful(const WalkItemCtx &cx, const double2 *gq, int nfull, double2 amb_c, double2 amb_n, int lane) {
+    // single positions from the global image of k_walk's table (coding part 2 replicas, non-coding part 8)
+    const int kc = cx.kc, kn = cx.kn, t = cx.t;
+    const double2 *tc0 = gq + (lane & 1), *tn8 = gq + (size_t)3 * nfull * 2 + (lane & 7);
+    const int pstep = 2 * nfull, nsh = kc - kn;
+    const uint32_t wmask = (1u << (kc + 1)) - 1u;
+    int j = cx.j;
+    StartRec cur = cx.st[j];
+    int target = pair_target(cur.sraw, cx.from_first, kc, t);
+    Acc4 acc = {0, 0, 0, 0};
+    int ph = (((-1 - kc) % 3) + 3) % 3;
+    for (int i = t - 1;; i--) {
+        while (i + 1 == target) {
+            Acc4 out;
+            out.cB = acc.cB; out.oB = acc.cB - acc.oB; out.cA = acc.cA; out.oA = acc.cA - acc.oA;
+            cx.sums[j] = out;
+            j = cur.link;
+            if (j < 0) return;
+            cur = cx.st[j];
+            target = pair_target(cur.sraw, cx.from_first, kc, t);
+        }
+        uint32_t hb, lb, ab, dummy;
+        window_bits(cx.lo, cx.hi, i - kc, kc + 1, hb, lb);
+        window_bits(cx.nm, cx.nm, i - kc, kc + 1, ab, dummy);
+        hb &= wmask; lb &= wmask;
+        double2 c2 = amb_c, n2 = amb_n;
+        if (!ab) {
+            c2 = __ldg(tc0 + ph * pstep + (((hb << (kc + 1)) | lb) << 1));
+            n2 = __ldg(tn8 + ((((hb >> nsh) << (kn + 1)) | (lb >> nsh)) << 3));
+        }
+        acc.cB += c2.x; acc.cA += c2.y; acc.oB += n2.x; acc.oA += n2.y;
+        ph = ph == 0 ? 2 : ph - 1;
+    }
+}
+
+__device__ __forceinline__ double2 lds_d2(uint32_t addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+
+// KC, KN >= 0: the orders are compile-time constants (all shifts and masks of a step fold); KC < 0: read from the model.
+template <int KC, int KN>
+__global__ void __launch_bounds__(WALK2_THREADS, 1) k_walk_pair(Planes pl, const DevModel *__restrict__ models, int n_models,
+                                                                const StartRec *const *starts_m, const ItemRec *const *items_m,
+                                                                const uint32_t *const *item_off_m, const uint32_t *const *unit_off_m,
+                                                                const uint32_t *__restrict__ unit_totals, Acc4 *const *sums_m,
+                                                                unsigned int *next_unit) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double2 *tbl = reinterpret_cast<double2 *>(smem_raw);
+    __shared__ int s_model, s_pair;
+    __shared__ uint32_t s_end;
+    __shared__ unsigned int s_next;
+    const int lane = lane_id();
+    int loaded_model = -1, loaded_pair = -1;
+    const uint32_t tbl_addr = (uint32_t)__cvta_generic_to_shared(tbl);
+    while (true) {
+        if (threadIdx.x == 0) {
+            unsigned int u = atomicAdd(next_unit, 1u);
+            int m = 0;
+            while (m < n_models && u >= unit_totals[m]) { u -= unit_totals[m]; m++; }
+            s_model = m;
+            if (m < n_models) {
+                const uint32_t *uoff = unit_off_m[m];
+                int lo = 0, hi = models[m].npair * pl.n_tiles;  // last (tile, pair) with uoff[.] <= u (uoff has one more entry)
+                while (lo + 1 < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (uoff[mid] <= u) lo = mid; else hi = mid;
+                }
+                s_pair = lo;
+                const uint32_t *ioff = item_off_m[m];
+                const uint32_t first = ioff[lo * WALK_CLASSES] + (u - uoff[lo]) * WALK2_CHUNK;
+                s_end = min(first + (uint32_t)WALK2_CHUNK, ioff[(lo + 1) * WALK_CLASSES]);
+                s_next = first;
+            }
+        }
+        __syncthreads();
+        const int mi = s_model;
+        if (mi >= n_models) break;
+        const DevModel &dm = models[mi];
+        const int pair = s_pair % dm.npair;   // s_pair counts (tile, pair) combinations, tile-major
+        const int kc = KC >= 0 ? KC : dm.kc, kn = KC >= 0 ? KN : dm.kn;
+        if (mi != loaded_model || pair != loaded_pair) {
+            const int4 *src = reinterpret_cast<const int4 *>(dm.wtab2 + (size_t)pair * dm.wtab2_n16);
+            int4 *dst = reinterpret_cast<int4 *>(tbl);
+            const int n16 = dm.wtab2_n16;
+#pragma unroll 4
+            for (int i = threadIdx.x; i < n16; i += WALK2_THREADS) dst[i] = __ldg(src + i);
+            loaded_model = mi;
+            loaded_pair = pair;
+            __syncthreads();
+        }
+        // shared-memory byte addresses: coding entry of (codon position p, window index x) at tc + p * pbytes + (x << (rcs + 4)),
+        // my replica folded into tc; non-coding entry of index y at tn + (y << 7) (8 replicas of 16 bytes)
+        const int rcs = KC == 4 ? 0 : 31 - __clz(dm.rc2);        // log2 of the coding replicas (order 4: one copy fills the SM)
+        const uint32_t pbytes = (uint32_t)(1u << (2 * (kc + 2))) << (rcs + 4);
+        const uint32_t tc = tbl_addr + ((uint32_t)(lane & ((1 << rcs) - 1)) << 4);
+        const uint32_t tn = tbl_addr + 3 * pbytes + ((uint32_t)(lane & 7) << 4);
+        const int nsh = kc - kn;
+        const uint32_t wmask = (1u << (kc + 2)) - 1u;
+        const int ph0 = (((-2 - kc) % 3) + 3) % 3;               // codon position of the first letter of the topmost pair window
+        const uint32_t end = s_end;
+        const ItemRec *items = items_m[mi];
+        const StartRec *starts = starts_m[mi];
+        Acc4 *sums_all = sums_m[mi];
+        while (true) {
+            uint32_t w_first = 0;
+            if (lane == 0) w_first = atomicAdd(&s_next, 32u);
+            w_first = __shfl_sync(0xffffffffu, w_first, 0);
+            if (w_first >= end) break;
+            if (w_first + lane >= end) continue;
+            const int4 ia = __ldg(reinterpret_cast<const int4 *>(items + w_first + lane));
+            const int4 ib = __ldg(reinterpret_cast<const int4 *>(items + w_first + lane) + 1);
+            const int t = ib.x;
+            const bool from_first = ((uint32_t)ib.w & 0x200u) != 0;
+            const uint32_t *lo = pl.lo + (uint32_t)ib.z, *hi = pl.hi + (uint32_t)ib.z;
+            const StartRec *st = starts + (uint32_t)ib.y;
+            Acc4 *sums = sums_all + (uint32_t)ib.y;
+            int j = ia.w;
+            const int lo2 = ia.y + ((t - ia.y) & 1);
+            if ((uint32_t)ia.x >> 31) {   // the walk touches an ambiguous letter
+                WalkItemCtx cx;
+                cx.lo = lo; cx.hi = hi; cx.nm = pl.nm + (uint32_t)ib.z; cx.st = st; cx.sums = sums;
+                cx.t = t; cx.kc = kc; cx.kn = kn; cx.lo2 = lo2; cx.j = j; cx.from_first = from_first;
+                walk_careful(cx, dm.wtab + (size_t)pair * dm.wtab_n16, dm.nfull,
+                             make_double2(dm.pair_amb[pair * 4 + 0], dm.pair_amb[pair * 4 + 1]),
+                             make_double2(dm.pair_amb[pair * 4 + 2], dm.pair_amb[pair * 4 + 3]), lane);
+                continue;
+            }
+            // the starts of my pair, from the one closest to the stop outwards; the next two records of the chain are kept
+            // loaded (starts of a gene often sit a few codons apart: one record ahead is not enough to hide the load)
+            StartRec cur = st[j];
+            int target = pair_target(cur.sraw, from_first, kc, t);
+            StartRec nxt = cur, nx2 = cur;
+            if (cur.link >= 0) {
+                nxt = st[cur.link];
+                nx2 = nxt;
+            }
+            bool nx2_pending = cur.link >= 0;           // nx2 still has to be loaded (needs nxt.link, which is in flight)
+            int steps = (t - lo2) >> 1;                 // pair steps of this walk
+            // Rounds of 16 pair steps, the same for every lane of the warp.  The window of step r of a round starts 2r letters
+            // below the round's first window; a 64-letter register pair per plane, whose bit 0 is the letter 30 below that first
+            // window, holds everything the round reads, so step r extracts its (kc+2)-mer with the CONSTANT shift 30 - 2r.
+            // Between rounds the register pair moves down by one 32-letter word — one new (unaligned: same bit offset `off`
+            // for the whole walk) word per plane, loaded a round ahead.  No lane-dependent refill inside the steps.
+            const int base = t - 2 - kc - 30;           // letter index of bit 0 in the first round (may be negative: unused letters)
+            int k = base >> 5;                          // word holding that letter (arithmetic shift: floor)
+            const int off = base & 31;
+            // plane words travel as 16-byte groups (4 words = 128 letters, one sector request per group and plane instead of
+            // one per word: the L1 left beside 224 KB of tables does not keep 2 x 512 word streams, and the outstanding
+            // sector misses of an SM are what bounds this kernel once the table lookups are halved)
+            const uint4 *lo4 = reinterpret_cast<const uint4 *>(lo), *hi4 = reinterpret_cast<const uint4 *>(hi);
+            auto pick = [](const uint4 &v, int q) { return q == 0 ? v.x : (q == 1 ? v.y : (q == 2 ? v.z : v.w)); };
+            const int k0 = k < 0 ? 0 : k;               // words below the contig hold no letter a window reads
+            uint4 gl = __ldg(lo4 + (k0 >> 2)), gh = __ldg(hi4 + (k0 >> 2));
+            uint32_t wl = pick(gl, k0 & 3), wh = pick(gh, k0 & 3);                       // W[k]
+            uint32_t ul, uh, vl, vh;                                                     // W[k+1], W[k+2]
+            {
+                const int k1 = k + 1 < 0 ? 0 : k + 1, k2 = k + 2 < 0 ? 0 : k + 2;
+                uint4 g2l = gl, g2h = gh;
+                if ((k2 >> 2) != (k0 >> 2)) { g2l = __ldg(lo4 + (k2 >> 2)); g2h = __ldg(hi4 + (k2 >> 2)); }
+                ul = (k1 >> 2) == (k0 >> 2) ? pick(gl, k1 & 3) : pick(g2l, k1 & 3);
+                uh = (k1 >> 2) == (k0 >> 2) ? pick(gh, k1 & 3) : pick(g2h, k1 & 3);
+                vl = (k2 >> 2) == (k0 >> 2) ? pick(gl, k2 & 3) : pick(g2l, k2 & 3);
+                vh = (k2 >> 2) == (k0 >> 2) ? pick(gh, k2 & 3) : pick(g2h, k2 & 3);
+            }
+            uint32_t low_l = __funnelshift_r(wl, ul, off), low_h = __funnelshift_r(wh, uh, off);
+            uint32_t high_l = __funnelshift_r(ul, vl, off), high_h = __funnelshift_r(uh, vh, off);
+            // coding tables of the three codon positions in the order this round's steps use them: step r reads tp[r % 3];
+            // a round has 16 steps, so the triple rotates by one between rounds
+            uint32_t tp0 = tc + (uint32_t)ph0 * pbytes, tp1 = tc + (uint32_t)((ph0 + 1) % 3) * pbytes, tp2 = tc + (uint32_t)((ph0 + 2) % 3) * pbytes;
+            double cB = 0, cA = 0, nB = 0, nA = 0;
+            int i = t - 1;                              // topmost position not yet summed
+            auto deliver = [&]() {
+                do {                                    // a virtual and a real start may share their first full-order position
+                    Acc4 out;
+                    out.cB = cB; out.oB = cB - nB; out.cA = cA; out.oA = cA - nA;
+                    sums[j] = out;
+                    j = cur.link;
+                    if (j < 0) { target = -1 << 30; break; }
+                    if (nx2_pending) { nx2 = nxt; if (nxt.link >= 0) nx2 = st[nxt.link]; nx2_pending = false; }
+                    cur = nxt;
+                    nxt = nx2;
+                    target = pair_target(cur.sraw, from_first, kc, t);
+                    if (nxt.link >= 0) nx2 = st[nxt.link];
+                } while (i + 1 == target);
+            };
+            if (i + 1 == target) deliver();             // starts with an empty (or one-position) full-order region
+            while (steps > 0) {
+                const int n_this = steps < 16 ? steps : 16;
+                steps -= n_this;
+                // next round's word: when it opens a new group, the group is on its way while this round runs
+                k--;
+                if (k >= 0 && (k & 3) == 3) { gl = __ldg(lo4 + (k >> 2)); gh = __ldg(hi4 + (k >> 2)); }
+                if (nx2_pending) { nx2 = nxt; if (nxt.link >= 0) nx2 = st[nxt.link]; nx2_pending = false; }
+                double2 c2, n2;
+                auto lookup = [&](int shift, uint32_t tp, double2 &c, double2 &n) {
+                    const uint32_t lb = __funnelshift_r(low_l, high_l, shift) & wmask;
+                    const uint32_t hb = __funnelshift_r(low_h, high_h, shift) & wmask;
+                    c = lds_d2(tp + (((hb << (kc + 2)) | lb) << (rcs + 4)));
+                    n = lds_d2(tn + ((((hb >> nsh) << (kn + 2)) | (lb >> nsh)) << 7));
+                };
+                lookup(30, tp0, c2, n2);
+#pragma unroll
+                for (int r = 0; r < 16; r++) {
+                    if (r < n_this) {
+                        double2 c3 = c2, n3 = n2;
+                        if (r + 1 < 16 && r + 1 < n_this)   // in flight while this pair is added
+                            lookup(28 - 2 * r, (r + 1) % 3 == 0 ? tp0 : ((r + 1) % 3 == 1 ? tp1 : tp2), c3, n3);
+                        cB += c2.x; cA += c2.y; nB += n2.x; nA += n2.y;
+                        i -= 2;
+                        if (i + 1 == target) deliver();
+                        c2 = c3; n2 = n3;
+                    }
+                }
+                const uint32_t nl = pick(gl, k & 3), nh = pick(gh, k & 3);   // k < 0: letters below the contig, never read
+                high_l = low_l; high_h = low_h;
+                low_l = __funnelshift_r(nl, wl, off); low_h = __funnelshift_r(nh, wh, off);
+                wl = nl; wh = nh;
+                { const uint32_t x = tp0; tp0 = tp1; tp1 = tp2; tp2 = x; }   // 16 steps further: codon position + 16 = + 1
+            }
+        }
+        __syncthreads();   // nobody still reads s_next / s_end of this unit when thread 0 fetches the next one
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // per-start totals: order ramp, domain choice, duration / start / stop terms, pruning, bucket histogram
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256, 4) k_final(Planes pl, const int64_t *__restrict__ cwoff, const int32_t *__restrict__ clen,
@@ -1225,7 +1484,7 @@ __global__ void __launch_bounds__(256, 4) k_final(Planes pl, const int64_t *__re
                                                const StartRec *const *starts_m, const Acc4 *const *sums_m,
                                                const unsigned long long *counters_m, Cand *const *surv_m, uint32_t *const *bcount_m,
                                                uint32_t *const *cover_m, unsigned long long *surv_counters, uint32_t cap_starts,
-                                               uint32_t cap_surv) {
+                                               uint32_t cap_surv, int pair_walk) {
     const int mi = blockIdx.y;
     const DevModel &dm = models[mi];
     const int lane = lane_id();
@@ -1277,6 +1536,9 @@ __global__ void __launch_bounds__(256, 4) k_final(Planes pl, const int64_t *__re
             const int fullstart = first + kc;
             Acc4 acc = {0, 0, 0, 0};
             if (fullstart <= t - 1) acc = sums[k];
+            // the pair walk advances two positions at a time from the stop: with an odd number of full-order positions it
+            // stopped one above `fullstart`, and that position is added below from the single-position table
+            const bool odd_one = pair_walk && fullstart <= t - 1 && ((t - fullstart) & 1);
             // Early pruning: with the largest possible ramp / start / stop terms of either domain the total stays <= 0 for most
             // starts of spurious ORFs; those never touch the planes or the ramp tables.  (Exact otherwise: only candidates
             // that the full computation would prune as well are dropped, with a 1e-6 guard band.)
@@ -1284,14 +1546,15 @@ __global__ void __launch_bounds__(256, 4) k_final(Planes pl, const int64_t *__re
             const double lgt = 2.0 * log(dl) - 1.3862943611198906;
             bool maybe = false;
             {
-                const double *ub = dm.pair_ub + pair * 6;
+                const double *ub = dm.pair_ub + pair * 8;
+                const double ub1B = odd_one ? ub[6] : 0.0, ub1A = odd_one ? ub[7] : 0.0;
                 if (secB >= 0) {
                     const SectionScalars *sb = dm.sc + secB;
-                    maybe |= acc.oB + ub[0] + lgt + dl * sb->dur_slope + sb->dur_const + (virt ? 0.0 : ub[1]) + (pstop ? 0.0 : ub[2]) > -1e-6;
+                    maybe |= acc.oB + ub1B + ub[0] + lgt + dl * sb->dur_slope + sb->dur_const + (virt ? 0.0 : ub[1]) + (pstop ? 0.0 : ub[2]) > -1e-6;
                 }
                 if (secA >= 0) {
                     const SectionScalars *sa = dm.sc + secA;
-                    maybe |= acc.oA + ub[3] + lgt + dl * sa->dur_slope + sa->dur_const + (virt ? 0.0 : ub[4]) + (pstop ? 0.0 : ub[5]) > -1e-6;
+                    maybe |= acc.oA + ub1A + ub[3] + lgt + dl * sa->dur_slope + sa->dur_const + (virt ? 0.0 : ub[4]) + (pstop ? 0.0 : ub[5]) > -1e-6;
                 }
             }
             if (maybe) {
@@ -1305,6 +1568,19 @@ __global__ void __launch_bounds__(256, 4) k_final(Planes pl, const int64_t *__re
                 uint32_t nb_, dummy;
                 window_bits(nmp, nmp, first, min(kc + 1, t + 3 - first), nb_, dummy);
                 ramp_bad = nb_ != 0;
+            }
+            if (odd_one) {   // position `fullstart`: window of kc+1 letters starting at `first`, codon position 0
+                uint32_t hb, lb;
+                window_bits(lo, hi, first, kc + 1, hb, lb);
+                if (ramp_bad) {   // the same window as the ramp's ambiguity test
+                    const double *pa = dm.pair_amb + pair * 4;
+                    acc.cB += pa[0]; acc.oB += pa[0] - pa[2]; acc.cA += pa[1]; acc.oA += pa[1] - pa[3];
+                } else {
+                    const Quad *q = dm.quad + (size_t)pair * 3 * dm.nfull + ((hb << (kc + 1)) | lb);
+                    const double2 x = __ldg(reinterpret_cast<const double2 *>(q));
+                    const double2 y = __ldg(reinterpret_cast<const double2 *>(q) + 1);
+                    acc.cB += x.x; acc.oB += x.y; acc.cA += y.x; acc.oA += y.y;
+                }
             }
             uint32_t rhb = 0, rlb = 0;   // the kc letters at `first`, read once; order j uses the first j+1 of them
             if (kc > 0 && !ramp_bad) window_bits(lo, hi, first, kc, rhb, rlb);
@@ -1901,7 +2177,8 @@ __global__ void __launch_bounds__(256) k_contig_finish(const ChainBufs *bufs_m, 
 __global__ void __launch_bounds__(128) k_windows(const mgc_gene *const *genes_m, const uint32_t *const *gene_off_m, int n_models,
                                                  const int32_t *__restrict__ clen, const int32_t *__restrict__ stride,
                                                  const int64_t *__restrict__ win_off, int32_t n_contigs, int32_t window,
-                                                 int32_t consecutive, int short_contigs, int32_t *labels, long long *cents_out) {
+                                                 int32_t consecutive, int short_contigs, int32_t *labels, long long *cents_out,
+                                                 unsigned long long *label_hist /* [MGC_MAX_MODELS] or null */) {
     const int64_t c = (int64_t)blockIdx.x;
     if (c >= n_contigs) return;
     const int L = clen[c], st = stride[c];
@@ -1912,7 +2189,8 @@ __global__ void __launch_bounds__(128) k_windows(const mgc_gene *const *genes_m,
     // rule 2: contigs too short for `consecutive` windows get the whole-contig argmax replicated (pipeline.py:227-275)
     const bool whole = !unclassified && (long long)L <= (long long)window + (long long)(consecutive - 1) * st;
     __shared__ long long tot[MGC_MAX_MODELS];
-    if (threadIdx.x < MGC_MAX_MODELS) tot[threadIdx.x] = 0;
+    __shared__ unsigned int hist[MGC_MAX_MODELS];
+    if (threadIdx.x < MGC_MAX_MODELS) { tot[threadIdx.x] = 0; hist[threadIdx.x] = 0; }
     __syncthreads();
     if (whole) {
         for (int m = 0; m < n_models; m++) {
@@ -1944,7 +2222,32 @@ __global__ void __launch_bounds__(128) k_windows(const mgc_gene *const *genes_m,
             if (m == 0 || s > best) { best = s; lab = m; }
         }
         labels[wbase + w] = unclassified ? 0 : lab;
+        if (label_hist) atomicAdd(&hist[unclassified ? 0 : lab], 1u);
     }
+    if (label_hist) {   // labels of the whole input: the smoothing treats all but the two most frequent as noise
+        __syncthreads();
+        if (threadIdx.x < MGC_MAX_MODELS && hist[threadIdx.x]) atomicAdd(&label_hist[threadIdx.x], (unsigned long long)hist[threadIdx.x]);
+    }
+}
+
+// noise labels of Pipeline.find_best_sequence_of_labels (bin/pipeline.py:1084-1086): the labels that occur, ordered as
+// np.argsort(counts)[::-1] orders them (ascending insertion sort is stable, so after the reversal equal counts put the
+// higher label first), minus the first two
+__global__ void k_noise_mask(const unsigned long long *label_hist, int n_models, uint32_t *mask_out) {
+    if (threadIdx.x || blockIdx.x) return;
+    int order[MGC_MAX_MODELS], n = 0;
+    for (int l = 0; l < n_models; l++) {
+        if (!label_hist[l]) continue;
+        int k = n++;
+        while (k > 0 && (label_hist[order[k - 1]] < label_hist[l] || (label_hist[order[k - 1]] == label_hist[l] && order[k - 1] < l))) {
+            order[k] = order[k - 1];
+            k--;
+        }
+        order[k] = l;
+    }
+    uint32_t mask = 0;
+    for (int k = 2; k < n; k++) mask |= 1u << order[k];
+    *mask_out = mask;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1954,10 +2257,12 @@ __global__ void __launch_bounds__(128) k_windows(const mgc_gene *const *genes_m,
 // off the array when a contig starts with a noise label).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(64) k_merge_labels(const int32_t *__restrict__ labels, const int64_t *__restrict__ win_off,
-                                                     int32_t n_contigs, int32_t consecutive, uint32_t noise_mask,
-                                                     int32_t *out, int32_t *run, int32_t *status) {
+                                                     int32_t n_contigs, int32_t consecutive, uint32_t noise_mask_value,
+                                                     const uint32_t *__restrict__ noise_mask_dev, int32_t *out, int32_t *run,
+                                                     int32_t *status) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_contigs) return;
+    const uint32_t noise_mask = noise_mask_dev ? *noise_mask_dev : noise_mask_value;
     const int64_t a = win_off[c];
     const int n = (int)(win_off[c + 1] - a);
     const int32_t *lab = labels + a;
@@ -2012,8 +2317,13 @@ __global__ void __launch_bounds__(64) k_merge_labels(const int32_t *__restrict__
 }
 
 void launch_merge_labels(const int32_t *labels, const int64_t *win_off, int32_t n_contigs, int32_t consecutive, uint32_t noise_mask,
-                         int32_t *out, int32_t *run, int32_t *status, cudaStream_t st) {
-    k_merge_labels<<<(unsigned)((n_contigs + 63) / 64), 64, 0, st>>>(labels, win_off, n_contigs, consecutive, noise_mask, out, run, status);
+                         const uint32_t *noise_mask_dev, int32_t *out, int32_t *run, int32_t *status, cudaStream_t st) {
+    k_merge_labels<<<(unsigned)((n_contigs + 63) / 64), 64, 0, st>>>(labels, win_off, n_contigs, consecutive, noise_mask, noise_mask_dev,
+                                                                     out, run, status);
+}
+
+void launch_noise_mask(const unsigned long long *label_hist, int n_models, uint32_t *mask_out, cudaStream_t st) {
+    k_noise_mask<<<1, 32, 0, st>>>(label_hist, n_models, mask_out);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2163,8 +2473,9 @@ int launch_orf_prep(Planes pl, const uint32_t *gcpre, const int64_t *cwoff, cons
 
 int launch_item_sort(const ItemRec *const *items_m, ItemRec *const *sorted_m, uint32_t *const *hist_m, uint32_t *const *item_off_m,
                      uint32_t *const *unit_off_m, const DevModel *models, int n_models, uint32_t *unit_totals,
-                     const unsigned long long *counters_m, uint32_t cap_items, int n_tiles, int n_sm, cudaStream_t st) {
-    k_item_plan<<<n_models, 1024, 0, st>>>(hist_m, item_off_m, unit_off_m, models, unit_totals, const_cast<unsigned long long *>(counters_m), n_tiles);
+                     const unsigned long long *counters_m, uint32_t cap_items, int n_tiles, int n_sm, bool pair_walk, cudaStream_t st) {
+    k_item_plan<<<n_models, 1024, 0, st>>>(hist_m, item_off_m, unit_off_m, models, unit_totals, const_cast<unsigned long long *>(counters_m), n_tiles,
+                                           pair_walk ? (uint32_t)WALK2_CHUNK : (uint32_t)WALK_CHUNK);
     dim3 grid(n_sm * 4, n_models);
     k_item_scatter<<<grid, 256, 0, st>>>(items_m, sorted_m, hist_m, counters_m, cap_items);
     return 2;
@@ -2176,10 +2487,21 @@ int launch_walk(Planes pl, const int64_t *cwoff, const DevModel *models, int n_m
                 const OrfRec *const *orfs_m,
                 const StartRec *const *starts_m, const ItemRec *const *items_m, const uint32_t *const *item_off_m,
                 const uint32_t *const *unit_off_m, const uint32_t *unit_totals, void *const *sums_m, unsigned int *next_unit, int n_sm,
-                cudaStream_t st) {
+                int pair_smem, bool pair_orders_uniform, cudaStream_t st) {
     const int smem = walk_smem_bytes(max_cod_order, max_non_order);
     Acc4 *const *sums = reinterpret_cast<Acc4 *const *>(sums_m);
-    if (smem <= 110 * 1024) {
+    if (pair_smem > 0) {
+        // pair tables (two positions per lookup): one CTA per SM with the whole shared memory
+        if (max_cod_order == 4 && max_non_order == 2 && pair_orders_uniform) {
+            cudaFuncSetAttribute(k_walk_pair<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, WALK2_SMEM_MAX);
+            k_walk_pair<4, 2><<<n_sm, WALK2_THREADS, pair_smem, st>>>(pl, models, n_models, starts_m, items_m, item_off_m, unit_off_m,
+                                                                      unit_totals, sums, next_unit);
+        } else {
+            cudaFuncSetAttribute(k_walk_pair<-1, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, WALK2_SMEM_MAX);
+            k_walk_pair<-1, -1><<<n_sm, WALK2_THREADS, pair_smem, st>>>(pl, models, n_models, starts_m, items_m, item_off_m, unit_off_m,
+                                                                        unit_totals, sums, next_unit);
+        }
+    } else if (smem <= 110 * 1024) {
         cudaFuncSetAttribute(k_walk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
         k_walk<true><<<n_sm * 2, WALK_UNIT, smem, st>>>(pl, cwoff, models, n_models, orfs_m, starts_m, items_m, item_off_m, unit_off_m,
                                                         unit_totals, sums, next_unit);
@@ -2194,10 +2516,10 @@ int launch_walk(Planes pl, const int64_t *cwoff, const DevModel *models, int n_m
 void launch_final(Planes pl, const int64_t *cwoff, const int32_t *clen, const DevModel *models, int n_models, const OrfRec *const *orfs_m,
                   const StartRec *const *starts_m, void *const *sums_m, const unsigned long long *counters_m, Cand *const *surv_m,
                   uint32_t *const *bcount_m, uint32_t *const *cover_m, unsigned long long *surv_counters, uint32_t cap_starts, uint32_t cap_surv, int n_sm,
-                  cudaStream_t st) {
+                  bool pair_walk, cudaStream_t st) {
     dim3 grid(n_sm * 8, n_models);
     k_final<<<grid, 256, 0, st>>>(pl, cwoff, clen, models, orfs_m, starts_m, reinterpret_cast<const Acc4 *const *>(sums_m), counters_m,
-                                  surv_m, bcount_m, cover_m, surv_counters, cap_starts, cap_surv);
+                                  surv_m, bcount_m, cover_m, surv_counters, cap_starts, cap_surv, pair_walk ? 1 : 0);
 }
 
 void launch_scatter(const Cand *const *surv_m, Cand *const *sorted_m, uint32_t *const *boff_m,
@@ -2227,9 +2549,9 @@ int launch_gather(const ChainBufs *bufs_m, mgc_gene *const *genes_m, const int32
 
 void launch_windows(const mgc_gene *const *genes_m, const uint32_t *const *gene_off_m, int n_models, const int32_t *clen,
                     const int32_t *stride, const int64_t *win_off, int32_t n_contigs, int32_t window, int32_t consecutive,
-                    int short_contigs, int32_t *labels, long long *cents, cudaStream_t st) {
+                    int short_contigs, int32_t *labels, long long *cents, unsigned long long *label_hist, cudaStream_t st) {
     k_windows<<<(unsigned)n_contigs, 128, 0, st>>>(genes_m, gene_off_m, n_models, clen, stride, win_off, n_contigs, window,
-                                                    consecutive, short_contigs, labels, cents);
+                                                    consecutive, short_contigs, labels, cents, label_hist);
 }
 
 }  // namespace mgc

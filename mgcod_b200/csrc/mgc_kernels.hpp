@@ -40,16 +40,17 @@ int launch_orf_prep(Planes pl, const uint32_t *gcpre, const int64_t *cwoff, cons
                     int n_sm, cudaStream_t st);
 int launch_item_sort(const ItemRec *const *items_m, ItemRec *const *sorted_m, uint32_t *const *hist_m, uint32_t *const *item_off_m,
                      uint32_t *const *unit_off_m, const DevModel *models, int n_models, uint32_t *unit_totals,
-                     const unsigned long long *counters_m, uint32_t cap_items, int n_tiles, int n_sm, cudaStream_t st);
+                     const unsigned long long *counters_m, uint32_t cap_items, int n_tiles, int n_sm, bool pair_walk, cudaStream_t st);
 int launch_walk(Planes pl, const int64_t *cwoff, const DevModel *models, int n_models, int max_cod_order, int max_non_order,
                 const OrfRec *const *orfs_m,
                 const StartRec *const *starts_m, const ItemRec *const *items_m, const uint32_t *const *item_off_m,
                 const uint32_t *const *unit_off_m, const uint32_t *unit_totals, void *const *sums_m, unsigned int *next_unit, int n_sm,
-                cudaStream_t st);
+                int pair_smem /* bytes of the pair walk's table, 0 = single-position walk */,
+                bool pair_orders_uniform /* every model has exactly the orders max_cod_order / max_non_order */, cudaStream_t st);
 void launch_final(Planes pl, const int64_t *cwoff, const int32_t *clen, const DevModel *models, int n_models, const OrfRec *const *orfs_m,
                   const StartRec *const *starts_m, void *const *sums_m, const unsigned long long *counters_m, Cand *const *surv_m,
                   uint32_t *const *bcount_m, uint32_t *const *cover_m, unsigned long long *surv_counters, uint32_t cap_starts, uint32_t cap_surv, int n_sm,
-                  cudaStream_t st);
+                  bool pair_walk, cudaStream_t st);
 void launch_scatter(const Cand *const *surv_m, Cand *const *sorted_m, uint32_t *const *boff_m,
                     const unsigned long long *surv_counters, const int64_t *cwoff, uint32_t cap_surv, int n_models, int n_sm,
                     cudaStream_t st);
@@ -59,9 +60,11 @@ int launch_gather(const ChainBufs *bufs_m, mgc_gene *const *genes_m, const int32
                   int32_t n_contigs, long long *model_cents, int n_models, int n_sm, cudaStream_t st);
 void launch_windows(const mgc_gene *const *genes_m, const uint32_t *const *gene_off_m, int n_models, const int32_t *clen,
                     const int32_t *stride, const int64_t *win_off, int32_t n_contigs, int32_t window, int32_t consecutive,
-                    int short_contigs, int32_t *labels, long long *cents, cudaStream_t st);
-
+                    int short_contigs, int32_t *labels, long long *cents, unsigned long long *label_hist /* [MGC_MAX_MODELS], may be null */,
+                    cudaStream_t st);
+// noise_mask_dev != null: the mask is read from device memory (written by launch_noise_mask) instead of noise_mask
 void launch_merge_labels(const int32_t *labels, const int64_t *win_off, int32_t n_contigs, int32_t consecutive, uint32_t noise_mask,
-                         int32_t *out, int32_t *run, int32_t *status, cudaStream_t st);
+                         const uint32_t *noise_mask_dev, int32_t *out, int32_t *run, int32_t *status, cudaStream_t st);
+void launch_noise_mask(const unsigned long long *label_hist, int n_models, uint32_t *mask_out, cudaStream_t st);
 
 }  // namespace mgc

@@ -33,6 +33,106 @@ def contig_rows(df, index: dict, contig):
     return df.iloc[:0] if pos is None else df.iloc[pos]
 
 
+def cents_of(logodd: np.ndarray) -> np.ndarray:
+    """the %.2f value of each log-odds score in 1/100 units, as printf rounds it (exact decimal value of the double, ties
+    to even): rint(v * 100) except within 1e-6 of a rounding boundary, where the formatted text decides — the rule of the
+    C writer (mgc_host.cpp TextOut::fixed2), so frames built from arrays equal frames parsed from the GFF files"""
+    a = np.abs(logodd) * 100.0
+    c = np.rint(a)
+    near = np.flatnonzero(np.abs(a - np.floor(a) - 0.5) < 1e-6)
+    for i in near:
+        c[i] = round(abs(float("%.2f" % logodd[i])) * 100.0)
+    return (np.sign(logodd) * c).astype(np.int64)
+
+
+class GeneFrames:
+    """label -> DataFrame of one model's genes in the reference's schema (bin/data.py:66-106 + the ``contig`` column of
+    bin/pipeline.py:68-76), built from the decoded gene arrays instead of re-reading the GFF files the run has just
+    written, and only when somebody asks: a metagenome run in --isoforms mode touches the rows of the few contigs with a
+    genetic-code switch, not 5 million attribute strings.  Behaves like the reference's dict of four frames."""
+
+    COLUMNS = GFF_COLUMNS + ["length", "contig"]
+
+    def __init__(self, genes_per_model, ids, codes=MGCOD_CODES):
+        self.genes = list(genes_per_model)            # GENE_DTYPE, (contig, left) order, contig = index into ids
+        self.ids = np.asarray(list(ids), dtype=object)
+        self.codes = tuple(codes)
+        n = len(self.ids)
+        self.first = [np.searchsorted(g["contig"], np.arange(n + 1)) for g in self.genes]   # row range of every contig
+        self._index_of = None
+        self._full = {}
+
+    # -- dict protocol (the reference iterates .items() / .values() and indexes by label)
+    def __len__(self):
+        return len(self.genes)
+
+    def __iter__(self):
+        return iter(range(len(self.genes)))
+
+    def keys(self):
+        return range(len(self.genes))
+
+    def values(self):
+        return [self[k] for k in self.keys()]
+
+    def items(self):
+        return [(k, self[k]) for k in self.keys()]
+
+    def __contains__(self, k):
+        return isinstance(k, (int, np.integer)) and 0 <= k < len(self.genes)
+
+    def __getitem__(self, lab):
+        lab = int(lab)
+        if lab not in self._full:
+            self._full[lab] = self.rows(lab, 0, len(self.genes[lab]))
+        return self._full[lab]
+
+    def contig_index(self, contig_id):
+        if self._index_of is None:
+            self._index_of = {c: i for i, c in enumerate(self.ids.tolist())}
+        return self._index_of.get(contig_id)
+
+    def contig_range(self, lab, contig_id):
+        c = self.contig_index(contig_id)
+        if c is None:
+            return 0, 0
+        f = self.first[int(lab)]
+        return int(f[c]), int(f[c + 1])
+
+    def contig_frame(self, lab, contig_id):
+        """the rows of one contig — what ``df[df.contig == contig_id]`` gives in the reference"""
+        a, b = self.contig_range(lab, contig_id)
+        if int(lab) in self._full:
+            return self._full[int(lab)].iloc[a:b]
+        return self.rows(lab, a, b)
+
+    def rows(self, lab, a, b):
+        g = self.genes[int(lab)][a:b]
+        code = self.codes[int(lab)]
+        n = len(g)
+        seq = self.ids[g["contig"]] if n else np.zeros(0, dtype=object)
+        left, right = g["left"].astype(np.int64), g["right"].astype(np.int64)
+        length = right - left + 1
+        dom, pl, pr, gc = g["domain"].tolist(), g["partial_left"].tolist(), g["partial_right"].tolist(), g["gc"].tolist()
+        ln = length.tolist()
+        attrs = np.empty(n, dtype=object)
+        attrs[:] = [f"gene_id {a + 1 + i}; gene_type {'archaea' if dom[i] else 'bacteria'}; "
+                    + (f"partial {pl[i]}{pr[i]}; " if (pl[i] or pr[i]) else "") + f"gc {gc[i]}; length {ln[i]};" for i in range(n)]
+        df = pd.DataFrame({"sequence": pd.array(seq, dtype="str") if n else pd.array([], dtype="str"),
+                           "source": pd.array(np.full(n, f"GeneMark.hmm2_{code}", dtype=object), dtype="str"),
+                           "feature": pd.array(np.full(n, "CDS", dtype=object), dtype="str"),
+                           "start": left, "end": right, "logodd": cents_of(g["logodd"]) / 100.0,
+                           "strand": pd.array(np.where(g["strand"] > 0, "+", "-").astype(object), dtype="str"),
+                           "phase": np.zeros(n, dtype=np.int64), "attributes": pd.array(attrs, dtype="str"), "length": length},
+                          index=pd.RangeIndex(a, b))
+        df["contig"] = list(df.sequence.values)      # as bin/pipeline.py:73-76 adds it
+        return df
+
+
+def frame_columns(frames) -> list:
+    return list(frames.COLUMNS) if isinstance(frames, GeneFrames) else list(frames[0].columns.values)
+
+
 class Record:
     """The slice of Biopython's SeqRecord that Mgcod touches: ``id``, ``description``, ``seq``, ``len()``.
     ``seq`` may be given as a uint8 view into a :class:`Fasta` buffer; it is decoded to ``str`` on first use."""
@@ -119,8 +219,11 @@ class Data:
         self._fasta = Fasta(self.path_to_genome)          # native reader; the letters stay in its (page-locked) buffer
         recs = self._fasta.records()
         self._file_order = recs
+        # the reference sorts a multi-FASTA by record id (bin/data.py:122); the engine keeps file order (gmhmmp2's output order)
+        self._sorted_to_file = np.arange(len(recs), dtype=np.int64)
         if len(recs) > 1:
-            recs = [recs[x] for x in np.argsort([r.id for r in recs])]
+            self._sorted_to_file = np.argsort(self._fasta.ids)            # the reference's very call
+            recs = [recs[x] for x in self._sorted_to_file.tolist()]
         self.records = recs
         return recs
 
@@ -128,52 +231,89 @@ class Data:
         return f"{self.path_to_predictions}mgm_{code}_{self.species}.gff"
 
     # -- bin/data.py:31-54
-    def run_mgm(self):
+    def run_mgm(self, need_genes=False):
+        """Decode and write the four ``mgm_<code>_<species>.gff`` files (those that do not exist yet, bin/data.py:39-51).  The
+        files are formatted by the C writer on background threads (no GIL) while the caller goes on with the gene arrays;
+        :meth:`finish_writes` waits for them.  ``need_genes``: decode even when all four files are cached (--isoforms works on
+        the decoded arrays and on the sequence resident on the device)."""
         logging.info(f"Running MGM models on {self.species}")
         if self.verbose:
             print(f"Running MGM models on {self.species}")
         missing = [c for c in MGCOD_CODES if not os.path.isfile(self._gff_path(c))]
-        if not missing:
+        if not missing and not need_genes:
             return
         if self.records is None:
             self.read_dna_sequence()
         recs = self._file_order                       # gmhmmp2 writes records in file order
+        self.result = self._decode()
+        self._decoded_order = recs
+        if not missing:
+            return
+        ids = self._fasta.ids if hasattr(self, "_fasta") else [r.id for r in recs]
+        lens = np.diff(self._fasta.offsets) if hasattr(self, "_fasta") else [len(r) for r in recs]
+        # the four files are formatted side by side (the C writer runs without the GIL)
+        from concurrent.futures import ThreadPoolExecutor
+        self._writer = ThreadPoolExecutor(max_workers=4)
+        self._write_jobs = [self._writer.submit(self.result.write, mi, ids, lens, str(self.path_to_genome),
+                                                os.path.join(self.model_dir, f"mgm_{code}.mod"), code, self._gff_path(code), "gff")
+                            for mi, code in enumerate(MGCOD_CODES) if code in missing]
+
+    def finish_writes(self):
+        """waits for the GFF files of :meth:`run_mgm`; raises what a writer raised"""
+        jobs, self._write_jobs = getattr(self, "_write_jobs", []), []
+        try:
+            for j in jobs:
+                j.result()
+        finally:
+            if getattr(self, "_writer", None) is not None:
+                self._writer.shutdown(wait=True)
+                self._writer = None
+
+    def _decode(self):
+        """all contigs of the file under the four parameter files on the GPU → engine.Result"""
         self.engine = shared_engine(self.model_dir, self.device)
         # inputs larger than one device batch are streamed in pieces and merged on the host (GFF files only: the window
         # labels of --isoforms and the recoded-stop scan need the whole input resident)
-        self.result = self.engine.decode_large(self._fasta.buffer, self._fasta.offsets)
+        result = self.engine.decode_large(self._fasta.buffer, self._fasta.offsets)
         self.engine._resident_owner = self if int(self._fasta.offsets[-1]) <= self.engine.MAX_BATCH_BP else None
-        self._decoded_order = recs
-        ids = [r.id for r in recs]
-        lens = [len(r) for r in recs]
-        # the four files are formatted side by side (the C writer runs without the GIL)
-        from concurrent.futures import ThreadPoolExecutor
-        with ThreadPoolExecutor(max_workers=4) as pool:
-            jobs = [pool.submit(self.result.write, mi, ids, lens, str(self.path_to_genome),
-                                os.path.join(self.model_dir, f"mgm_{code}.mod"), code, self._gff_path(code), "gff")
-                    for mi, code in enumerate(MGCOD_CODES) if code in missing]
-            for j in jobs:
-                j.result()
+        return result
 
     def ensure_resident(self):
-        """→ (engine, record ids in batch order) with this genome's packed sequence resident on the device — what
-        :class:`mgcod_b200.results.Results` scans for recoded stops.  Decodes again when run_mgm was served from the
-        on-disk cache (or another genome has been decoded since)."""
+        """→ (engine, record ids in batch order) with this genome's genes and packed sequence resident on the device — what
+        the window labels of --isoforms and the recoded-stop scan of :class:`mgcod_b200.results.Results` work on.  Decodes
+        again when run_mgm was served from the on-disk cache or another genome has been decoded since; an input that does
+        not fit one device batch cannot be made resident."""
         if self.records is None:
             self.read_dna_sequence()
         recs = self._file_order
         if self.engine is None:
             self.engine = shared_engine(self.model_dir, self.device)
         if self.result is None or getattr(self.engine, "_resident_owner", None) is not self:
+            if int(self._fasta.offsets[-1]) > self.engine.MAX_BATCH_BP:
+                raise RuntimeError(f"{self.path_to_genome}: {int(self._fasta.offsets[-1])} letters exceed one device batch "
+                                   f"({self.engine.MAX_BATCH_BP}); --isoforms and the recoded-stop scan need the whole input "
+                                   f"resident — split the file (bin/multiprocess_mgcod.py usage) or run the default mode")
             self.result = self.engine.decode_buffer(self._fasta.buffer, self._fasta.offsets)
         self.engine._resident_owner = self
         return self.engine, [r.id for r in recs]
+
+    def gene_frames(self):
+        """label → DataFrame of that model's genes (the reference's ``label_to_gene_coords``).  From the decoded arrays when
+        this run decoded (no parse of the files just written), else parsed from the cached GFF files as the reference does."""
+        if self.result is not None:
+            ids = self._fasta.ids if hasattr(self, "_fasta") else [r.id for r in self._file_order]
+            return GeneFrames([self.result.genes(m) for m in range(len(MGCOD_CODES))], ids)
+        frames = self.extract_gene_coords()
+        for df in frames:
+            df.loc[:, "contig"] = list(df.sequence.values)       # bin/pipeline.py:73-76
+        return dict(enumerate(frames))
 
     # -- bin/data.py:56-106
     def extract_gene_coords(self):
         logging.info(f"Extracting gene coordinates predicted in {self.species}")
         if self.verbose:
             print(f"Extracting gene coordinates predicted in {self.species}")
+        self.finish_writes()
         frames = []
         for code in MGCOD_CODES:
             df = pd.read_csv(self._gff_path(code), sep="\t", header=None, comment="#", names=GFF_COLUMNS)

@@ -281,10 +281,36 @@ class Engine:
         nw = int(offs[-1])
         labels = np.zeros(max(nw, 1), dtype=np.int32)
         cents = np.zeros((max(nw, 1), self.n_models), dtype=np.int64)
-        _check(L.mgc_window_labels(self._h, st.ctypes.data_as(C.POINTER(C.c_int32)), window, consecutive, int(short_contigs),
+        _check(L.mgc_window_labels(self._h, st.ctypes.data_as(C.POINTER(C.c_int32)), len(lens), window, consecutive, int(short_contigs),
                                    offs.ctypes.data_as(C.POINTER(C.c_int64)), labels.ctypes.data_as(C.POINTER(C.c_int32)),
                                    cents.ctypes.data_as(C.POINTER(C.c_int64))))
         return offs, labels[:nw], cents[:nw]
+
+    def isoform_labels(self, contig_len: Sequence[int], stride: Sequence[int], window: int, consecutive: int,
+                       short_contigs: bool) -> tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray, np.ndarray]:
+        """Window sums, argmax labels and their smoothing for the last decoded batch in one device call (reference
+        bin/pipeline.py:157-385, then :98-110 with :1064-1168): → (win_offsets[n+1], labels[nwin], cents[nwin, n_models],
+        merged[nwin], status[n]).  Contigs whose status is 1 (the reference raises IndexError there) keep their input labels."""
+        L = _lib.lib()
+        lens = np.ascontiguousarray(contig_len, dtype=np.int64)
+        st = np.ascontiguousarray(stride, dtype=np.int32)
+        n = len(lens)
+        offs = np.zeros(n + 1, dtype=np.int64)
+        _check(L.mgc_window_counts(lens.ctypes.data_as(C.POINTER(C.c_int64)), st.ctypes.data_as(C.POINTER(C.c_int32)), n,
+                                   window, consecutive, int(short_contigs), offs.ctypes.data_as(C.POINTER(C.c_int64))))
+        nw = int(offs[-1])
+        labels = np.empty(max(nw, 1), dtype=np.int32)
+        merged = np.empty(max(nw, 1), dtype=np.int32)
+        cents = np.empty((max(nw, 1), self.n_models), dtype=np.int64)
+        status = np.zeros(max(n, 1), dtype=np.int32)
+        i32p = C.POINTER(C.c_int32)
+        _check(L.mgc_isoform_labels(self._h, st.ctypes.data_as(i32p), n, window, consecutive, int(short_contigs),
+                                    offs.ctypes.data_as(C.POINTER(C.c_int64)), labels.ctypes.data_as(i32p),
+                                    cents.ctypes.data_as(C.POINTER(C.c_int64)), merged.ctypes.data_as(i32p), status.ctypes.data_as(i32p)))
+        labels, merged, cents, status = labels[:nw], merged[:nw], cents[:nw], status[:n]
+        for c in np.flatnonzero(status):
+            merged[offs[c]:offs[c + 1]] = labels[offs[c]:offs[c + 1]]
+        return offs, labels, cents, merged, status
 
     def merge_labels_flat(self, flat: np.ndarray, offs: np.ndarray, consecutive: int) -> tuple[np.ndarray, np.ndarray]:
         """Label smoothing of all contigs in one device call on the flat layout ``window_labels`` returns.

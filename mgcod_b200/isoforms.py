@@ -30,7 +30,7 @@ import numpy as np
 import pandas as pd
 
 from . import labels as L
-from .data import contig_rows, rows_by_contig
+from .data import GeneFrames, contig_rows, frame_columns, rows_by_contig
 
 
 def _rest(attributes: str) -> str:
@@ -383,37 +383,50 @@ def compare_contig(S1: _GeneSet, S2: _GeneSet, code_1, code_2, tolerance: int, s
 
 def compare_sets_of_predicted_genes(P):
     """``P`` is a :class:`mgcod_b200.pipeline.Pipeline` after label smoothing.  Returns what the reference returns:
-    (coords, gene_labels_to_gcode, coords_w_isoforms)."""
+    (coords, gene_labels_to_gcode, coords_w_isoforms).
+
+    Only contigs whose smoothed labels name two genetic codes are compared; the others contribute nothing to the isoform
+    table and a one-entry dict to ``gene_labels_to_gcode``.  ``coords`` (the plain table, which nothing downstream reads)
+    is returned as a :class:`LazyCoords` that builds the frame when somebody looks at it."""
     logging.info(f"Comparing sets of predicted genes in {P.species}")
     if P.verbose:
         print(f"Comparing sets of predicted genes in {P.species}")
-    columns = list(P.label_to_gene_coords[0].columns.values)
-    index = {lab: rows_by_contig(df) for lab, df in P.label_to_gene_coords.items()}
+    frames = P.label_to_gene_coords
+    columns = frame_columns(frames)
+    lazy = isinstance(frames, GeneFrames)
+    index = None if lazy else {lab: rows_by_contig(df) for lab, df in frames.items()}
+
+    def contig_frame(lab, contig_id):
+        return frames.contig_frame(lab, contig_id) if lazy else contig_rows(frames[lab], index[lab], contig_id)
+
+    lmin, lmax = getattr(P, "_label_min", None), getattr(P, "_label_max", None)
+    if lmin is None:
+        lmin = np.array([int(np.min(u)) if len(u) else -1 for u in P.updated_genome_labels], dtype=np.int64)
+        lmax = np.array([int(np.max(u)) if len(u) else -1 for u in P.updated_genome_labels], dtype=np.int64)
     gene_labels_to_gcode = {}
-    compared: list[pd.DataFrame] = []
-    single: dict[int, list] = {}
+    compared: dict[int, pd.DataFrame] = {}
+    single: list[tuple[int, int]] = []          # (position in P.sequence, label) of contigs with one genetic code
     with_isoforms: list[dict] = []
+    code_of = {int(k): v for k, v in P.label_to_gcode.items()}
+    one_code = (lmin == lmax).tolist()
+    lmin_l = lmin.tolist()
+    messages = []
     for n, rec in enumerate(P.sequence):
-        labs = np.unique(P.updated_genome_labels[n])
-        if labs.shape[0] == 1:
+        if one_code[n]:
             # Nothing goes to the isoform table (the reference's append to it is commented out, bin/pipeline.py:577), so the
             # final GFF of a mixed input lists only the contigs with a switch.  One deliberate difference in the plain
             # table, which nothing downstream reads: the reference appends the model's genes of EVERY contig here
             # (no contig filter, :574-576) — contigs x genes rows for a metagenome; this keeps the contig's own genes.
-            pos = index[int(labs[0])].get(rec.id)
-            if pos is not None:
-                single.setdefault(int(labs[0]), []).append((n, pos))     # taken from the model's table in one go below
-            gene_labels_to_gcode[rec.id] = {1: P.label_to_gcode[int(labs[0])]}
+            single.append((n, lmin_l[n]))
+            gene_labels_to_gcode[rec.id] = {1: code_of[lmin_l[n]]}
             continue
+        labs = np.unique(P.updated_genome_labels[n])
         label_1, label_2 = int(labs[0]), int(labs[1])
         code_1, code_2 = P.label_to_gcode[label_1], P.label_to_gcode[label_2]
-        msg = f"Contig {rec.id} in {P.species} carries genetic code {code_1} and {code_2}"
-        logging.info(msg)
-        if P.verbose:
-            print(msg)
+        messages.append(f"Contig {rec.id} in {P.species} carries genetic code {code_1} and {code_2}")
         gene_labels_to_gcode[rec.id] = {1: str(code_1), 2: str(code_2), 3: f"{code_1}_{code_2}"}
-        S1 = _GeneSet(contig_rows(P.label_to_gene_coords[label_1], index[label_1], rec.id))
-        S2 = _GeneSet(contig_rows(P.label_to_gene_coords[label_2], index[label_2], rec.id))
+        S1 = _GeneSet(contig_frame(label_1, rec.id))
+        S2 = _GeneSet(contig_frame(label_2, rec.id))
         cur, iso = compare_contig(S1, S2, code_1, code_2, P.tolerance, rec.seq)
         # ref: DataFrame.sort_values('start') on an object column = numpy's quicksort over Python ints; rows with equal
         # starts (an isoform pair's two genes) come out in that sort's order, and the smoothing below sees them so
@@ -424,22 +437,48 @@ def compare_sets_of_predicted_genes(P):
                                                  P.consecutive_gene_labels, allow_multiple_labels=True)
         frame = pd.DataFrame(cur, columns=columns + ["gene_label"])
         frame["updated_gene_label"] = updated
-        frame["_block"] = n
-        compared.append(frame)
+        compared[n] = frame
         with_isoforms.extend(iso)
-        msg = f"Identified {sum(1 for r in iso if r['logodd'] == '.')} possible isoforms in {rec.id} in {P.species}"
-        logging.info(msg)
+        messages.append(f"Identified {sum(1 for r in iso if r['logodd'] == '.')} possible isoforms in {rec.id} in {P.species}")
+    if messages:
+        logging.info("\n".join(messages))
         if P.verbose:
-            print(msg)
-    for lab, pieces in single.items():
-        frame = P.label_to_gene_coords[lab].iloc[np.concatenate([pos for _, pos in pieces])].copy()
-        frame["updated_gene_label"] = 1
-        frame["_block"] = np.concatenate([np.full(len(pos), n, dtype=np.int64) for n, pos in pieces])
-        compared.append(frame)
-    if compared:       # one block per contig, in contig order
-        coords = pd.concat(compared, sort=True)
-        coords = coords.iloc[np.argsort(coords["_block"].values, kind="stable")].drop(columns="_block")
-    else:
-        coords = pd.DataFrame(columns=columns)
+            print("\n".join(messages))
+
+    def build_coords():       # one block per contig, in contig order
+        blocks = dict(compared)
+        for n, lab in single:
+            f = contig_frame(lab, P.sequence[n].id)
+            if len(f):
+                f = f.copy()
+                f["updated_gene_label"] = 1
+                blocks[n] = f
+        if not blocks:
+            return pd.DataFrame(columns=columns)
+        return pd.concat([blocks[n] for n in sorted(blocks)], sort=True)
+
     coords_w_isoforms = pd.DataFrame(with_isoforms, columns=columns + ["gene_label"])
-    return coords, gene_labels_to_gcode, coords_w_isoforms
+    return LazyCoords(build_coords), gene_labels_to_gcode, coords_w_isoforms
+
+
+class LazyCoords:
+    """The plain comparison table (``Pipeline.coords``): every gene of every contig with its label.  Nothing in the
+    reference or here reads it after it is made, and for a metagenome it is the whole gene table, so it is only put
+    together when somebody touches it (any attribute / item access goes to the frame)."""
+
+    def __init__(self, build):
+        self._build, self._frame = build, None
+
+    def frame(self):
+        if self._frame is None:
+            self._frame = self._build()
+        return self._frame
+
+    def __getattr__(self, name):
+        return getattr(self.frame(), name)
+
+    def __getitem__(self, key):
+        return self.frame()[key]
+
+    def __len__(self):
+        return len(self.frame())

@@ -23,7 +23,7 @@ import numpy as np
 
 from . import isoforms as iso_compare
 from . import labels as L
-from .data import Data, rows_by_contig
+from .data import Data, GeneFrames, rows_by_contig
 from .engine import MGCOD_CODES
 
 
@@ -52,39 +52,58 @@ class Pipeline:
         self.device = device
         self.coords_w_isoforms = None
 
+    # the reference's four frame attributes, built on first use (GeneFrames)
+    gene_coords_11 = property(lambda self: self.label_to_gene_coords[0])
+    gene_coords_4 = property(lambda self: self.label_to_gene_coords[1])
+    gene_coords_15 = property(lambda self: self.label_to_gene_coords[2])
+    gene_coords_101 = property(lambda self: self.label_to_gene_coords[3])
+
     def __call__(self):
         data = Data(self.path_to_genome, self.path_to_predictions, self.verbose, self.cwd, self.species,
                     model_dir=self.model_dir, device=self.device)
         self.data = data
         self.sequence = data.read_dna_sequence()
         self.nr_contigs = len(self.sequence)
-        data.run_mgm()
-        (self.gene_coords_11, self.gene_coords_4, self.gene_coords_15, self.gene_coords_101) = data.extract_gene_coords()
-        for df in (self.gene_coords_11, self.gene_coords_4, self.gene_coords_15, self.gene_coords_101):
-            df.loc[:, "contig"] = list(df.sequence.values)
-        self.label_to_gene_coords = {0: self.gene_coords_11, 1: self.gene_coords_4, 2: self.gene_coords_15,
-                                     3: self.gene_coords_101}
+        data.run_mgm(need_genes=self.isoforms)      # the four GFF files are written in the background meanwhile
+        try:
+            self._analyse()
+        finally:
+            data.finish_writes()
+
+    def _analyse(self):
+        data = self.data
+        # label -> frame of that model's genes (reference: four DataFrames parsed back from the GFF files, plus the `contig`
+        # column of bin/pipeline.py:68-76); here built from the decoded arrays, lazily
+        self.label_to_gene_coords = data.gene_frames()
         if not self.isoforms:
             self.genome_label = self.classify_complete_sequence()
             self.coords_w_isoforms = self.label_to_gene_coords[self.gcode_to_label[self.genome_label]]
             return
-        self.genome_label, self.logodd_scores = self.identify_most_common_codes()
         n = self.consecutive_windows
-        padded = self.circular and self.nr_contigs == 1
-        if padded:
-            # circular single contig: wrap n labels around both ends (pipeline.py:91-97)
+        if self.circular and self.nr_contigs == 1:
+            self.genome_label, self.logodd_scores = self.identify_most_common_codes()
+            # circular single contig: wrap n labels around both ends (pipeline.py:91-97), smooth, drop the padding
             first, last = self.genome_label[0][:n].copy(), self.genome_label[0][-n:].copy()
             if first.shape[0] < n or last.shape[0] < n:
                 self.consecutive_windows = n = min(first.shape[0], last.shape[0])
                 warnings.warn(f"Setting consecutive windows to {n}")
-            self.genome_label = [np.concatenate([last, self.genome_label[0].copy(), first])]
-        # smoothing of every contig's labels in one device call (host restatement: labels.find_best_sequence_of_labels)
-        updated = self.data.engine.merge_labels(self.genome_label, n)
-        if padded:
-            updated = [updated[0][n:-n]]
-            self.genome_label = [self.genome_label[0][n:-n]]
+            padded = [np.concatenate([last, self.genome_label[0].copy(), first])]
+            updated = [self.data.engine.merge_labels(padded, n)[0][n:-n]]
+        else:
+            # window sums, labels and their smoothing in one device call (host restatement: labels.find_best_sequence_of_labels)
+            self.genome_label, self.logodd_scores, updated = self.identify_most_common_codes(smooth=True)
         self.updated_genome_labels = updated
-        if np.unique(np.concatenate(updated)).shape[0] == 1:
+        flat = np.concatenate(updated) if updated else np.zeros(0, dtype=np.int64)
+        # per contig: smallest / largest smoothed label (equal = one genetic code on that contig)
+        sizes = np.array([u.shape[0] for u in updated], dtype=np.int64)
+        starts = np.concatenate([[0], np.cumsum(sizes)[:-1]]) if len(sizes) else np.zeros(0, dtype=np.int64)
+        nonempty = sizes > 0
+        self._label_min = np.full(len(sizes), -1, dtype=np.int64)
+        self._label_max = np.full(len(sizes), -1, dtype=np.int64)
+        if nonempty.any():
+            self._label_min[nonempty] = np.minimum.reduceat(flat, starts[nonempty])
+            self._label_max[nonempty] = np.maximum.reduceat(flat, starts[nonempty])
+        if np.unique(flat).shape[0] == 1:
             code = self.label_to_gcode[int(updated[0][0])]
             logging.info(f"{self.species} is genetic code {code}")
             if self.verbose:
@@ -97,6 +116,9 @@ class Pipeline:
         self.confident_1, self.confident_2, self.segment_labels = self.segment_genome_based_on_window_labels()
         self.predicted_switch_regions = {}
         for k, seq in enumerate(self.sequence):
+            if self._label_min[k] == self._label_max[k]:
+                self.predicted_switch_regions[seq.id] = (self.updated_genome_labels[k][:1].copy(), [])
+                continue
             segs = sorted(self.confident_1[seq.id] + self.confident_2[seq.id])
             self.predicted_switch_regions[seq.id] = (np.unique(self.updated_genome_labels[k]),
                                                      [(segs[i][1], segs[i + 1][0]) for i in range(len(segs) - 1)])
@@ -117,37 +139,56 @@ class Pipeline:
         return self.label_to_gcode[best]
 
     # ---- bin/pipeline.py:157-385 -------------------------------------------------------------------------
-    def identify_most_common_codes(self):
+    def identify_most_common_codes(self, smooth=False):
+        """→ (labels per contig, window scores per contig), contigs in the reference's order (sorted by id).  ``smooth=True``
+        also returns the smoothed labels (the reference's next step, find_best_sequence_of_labels per contig with the noise
+        labels of the whole input, bin/pipeline.py:98-110), computed in the same device call."""
         logging.info(f"Identifying most common genetic codes in {self.species}")
         if self.verbose:
             print(f"Identifying most common genetic codes in {self.species}")
-        if self.data.result is None:
-            raise RuntimeError("window labels need the genes of this run on the device: remove the cached "
-                               "mgm_*.gff files (or run without -p reuse) so that run_mgm decodes the input")
-        order = {r.id: i for i, r in enumerate(self.data._decoded_order)}   # engine contig index (file order)
-        lens_file = [len(r) for r in self.data._decoded_order]
-        stride_file = [L.resolve_stride(self.stride, n) for n in lens_file]
-        offs, labs, cents = self.data.engine.window_labels(lens_file, stride_file, self.window_size, self.consecutive_windows,
-                                                           self.short_contigs)
-        out_l, out_s = [], []
-        not_classified, short = [], []
-        for seq in self.sequence:                          # reference order: sorted by contig id
-            c = order[seq.id]
-            a, b = int(offs[c]), int(offs[c + 1])
-            out_l.append(labs[a:b].astype(np.int64))
-            out_s.append(cents[a:b].astype(np.float64) / 100.0)
+        engine, _ = self.data.ensure_resident()            # decodes (again) when run_mgm was served from cached GFF files
+        recs = self.data._file_order
+        lens_file = np.fromiter((len(r) for r in recs), dtype=np.int64, count=len(recs))
+        if self.stride is not None:
+            stride_file = np.full(len(recs), int(self.stride), dtype=np.int32)
+        else:
+            stride_file = np.where(lens_file <= 100000, 2500, 5000).astype(np.int32)      # bin/pipeline.py:172-183
+        if smooth:
+            offs, labs, cents, merged, status = engine.isoform_labels(lens_file, stride_file, self.window_size,
+                                                                      self.consecutive_windows, self.short_contigs)
+            if (status != 0).any():
+                raise IndexError(f"label smoothing walks off the array for contig {recs[int(np.flatnonzero(status)[0])].id} "
+                                 f"(as the reference does)")
+        else:
+            offs, labs, cents = engine.window_labels(lens_file, stride_file, self.window_size, self.consecutive_windows,
+                                                     self.short_contigs)
+            merged = None
+        labs = labs.astype(np.int64)
+        scores = cents.astype(np.float64) / 100.0
+        order = self.data._sorted_to_file                    # reference order: sorted by contig id
+        lo, hi = offs[:-1][order].tolist(), offs[1:][order].tolist()
+        out_l = [labs[a:b] for a, b in zip(lo, hi)]
+        out_s = [scores[a:b] for a, b in zip(lo, hi)]
+        lens_sorted = lens_file[order]
+        short = np.flatnonzero(lens_sorted <= 5000)
+        not_classified, below = [], []
+        for k in short.tolist():
+            seq = self.sequence[k]
             if len(seq) < 5000:
                 logging.warning(f"Contig {seq.id} in {self.species} is shorter than 5000bp. Classification results may be "
                                 f"not as reliable")
-            if len(seq) <= 5000 and not self.short_contigs:
+            if not self.short_contigs:
                 not_classified.append(seq.id)
             elif len(seq) < 5000:
-                short.append(seq.id)
-        if short and self.short_contigs:
-            warnings.warn(f"Contig {short[-1]} in {self.species} is shorter than 5000bp. Classification results may be not as reliable")
+                below.append(seq.id)
+        if below and self.short_contigs:
+            warnings.warn(f"Contig {below[-1]} in {self.species} is shorter than 5000bp. Classification results may be not as reliable")
         if not_classified:
             warnings.warn(f"Contig(s) {', '.join(not_classified)} in {self.species} are shorter than 5000bp. Genetic code has been "
                           f"set to 11. Use --short_contigs to predict genetic code of these contigs")
+        if smooth:
+            merged = merged.astype(np.int64)
+            return out_l, out_s, [merged[a:b] for a, b in zip(lo, hi)]
         return out_l, out_s
 
     # ---- bin/pipeline.py:387-492 -------------------------------------------------------------------------
@@ -156,23 +197,30 @@ class Pipeline:
         if self.verbose:
             print(f"Segmenting genome of {self.species}")
         conf_1, conf_2, seg_labels = {}, {}, {}
-        index = {lab: rows_by_contig(df) for lab, df in self.label_to_gene_coords.items()}
-        cols = {lab: (df.start.values, df.end.values, np.where(df.strand.values == "+", 1, -1))
-                for lab, df in self.label_to_gene_coords.items()}
-        none = np.zeros(0, dtype=np.int64)
+        frames = self.label_to_gene_coords
+        lmin = getattr(self, "_label_min", None)
+        messages = []
         for k, seq in enumerate(self.sequence):
+            labels_k = self.updated_genome_labels[k]
+            single = (lmin[k] == self._label_max[k]) if lmin is not None else np.unique(labels_k).shape[0] == 1
+            if single and labels_k.shape[0]:
+                # one genetic code on the whole contig: one block, no gene coordinates needed
+                code = self.label_to_gcode[int(labels_k[0])]
+                conf_1[seq.id], conf_2[seq.id], seg_labels[seq.id] = [(1, int(len(seq)))], [], [code]
+                messages.append(f"Contig {seq.id} in {self.species} has genetic code {code} from 1 to {len(seq)}")
+                continue
             genes = {}
-            if np.unique(self.updated_genome_labels[k]).shape[0] > 1:      # genes matter only where the label changes
-                for lab in self.label_to_gene_coords:
-                    pos = index[lab].get(seq.id, none)
-                    genes[lab] = tuple(c[pos] for c in cols[lab])
-            c1, c2, codes = L.segment_contig(self.updated_genome_labels[k], len(seq), L.resolve_stride(self.stride, len(seq)),
+            for lab in np.unique(labels_k).tolist():           # genes matter only where the label changes
+                genes[int(lab)] = _gene_columns(frames, int(lab), seq.id)
+            c1, c2, codes = L.segment_contig(labels_k, len(seq), L.resolve_stride(self.stride, len(seq)),
                                              self.window_size, genes, self.label_to_gcode)
             conf_1[seq.id], conf_2[seq.id], seg_labels[seq.id] = c1, c2, codes
             for (a, b), code in zip(sorted(c1 + c2), codes):
-                logging.info(f"Contig {seq.id} in {self.species} has genetic code {code} from {a} to {b}")
-                if self.verbose:
-                    print(f"Contig {seq.id} in {self.species} has genetic code {code} from {a} to {b}")
+                messages.append(f"Contig {seq.id} in {self.species} has genetic code {code} from {a} to {b}")
+        if messages:
+            logging.info("\n".join(messages))        # one record: a metagenome has tens of thousands of these lines
+            if self.verbose:
+                print("\n".join(messages))
         return conf_1, conf_2, seg_labels
 
     # ---- bin/pipeline.py:559-951 -------------------------------------------------------------------------
@@ -180,3 +228,14 @@ class Pipeline:
         return iso_compare.compare_sets_of_predicted_genes(self)
 
     find_best_sequence_of_labels = staticmethod(L.find_best_sequence_of_labels)
+
+
+def _gene_columns(frames, lab, contig_id):
+    """(left, right, strand as +1/-1) of one model's genes on one contig, in file order"""
+    if isinstance(frames, GeneFrames):
+        a, b = frames.contig_range(lab, contig_id)
+        g = frames.genes[lab][a:b]
+        return g["left"].astype(np.int64), g["right"].astype(np.int64), np.where(g["strand"] > 0, 1, -1)
+    df = frames[lab]
+    df = df[df.contig == contig_id]
+    return df.start.values, df.end.values, np.where(df.strand.values == "+", 1, -1)

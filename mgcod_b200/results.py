@@ -25,7 +25,7 @@ import warnings
 
 import numpy as np
 
-from .data import contig_rows, rows_by_contig
+from .data import contig_rows, frame_columns, rows_by_contig
 from .engine import GENE_DTYPE, MGCOD_CODES
 
 VERSION_BANNER = "GeneMark.hmm-2 version 1.17"   # line 2 of the binary's usage text (bin/results.py:185)
@@ -94,37 +94,38 @@ class Results:
         coords = P.coords_w_isoforms
         engine, file_ids = P.data.ensure_resident()
         index_of = {rid: i for i, rid in enumerate(file_ids)}
-        per_contig = []          # rows of each contig in the order the reference visits them
+        # rows in the order the reference visits them: contig by contig in sorted-id order, frame order inside a contig,
+        # parents of isoform pairs (logodd '.') left out (bin/results.py:362-372)
         index = rows_by_contig(coords)
-        for n in range(P.nr_contigs):
-            cur = contig_rows(coords, index, P.sequence[n].id)
-            cur = cur[cur.logodd != "."].reset_index(drop=True)
-            per_contig.append(cur)
-        genes = np.zeros(sum(len(c) for c in per_contig), dtype=GENE_DTYPE)
-        k = 0
-        for n, cur in enumerate(per_contig):
-            m = len(cur)
-            genes["contig"][k:k + m] = index_of[P.sequence[n].id]
-            genes["left"][k:k + m] = cur.start.values
-            genes["right"][k:k + m] = cur.end.values
-            genes["strand"][k:k + m] = np.where(cur.strand.values == "-", -1, 1)
-            k += m
+        present = [(n, index[seq.id]) for n, seq in enumerate(P.sequence) if seq.id in index] if len(index) else []
+        rows = np.concatenate([pos for _, pos in present]) if present else np.zeros(0, dtype=np.int64)
+        contig_file = (np.concatenate([np.full(len(pos), index_of[P.sequence[n].id], dtype=np.int32) for n, pos in present])
+                       if present else np.zeros(0, dtype=np.int32))
+        logodd = coords.logodd.values
+        if logodd.dtype == object and len(rows):
+            keep = np.fromiter((not (isinstance(v, str) and v == ".") for v in logodd[rows]), dtype=bool, count=len(rows))
+            rows, contig_file = rows[keep], contig_file[keep]
+        genes = np.zeros(len(rows), dtype=GENE_DTYPE)
+        genes["contig"] = contig_file
+        genes["left"] = coords.start.values[rows].astype(np.int64)
+        genes["right"] = coords.end.values[rows].astype(np.int64)
+        genes["strand"] = np.where(coords.strand.values[rows] == "-", -1, 1)
         counts, offs, pos = engine.recoded_stops(genes)      # GPU: in-frame stops of every gene
-        stop_recodings = []
-        for g in range(len(genes)):
-            # dict order of the reference: TAG, TGA, TAA (bin/results.py:285-288)
-            d = {}
-            for name in ("TAG", "TGA", "TAA"):
-                t = STOPS.index(name)
-                d[name] = pos[offs[3 * g + t]:offs[3 * g + t + 1]].tolist()
-            stop_recodings.append(d)
+        # dict order of the reference: TAG, TGA, TAA (bin/results.py:285-288); stop order of the engine: TAA, TAG, TGA
+        pos_l, offs_l = pos.tolist(), offs.tolist()
+        stop_recodings = [{"TAG": pos_l[offs_l[3 * g + 1]:offs_l[3 * g + 2]], "TGA": pos_l[offs_l[3 * g + 2]:offs_l[3 * g + 3]],
+                           "TAA": pos_l[offs_l[3 * g]:offs_l[3 * g + 1]]} for g in range(len(genes))]
         if self.nucleotides or self.amino_acids:
+            per_contig = []          # (position in P.sequence, rows of that contig without parents)
+            for n, pos_n in present:
+                cur = coords.iloc[pos_n]
+                per_contig.append((n, cur[cur.logodd != "."].reset_index(drop=True)))
             nt = self._nucleotide_records(per_contig, stop_recodings)
             if self.nucleotides:
                 _write_fasta(nt, self.path_to_nt_seqs)
             if self.amino_acids:
                 # as in the reference, the loop bound is the gene count of the LAST contig (bin/results.py:378)
-                last = per_contig[-1] if per_contig else []
+                last = per_contig[-1][1] if per_contig and per_contig[-1][0] == P.nr_contigs - 1 else []
                 aa = [self.translate_seq(last.iloc[i], nt[i], stop_recodings[i]) for i in range(len(last))]
                 _write_fasta(aa, self.path_to_aa_seqs)
         return stop_recodings
@@ -133,7 +134,7 @@ class Results:
         """[(id, description, sequence)]: lower case, recoded in-frame stop codons upper case (bin/results.py:269-294)"""
         out = []
         g = 0
-        for n, cur in enumerate(per_contig):
+        for n, cur in per_contig:
             rec = self.results.sequence[n]
             for i in range(len(cur)):
                 p = cur.iloc[i]
@@ -212,12 +213,12 @@ class Results:
                                 "Nr isoforms", "Total gene count"):
                         table.add_row((c, key))
             segments = sorted(P.confident_1[contig] + P.confident_2[contig])
-            coords = contig_rows(coords_all, index, contig)
             if len(g) == 1:
                 table.set((contig, "Coordinates in bp"), "Sequence", str(segments[0]))
                 table.set((contig, "Major genetic code"), "Sequence", g[1])
-                table.set((contig, "Total gene count"), "Sequence", coords.shape[0])
+                table.set((contig, "Total gene count"), "Sequence", len(index.get(contig, ())))
                 continue
+            coords = contig_rows(coords_all, index, contig)
             start = coords.start.values.astype(np.int64)
             is_parent = np.array([isinstance(v, str) and v == "." for v in coords.logodd.values], dtype=bool)
             source = coords.source.values
@@ -270,7 +271,7 @@ class Results:
         coords = P.coords_w_isoforms
         if coords.shape[0] == 0:
             warnings.warn("No genes were predicted, automatically assign genetic code 11")
-        columns = [c for c in P.label_to_gene_coords[0].columns.values if c in coords.columns]
+        columns = [c for c in frame_columns(P.label_to_gene_coords) if c in coords.columns]
         with open(self.path_to_final_annotations, "w+") as out:
             out.write("##gff-version 2\n")
             out.write("#" + VERSION_BANNER + "\n")
