@@ -91,6 +91,10 @@ int mgc_decode_resident(mgc_engine *e, mgc_result **out);
 int mgc_prefetch_batch(mgc_engine *e, const char *seq, const int64_t *offsets, int32_t n_contigs);
 
 int mgc_engine_stats(const mgc_engine *e, mgc_stats *out);
+/* The gene table of the last decode as it sits in DEVICE memory (mgc_gene rows ordered by (contig, left); contig index local
+ * to the batch): for a multi-GPU gather over NCCL straight from the engine's memory — the final gather of
+ * bin/multiprocess_mgcod.py:140-145's fan-out.  Valid until the next decode / upload on this engine. */
+int mgc_engine_device_genes(mgc_engine *e, int model, const void **dev_genes, int64_t *count);
 
 /* ---- results ----
  * A result is returned as soon as the decode has finished on the device; its gene tables and totals travel to page-locked host
@@ -187,17 +191,11 @@ int mgc_fasta_read(const char *path, int page_locked, mgc_fasta **out);
 int32_t mgc_fasta_num_records(const mgc_fasta *f);
 const char *mgc_fasta_id(const mgc_fasta *f, int32_t i);
 const char *mgc_fasta_defline(const mgc_fasta *f, int32_t i);
+/* all ids (deflines != 0: all deflines) in one buffer, each followed by '\n'; *len = its size.  Valid until mgc_fasta_free. */
+const char *mgc_fasta_ids_joined(const mgc_fasta *f, int deflines, int64_t *len);
 const char *mgc_fasta_sequence(const mgc_fasta *f);      /* concatenated letters, no separators */
 const int64_t *mgc_fasta_offsets(const mgc_fasta *f);    /* n + 1 entries */
 void mgc_fasta_free(mgc_fasta *f);
-
-/* ---- synthetic workload (BASELINE.json config 5) — host only ---- */
-/* Draws contig lengths ~ L^-2 on [min_len,max_len] until total >= total_bp; returns count. */
-int64_t mgc_synth_lengths(uint64_t seed, int64_t total_bp, int32_t min_len, int32_t max_len, int64_t *lens,
-                          int64_t cap);
-/* Fills seq (sum of lens bytes, ACGT) with gene-like content; truth_code[c] receives 11/4/15/101. */
-int mgc_synth_contigs(uint64_t seed, const int64_t *lens, int64_t n, char *seq, int32_t *truth_code,
-                      int threads);
 
 #ifdef __cplusplus
 }

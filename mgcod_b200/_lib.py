@@ -40,8 +40,8 @@ EXPORTS = (
     "mgc_engine_create", "mgc_engine_destroy", "mgc_decode_batch", "mgc_upload_batch", "mgc_prefetch_batch", "mgc_decode_resident",
     "mgc_engine_stats", "mgc_result_num_genes", "mgc_result_genes", "mgc_result_contig_totals",
     "mgc_result_model_cents", "mgc_result_min_gene_length", "mgc_result_set_min_gene_length", "mgc_result_free", "mgc_result_create", "mgc_recoded_stops", "mgc_window_counts", "mgc_window_labels", "mgc_isoform_labels", "mgc_merge_labels", "mgc_debug_candidates",
-    "mgc_write_gff", "mgc_synth_lengths", "mgc_synth_contigs",
-    "mgc_fasta_read", "mgc_fasta_num_records", "mgc_fasta_id", "mgc_fasta_defline", "mgc_fasta_sequence", "mgc_fasta_offsets", "mgc_fasta_free",
+    "mgc_write_gff", "mgc_engine_device_genes",
+    "mgc_fasta_read", "mgc_fasta_num_records", "mgc_fasta_id", "mgc_fasta_defline", "mgc_fasta_ids_joined", "mgc_fasta_sequence", "mgc_fasta_offsets", "mgc_fasta_free",
 )
 
 _LIB = None
@@ -100,9 +100,7 @@ def lib():
     L.mgc_debug_candidates.argtypes = [vp, C.c_int, C.POINTER(Candidate), i64]
     L.mgc_debug_candidates.restype = i64
     L.mgc_write_gff.argtypes = [vp, C.c_int, C.POINTER(cp), C.POINTER(i64), i32, cp, cp, C.c_int, cp, cp]
-    L.mgc_synth_lengths.argtypes = [C.c_uint64, i64, i32, i32, C.POINTER(i64), i64]
-    L.mgc_synth_lengths.restype = i64
-    L.mgc_synth_contigs.argtypes = [C.c_uint64, C.POINTER(i64), i64, vp, C.POINTER(i32), C.c_int]
+    L.mgc_engine_device_genes.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(i64)]
     L.mgc_fasta_read.argtypes = [cp, C.c_int, C.POINTER(vp)]
     L.mgc_fasta_num_records.argtypes = [vp]
     L.mgc_fasta_num_records.restype = i32
@@ -110,6 +108,8 @@ def lib():
     L.mgc_fasta_id.restype = cp
     L.mgc_fasta_defline.argtypes = [vp, i32]
     L.mgc_fasta_defline.restype = cp
+    L.mgc_fasta_ids_joined.argtypes = [vp, C.c_int, C.POINTER(i64)]
+    L.mgc_fasta_ids_joined.restype = vp
     L.mgc_fasta_sequence.argtypes = [vp]
     L.mgc_fasta_sequence.restype = vp
     L.mgc_fasta_offsets.argtypes = [vp]

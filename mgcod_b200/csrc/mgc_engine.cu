@@ -219,6 +219,7 @@ struct mgc_engine {
     int cap_scale = 1;     // multiplier of the scratch capacities, raised on overflow
     std::vector<unsigned char> table_sig;   // contents of the device pointer tables as last uploaded
     bool have_batch = false, have_genes = false;
+    std::vector<int64_t> dev_gene_count;   // genes of the last decode per model, as they sit in pm[i].genes on the device
     mgc_stats stats;
     std::shared_ptr<PinnedPool> pool = std::make_shared<PinnedPool>();
 };
@@ -869,6 +870,7 @@ mgc_result *run_pipeline(mgc_engine *e, bool *amb_out) {
     e->stats.d2h = 0;
     e->stats.kernel_launches = launches;
     e->have_genes = true;
+    e->dev_gene_count.assign(h_gtot.begin(), h_gtot.end());
     return res.release();
 }
 
@@ -1204,6 +1206,17 @@ int64_t mgc_debug_candidates(mgc_engine *e, int model, mgc_candidate *out, int64
     return rc == MGC_OK ? n : rc;
 }
 
+int mgc_engine_device_genes(mgc_engine *e, int model, const void **dev_genes, int64_t *count) {
+    if (!e || !dev_genes || !count || model < 0 || model >= e->n_models) return mgc::set_error(MGC_E_ARG, "bad argument");
+    if (!e->have_genes || (size_t)model >= e->dev_gene_count.size()) return mgc::set_error(MGC_E_ARG, "decode a batch first");
+    return guarded([&] {
+        CUDA_TRY(cudaSetDevice(e->device));
+        CUDA_TRY(cudaStreamSynchronize(e->stream));   // the gene tables are complete (the caller reads them on another stream)
+        *dev_genes = e->pm[model].genes.p;
+        *count = e->dev_gene_count[model];
+    });
+}
+
 int mgc_engine_stats(const mgc_engine *ce, mgc_stats *out) {
     if (!ce || !out) return mgc::set_error(MGC_E_ARG, "null argument");
     mgc_engine *e = const_cast<mgc_engine *>(ce);
@@ -1269,6 +1282,13 @@ int mgc_result_create(int n_models, int32_t n_contigs, const mgc_gene *const *ge
         g.p = std::malloc(g.bytes);
         t.bytes = (size_t)std::max<int32_t>(n_contigs, 1) * 8;
         t.p = std::malloc(t.bytes);
+        if (!g.p || !t.p) {
+            std::free(g.p);
+            std::free(t.p);
+            r->host_owned = true;
+            mgc_result_free(r);
+            return mgc::set_error(MGC_E_NOMEM, "out of host memory for the gene tables");
+        }
         if (counts[m]) std::memcpy(g.p, genes[m], (size_t)counts[m] * sizeof(mgc_gene));
         if (n_contigs) std::memcpy(t.p, totals[m], (size_t)n_contigs * 8);
         r->gene_blk.push_back(g);

@@ -3,12 +3,14 @@
 // Writers reproduce gmhmmp2's Output::PrintGenes_GFF / PrintGenes_LST byte for byte except for the
 // date lines (format strings: SURVEY.md §8b, pinned by tests/golden).  The reference reads the GFF
 // back with pandas (bin/data.py:66-96) and caches it on disk (bin/data.py:39).
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -38,124 +40,6 @@ std::string now_string() {
     std::strftime(buf, sizeof buf, "%a %b %e %H:%M:%S %Y", std::localtime(&t));
     // ctime pads the day with a space ("Oct  9"); gmhmmp2 prints the same form
     return buf;
-}
-
-// ---- xoshiro256** ----
-struct Rng {
-    uint64_t s[4];
-    static uint64_t splitmix(uint64_t &x) {
-        uint64_t z = (x += 0x9e3779b97f4a7c15ULL);
-        z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
-        z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
-        return z ^ (z >> 31);
-    }
-    explicit Rng(uint64_t seed) {
-        for (auto &v : s) v = splitmix(seed);
-    }
-    static uint64_t rotl(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
-    uint64_t next() {
-        uint64_t r = rotl(s[1] * 5, 7) * 9, t = s[1] << 17;
-        s[2] ^= s[0]; s[3] ^= s[1]; s[1] ^= s[2]; s[0] ^= s[3]; s[2] ^= t; s[3] = rotl(s[3], 45);
-        return r;
-    }
-    double uni() { return (double)(next() >> 11) * (1.0 / 9007199254740992.0); }  // [0,1)
-};
-
-const char NT[4] = {'A', 'C', 'G', 'T'};
-
-// codon distribution at GC level gc for genetic code 11 (same construction as mgcod_b200/synth.py codon_usage)
-void codon_usage(double gc, double C[64]) {
-    const double at = (1.0 - gc) / 2.0, g_c = gc / 2.0;
-    const double base[4] = {at, g_c, g_c, at};
-    const double f1[4] = {1.15, 0.80, 1.45, 0.70}, f2[4] = {1.20, 0.95, 0.75, 1.10}, f3[4] = {0.95, 1.05, 0.95, 1.05};
-    double p1[4], p2[4], p3[4], s1 = 0, s2 = 0, s3 = 0;
-    for (int x = 0; x < 4; x++) {
-        p1[x] = base[x] * f1[x];
-        p2[x] = base[x] * f2[x];
-        double w = (x == 1 || x == 2) ? gc : 1.0 - gc;
-        p3[x] = std::pow(w, 1.0 + 2.0 * 0.35) * f3[x];
-        s1 += p1[x]; s2 += p2[x]; s3 += p3[x];
-    }
-    double tot = 0;
-    for (int i = 0; i < 64; i++) {
-        int a = i >> 4, b = (i >> 2) & 3, c = i & 3;
-        double v = (p1[a] / s1) * (p2[b] / s2) * (p3[c] / s3);
-        v *= 1.0 + 0.45 * std::sin(1.7 * i + 0.3) * std::cos(0.9 * i);
-        if (i == 48 || i == 50 || i == 56) v = 0.0;  // TAA TAG TGA never inside a gene before recoding
-        C[i] = v;
-        tot += v;
-    }
-    for (int i = 0; i < 64; i++) C[i] /= tot;
-}
-
-int draw(const double *cdf, int n, double u) {
-    int lo = 0, hi = n - 1;
-    while (lo < hi) {
-        int mid = (lo + hi) / 2;
-        if (cdf[mid] > u) hi = mid; else lo = mid + 1;
-    }
-    return lo;
-}
-
-void revcomp_inplace(char *s, int64_t n) {
-    for (int64_t i = 0, j = n - 1; i <= j; i++, j--) {
-        auto comp = [](char c) { return c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : 'A'; };
-        char a = comp(s[i]), b = comp(s[j]);
-        s[i] = b;
-        s[j] = a;
-    }
-}
-
-void synth_one(uint64_t seed, int64_t index, char *out, int64_t L, int32_t *truth) {
-    uint64_t sd = seed * 0x9e3779b97f4a7c15ULL + (uint64_t)index * 0xd1342543de82ef95ULL + 1;
-    Rng rng(sd);
-    static const int gcs[4] = {30, 40, 50, 60};
-    static const int codes[4] = {11, 4, 15, 101};
-    const double gc = gcs[rng.next() & 3] / 100.0;
-    const int code = codes[rng.next() & 3];
-    if (truth) *truth = code;
-    double C[64], cdf[64], acc = 0;
-    codon_usage(gc, C);
-    for (int i = 0; i < 64; i++) { acc += C[i]; cdf[i] = acc; }
-    cdf[63] = 1.0;
-    const double ntp[4] = {(1 - gc) / 2, gc / 2, gc / 2, (1 - gc) / 2};
-    const double ntcdf[4] = {ntp[0], ntp[0] + ntp[1], ntp[0] + ntp[1] + ntp[2], 1.0};
-    // stop codons valid under the true code and the (sense codon -> reassigned stop) substitution, p = 0.8
-    // (utils/simulate_gcodes.py:96-101, 112-149 in the reference)
-    int stops[3], nstop = 0, sense_from = -1, sense_to = -1;
-    switch (code) {
-        case 4: stops[0] = 48; stops[1] = 50; nstop = 2; sense_from = 58 /*TGG*/; sense_to = 56 /*TGA*/; break;
-        case 15: stops[0] = 48; stops[1] = 56; nstop = 2; sense_from = 18 /*CAG*/; sense_to = 50 /*TAG*/; break;
-        case 101: stops[0] = 50; stops[1] = 56; nstop = 2; sense_from = 16 /*CAA*/; sense_to = 48 /*TAA*/; break;
-        default: stops[0] = 48; stops[1] = 50; stops[2] = 56; nstop = 3;
-    }
-    int64_t pos = 0;
-    std::vector<char> gene;
-    while (pos < L) {
-        // intergenic stretch, geometric with mean 150
-        int64_t ig = (int64_t)(-150.0 * std::log(1.0 - rng.uni())) + 1;
-        for (int64_t k = 0; k < ig && pos < L; k++) out[pos++] = NT[draw(ntcdf, 4, rng.uni())];
-        if (pos >= L) break;
-        // gene: 3 * (30 + Gamma(2, 135)) codons' worth of nt, i.e. mean ~900 nt
-        double gam = -135.0 * (std::log(1.0 - rng.uni()) + std::log(1.0 - rng.uni()));
-        int64_t ncod = 30 + (int64_t)gam;
-        ncod = std::max<int64_t>(ncod, 32);
-        gene.clear();
-        double us = rng.uni();
-        const char *sc = us < 0.85 ? "ATG" : (us < 0.95 ? "GTG" : "TTG");
-        gene.insert(gene.end(), sc, sc + 3);
-        for (int64_t k = 0; k < ncod; k++) {
-            int cd = draw(cdf, 64, rng.uni());
-            if (cd == sense_from && rng.uni() < 0.8) cd = sense_to;
-            gene.push_back(NT[cd >> 4]); gene.push_back(NT[(cd >> 2) & 3]); gene.push_back(NT[cd & 3]);
-        }
-        int st;
-        if (nstop == 3) { double u = rng.uni(); st = u < 0.5 ? 48 : (u < 0.7 ? 50 : 56); }
-        else st = rng.uni() < 0.35 ? stops[0] : stops[1];
-        gene.push_back(NT[st >> 4]); gene.push_back(NT[(st >> 2) & 3]); gene.push_back(NT[st & 3]);
-        if (rng.next() & 1) revcomp_inplace(gene.data(), (int64_t)gene.size());
-        for (size_t k = 0; k < gene.size() && pos < L; k++) out[pos++] = gene[k];
-    }
 }
 
 }  // namespace
@@ -286,39 +170,6 @@ int mgc_write_gff(const mgc_result *r, int model, const char *const *contig_ids,
     return MGC_OK;
 }
 
-int64_t mgc_synth_lengths(uint64_t seed, int64_t total_bp, int32_t min_len, int32_t max_len, int64_t *lens, int64_t cap) {
-    if (!lens || min_len <= 0 || max_len < min_len) return mgc::set_error(MGC_E_ARG, "bad argument");
-    Rng rng(seed);
-    int64_t n = 0, acc = 0;
-    const double a = (double)min_len, b = (double)max_len;
-    while (acc < total_bp) {
-        if (n >= cap) return mgc::set_error(MGC_E_NOMEM, "length buffer too small");
-        // inverse CDF of p(L) ~ L^-2 on [a, b]
-        double u = rng.uni();
-        double L = 1.0 / (1.0 / a - u * (1.0 / a - 1.0 / b));
-        int64_t l = (int64_t)L;
-        if (l < min_len) l = min_len;
-        if (l > max_len) l = max_len;
-        lens[n++] = l;
-        acc += l;
-    }
-    return n;
-}
-
-int mgc_synth_contigs(uint64_t seed, const int64_t *lens, int64_t n, char *seq, int32_t *truth_code, int threads) {
-    if (!lens || !seq || n < 0) return mgc::set_error(MGC_E_ARG, "bad argument");
-    std::vector<int64_t> off(n + 1, 0);
-    for (int64_t i = 0; i < n; i++) off[i + 1] = off[i] + lens[i];
-    if (threads < 1) threads = 1;
-    std::vector<std::thread> pool;
-    for (int t = 0; t < threads; t++)
-        pool.emplace_back([&, t] {
-            for (int64_t i = t; i < n; i += threads) synth_one(seed, i, seq + off[i], lens[i], truth_code ? truth_code + i : nullptr);
-        });
-    for (auto &th : pool) th.join();
-    return MGC_OK;
-}
-
 }  // extern "C"
 
 // ------------------------------------------------------------------------------------------------
@@ -332,18 +183,123 @@ int mgc_synth_contigs(uint64_t seed, const int64_t *lens, int64_t n, char *seq, 
 #include <sys/stat.h>
 #include <unistd.h>
 
+// Page-locked letter buffers are kept for the next file of the process (python -m mgcod_b200.multi reads thousands):
+// cudaHostAlloc costs ~0.3 ms per MB, more than reading the file.  At most kBufCacheMax bytes stay cached.
+namespace {
+struct LetterBuffers {
+    struct Block { char *p; size_t bytes; };
+    std::mutex mu;
+    std::vector<Block> free_blocks;
+    size_t cached = 0;
+    static constexpr size_t kBufCacheMax = (size_t)6 << 30;
+    char *acquire(size_t need, size_t *got) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            size_t best = free_blocks.size();
+            for (size_t i = 0; i < free_blocks.size(); i++)
+                if (free_blocks[i].bytes >= need && (best == free_blocks.size() || free_blocks[i].bytes < free_blocks[best].bytes)) best = i;
+            if (best != free_blocks.size()) {
+                Block b = free_blocks[best];
+                free_blocks.erase(free_blocks.begin() + best);
+                cached -= b.bytes;
+                *got = b.bytes;
+                return b.p;
+            }
+        }
+        char *p = nullptr;
+        const size_t bytes = need + need / 8 + 4096;
+        if (cudaHostAlloc(reinterpret_cast<void **>(&p), bytes, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        *got = bytes;
+        return p;
+    }
+    void release(char *p, size_t bytes) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            if (cached + bytes <= kBufCacheMax) {
+                free_blocks.push_back(Block{p, bytes});
+                cached += bytes;
+                return;
+            }
+        }
+        cudaFreeHost(p);
+    }
+};
+LetterBuffers &letter_buffers() {
+    static LetterBuffers *b = new LetterBuffers();   // never destroyed: the CUDA runtime may be gone at exit
+    return *b;
+}
+}  // namespace
+
 struct mgc_fasta {
     std::vector<std::string> ids, deflines;
+    std::string ids_joined, deflines_joined;   // '\n'-separated, for one-call retrieval
     std::vector<int64_t> offsets;
     char *seq = nullptr;
+    size_t seq_bytes = 0;
     bool pinned = false;
     ~mgc_fasta() {
         if (seq) {
-            if (pinned) cudaFreeHost(seq);
+            if (pinned) letter_buffers().release(seq, seq_bytes);
             else std::free(seq);
         }
     }
 };
+
+// Multi-threaded reader.  Three passes, the last two spread over the host cores by bytes:
+//   1. record starts: '>' at the beginning of a line (memchr over disjoint byte ranges);
+//   2. letters per record (bytes above 0x20 in the body) -> offsets by a prefix sum;
+//   3. the bodies copied line by line into their final place, whitespace removed.
+// Text semantics follow Biopython's FASTA parser (bin/data.py:117 uses SeqIO.parse): the id is the first
+// whitespace-delimited token of the defline — "> id x" has the id "id" —, line ends and blanks anywhere in the sequence
+// are dropped, text in front of the first '>' is ignored.
+namespace {
+
+constexpr size_t kPinnedMax = (size_t)8 << 30;   // larger letter buffers stay in ordinary pages (the copy is then staged)
+
+inline bool is_blank(unsigned char c) { return c <= 0x20; }
+
+int64_t count_letters(const char *a, const char *b) {
+    int64_t n = 0;
+    for (const char *p = a; p < b; p++) n += (unsigned char)*p > 0x20;
+    return n;
+}
+
+// copies [a, b) without blanks, line by line (memchr + memcpy; a line holding an interior blank is compacted bytewise)
+char *copy_letters(const char *a, const char *b, char *dst) {
+    while (a < b) {
+        const char *nl = static_cast<const char *>(std::memchr(a, '\n', (size_t)(b - a)));
+        const char *le = nl ? nl : b;
+        const char *x = a, *y = le;
+        while (y > x && is_blank((unsigned char)y[-1])) y--;
+        while (x < y && is_blank((unsigned char)*x)) x++;
+        const size_t len = (size_t)(y - x);
+        if (len) {
+            if ((size_t)count_letters(x, y) != len) {   // a blank inside the line
+                for (const char *p = x; p < y; p++) {
+                    *dst = *p;
+                    dst += (unsigned char)*p > 0x20;
+                }
+            } else {
+                std::memcpy(dst, x, len);
+                dst += len;
+            }
+        }
+        a = nl ? nl + 1 : b;
+    }
+    return dst;
+}
+
+template <class F> void parallel_ranges(int threads, F fn) {
+    if (threads <= 1) { fn(0); return; }
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; t++) pool.emplace_back(fn, t);
+    for (auto &th : pool) th.join();
+}
+
+}  // namespace
 
 int mgc_fasta_read(const char *path, int page_locked, mgc_fasta **out) {
     if (!path || !out) return mgc::set_error(MGC_E_ARG, "null argument");
@@ -354,48 +310,103 @@ int mgc_fasta_read(const char *path, int page_locked, mgc_fasta **out) {
     const size_t size = (size_t)sb.st_size;
     const char *map = nullptr;
     if (size) {
-        map = static_cast<const char *>(::mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0));
+        map = static_cast<const char *>(::mmap(nullptr, size, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0));
         if (map == MAP_FAILED) { ::close(fd); return mgc::set_error(MGC_E_IO, std::string("cannot map ") + path); }
-        ::madvise(const_cast<char *>(map), size, MADV_SEQUENTIAL);
     }
-    std::unique_ptr<mgc_fasta> f(new mgc_fasta());
-    if (page_locked && cudaHostAlloc(reinterpret_cast<void **>(&f->seq), size + 64, cudaHostAllocDefault) == cudaSuccess) f->pinned = true;
-    else {
-        cudaGetLastError();  // no device / no memory: ordinary pages still work, copies are then staged by the driver
-        f->seq = static_cast<char *>(std::malloc(size + 64));
-    }
-    if (!f->seq) {
+    auto unmap = [&] {
         if (map) ::munmap(const_cast<char *>(map), size);
         ::close(fd);
+    };
+    (void)unmap;
+    const bool trace = std::getenv("MGCOD_B200_TRACE") != nullptr;
+    auto now = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
+    const double t0 = now();
+    std::unique_ptr<mgc_fasta> f(new mgc_fasta());
+    int threads = (int)std::min<size_t>(std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u), size / (4u << 20) + 1);
+    if (const char *env = std::getenv("MGCOD_B200_FASTA_THREADS")) threads = std::max(1, std::atoi(env));
+    // pass 1: record starts
+    std::vector<std::vector<size_t>> found(threads);
+    parallel_ranges(threads, [&](int t) {
+        const size_t lo = size * (size_t)t / threads, hi = size * (size_t)(t + 1) / threads;
+        const char *p = map + lo, *end = map + hi;
+        while (p < end) {
+            p = static_cast<const char *>(std::memchr(p, '>', (size_t)(end - p)));
+            if (!p) break;
+            if (p == map || p[-1] == '\n') found[t].push_back((size_t)(p - map));
+            p++;
+        }
+    });
+    const double t1 = now();
+    std::vector<size_t> head;
+    for (auto &v : found) head.insert(head.end(), v.begin(), v.end());
+    const size_t n_rec = head.size();
+    std::vector<size_t> body(n_rec);           // first byte behind the defline
+    f->ids.resize(n_rec);
+    f->deflines.resize(n_rec);
+    for (size_t i = 0; i < n_rec; i++) {
+        const char *a = map + head[i] + 1, *lim = map + (i + 1 < n_rec ? head[i + 1] : size);
+        const char *nl = static_cast<const char *>(std::memchr(a, '\n', (size_t)(lim - a)));
+        const char *b = nl ? nl : lim;
+        body[i] = (size_t)((nl ? nl + 1 : lim) - map);
+        while (b > a && is_blank((unsigned char)b[-1])) b--;
+        f->deflines[i].assign(a, b);
+        const char *x = a;
+        while (x < b && (*x == ' ' || *x == '\t')) x++;
+        const char *y = x;
+        while (y < b && *y != ' ' && *y != '\t') y++;
+        f->ids[i].assign(x, y);
+    }
+    // work split of passes 2 and 3: record ranges of about equal bytes
+    std::vector<size_t> cut(threads + 1, n_rec);
+    cut[0] = 0;
+    for (int t = 1; t < threads; t++) {
+        const size_t want = size * (size_t)t / threads;
+        cut[t] = (size_t)(std::lower_bound(head.begin(), head.end(), want) - head.begin());
+    }
+    // pass 2: letters per record
+    const double t2 = now();
+    f->offsets.assign(n_rec + 1, 0);
+    parallel_ranges(threads, [&](int t) {
+        for (size_t i = cut[t]; i < cut[t + 1]; i++)
+            f->offsets[i + 1] = count_letters(map + body[i], map + (i + 1 < n_rec ? head[i + 1] : size));
+    });
+    for (size_t i = 0; i < n_rec; i++) f->offsets[i + 1] += f->offsets[i];
+    const size_t total = (size_t)f->offsets[n_rec];
+    const double t3 = now();
+    if (page_locked && total + 64 <= kPinnedMax) f->seq = letter_buffers().acquire(total + 64, &f->seq_bytes);
+    if (f->seq) f->pinned = true;
+    else f->seq = static_cast<char *>(std::malloc(total + 64));   // no device / no memory / too large: ordinary pages still work,
+                                                                   // copies are then staged by the driver
+    if (!f->seq) {
+        unmap();
         return mgc::set_error(MGC_E_NOMEM, "out of host memory");
     }
-    int64_t n = 0;
-    const char *p = map, *end = map + size;
-    bool in_record = false;
-    while (p < end) {
-        const char *nl = static_cast<const char *>(std::memchr(p, '\n', (size_t)(end - p)));
-        const char *le = nl ? nl : end;
-        const char *a = p, *b = le;
-        while (b > a && (b[-1] == '\r' || b[-1] == ' ' || b[-1] == '\t')) b--;
-        if (a < b && *a == '>') {
-            f->offsets.push_back(n);   // start of this record; the end of the last one is appended after the loop
-            std::string def(a + 1, b);
-            size_t k = 0;
-            while (k < def.size() && def[k] != ' ' && def[k] != '\t') k++;
-            f->ids.emplace_back(def.substr(0, k));
-            f->deflines.emplace_back(std::move(def));
-            in_record = true;
-        } else if (in_record) {
-            while (a < b && (*a == ' ' || *a == '\t')) a++;
-            std::memcpy(f->seq + n, a, (size_t)(b - a));
-            n += b - a;
+    // pass 3: bodies into place
+    const double t4 = now();
+    bool ok = true;
+    parallel_ranges(threads, [&](int t) {
+        for (size_t i = cut[t]; i < cut[t + 1]; i++) {
+            char *dst = f->seq + f->offsets[i];
+            char *e = copy_letters(map + body[i], map + (i + 1 < n_rec ? head[i + 1] : size), dst);
+            if (e != f->seq + f->offsets[i + 1]) ok = false;
         }
-        p = nl ? nl + 1 : end;
+    });
+    const double t5 = now();
+    for (size_t i = 0; i < n_rec; i++) {
+        f->ids_joined += f->ids[i];
+        f->ids_joined += '\n';
+        f->deflines_joined += f->deflines[i];
+        f->deflines_joined += '\n';
     }
-    f->offsets.push_back(n);
-    if (f->ids.empty()) f->offsets.assign(1, 0);
-    if (map) ::munmap(const_cast<char *>(map), size);
-    ::close(fd);
+    std::thread([map, size, fd] {     // returning the mapping takes milliseconds for a large file: not on the caller's time
+        if (map) ::munmap(const_cast<char *>(map), size);
+        ::close(fd);
+    }).detach();
+    map = nullptr;
+    if (trace)
+        std::fprintf(stderr, "fasta_read: %d threads, map+starts %.2f ms, deflines %.2f, count %.2f, alloc %.2f, copy %.2f, unmap %.2f\n", threads,
+                     t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4, now() - t5);
+    if (!ok) return mgc::set_error(MGC_E_IO, "FASTA reader: letter counts of the two passes differ (file changed while reading?)");
     *out = f.release();
     return MGC_OK;
 }
@@ -404,6 +415,12 @@ int32_t mgc_fasta_num_records(const mgc_fasta *f) { return f ? (int32_t)f->ids.s
 const char *mgc_fasta_id(const mgc_fasta *f, int32_t i) { return f && i >= 0 && i < (int32_t)f->ids.size() ? f->ids[i].c_str() : nullptr; }
 const char *mgc_fasta_defline(const mgc_fasta *f, int32_t i) {
     return f && i >= 0 && i < (int32_t)f->deflines.size() ? f->deflines[i].c_str() : nullptr;
+}
+const char *mgc_fasta_ids_joined(const mgc_fasta *f, int deflines, int64_t *len) {
+    if (!f) return nullptr;
+    const std::string &s = deflines ? f->deflines_joined : f->ids_joined;
+    if (len) *len = (int64_t)s.size();
+    return s.data();
 }
 const char *mgc_fasta_sequence(const mgc_fasta *f) { return f ? f->seq : nullptr; }
 const int64_t *mgc_fasta_offsets(const mgc_fasta *f) { return f ? f->offsets.data() : nullptr; }

@@ -1543,18 +1543,18 @@ __global__ void __launch_bounds__(256, 4) k_final(Planes pl, const int64_t *__re
             // starts of spurious ORFs; those never touch the planes or the ramp tables.  (Exact otherwise: only candidates
             // that the full computation would prune as well are dropped, with a 1e-6 guard band.)
             const double dl = (double)len;
-            const double lgt = 2.0 * log(dl) - 1.3862943611198906;
+            const double lgt = 2.0 * log(dl);
             bool maybe = false;
             {
                 const double *ub = dm.pair_ub + pair * 8;
                 const double ub1B = odd_one ? ub[6] : 0.0, ub1A = odd_one ? ub[7] : 0.0;
                 if (secB >= 0) {
                     const SectionScalars *sb = dm.sc + secB;
-                    maybe |= acc.oB + ub1B + ub[0] + lgt + dl * sb->dur_slope + sb->dur_const + (virt ? 0.0 : ub[1]) + (pstop ? 0.0 : ub[2]) > -1e-6;
+                    maybe |= acc.oB + ub1B + ub[0] + lgt + sb->tr + dl * sb->dur_slope + sb->dur_const + (virt ? 0.0 : ub[1]) + (pstop ? 0.0 : ub[2]) > -1e-6;
                 }
                 if (secA >= 0) {
                     const SectionScalars *sa = dm.sc + secA;
-                    maybe |= acc.oA + ub1A + ub[3] + lgt + dl * sa->dur_slope + sa->dur_const + (virt ? 0.0 : ub[4]) + (pstop ? 0.0 : ub[5]) > -1e-6;
+                    maybe |= acc.oA + ub1A + ub[3] + lgt + sa->tr + dl * sa->dur_slope + sa->dur_const + (virt ? 0.0 : ub[4]) + (pstop ? 0.0 : ub[5]) > -1e-6;
                 }
             }
             if (maybe) {
@@ -1592,9 +1592,11 @@ __global__ void __launch_bounds__(256, 4) k_final(Planes pl, const int64_t *__re
                 acc.cB += x.x; acc.oB += x.y; acc.cA += y.x; acc.oA += y.y;
             }
             if (secB >= 0 || secA >= 0) {
-                const bool arc = secB < 0 || (secA >= 0 && acc.cA > acc.cB);
+                // the domain with the larger coding log-likelihood plus its transition term ln(to_mgm * to_atypical) — the terms
+                // are equal (ln 0.25) unless the parameter file sets $TO_ATYPICAL_*; ties -> bacteria
+                const bool arc = secB < 0 || (secA >= 0 && acc.cA + dm.sc[secA].tr > acc.cB + dm.sc[secB].tr);
                 const SectionScalars *sc = dm.sc + (arc ? secA : secB);
-                double total = (arc ? acc.oA : acc.oB) + 2.0 * log(dl) + dl * sc->dur_slope + sc->dur_const - 1.3862943611198906;
+                double total = (arc ? acc.oA : acc.oB) + 2.0 * log(dl) + dl * sc->dur_slope + sc->dur_const + sc->tr;
                 if (!virt) {
                     uint32_t hb, lb;
                     window_bits(lo, hi, s, 1, hb, lb);

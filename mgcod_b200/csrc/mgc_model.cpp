@@ -2,7 +2,9 @@
 // See mgc_model.hpp for what it replaces in the reference.
 #include "mgc_model.hpp"
 
+#include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
@@ -19,6 +21,8 @@ struct RawSection {
     std::vector<double> cod;  // [4^(kc+1)][3] natural index
     std::vector<double> non;  // [4^(kn+1)]
     bool has_cod = false, has_non = false;
+    std::string label;        // as written ("__B_GC_35"): the binary visits sections in the lexicographic order of these
+    long gc_dist_values = 0;  // lines seen under $GENE_GC_DIST_MAT
 };
 
 int letter(char c) {
@@ -70,7 +74,7 @@ Model parse_model_file(const std::string &path) {
     if (!in) throw std::runtime_error("error, cannot open file: " + path);
     std::vector<RawSection> raw;
     RawSection *cur = nullptr;
-    enum { SCALARS, NON, COD, SKIP } mode = SCALARS;
+    enum { SCALARS, NON, COD, SKIP, GC_DIST } mode = SCALARS;
     std::string line;
     while (std::getline(in, line)) {
         std::istringstream ls(line);
@@ -89,6 +93,7 @@ Model parse_model_file(const std::string &path) {
                 cur = &raw.back();
                 cur->domain = dom;
                 cur->gc = gc;
+                cur->label = tok;
             }
             continue;  // other sections (__NATIVE, __START, ...) are not on the -M path
         }
@@ -98,14 +103,18 @@ Model parse_model_file(const std::string &path) {
             mode = SCALARS;
             if (key == "NON_MAT") {
                 int kn = (int)need(*cur, "NON_ORDER");
+                if (kn < 0 || kn > kMaxOrder) throw std::runtime_error("error, $NON_ORDER outside 0..5");
                 cur->non.assign(pow4(kn + 1), 0.0);
                 cur->has_non = true;
                 mode = NON;
             } else if (key == "COD_MAT") {
                 int kc = (int)need(*cur, "COD_ORDER");
+                if (kc < 0 || kc > kMaxOrder) throw std::runtime_error("error, $COD_ORDER outside 0..5");
                 cur->cod.assign(pow4(kc + 1) * 3, 0.0);
                 cur->has_cod = true;
                 mode = COD;
+            } else if (key == "GENE_GC_DIST_MAT") {
+                mode = GC_DIST;
             } else if (key.size() > 4 && key.compare(key.size() - 4, 4, "_MAT") == 0) {
                 mode = SKIP;
             } else {
@@ -118,6 +127,7 @@ Model parse_model_file(const std::string &path) {
             }
             continue;
         }
+        if (mode == GC_DIST) { cur->gc_dist_values++; continue; }
         if (mode == NON || mode == COD) {
             long id = natural_index(tok);
             int want = (int)need(*cur, mode == NON ? "NON_ORDER" : "COD_ORDER") + 1;
@@ -242,6 +252,43 @@ Model parse_model_file(const std::string &path) {
         }
         sc.ln_pn = std::log(need(s, "COD_P_N") / need(s, "NON_P_N"));
         sc.ln_cpn = std::log(need(s, "COD_P_N"));
+    }
+    // Optional keys (each probed against the binary, DESIGN.md §2 rule 9).  $TO_MGM, $TO_ATYPICAL_FIRST_BACTERIA and
+    // $TO_ATYPICAL_SECOND_ARCHAEA are FILE-level: the binary walks its sections in the lexicographic order of their labels
+    // ("__A_GC_35" < "__B_GC_100" < "__B_GC_35" < "__B_GC_9") and every section that carries a key overwrites the value.
+    // $GENE_GC_DIST only has its matrix checked (101 entries), it does not change the -M path's output; $TO_NATIVE, $BUILD
+    // and unknown keys are ignored; a non-zero $RBS / $PROMOTER / $SC_RBS / $SC_PROMOTER switches a site model on, whose
+    // scores this build does not reproduce: refused rather than scored silently wrong.
+    {
+        std::vector<const RawSection *> order(slots.begin(), slots.end());
+        std::sort(order.begin(), order.end(), [](const RawSection *a, const RawSection *b) { return a->label < b->label; });
+        double to_mgm = 0.5, to_atyp[2] = {0.5, 0.5};
+        const char *names[3] = {"TO_MGM", "TO_ATYPICAL_FIRST_BACTERIA", "TO_ATYPICAL_SECOND_ARCHAEA"};
+        for (const RawSection *s : order) {
+            for (const char *k : {"RBS", "PROMOTER", "SC_RBS", "SC_PROMOTER"})
+                if (opt(*s, k, 0.0) != 0.0)
+                    throw std::runtime_error(std::string("error, $") + k + " site models are not supported on the -M path of this build");
+            if (opt(*s, "GENE_GC_DIST", 0.0) != 0.0) {
+                if (s->gc_dist_values == 0) throw std::runtime_error("error, parameter not found: $GENE_GC_DIST_MAT");
+                if (s->gc_dist_values != 101)
+                    throw std::runtime_error("error, diff between expected and observed number of values for key $GENE_GC_DIST_MAT 101 " +
+                                             std::to_string(s->gc_dist_values));
+            }
+            auto it = s->num.find(names[0]);
+            if (it != s->num.end()) to_mgm = it->second;
+            for (int d = 0; d < 2; d++) {
+                it = s->num.find(names[1 + d]);
+                if (it != s->num.end()) to_atyp[d] = it->second;
+            }
+        }
+        const double vals[3] = {to_mgm, to_atyp[0], to_atyp[1]};
+        for (int i = 0; i < 3; i++)
+            if (vals[i] < 0) {
+                char buf[160];
+                std::snprintf(buf, sizeof buf, "error in value of the parameter with key: $%s %g", names[i], vals[i]);
+                throw std::runtime_error(buf);
+            }
+        for (int si = 0; si < m.nsec; si++) m.sc[si].tr = std::log(to_mgm * to_atyp[slots[si]->domain]);
     }
     // a section serves the GC values up to its label: missing bin -> next higher provided; above all -> highest
     for (int d = 0; d < 2; d++) {

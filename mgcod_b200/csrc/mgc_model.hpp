@@ -20,6 +20,8 @@ struct SectionScalars {
     double stop_lo[3];      // ln(P(TAA|TAG|TGA) / Pnon(codon))
     double ln_pn;           // ln($COD_P_N / $NON_P_N)
     double ln_cpn;          // ln($COD_P_N)
+    double tr;              // ln(to_mgm * to_atypical of the section's domain): ln 0.25 unless the file sets $TO_MGM /
+                            // $TO_ATYPICAL_FIRST_BACTERIA / $TO_ATYPICAL_SECOND_ARCHAEA (file-level values, DESIGN.md §2 rule 9)
 };
 
 // One parsed file.  Section slots are numbered 0..nsec-1 in the order (domain, gc).

@@ -163,8 +163,13 @@ class Fasta:
         if rc != 0:
             raise OSError(_lib.last_error())
         n = L.mgc_fasta_num_records(self._h)
-        self.ids = [L.mgc_fasta_id(self._h, i).decode() for i in range(n)]
-        self.deflines = [L.mgc_fasta_defline(self._h, i).decode() for i in range(n)]
+
+        def joined(which):       # all ids / deflines in one call, each followed by a newline
+            ln = C.c_int64()
+            p = L.mgc_fasta_ids_joined(self._h, which, C.byref(ln))
+            return C.string_at(p, ln.value).decode(errors="replace").split("\n")[:n] if n else []
+        self.ids = joined(0)
+        self.deflines = joined(1)
         self.offsets = np.ctypeslib.as_array(L.mgc_fasta_offsets(self._h), shape=(n + 1,)).copy()
         total = int(self.offsets[-1])
         ptr = L.mgc_fasta_sequence(self._h)

@@ -125,6 +125,17 @@ class Result:
             self._h = None
 
 
+class DeviceGenes:
+    """n gene rows of 32 bytes in device memory (see :meth:`Engine.device_genes`)."""
+
+    def __init__(self, ptr: int, n: int):
+        self.ptr, self.n = ptr, n
+        self.__cuda_array_interface__ = {"shape": (n * 32,), "typestr": "|u1", "data": (ptr, True), "version": 2, "strides": None}
+
+    def __len__(self):
+        return self.n
+
+
 class Engine:
     """One per process per GPU.  ``models`` in label order (Mgcod: codes 11, 4, 15, 101)."""
 
@@ -232,6 +243,14 @@ class Engine:
         _check(_lib.lib().mgc_decode_batch(self._h, C.c_void_p(buf.ctypes.data), offsets.ctypes.data_as(C.POINTER(C.c_int64)),
                                            self.n_contigs, C.byref(r)))
         return Result(r, self.n_models, self.n_contigs)
+
+    def device_genes(self, model: int) -> "DeviceGenes":
+        """The gene table of the last decode where it sits in device memory (GENE_DTYPE rows as bytes), exposed through
+        ``__cuda_array_interface__`` so that ``torch.as_tensor(x, device='cuda')`` wraps it without a copy — the send buffer of
+        the multi-GPU gather (:func:`mgcod_b200.shard.gather_genes_device`).  Valid until the next decode on this engine."""
+        p, n = C.c_void_p(), C.c_int64()
+        _check(_lib.lib().mgc_engine_device_genes(self._h, model, C.byref(p), C.byref(n)))
+        return DeviceGenes(p.value or 0, int(n.value))
 
     def stats(self) -> dict:
         s = Stats()
@@ -355,24 +374,8 @@ class Engine:
         self.close()
 
 
-def synth_metagenome(seed: int, total_bp: int, min_len: int = 5000, max_len: int = 500000, threads: int = 8,
-                     out: np.ndarray | None = None) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
-    """Synthetic contigs of BASELINE.json config 5: lengths ~ L^-2 on [min_len, max_len] until
-    ``total_bp``; gene-like content with a per-contig GC regime and true genetic code.
-    → (ascii buffer uint8, offsets int64[n+1], truth_code int32[n])."""
-    L = _lib.lib()
-    cap = total_bp // min_len + 16
-    lens = np.zeros(cap, dtype=np.int64)
-    n = L.mgc_synth_lengths(seed, total_bp, min_len, max_len, lens.ctypes.data_as(C.POINTER(C.c_int64)), cap)
-    if n < 0:
-        raise MgcodError(int(n), _lib.last_error())
-    lens = lens[:n].copy()
-    offs = np.zeros(n + 1, dtype=np.int64)
-    np.cumsum(lens, out=offs[1:])
-    buf = out if out is not None else np.empty(int(offs[-1]), dtype=np.uint8)
-    if buf.size < offs[-1]:
-        raise ValueError("output buffer too small")
-    truth = np.zeros(n, dtype=np.int32)
-    _check(L.mgc_synth_contigs(seed, lens.ctypes.data_as(C.POINTER(C.c_int64)), n, C.c_void_p(buf.ctypes.data),
-                               truth.ctypes.data_as(C.POINTER(C.c_int32)), threads))
-    return buf[:int(offs[-1])], offs, truth
+def synth_metagenome(*args, **kw):
+    """The synthetic workload of BASELINE.json config 5 — lives in the host-only ``workload`` package (its own small
+    library), re-exported here for the tests and tools that have always imported it from the engine module."""
+    from workload import synth_metagenome as _synth
+    return _synth(*args, **kw)

@@ -17,6 +17,8 @@ import sys
 
 from . import cli
 
+DRIVER_FLAGS = ("--genomes", "--threads", "--batch_size", "-i", "--path_to_genome", "--device")   # not part of the per-genome command
+
 
 def main(argv=None) -> int:
     p = cli.build_parser()
@@ -38,8 +40,10 @@ def main(argv=None) -> int:
         if skip_next:
             skip_next = False
             continue
-        if tok in ("--genomes", "--threads", "--batch_size", "-i", "--path_to_genome", "--device"):
+        if tok in DRIVER_FLAGS:
             skip_next = True
+            continue
+        if tok.split("=", 1)[0] in DRIVER_FLAGS and "=" in tok:      # --genomes=list.txt, --threads=8, ...
             continue
         base.append(tok)
     failed = 0

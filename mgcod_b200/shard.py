@@ -47,3 +47,74 @@ def gather_genes(local_genes: np.ndarray, local_contigs: np.ndarray, group=None)
     genes = [np.frombuffer(g, dtype=np.dtype(d)) for g, _, d in gathered]
     contigs = [np.frombuffer(c, dtype=np.int64) for _, c, _ in gathered]
     return merge_rank_genes(genes, contigs)
+
+
+def partition_ranges(lengths: Sequence[int], n_ranks: int) -> np.ndarray:
+    """Contiguous ranges of contigs of about equal bp: → cut[n_ranks + 1]; rank r owns contigs cut[r] .. cut[r+1]-1.
+    What the GPU path uses: a rank's contigs are one slice of the host letter buffer (``offsets[cut[r]:cut[r+1]+1]`` goes to
+    the engine as it is, nothing is copied together), the shares differ by at most one contig, and the rank-local gene tables
+    concatenated in rank order are already in global (contig, left) order."""
+    lengths = np.asarray(lengths, dtype=np.int64)
+    n = len(lengths)
+    ends = np.cumsum(lengths)
+    total = int(ends[-1]) if n else 0
+    cut = np.zeros(n_ranks + 1, dtype=np.int64)
+    for r in range(1, n_ranks):
+        target = total * r / n_ranks
+        c = int(np.searchsorted(ends, target, side="left"))          # ends[c] >= target > ends[c - 1]
+        if c < n and (c == 0 or ends[c] - target <= target - ends[c - 1]):
+            c += 1                                                    # the cut behind contig c is the nearer one
+        cut[r] = max(min(c, n), cut[r - 1])
+    cut[n_ranks] = n
+    return cut
+
+
+def gather_genes_device(engine, first_contig: int, group=None, dst: int = 0):
+    """Final gather of a sharded decode over NCCL, straight from the engines' device memory: every rank contributes the gene
+    tables of its last decode (all models, 32-byte rows), rank ``dst`` returns them merged per model in global contig order
+    (other ranks return None).  ``first_contig`` = global index of the rank's first contig (``partition_ranges``).
+    Replaces the result collection of the reference's process pool (bin/multiprocess_mgcod.py:140-145)."""
+    import torch
+    return gather_gene_tables([engine.device_genes(m) for m in range(engine.n_models)], first_contig,
+                              torch.device("cuda", torch.cuda.current_device()), group, dst)
+
+
+def gather_gene_tables(tables, first_contig: int, device, group=None, dst: int = 0):
+    """The collective under :func:`gather_genes_device`.  ``tables``: one gene table per model, each either a
+    :class:`mgcod_b200.engine.DeviceGenes` (device memory, NCCL) or a GENE_DTYPE numpy array (host memory; the gloo tests).
+
+    Layout on the wire: per rank one uint8 tensor holding model 0's rows, then model 1's, ...; ranks exchange their
+    per-model counts first (one small all_gather) and pad to the largest total, because a gather takes equal sizes."""
+    import torch
+    import torch.distributed as dist
+    from .engine import GENE_DTYPE
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    M = len(tables)
+    counts = torch.tensor([len(t) for t in tables] + [int(first_contig)], dtype=torch.int64, device=device)
+    all_counts = [torch.zeros_like(counts) for _ in range(world)]
+    dist.all_gather(all_counts, counts, group=group)
+    all_counts = torch.stack(all_counts).cpu().numpy()            # [world, M + 1]
+    width = int(all_counts[:, :M].sum(axis=1).max()) * 32
+    send = torch.zeros(max(width, 32), dtype=torch.uint8, device=device)
+    at = 0
+    for t in tables:
+        if len(t):
+            src = (torch.from_numpy(np.ascontiguousarray(t, dtype=GENE_DTYPE).view(np.uint8).copy()) if isinstance(t, np.ndarray)
+                   else torch.as_tensor(t, device=device))
+            send[at:at + len(t) * 32].copy_(src)
+        at += len(t) * 32
+    recv = [torch.empty_like(send) for _ in range(world)] if rank == dst else None
+    dist.gather(send, recv, dst=dst, group=group)
+    if rank != dst:
+        return None
+    host = torch.stack(recv).cpu().numpy()                         # one copy to the host for all ranks
+    merged = []
+    for m in range(M):
+        parts = []
+        for r in range(world):
+            a = int(all_counts[r, :m].sum()) * 32
+            g = host[r, a:a + int(all_counts[r, m]) * 32].view(GENE_DTYPE).copy()
+            g["contig"] += int(all_counts[r, M])
+            parts.append(g)
+        merged.append(np.concatenate(parts))
+    return merged

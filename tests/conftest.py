@@ -11,7 +11,8 @@ if ROOT not in sys.path:
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
     # a fresh checkout has no built libraries (they are git-ignored): build product + oracle once, like the driver's build()
-    need = [os.path.join(ROOT, "mgcod_b200", "libmgcod_b200.so"), os.path.join(ROOT, "oracle", "liboracle.so")]
+    need = [os.path.join(ROOT, "mgcod_b200", "libmgcod_b200.so"), os.path.join(ROOT, "oracle", "liboracle.so"),
+            os.path.join(ROOT, "workload", "libmgc_workload.so")]
     if not all(os.path.exists(p) for p in need):
         import __graft_entry__
         __graft_entry__.build()

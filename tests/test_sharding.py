@@ -56,3 +56,59 @@ def test_two_rank_gather_equals_single_rank(model_dir):
             p.join(180)
             assert p.exitcode == 0
         assert ret["ok"] and ret["n"] > 50
+
+
+def test_range_partition_is_contiguous_and_balanced():
+    rng = np.random.default_rng(2)
+    lens = rng.integers(5000, 500000, 1000)
+    for n in (1, 2, 3, 8):
+        cut = shard.partition_ranges(lens, n)
+        assert cut[0] == 0 and cut[-1] == 1000 and (np.diff(cut) >= 0).all()
+        loads = np.array([lens[cut[r]:cut[r + 1]].sum() for r in range(n)])
+        assert loads.max() - loads.min() <= lens.max()
+    assert shard.partition_ranges([10, 10], 4).tolist() == [0, 1, 1, 2, 2]       # more ranks than contigs: empty shares
+    assert shard.partition_ranges([], 3).tolist() == [0, 0, 0, 0]
+
+
+def _range_worker(rank, world, port, model_paths, ret):
+    import torch
+    import torch.distributed as dist
+    from mgcod_b200.engine import synth_metagenome
+    from oracle import gmhmm
+    from tests import fixtures as fx
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    buf, offs, _ = synth_metagenome(6, 150000, threads=1)
+    cut = shard.partition_ranges(np.diff(offs), world)
+    models = [gmhmm.Model(p) for p in model_paths]
+    mine = range(int(cut[rank]), int(cut[rank + 1]))
+    tables = [fx.genes_array_from_oracle(m, [buf[offs[c]:offs[c + 1]].tobytes() for c in mine])[0] for m in models]
+    merged = shard.gather_gene_tables(tables, int(cut[rank]), torch.device("cpu"))
+    if rank == 0:
+        full = [fx.genes_array_from_oracle(m, [buf[offs[c]:offs[c + 1]].tobytes() for c in range(len(offs) - 1)])[0] for m in models]
+        ret["ok"] = all(a.shape == b.shape and (a == b).all() for a, b in zip(merged, full))
+        ret["n"] = int(sum(len(f) for f in full))
+    else:
+        assert merged is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_table_gather_equals_single_rank(model_dir):
+    """the collective of the GPU path (counts all_gather + padded gather of the 32-byte gene rows of all models) on gloo"""
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    with ctx.Manager() as man:
+        ret = man.dict()
+        paths = [f"{model_dir}/mgm_11.mod", f"{model_dir}/mgm_4.mod"]
+        procs = [ctx.Process(target=_range_worker, args=(r, 2, port, paths, ret)) for r in range(2)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(180)
+            assert p.exitcode == 0
+        assert ret["ok"] and ret["n"] > 100

@@ -130,14 +130,18 @@ def compare_gff(work, modpath, seq):
     fa, out = os.path.join(work, "c.fa"), os.path.join(work, "c.gff")
     open(fa, "w").write(f">t\n{seq}\n")
     code, text = run_gm(modpath, fa, out)
-    if code != 0:
+    if code != 0 or not os.path.exists(out):       # the binary reports some errors with exit status 0 and no output
         try:
             gmhmm.Model(modpath)
         except RuntimeError:
             return [], 0      # both refuse the file
         return [f"binary failed ({text.strip()[:80]}), oracle accepted"], 0
     ref = gff_rows(out)
-    mine = oracle_rows(gmhmm.Model(modpath), seq)
+    try:
+        model = gmhmm.Model(modpath)
+    except RuntimeError as ex:
+        return [f"oracle refused ({ex}), binary accepted"], len(ref)
+    mine = oracle_rows(model, seq)
     if mine != ref:
         a, b = set(mine), set(ref)
         return [f"genes only oracle {sorted(a - b)[:3]} only binary {sorted(b - a)[:3]}"], len(ref)
@@ -190,8 +194,10 @@ def main():
             kc = rng.choice([1, 2, 3, 4, 5])
             kn = min(rng.choice([0, 1, 2, 3]), kc)
             doms = rng.choice([("B",), ("B", "A")])
-            secs = synth.trained_sections(xph, code, kc, kn, bins=sorted(rng.sample(range(20, 50), rng.choice([1, 3]))),
-                                          domains=doms)
+            bins = sorted(rng.sample(range(20, 50), rng.choice([1, 3])))
+            if mode == "keys":      # labels whose lexicographic and numeric orders differ (9 / 35 / 100)
+                bins = sorted(rng.sample([5, 9, 20, 28, 35, 42, 100], rng.choice([2, 3, 4])))
+            secs = synth.trained_sections(xph, code, kc, kn, bins=bins, domains=doms)
             for s in secs:
                 if s.label.startswith("__A"):
                     s.cod_p_n, s.non_p_n = 0.3, 0.7
@@ -218,11 +224,13 @@ def main():
                 for _ in range(rng.choice([0, 1, 2])):
                     s[rng.choice([rng.randrange(0, 8), L - 1 - rng.randrange(0, 8)])] = "N"
             elif mode == "keys":
-                extra = rng.sample(KEY_LINES, rng.choice([1, 1, 2, 3]))
+                # optional keys in front of the matrices of randomly chosen sections (the binary lets the section that comes
+                # last in the lexicographic order of the labels decide)
                 text = open(mp).read().split("\n")
-                # the optional keys go in front of the matrices of the first section
-                at = next(i for i, l in enumerate(text) if l.startswith("$NON_MAT"))
-                text[at:at] = extra
+                ats = [i for i, l in enumerate(text) if l.startswith("$NON_MAT")]
+                for at in sorted(rng.sample(ats, rng.randint(1, len(ats))), reverse=True):
+                    text[at:at] = [k.format(v=rng.choice(["0.3", "0.7", "0.05", "0.5", "1", "0.9"]))
+                                   for k in rng.sample(KEY_LINES, rng.choice([1, 1, 2, 3]))]
                 open(mp, "w").write("\n".join(text))
             msgs, n = compare_gff(work, mp, "".join(s))
             tag = f"code {code} orders {kc}/{kn} sections {len(secs)} L {L}"
@@ -238,8 +246,8 @@ def main():
 
 
 # optional keys of SURVEY.md §A.2 with a value the parser accepts (see DESIGN.md §2 for what each one does)
-KEY_LINES = ["$TO_MGM 0.3", "$TO_NATIVE 0.7", "$TO_ATYPICAL_FIRST_BACTERIA 0.7", "$TO_ATYPICAL_SECOND_ARCHAEA 0.2",
-             "$BUILD test"]
+KEY_LINES = ["$TO_MGM {v}", "$TO_NATIVE {v}", "$TO_ATYPICAL_FIRST_BACTERIA {v}", "$TO_ATYPICAL_SECOND_ARCHAEA {v}",
+             "$BUILD test", "$RBS 0", "$PROMOTER 0", "$GENE_GC_DIST 0", "$TO_MGM -1"]
 
 if __name__ == "__main__":
     sys.exit(main())
