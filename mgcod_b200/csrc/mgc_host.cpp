@@ -54,17 +54,18 @@ struct TextOut {
     FILE *f;
     std::vector<char> buf;
     size_t n = 0;
-    explicit TextOut(FILE *fp) : f(fp), buf(1 << 22) {}
+    explicit TextOut(FILE *fp, size_t reserve = 1 << 22) : f(fp), buf(reserve) {}
     void room(size_t need) {
-        if (n + need > buf.size()) flush();
+        if (n + need <= buf.size()) return;
+        if (f) flush();
+        if (n + need > buf.size()) buf.resize(std::max(buf.size() * 2, n + need));   // memory-only mode (f == nullptr): grow
     }
     void flush() {
-        if (n) std::fwrite(buf.data(), 1, n, f);
-        n = 0;
+        if (n && f) std::fwrite(buf.data(), 1, n, f);
+        if (f) n = 0;
     }
     void str(const char *s, size_t len) {
         room(len);
-        if (len > buf.size()) { std::fwrite(s, 1, len, f); return; }
         std::memcpy(buf.data() + n, s, len);
         n += len;
     }
@@ -121,50 +122,83 @@ int mgc_write_gff(const mgc_result *r, int model, const char *const *contig_ids,
     std::fprintf(f, "# File with MetaGeneMark parameters: %s\n", mod_file_name ? mod_file_name : "");
     std::fprintf(f, "# translation table: %d\n", gcode);
     std::fprintf(f, "# output date start: %s\n", date.c_str());
-    int64_t k = 0;
-    long gene_id = 0;
-    TextOut o(f);
-    char tmp[256];
-    for (int32_t c = 0; c < n_contigs; c++) {
-        const char *id = contig_ids[c];
-        const size_t idlen = std::strlen(id);
-        const long long L = (long long)contig_len[c];
-        o.ch('\n');
-        if (lst) {
-            o.str("# sequence-region "); o.ch(L > 0 ? '1' : '0'); o.ch(' '); o.i64(L); o.str("\nSequenceID: "); o.str(id, idlen); o.ch('\n');
-        } else {
-            o.str("##sequence-region "); o.str(id, idlen); o.ch(' '); o.ch(L > 0 ? '1' : '0'); o.ch(' '); o.i64(L); o.ch('\n');
+    // The records are formatted by several threads, each a contiguous range of contigs with about the same number of genes,
+    // into memory; the pieces are written in order.  gene_id counts across records, so a piece starts at 1 + the number of
+    // genes in front of it (the table is ordered by contig).
+    std::vector<int64_t> first_gene((size_t)n_contigs + 1, ng);     // first gene of every contig
+    {
+        int64_t k = 0;
+        for (int32_t c = 0; c < n_contigs; c++) {
+            first_gene[c] = k;
+            while (k < ng && genes[k].contig == c) k++;
         }
-        int64_t first = k;
-        long long len_sum = 0;
-        while (k < ng && genes[k].contig == c) {
-            const mgc_gene &g = genes[k];
-            const int len = g.right - g.left + 1;
-            len_sum += len;
-            gene_id++;
-            const char *type = g.domain ? "archaea" : "bacteria";
-            if (lst) {
-                const int n = std::snprintf(tmp, sizeof tmp, "%6ld   %c   %c%d   %c%d %7d %s\n", gene_id, g.strand > 0 ? '+' : '-',
-                                            g.partial_left ? '<' : ' ', g.left, g.partial_right ? '>' : ' ', g.right, len, type);
-                o.str(tmp, (size_t)n);
-            } else {
-                o.str(id, idlen); o.str("\tGeneMark.hmm2\tCDS\t"); o.i64(g.left); o.ch('\t'); o.i64(g.right); o.ch('\t'); o.fixed2(g.logodd);
-                o.ch('\t'); o.ch(g.strand > 0 ? '+' : '-'); o.str("\t0\tgene_id "); o.i64(gene_id); o.str("; gene_type "); o.str(type); o.str("; ");
-                if (g.partial_left || g.partial_right) { o.str("partial "); o.ch(g.partial_left ? '1' : '0'); o.ch(g.partial_right ? '1' : '0'); o.str("; "); }
-                o.str("gc "); o.i64(g.gc); o.str("; length "); o.i64(len); o.str(";\n");
-            }
-            k++;
-        }
-        const int64_t n = k - first;
-        if (n > 0) {
-            const int m = std::snprintf(tmp, sizeof tmp, "\ttotal_logodd\t%g\taverage_length\t%lld\taverage_density\t%.2f\n", totals[c],
-                                        (long long)((double)len_sum / (double)n + 0.5), (double)n / ((double)L / 1000.0));
-            o.str("# "); o.str(id, idlen); o.str(tmp, (size_t)m);
-        } else if (L >= min_len) {  // a record the binary decoded without finding a gene; shorter records are skipped outright
-            o.str("# "); o.str(id, idlen); o.str("\ttotal_logodd\t0\taverage_length\t0\taverage_density\t0.00\n");
-        }
+        first_gene[n_contigs] = k;
     }
-    o.flush();
+    int pieces = (int)std::min<int64_t>(std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency() / 4), 8u), ng / 20000 + 1);
+    if (const char *env = std::getenv("MGCOD_B200_WRITER_THREADS")) pieces = std::max(1, std::atoi(env));
+    std::vector<int32_t> cut((size_t)pieces + 1, n_contigs);
+    cut[0] = 0;
+    for (int t = 1; t < pieces; t++) {
+        const int64_t want = ng * t / pieces;
+        cut[t] = (int32_t)(std::lower_bound(first_gene.begin(), first_gene.end(), want) - first_gene.begin());
+        cut[t] = std::min<int32_t>(std::max(cut[t], cut[t - 1]), n_contigs);
+    }
+    std::vector<TextOut> outs;
+    outs.reserve(pieces);
+    for (int t = 0; t < pieces; t++) outs.emplace_back(nullptr, (size_t)((first_gene[cut[t + 1]] - first_gene[cut[t]]) * 112 + (cut[t + 1] - cut[t]) * 160 + 4096));
+    auto format_range = [&](int t) {
+        TextOut &o = outs[t];
+        char tmp[256];
+        int64_t k = first_gene[cut[t]];
+        long gene_id = (long)k;
+        for (int32_t c = cut[t]; c < cut[t + 1]; c++) {
+            const char *id = contig_ids[c];
+            const size_t idlen = std::strlen(id);
+            const long long L = (long long)contig_len[c];
+            o.ch('\n');
+            if (lst) {
+                o.str("# sequence-region "); o.ch(L > 0 ? '1' : '0'); o.ch(' '); o.i64(L); o.str("\nSequenceID: "); o.str(id, idlen); o.ch('\n');
+            } else {
+                o.str("##sequence-region "); o.str(id, idlen); o.ch(' '); o.ch(L > 0 ? '1' : '0'); o.ch(' '); o.i64(L); o.ch('\n');
+            }
+            int64_t first = k;
+            long long len_sum = 0;
+            while (k < ng && genes[k].contig == c) {
+                const mgc_gene &g = genes[k];
+                const int len = g.right - g.left + 1;
+                len_sum += len;
+                gene_id++;
+                const char *type = g.domain ? "archaea" : "bacteria";
+                if (lst) {
+                    const int n = std::snprintf(tmp, sizeof tmp, "%6ld   %c   %c%d   %c%d %7d %s\n", gene_id, g.strand > 0 ? '+' : '-',
+                                                g.partial_left ? '<' : ' ', g.left, g.partial_right ? '>' : ' ', g.right, len, type);
+                    o.str(tmp, (size_t)n);
+                } else {
+                    o.str(id, idlen); o.str("\tGeneMark.hmm2\tCDS\t"); o.i64(g.left); o.ch('\t'); o.i64(g.right); o.ch('\t'); o.fixed2(g.logodd);
+                    o.ch('\t'); o.ch(g.strand > 0 ? '+' : '-'); o.str("\t0\tgene_id "); o.i64(gene_id); o.str("; gene_type "); o.str(type); o.str("; ");
+                    if (g.partial_left || g.partial_right) { o.str("partial "); o.ch(g.partial_left ? '1' : '0'); o.ch(g.partial_right ? '1' : '0'); o.str("; "); }
+                    o.str("gc "); o.i64(g.gc); o.str("; length "); o.i64(len); o.str(";\n");
+                }
+                k++;
+            }
+            const int64_t n = k - first;
+            if (n > 0) {
+                const int m = std::snprintf(tmp, sizeof tmp, "\ttotal_logodd\t%g\taverage_length\t%lld\taverage_density\t%.2f\n", totals[c],
+                                            (long long)((double)len_sum / (double)n + 0.5), (double)n / ((double)L / 1000.0));
+                o.str("# "); o.str(id, idlen); o.str(tmp, (size_t)m);
+            } else if (L >= min_len) {  // a record the binary decoded without finding a gene; shorter records are skipped outright
+                o.str("# "); o.str(id, idlen); o.str("\ttotal_logodd\t0\taverage_length\t0\taverage_density\t0.00\n");
+            }
+        }
+    };
+    if (pieces == 1) format_range(0);
+    else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < pieces; t++) pool.emplace_back(format_range, t);
+        for (auto &th : pool) th.join();
+    }
+    for (int t = 0; t < pieces; t++)
+        if (outs[t].n) std::fwrite(outs[t].buf.data(), 1, outs[t].n, f);
     if (lst) std::fprintf(f, "\n# output date end: %s\n# Done with file: %s\n", date.c_str(), seq_file_name ? seq_file_name : "");
     if (std::fclose(f) != 0) return mgc::set_error(MGC_E_IO, "write failed");
     return MGC_OK;

@@ -70,18 +70,38 @@ std::vector<double> prefix_marginal(const std::vector<double> &t, int cols) {
 }  // namespace
 
 Model parse_model_file(const std::string &path) {
-    std::ifstream in(path);
-    if (!in) throw std::runtime_error("error, cannot open file: " + path);
+    // the whole file at once, then tokens by hand: a real mgm_*.mod is ~100 000 lines of "KMER p1 p2 p3", and one
+    // istringstream per line cost more than everything else the engine does for a small genome
+    std::string text;
+    {
+        std::ifstream in(path, std::ios::binary);
+        if (!in) throw std::runtime_error("error, cannot open file: " + path);
+        in.seekg(0, std::ios::end);
+        const std::streamoff n = in.tellg();
+        in.seekg(0, std::ios::beg);
+        text.resize(n > 0 ? (size_t)n : 0);
+        if (n > 0) in.read(&text[0], n);
+    }
     std::vector<RawSection> raw;
-    RawSection *cur = nullptr;
+    raw.reserve(256);          // cur points into it: no reallocation while parsing (sections beyond are appended by index)
+    size_t cur_i = (size_t)-1;
     enum { SCALARS, NON, COD, SKIP, GC_DIST } mode = SCALARS;
-    std::string line;
-    while (std::getline(in, line)) {
-        std::istringstream ls(line);
-        std::string tok;
-        if (!(ls >> tok)) continue;
-        if (tok.rfind("__", 0) == 0) {
-            cur = nullptr;
+    int want = 0;              // k-mer length of the matrix being read
+    const char *p = text.data(), *end = p + text.size();
+    auto blank = [](char c) { return c == ' ' || c == '\t' || c == '\r'; };
+    while (p < end) {
+        const char *le = static_cast<const char *>(std::memchr(p, '\n', (size_t)(end - p)));
+        if (!le) le = end;
+        const char *a = p;
+        p = le < end ? le + 1 : end;
+        while (a < le && blank(*a)) a++;
+        if (a == le) continue;
+        const char *b = a;
+        while (b < le && !blank(*b)) b++;          // first token [a, b)
+        RawSection *cur = cur_i == (size_t)-1 ? nullptr : &raw[cur_i];
+        if (b - a >= 2 && a[0] == '_' && a[1] == '_') {
+            const std::string tok(a, b);
+            cur_i = (size_t)-1;
             mode = SCALARS;
             int dom = -1;
             if (tok.rfind("__B_GC_", 0) == 0) dom = 0;
@@ -90,16 +110,16 @@ Model parse_model_file(const std::string &path) {
                 int gc = std::atoi(tok.c_str() + 7);
                 if (gc < 0 || gc > 100) throw std::runtime_error("error, GC bin out of range: " + tok);
                 raw.emplace_back();
-                cur = &raw.back();
-                cur->domain = dom;
-                cur->gc = gc;
-                cur->label = tok;
+                cur_i = raw.size() - 1;
+                raw[cur_i].domain = dom;
+                raw[cur_i].gc = gc;
+                raw[cur_i].label = tok;
             }
             continue;  // other sections (__NATIVE, __START, ...) are not on the -M path
         }
         if (!cur) continue;
-        if (tok[0] == '$') {
-            std::string key = tok.substr(1);
+        if (*a == '$') {
+            const std::string key(a + 1, b);
             mode = SCALARS;
             if (key == "NON_MAT") {
                 int kn = (int)need(*cur, "NON_ORDER");
@@ -107,36 +127,51 @@ Model parse_model_file(const std::string &path) {
                 cur->non.assign(pow4(kn + 1), 0.0);
                 cur->has_non = true;
                 mode = NON;
+                want = kn + 1;
             } else if (key == "COD_MAT") {
                 int kc = (int)need(*cur, "COD_ORDER");
                 if (kc < 0 || kc > kMaxOrder) throw std::runtime_error("error, $COD_ORDER outside 0..5");
                 cur->cod.assign(pow4(kc + 1) * 3, 0.0);
                 cur->has_cod = true;
                 mode = COD;
+                want = kc + 1;
             } else if (key == "GENE_GC_DIST_MAT") {
                 mode = GC_DIST;
             } else if (key.size() > 4 && key.compare(key.size() - 4, 4, "_MAT") == 0) {
                 mode = SKIP;
             } else {
-                std::string val;
-                if (ls >> val) {
-                    char *end = nullptr;
-                    double v = std::strtod(val.c_str(), &end);
-                    if (end != val.c_str()) cur->num[key] = v;
+                const char *v = b;
+                while (v < le && blank(*v)) v++;
+                if (v < le) {
+                    const std::string val(v, le);      // strtod needs a terminated string
+                    char *stop = nullptr;
+                    const double x = std::strtod(val.c_str(), &stop);
+                    if (stop != val.c_str()) cur->num[key] = x;
                 }
             }
             continue;
         }
         if (mode == GC_DIST) { cur->gc_dist_values++; continue; }
         if (mode == NON || mode == COD) {
-            long id = natural_index(tok);
-            int want = (int)need(*cur, mode == NON ? "NON_ORDER" : "COD_ORDER") + 1;
-            if (id < 0 || (int)tok.size() != want) throw std::runtime_error("error, label has unexpected length");
-            if (mode == NON) {
-                if (!(ls >> cur->non[id])) throw std::runtime_error("error, missing value in $NON_MAT");
-            } else {
-                for (int c = 0; c < 3; c++)
-                    if (!(ls >> cur->cod[id * 3 + c])) throw std::runtime_error("error, missing value in $COD_MAT");
+            long id = 0;
+            bool ok = (int)(b - a) == want;
+            for (const char *q = a; q < b && ok; q++) {
+                const int x = letter(*q);
+                ok = x >= 0;
+                id = id * 4 + x;
+            }
+            if (!ok) throw std::runtime_error("error, label has unexpected length");
+            // the values: up to three numbers behind the k-mer; the line ends at a newline, which stops strtod
+            const char *v = b;
+            const int cols = mode == NON ? 1 : 3;
+            for (int c = 0; c < cols; c++) {
+                while (v < le && blank(*v)) v++;
+                char *stop = nullptr;
+                const double x = v < le ? std::strtod(v, &stop) : 0.0;     // text ends with the file's own bytes; a number never runs past '\n'
+                if (v >= le || stop == v || stop > le) throw std::runtime_error(mode == NON ? "error, missing value in $NON_MAT" : "error, missing value in $COD_MAT");
+                if (mode == NON) cur->non[id] = x;
+                else cur->cod[id * 3 + c] = x;
+                v = stop;
             }
         }
     }

@@ -197,7 +197,10 @@ def shared_engine(model_dir: str, device: int = 0) -> Engine:
     not once per genome as in the reference (4 subprocesses per FASTA)."""
     key = (os.path.abspath(model_dir), device)
     if key not in _ENGINES:
-        _ENGINES[key] = Engine([ModelFile(os.path.join(model_dir, f"mgm_{c}.mod")) for c in MGCOD_CODES], device=device)
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(len(MGCOD_CODES)) as pool:      # the four parameter files are parsed side by side (no GIL inside)
+            models = list(pool.map(lambda c: ModelFile(os.path.join(model_dir, f"mgm_{c}.mod")), MGCOD_CODES))
+        _ENGINES[key] = Engine(models, device=device)
     return _ENGINES[key]
 
 
@@ -276,7 +279,10 @@ class Data:
 
     def _decode(self):
         """all contigs of the file under the four parameter files on the GPU → engine.Result"""
+        import time
+        t0 = time.perf_counter()
         self.engine = shared_engine(self.model_dir, self.device)
+        self.timings = {"engine_setup": round(time.perf_counter() - t0, 4)}
         # inputs larger than one device batch are streamed in pieces and merged on the host (GFF files only: the window
         # labels of --isoforms and the recoded-stop scan need the whole input resident)
         result = self.engine.decode_large(self._fasta.buffer, self._fasta.offsets)

@@ -101,7 +101,8 @@ class Result:
         if n == 0:
             return np.zeros(0, GENE_DTYPE)
         p = L.mgc_result_genes(self._h, model)
-        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(n * 32,)).view(GENE_DTYPE).copy()
+        # copied as plain bytes (numpy copies a structured array field by field, 10x slower), then viewed as rows
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(n * 32,)).copy().view(GENE_DTYPE)
 
     def contig_totals(self, model: int) -> np.ndarray:
         p = _lib.lib().mgc_result_contig_totals(self._h, model)

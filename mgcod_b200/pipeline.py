@@ -59,16 +59,26 @@ class Pipeline:
     gene_coords_101 = property(lambda self: self.label_to_gene_coords[3])
 
     def __call__(self):
+        import time
+        t = [time.perf_counter()]
         data = Data(self.path_to_genome, self.path_to_predictions, self.verbose, self.cwd, self.species,
                     model_dir=self.model_dir, device=self.device)
         self.data = data
         self.sequence = data.read_dna_sequence()
         self.nr_contigs = len(self.sequence)
+        t.append(time.perf_counter())
         data.run_mgm(need_genes=self.isoforms)      # the four GFF files are written in the background meanwhile
+        t.append(time.perf_counter())
         try:
             self._analyse()
+            t.append(time.perf_counter())
         finally:
             data.finish_writes()
+        t.append(time.perf_counter())
+        # where the wall time of this run went (seconds): reading the FASTA, decode (incl. engine set-up on first use),
+        # labelling + comparison + segmentation, waiting for the background GFF writers
+        self.timings = dict(zip(("read", "decode", "analyse", "wait_for_gff_writers"), np.diff(t).round(4).tolist()))
+        self.timings.update(getattr(data, "timings", {}))
 
     def _analyse(self):
         data = self.data

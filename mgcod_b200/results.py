@@ -208,10 +208,8 @@ class Results:
         for i, contig in enumerate(level_1):
             g = P.gene_label_to_gcode[contig]
             if i == 0:
-                for c in level_1:
-                    for key in ("Coordinates in bp", "Major genetic code", f"Nr genes with {g[1]}", "Nr identical genes",
-                                "Nr isoforms", "Total gene count"):
-                        table.add_row((c, key))
+                table.add_rows(level_1, ("Coordinates in bp", "Major genetic code", f"Nr genes with {g[1]}", "Nr identical genes",
+                                         "Nr isoforms", "Total gene count"))
             segments = sorted(P.confident_1[contig] + P.confident_2[contig])
             if len(g) == 1:
                 table.set((contig, "Coordinates in bp"), "Sequence", str(segments[0]))
@@ -319,35 +317,54 @@ class Results:
 
 
 class _Table:
-    """The cells of the reference's classification DataFrame in the order it creates them (bin/results.py:101-157)."""
+    """The cells of the reference's classification DataFrame in the order it creates them (bin/results.py:101-157).
+    Rows keep their cells in a dict of their own: a metagenome has six rows per contig, most of them empty."""
 
     def __init__(self):
-        self.rows, self.cols, self.kind, self.cell, self._known = [], [], {}, {}, set()
+        self.rows, self.cols, self.kind, self.cells = [], [], {}, {}
 
     def add_row(self, key):
-        if key not in self._known:
-            self._known.add(key)
+        if key not in self.cells:
+            self.cells[key] = {}
             self.rows.append(key)
+
+    def add_rows(self, contigs, keys):
+        """the reference's first pass: every contig gets the same rows (values come later)"""
+        cells, rows = self.cells, self.rows
+        for c in contigs:
+            for k in keys:
+                key = (c, k)
+                if key not in cells:
+                    cells[key] = {}
+                    rows.append(key)
 
     def set(self, row, col, value):
         self.add_row(row)
         text = isinstance(value, str)
-        if col not in self.cols:
+        if col not in self.kind:
             self.cols.append(col)
             self.kind[col] = "object" if text else "float"
         elif text:
             self.kind[col] = "object"
-        self.cell[(row, col)] = float(value) if self.kind[col] == "float" else value
+        self.cells[row][col] = float(value) if self.kind[col] == "float" else value
 
     def row_sum(self, row):
-        vals = [self.cell[(row, c)] for c in self.cols if (row, c) in self.cell]
+        vals = self.cells.get(row, {})
+        vals = [vals[c] for c in self.cols if c in vals]
         return sum(vals) if vals else 0
 
     def write(self, path):
+        cols = self.cols
+        empty = "\t".join(["-"] * len(cols))
+        out = ["\t\t" + "\t".join(cols)]
+        for row in self.rows:
+            cells = self.cells[row]
+            if cells:
+                out.append(f"{row[0]}\t{row[1]}\t" + "\t".join([str(cells[c]) if c in cells else "-" for c in cols]))
+            else:
+                out.append(f"{row[0]}\t{row[1]}\t{empty}")
         with open(path, "w") as fh:
-            fh.write("\t\t" + "\t".join(self.cols) + "\n")
-            for row in self.rows:
-                fh.write("\t".join([str(row[0]), str(row[1])] + [str(self.cell.get((row, c), "-")) for c in self.cols]) + "\n")
+            fh.write("\n".join(out) + "\n")
 
 
 def _write_fasta(records, path):
