@@ -131,7 +131,7 @@ class DeviceGenes:
 
     def __init__(self, ptr: int, n: int):
         self.ptr, self.n = ptr, n
-        self.__cuda_array_interface__ = {"shape": (n * 32,), "typestr": "|u1", "data": (ptr, True), "version": 2, "strides": None}
+        self.__cuda_array_interface__ = {"shape": (n * 32,), "typestr": "|u1", "data": (ptr, False), "version": 2, "strides": None}
 
     def __len__(self):
         return self.n

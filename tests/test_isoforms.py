@@ -225,6 +225,34 @@ def test_switch_run_end_to_end_on_the_gpu(case, via_cli, tmp_path):
     assert open(f"{out}{case}_stats.tab").read() == fx.xz_text(f"iso_{case}_stats.tab.xz")
 
 
+@pytest.mark.gpu
+def test_isoforms_run_on_cached_predictions(tmp_path):
+    """`cli -i g.fa` followed by `cli -i g.fa --isoforms` with the same -p directory: the second run finds all four
+    mgm_<code>_<species>.gff files cached (bin/data.py:39-51 skips gmhmmp2 then), decodes again for the window labels
+    instead of failing, leaves the cached files alone and writes the reference's files"""
+    from mgcod_b200 import cli
+    tmp = str(tmp_path)
+    case = "mixed"
+    ref = json.loads(fx.xz_text(f"iso_{case}.json.xz"))
+    a = ref["args"]
+    mdir = os.path.dirname(fx.trained_models(tmp)[11])
+    fa = os.path.join(tmp, f"{case}.fasta")
+    open(fa, "w").write(_case_text(case))
+    pred, out1, out2 = os.path.join(tmp, "pred") + "/", os.path.join(tmp, "out1") + "/", os.path.join(tmp, "out2") + "/"
+    assert cli.main(["-i", fa, "-p", pred, "-o", out1, "--model_dir", mdir]) == 0
+    cached = {c: os.stat(f"{pred}mgm_{c}_{case}.gff").st_mtime_ns for c in fx.CODES}
+    assert cli.main(["-i", fa, "-p", pred, "-o", out2, "--isoforms", "-w", str(a["window"]), "-st", str(a["stride"]), "-n", str(a["n"]),
+                     "-g", str(a["genes"]), "-t", str(a["tol"]), "--model_dir", mdir]) == 0
+    assert cached == {c: os.stat(f"{pred}mgm_{c}_{case}.gff").st_mtime_ns for c in fx.CODES}
+    assert open(f"{out2}{case}.tab").read() == fx.xz_text(f"iso_{case}.tab.xz")
+    assert open(f"{out2}{case}_stats.tab").read() == fx.xz_text(f"iso_{case}_stats.tab.xz")
+    # default mode on the cache (no decode at all): the frames come from the files, as in the reference
+    out3 = os.path.join(tmp, "out3") + "/"
+    assert cli.main(["-i", fa, "-p", pred, "-o", out3, "--model_dir", mdir]) == 0
+    assert open(f"{out3}{case}.tab").read() == open(f"{out1}{case}.tab").read()
+    assert fx.strip_dates(open(f"{out3}{case}.gff").read()) == fx.strip_dates(open(f"{out1}{case}.gff").read())
+
+
 def test_comparison_against_reference_on_random_gene_sets():
     """300 perturbed pairs of gene sets (tests/golden/make_golden_isoform_cases.py): both tables as the reference builds them"""
     import sys

@@ -112,3 +112,33 @@ def test_two_rank_table_gather_equals_single_rank(model_dir):
             p.join(180)
             assert p.exitcode == 0
         assert ret["ok"] and ret["n"] > 100
+
+
+@pytest.mark.gpu
+def test_device_gather_on_one_gpu(model_dir):
+    """the NCCL path of the multi-GPU gather with a process group of one rank: the engine's device gene tables wrapped as
+    torch tensors without a copy, counts exchanged, rows gathered — equal to the host-side result"""
+    import torch
+    import torch.distributed as dist
+    from mgcod_b200.engine import Engine, synth_metagenome
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(0)
+    dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    try:
+        buf, offs, _ = synth_metagenome(8, 400000, threads=2)
+        eng = Engine([f"{model_dir}/mgm_{c}.mod" for c in (11, 4, 15, 101)])
+        cut = shard.partition_ranges(np.diff(offs), 3)         # pretend to be the middle rank of three
+        mine = offs[int(cut[1]):int(cut[2]) + 1]
+        res = eng.decode_buffer(buf, mine)
+        merged = shard.gather_genes_device(eng, int(cut[1]))
+        for m in range(4):
+            want = res.genes(m)
+            want["contig"] += int(cut[1])
+            assert len(want) > 20 and merged[m].tobytes() == want.tobytes()
+        eng.close()
+    finally:
+        dist.destroy_process_group()
