@@ -79,23 +79,39 @@ def gather_genes_device(engine, first_contig: int, group=None, dst: int = 0):
                               torch.device("cuda", torch.cuda.current_device()), group, dst)
 
 
+_PINNED = {}      # device index -> page-locked receive buffer of rank dst (grown on demand, kept between calls)
+
+
+def _pinned_bytes(device, n: int):
+    import torch
+    key = str(device)
+    buf = _PINNED.get(key)
+    if buf is None or buf.numel() < n:
+        buf = torch.empty(int(n * 1.25) + 4096, dtype=torch.uint8, pin_memory=device.type == "cuda")
+        _PINNED[key] = buf
+    return buf
+
+
 def gather_gene_tables(tables, first_contig: int, device, group=None, dst: int = 0):
     """The collective under :func:`gather_genes_device`.  ``tables``: one gene table per model, each either a
     :class:`mgcod_b200.engine.DeviceGenes` (device memory, NCCL) or a GENE_DTYPE numpy array (host memory; the gloo tests).
 
-    Layout on the wire: per rank one uint8 tensor holding model 0's rows, then model 1's, ...; ranks exchange their
-    per-model counts first (one small all_gather) and pad to the largest total, because a gather takes equal sizes."""
+    On the wire: per rank one uint8 tensor holding model 0's rows, then model 1's, ... with the rank's first contig already
+    added to the rows' contig field (a strided int32 add on the send buffer); ranks exchange their per-model counts first
+    (one small all_gather) and pad to the largest total, because a gather takes equal sizes.  Rank ``dst`` then strings the
+    ranks' pieces of each model together ON THE DEVICE and brings every model's table to the host with one copy into a
+    page-locked buffer; the returned arrays are views of it (valid until the next call)."""
     import torch
     import torch.distributed as dist
     from .engine import GENE_DTYPE
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     M = len(tables)
-    counts = torch.tensor([len(t) for t in tables] + [int(first_contig)], dtype=torch.int64, device=device)
+    counts = torch.tensor([len(t) for t in tables], dtype=torch.int64, device=device)
     all_counts = [torch.zeros_like(counts) for _ in range(world)]
     dist.all_gather(all_counts, counts, group=group)
-    all_counts = torch.stack(all_counts).cpu().numpy()            # [world, M + 1]
-    width = int(all_counts[:, :M].sum(axis=1).max()) * 32
-    send = torch.zeros(max(width, 32), dtype=torch.uint8, device=device)
+    all_counts = torch.stack(all_counts).cpu().numpy()            # [world, M]
+    width = int(all_counts.sum(axis=1).max()) * 32
+    send = torch.empty(max(width, 32), dtype=torch.uint8, device=device)
     at = 0
     for t in tables:
         if len(t):
@@ -103,18 +119,25 @@ def gather_gene_tables(tables, first_contig: int, device, group=None, dst: int =
                    else torch.as_tensor(t, device=device))
             send[at:at + len(t) * 32].copy_(src)
         at += len(t) * 32
+    if at and first_contig:
+        send[:at].view(torch.int32).view(-1, 8)[:, 0] += int(first_contig)    # contig = first field of the 32-byte row
     recv = [torch.empty_like(send) for _ in range(world)] if rank == dst else None
     dist.gather(send, recv, dst=dst, group=group)
     if rank != dst:
         return None
-    host = torch.stack(recv).cpu().numpy()                         # one copy to the host for all ranks
-    merged = []
+    total = int(all_counts.sum()) * 32
+    host = _pinned_bytes(device, max(total, 32))
+    merged, at = [], 0
     for m in range(M):
-        parts = []
+        pieces = []
         for r in range(world):
             a = int(all_counts[r, :m].sum()) * 32
-            g = host[r, a:a + int(all_counts[r, m]) * 32].view(GENE_DTYPE).copy()
-            g["contig"] += int(all_counts[r, M])
-            parts.append(g)
-        merged.append(np.concatenate(parts))
+            pieces.append(recv[r][a:a + int(all_counts[r, m]) * 32])
+        n = int(all_counts[:, m].sum()) * 32
+        if n:
+            host[at:at + n].copy_(torch.cat(pieces), non_blocking=True)
+        merged.append(host[at:at + n].numpy().view(GENE_DTYPE))
+        at += n
+    if device.type == "cuda":
+        torch.cuda.current_stream().synchronize()
     return merged
