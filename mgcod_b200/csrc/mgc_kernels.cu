@@ -2094,28 +2094,40 @@ __global__ void __launch_bounds__(128, 8) k_chain(const ChainBufs *bufs_m, int *
                 }
             }
         }
-        // traceback (reverse-strand genes follow their ORF's shared pointer)
+        // the traceback is a chain of dependent loads: it runs in k_chain_trace, a thread per piece, instead of on lane 0
+        // of this warp with 31 lanes idle.  gene_count[slot] carries the end of the best chain until then.
         if (lane == 0) {
-            int ng = 0;
-            double tot = 0.0;
-            if (S.head > 0) {
-                tot = S.pm_val;
-                int g = S.pm_arg;
-                const int limit = (int)(ce - cs);
-                int k = limit;
-                while (g >= 0 && k > 0) {
-                    B.chain[cs + (--k)] = g;
-                    const Cand cd = B.sorted[g];
-                    g = cd.strand < 0 ? B.gptr[cd.orf] : B.prev[g];
-                    ng++;
-                }
-                for (int q = 0; q < ng; q++) B.chain[cs + q] = B.chain[cs + k + q];
-            }
-            B.gene_count[slot] = ng;
-            B.piece_total[slot] = tot;
+            B.gene_count[slot] = S.head > 0 ? S.pm_arg : -1;
+            B.piece_total[slot] = S.head > 0 ? S.pm_val : 0.0;
         }
         __syncwarp();
     }
+}
+
+// traceback of every piece (reverse-strand genes follow their ORF's shared pointer): thread per piece, the candidate and
+// back-pointer loads of half a million pieces in flight at once
+__global__ void __launch_bounds__(128) k_chain_trace(const ChainBufs *bufs_m, const int *work_counters) {
+    const int mi = blockIdx.y;
+    const ChainBufs B = bufs_m[mi];
+    const int n_work = work_counters[2 * mi];
+    const int item = blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= n_work) return;
+    const int slot = B.work[item];
+    const int64_t b_first = B.piece_b0[slot], b_last = B.piece_b1[slot];
+    const uint32_t cs = b_first ? B.bend[b_first - 1] : 0u;
+    const uint32_t ce = B.bend[b_last];
+    int g = B.gene_count[slot];
+    int ng = 0;
+    const int limit = (int)(ce - cs);
+    int k = limit;
+    while (g >= 0 && k > 0) {
+        B.chain[cs + (--k)] = g;
+        const Cand cd = B.sorted[g];
+        g = cd.strand < 0 ? B.gptr[cd.orf] : B.prev[g];
+        ng++;
+    }
+    for (int q = 0; q < ng; q++) B.chain[cs + q] = B.chain[cs + k + q];
+    B.gene_count[slot] = ng;
 }
 
 // genes of all contigs, contiguous, ordered by (contig, left); per-model sum of round(logodd, 2) in cents
@@ -2537,7 +2549,8 @@ int launch_chain(const ChainBufs *bufs_m, const int64_t *cwoff, const int32_t *c
     k_chain_plan<<<dim3((unsigned)((n_slots + 127) / 128), n_models), 128, 0, st>>>(bufs_m, cwoff, clen, slotbase, slot_contig, n_slots,
                                                                                      work_counters);
     k_chain<<<dim3((unsigned)n_sm * 16, n_models), 128, 0, st>>>(bufs_m, work_counters);
-    return 3;
+    k_chain_trace<<<dim3((unsigned)((n_slots + 127) / 128), n_models), 128, 0, st>>>(bufs_m, work_counters);
+    return 4;
 }
 
 int launch_gather(const ChainBufs *bufs_m, mgc_gene *const *genes_m, const int32_t *slot_contig, int32_t n_slots, const int32_t *slotbase,
