@@ -508,7 +508,7 @@ def main():
             out = {
                 "metric": METRIC, "value": all_units * args.steps / dt_res, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1e3 * dt_res / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": dict(config, contigs_per_gpu=int(len(truth))),
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "contigs_per_gpu": int(len(truth)),
                 "e2e": {"value": all_units * args.steps / dt_e2e, "unit": UNIT, "h2d_bytes_per_step": int(total_bp + 8 * (len(offs))),
                         "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": 1e3 * dt_e2e / args.steps,
                         "api": "Engine.decode_stream (H2D of batch i+1 overlaps the decode of batch i)",
@@ -649,6 +649,7 @@ def file_legs(engine, buf, offs, truth, model_paths, workdir, local, torch):
             P()
             t5 = time.perf_counter()
             Results(P, tag, pred_dir, path, cli_out, datetime.datetime.now(), False, False, False, False, workdir)()
+            P.close()                      # as mgcod_b200.cli does: buffers back to their pools
             t6 = time.perf_counter()
             tab = open(os.path.join(cli_out, f"{tag}.tab")).read().split("\n")
             windows = float(np.sum(np.ceil(lens2 / np.where(lens2 > 100000, 5000, 2500))))

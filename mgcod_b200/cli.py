@@ -86,6 +86,7 @@ def main(argv=None) -> int:
     pipeline()
     results = Results(pipeline, species, pred, a.path_to_genome, out, date, a.delete, a.amino_acids, a.nucleotides, a.verbose, a.cwd)
     results()
+    pipeline.close()
     if a.verbose:
         print("----------------------------Done----------------------------")
     return 0

@@ -139,6 +139,7 @@ class Record:
 
     def __init__(self, rid: str, description: str, seq):
         self.id, self.description, self._seq = rid, description, seq
+        self._len = len(seq)
 
     @property
     def seq(self) -> str:
@@ -147,7 +148,7 @@ class Record:
         return self._seq
 
     def __len__(self):
-        return len(self._seq)
+        return self._len
 
 
 class Fasta:
@@ -276,6 +277,18 @@ class Data:
             if getattr(self, "_writer", None) is not None:
                 self._writer.shutdown(wait=True)
                 self._writer = None
+
+    def close(self):
+        """releases the letter buffer (back to the reader's page-locked pool) and the decode result; the records' sequences
+        are detached first (materialised as str only where somebody already asked for them)"""
+        self.finish_writes()
+        for r in getattr(self, "_file_order", None) or []:
+            if not isinstance(r._seq, str):
+                r._seq = ""
+        self.result = None
+        f = getattr(self, "_fasta", None)
+        if f is not None:
+            f.close()
 
     def _decode(self):
         """all contigs of the file under the four parameter files on the GPU → engine.Result"""

@@ -445,10 +445,13 @@ def compare_sets_of_predicted_genes(P):
         if P.verbose:
             print("\n".join(messages))
 
+    ids = [rec.id for rec in P.sequence]      # the closure below must not hold P: P.coords -> closure -> P would be a cycle, and the
+    #                                           FASTA buffer and gene tables of a finished run would wait for the cyclic collector
+
     def build_coords():       # one block per contig, in contig order
         blocks = dict(compared)
         for n, lab in single:
-            f = contig_frame(lab, P.sequence[n].id)
+            f = contig_frame(lab, ids[n])
             if len(f):
                 f = f.copy()
                 f["updated_gene_label"] = 1

@@ -80,6 +80,13 @@ class Pipeline:
         self.timings = dict(zip(("read", "decode", "analyse", "wait_for_gff_writers"), np.diff(t).round(4).tolist()))
         self.timings.update(getattr(data, "timings", {}))
 
+    def close(self):
+        """Hands the run's large buffers back (the page-locked letter buffer of the FASTA reader, the gene tables): called by
+        the command line when the result files are written; a later genome of the same process reuses them."""
+        data = getattr(self, "data", None)
+        if data is not None:
+            data.close()
+
     def _analyse(self):
         data = self.data
         # label -> frame of that model's genes (reference: four DataFrames parsed back from the GFF files, plus the `contig`
