@@ -1072,6 +1072,8 @@ void mgc_engine_destroy(mgc_engine *e) {
                       &e->t_unit_off, &e->t_sums, &e->ascii_next, &e->slotbase, &e->slot_contig, &e->nm, &e->ncount, &e->codon, &e->cflags, &e->plen, &e->gaps, &e->gap_count, &e->unit_totals, &e->next_unit, &e->win_stride, &e->win_off, &e->win_labels, &e->win_cents, &e->win_merged, &e->win_run, &e->win_status, &e->win_hist})
         b->release();
     for (auto &ev : e->ev) cudaEventDestroy(ev);
+    e->pool->release(e->win_host);   // back to the pool, which frees its blocks with the last result / engine holding it
+    e->win_host = PinnedPool::Block();
     if (e->last_ready) e->last_ready->wait();
     e->last_ready.reset();
     if (e->d2h_stream) { cudaStreamSynchronize(e->d2h_stream); cudaStreamDestroy(e->d2h_stream); }

@@ -58,7 +58,8 @@ class GeneFrames:
         self.ids = np.asarray(list(ids), dtype=object)
         self.codes = tuple(codes)
         n = len(self.ids)
-        self.first = [np.searchsorted(g["contig"], np.arange(n + 1)) for g in self.genes]   # row range of every contig
+        # row range of every contig (the contig field is a strided view of the 32-byte rows: made contiguous for the search)
+        self.first = [np.searchsorted(np.ascontiguousarray(g["contig"]), np.arange(n + 1)) for g in self.genes]
         self._index_of = None
         self._full = {}
 

@@ -3,11 +3,11 @@
 bin/data.py:40-41) against the CPU oracle on fresh synthetic metagenomes under the four parametric
 82-section parameter files.  Build container only (the binary's checkout is absent on the GPU box).
 
-    python tests/tools/fuzz_vs_binary.py [--seeds 987654 31337 4242] [--bp 4000000] [--jobs 8] [--engine]
+    python tests/tools/fuzz_vs_binary.py [--seeds 987654 31337 4242] [--bp 4000000] [--jobs 8]
 
 Compares the gene lines of the GFF text (contig, left, right, %.2f score, strand, attributes incl. gene_type and gc)
-and prints every difference with the GC fraction of the gene, so that tie effects are visible.
---engine additionally decodes with the CUDA engine (needs a GPU) and compares it the same way.
+and prints every difference with the GC fraction of the gene, so that tie effects are visible.  The same comparison for the
+CUDA engine runs on the GPU box against the staged binary: tests/test_live_binary.py.
 """
 from __future__ import annotations
 
