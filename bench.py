@@ -198,8 +198,37 @@ def cpu_reference_run(buf: np.ndarray, offs: np.ndarray, model_paths: list[str],
         kind = "port"
         used = nshard
     dt = time.perf_counter() - t0
-    return {"value": bp * len(model_paths) / dt, "unit": UNIT, "cores": used, "kind": kind,
-            "sample": f"first {n} contigs = {bp} bp x {len(model_paths)} models of the step's workload, {dt:.2f} s wall"}
+    out = {"value": bp * len(model_paths) / dt, "unit": UNIT, "cores": used, "kind": kind,
+           "sample": f"first {n} contigs = {bp} bp x {len(model_paths)} models of the step's workload, {dt:.2f} s wall"}
+    if binary:
+        out["_gff"] = [[os.path.join(workdir, f"out_{si}_{mi}.gff") for si in range(nshard)] for mi in range(len(model_paths))]
+        out["_contigs"] = n
+    return out
+
+
+def parity_against_baseline(engine, buf, offs, base: dict) -> dict:
+    """The gene lines the reference binary has just printed for the CPU-baseline sample against the engine's genes for the same
+    contigs: left, right, strand, %.2f score and the attributes behind the gene id (gene_type, partial, gc, length)."""
+    import pandas as pd
+    from mgcod_b200.data import GFF_COLUMNS, GeneFrames
+    n = base["_contigs"]
+    res = engine.decode_buffer(buf, offs[:n + 1])
+    frames = GeneFrames([res.genes(m) for m in range(engine.n_models)], [f"c{i}" for i in range(n)])
+    genes = differing = 0
+    for mi, files in enumerate(base["_gff"]):
+        ref = pd.concat([pd.read_csv(f, sep="\t", header=None, comment="#", names=GFF_COLUMNS) for f in files], ignore_index=True)
+        mine = frames[mi]
+        genes += len(ref)
+        if len(ref) != len(mine):
+            differing += abs(len(ref) - len(mine))
+            continue
+        same = ((ref["sequence"].astype(str).values == mine["sequence"].values) & (ref["start"].values == mine["start"].values)
+                & (ref["end"].values == mine["end"].values) & (ref["strand"].values == mine["strand"].values)
+                & (ref["logodd"].values == mine["logodd"].values)
+                & (ref["attributes"].str.split(";", n=1).str[1].values == mine["attributes"].str.split(";", n=1).str[1].values))
+        differing += int((~same).sum())
+    return {"against": "the gene lines oracle/_ref/gmhmmp2 printed in the cpu_baseline leg of this run", "contigs": n, "genes": genes,
+            "differing": differing}
 
 
 def cpu_reference_b1(buf: np.ndarray, offs: np.ndarray, model_paths: list[str], n_contigs: int, workdir: str, cores: int) -> dict | None:
@@ -291,7 +320,7 @@ def main():
                     vals.append(r)
             v = float(np.mean([r["value"] for r in vals]))
             bp = int(offs[-1])
-            last = vals[-1]
+            last = {k: x for k, x in vals[-1].items() if not k.startswith("_")}
             last["value"] = v
             print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                               "warmup": args.warmup, "ms_per_step": 1e3 * bp * 4 / v, "higher_is_better": True, "scaling": "weak",
@@ -550,7 +579,13 @@ def main():
             if small:
                 out["small_input_latency"] = small
             if world == 1 and not args.no_cpu_baseline:
-                out["cpu_baseline"] = cpu_reference_run(buf, offs, model_paths, args.cpu_sample_bp, workdir, cores)
+                base = cpu_reference_run(buf, offs, model_paths, args.cpu_sample_bp, workdir, cores)
+                if "_gff" in base:       # the binary's output is at hand: compare it with the engine's genes, line by line
+                    try:
+                        out["parity_sample"] = parity_against_baseline(engine, buf, offs, base)
+                    except Exception as ex:
+                        out["parity_sample"] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
+                out["cpu_baseline"] = {k: v for k, v in base.items() if not k.startswith("_")}
                 if args.b1_contigs > 0:
                     b1 = cpu_reference_b1(buf, offs, model_paths, args.b1_contigs, workdir, cores)
                     if b1:
