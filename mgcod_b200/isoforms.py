@@ -31,6 +31,7 @@ import pandas as pd
 
 from . import labels as L
 from .data import GeneFrames, contig_rows, frame_columns, rows_by_contig
+from .percontig import PerContig
 
 
 def _rest(attributes: str) -> str:
@@ -403,28 +404,19 @@ def compare_sets_of_predicted_genes(P):
     if lmin is None:
         lmin = np.array([int(np.min(u)) if len(u) else -1 for u in P.updated_genome_labels], dtype=np.int64)
         lmax = np.array([int(np.max(u)) if len(u) else -1 for u in P.updated_genome_labels], dtype=np.int64)
-    gene_labels_to_gcode = {}
     compared: dict[int, pd.DataFrame] = {}
-    single: list[tuple[int, int]] = []          # (position in P.sequence, label) of contigs with one genetic code
+    explicit: dict = {}
     with_isoforms: list[dict] = []
     code_of = {int(k): v for k, v in P.label_to_gcode.items()}
-    one_code = (lmin == lmax).tolist()
-    lmin_l = lmin.tolist()
     messages = []
-    for n, rec in enumerate(P.sequence):
-        if one_code[n]:
-            # Nothing goes to the isoform table (the reference's append to it is commented out, bin/pipeline.py:577), so the
-            # final GFF of a mixed input lists only the contigs with a switch.  One deliberate difference in the plain
-            # table, which nothing downstream reads: the reference appends the model's genes of EVERY contig here
-            # (no contig filter, :574-576) — contigs x genes rows for a metagenome; this keeps the contig's own genes.
-            single.append((n, lmin_l[n]))
-            gene_labels_to_gcode[rec.id] = {1: code_of[lmin_l[n]]}
-            continue
+    seq_ids = getattr(P, "_ids", None) or [rec.id for rec in P.sequence]
+    for n in np.flatnonzero(lmin != lmax).tolist():          # contigs whose smoothed labels name two genetic codes
+        rec = P.sequence[n]
         labs = np.unique(P.updated_genome_labels[n])
         label_1, label_2 = int(labs[0]), int(labs[1])
         code_1, code_2 = P.label_to_gcode[label_1], P.label_to_gcode[label_2]
         messages.append(f"Contig {rec.id} in {P.species} carries genetic code {code_1} and {code_2}")
-        gene_labels_to_gcode[rec.id] = {1: str(code_1), 2: str(code_2), 3: f"{code_1}_{code_2}"}
+        explicit[rec.id] = {1: str(code_1), 2: str(code_2), 3: f"{code_1}_{code_2}"}
         S1 = _GeneSet(contig_frame(label_1, rec.id))
         S2 = _GeneSet(contig_frame(label_2, rec.id))
         cur, iso = compare_contig(S1, S2, code_1, code_2, P.tolerance, rec.seq)
@@ -440,6 +432,12 @@ def compare_sets_of_predicted_genes(P):
         compared[n] = frame
         with_isoforms.extend(iso)
         messages.append(f"Identified {sum(1 for r in iso if r['logodd'] == '.')} possible isoforms in {rec.id} in {P.species}")
+    # Contigs with one genetic code: nothing goes to the isoform table (the reference's append to it is commented out,
+    # bin/pipeline.py:577), so the final GFF of a mixed input lists only the contigs with a switch.  One deliberate difference
+    # in the plain table, which nothing downstream reads: the reference appends the model's genes of EVERY contig there
+    # (no contig filter, :574-576) — contigs x genes rows for a metagenome; this keeps the contig's own genes.
+    lmin_l = lmin.tolist()
+    gene_labels_to_gcode = PerContig(seq_ids, explicit, lambda n: {1: code_of.get(lmin_l[n], code_of[0])})
     if messages:
         logging.info("\n".join(messages))
         if P.verbose:
@@ -450,7 +448,8 @@ def compare_sets_of_predicted_genes(P):
 
     def build_coords():       # one block per contig, in contig order
         blocks = dict(compared)
-        for n, lab in single:
+        for n in np.flatnonzero((lmin == lmax) & (lmin >= 0)).tolist():
+            lab = lmin_l[n]
             f = contig_frame(lab, ids[n])
             if len(f):
                 f = f.copy()

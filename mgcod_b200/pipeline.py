@@ -25,6 +25,7 @@ from . import isoforms as iso_compare
 from . import labels as L
 from .data import Data, GeneFrames, rows_by_contig
 from .engine import MGCOD_CODES
+from .percontig import PerContig, Ragged
 
 
 class Pipeline:
@@ -110,18 +111,33 @@ class Pipeline:
             # window sums, labels and their smoothing in one device call (host restatement: labels.find_best_sequence_of_labels)
             self.genome_label, self.logodd_scores, updated = self.identify_most_common_codes(smooth=True)
         self.updated_genome_labels = updated
-        flat = np.concatenate(updated) if updated else np.zeros(0, dtype=np.int64)
+        flat = updated.concatenated() if isinstance(updated, Ragged) else (np.concatenate(updated) if updated else np.zeros(0, dtype=np.int64))
         # per contig: smallest / largest smoothed label (equal = one genetic code on that contig)
-        sizes = np.array([u.shape[0] for u in updated], dtype=np.int64)
-        starts = np.concatenate([[0], np.cumsum(sizes)[:-1]]) if len(sizes) else np.zeros(0, dtype=np.int64)
+        if isinstance(updated, Ragged):
+            lo, sizes = updated.lo, updated.hi - updated.lo
+            src = updated.flat
+        else:
+            sizes = np.array([u.shape[0] for u in updated], dtype=np.int64)
+            lo = np.concatenate([[0], np.cumsum(sizes)[:-1]]) if len(sizes) else np.zeros(0, dtype=np.int64)
+            src = flat
         nonempty = sizes > 0
         self._label_min = np.full(len(sizes), -1, dtype=np.int64)
         self._label_max = np.full(len(sizes), -1, dtype=np.int64)
         if nonempty.any():
-            self._label_min[nonempty] = np.minimum.reduceat(flat, starts[nonempty])
-            self._label_max[nonempty] = np.maximum.reduceat(flat, starts[nonempty])
-        if np.unique(flat).shape[0] == 1:
-            code = self.label_to_gcode[int(updated[0][0])]
+            # reduceat wants ascending starts: the contigs in the order of their slices, results scattered back
+            order = np.argsort(lo[nonempty], kind="stable")
+            idx = np.flatnonzero(nonempty)[order]
+            starts = lo[idx]
+            ends = starts + sizes[idx]
+            if bool((ends[:-1] == starts[1:]).all()) and ends[-1] == src.shape[0] and starts[0] == 0:
+                self._label_min[idx] = np.minimum.reduceat(src, starts)
+                self._label_max[idx] = np.maximum.reduceat(src, starts)
+            else:       # slices with holes between them (does not happen for the engine's layouts)
+                self._label_min[idx] = [int(src[a:b].min()) for a, b in zip(starts, ends)]
+                self._label_max[idx] = [int(src[a:b].max()) for a, b in zip(starts, ends)]
+        present = self._label_min[nonempty]
+        if present.size and int(present.min()) == int(self._label_max[nonempty].max()):
+            code = self.label_to_gcode[int(present[0])]
             logging.info(f"{self.species} is genetic code {code}")
             if self.verbose:
                 print(f"{self.species} is genetic code {code}")
@@ -129,16 +145,17 @@ class Pipeline:
             self.coords_w_isoforms = self.label_to_gene_coords[self.gcode_to_label[code]]
             self.predicted_switch_regions = {seq.id: None for seq in self.sequence}
             return
+        self._ids = [seq.id for seq in self.sequence]
+        self._lens = np.fromiter((len(seq) for seq in self.sequence), dtype=np.int64, count=len(self.sequence))
         self.coords, self.gene_label_to_gcode, self.coords_w_isoforms = self.compare_sets_of_predicted_genes()
         self.confident_1, self.confident_2, self.segment_labels = self.segment_genome_based_on_window_labels()
-        self.predicted_switch_regions = {}
-        for k, seq in enumerate(self.sequence):
-            if self._label_min[k] == self._label_max[k]:
-                self.predicted_switch_regions[seq.id] = (self.updated_genome_labels[k][:1].copy(), [])
-                continue
-            segs = sorted(self.confident_1[seq.id] + self.confident_2[seq.id])
-            self.predicted_switch_regions[seq.id] = (np.unique(self.updated_genome_labels[k]),
-                                                     [(segs[i][1], segs[i + 1][0]) for i in range(len(segs) - 1)])
+        explicit = {}
+        for k in np.flatnonzero(self._label_min != self._label_max).tolist():
+            cid = self._ids[k]
+            segs = sorted(self.confident_1[cid] + self.confident_2[cid])
+            explicit[cid] = (np.unique(self.updated_genome_labels[k]), [(segs[i][1], segs[i + 1][0]) for i in range(len(segs) - 1)])
+        upd = self.updated_genome_labels
+        self.predicted_switch_regions = PerContig(self._ids, explicit, lambda k: (upd[k][:1].copy(), []))
 
     # ---- bin/pipeline.py:139-155 -------------------------------------------------------------------------
     def classify_complete_sequence(self):
@@ -183,9 +200,9 @@ class Pipeline:
         labs = labs.astype(np.int64)
         scores = cents.astype(np.float64) / 100.0
         order = self.data._sorted_to_file                    # reference order: sorted by contig id
-        lo, hi = offs[:-1][order].tolist(), offs[1:][order].tolist()
-        out_l = [labs[a:b] for a, b in zip(lo, hi)]
-        out_s = [scores[a:b] for a, b in zip(lo, hi)]
+        lo, hi = offs[:-1][order], offs[1:][order]
+        out_l = Ragged(labs, lo, hi)                         # list-like: one array per contig, made when asked for
+        out_s = Ragged(scores, lo, hi)
         lens_sorted = lens_file[order]
         short = np.flatnonzero(lens_sorted <= 5000)
         not_classified, below = [], []
@@ -204,8 +221,7 @@ class Pipeline:
             warnings.warn(f"Contig(s) {', '.join(not_classified)} in {self.species} are shorter than 5000bp. Genetic code has been "
                           f"set to 11. Use --short_contigs to predict genetic code of these contigs")
         if smooth:
-            merged = merged.astype(np.int64)
-            return out_l, out_s, [merged[a:b] for a, b in zip(lo, hi)]
+            return out_l, out_s, Ragged(merged.astype(np.int64), lo, hi)
         return out_l, out_s
 
     # ---- bin/pipeline.py:387-492 -------------------------------------------------------------------------
@@ -213,28 +229,39 @@ class Pipeline:
         logging.info(f"Segmenting genome of {self.species}")
         if self.verbose:
             print(f"Segmenting genome of {self.species}")
-        conf_1, conf_2, seg_labels = {}, {}, {}
         frames = self.label_to_gene_coords
-        lmin = getattr(self, "_label_min", None)
-        messages = []
-        for k, seq in enumerate(self.sequence):
+        ids = getattr(self, "_ids", None) or [seq.id for seq in self.sequence]
+        lens = getattr(self, "_lens", None)
+        if lens is None:
+            lens = np.fromiter((len(seq) for seq in self.sequence), dtype=np.int64, count=len(self.sequence))
+        lmin, lmax = getattr(self, "_label_min", None), getattr(self, "_label_max", None)
+        if lmin is None:
+            lmin = np.array([int(np.min(u)) if len(u) else -1 for u in self.updated_genome_labels], dtype=np.int64)
+            lmax = np.array([int(np.max(u)) if len(u) else -1 for u in self.updated_genome_labels], dtype=np.int64)
+        code_of = {int(k): v for k, v in self.label_to_gcode.items()}
+        c1, c2, sl = {}, {}, {}
+        switch_msgs = {}
+        for k in np.flatnonzero(lmin != lmax).tolist():        # genes matter only where the label changes
             labels_k = self.updated_genome_labels[k]
-            single = (lmin[k] == self._label_max[k]) if lmin is not None else np.unique(labels_k).shape[0] == 1
-            if single and labels_k.shape[0]:
-                # one genetic code on the whole contig: one block, no gene coordinates needed
-                code = self.label_to_gcode[int(labels_k[0])]
-                conf_1[seq.id], conf_2[seq.id], seg_labels[seq.id] = [(1, int(len(seq)))], [], [code]
-                messages.append(f"Contig {seq.id} in {self.species} has genetic code {code} from 1 to {len(seq)}")
-                continue
-            genes = {}
-            for lab in np.unique(labels_k).tolist():           # genes matter only where the label changes
-                genes[int(lab)] = _gene_columns(frames, int(lab), seq.id)
-            c1, c2, codes = L.segment_contig(labels_k, len(seq), L.resolve_stride(self.stride, len(seq)),
-                                             self.window_size, genes, self.label_to_gcode)
-            conf_1[seq.id], conf_2[seq.id], seg_labels[seq.id] = c1, c2, codes
-            for (a, b), code in zip(sorted(c1 + c2), codes):
-                messages.append(f"Contig {seq.id} in {self.species} has genetic code {code} from {a} to {b}")
-        if messages:
+            genes = {int(lab): _gene_columns(frames, int(lab), ids[k]) for lab in np.unique(labels_k).tolist()}
+            a, b, codes = L.segment_contig(labels_k, int(lens[k]), L.resolve_stride(self.stride, int(lens[k])), self.window_size, genes,
+                                           self.label_to_gcode)
+            c1[ids[k]], c2[ids[k]], sl[ids[k]] = a, b, codes
+            switch_msgs[k] = [f"Contig {ids[k]} in {self.species} has genetic code {code} from {x} to {y}"
+                              for (x, y), code in zip(sorted(a + b), codes)]
+        # one genetic code on the whole contig: one block, no gene coordinates needed — made when somebody asks
+        lens_l, lmin_l = lens.tolist(), lmin.tolist()
+        conf_1 = PerContig(ids, c1, lambda k: [(1, lens_l[k])])
+        conf_2 = PerContig(ids, c2, lambda k: [])
+        seg_labels = PerContig(ids, sl, lambda k: [code_of.get(lmin_l[k], code_of[0])])
+        if logging.getLogger().isEnabledFor(logging.INFO) or self.verbose:
+            sp = self.species
+            messages = []
+            for k, cid in enumerate(ids):
+                if k in switch_msgs:
+                    messages.extend(switch_msgs[k])
+                else:
+                    messages.append(f"Contig {cid} in {sp} has genetic code {code_of.get(lmin_l[k], code_of[0])} from 1 to {lens_l[k]}")
             logging.info("\n".join(messages))        # one record: a metagenome has tens of thousands of these lines
             if self.verbose:
                 print("\n".join(messages))

@@ -201,21 +201,34 @@ class Results:
         # a switch somewhere: one column per segment.  The reference fills a DataFrame cell by cell; _Table keeps what
         # decides the bytes of its to_csv: row and column order of first use, and whether a column started numeric
         # (floats, "22.0") or with text (values kept as they are, "22").
-        table = _Table()
-        level_1 = [seq.id for seq in P.sequence]
+        level_1 = getattr(P, "_ids", None) or [seq.id for seq in P.sequence]
         coords_all = P.coords_w_isoforms
         index = rows_by_contig(coords_all)
-        for i, contig in enumerate(level_1):
+        lmin, lmax = getattr(P, "_label_min", None), getattr(P, "_label_max", None)
+        if lmin is not None:
+            single = lmin == lmax
+            code_of = {int(k): v for k, v in P.label_to_gcode.items()}
+            single_code = [code_of.get(x, code_of[0]) for x in lmin.tolist()]
+            lens = P._lens.tolist()
+        else:       # a Pipeline-like object with plain dicts (tests): the same rules, contig by contig
+            single = np.array([len(P.gene_label_to_gcode[c]) == 1 for c in level_1], dtype=bool)
+            single_code = [P.gene_label_to_gcode[c][1] for c in level_1]
+            lens = None
+        first_g = P.gene_label_to_gcode[level_1[0]]
+        table = _Table(level_1, ("Coordinates in bp", "Major genetic code", f"Nr genes with {first_g[1]}", "Nr identical genes",
+                                 "Nr isoforms", "Total gene count"))
+        prev = 0
+        for i in np.flatnonzero(~single).tolist() + [len(level_1)]:
+            if i > prev:
+                # a run of contigs with one genetic code: each sets a text cell first ("Coordinates in bp") and two numbers in
+                # the column "Sequence"; for the table's state that is: the column exists and holds text from here on
+                table.touch_text("Sequence")
+            prev = i + 1
+            if i == len(level_1):
+                break
+            contig = level_1[i]
             g = P.gene_label_to_gcode[contig]
-            if i == 0:
-                table.add_rows(level_1, ("Coordinates in bp", "Major genetic code", f"Nr genes with {g[1]}", "Nr identical genes",
-                                         "Nr isoforms", "Total gene count"))
             segments = sorted(P.confident_1[contig] + P.confident_2[contig])
-            if len(g) == 1:
-                table.set((contig, "Coordinates in bp"), "Sequence", str(segments[0]))
-                table.set((contig, "Major genetic code"), "Sequence", g[1])
-                table.set((contig, "Total gene count"), "Sequence", len(index.get(contig, ())))
-                continue
             coords = contig_rows(coords_all, index, contig)
             start = coords.start.values.astype(np.int64)
             is_parent = np.array([isinstance(v, str) and v == "." for v in coords.logodd.values], dtype=bool)
@@ -238,7 +251,14 @@ class Results:
                     table.set((contig, key), col, v)
             for key in keys:
                 table.set((contig, key), "Sequence", table.row_sum((contig, key)))
-        table.write(self.path_to_output)
+        # the contigs with one code, as the reference fills them (bin/results.py:112-118): coordinates of their one segment,
+        # the code, and the number of rows they have in the isoform table (none: only contigs with a switch go there)
+        if lens is not None:
+            coord_text = [f"(1, {n})" for n in lens]
+        else:
+            coord_text = [str(sorted(P.confident_1[c] + P.confident_2[c])[0]) if s_ else "" for c, s_ in zip(level_1, single.tolist())]
+        counts = [len(index.get(c, ())) for c in level_1] if len(index) else None
+        table.write(self.path_to_output, single.tolist(), coord_text, single_code, counts)
 
     # ---- bin/results.py:159-181 --------------------------------------------------------------------------------
     def write_stats(self):
@@ -317,29 +337,25 @@ class Results:
 
 
 class _Table:
-    """The cells of the reference's classification DataFrame in the order it creates them (bin/results.py:101-157).
-    Rows keep their cells in a dict of their own: a metagenome has six rows per contig, most of them empty."""
+    """The cells of the reference's classification DataFrame in the order it creates them (bin/results.py:101-157): every contig
+    gets the six standard rows first (implicit here), rows with other keys are appended at first use, columns appear at first
+    use, and a column is numeric (floats, "22.0") until a text value is stored in it (values kept as they are from then on)."""
 
-    def __init__(self):
-        self.rows, self.cols, self.kind, self.cells = [], [], {}, {}
+    def __init__(self, contigs, std_keys):
+        self.contigs, self.std_keys = contigs, tuple(std_keys)
+        self._std = set(self.std_keys)
+        self.extra, self.cols, self.kind, self.cells = [], [], {}, {}
 
-    def add_row(self, key):
-        if key not in self.cells:
-            self.cells[key] = {}
-            self.rows.append(key)
-
-    def add_rows(self, contigs, keys):
-        """the reference's first pass: every contig gets the same rows (values come later)"""
-        cells, rows = self.cells, self.rows
-        for c in contigs:
-            for k in keys:
-                key = (c, k)
-                if key not in cells:
-                    cells[key] = {}
-                    rows.append(key)
+    def touch_text(self, col):
+        if col not in self.kind:
+            self.cols.append(col)
+        self.kind[col] = "object"
 
     def set(self, row, col, value):
-        self.add_row(row)
+        if row not in self.cells:
+            self.cells[row] = {}
+            if row[1] not in self._std:
+                self.extra.append(row)
         text = isinstance(value, str)
         if col not in self.kind:
             self.cols.append(col)
@@ -353,16 +369,30 @@ class _Table:
         vals = [vals[c] for c in self.cols if c in vals]
         return sum(vals) if vals else 0
 
-    def write(self, path):
+    def write(self, path, single, coord_text, single_code, counts):
         cols = self.cols
-        empty = "\t".join(["-"] * len(cols))
+        dashes = "\t".join(["-"] * len(cols))
+        k0, k1, k2, k3, k4, k5 = self.std_keys
+        if "Sequence" in cols:
+            si = cols.index("Sequence")
+            left, right = "-\t" * si, "\t-" * (len(cols) - si - 1)
         out = ["\t\t" + "\t".join(cols)]
-        for row in self.rows:
-            cells = self.cells[row]
-            if cells:
-                out.append(f"{row[0]}\t{row[1]}\t" + "\t".join([str(cells[c]) if c in cells else "-" for c in cols]))
-            else:
-                out.append(f"{row[0]}\t{row[1]}\t{empty}")
+        cells = self.cells
+        for n, c in enumerate(self.contigs):
+            if single[n]:
+                cnt = counts[n] if counts is not None else 0
+                out.append(f"{c}\t{k0}\t{left}{coord_text[n]}{right}\n{c}\t{k1}\t{left}{single_code[n]}{right}\n"
+                           f"{c}\t{k2}\t{dashes}\n{c}\t{k3}\t{dashes}\n{c}\t{k4}\t{dashes}\n{c}\t{k5}\t{left}{cnt}{right}")
+                continue
+            for key in self.std_keys:
+                row = cells.get((c, key))
+                if row:
+                    out.append(f"{c}\t{key}\t" + "\t".join([str(row[x]) if x in row else "-" for x in cols]))
+                else:
+                    out.append(f"{c}\t{key}\t{dashes}")
+        for row_key in self.extra:
+            row = cells[row_key]
+            out.append(f"{row_key[0]}\t{row_key[1]}\t" + "\t".join([str(row[x]) if x in row else "-" for x in cols]))
         with open(path, "w") as fh:
             fh.write("\n".join(out) + "\n")
 

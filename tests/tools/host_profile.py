@@ -84,7 +84,7 @@ def main():
         P = run()
         pr.disable()
     dt = time.perf_counter() - t0
-    nwin = sum(len(l) for l in P.genome_label) if isinstance(P.genome_label, list) else 0
+    nwin = sum(len(l) for l in P.genome_label) if not isinstance(P.genome_label, (int, np.integer)) else 0
     print(f"host layer: {dt:.3f} s for {nwin} windows -> {nwin / dt:.0f} windows/s"
           f"{' (under cProfile)' if not a.no_profile else ''}")
     if not a.no_profile:
