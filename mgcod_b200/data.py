@@ -107,6 +107,27 @@ class GeneFrames:
             return self._full[int(lab)].iloc[a:b]
         return self.rows(lab, a, b)
 
+    def contig_columns(self, lab, contig_id) -> dict:
+        """the rows of one contig as a dict of columns (same names, order and values as the frame's) — for consumers that
+        turn the rows into Python objects anyway (the isoform comparison)"""
+        a, b = self.contig_range(lab, contig_id)
+        return self.columns(lab, a, b)
+
+    def columns(self, lab, a, b) -> dict:
+        g = self.genes[int(lab)][a:b]
+        code = self.codes[int(lab)]
+        n = len(g)
+        seq = self.ids[g["contig"]].tolist() if n else []
+        left, right = g["left"].astype(np.int64), g["right"].astype(np.int64)
+        length = right - left + 1
+        dom, pl, pr, gc = g["domain"].tolist(), g["partial_left"].tolist(), g["partial_right"].tolist(), g["gc"].tolist()
+        ln = length.tolist()
+        attrs = [f"gene_id {a + 1 + i}; gene_type {'archaea' if dom[i] else 'bacteria'}; "
+                 + (f"partial {pl[i]}{pr[i]}; " if (pl[i] or pr[i]) else "") + f"gc {gc[i]}; length {ln[i]};" for i in range(n)]
+        return {"sequence": seq, "source": [f"GeneMark.hmm2_{code}"] * n, "feature": ["CDS"] * n, "start": left, "end": right,
+                "logodd": cents_of(g["logodd"]) / 100.0, "strand": np.where(g["strand"] > 0, "+", "-").tolist(),
+                "phase": [0] * n, "attributes": attrs, "length": length, "contig": list(seq)}
+
     def rows(self, lab, a, b):
         g = self.genes[int(lab)][a:b]
         code = self.codes[int(lab)]

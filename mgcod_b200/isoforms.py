@@ -48,12 +48,21 @@ def gc_percent(seq: str) -> float:
 class _GeneSet:
     """One model's genes on one contig, in file order, indexed for the six lookups."""
 
-    def __init__(self, frame: pd.DataFrame):
-        self.rows = frame.to_dict("records")
-        self.start = frame.start.values.astype(np.int64)
-        self.end = frame.end.values.astype(np.int64)
-        self.strand = frame.strand.values.astype(object)
-        self.logodd = frame.logodd.values.astype(np.float64)
+    def __init__(self, frame):
+        if isinstance(frame, dict):      # columns as lists / arrays (GeneFrames.columns: no DataFrame on the way)
+            keys = list(frame)
+            cols = [frame[k].tolist() if isinstance(frame[k], np.ndarray) else list(frame[k]) for k in keys]
+            self.rows = [dict(zip(keys, vals)) for vals in zip(*cols)]
+            self.start = np.asarray(frame["start"], dtype=np.int64)
+            self.end = np.asarray(frame["end"], dtype=np.int64)
+            self.strand = np.asarray(frame["strand"], dtype=object)
+            self.logodd = np.asarray(frame["logodd"], dtype=np.float64)
+        else:
+            self.rows = frame.to_dict("records")
+            self.start = frame.start.values.astype(np.int64)
+            self.end = frame.end.values.astype(np.int64)
+            self.strand = frame.strand.values.astype(object)
+            self.logodd = frame.logodd.values.astype(np.float64)
         self.order = np.argsort(self.start, kind="stable")
         self.sorted_start = self.start[self.order]
         self.max_len = int((self.end - self.start).max()) if len(self.rows) else 0
@@ -400,6 +409,9 @@ def compare_sets_of_predicted_genes(P):
     def contig_frame(lab, contig_id):
         return frames.contig_frame(lab, contig_id) if lazy else contig_rows(frames[lab], index[lab], contig_id)
 
+    def contig_columns(lab, contig_id):      # the same rows as plain columns when the frames come from arrays
+        return frames.contig_columns(lab, contig_id) if lazy else contig_frame(lab, contig_id)
+
     lmin, lmax = getattr(P, "_label_min", None), getattr(P, "_label_max", None)
     if lmin is None:
         lmin = np.array([int(np.min(u)) if len(u) else -1 for u in P.updated_genome_labels], dtype=np.int64)
@@ -417,8 +429,8 @@ def compare_sets_of_predicted_genes(P):
         code_1, code_2 = P.label_to_gcode[label_1], P.label_to_gcode[label_2]
         messages.append(f"Contig {rec.id} in {P.species} carries genetic code {code_1} and {code_2}")
         explicit[rec.id] = {1: str(code_1), 2: str(code_2), 3: f"{code_1}_{code_2}"}
-        S1 = _GeneSet(contig_frame(label_1, rec.id))
-        S2 = _GeneSet(contig_frame(label_2, rec.id))
+        S1 = _GeneSet(contig_columns(label_1, rec.id))
+        S2 = _GeneSet(contig_columns(label_2, rec.id))
         cur, iso = compare_contig(S1, S2, code_1, code_2, P.tolerance, rec.seq)
         # ref: DataFrame.sort_values('start') on an object column = numpy's quicksort over Python ints; rows with equal
         # starts (an isoform pair's two genes) come out in that sort's order, and the smoothing below sees them so

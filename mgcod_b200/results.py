@@ -263,6 +263,10 @@ class Results:
     # ---- bin/results.py:159-181 --------------------------------------------------------------------------------
     def write_stats(self):
         coords = self.results.coords_w_isoforms
+        attributes = coords["attributes"].tolist()      # row n of the frame (its index is 0..n-1, bin/results.py:175 uses .loc[n])
+        if list(coords.index[:3]) != list(range(min(3, len(coords)))):
+            attributes = [coords.loc[n, "attributes"] for n in range(len(self.stop_recodings))]
+        lines = []
         with open(self.path_to_output.replace(".tab", "_stats.tab"), "w+") as stat:
             for n, recodings in enumerate(self.stop_recodings):
                 positions, stops = [], []
@@ -273,10 +277,11 @@ class Results:
                     order = np.argsort(positions)
                     positions = [positions[i] for i in order]
                     stops = [stops[i] for i in order]
-                line = f"{coords.loc[n, 'attributes'].split(';')[0]} recodings {len(positions)} codon_index_values"
+                line = f"{attributes[n].split(';')[0]} recodings {len(positions)} codon_index_values"
                 for p, s in zip(positions, stops):
                     line += f" {p} {s}"
-                stat.write(line.replace(" ", "\t") + "\n")
+                lines.append(line.replace(" ", "\t"))
+            stat.write("\n".join(lines) + ("\n" if lines else ""))
 
     # ---- bin/results.py:181-251 --------------------------------------------------------------------------------
     def write_final_results(self):
@@ -284,7 +289,9 @@ class Results:
         if isinstance(P.genome_label, (int, np.integer)):
             tables = [str(P.genome_label)]
         else:   # every label a window ever got, not only the two that survive the smoothing
-            tables = sorted({str(P.label_to_gcode[int(x)]) for y in P.genome_label for x in y})
+            labels = (P.genome_label.concatenated() if hasattr(P.genome_label, "concatenated")
+                      else np.concatenate([np.asarray(y) for y in P.genome_label]))
+            tables = sorted({str(P.label_to_gcode[int(x)]) for x in np.unique(labels).tolist()})
         parameters = ", ".join(f"{self.cwd}/dependencies/mgm_{x}.mod" for x in tables)
         coords = P.coords_w_isoforms
         if coords.shape[0] == 0:
@@ -298,11 +305,11 @@ class Results:
             out.write(f"# translation table: {', '.join(tables)}\n")
             out.write(f"# output date start: {self.date.strftime('%a %b %d %Y %H:%M:%S')}\n")
             index = rows_by_contig(coords)
-            for n in range(P.nr_contigs):
-                size = len(P.sequence[n])
-                if P.sequence[n].id not in index:       # no genes on this contig: no block in the file
+            for n, seq in enumerate(P.sequence):
+                if seq.id not in index:       # no genes on this contig: no block in the file
                     continue
-                cur = contig_rows(coords, index, P.sequence[n].id).copy()
+                size = len(seq)
+                cur = contig_rows(coords, index, seq.id).copy()
                 cur = cur.loc[:, columns]
                 cur.reset_index(drop=True, inplace=True)
                 accession = cur.iloc[0, 0]
