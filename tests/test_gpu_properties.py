@@ -166,6 +166,39 @@ def test_model_orders_codes_and_domains_match_oracle(kc, kn, gcode, domains, bin
     eng.close()
 
 
+@pytest.mark.parametrize("walk", ["pair", "single"])
+def test_models_of_different_orders_in_one_engine(walk, tmp_path, monkeypatch):
+    """four parameter files with different Markov orders (4/2, 3/1, 2/0, 1/1) in ONE engine: the pair walk runs its generic
+    kernel (orders read per work unit, a different table layout and replica count per model, tables reloaded when the model
+    changes); MGCOD_B200_WALK=single sends the same input through the single-position walk.  Both equal the oracle."""
+    import lzma, os
+    from mgcod_b200 import synth
+    from mgcod_b200.engine import Engine, synth_metagenome
+    from oracle import gmhmm
+    from tests import parity
+    if walk == "single":
+        monkeypatch.setenv("MGCOD_B200_WALK", "single")
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "phage2.fa.xz")
+    template = "".join(l.strip() for l in lzma.open(golden, "rt") if not l.startswith(">")).upper()
+    specs = [(4, 2, 11, ("B", "A"), [30, 45]), (3, 1, 4, ("B", "A"), [35]), (2, 0, 15, ("B",), [33, 44]), (1, 1, 101, ("B", "A"), [40])]
+    mods = []
+    for i, (kc, kn, gcode, domains, bins) in enumerate(specs):
+        mods.append(str(tmp_path / f"m{i}.mod"))
+        synth.write_mod(mods[-1], synth.trained_sections(synth.encode(template), gcode, kc, kn, bins=bins, domains=domains))
+    buf, offs, truth = synth_metagenome(777, 150000, threads=2)
+    seqs = [buf[offs[i]:offs[i + 1]].tobytes() for i in range(len(truth))] + [template[60000:90000].encode()]
+    eng = Engine(mods)
+    res = eng.decode(seqs)
+    for mi, mod in enumerate(mods):
+        orc = gmhmm.Model(mod)
+        rows, totals = parity.oracle_genes(orc, seqs)
+        assert len(rows) > 20
+        diffs = parity.compare_genes(res.genes(mi), rows)
+        assert not diffs, f"model {mi}: " + "; ".join(diffs[:6])
+        np.testing.assert_allclose(res.contig_totals(mi), totals, rtol=1e-9, atol=1e-9)
+    eng.close()
+
+
 def test_low_complexity_repeats_grow_the_scratch_buffers(engine):
     """(ATG)n / (CAT)n repeats hold a start codon every three letters — far more starts per letter than the scratch
     capacities assume; the engine must notice, grow and still agree with the oracle"""
