@@ -123,6 +123,12 @@ static_assert(sizeof(Cand) == 32, "Cand must be 32 bytes");
 
 constexpr int32_t GPTR_UNSET = (int32_t)0x80808080;
 
+// predecessor state of the thread-per-piece chain
+struct __align__(16) ChainSt {
+    int4 i;      // right, left, len * 2 + (strand < 0), sorted index
+    double2 d;   // cum, prefix maximum of cum
+};
+
 struct ChainBufs {
     const Cand *sorted;
     const uint32_t *bend;   // bucket ends (bucket b spans [b ? bend[b-1] : 0, bend[b]))
@@ -136,6 +142,7 @@ struct ChainBufs {
     int32_t *av_idx;
     double *av_cum, *av_pmax;
     int32_t *av_parg;
+    ChainSt *st;            // thread-per-piece chain (k_chain_flat): one record per state
     int32_t *chain;         // traceback output, piece-local, stored at the piece's sorted range
     // chain pieces: a contig is cut where no candidate spans a bucket boundary; pieces are independent chains.
     // Slot of the piece starting at relative bucket rb of contig c: slotbase[c] + rb / PIECE_BUCKETS.

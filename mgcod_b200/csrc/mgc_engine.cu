@@ -150,7 +150,7 @@ struct PerModel {
     DevBuf lc_full, ln_full, lc_ramp, ln_ramp, sc, quad, rquad, wtab, wtab2, pair_amb, pair_ub;
     DevBuf ls, ls_tile, orfs, starts, items, items_sorted, hist, item_off, unit_off, sums;
     DevBuf surv, sorted, bcount, cum, prev, gptr;
-    DevBuf av_right, av_left, av_ls, av_idx, av_cum, av_pmax, av_parg, chain, gene_count, gene_off, contig_total, genes;
+    DevBuf av_right, av_left, av_ls, av_idx, av_cum, av_pmax, av_parg, st, chain, gene_count, gene_off, contig_total, genes;
     DevBuf piece_b0, piece_b1, work, piece_total, slot_gene_off, cover, minleft;
 };
 
@@ -211,6 +211,7 @@ struct mgc_engine {
     DevBuf counters;     // [M][8] unsigned long long: 0 orfs, 1 starts
     DevBuf surv_counters;  // [M]
     DevBuf work_counters;  // [M] int
+    bool chain_warp = false;  // MGCOD_B200_CHAIN=warp: the warp-per-piece chain kernel of round 1 (A/B measurements, tests)
     DevBuf model_cents;    // [M]
     DevBuf gene_totals;    // [M] uint32 grand totals of the gene scans
     DevBuf win_stride, win_off, win_labels, win_cents, win_merged, win_run, win_status, win_hist;   // labelling scratch, kept between calls
@@ -444,6 +445,7 @@ void upload_models(mgc_engine *e) {
     // the pair walk needs every model's pair tables in one SM's shared memory (orders <= 4); otherwise, or with
     // MGCOD_B200_WALK=single (A/B measurements, tests of the older kernel), the single-position walk runs
     e->pair_smem = 0;
+    if (const char *cm = std::getenv("MGCOD_B200_CHAIN")) e->chain_warp = std::strcmp(cm, "warp") == 0;
     {
         const char *mode = std::getenv("MGCOD_B200_WALK");
         bool all = !(mode && std::strcmp(mode, "single") == 0);
@@ -509,13 +511,13 @@ void ensure_batch_buffers(mgc_engine *e) {
         p.cum.ensure((size_t)e->cap_surv * 8);
         p.prev.ensure((size_t)e->cap_surv * 4);
         p.gptr.ensure((size_t)e->cap_orf * 4);
-        p.av_right.ensure((size_t)e->cap_surv * 4);
-        p.av_left.ensure((size_t)e->cap_surv * 4);
-        p.av_ls.ensure((size_t)e->cap_surv * 4);
-        p.av_idx.ensure((size_t)e->cap_surv * 4);
-        p.av_cum.ensure((size_t)e->cap_surv * 8);
-        p.av_pmax.ensure((size_t)e->cap_surv * 8);
         p.av_parg.ensure((size_t)e->cap_surv * 4);
+        if (e->chain_warp) {
+            for (DevBuf *b : {&p.av_right, &p.av_left, &p.av_ls, &p.av_idx}) b->ensure((size_t)e->cap_surv * 4);
+            for (DevBuf *b : {&p.av_cum, &p.av_pmax}) b->ensure((size_t)e->cap_surv * 8);
+        } else {
+            p.st.ensure((size_t)e->cap_surv * sizeof(ChainSt));
+        }
         p.chain.ensure((size_t)e->cap_surv * 4);
         p.gene_count.ensure((size_t)(e->n_slots + 8) * 4);
         p.slot_gene_off.ensure((size_t)(e->n_slots + 8) * 4);
@@ -530,7 +532,7 @@ void ensure_batch_buffers(mgc_engine *e) {
         t_bcount[i] = p.bcount.p; t_cover[i] = p.cover.p; t_gene_off[i] = p.gene_off.p; t_genes[i] = p.genes.p;
         t_scan_buckets[i] = p.bcount.p; t_scan_buckets[M + i] = p.cover.p; t_gene_count[i] = p.gene_count.p; t_slot_gene_off[i] = p.slot_gene_off.p;
         ChainBufs &c = cb[i];
-        c.sorted = p.sorted.as<Cand>();
+        c.sorted = p.surv.as<Cand>();   // k_final's survivors are scattered into p.sorted by bucket, then ordered inside the buckets back into p.surv
         c.bend = p.bcount.as<uint32_t>();
         c.cover = p.cover.as<uint32_t>();
         c.minleft = p.minleft.as<uint32_t>();
@@ -544,6 +546,7 @@ void ensure_batch_buffers(mgc_engine *e) {
         c.av_cum = p.av_cum.as<double>();
         c.av_pmax = p.av_pmax.as<double>();
         c.av_parg = p.av_parg.as<int32_t>();
+        c.st = p.st.as<ChainSt>();
         c.chain = p.chain.as<int32_t>();
         c.piece_b0 = p.piece_b0.as<int32_t>();
         c.piece_b1 = p.piece_b1.as<int32_t>();
@@ -794,10 +797,22 @@ mgc_result *run_pipeline(mgc_engine *e, bool *amb_out) {
     launches += 1;
     CUDA_TRY(cudaPeekAtLastError());   // a failed launch must not go unnoticed until the end
     CUDA_TRY(cudaEventRecord(e->ev[4], st));
-    launches += launch_chain(e->t_chainbufs.as<ChainBufs>(), e->cwoff.as<int64_t>(), e->clen.as<int32_t>(), e->slotbase.as<int32_t>(),
-                             e->slot_contig.as<int32_t>(), e->n_slots, nb, e->work_counters.as<int>(), M, e->n_sm, st);
+    launches += launch_chain(e->t_chainbufs.as<ChainBufs>(), e->t_sorted.as<const Cand *>(), e->t_surv.as<Cand *>(), e->cwoff.as<int64_t>(), e->clen.as<int32_t>(), e->slotbase.as<int32_t>(),
+                             e->slot_contig.as<int32_t>(), e->n_slots, nb, e->work_counters.as<int>(), M, e->n_sm, e->chain_warp, st);
     CUDA_TRY(cudaPeekAtLastError());   // a failed launch must not go unnoticed until the end
     CUDA_TRY(cudaEventRecord(e->ev[5], st));
+    if (std::getenv("MGCOD_B200_PIECE_STATS")) {   // diagnostic: sizes of the chain pieces of model 0
+        unsigned int *d_hist = nullptr, h_hist[40];
+        CUDA_TRY(cudaMalloc(&d_hist, sizeof(h_hist)));
+        CUDA_TRY(cudaMemsetAsync(d_hist, 0, sizeof(h_hist), st));
+        launch_piece_stats(e->t_chainbufs.as<ChainBufs>(), e->work_counters.as<int>(), e->n_slots, d_hist, st);
+        CUDA_TRY(cudaMemcpyAsync(h_hist, d_hist, sizeof(h_hist), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        cudaFree(d_hist);
+        std::fprintf(stderr, "[mgcod_b200] chain pieces of model 0: %u, largest %u candidates; log2 histogram:", h_hist[33], h_hist[32]);
+        for (int i = 0; i < 32; i++) if (h_hist[i]) std::fprintf(stderr, " [<2^%d]=%u", i, h_hist[i]);
+        std::fprintf(stderr, "\n");
+    }
     // gene_count[n_slots] stays 0 so that the exclusive scan yields the total at slot_gene_off[n_slots]
     launches += launch_exclusive_scan_multi(e->t_gene_count.as<const uint32_t *>(), e->t_slot_gene_off.as<uint32_t *>(), M,
                                             e->tile_sums.as<uint32_t>(), (int64_t)e->n_slots + 1, e->gene_totals.as<uint32_t>(), 1, st);
@@ -1060,7 +1075,7 @@ void mgc_engine_destroy(mgc_engine *e) {
     for (auto &p : e->pm) {
         for (DevBuf *b : {&p.lc_full, &p.ln_full, &p.lc_ramp, &p.ln_ramp, &p.sc, &p.quad, &p.rquad, &p.wtab, &p.wtab2, &p.pair_amb, &p.pair_ub, &p.ls, &p.ls_tile, &p.items, &p.items_sorted, &p.hist,
                           &p.item_off, &p.unit_off, &p.sums, &p.orfs, &p.starts, &p.surv, &p.sorted, &p.bcount,
-                          &p.cum, &p.prev, &p.gptr, &p.av_right, &p.av_left, &p.av_ls, &p.av_idx, &p.av_cum, &p.av_pmax, &p.av_parg,
+                          &p.cum, &p.prev, &p.gptr, &p.av_right, &p.av_left, &p.av_ls, &p.av_idx, &p.av_cum, &p.av_pmax, &p.av_parg, &p.st,
                           &p.chain, &p.gene_count, &p.gene_off, &p.contig_total, &p.genes, &p.piece_b0, &p.piece_b1, &p.work,
                           &p.piece_total, &p.slot_gene_off, &p.cover, &p.minleft})
             b->release();
@@ -1175,7 +1190,7 @@ int64_t mgc_debug_candidates(mgc_engine *e, int model, mgc_candidate *out, int64
         std::vector<Cand> c(ns);
         std::vector<double> cum(ns);
         if (ns) {
-            CUDA_TRY(cudaMemcpy(c.data(), e->pm[model].sorted.p, ns * sizeof(Cand), cudaMemcpyDeviceToHost));
+            CUDA_TRY(cudaMemcpy(c.data(), e->pm[model].surv.p, ns * sizeof(Cand), cudaMemcpyDeviceToHost));
             CUDA_TRY(cudaMemcpy(cum.data(), e->pm[model].cum.p, ns * 8, cudaMemcpyDeviceToHost));
         }
         n = (int64_t)ns;

@@ -14,7 +14,7 @@
 //   k_walk           thread per item: 3-periodic Markov log-likelihood sums from the stop down, the pair's tables in shared memory
 //   k_final          per start: order ramp, duration / start / stop terms, domain choice, pruning (total > 0), bucket histogram
 //   scan + k_scatter survivors into position buckets (128 nt) -> right-end order per contig
-//   k_chain_minleft / k_chain_plan / k_chain   cut points, then one warp per piece: max-plus chain with overlap penalties, traceback
+//   k_bucket_order / k_chain_plan / k_chain_flat (k_chain)   cut points, then one warp per piece: max-plus chain with overlap penalties, traceback
 //   scan + k_gather + k_contig_finish   genes ordered by (contig, left), per-model sums in 1/100 units, per-contig totals
 //   on request: k_windows, k_merge_labels (window labels), k_recoded_stops (in-frame stops per gene), k_find_gaps
 //
@@ -1925,13 +1925,40 @@ __device__ __forceinline__ void chain_bucket(const ChainBufs &B, ChainRing &R, u
 // left end lies before the boundary, so with minleft[b] = smallest left end among the candidates ending in b,
 //   boundary k is safe  <=>  min(minleft[k .. k+H)) >= position of k   and no LONG candidate (>= H boundaries) spans k,
 // the long ones being counted by k_final in a prefix-summed difference array (ChainBufs::cover).  H = PIECE_BUCKETS.
-__global__ void __launch_bounds__(256) k_chain_minleft(const ChainBufs *bufs_m, int64_t n_buckets) {
-    const ChainBufs B = bufs_m[blockIdx.y];
-    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= n_buckets) return;
-    uint32_t m = 0xffffffffu;
-    for (uint32_t k = b ? B.bend[b - 1] : 0u, e = B.bend[b]; k < e; k++) m = min(m, (uint32_t)B.sorted[k].left);
-    B.minleft[b] = m;
+// k_scatter leaves a bucket unordered.  Thread per candidate: its rank inside its bucket in chain order (right end, direct strand
+// first, left end, real start before a virtual one at the same position) = the number of members with a smaller key; the
+// record moves to its final place in `out` (ChainBufs::sorted).  The member with rank 0 also stores the bucket's smallest left end
+// (empty buckets keep a stale value: k_chain_plan tests for emptiness first).  Neighbouring lanes hold the members of one bucket,
+// so the member loop runs over lines the warp has just loaded.
+__global__ void __launch_bounds__(256) k_bucket_order(const ChainBufs *bufs_m, const Cand *const *tmp_m, Cand *const *out_m,
+                                                      const int64_t *__restrict__ cwoff, int64_t n_buckets) {
+    const int mi = blockIdx.y;
+    const ChainBufs B = bufs_m[mi];
+    const Cand *__restrict__ tmp = tmp_m[mi];
+    Cand *__restrict__ out = out_m[mi];
+    const int64_t n = B.bend[n_buckets - 1];
+    auto key_of = [](int right, int strand, int left, int flags) {
+        return ((unsigned long long)((uint32_t)right & 127u) << 40) | ((unsigned long long)(strand < 0) << 39) |
+               (((unsigned long long)(uint32_t)left << 1) | (((uint32_t)flags >> 1) & 1u));
+    };
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        const Cand me = tmp[k];
+        const int64_t b = (cwoff[me.contig] * 32 + me.right) >> 7;
+        const uint32_t s = b ? B.bend[b - 1] : 0u, e = B.bend[b];
+        uint32_t rank = 0, minl = (uint32_t)me.left;
+        if (e - s > 1) {
+            const unsigned long long mine = key_of(me.right, me.strand, me.left, me.flags);
+            for (uint32_t j = s; j < e; j++) {
+                const int4 a = *reinterpret_cast<const int4 *>(&tmp[j]);            // contig, left, right, orf
+                const int4 c = *(reinterpret_cast<const int4 *>(&tmp[j]) + 1);        // total (2 words), gc | strand | flags, len
+                const unsigned long long kj = key_of(a.z, (int)(int8_t)((uint32_t)c.z >> 16), a.y, (int)(((uint32_t)c.z >> 24) & 0xffu));
+                rank += kj < mine;
+                minl = min(minl, (uint32_t)a.y);
+            }
+        }
+        out[s + rank] = me;
+        if (rank == 0) B.minleft[b] = minl;
+    }
 }
 
 // Thread per piece slot = aligned window of PIECE_BUCKETS buckets of a contig; a window contributes its first safe
@@ -1953,14 +1980,16 @@ __global__ void __launch_bounds__(128) k_chain_plan(const ChainBufs *bufs_m, con
     if (ce == cs) return;
     const uint32_t *cov = B.cover + b_first + 1;  // cov[rb]: LONG candidates spanning the boundary in front of relative bucket rb
     const uint32_t *ml = B.minleft + b_first;     // ml[rb]: smallest (contig-relative) left end among the candidates ending in rb
+    const uint32_t *be = B.bend + b_first;        // a bucket is empty when its end equals its predecessor's (its minleft entry is stale then)
+    auto ml_at = [&](int rb) { return be[rb] == ((b_first + rb) ? be[rb - 1] : 0u) ? 0xffffffffu : ml[rb]; };
     auto cut_of = [&](int win) {  // first safe boundary of the window, -1 if none
         if (win == 0) return 0;
         const int lo = win * PIECE_BUCKETS, hi = min(lo + PIECE_BUCKETS - 1, nbk - 1);
         uint32_t run = 0xffffffffu;  // min(minleft[rb .. hi + H)), built from the far end
-        for (int rb = min(hi + PIECE_BUCKETS - 1, nbk - 1); rb > hi; rb--) run = min(run, ml[rb]);
+        for (int rb = min(hi + PIECE_BUCKETS - 1, nbk - 1); rb > hi; rb--) run = min(run, ml_at(rb));
         int best = -1;
         for (int rb = hi; rb >= lo; rb--) {
-            run = min(run, ml[rb]);
+            run = min(run, ml_at(rb));
             if (run >= (uint32_t)rb * 128u && cov[rb] == 0u) best = rb;
         }
         return best;
@@ -2101,6 +2130,128 @@ __global__ void __launch_bounds__(128, 8) k_chain(const ChainBufs *bufs_m, int *
             B.piece_total[slot] = S.head > 0 ? S.pm_val : 0.0;
         }
         __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// chain DP, thread per piece (round 2).  The warp-per-piece kernel above spends ~300 warp instructions per candidate on
+// warp-wide bookkeeping (minima, ballots, broadcasts) for buckets that hold 1.2 candidates on average.  Here every thread
+// runs the plain serial recurrence of its piece, in the order of oracle/gmhmm_oracle.c orc_chain (k_bucket_order has
+// sorted every bucket: right end, direct strand first, left end, real start before virtual): groups of equal right end see
+// the states written before the group; the direct-strand members' best becomes the stop's one state, appended before the
+// group's reverse-strand members.
+// The recurrence is written as ONE flat loop whose iteration examines one predecessor state of the thread's current
+// candidate: nested data-dependent loops (candidates x states) would leave a warp's 32 pieces at 32 different program
+// points and issue every instruction for one lane; in the flat loop all lanes meet at "examine a state" every iteration,
+// and the rarer sections (next candidate, finish candidate, next piece) are entered by the lanes that need them.
+// States are 32-byte records {right, left, len*2+rev, index, cum, prefix max}, written and re-read by the same thread.
+// Pieces are handed out one at a time per THREAD: a lane that finishes its piece takes the next while its neighbours go on.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 8) k_chain_flat(const ChainBufs *bufs_m, int *work_counters) {
+    const int mi = blockIdx.y;
+    const ChainBufs B = bufs_m[mi];
+    const Cand *__restrict__ C = B.sorted;
+    const int n_work = work_counters[2 * mi];
+    // piece
+    int slot = 0;
+    uint32_t k = 0, ce = 0;              // next candidate, end of the piece
+    ChainSt *st = nullptr;
+    int32_t *parg = nullptr;
+    int na = 0, head = 0, pm_arg = -1;
+    double pm_val = 0.0;
+    // group (equal right end): its pending direct-strand state
+    int grp_right = -1, bidx = -1, bleft = 0, blen = 0;
+    double bc = 0.0;
+    // candidate under evaluation
+    Cand g;
+    uint32_t gi = 0;
+    int sk = -1, best_idx = -1;
+    int4 s = make_int4(0, 0, 0, 0);        // state sk: right, left, len * 2 + rev, index
+    double2 sd = make_double2(0.0, 0.0);   //           cum, prefix maximum
+    double best_v = 0.0;
+    bool have_piece = false, scanning = false;
+
+    auto append = [&](int idx, double cum, int right, int left, int ls) {
+        if (head == 0 || cum > pm_val) { pm_val = cum; pm_arg = idx; }
+        st[head].i = make_int4(right, left, ls, idx);
+        st[head].d = make_double2(cum, pm_val);
+        parg[head] = pm_arg;
+        head++;
+    };
+
+    while (true) {
+        if (!scanning) {
+            if (have_piece && k >= ce) {   // piece finished
+                if (bidx >= 0) append(bidx, bc, grp_right, bleft, blen * 2);
+                B.gene_count[slot] = head > 0 ? pm_arg : -1;   // end of the best chain, until k_chain_trace
+                B.piece_total[slot] = head > 0 ? pm_val : 0.0;
+                have_piece = false;
+            }
+            if (!have_piece) {
+                const int item = atomicAdd(&work_counters[2 * mi + 1], 1);
+                if (item >= n_work) break;
+                slot = B.work[item];
+                const int64_t b_first = B.piece_b0[slot], b_last = B.piece_b1[slot];
+                const uint32_t cs = b_first ? B.bend[b_first - 1] : 0u;
+                ce = B.bend[b_last];
+                k = cs;
+                st = B.st + cs; parg = B.av_parg + cs;
+                na = 0; head = 0; pm_val = 0.0; pm_arg = -1;
+                grp_right = -1; bidx = -1;
+                have_piece = true;
+                if (k >= ce) continue;
+            }
+            // next candidate
+            g = C[k];
+            gi = k++;
+            if (g.right != grp_right) {
+                if (bidx >= 0) { append(bidx, bc, grp_right, bleft, blen * 2); bidx = -1; }
+                na = head;
+                grp_right = g.right;
+            } else if (g.strand < 0 && bidx >= 0) {
+                append(bidx, bc, grp_right, bleft, blen * 2);
+                bidx = -1;
+            }
+            sk = na - 1;
+            best_v = 0.0;
+            best_idx = -1;
+            if (sk >= 0) { s = st[sk].i; sd = st[sk].d; }
+            scanning = true;
+        }
+        if (sk >= 0 && s.x >= g.left) {
+            // one state whose right end lies inside the candidate; its older neighbour is requested before the evaluation
+            const int pk = sk > 0 ? sk - 1 : 0;
+            const int4 nx = st[pk].i;
+            const double2 nd = st[pk].d;
+            if (s.y < g.left) {
+                const double v = sd.x - overlap_penalty(g.left, g.len, g.strand, s.x, s.z >> 1, (s.z & 1) ? -1 : 1);
+                if (v >= best_v && v > 0.0) { best_v = v; best_idx = s.w; }   // descending index: ties go to the earliest state
+            }
+            sk--;
+            s = nx;
+            sd = nd;
+        } else {
+            // finish the candidate: best non-overlapping predecessor = prefix maximum at the first state ending before it
+            double b = 0.0;
+            int bp = -1;
+            if (sk >= 0 && sd.y > 0.0) { b = sd.y; bp = parg[sk]; }
+            const int bp_non = bp;
+            const bool over = best_idx >= 0 && best_v > b;   // an overlap wins only if strictly better
+            if (over) { b = best_v; bp = best_idx; }
+            const double cumg = g.total + b;
+            B.cum[gi] = cumg;
+            B.prev[gi] = bp;
+            if (g.strand > 0) {
+                if (bidx < 0 || cumg > bc) { bc = cumg; bidx = (int)gi; bleft = g.left; blen = g.len; }   // sorted by left: ties keep the smallest
+            } else {
+                int gp = (g.flags & 8) ? GPTR_UNSET : B.gptr[g.orf];   // the ORF's shared back-pointer (rule 6)
+                if (gp == GPTR_UNSET) gp = bp_non;
+                if (over) gp = bp;
+                B.gptr[g.orf] = gp;
+                append((int)gi, cumg, g.right, g.left, g.len * 2 + 1);
+            }
+            scanning = false;
+        }
     }
 }
 
@@ -2543,12 +2694,31 @@ void launch_scatter(const Cand *const *surv_m, Cand *const *sorted_m, uint32_t *
     k_scatter<<<grid, 256, 0, st>>>(surv_m, sorted_m, boff_m, surv_counters, cwoff, cap_surv);
 }
 
-int launch_chain(const ChainBufs *bufs_m, const int64_t *cwoff, const int32_t *clen, const int32_t *slotbase, const int32_t *slot_contig,
-                 int32_t n_slots, int64_t n_buckets, int *work_counters, int n_models, int n_sm, cudaStream_t st) {
-    k_chain_minleft<<<dim3((unsigned)((n_buckets + 255) / 256), n_models), 256, 0, st>>>(bufs_m, n_buckets);
+// diagnostic (MGCOD_B200_PIECE_STATS): log2 histogram of candidates per chain piece of model 0; hist[32] = largest piece, hist[33] = pieces
+__global__ void k_piece_stats(const ChainBufs *bufs_m, const int *work_counters, unsigned int *hist) {
+    const ChainBufs B = bufs_m[0];
+    const int n_work = work_counters[0];
+    const int item = blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= n_work) return;
+    const int slot = B.work[item];
+    const int64_t b_first = B.piece_b0[slot], b_last = B.piece_b1[slot];
+    const uint32_t n = B.bend[b_last] - (b_first ? B.bend[b_first - 1] : 0u);
+    atomicAdd(&hist[n ? 32 - __clz(n) : 0], 1u);
+    atomicMax(&hist[32], n);
+    atomicAdd(&hist[33], 1u);
+}
+void launch_piece_stats(const ChainBufs *bufs_m, const int *work_counters, int32_t n_slots, unsigned int *hist, cudaStream_t st) {
+    k_piece_stats<<<(unsigned)((n_slots + 127) / 128), 128, 0, st>>>(bufs_m, work_counters, hist);
+}
+
+int launch_chain(const ChainBufs *bufs_m, const Cand *const *scattered_m, Cand *const *ordered_m, const int64_t *cwoff, const int32_t *clen,
+                 const int32_t *slotbase, const int32_t *slot_contig, int32_t n_slots, int64_t n_buckets, int *work_counters, int n_models,
+                 int n_sm, bool warp_per_piece, cudaStream_t st) {
+    k_bucket_order<<<dim3((unsigned)n_sm * 8, n_models), 256, 0, st>>>(bufs_m, scattered_m, ordered_m, cwoff, n_buckets);
     k_chain_plan<<<dim3((unsigned)((n_slots + 127) / 128), n_models), 128, 0, st>>>(bufs_m, cwoff, clen, slotbase, slot_contig, n_slots,
                                                                                      work_counters);
-    k_chain<<<dim3((unsigned)n_sm * 16, n_models), 128, 0, st>>>(bufs_m, work_counters);
+    if (warp_per_piece) k_chain<<<dim3((unsigned)n_sm * 16, n_models), 128, 0, st>>>(bufs_m, work_counters);
+    else k_chain_flat<<<dim3((unsigned)n_sm * 8, n_models), 128, 0, st>>>(bufs_m, work_counters);
     k_chain_trace<<<dim3((unsigned)((n_slots + 127) / 128), n_models), 128, 0, st>>>(bufs_m, work_counters);
     return 4;
 }

@@ -54,8 +54,10 @@ void launch_final(Planes pl, const int64_t *cwoff, const int32_t *clen, const De
 void launch_scatter(const Cand *const *surv_m, Cand *const *sorted_m, uint32_t *const *boff_m,
                     const unsigned long long *surv_counters, const int64_t *cwoff, uint32_t cap_surv, int n_models, int n_sm,
                     cudaStream_t st);
-int launch_chain(const ChainBufs *bufs_m, const int64_t *cwoff, const int32_t *clen, const int32_t *slotbase, const int32_t *slot_contig,
-                 int32_t n_slots, int64_t n_buckets, int *work_counters, int n_models, int n_sm, cudaStream_t st);
+void launch_piece_stats(const ChainBufs *bufs_m, const int *work_counters, int32_t n_slots, unsigned int *hist, cudaStream_t st);
+int launch_chain(const ChainBufs *bufs_m, const Cand *const *scattered_m, Cand *const *ordered_m, const int64_t *cwoff, const int32_t *clen,
+                 const int32_t *slotbase, const int32_t *slot_contig, int32_t n_slots, int64_t n_buckets, int *work_counters, int n_models,
+                 int n_sm, bool warp_per_piece, cudaStream_t st);
 int launch_gather(const ChainBufs *bufs_m, mgc_gene *const *genes_m, const int32_t *slot_contig, int32_t n_slots, const int32_t *slotbase,
                   int32_t n_contigs, long long *model_cents, int n_models, int n_sm, cudaStream_t st);
 void launch_windows(const mgc_gene *const *genes_m, const uint32_t *const *gene_off_m, int n_models, const int32_t *clen,
