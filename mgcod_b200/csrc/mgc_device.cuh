@@ -125,7 +125,7 @@ constexpr int32_t GPTR_UNSET = (int32_t)0x80808080;
 
 // predecessor state of the thread-per-piece chain
 struct __align__(16) ChainSt {
-    int4 i;      // right, left, len * 2 + (strand < 0), sorted index
+    int4 i;      // len * 2 + (strand < 0), sorted index, sorted index of the prefix maximum, unused
     double2 d;   // cum, prefix maximum of cum
 };
 
@@ -143,6 +143,7 @@ struct ChainBufs {
     double *av_cum, *av_pmax;
     int32_t *av_parg;
     ChainSt *st;            // thread-per-piece chain (k_chain_flat): one record per state
+    int2 *st_rl;            //   and its {right, left}, what the scan over predecessor states reads
     int32_t *chain;         // traceback output, piece-local, stored at the piece's sorted range
     // chain pieces: a contig is cut where no candidate spans a bucket boundary; pieces are independent chains.
     // Slot of the piece starting at relative bucket rb of contig c: slotbase[c] + rb / PIECE_BUCKETS.

@@ -150,7 +150,7 @@ struct PerModel {
     DevBuf lc_full, ln_full, lc_ramp, ln_ramp, sc, quad, rquad, wtab, wtab2, pair_amb, pair_ub;
     DevBuf ls, ls_tile, orfs, starts, items, items_sorted, hist, item_off, unit_off, sums;
     DevBuf surv, sorted, bcount, cum, prev, gptr;
-    DevBuf av_right, av_left, av_ls, av_idx, av_cum, av_pmax, av_parg, st, chain, gene_count, gene_off, contig_total, genes;
+    DevBuf av_right, av_left, av_ls, av_idx, av_cum, av_pmax, av_parg, st, st_rl, chain, gene_count, gene_off, contig_total, genes;
     DevBuf piece_b0, piece_b1, work, piece_total, slot_gene_off, cover, minleft;
 };
 
@@ -210,7 +210,7 @@ struct mgc_engine {
     int pair_smem = 0;     // bytes of the pair walk's shared-memory table; 0 = single-position walk (order 5, or MGCOD_B200_WALK=single)
     DevBuf counters;     // [M][8] unsigned long long: 0 orfs, 1 starts
     DevBuf surv_counters;  // [M]
-    DevBuf work_counters;  // [M] int
+    DevBuf work_counters;  // [M][4] int: long pieces, consumers' cursor, other pieces, unused
     bool chain_warp = false;  // MGCOD_B200_CHAIN=warp: the warp-per-piece chain kernel of round 1 (A/B measurements, tests)
     DevBuf model_cents;    // [M]
     DevBuf gene_totals;    // [M] uint32 grand totals of the gene scans
@@ -517,6 +517,7 @@ void ensure_batch_buffers(mgc_engine *e) {
             for (DevBuf *b : {&p.av_cum, &p.av_pmax}) b->ensure((size_t)e->cap_surv * 8);
         } else {
             p.st.ensure((size_t)e->cap_surv * sizeof(ChainSt));
+            p.st_rl.ensure(((size_t)e->cap_surv + 8) * 8);   // the scan reads aligned groups of four: up to three records past the last
         }
         p.chain.ensure((size_t)e->cap_surv * 4);
         p.gene_count.ensure((size_t)(e->n_slots + 8) * 4);
@@ -547,6 +548,7 @@ void ensure_batch_buffers(mgc_engine *e) {
         c.av_pmax = p.av_pmax.as<double>();
         c.av_parg = p.av_parg.as<int32_t>();
         c.st = p.st.as<ChainSt>();
+        c.st_rl = p.st_rl.as<int2>();
         c.chain = p.chain.as<int32_t>();
         c.piece_b0 = p.piece_b0.as<int32_t>();
         c.piece_b1 = p.piece_b1.as<int32_t>();
@@ -598,7 +600,7 @@ void ensure_batch_buffers(mgc_engine *e) {
     e->next_unit.ensure(16);
     e->counters.ensure((size_t)M * 8 * 8);
     e->surv_counters.ensure((size_t)M * 8);
-    e->work_counters.ensure((size_t)M * 8);
+    e->work_counters.ensure((size_t)M * 16);
     e->model_cents.ensure((size_t)M * 8);
     e->gene_totals.ensure((size_t)M * 4);
 }
@@ -662,6 +664,8 @@ void set_slots(mgc_engine *e) {
 void do_upload(mgc_engine *e, const char *seq, const int64_t *offsets, int32_t n) {
     if (n <= 0) throw std::invalid_argument("n_contigs must be positive");
     CUDA_TRY(cudaSetDevice(e->device));
+    const bool trace = std::getenv("MGCOD_TRACE") != nullptr;
+    const double tu0 = now_ms();
     e->have_batch = e->have_genes = false;
     e->segmented = false;
     e->n_parents = n;
@@ -691,10 +695,15 @@ void do_upload(mgc_engine *e, const char *seq, const int64_t *offsets, int32_t n
         e->ascii.ensure((size_t)(a1 - a0) + 2 * PACK_SLACK);
         CUDA_TRY(cudaMemcpyAsync(e->ascii.as<char>() + PACK_SLACK, seq + a0, (size_t)(a1 - a0), cudaMemcpyHostToDevice, st));
     }
+    const double tu1 = now_ms();
     CUDA_TRY(cudaMemcpyAsync(e->plen.p, e->h_parent_len.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    const double tu2 = now_ms();
     set_slots(e);
+    const double tu3 = now_ms();
     CUDA_TRY(cudaEventRecord(e->ev[1], st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    if (trace) std::fprintf(stderr, "do_upload: host tables + letters queued %.2f ms, lengths queued %.2f ms, set_slots %.2f ms, sync %.2f ms (adopted %d)\n",
+                            tu1 - tu0, tu2 - tu1, tu3 - tu2, now_ms() - tu3, (int)adopted);
     float ms = 0;
     cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]);
     e->stats = mgc_stats();
@@ -720,7 +729,7 @@ mgc_result *run_pipeline(mgc_engine *e, bool *amb_out) {
     CUDA_TRY(cudaMemsetAsync(e->flags.p, 0, 64, st));
     CUDA_TRY(cudaMemsetAsync(e->counters.p, 0, (size_t)M * 64, st));
     CUDA_TRY(cudaMemsetAsync(e->surv_counters.p, 0, (size_t)M * 8, st));
-    CUDA_TRY(cudaMemsetAsync(e->work_counters.p, 0, (size_t)M * 8, st));
+    CUDA_TRY(cudaMemsetAsync(e->work_counters.p, 0, (size_t)M * 16, st));
     CUDA_TRY(cudaMemsetAsync(e->model_cents.p, 0, (size_t)M * 8, st));
     CUDA_TRY(cudaMemsetAsync(e->next_unit.p, 0, 16, st));
     for (int i = 0; i < M; i++) {
@@ -1075,7 +1084,7 @@ void mgc_engine_destroy(mgc_engine *e) {
     for (auto &p : e->pm) {
         for (DevBuf *b : {&p.lc_full, &p.ln_full, &p.lc_ramp, &p.ln_ramp, &p.sc, &p.quad, &p.rquad, &p.wtab, &p.wtab2, &p.pair_amb, &p.pair_ub, &p.ls, &p.ls_tile, &p.items, &p.items_sorted, &p.hist,
                           &p.item_off, &p.unit_off, &p.sums, &p.orfs, &p.starts, &p.surv, &p.sorted, &p.bcount,
-                          &p.cum, &p.prev, &p.gptr, &p.av_right, &p.av_left, &p.av_ls, &p.av_idx, &p.av_cum, &p.av_pmax, &p.av_parg, &p.st,
+                          &p.cum, &p.prev, &p.gptr, &p.av_right, &p.av_left, &p.av_ls, &p.av_idx, &p.av_cum, &p.av_pmax, &p.av_parg, &p.st, &p.st_rl,
                           &p.chain, &p.gene_count, &p.gene_off, &p.contig_total, &p.genes, &p.piece_b0, &p.piece_b1, &p.work,
                           &p.piece_total, &p.slot_gene_off, &p.cover, &p.minleft})
             b->release();

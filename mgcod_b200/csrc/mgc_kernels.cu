@@ -1961,6 +1961,14 @@ __global__ void __launch_bounds__(256) k_bucket_order(const ChainBufs *bufs_m, c
     }
 }
 
+// work list of a model (k_chain_plan): wc[0] long pieces at the front of `work`, wc[2] others from its back, wc[1] the consumers' cursor
+constexpr int CHAIN_BIG_PIECE = 96;
+__device__ __forceinline__ int work_count(const int *wc) { return wc[0] + wc[2]; }
+__device__ __forceinline__ int work_slot(const ChainBufs &B, const int *wc, int item, int n_slots) {
+    const int nb = wc[0];
+    return item < nb ? B.work[item] : B.work[n_slots - 1 - (item - nb)];
+}
+
 // Thread per piece slot = aligned window of PIECE_BUCKETS buckets of a contig; a window contributes its first safe
 // boundary as a cut (window 0: the contig start), and the piece runs up to the next window's cut.  Fully parallel, also
 // inside one long contig.
@@ -2005,22 +2013,25 @@ __global__ void __launch_bounds__(128) k_chain_plan(const ChainBufs *bufs_m, con
     if (pe == ps) return;  // nothing ends inside this piece
     B.piece_b0[s] = (int32_t)(b_first + mine);
     B.piece_b1[s] = (int32_t)(b_first + last);
-    B.work[atomicAdd(&work_counters[2 * mi], 1)] = s;
+    // pieces in processing order: the long ones from the front of `work` (taken first, so that the longest serial chains start
+    // at once), the others from its back
+    if (pe - ps >= (uint32_t)CHAIN_BIG_PIECE) B.work[atomicAdd(&work_counters[4 * mi], 1)] = s;
+    else B.work[n_slots - 1 - atomicAdd(&work_counters[4 * mi + 2], 1)] = s;
 }
 
-__global__ void __launch_bounds__(128, 8) k_chain(const ChainBufs *bufs_m, int *work_counters) {
+__global__ void __launch_bounds__(128, 8) k_chain(const ChainBufs *bufs_m, int *work_counters, int n_slots) {
     __shared__ ChainRing rings[4];
     const int mi = blockIdx.y;
     const ChainBufs B = bufs_m[mi];
     const int lane = lane_id();
     ChainRing &R = rings[threadIdx.x >> 5];
-    const int n_work = work_counters[2 * mi];
+    const int n_work = work_count(work_counters + 4 * mi);
     while (true) {
         int item = 0;
-        if (lane == 0) item = atomicAdd(&work_counters[2 * mi + 1], 1);
+        if (lane == 0) item = atomicAdd(&work_counters[4 * mi + 1], 1);
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item >= n_work) break;
-        const int slot = B.work[item];
+        const int slot = work_slot(B, work_counters + 4 * mi, item, n_slots);
         const int64_t b_first = B.piece_b0[slot], b_last = B.piece_b1[slot];
         const uint32_t cs = b_first ? B.bend[b_first - 1] : 0u;
         const uint32_t ce = B.bend[b_last];
@@ -2140,130 +2151,199 @@ __global__ void __launch_bounds__(128, 8) k_chain(const ChainBufs *bufs_m, int *
 // sorted every bucket: right end, direct strand first, left end, real start before virtual): groups of equal right end see
 // the states written before the group; the direct-strand members' best becomes the stop's one state, appended before the
 // group's reverse-strand members.
-// The recurrence is written as ONE flat loop whose iteration examines one predecessor state of the thread's current
-// candidate: nested data-dependent loops (candidates x states) would leave a warp's 32 pieces at 32 different program
-// points and issue every instruction for one lane; in the flat loop all lanes meet at "examine a state" every iteration,
-// and the rarer sections (next candidate, finish candidate, next piece) are entered by the lanes that need them.
-// States are 32-byte records {right, left, len*2+rev, index, cum, prefix max}, written and re-read by the same thread.
+// Written as nested loops (pieces x candidates x states) the 32 pieces of a warp would sit at 32 different program points
+// and every instruction would be issued for 3-4 lanes (measured).  Instead each lane is a small state machine that WANTS
+// one of four sections — fetch the next candidate (and, at the end of a piece, the next piece), scan predecessor states,
+// evaluate one overlap penalty (two divisions and a log: the expensive one), finish the candidate — and every iteration the
+// warp runs the ONE section most lanes want; the others wait a turn.  The sections are executed with a third to a half of
+// the lanes instead of a tenth.
+// The scan over predecessor states is the bulk of the work (24 states per candidate on average, most of them nested inside
+// the candidate and skipped): it reads 8-byte {right, left} records, four per 32-byte sector, the group below requested ahead.
 // Pieces are handed out one at a time per THREAD: a lane that finishes its piece takes the next while its neighbours go on.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128, 8) k_chain_flat(const ChainBufs *bufs_m, int *work_counters) {
+#ifndef CHAIN_MINB
+#define CHAIN_MINB 5
+#endif
+enum { W_FETCH = 0, W_SCAN = 1, W_EVAL = 2, W_FINAL = 3, W_DONE = 4 };
+
+__device__ __forceinline__ void load_group(const int2 *rl, int gb, int2 (&out)[4]) {   // four states' {right, left}: one aligned 32-byte sector
+    const int4 a = *reinterpret_cast<const int4 *>(rl + gb), b = *reinterpret_cast<const int4 *>(rl + gb + 2);
+    out[0] = make_int2(a.x, a.y); out[1] = make_int2(a.z, a.w); out[2] = make_int2(b.x, b.y); out[3] = make_int2(b.z, b.w);
+}
+
+__global__ void __launch_bounds__(128, CHAIN_MINB) k_chain_flat(const ChainBufs *bufs_m, int *work_counters, int n_slots) {
     const int mi = blockIdx.y;
     const ChainBufs B = bufs_m[mi];
     const Cand *__restrict__ C = B.sorted;
-    const int n_work = work_counters[2 * mi];
+    const int *wc = work_counters + 4 * mi;
+    const int n_work = work_count(wc);
+    // States of a piece live at the piece's candidate range [a0, ...) of two arrays: rl = {right, left} (8 bytes: what the scan
+    // reads, four states per 32-byte sector) and det = {len*2+rev, index, index of the prefix maximum | cum, prefix maximum}.
+    int2 *__restrict__ rl = B.st_rl;
+    ChainSt *__restrict__ det = B.st;
     // piece
     int slot = 0;
     uint32_t k = 0, ce = 0;              // next candidate, end of the piece
-    ChainSt *st = nullptr;
-    int32_t *parg = nullptr;
-    int na = 0, head = 0, pm_arg = -1;
+    int a0 = 0, na = 0, head = 0, pm_arg = -1;   // first state (absolute index), visible / written states
     double pm_val = 0.0;
+    bool have_piece = false;
     // group (equal right end): its pending direct-strand state
     int grp_right = -1, bidx = -1, bleft = 0, blen = 0;
     double bc = 0.0;
     // candidate under evaluation
-    Cand g;
+    Cand g, gn;                          // gn: the next candidate of the piece, requested while g is evaluated
+    g.left = 0; g.right = 0; g.len = 1; g.strand = 1; g.flags = 0; g.orf = 0; g.total = 0.0;
+    gn = g;
     uint32_t gi = 0;
-    int sk = -1, best_idx = -1;
-    int4 s = make_int4(0, 0, 0, 0);        // state sk: right, left, len * 2 + rev, index
-    double2 sd = make_double2(0.0, 0.0);   //           cum, prefix maximum
+    int gp_pre = GPTR_UNSET;             // shared back-pointer of g's ORF (reverse strand), requested at fetch time
+    double fin_pm = 0.0;                 // prefix maximum / its index at the state the scan stopped at, requested when it stops
+    int fin_parg = -1;
+    int ak = -1;                         // absolute index of the state under examination (< a0: none left)
+    int2 cur[4], nxt[4];                 // the aligned group of four states holding ak, and the group below it (requested ahead)
+#pragma unroll
+    for (int u = 0; u < 4; u++) cur[u] = nxt[u] = make_int2(0, 0);
+    int ev_right = 0, best_idx = -1;
     double best_v = 0.0;
-    bool have_piece = false, scanning = false;
+    int want = W_FETCH;
 
     auto append = [&](int idx, double cum, int right, int left, int ls) {
         if (head == 0 || cum > pm_val) { pm_val = cum; pm_arg = idx; }
-        st[head].i = make_int4(right, left, ls, idx);
-        st[head].d = make_double2(cum, pm_val);
-        parg[head] = pm_arg;
+        rl[a0 + head] = make_int2(right, left);
+        det[a0 + head].i = make_int4(ls, idx, pm_arg, 0);
+        det[a0 + head].d = make_double2(cum, pm_val);
         head++;
+    };
+    auto advance = [&]() {   // the scan moves to the next older state
+        const bool cross = (ak & 3) == 0;
+        ak--;
+        if (cross) {
+#pragma unroll
+            for (int u = 0; u < 4; u++) cur[u] = nxt[u];
+            const int gb = (ak & ~3) - 4;
+            if (gb >= 0 && gb + 3 >= a0) load_group(rl, gb, nxt);
+        }
     };
 
     while (true) {
-        if (!scanning) {
-            if (have_piece && k >= ce) {   // piece finished
-                if (bidx >= 0) append(bidx, bc, grp_right, bleft, blen * 2);
-                B.gene_count[slot] = head > 0 ? pm_arg : -1;   // end of the best chain, until k_chain_trace
-                B.piece_total[slot] = head > 0 ? pm_val : 0.0;
-                have_piece = false;
+        const uint32_t m_fetch = __ballot_sync(0xffffffffu, want == W_FETCH);
+        const uint32_t m_scan = __ballot_sync(0xffffffffu, want == W_SCAN);
+        const uint32_t m_eval = __ballot_sync(0xffffffffu, want == W_EVAL);
+        const uint32_t m_final = __ballot_sync(0xffffffffu, want == W_FINAL);
+        if (!(m_fetch | m_scan | m_eval | m_final)) break;
+        int pick = W_FETCH, most = __popc(m_fetch);
+        if (__popc(m_scan) > most) { pick = W_SCAN; most = __popc(m_scan); }
+        if (__popc(m_final) > most) { pick = W_FINAL; most = __popc(m_final); }
+        if (__popc(m_eval) > most) pick = W_EVAL;   // (a section nobody wants must never be picked: the loop would spin)
+
+        if (pick == W_FETCH) {
+            if (want == W_FETCH) {
+                if (have_piece && k >= ce) {   // piece finished
+                    if (bidx >= 0) append(bidx, bc, grp_right, bleft, blen * 2);
+                    B.gene_count[slot] = head > 0 ? pm_arg : -1;   // end of the best chain, until k_chain_trace
+                    B.piece_total[slot] = head > 0 ? pm_val : 0.0;
+                    have_piece = false;
+                }
+                if (!have_piece) {
+                    const int item = atomicAdd(&work_counters[4 * mi + 1], 1);
+                    if (item >= n_work) want = W_DONE;
+                    else {
+                        slot = work_slot(B, wc, item, n_slots);
+                        const int64_t b_first = B.piece_b0[slot], b_last = B.piece_b1[slot];
+                        const uint32_t cs = b_first ? B.bend[b_first - 1] : 0u;
+                        ce = B.bend[b_last];   // > cs: k_chain_plan lists no empty piece
+                        k = cs;
+                        a0 = (int)cs;
+                        na = 0; head = 0; pm_val = 0.0; pm_arg = -1;
+                        grp_right = -1; bidx = -1;
+                        have_piece = true;
+                        gn = C[k];
+                    }
+                }
+                if (want != W_DONE) {
+                    g = gn;
+                    gi = k++;
+                    if (k < ce) gn = C[k];
+                    // only this thread writes the pointer of the ORFs of its piece, and not before this candidate is finished
+                    if (g.strand < 0 && !(g.flags & 8)) gp_pre = B.gptr[g.orf];
+                    if (g.right != grp_right) {
+                        if (bidx >= 0) { append(bidx, bc, grp_right, bleft, blen * 2); bidx = -1; }
+                        na = head;
+                        grp_right = g.right;
+                    } else if (g.strand < 0 && bidx >= 0) {
+                        append(bidx, bc, grp_right, bleft, blen * 2);
+                        bidx = -1;
+                    }
+                    ak = a0 + na - 1;
+                    best_v = 0.0;
+                    best_idx = -1;
+                    if (na > 0) {
+                        const int gb = ak & ~3;
+                        load_group(rl, gb, cur);
+                        if (gb - 4 >= 0 && gb - 1 >= a0) load_group(rl, gb - 4, nxt);
+                    }
+                    want = W_SCAN;
+                }
             }
-            if (!have_piece) {
-                const int item = atomicAdd(&work_counters[2 * mi + 1], 1);
-                if (item >= n_work) break;
-                slot = B.work[item];
-                const int64_t b_first = B.piece_b0[slot], b_last = B.piece_b1[slot];
-                const uint32_t cs = b_first ? B.bend[b_first - 1] : 0u;
-                ce = B.bend[b_last];
-                k = cs;
-                st = B.st + cs; parg = B.av_parg + cs;
-                na = 0; head = 0; pm_val = 0.0; pm_arg = -1;
-                grp_right = -1; bidx = -1;
-                have_piece = true;
-                if (k >= ce) continue;
+        } else if (pick == W_SCAN) {
+            // states whose right end lies inside the candidate, newest first (the rest of the group in registers, at most four a
+            // turn); one that starts before the candidate needs its penalty; the first that ends before it closes the scan
+#pragma unroll
+            for (int u = 3; u >= 0; u--) {
+                if (want == W_SCAN && (ak < a0 || (ak & 3) == u)) {
+                    const int2 e = cur[u];
+                    if (ak < a0 || e.x < g.left) {
+                        want = W_FINAL;
+                        if (ak >= a0) { fin_pm = det[ak].d.y; fin_parg = det[ak].i.z; }
+                    } else if (e.y < g.left) {
+                        want = W_EVAL;
+                        ev_right = e.x;
+                    } else advance();
+                }
             }
-            // next candidate
-            g = C[k];
-            gi = k++;
-            if (g.right != grp_right) {
-                if (bidx >= 0) { append(bidx, bc, grp_right, bleft, blen * 2); bidx = -1; }
-                na = head;
-                grp_right = g.right;
-            } else if (g.strand < 0 && bidx >= 0) {
-                append(bidx, bc, grp_right, bleft, blen * 2);
-                bidx = -1;
+        } else if (pick == W_EVAL) {
+            if (want == W_EVAL) {
+                const int4 di = det[ak].i;
+                const double v = det[ak].d.x - overlap_penalty(g.left, g.len, g.strand, ev_right, di.x >> 1, (di.x & 1) ? -1 : 1);
+                if (v >= best_v && v > 0.0) { best_v = v; best_idx = di.y; }   // descending index: ties go to the earliest state
+                advance();
+                want = W_SCAN;
             }
-            sk = na - 1;
-            best_v = 0.0;
-            best_idx = -1;
-            if (sk >= 0) { s = st[sk].i; sd = st[sk].d; }
-            scanning = true;
-        }
-        if (sk >= 0 && s.x >= g.left) {
-            // one state whose right end lies inside the candidate; its older neighbour is requested before the evaluation
-            const int pk = sk > 0 ? sk - 1 : 0;
-            const int4 nx = st[pk].i;
-            const double2 nd = st[pk].d;
-            if (s.y < g.left) {
-                const double v = sd.x - overlap_penalty(g.left, g.len, g.strand, s.x, s.z >> 1, (s.z & 1) ? -1 : 1);
-                if (v >= best_v && v > 0.0) { best_v = v; best_idx = s.w; }   // descending index: ties go to the earliest state
-            }
-            sk--;
-            s = nx;
-            sd = nd;
         } else {
-            // finish the candidate: best non-overlapping predecessor = prefix maximum at the first state ending before it
-            double b = 0.0;
-            int bp = -1;
-            if (sk >= 0 && sd.y > 0.0) { b = sd.y; bp = parg[sk]; }
-            const int bp_non = bp;
-            const bool over = best_idx >= 0 && best_v > b;   // an overlap wins only if strictly better
-            if (over) { b = best_v; bp = best_idx; }
-            const double cumg = g.total + b;
-            B.cum[gi] = cumg;
-            B.prev[gi] = bp;
-            if (g.strand > 0) {
-                if (bidx < 0 || cumg > bc) { bc = cumg; bidx = (int)gi; bleft = g.left; blen = g.len; }   // sorted by left: ties keep the smallest
-            } else {
-                int gp = (g.flags & 8) ? GPTR_UNSET : B.gptr[g.orf];   // the ORF's shared back-pointer (rule 6)
-                if (gp == GPTR_UNSET) gp = bp_non;
-                if (over) gp = bp;
-                B.gptr[g.orf] = gp;
-                append((int)gi, cumg, g.right, g.left, g.len * 2 + 1);
+            if (want == W_FINAL) {
+                // best non-overlapping predecessor = prefix maximum at the first state ending before the candidate
+                double b = 0.0;
+                int bp = -1;
+                if (ak >= a0 && fin_pm > 0.0) { b = fin_pm; bp = fin_parg; }
+                const int bp_non = bp;
+                const bool over = best_idx >= 0 && best_v > b;   // an overlap wins only if strictly better
+                if (over) { b = best_v; bp = best_idx; }
+                const double cumg = g.total + b;
+                B.cum[gi] = cumg;
+                B.prev[gi] = bp;
+                if (g.strand > 0) {
+                    if (bidx < 0 || cumg > bc) { bc = cumg; bidx = (int)gi; bleft = g.left; blen = g.len; }   // sorted by left: ties keep the smallest
+                } else {
+                    int gp = (g.flags & 8) ? GPTR_UNSET : gp_pre;   // the ORF's shared back-pointer (rule 6)
+                    if (gp == GPTR_UNSET) gp = bp_non;
+                    if (over) gp = bp;
+                    B.gptr[g.orf] = gp;
+                    append((int)gi, cumg, g.right, g.left, g.len * 2 + 1);
+                }
+                want = W_FETCH;
             }
-            scanning = false;
         }
     }
 }
 
 // traceback of every piece (reverse-strand genes follow their ORF's shared pointer): thread per piece, the candidate and
 // back-pointer loads of half a million pieces in flight at once
-__global__ void __launch_bounds__(128) k_chain_trace(const ChainBufs *bufs_m, const int *work_counters) {
+__global__ void __launch_bounds__(128) k_chain_trace(const ChainBufs *bufs_m, const int *work_counters, int n_slots) {
     const int mi = blockIdx.y;
     const ChainBufs B = bufs_m[mi];
-    const int n_work = work_counters[2 * mi];
+    const int n_work = work_count(work_counters + 4 * mi);
     const int item = blockIdx.x * blockDim.x + threadIdx.x;
     if (item >= n_work) return;
-    const int slot = B.work[item];
+    const int slot = work_slot(B, work_counters + 4 * mi, item, n_slots);
     const int64_t b_first = B.piece_b0[slot], b_last = B.piece_b1[slot];
     const uint32_t cs = b_first ? B.bend[b_first - 1] : 0u;
     const uint32_t ce = B.bend[b_last];
@@ -2695,12 +2775,12 @@ void launch_scatter(const Cand *const *surv_m, Cand *const *sorted_m, uint32_t *
 }
 
 // diagnostic (MGCOD_B200_PIECE_STATS): log2 histogram of candidates per chain piece of model 0; hist[32] = largest piece, hist[33] = pieces
-__global__ void k_piece_stats(const ChainBufs *bufs_m, const int *work_counters, unsigned int *hist) {
+__global__ void k_piece_stats(const ChainBufs *bufs_m, const int *work_counters, int n_slots, unsigned int *hist) {
     const ChainBufs B = bufs_m[0];
-    const int n_work = work_counters[0];
+    const int n_work = work_count(work_counters);
     const int item = blockIdx.x * blockDim.x + threadIdx.x;
     if (item >= n_work) return;
-    const int slot = B.work[item];
+    const int slot = work_slot(B, work_counters, item, n_slots);
     const int64_t b_first = B.piece_b0[slot], b_last = B.piece_b1[slot];
     const uint32_t n = B.bend[b_last] - (b_first ? B.bend[b_first - 1] : 0u);
     atomicAdd(&hist[n ? 32 - __clz(n) : 0], 1u);
@@ -2708,7 +2788,7 @@ __global__ void k_piece_stats(const ChainBufs *bufs_m, const int *work_counters,
     atomicAdd(&hist[33], 1u);
 }
 void launch_piece_stats(const ChainBufs *bufs_m, const int *work_counters, int32_t n_slots, unsigned int *hist, cudaStream_t st) {
-    k_piece_stats<<<(unsigned)((n_slots + 127) / 128), 128, 0, st>>>(bufs_m, work_counters, hist);
+    k_piece_stats<<<(unsigned)((n_slots + 127) / 128), 128, 0, st>>>(bufs_m, work_counters, n_slots, hist);
 }
 
 int launch_chain(const ChainBufs *bufs_m, const Cand *const *scattered_m, Cand *const *ordered_m, const int64_t *cwoff, const int32_t *clen,
@@ -2717,9 +2797,12 @@ int launch_chain(const ChainBufs *bufs_m, const Cand *const *scattered_m, Cand *
     k_bucket_order<<<dim3((unsigned)n_sm * 8, n_models), 256, 0, st>>>(bufs_m, scattered_m, ordered_m, cwoff, n_buckets);
     k_chain_plan<<<dim3((unsigned)((n_slots + 127) / 128), n_models), 128, 0, st>>>(bufs_m, cwoff, clen, slotbase, slot_contig, n_slots,
                                                                                      work_counters);
-    if (warp_per_piece) k_chain<<<dim3((unsigned)n_sm * 16, n_models), 128, 0, st>>>(bufs_m, work_counters);
-    else k_chain_flat<<<dim3((unsigned)n_sm * 8, n_models), 128, 0, st>>>(bufs_m, work_counters);
-    k_chain_trace<<<dim3((unsigned)((n_slots + 127) / 128), n_models), 128, 0, st>>>(bufs_m, work_counters);
+    // grids sized so that the blocks of ALL models are resident together: a model's pieces then share the machine for the whole
+    // kernel instead of four runs one after the other, each ending on its longest piece
+    const unsigned per_model = (unsigned)std::max(1, n_sm * 8 / std::max(1, n_models));
+    if (warp_per_piece) k_chain<<<dim3(per_model * 2, n_models), 128, 0, st>>>(bufs_m, work_counters, n_slots);
+    else k_chain_flat<<<dim3(per_model, n_models), 128, 0, st>>>(bufs_m, work_counters, n_slots);
+    k_chain_trace<<<dim3((unsigned)((n_slots + 127) / 128), n_models), 128, 0, st>>>(bufs_m, work_counters, n_slots);
     return 4;
 }
 

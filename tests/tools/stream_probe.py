@@ -24,3 +24,16 @@ for it in range(4):
     eng.upload(buf, offs); dd = time.perf_counter()
     print(f"stream: prefetch {1e3*(b-a):.1f} decode {1e3*(c-b):.1f} adopt {1e3*(dd-c):.1f} dev_total {st['total']:.1f} "
           + " ".join(f"{k}={st[k]:.1f}" for k in ("pack", "orf_find", "orf_prep", "orf_score", "orf_final", "chain", "d2h")))
+# the loop bench.py times as e2e: the generator, the scores read, the result dropped at once
+marks = []
+def batches(n):
+    for _ in range(n):
+        yield buf, offs
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+for res in eng.decode_stream(batches(5)):
+    a = time.perf_counter(); cents = res.model_cents(); b = time.perf_counter(); del res; c = time.perf_counter()
+    marks.append((a - t0, b - a, c - b))
+    t0 = time.perf_counter()
+torch.cuda.synchronize()
+print("generator loop: " + "; ".join(f"step {1e3*x:.1f} cents {1e3*y:.2f} free {1e3*z:.2f}" for x, y, z in marks), f"tail {1e3*(time.perf_counter()-t0):.1f}")
