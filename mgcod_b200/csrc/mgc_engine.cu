@@ -210,6 +210,7 @@ struct mgc_engine {
     int pair_smem = 0;     // bytes of the pair walk's shared-memory table; 0 = single-position walk (order 5, or MGCOD_B200_WALK=single)
     DevBuf counters;     // [M][8] unsigned long long: 0 orfs, 1 starts
     DevBuf surv_counters;  // [M]
+    PinnedPool::Block table_stage;   // page-locked staging of the slot tables (set_slots)
     DevBuf work_counters;  // [M][4] int: long pieces, consumers' cursor, other pieces, unused
     bool chain_warp = false;  // MGCOD_B200_CHAIN=warp: the warp-per-piece chain kernel of round 1 (A/B measurements, tests)
     DevBuf model_cents;    // [M]
@@ -648,17 +649,33 @@ void set_slots(mgc_engine *e) {
     e->slotbase.ensure((size_t)(n + 1) * 4);
     e->slot_contig.ensure((size_t)e->n_slots * 4 + 16);
     cudaStream_t st = e->stream;
-    CUDA_TRY(cudaMemcpyAsync(e->slotbase.p, slotbase.data(), (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(e->slot_contig.p, slot_contig.data(), (size_t)e->n_slots * 4, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(e->aoff.p, e->h_aoff.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(e->cwoff.p, e->h_cwoff.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(e->clen.p, e->h_clen.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(e->cflags.p, cflags.data(), (size_t)n, cudaMemcpyHostToDevice, st));
+    // the six tables go through one page-locked staging block kept by the engine: a copy from pageable memory waits for the
+    // previous result's device-to-host copy (2 ms per step of a stream of batches), a page-locked one is queued at once
+    {
+        struct Part { void *dst; const void *src; size_t bytes; };
+        const Part parts[6] = {{e->slotbase.p, slotbase.data(), (size_t)(n + 1) * 4}, {e->slot_contig.p, slot_contig.data(), (size_t)e->n_slots * 4},
+                               {e->aoff.p, e->h_aoff.data(), (size_t)(n + 1) * 8},     {e->cwoff.p, e->h_cwoff.data(), (size_t)(n + 1) * 8},
+                               {e->clen.p, e->h_clen.data(), (size_t)n * 4},           {e->cflags.p, cflags.data(), (size_t)n}};
+        size_t total = 0;
+        for (const Part &q : parts) total += (q.bytes + 63) / 64 * 64;
+        if (e->table_stage.bytes < total) {
+            e->pool->release(e->table_stage);
+            e->table_stage = e->pool->acquire(total);
+        }
+        size_t at = 0;
+        for (const Part &q : parts) {
+            if (!q.bytes) continue;
+            std::memcpy(static_cast<char *>(e->table_stage.p) + at, q.src, q.bytes);
+            CUDA_TRY(cudaMemcpyAsync(q.dst, static_cast<char *>(e->table_stage.p) + at, q.bytes, cudaMemcpyHostToDevice, st));
+            at += (q.bytes + 63) / 64 * 64;
+        }
+    }
     launch_groups(e->cwoff.as<int64_t>(), n, e->W / 4, e->grp2contig.as<int32_t>(), st);
     const double t3 = now_ms();
     CUDA_TRY(cudaStreamSynchronize(st));  // cflags and the slot tables are local staging buffers
     CUDA_TRY(cudaGetLastError());
-    if (trace) std::fprintf(stderr, "set_slots: tables %.2f ms, ensure %.2f ms, uploads %.2f ms, sync %.2f ms\n", t1 - t0, t2 - t1, t3 - t2, now_ms() - t3);
+    const double t4 = now_ms();
+    if (trace) std::fprintf(stderr, "set_slots: tables %.2f ms, ensure %.2f ms, uploads %.2f ms, sync %.2f ms (entered %.3f, left %.3f)\n", t1 - t0, t2 - t1, t3 - t2, t4 - t3, t0, t4);
 }
 
 void do_upload(mgc_engine *e, const char *seq, const int64_t *offsets, int32_t n) {
@@ -702,8 +719,8 @@ void do_upload(mgc_engine *e, const char *seq, const int64_t *offsets, int32_t n
     const double tu3 = now_ms();
     CUDA_TRY(cudaEventRecord(e->ev[1], st));
     CUDA_TRY(cudaStreamSynchronize(st));
-    if (trace) std::fprintf(stderr, "do_upload: host tables + letters queued %.2f ms, lengths queued %.2f ms, set_slots %.2f ms, sync %.2f ms (adopted %d)\n",
-                            tu1 - tu0, tu2 - tu1, tu3 - tu2, now_ms() - tu3, (int)adopted);
+    if (trace) std::fprintf(stderr, "do_upload: host tables + letters queued %.2f ms, lengths queued %.2f ms, set_slots %.2f ms, sync %.2f ms (adopted %d; set_slots called %.3f, back %.3f)\n",
+                            tu1 - tu0, tu2 - tu1, tu3 - tu2, now_ms() - tu3, (int)adopted, tu2, tu3);
     float ms = 0;
     cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]);
     e->stats = mgc_stats();
@@ -1096,6 +1113,7 @@ void mgc_engine_destroy(mgc_engine *e) {
                       &e->t_unit_off, &e->t_sums, &e->ascii_next, &e->slotbase, &e->slot_contig, &e->nm, &e->ncount, &e->codon, &e->cflags, &e->plen, &e->gaps, &e->gap_count, &e->unit_totals, &e->next_unit, &e->win_stride, &e->win_off, &e->win_labels, &e->win_cents, &e->win_merged, &e->win_run, &e->win_status, &e->win_hist})
         b->release();
     for (auto &ev : e->ev) cudaEventDestroy(ev);
+    e->pool->release(e->table_stage);
     e->pool->release(e->win_host);   // back to the pool, which frees its blocks with the last result / engine holding it
     e->win_host = PinnedPool::Block();
     if (e->last_ready) e->last_ready->wait();
@@ -1463,7 +1481,8 @@ int mgc_isoform_labels(mgc_engine *e, const int32_t *stride, int32_t n_contigs, 
         const size_t o_cen = (o_sta + (size_t)std::max(n, 1) * 4 + 15) & ~(size_t)15;
         const size_t need = o_cen + (cents ? (size_t)nw1 * M * 8 : 0);
         if (e->win_host.bytes < need) {
-            e->pool->release(e->win_host);
+            e->pool->release(e->table_stage);
+    e->pool->release(e->win_host);
             e->win_host = PinnedPool::Block();
             e->win_host = e->pool->acquire(need);
         }

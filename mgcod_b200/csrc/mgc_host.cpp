@@ -3,6 +3,9 @@
 // Writers reproduce gmhmmp2's Output::PrintGenes_GFF / PrintGenes_LST byte for byte except for the
 // date lines (format strings: SURVEY.md §8b, pinned by tests/golden).  The reference reads the GFF
 // back with pandas (bin/data.py:66-96) and caches it on disk (bin/data.py:39).
+#include <fcntl.h>
+#include <unistd.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -50,21 +53,68 @@ namespace {
 
 // Append-only text buffer flushed to a FILE in large blocks: the gene lines are formatted by hand (decimal integers and
 // "%.2f" with an exact fallback), which is ~6x faster than one fprintf per field for the ~100 bytes per gene.
+// Text buffers are kept for the next file of the process (up to kTextCacheMax bytes): a fresh 8 MB block costs its page
+// faults again — more than formatting into it (python -m mgcod_b200.multi writes four files per genome).
+struct TextBlocks {
+    struct Block { char *p; size_t bytes; };
+    std::mutex mu;
+    std::vector<Block> free_blocks;
+    size_t cached = 0;
+    static constexpr size_t kTextCacheMax = (size_t)512 << 20;
+    char *acquire(size_t need, size_t *got) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            size_t best = free_blocks.size();
+            for (size_t i = 0; i < free_blocks.size(); i++)
+                if (free_blocks[i].bytes >= need && (best == free_blocks.size() || free_blocks[i].bytes < free_blocks[best].bytes)) best = i;
+            if (best != free_blocks.size()) {
+                const Block b = free_blocks[best];
+                free_blocks.erase(free_blocks.begin() + best);
+                cached -= b.bytes;
+                *got = b.bytes;
+                return b.p;
+            }
+        }
+        *got = need + need / 8;
+        return static_cast<char *>(std::malloc(*got));   // never zero-filled: the formatting thread touches its own pages first
+    }
+    void release(char *p, size_t bytes) {
+        if (!p) return;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            if (cached + bytes <= kTextCacheMax) {
+                free_blocks.push_back(Block{p, bytes});
+                cached += bytes;
+                return;
+            }
+        }
+        std::free(p);
+    }
+};
+TextBlocks &text_blocks() {
+    static TextBlocks *b = new TextBlocks();
+    return *b;
+}
+
 struct TextOut {
     FILE *f;
-    char *buf = nullptr;      // malloc'ed, never zero-filled: formatting threads touch their own pages first
+    char *buf = nullptr;
     size_t cap = 0, n = 0;
     explicit TextOut(FILE *fp, size_t reserve = 1 << 22) : f(fp), cap(reserve) {}
     TextOut(TextOut &&o) noexcept : f(o.f), buf(o.buf), cap(o.cap), n(o.n) { o.buf = nullptr; }
     TextOut(const TextOut &) = delete;
-    ~TextOut() { std::free(buf); }
+    ~TextOut() { text_blocks().release(buf, cap); }
     void room(size_t need) {
-        if (!buf) buf = static_cast<char *>(std::malloc(cap = std::max(cap, need)));
+        if (!buf) buf = text_blocks().acquire(std::max(cap, need), &cap);
         if (n + need <= cap) return;
         if (f) flush();
         if (n + need > cap) {     // memory-only mode (f == nullptr): grow
-            cap = std::max(cap * 2, n + need);
-            buf = static_cast<char *>(std::realloc(buf, cap));
+            size_t got = 0;
+            char *nb = text_blocks().acquire(std::max(cap * 2, n + need), &got);
+            std::memcpy(nb, buf, n);
+            text_blocks().release(buf, cap);
+            buf = nb;
+            cap = got;
         }
     }
     void flush() {
@@ -87,6 +137,38 @@ struct TextOut {
     }
     void i64(long long v) {
         if (v < 0) { ch('-'); u64((unsigned long long)(-v)); } else u64((unsigned long long)v);
+    }
+    // --- unchecked appends for a line whose maximum length was reserved with line(): the gene lines are ~25 small pieces each,
+    // and a capacity test per piece costs more than the formatting ---
+    char *line(size_t max_len) { room(max_len); return buf + n; }
+    void done(char *end) { n = (size_t)(end - buf); }
+    static char *put(char *p, const char *s, size_t len) { std::memcpy(p, s, len); return p + len; }
+    static char *put_u64(char *p, unsigned long long v) {
+        static const char digits[201] =
+            "00010203040506070809101112131415161718192021222324252627282930313233343536373839404142434445464748495051525354555657585960616263646566676869707172737475767778798081828384858687888990919293949596979899";
+        char t[24];
+        int k = 24;
+        while (v >= 100) { const unsigned d = (unsigned)(v % 100) * 2; v /= 100; t[--k] = digits[d + 1]; t[--k] = digits[d]; }
+        if (v >= 10) { const unsigned d = (unsigned)v * 2; t[--k] = digits[d + 1]; t[--k] = digits[d]; }
+        else t[--k] = (char)('0' + v);
+        std::memcpy(p, t + k, (size_t)(24 - k));
+        return p + (24 - k);
+    }
+    static char *put_i64(char *p, long long v) {
+        if (v < 0) { *p++ = '-'; return put_u64(p, (unsigned long long)(-v)); }
+        return put_u64(p, (unsigned long long)v);
+    }
+    static char *put_fixed2(char *p, double v) {   // as fixed2() below
+        const double a = std::fabs(v) * 100.0;
+        const double fl = std::floor(a), fr = a - fl;
+        if (!(a < 9e15) || std::fabs(fr - 0.5) < 1e-6) return p + std::snprintf(p, 64, "%.2f", v);
+        const unsigned long long r = (unsigned long long)fl + (fr > 0.5 ? 1ull : 0ull);
+        if (std::signbit(v)) *p++ = '-';
+        p = put_u64(p, r / 100);
+        *p++ = '.';
+        *p++ = (char)('0' + (r / 10) % 10);
+        *p++ = (char)('0' + r % 10);
+        return p;
     }
     // printf("%.2f"): exact unless v*100 lies within 1e-6 of a rounding boundary, where snprintf decides
     void fixed2(double v) {
@@ -119,16 +201,13 @@ int mgc_write_gff(const mgc_result *r, int model, const char *const *contig_ids,
     const mgc_gene *genes = mgc_result_genes(r, model);
     const double *totals = mgc_result_contig_totals(r, model);
     const long long min_len = mgc_result_min_gene_length(r, model);
-    FILE *f = std::fopen(out_path, "w");
-    if (!f) return mgc::set_error(MGC_E_IO, std::string("cannot open output file: ") + out_path);
     const std::string date = now_string();
-    if (lst) std::fprintf(f, "# GeneMark.hmm-2 LST format\n");
-    else std::fprintf(f, "##gff-version 2\n");
-    std::fprintf(f, "# GeneMark.hmm-2 prokaryotic version: 1.17\n");
-    std::fprintf(f, "# File with sequence: %s\n", seq_file_name ? seq_file_name : "");
-    std::fprintf(f, "# File with MetaGeneMark parameters: %s\n", mod_file_name ? mod_file_name : "");
-    std::fprintf(f, "# translation table: %d\n", gcode);
-    std::fprintf(f, "# output date start: %s\n", date.c_str());
+    std::string head = lst ? "# GeneMark.hmm-2 LST format\n" : "##gff-version 2\n";
+    head += "# GeneMark.hmm-2 prokaryotic version: 1.17\n";
+    head += std::string("# File with sequence: ") + (seq_file_name ? seq_file_name : "") + "\n";
+    head += std::string("# File with MetaGeneMark parameters: ") + (mod_file_name ? mod_file_name : "") + "\n";
+    head += "# translation table: " + std::to_string(gcode) + "\n";
+    head += "# output date start: " + date + "\n";
     // The records are formatted by several threads, each a contiguous range of contigs with about the same number of genes,
     // into memory; the pieces are written in order.  gene_id counts across records, so a piece starts at 1 + the number of
     // genes in front of it (the table is ordered by contig).
@@ -181,10 +260,14 @@ int mgc_write_gff(const mgc_result *r, int model, const char *const *contig_ids,
                                                 g.partial_left ? '<' : ' ', g.left, g.partial_right ? '>' : ' ', g.right, len, type);
                     o.str(tmp, (size_t)n);
                 } else {
-                    o.str(id, idlen); o.str("\tGeneMark.hmm2\tCDS\t"); o.i64(g.left); o.ch('\t'); o.i64(g.right); o.ch('\t'); o.fixed2(g.logodd);
-                    o.ch('\t'); o.ch(g.strand > 0 ? '+' : '-'); o.str("\t0\tgene_id "); o.i64(gene_id); o.str("; gene_type "); o.str(type); o.str("; ");
-                    if (g.partial_left || g.partial_right) { o.str("partial "); o.ch(g.partial_left ? '1' : '0'); o.ch(g.partial_right ? '1' : '0'); o.str("; "); }
-                    o.str("gc "); o.i64(g.gc); o.str("; length "); o.i64(len); o.str(";\n");
+                    char *q = o.line(idlen + 256);
+                    q = TextOut::put(q, id, idlen); q = TextOut::put(q, "\tGeneMark.hmm2\tCDS\t", sizeof("\tGeneMark.hmm2\tCDS\t") - 1); q = TextOut::put_i64(q, g.left); *q++ = '\t';
+                    q = TextOut::put_i64(q, g.right); *q++ = '\t'; q = TextOut::put_fixed2(q, g.logodd);
+                    *q++ = '\t'; *q++ = g.strand > 0 ? '+' : '-'; q = TextOut::put(q, "\t0\tgene_id ", sizeof("\t0\tgene_id ") - 1); q = TextOut::put_i64(q, gene_id);
+                    q = g.domain ? TextOut::put(q, "; gene_type archaea; ", sizeof("; gene_type archaea; ") - 1) : TextOut::put(q, "; gene_type bacteria; ", sizeof("; gene_type bacteria; ") - 1);
+                    if (g.partial_left || g.partial_right) { q = TextOut::put(q, "partial ", sizeof("partial ") - 1); *q++ = g.partial_left ? '1' : '0'; *q++ = g.partial_right ? '1' : '0'; q = TextOut::put(q, "; ", sizeof("; ") - 1); }
+                    q = TextOut::put(q, "gc ", sizeof("gc ") - 1); q = TextOut::put_i64(q, g.gc); q = TextOut::put(q, "; length ", sizeof("; length ") - 1); q = TextOut::put_i64(q, len); q = TextOut::put(q, ";\n", sizeof(";\n") - 1);
+                    o.done(q);
                 }
                 k++;
             }
@@ -208,11 +291,25 @@ int mgc_write_gff(const mgc_result *r, int model, const char *const *contig_ids,
         for (auto &th : pool) th.join();
     }
     const double t1 = now();
-    for (int t = 0; t < pieces; t++)
-        if (outs[t].n) std::fwrite(outs[t].buf, 1, outs[t].n, f);
-    if (trace) std::fprintf(stderr, "write_gff: %d pieces, format %.2f ms, fwrite %.2f ms\n", pieces, t1 - t0, now() - t1);
-    if (lst) std::fprintf(f, "\n# output date end: %s\n# Done with file: %s\n", date.c_str(), seq_file_name ? seq_file_name : "");
-    if (std::fclose(f) != 0) return mgc::set_error(MGC_E_IO, "write failed");
+    // plain write(2) of header, pieces, footer (buffered writes to ONE file are serialised by the kernel: writing the pieces
+    // side by side with pwrite was slower; the four files of a run are written side by side by their callers)
+    std::string foot;
+    if (lst) foot = "\n# output date end: " + date + "\n# Done with file: " + (seq_file_name ? seq_file_name : "") + "\n";
+    const int fd = ::open(out_path, O_WRONLY | O_CREAT | O_TRUNC, 0666);
+    if (fd < 0) return mgc::set_error(MGC_E_IO, std::string("cannot open output file: ") + out_path);
+    auto put_all = [fd](const char *p, size_t n) {
+        while (n) {
+            const ssize_t k = ::write(fd, p, n);
+            if (k <= 0) return false;
+            p += k; n -= (size_t)k;
+        }
+        return true;
+    };
+    bool ok = put_all(head.data(), head.size());
+    for (int t = 0; t < pieces && ok; t++) ok = put_all(outs[t].buf, outs[t].n);
+    ok = ok && put_all(foot.data(), foot.size());
+    if (trace) std::fprintf(stderr, "write_gff: %d pieces, format %.2f ms, write %.2f ms\n", pieces, t1 - t0, now() - t1);
+    if (::close(fd) != 0 || !ok) return mgc::set_error(MGC_E_IO, "write failed");
     return MGC_OK;
 }
 
