@@ -700,6 +700,13 @@ void do_upload(mgc_engine *e, const char *seq, const int64_t *offsets, int32_t n
     e->h_parent_aoff[n] = a1 - a0;
     cudaStream_t st = e->stream;
     e->plen.ensure((size_t)n * 4 + 16);
+    {   // a kernel first: an event recorded as the first operation after the last step's read-back copies would wait for the
+        // previous result's device-to-host copy (see run_pipeline)
+        ClearList cl;
+        e->flags.ensure(64);
+        cl.add(e->flags.p, 64);
+        launch_clear(cl, 1, st);
+    }
     CUDA_TRY(cudaEventRecord(e->ev[0], st));
     const bool adopted = e->pending.valid && e->pending.seq == seq && (int32_t)e->pending.offsets.size() == n + 1 &&
                          std::memcmp(e->pending.offsets.data(), offsets, (size_t)(n + 1) * 8) == 0;
@@ -737,26 +744,38 @@ mgc_result *run_pipeline(mgc_engine *e, bool *amb_out) {
     const int64_t W = e->W, nb = W / 4;
     cudaStream_t st = e->stream;
     int launches = 0;
+    const bool trace = std::getenv("MGCOD_TRACE") != nullptr;
+    const double tp0 = now_ms();
     float h2d = e->stats.h2d;
     e->stats = mgc_stats();
     e->stats.h2d = h2d;
     e->have_genes = false;
 
-    CUDA_TRY(cudaEventRecord(e->ev[0], st));
-    CUDA_TRY(cudaMemsetAsync(e->flags.p, 0, 64, st));
-    CUDA_TRY(cudaMemsetAsync(e->counters.p, 0, (size_t)M * 64, st));
-    CUDA_TRY(cudaMemsetAsync(e->surv_counters.p, 0, (size_t)M * 8, st));
-    CUDA_TRY(cudaMemsetAsync(e->work_counters.p, 0, (size_t)M * 16, st));
-    CUDA_TRY(cudaMemsetAsync(e->model_cents.p, 0, (size_t)M * 8, st));
-    CUDA_TRY(cudaMemsetAsync(e->next_unit.p, 0, 16, st));
-    for (int i = 0; i < M; i++) {
-        CUDA_TRY(cudaMemsetAsync(e->pm[i].gene_count.p, 0, (size_t)(e->n_slots + 1) * 4, st));
-        CUDA_TRY(cudaMemsetAsync(e->pm[i].piece_total.p, 0, (size_t)(e->n_slots + 1) * 8, st));
-        CUDA_TRY(cudaMemsetAsync(e->pm[i].piece_b1.p, 0xff, (size_t)(e->n_slots + 1) * 4, st));  // -1 = slot not used
-        CUDA_TRY(cudaMemsetAsync(e->pm[i].bcount.p, 0, (size_t)(nb + 8) * 4, st));
-        CUDA_TRY(cudaMemsetAsync(e->pm[i].cover.p, 0, (size_t)(nb + 8) * 4, st));
-        CUDA_TRY(cudaMemsetAsync(e->pm[i].hist.p, 0, e->pm[i].hist.bytes, st));
+    {
+        ClearList cl;   // one kernel instead of 30 cudaMemsetAsync calls (which run on a copy engine, behind the previous result's read-back)
+        cl.add(e->flags.p, 64);
+        cl.add(e->counters.p, (size_t)M * 64);
+        cl.add(e->surv_counters.p, (size_t)M * 8);
+        cl.add(e->work_counters.p, (size_t)M * 16);
+        cl.add(e->model_cents.p, (size_t)M * 8);
+        cl.add(e->next_unit.p, 16);
+        for (int i = 0; i < M; i++) {
+            cl.add(e->pm[i].gene_count.p, (size_t)(e->n_slots + 1) * 4);
+            cl.add(e->pm[i].piece_total.p, (size_t)(e->n_slots + 1) * 8);
+            cl.add(e->pm[i].piece_b1.p, (size_t)(e->n_slots + 1) * 4, 0xffffffffu);  // -1 = slot not used
+            cl.add(e->pm[i].bcount.p, (size_t)(nb + 8) * 4);
+            cl.add(e->pm[i].cover.p, (size_t)(nb + 8) * 4);
+            cl.add(e->pm[i].hist.p, e->pm[i].hist.bytes);
+        }
+        if (cl.n >= ClearList::kMax) throw std::runtime_error("clear list too small");
+        launch_clear(cl, e->n_sm, st);
+        launches += 1;
     }
+    // The step's first event is recorded AFTER its first kernel.  The stream's previous operation was the small read-back copy of
+    // the last step, and an event record on an otherwise idle stream is queued to the engine the stream used last — the
+    // device-to-host copy engine, busy for 3 ms with the previous result's gene tables on the copy-out stream: every kernel of the
+    // step then started 3 ms late (measured with cudaEventQuery polling; a clear of 260 MB takes 0.1 ms and is not in `pack`).
+    CUDA_TRY(cudaEventRecord(e->ev[0], st));
     // pack + GC prefix
     launch_pack(e->ascii.as<char>() + PACK_SLACK, e->aoff.as<int64_t>(), e->cwoff.as<int64_t>(), e->clen.as<int32_t>(),
                 e->grp2contig.as<int32_t>(), W, e->lo.as<uint32_t>(), e->hi.as<uint32_t>(), e->nm.as<uint32_t>(), e->gc.as<uint32_t>(),
@@ -849,6 +868,14 @@ mgc_result *run_pipeline(mgc_engine *e, bool *amb_out) {
     CUDA_TRY(cudaEventRecord(e->ev[6], st));
 
     // small read-backs
+    const double tp1 = now_ms();
+    double tq0 = 0, tq6 = 0;
+    if (trace) {   // when do the first and the last event of the step fire (host clock)?
+        while (cudaEventQuery(e->ev[0]) == cudaErrorNotReady) {}
+        tq0 = now_ms();
+        while (cudaEventQuery(e->ev[6]) == cudaErrorNotReady) {}
+        tq6 = now_ms();
+    }
     std::vector<unsigned long long> h_counters((size_t)M * 8), h_surv(M);
     std::vector<uint32_t> h_gtot(M);
     std::vector<long long> h_cents(M);
@@ -860,6 +887,7 @@ mgc_result *run_pipeline(mgc_engine *e, bool *amb_out) {
     CUDA_TRY(cudaMemcpyAsync(h_flags, e->flags.p, 64, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaGetLastError());
+    const double tp2 = now_ms();
     if (h_flags[0]) throw AlphabetError("error, unexpected letter found in FASTA sequence (accepted: ACGTU and the IUPAC codes RYSWKMBDHVN)");
     *amb_out = h_flags[1] != 0;
     for (int i = 0; i < M; i++) {
@@ -912,6 +940,9 @@ mgc_result *run_pipeline(mgc_engine *e, bool *amb_out) {
     e->stats.kernel_launches = launches;
     e->have_genes = true;
     e->dev_gene_count.assign(h_gtot.begin(), h_gtot.end());
+    if (trace) std::fprintf(stderr, "run_pipeline: entered %.3f, all launched +%.2f ms, device done +%.2f ms, result queued +%.2f ms, first event +%.2f ms, last event +%.2f ms (device %.2f ms: pack %.2f find %.2f prep %.2f walk %.2f final %.2f order %.2f chain %.2f aggregate %.2f)\n",
+                            tp0, tp1 - tp0, tp2 - tp0, now_ms() - tp0, tq0 - tp0, tq6 - tp0, e->stats.total, e->stats.pack, e->stats.orf_find, e->stats.orf_prep, e->stats.orf_score,
+                            e->stats.orf_final, e->stats.order, e->stats.chain, e->stats.aggregate);
     return res.release();
 }
 

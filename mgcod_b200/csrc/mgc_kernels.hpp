@@ -54,6 +54,18 @@ void launch_final(Planes pl, const int64_t *cwoff, const int32_t *clen, const De
 void launch_scatter(const Cand *const *surv_m, Cand *const *sorted_m, uint32_t *const *boff_m,
                     const unsigned long long *surv_counters, const int64_t *cwoff, uint32_t cap_surv, int n_models, int n_sm,
                     cudaStream_t st);
+// regions cleared by one k_clear launch (whole 32-bit words, 16-byte aligned bases)
+struct ClearList {
+    static constexpr int kMax = 64;
+    void *ptr[kMax];
+    size_t words[kMax];
+    uint32_t value[kMax];
+    int n = 0;
+    void add(void *p, size_t bytes, uint32_t v = 0) {
+        if (n < kMax && bytes) { ptr[n] = p; words[n] = (bytes + 3) / 4; value[n] = v; n++; }
+    }
+};
+void launch_clear(const ClearList &list, int n_sm, cudaStream_t st);
 void launch_piece_stats(const ChainBufs *bufs_m, const int *work_counters, int32_t n_slots, unsigned int *hist, cudaStream_t st);
 int launch_chain(const ChainBufs *bufs_m, const Cand *const *scattered_m, Cand *const *ordered_m, const int64_t *cwoff, const int32_t *clen,
                  const int32_t *slotbase, const int32_t *slot_contig, int32_t n_slots, int64_t n_buckets, int *work_counters, int n_models,

@@ -37,3 +37,12 @@ for res in eng.decode_stream(batches(5)):
     t0 = time.perf_counter()
 torch.cuda.synchronize()
 print("generator loop: " + "; ".join(f"step {1e3*x:.1f} cents {1e3*y:.2f} free {1e3*z:.2f}" for x, y, z in marks), f"tail {1e3*(time.perf_counter()-t0):.1f}")
+# device-resident loop as bench.py times it
+eng.upload(buf, offs)
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+for _ in range(4):
+    a = time.perf_counter(); res = eng.decode_resident(); b = time.perf_counter(); del res
+    print(f"resident: decode_resident {1e3*(b-a):.2f} ms, free {1e3*(time.perf_counter()-b):.2f} ms", file=sys.stderr)
+torch.cuda.synchronize()
+print(f"resident loop: {1e3*(time.perf_counter()-t0)/4:.2f} ms per step")
