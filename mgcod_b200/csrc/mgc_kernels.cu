@@ -2285,19 +2285,42 @@ __global__ void __launch_bounds__(128, CHAIN_MINB) k_chain_flat(const ChainBufs 
                 }
             }
         } else if (pick == W_SCAN) {
-            // states whose right end lies inside the candidate, newest first (the rest of the group in registers, at most four a
-            // turn); one that starts before the candidate needs its penalty; the first that ends before it closes the scan
+            // States whose right end lies inside the candidate, newest first, a group of four per turn: one comparison mask for
+            // "ends before the candidate" (closes the scan) and one for "starts before it" (needs its penalty); the highest flagged
+            // entry at or below ak decides, a group without flags is skipped whole (most states are nested inside the candidate).
+            if (want == W_SCAN) {
+                if (ak < a0) want = W_FINAL;
+                else {
+                    const int gb = ak & ~3;
+                    uint32_t ends = 0, ovl = 0;
 #pragma unroll
-            for (int u = 3; u >= 0; u--) {
-                if (want == W_SCAN && (ak < a0 || (ak & 3) == u)) {
-                    const int2 e = cur[u];
-                    if (ak < a0 || e.x < g.left) {
-                        want = W_FINAL;
-                        if (ak >= a0) { fin_pm = det[ak].d.y; fin_parg = det[ak].i.z; }
-                    } else if (e.y < g.left) {
-                        want = W_EVAL;
-                        ev_right = e.x;
-                    } else advance();
+                    for (int u = 0; u < 4; u++) {
+                        ends |= (uint32_t)(cur[u].x < g.left) << u;
+                        ovl |= (uint32_t)(cur[u].y < g.left) << u;
+                    }
+                    uint32_t valid = (2u << (ak & 3)) - 1u;                   // entries at or below ak ...
+                    if (a0 > gb) valid &= ~((1u << (a0 - gb)) - 1u);          // ... that belong to this piece
+                    const uint32_t ev = (ends | ovl) & valid;
+                    if (!ev) {   // nothing here: on to the group below
+                        ak = max(gb, a0) - 1;
+                        if (ak >= a0) {
+#pragma unroll
+                            for (int u = 0; u < 4; u++) cur[u] = nxt[u];
+                            const int nb = gb - 8;
+                            if (nb >= 0 && nb + 3 >= a0) load_group(rl, nb, nxt);
+                        } else want = W_FINAL;
+                    } else {
+                        const int u = 31 - __clz(ev);
+                        ak = gb + u;
+                        if ((ends >> u) & 1u) {
+                            want = W_FINAL;
+                            fin_pm = det[ak].d.y;
+                            fin_parg = det[ak].i.z;
+                        } else {
+                            want = W_EVAL;
+                            ev_right = u == 0 ? cur[0].x : (u == 1 ? cur[1].x : (u == 2 ? cur[2].x : cur[3].x));
+                        }
+                    }
                 }
             }
         } else if (pick == W_EVAL) {
