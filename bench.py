@@ -578,7 +578,7 @@ def main():
                                  "gather_ms_per_step": 1e3 * dt_gather / args.steps, "partition_ms": strong["partition_ms"],
                                  "rank0_bp": strong["my_bp"], "rank0_contigs": strong["my_contigs"],
                                  "merged_equals_single_gpu_decode": strong["equal"],
-                                 "api": "shard.partition_ranges -> Engine.decode_buffer(host slice) per rank -> shard.gather_genes_device (NCCL "
+                                 "api": "shard.partition_ranges -> Engine.decode_buffer(host slice) per rank -> shard.gather_genes_device (ranks of one node: rows copied into a host segment all ranks map; else NCCL "
                                         "gather of the 32-byte gene rows from device memory), max over ranks"}
             if shape2:
                 out["other_shapes"] = [shape2]

@@ -212,7 +212,7 @@ struct mgc_engine {
     DevBuf surv_counters;  // [M]
     PinnedPool::Block table_stage;   // page-locked staging of the slot tables (set_slots)
     DevBuf work_counters;  // [M][4] int: long pieces, consumers' cursor, other pieces, unused
-    bool chain_warp = false;  // MGCOD_B200_CHAIN=warp: the warp-per-piece chain kernel of round 1 (A/B measurements, tests)
+    int chain_mode = 0;       // MGCOD_B200_CHAIN=warp / thread: all pieces through one of the two chain kernels (A/B measurements, tests)
     DevBuf model_cents;    // [M]
     DevBuf gene_totals;    // [M] uint32 grand totals of the gene scans
     DevBuf win_stride, win_off, win_labels, win_cents, win_merged, win_run, win_status, win_hist;   // labelling scratch, kept between calls
@@ -446,7 +446,7 @@ void upload_models(mgc_engine *e) {
     // the pair walk needs every model's pair tables in one SM's shared memory (orders <= 4); otherwise, or with
     // MGCOD_B200_WALK=single (A/B measurements, tests of the older kernel), the single-position walk runs
     e->pair_smem = 0;
-    if (const char *cm = std::getenv("MGCOD_B200_CHAIN")) e->chain_warp = std::strcmp(cm, "warp") == 0;
+    if (const char *cm = std::getenv("MGCOD_B200_CHAIN")) e->chain_mode = std::strcmp(cm, "warp") == 0 ? 1 : (std::strcmp(cm, "thread") == 0 ? 2 : 0);
     {
         const char *mode = std::getenv("MGCOD_B200_WALK");
         bool all = !(mode && std::strcmp(mode, "single") == 0);
@@ -513,10 +513,11 @@ void ensure_batch_buffers(mgc_engine *e) {
         p.prev.ensure((size_t)e->cap_surv * 4);
         p.gptr.ensure((size_t)e->cap_orf * 4);
         p.av_parg.ensure((size_t)e->cap_surv * 4);
-        if (e->chain_warp) {
+        if (e->chain_mode != 2) {
             for (DevBuf *b : {&p.av_right, &p.av_left, &p.av_ls, &p.av_idx}) b->ensure((size_t)e->cap_surv * 4);
             for (DevBuf *b : {&p.av_cum, &p.av_pmax}) b->ensure((size_t)e->cap_surv * 8);
-        } else {
+        }
+        if (e->chain_mode != 1) {
             p.st.ensure((size_t)e->cap_surv * sizeof(ChainSt));
             p.st_rl.ensure(((size_t)e->cap_surv + 8) * 8);   // the scan reads aligned groups of four: up to three records past the last
         }
@@ -608,6 +609,9 @@ void ensure_batch_buffers(mgc_engine *e) {
 
 // (re)builds the slot table from e->segs and uploads it; the ASCII letters stay where they are
 static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+// Up to this many bp x models in a batch the long chain pieces go to the warp-per-piece kernel (measured: 125 Mbp x 4 chain phase
+// 3.0 -> 2.2 ms, 1 Gbp x 4 7.5 -> 10.6 ms: there the threads have several pieces each and the long ones, started first, hide)
+constexpr int64_t kChainHybridMaxUnits = 1200000000;
 void set_slots(mgc_engine *e) {
     const bool trace = std::getenv("MGCOD_TRACE") != nullptr;
     const double t0 = now_ms();
@@ -843,7 +847,9 @@ mgc_result *run_pipeline(mgc_engine *e, bool *amb_out) {
     CUDA_TRY(cudaPeekAtLastError());   // a failed launch must not go unnoticed until the end
     CUDA_TRY(cudaEventRecord(e->ev[4], st));
     launches += launch_chain(e->t_chainbufs.as<ChainBufs>(), e->t_sorted.as<const Cand *>(), e->t_surv.as<Cand *>(), e->cwoff.as<int64_t>(), e->clen.as<int32_t>(), e->slotbase.as<int32_t>(),
-                             e->slot_contig.as<int32_t>(), e->n_slots, nb, e->work_counters.as<int>(), M, e->n_sm, e->chain_warp, st);
+                             e->slot_contig.as<int32_t>(), e->n_slots, nb, e->work_counters.as<int>(), M, e->n_sm,
+                             // small batches (the per-rank shares of one input over several GPUs): long pieces by warps, see launch_chain
+                             e->chain_mode == 0 && e->total_nt * M > kChainHybridMaxUnits ? 2 : e->chain_mode, st);
     CUDA_TRY(cudaPeekAtLastError());   // a failed launch must not go unnoticed until the end
     CUDA_TRY(cudaEventRecord(e->ev[5], st));
     if (std::getenv("MGCOD_B200_PIECE_STATS")) {   // diagnostic: sizes of the chain pieces of model 0

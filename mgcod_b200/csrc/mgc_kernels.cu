@@ -2019,16 +2019,17 @@ __global__ void __launch_bounds__(128) k_chain_plan(const ChainBufs *bufs_m, con
     else B.work[n_slots - 1 - atomicAdd(&work_counters[4 * mi + 2], 1)] = s;
 }
 
-__global__ void __launch_bounds__(128, 8) k_chain(const ChainBufs *bufs_m, int *work_counters, int n_slots) {
+__global__ void __launch_bounds__(128, 8) k_chain(const ChainBufs *bufs_m, int *work_counters, int n_slots, int long_only) {
     __shared__ ChainRing rings[4];
     const int mi = blockIdx.y;
     const ChainBufs B = bufs_m[mi];
     const int lane = lane_id();
     ChainRing &R = rings[threadIdx.x >> 5];
-    const int n_work = work_count(work_counters + 4 * mi);
+    // long_only: the long pieces at the front of the work list (their own cursor); k_chain_flat takes the others
+    const int n_work = long_only ? work_counters[4 * mi] : work_count(work_counters + 4 * mi);
     while (true) {
         int item = 0;
-        if (lane == 0) item = atomicAdd(&work_counters[4 * mi + 1], 1);
+        if (lane == 0) item = atomicAdd(&work_counters[4 * mi + (long_only ? 3 : 1)], 1);
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item >= n_work) break;
         const int slot = work_slot(B, work_counters + 4 * mi, item, n_slots);
@@ -2171,12 +2172,13 @@ __device__ __forceinline__ void load_group(const int2 *rl, int gb, int2 (&out)[4
     out[0] = make_int2(a.x, a.y); out[1] = make_int2(a.z, a.w); out[2] = make_int2(b.x, b.y); out[3] = make_int2(b.z, b.w);
 }
 
-__global__ void __launch_bounds__(128, CHAIN_MINB) k_chain_flat(const ChainBufs *bufs_m, int *work_counters, int n_slots) {
+__global__ void __launch_bounds__(128, CHAIN_MINB) k_chain_flat(const ChainBufs *bufs_m, int *work_counters, int n_slots, int skip_long) {
     const int mi = blockIdx.y;
     const ChainBufs B = bufs_m[mi];
     const Cand *__restrict__ C = B.sorted;
     const int *wc = work_counters + 4 * mi;
     const int n_work = work_count(wc);
+    const int first_item = skip_long ? wc[0] : 0;   // the long pieces at the front of the list go to the warp-per-piece kernel
     // States of a piece live at the piece's candidate range [a0, ...) of two arrays: rl = {right, left} (8 bytes: what the scan
     // reads, four states per 32-byte sector) and det = {len*2+rev, index, index of the prefix maximum | cum, prefix maximum}.
     int2 *__restrict__ rl = B.st_rl;
@@ -2244,7 +2246,7 @@ __global__ void __launch_bounds__(128, CHAIN_MINB) k_chain_flat(const ChainBufs 
                     have_piece = false;
                 }
                 if (!have_piece) {
-                    const int item = atomicAdd(&work_counters[4 * mi + 1], 1);
+                    const int item = first_item + atomicAdd(&work_counters[4 * mi + 1], 1);
                     if (item >= n_work) want = W_DONE;
                     else {
                         slot = work_slot(B, wc, item, n_slots);
@@ -2834,17 +2836,25 @@ void launch_piece_stats(const ChainBufs *bufs_m, const int *work_counters, int32
 
 int launch_chain(const ChainBufs *bufs_m, const Cand *const *scattered_m, Cand *const *ordered_m, const int64_t *cwoff, const int32_t *clen,
                  const int32_t *slotbase, const int32_t *slot_contig, int32_t n_slots, int64_t n_buckets, int *work_counters, int n_models,
-                 int n_sm, bool warp_per_piece, cudaStream_t st) {
+                 int n_sm, int chain_mode, cudaStream_t st) {
     k_bucket_order<<<dim3((unsigned)n_sm * 8, n_models), 256, 0, st>>>(bufs_m, scattered_m, ordered_m, cwoff, n_buckets);
     k_chain_plan<<<dim3((unsigned)((n_slots + 127) / 128), n_models), 128, 0, st>>>(bufs_m, cwoff, clen, slotbase, slot_contig, n_slots,
                                                                                      work_counters);
     // grids sized so that the blocks of ALL models are resident together: a model's pieces then share the machine for the whole
     // kernel instead of four runs one after the other, each ending on its longest piece
     const unsigned per_model = (unsigned)std::max(1, n_sm * 8 / std::max(1, n_models));
-    if (warp_per_piece) k_chain<<<dim3(per_model * 2, n_models), 128, 0, st>>>(bufs_m, work_counters, n_slots);
-    else k_chain_flat<<<dim3(per_model, n_models), 128, 0, st>>>(bufs_m, work_counters, n_slots);
+    // Pieces of CHAIN_BIG_PIECE candidates and more (3 % of the pieces, 7 % of the candidates) go to the warp-per-piece kernel: a
+    // thread needs ~9 us per candidate of its piece (a dozen dependent sections), so the longest pieces set the floor of
+    // k_chain_flat — 3 ms of a 125 Mbp batch's 3.3 ms chain phase (the per-rank share of 1 Gbp over 8 GPUs); a warp does them in a
+    // tenth of that.  mode 1: everything through the warp kernel, mode 2: everything through the thread kernel (measurements).
+    if (chain_mode == 1) k_chain<<<dim3(per_model * 2, n_models), 128, 0, st>>>(bufs_m, work_counters, n_slots, 0);
+    else if (chain_mode == 2) k_chain_flat<<<dim3(per_model, n_models), 128, 0, st>>>(bufs_m, work_counters, n_slots, 0);
+    else {
+        k_chain<<<dim3(per_model, n_models), 128, 0, st>>>(bufs_m, work_counters, n_slots, 1);
+        k_chain_flat<<<dim3(per_model, n_models), 128, 0, st>>>(bufs_m, work_counters, n_slots, 1);
+    }
     k_chain_trace<<<dim3((unsigned)((n_slots + 127) / 128), n_models), 128, 0, st>>>(bufs_m, work_counters, n_slots);
-    return 4;
+    return chain_mode == 0 ? 5 : 4;
 }
 
 int launch_gather(const ChainBufs *bufs_m, mgc_gene *const *genes_m, const int32_t *slot_contig, int32_t n_slots, const int32_t *slotbase,

@@ -69,7 +69,7 @@ void launch_clear(const ClearList &list, int n_sm, cudaStream_t st);
 void launch_piece_stats(const ChainBufs *bufs_m, const int *work_counters, int32_t n_slots, unsigned int *hist, cudaStream_t st);
 int launch_chain(const ChainBufs *bufs_m, const Cand *const *scattered_m, Cand *const *ordered_m, const int64_t *cwoff, const int32_t *clen,
                  const int32_t *slotbase, const int32_t *slot_contig, int32_t n_slots, int64_t n_buckets, int *work_counters, int n_models,
-                 int n_sm, bool warp_per_piece, cudaStream_t st);
+                 int n_sm, int chain_mode /* 0 long pieces by warps + the others by threads, 1 warps only, 2 threads only */, cudaStream_t st);
 int launch_gather(const ChainBufs *bufs_m, mgc_gene *const *genes_m, const int32_t *slot_contig, int32_t n_slots, const int32_t *slotbase,
                   int32_t n_contigs, long long *model_cents, int n_models, int n_sm, cudaStream_t st);
 void launch_windows(const mgc_gene *const *genes_m, const uint32_t *const *gene_off_m, int n_models, const int32_t *clen,

@@ -70,13 +70,120 @@ def partition_ranges(lengths: Sequence[int], n_ranks: int) -> np.ndarray:
 
 
 def gather_genes_device(engine, first_contig: int, group=None, dst: int = 0):
-    """Final gather of a sharded decode over NCCL, straight from the engines' device memory: every rank contributes the gene
-    tables of its last decode (all models, 32-byte rows), rank ``dst`` returns them merged per model in global contig order
-    (other ranks return None).  ``first_contig`` = global index of the rank's first contig (``partition_ranges``).
-    Replaces the result collection of the reference's process pool (bin/multiprocess_mgcod.py:140-145)."""
+    """Final gather of a sharded decode, straight from the engines' device memory: every rank contributes the gene tables of
+    its last decode (all models, 32-byte rows), rank ``dst`` returns them merged per model in global contig order (other ranks
+    return None).  ``first_contig`` = global index of the rank's first contig (``partition_ranges``).
+    Replaces the result collection of the reference's process pool (bin/multiprocess_mgcod.py:140-145).
+
+    Ranks of ONE node (the usual case: torchrun sets LOCAL_WORLD_SIZE == WORLD_SIZE) write their rows into one host segment
+    that all of them map (:func:`gather_gene_tables_shared`): N device-to-host copies over N PCIe links side by side, where
+    the NCCL gather to one GPU (:func:`gather_gene_tables`; several nodes, or ``MGCOD_B200_GATHER=nccl``) ends in one copy of
+    everything over rank ``dst``'s link."""
+    import os
     import torch
-    return gather_gene_tables([engine.device_genes(m) for m in range(engine.n_models)], first_contig,
-                              torch.device("cuda", torch.cuda.current_device()), group, dst)
+    tables = [engine.device_genes(m) for m in range(engine.n_models)]
+    device = torch.device("cuda", torch.cuda.current_device())
+    one_node = os.environ.get("LOCAL_WORLD_SIZE", "1") == os.environ.get("WORLD_SIZE", "1")
+    if one_node and os.environ.get("MGCOD_B200_GATHER", "shared") != "nccl":
+        return gather_gene_tables_shared(tables, first_contig, device, group, dst)
+    return gather_gene_tables(tables, first_contig, device, group, dst)
+
+
+_SHARED = {}      # the host segment of this process: capacity, generation, mapping, tensor view
+
+
+def _shared_segment(total: int, rank: int, dst: int, group, cuda: bool):
+    """A host memory segment of at least ``total`` bytes mapped by every rank of the node (a file under /dev/shm, created by
+    rank ``dst``, unlinked as soon as everybody has mapped it) and, with CUDA, page-locked in every process.  All ranks call
+    this with the same ``total``, so they agree on capacity and generation without talking."""
+    import mmap
+    import os
+    import torch
+    import torch.distributed as dist
+    st = _SHARED
+    if st.get("cap", 0) >= total:
+        return st["tensor"]
+    if st.get("tensor") is not None:
+        if st["registered"]:
+            torch.cuda.cudart().cudaHostUnregister(st["tensor"].data_ptr())
+        st["tensor"] = None
+        st["map"] = None          # unmapped when the last view dies
+    cap = (int(total * 1.25) + (1 << 20) + 4095) // 4096 * 4096
+    gen = st.get("gen", 0) + 1
+    path = f"/dev/shm/mgcod_b200_{os.getuid()}_{os.environ.get('MASTER_PORT', '0')}_{gen}"
+    if rank == dst:
+        fd = os.open(path, os.O_CREAT | os.O_TRUNC | os.O_RDWR, 0o600)
+        os.ftruncate(fd, cap)
+    dist.barrier(group)
+    if rank != dst:
+        fd = os.open(path, os.O_RDWR)
+    mm = mmap.mmap(fd, cap)
+    os.close(fd)
+    dist.barrier(group)
+    if rank == dst:
+        os.unlink(path)           # the mappings keep the memory; nothing is left behind if a rank dies
+    t = torch.frombuffer(mm, dtype=torch.uint8)
+    registered = False
+    if cuda:
+        rc = torch.cuda.cudart().cudaHostRegister(t.data_ptr(), cap, 0)
+        registered = int(rc) == 0        # not page-locked: the copies still work, through the driver's staging buffer
+    st.update(cap=cap, gen=gen, map=mm, tensor=t, registered=registered)
+    return t
+
+
+def gather_gene_tables_shared(tables, first_contig: int, device, group=None, dst: int = 0):
+    """Gather through host memory shared by the ranks of one node.  ``tables`` as for :func:`gather_gene_tables`.  Ranks
+    exchange their per-model counts (one small all_gather: also the point after which rank ``dst`` no longer reads the arrays
+    of the previous call), every rank copies its rows of model m — contig field already global — to
+    ``offset(m) + rows of lower ranks`` of the segment, a barrier closes the call.  The arrays rank ``dst`` returns are views of
+    the segment, valid until the next call."""
+    import torch
+    import torch.distributed as dist
+    from .engine import GENE_DTYPE
+    import os
+    import time
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    M = len(tables)
+    cuda = device.type == "cuda"
+    trace = os.environ.get("MGCOD_TRACE") and rank == dst
+    t0 = time.perf_counter()
+    counts = torch.tensor([len(t) for t in tables], dtype=torch.int64, device=device)
+    all_counts = [torch.zeros_like(counts) for _ in range(world)]
+    dist.all_gather(all_counts, counts, group=group)
+    all_counts = torch.stack(all_counts).cpu().numpy()            # [world, M]
+    per_model = all_counts.sum(axis=0)
+    total = int(per_model.sum()) * 32
+    t1 = time.perf_counter()
+    seg = _shared_segment(max(total, 32), rank, dst, group, cuda)
+    t2 = time.perf_counter()
+    base = np.concatenate(([0], np.cumsum(per_model)))[:M] * 32
+    for m, t in enumerate(tables):
+        n = len(t) * 32
+        if not n:
+            continue
+        at = int(base[m]) + int(all_counts[:rank, m].sum()) * 32
+        if isinstance(t, np.ndarray):
+            rows = np.ascontiguousarray(t, dtype=GENE_DTYPE).copy()
+            rows["contig"] += int(first_contig)
+            seg[at:at + n].copy_(torch.from_numpy(rows.view(np.uint8)))
+        else:
+            rows = torch.as_tensor(t, device=device)
+            if first_contig:
+                rows = rows.clone()
+                rows.view(torch.int32).view(-1, 8)[:, 0] += int(first_contig)    # contig = first field of the 32-byte row
+            seg[at:at + n].copy_(rows, non_blocking=True)
+    if cuda:
+        torch.cuda.current_stream().synchronize()
+    t3 = time.perf_counter()
+    dist.barrier(group)
+    if trace:
+        import sys
+        print(f"gather (shared segment, registered {_SHARED.get('registered')}): counts {1e3 * (t1 - t0):.2f} ms, segment {1e3 * (t2 - t1):.2f} ms, "
+              f"copies {1e3 * (t3 - t2):.2f} ms, barrier {1e3 * (time.perf_counter() - t3):.2f} ms", file=sys.stderr)
+    if rank != dst:
+        return None
+    host = seg.numpy()
+    return [host[int(base[m]):int(base[m]) + int(per_model[m]) * 32].view(GENE_DTYPE) for m in range(M)]
 
 
 _PINNED = {}      # device index -> page-locked receive buffer of rank dst (grown on demand, kept between calls)

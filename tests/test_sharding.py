@@ -70,7 +70,7 @@ def test_range_partition_is_contiguous_and_balanced():
     assert shard.partition_ranges([], 3).tolist() == [0, 0, 0, 0]
 
 
-def _range_worker(rank, world, port, model_paths, ret):
+def _range_worker(rank, world, port, model_paths, ret, how="collective"):
     import torch
     import torch.distributed as dist
     from mgcod_b200.engine import synth_metagenome
@@ -83,7 +83,10 @@ def _range_worker(rank, world, port, model_paths, ret):
     models = [gmhmm.Model(p) for p in model_paths]
     mine = range(int(cut[rank]), int(cut[rank + 1]))
     tables = [fx.genes_array_from_oracle(m, [buf[offs[c]:offs[c + 1]].tobytes() for c in mine])[0] for m in models]
-    merged = shard.gather_gene_tables(tables, int(cut[rank]), torch.device("cpu"))
+    gather = shard.gather_gene_tables_shared if how == "shared" else shard.gather_gene_tables
+    merged = gather(tables, int(cut[rank]), torch.device("cpu"))
+    if how == "shared":      # a second call re-uses the segment; the first call's arrays are no longer valid
+        merged = gather(tables, int(cut[rank]), torch.device("cpu"))
     if rank == 0:
         full = [fx.genes_array_from_oracle(m, [buf[offs[c]:offs[c + 1]].tobytes() for c in range(len(offs) - 1)])[0] for m in models]
         ret["ok"] = all(a.shape == b.shape and (a == b).all() for a, b in zip(merged, full))
@@ -94,8 +97,10 @@ def _range_worker(rank, world, port, model_paths, ret):
     dist.destroy_process_group()
 
 
-def test_two_rank_table_gather_equals_single_rank(model_dir):
-    """the collective of the GPU path (counts all_gather + padded gather of the 32-byte gene rows of all models) on gloo"""
+@pytest.mark.parametrize("how", ["collective", "shared"])
+def test_two_rank_table_gather_equals_single_rank(model_dir, how):
+    """the two gathers of the GPU path on gloo: the collective (counts all_gather + padded gather of the 32-byte gene rows of all
+    models) and, for ranks of one node, the host segment every rank maps and writes its rows into"""
     import torch.multiprocessing as mp
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -105,7 +110,7 @@ def test_two_rank_table_gather_equals_single_rank(model_dir):
     with ctx.Manager() as man:
         ret = man.dict()
         paths = [f"{model_dir}/mgm_11.mod", f"{model_dir}/mgm_4.mod"]
-        procs = [ctx.Process(target=_range_worker, args=(r, 2, port, paths, ret)) for r in range(2)]
+        procs = [ctx.Process(target=_range_worker, args=(r, 2, port, paths, ret, how)) for r in range(2)]
         for p in procs:
             p.start()
         for p in procs:
@@ -116,7 +121,7 @@ def test_two_rank_table_gather_equals_single_rank(model_dir):
 
 @pytest.mark.gpu
 def test_device_gather_on_one_gpu(model_dir):
-    """the NCCL path of the multi-GPU gather with a process group of one rank: the engine's device gene tables wrapped as
+    """both paths of the multi-GPU gather with a process group of one rank: the engine's device gene tables wrapped as
     torch tensors without a copy, counts exchanged, rows gathered — equal to the host-side result"""
     import torch
     import torch.distributed as dist
@@ -134,11 +139,14 @@ def test_device_gather_on_one_gpu(model_dir):
         cut = shard.partition_ranges(np.diff(offs), 3)         # pretend to be the middle rank of three
         mine = offs[int(cut[1]):int(cut[2]) + 1]
         res = eng.decode_buffer(buf, mine)
-        merged = shard.gather_genes_device(eng, int(cut[1]))
-        for m in range(4):
-            want = res.genes(m)
-            want["contig"] += int(cut[1])
-            assert len(want) > 20 and merged[m].tobytes() == want.tobytes()
+        for how in ("shared", "nccl"):         # the host segment mapped by the ranks of a node, then the NCCL gather
+            os.environ["MGCOD_B200_GATHER"] = how
+            merged = shard.gather_genes_device(eng, int(cut[1]))
+            for m in range(4):
+                want = res.genes(m)
+                want["contig"] += int(cut[1])
+                assert len(want) > 20 and merged[m].tobytes() == want.tobytes(), how
+        os.environ.pop("MGCOD_B200_GATHER", None)
         eng.close()
     finally:
         dist.destroy_process_group()
