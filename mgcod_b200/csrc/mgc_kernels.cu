@@ -1303,9 +1303,17 @@ __global__ void __launch_bounds__(WALK2_THREADS, 1) k_walk_pair(Planes pl, const
     __shared__ int s_model, s_pair;
     __shared__ uint32_t s_end;
     __shared__ unsigned int s_next;
+    __shared__ __align__(8) unsigned long long s_mbar;   // completion of the table's bulk copies (transaction bytes)
     const int lane = lane_id();
     int loaded_model = -1, loaded_pair = -1;
     const uint32_t tbl_addr = (uint32_t)__cvta_generic_to_shared(tbl);
+    const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(&s_mbar);
+    uint32_t tbl_phase = 0;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
     while (true) {
         if (threadIdx.x == 0) {
             unsigned int u = atomicAdd(next_unit, 1u);
@@ -1333,14 +1341,32 @@ __global__ void __launch_bounds__(WALK2_THREADS, 1) k_walk_pair(Planes pl, const
         const int pair = s_pair % dm.npair;   // s_pair counts (tile, pair) combinations, tile-major
         const int kc = KC >= 0 ? KC : dm.kc, kn = KC >= 0 ? KN : dm.kn;
         if (mi != loaded_model || pair != loaded_pair) {
-            const int4 *src = reinterpret_cast<const int4 *>(dm.wtab2 + (size_t)pair * dm.wtab2_n16);
-            int4 *dst = reinterpret_cast<int4 *>(tbl);
-            const int n16 = dm.wtab2_n16;
-#pragma unroll 4
-            for (int i = threadIdx.x; i < n16; i += WALK2_THREADS) dst[i] = __ldg(src + i);
+            // The unit's tables (up to 224 KB, the SM's whole shared memory: nothing to double-buffer into) come in by bulk
+            // copies of the async proxy (cp.async.bulk, 32 KB each) that one thread issues; everybody waits on the mbarrier
+            // they complete.  Nobody still reads the previous tables: all threads passed the barrier that ended the last unit.
+            const uint32_t bytes = (uint32_t)dm.wtab2_n16 * 16u;
+            if (threadIdx.x == 0) {
+                const char *src = reinterpret_cast<const char *>(dm.wtab2 + (size_t)pair * dm.wtab2_n16);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+                for (uint32_t at = 0; at < bytes; at += 32768u) {
+                    const uint32_t n = min(32768u, bytes - at);
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tbl_addr + at),
+                                 "l"(src + at), "r"(n), "r"(mbar)
+                                 : "memory");
+                }
+            }
+            uint32_t done = 0;
+            for (uint32_t spins = 0; !done; spins++) {
+                asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                             : "=r"(done)
+                             : "r"(mbar), "r"(tbl_phase)
+                             : "memory");
+                if (spins > (1u << 26)) __trap();   // a copy that never completes must not hang the device
+            }
+            tbl_phase ^= 1u;
             loaded_model = mi;
             loaded_pair = pair;
-            __syncthreads();
         }
         // shared-memory byte addresses: coding entry of (codon position p, window index x) at tc + p * pbytes + (x << (rcs + 4)),
         // my replica folded into tc; non-coding entry of index y at tn + (y << 7) (8 replicas of 16 bytes)
