@@ -1569,7 +1569,10 @@ __global__ void __launch_bounds__(256, 4) k_final(Planes pl, const int64_t *__re
             // starts of spurious ORFs; those never touch the planes or the ramp tables.  (Exact otherwise: only candidates
             // that the full computation would prune as well are dropped, with a 1e-6 guard band.)
             const double dl = (double)len;
-            const double lgt = 2.0 * log(dl);
+            // 2 ln(len) for the bound only: the single-precision logarithm plus a margin far above its error (conversion 6e-8,
+            // __logf 3 ulp ~ 6e-6 at ln 1e7) — the double-precision log of all 145 M starts was 12 % of this kernel's
+            // instructions; survivors of the bound take the exact one below
+            const double lgt = 2.0 * ((double)__logf((float)len) + 1e-4);
             bool maybe = false;
             {
                 const double *ub = dm.pair_ub + pair * 8;
