@@ -50,10 +50,11 @@ SEED = 20260101
 METRIC = "bp_x_models_per_s_decoded"
 UNIT = "bp*models/s"
 # One launch of the dominant kernel (k_walk_pair) on the default workload (1 Gbp x 4 models), from the committed ncu capture
-# profiles/r2_k_walk_pair_1Gbp.txt (ncu --set full): DRAM bytes moved and L1 data-pipe wavefronts (shared + global).
-WALK_PROFILE = "profiles/r2_k_walk_pair_1Gbp.txt"
-WALK_DRAM_BYTES_1GBP = 22.71e9
-WALK_L1_WAVEFRONTS_1GBP = 5.5e9
+# profiles/r3_k_walk_pair_1Gbp.txt (ncu --set full): DRAM bytes moved and L1 data-pipe wavefronts (shared 4.51e9 + global:
+# 73.8 % of one wavefront per SM and clock over the launch's 50.1 M cycles).
+WALK_PROFILE = "profiles/r3_k_walk_pair_1Gbp.txt"
+WALK_DRAM_BYTES_1GBP = 22.78e9
+WALK_L1_WAVEFRONTS_1GBP = 5.47e9
 SURVEY_BYTES_PER_UNIT = 0.40          # algorithmic bytes per bp x model
 
 
