@@ -101,7 +101,7 @@ def _shared_segment(total: int, rank: int, dst: int, group, cuda: bool):
     import torch
     import torch.distributed as dist
     st = _SHARED
-    if st.get("cap", 0) >= total:
+    if st.get("cap", 0) >= total and st.get("tensor") is not None:
         return st["tensor"]
     if st.get("tensor") is not None:
         if st["registered"]:
@@ -110,11 +110,22 @@ def _shared_segment(total: int, rank: int, dst: int, group, cuda: bool):
         st["map"] = None          # unmapped when the last view dies
     cap = (int(total * 1.25) + (1 << 20) + 4095) // 4096 * 4096
     gen = st.get("gen", 0) + 1
+    st.update(cap=0, gen=gen)
     path = f"/dev/shm/mgcod_b200_{os.getuid()}_{os.environ.get('MASTER_PORT', '0')}_{gen}"
+    ok = torch.zeros(1, dtype=torch.int64, device="cuda" if cuda else "cpu")
     if rank == dst:
-        fd = os.open(path, os.O_CREAT | os.O_TRUNC | os.O_RDWR, 0o600)
-        os.ftruncate(fd, cap)
-    dist.barrier(group)
+        # a container's /dev/shm may be 64 MB: writing past its free space is a SIGBUS, not an error code
+        try:
+            fs = os.statvfs("/dev/shm")
+            if fs.f_bavail * fs.f_frsize >= cap + (64 << 20):
+                fd = os.open(path, os.O_CREAT | os.O_TRUNC | os.O_RDWR, 0o600)
+                os.ftruncate(fd, cap)
+                ok += 1
+        except OSError:
+            pass
+    dist.broadcast(ok, src=dst, group=group)      # also: the file exists before the others open it
+    if int(ok.item()) == 0:
+        return None                               # the caller falls back to the collective
     if rank != dst:
         fd = os.open(path, os.O_RDWR)
     mm = mmap.mmap(fd, cap)
@@ -155,6 +166,8 @@ def gather_gene_tables_shared(tables, first_contig: int, device, group=None, dst
     total = int(per_model.sum()) * 32
     t1 = time.perf_counter()
     seg = _shared_segment(max(total, 32), rank, dst, group, cuda)
+    if seg is None:       # no room under /dev/shm
+        return gather_gene_tables(tables, first_contig, device, group, dst)
     t2 = time.perf_counter()
     base = np.concatenate(([0], np.cumsum(per_model)))[:M] * 32
     for m, t in enumerate(tables):
