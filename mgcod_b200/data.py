@@ -157,17 +157,30 @@ def frame_columns(frames) -> list:
 
 class Record:
     """The slice of Biopython's SeqRecord that Mgcod touches: ``id``, ``description``, ``seq``, ``len()``.
-    ``seq`` may be given as a uint8 view into a :class:`Fasta` buffer; it is decoded to ``str`` on first use."""
+    ``seq`` is a ``str``, a uint8 view into a :class:`Fasta` buffer, or — what :meth:`Fasta.records` makes for the 20 000
+    contigs of a metagenome — just the record's number in its file: the view is cut and decoded to ``str`` on first use."""
 
-    def __init__(self, rid: str, description: str, seq):
+    __slots__ = ("id", "description", "_seq", "_len", "_fasta", "_k")
+
+    def __init__(self, rid: str, description: str, seq=None, fasta=None, k=0, length=None):
         self.id, self.description, self._seq = rid, description, seq
-        self._len = len(seq)
+        self._fasta, self._k = fasta, k
+        self._len = len(seq) if length is None else length
 
     @property
     def seq(self) -> str:
+        if self._seq is None:
+            f = self._fasta
+            self._seq = f.buffer[f.offsets[self._k]:f.offsets[self._k + 1]] if f is not None and len(f.buffer) else ""
         if not isinstance(self._seq, str):
             self._seq = self._seq.tobytes().decode("ascii", errors="replace")
         return self._seq
+
+    def detach(self):
+        """the letters are about to be released: keep the sequence only if somebody has asked for it"""
+        if not isinstance(self._seq, str):
+            self._seq = ""
+        self._fasta = None
 
     def __len__(self):
         return self._len
@@ -200,7 +213,8 @@ class Fasta:
                        if ptr else np.zeros(0, np.uint8))
 
     def records(self) -> list:
-        return [Record(i, d, self.buffer[self.offsets[k]:self.offsets[k + 1]]) for k, (i, d) in enumerate(zip(self.ids, self.deflines))]
+        lens = np.diff(self.offsets).tolist()
+        return [Record(i, d, None, self, k, n) for k, (i, d, n) in enumerate(zip(self.ids, self.deflines, lens))]
 
     def close(self):
         if getattr(self, "_h", None) and _lib is not None and getattr(_lib, "lib", None):   # None during interpreter shutdown
@@ -305,8 +319,7 @@ class Data:
         are detached first (materialised as str only where somebody already asked for them)"""
         self.finish_writes()
         for r in getattr(self, "_file_order", None) or []:
-            if not isinstance(r._seq, str):
-                r._seq = ""
+            r.detach()
         self.result = None
         f = getattr(self, "_fasta", None)
         if f is not None:
