@@ -45,6 +45,14 @@ def gc_percent(seq: str) -> float:
     return sum(seq.count(x) for x in "GCgcSs") * 100.0 / len(seq)
 
 
+class _Idx(list):
+    """row indices of an exact-start lookup: a list that answers ``.shape[0]`` like the index arrays of the range lookups"""
+
+    @property
+    def shape(self):
+        return (len(self),)
+
+
 class _GeneSet:
     """One model's genes on one contig, in file order, indexed for the six lookups."""
 
@@ -67,8 +75,13 @@ class _GeneSet:
         self.sorted_start = self.start[self.order]
         self.max_len = int((self.end - self.start).max()) if len(self.rows) else 0
         self.by_end: dict[int, list[int]] = {}
-        for i, e in enumerate(self.end.tolist()):
+        self.end_l = self.end.tolist()
+        for i, e in enumerate(self.end_l):
             self.by_end.setdefault(e, []).append(i)
+        self.by_start: dict[int, list[int]] = {}      # the three exact-start lookups are dictionary hits, no array call
+        for i, b in enumerate(self.start.tolist()):
+            self.by_start.setdefault(b, []).append(i)
+        self.strand_l = self.strand.tolist()
         self.seen = np.zeros(len(self.rows), dtype=bool)
 
     def __len__(self):
@@ -81,16 +94,14 @@ class _GeneSet:
         return np.sort(self.order[a:b])
 
     def identical(self, s, e, st):
-        i = self._window(s, s + 1)
-        return i[(self.end[i] == e) & (self.strand[i] == st)]
+        return _Idx(i for i in self.by_start.get(int(s), ()) if self.end_l[i] == e and self.strand_l[i] == st)
 
     def same_end(self, e, st):
         i = np.asarray(self.by_end.get(int(e), []), dtype=np.int64)
         return i[self.strand[i] == st]
 
     def same_start(self, s, st):
-        i = self._window(s, s + 1)
-        return i[self.strand[i] == st]
+        return _Idx(i for i in self.by_start.get(int(s), ()) if self.strand_l[i] == st)
 
     def overspanning(self, s, e, st):
         i = self._window(s - self.max_len - 1, s)          # a gene reaching beyond e >= s starts no earlier than that
@@ -105,8 +116,7 @@ class _GeneSet:
         return i[m]
 
     def equal(self, s, e):
-        i = self._window(s, s + 1)
-        return i[self.end[i] == e]                          # ref: no strand test on set 1
+        return _Idx(i for i in self.by_start.get(int(s), ()) if self.end_l[i] == e)      # ref: no strand test on set 1
 
     def copies(self, idx) -> list[dict]:
         return [dict(self.rows[int(i)]) for i in idx]

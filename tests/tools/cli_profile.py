@@ -50,6 +50,7 @@ def main():
     print("third call under cProfile", r)
     st = pstats.Stats(pr)
     st.sort_stats("tottime").print_stats(top)
+    st.sort_stats("cumulative").print_stats("mgcod_b200", top)
 
 
 if __name__ == "__main__":
