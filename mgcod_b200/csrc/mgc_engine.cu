@@ -612,6 +612,7 @@ static double now_ms() { return std::chrono::duration<double, std::milli>(std::c
 // Up to this many bp x models in a batch the long chain pieces go to the warp-per-piece kernel (measured: 125 Mbp x 4 chain phase
 // 3.0 -> 2.2 ms, 1 Gbp x 4 7.5 -> 10.6 ms: there the threads have several pieces each and the long ones, started first, hide)
 constexpr int64_t kChainHybridMaxUnits = 1200000000;
+constexpr int64_t kChainWarpMaxUnits = 600000000;    // up to 150 Mbp x 4: all pieces to the warp-per-piece kernel (20 Mbp x 4: chain 1.36 -> 0.69 ms, 125 Mbp x 4: 2.19 -> 2.02)
 void set_slots(mgc_engine *e) {
     const bool trace = std::getenv("MGCOD_TRACE") != nullptr;
     const double t0 = now_ms();
@@ -848,8 +849,11 @@ mgc_result *run_pipeline(mgc_engine *e, bool *amb_out) {
     CUDA_TRY(cudaEventRecord(e->ev[4], st));
     launches += launch_chain(e->t_chainbufs.as<ChainBufs>(), e->t_sorted.as<const Cand *>(), e->t_surv.as<Cand *>(), e->cwoff.as<int64_t>(), e->clen.as<int32_t>(), e->slotbase.as<int32_t>(),
                              e->slot_contig.as<int32_t>(), e->n_slots, nb, e->work_counters.as<int>(), M, e->n_sm,
-                             // small batches (the per-rank shares of one input over several GPUs): long pieces by warps, see launch_chain
-                             e->chain_mode == 0 && e->total_nt * M > kChainHybridMaxUnits ? 2 : e->chain_mode, st);
+                             // small batches (the per-rank shares of one input over several GPUs): long pieces by warps, see launch_chain;
+                             // a single genome: every piece by a warp (a thread needs ~9 us per candidate, phage2's longest piece 0.6 ms)
+                             e->chain_mode != 0 ? e->chain_mode
+                                                : (e->total_nt * M > kChainHybridMaxUnits ? 2 : (e->total_nt * M <= kChainWarpMaxUnits ? 1 : 0)),
+                             st);
     CUDA_TRY(cudaPeekAtLastError());   // a failed launch must not go unnoticed until the end
     CUDA_TRY(cudaEventRecord(e->ev[5], st));
     if (std::getenv("MGCOD_B200_PIECE_STATS")) {   // diagnostic: sizes of the chain pieces of model 0
