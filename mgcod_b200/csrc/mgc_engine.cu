@@ -212,7 +212,7 @@ struct mgc_engine {
     DevBuf surv_counters;  // [M]
     PinnedPool::Block table_stage;   // page-locked staging of the slot tables (set_slots)
     DevBuf work_counters;  // [M][4] int: long pieces, consumers' cursor, other pieces, unused
-    int chain_mode = 0;       // MGCOD_B200_CHAIN=warp / thread: all pieces through one of the two chain kernels (A/B measurements, tests)
+    int chain_mode = -1;      // -1: by batch size (launch_chain's caller); MGCOD_B200_CHAIN=hybrid / warp / thread forces 0 / 1 / 2 (tests, A/B measurements)
     DevBuf model_cents;    // [M]
     DevBuf gene_totals;    // [M] uint32 grand totals of the gene scans
     DevBuf win_stride, win_off, win_labels, win_cents, win_merged, win_run, win_status, win_hist;   // labelling scratch, kept between calls
@@ -446,7 +446,7 @@ void upload_models(mgc_engine *e) {
     // the pair walk needs every model's pair tables in one SM's shared memory (orders <= 4); otherwise, or with
     // MGCOD_B200_WALK=single (A/B measurements, tests of the older kernel), the single-position walk runs
     e->pair_smem = 0;
-    if (const char *cm = std::getenv("MGCOD_B200_CHAIN")) e->chain_mode = std::strcmp(cm, "warp") == 0 ? 1 : (std::strcmp(cm, "thread") == 0 ? 2 : 0);
+    if (const char *cm = std::getenv("MGCOD_B200_CHAIN")) e->chain_mode = std::strcmp(cm, "warp") == 0 ? 1 : (std::strcmp(cm, "thread") == 0 ? 2 : (std::strcmp(cm, "hybrid") == 0 ? 0 : -1));
     {
         const char *mode = std::getenv("MGCOD_B200_WALK");
         bool all = !(mode && std::strcmp(mode, "single") == 0);
@@ -851,7 +851,7 @@ mgc_result *run_pipeline(mgc_engine *e, bool *amb_out) {
                              e->slot_contig.as<int32_t>(), e->n_slots, nb, e->work_counters.as<int>(), M, e->n_sm,
                              // small batches (the per-rank shares of one input over several GPUs): long pieces by warps, see launch_chain;
                              // a single genome: every piece by a warp (a thread needs ~9 us per candidate, phage2's longest piece 0.6 ms)
-                             e->chain_mode != 0 ? e->chain_mode
+                             e->chain_mode >= 0 ? e->chain_mode
                                                 : (e->total_nt * M > kChainHybridMaxUnits ? 2 : (e->total_nt * M <= kChainWarpMaxUnits ? 1 : 0)),
                              st);
     CUDA_TRY(cudaPeekAtLastError());   // a failed launch must not go unnoticed until the end

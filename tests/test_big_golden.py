@@ -63,10 +63,15 @@ def test_oracle_equals_binary_digests(big):
 
 
 @pytest.mark.gpu
-def test_engine_equals_binary_digests(big):
-    """GPU: the whole 24 Mbp batch through the C-ABI; every contig's gene lines and every tie gene as the binary printed"""
+@pytest.mark.parametrize("chain", ["auto", "thread", "hybrid", "warp"])
+def test_engine_equals_binary_digests(big, chain, monkeypatch):
+    """GPU: the whole 24 Mbp batch through the C-ABI; every contig's gene lines and every tie gene as the binary printed.
+    Once as the engine chooses for a batch of this size and once with each chain kernel forced (MGCOD_B200_CHAIN: all pieces by
+    threads — what a 1 Gbp batch gets —, long pieces by warps and the others by threads, all by warps)."""
     from mgcod_b200.engine import Engine
     meta, buf, offs, paths = big
+    if chain != "auto":
+        monkeypatch.setenv("MGCOD_B200_CHAIN", chain)
     eng = Engine([paths[c] for c in fx.CODES])
     res = eng.decode_buffer(buf, offs)
     checked = 0
