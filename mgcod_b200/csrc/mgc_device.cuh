@@ -177,7 +177,7 @@ struct Planes {
 
 __device__ __forceinline__ uint32_t frame_pattern(int r) {
     // bits b with b % 3 == r
-    return r == 0 ? 0x49249249u : (r == 1 ? 0x92492492u : 0x24924924u);
+    return 0x49249249u << r;   // r in {0, 1, 2}: 0x49249249, 0x92492492, 0x24924924
 }
 
 // letters of 32 consecutive positions starting at word w (needs w+1 for the two look-ahead letters)

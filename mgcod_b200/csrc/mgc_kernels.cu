@@ -514,7 +514,7 @@ __device__ __forceinline__ bool make_orf(const FindCtx &cx, const DevModel &dm, 
         bool any = false;
         const int w_end = min(s_hi >> 5, (s_lo >> 5) + 3);
         for (int w = s_lo >> 5; w <= w_end && !any; w++) {
-            const int r = ((f - (w * 32) % 3) % 3 + 3) % 3;
+            const int r = (f + w) % 3;   // (f - 32 w) mod 3: 32 = 2 = -1 (mod 3); w >= 0
             any = (starts_at(cx, w) & frame_pattern(r) & bit_range(s_lo - 32 * w, s_hi - 32 * w)) != 0;
         }
         if (!any && (s_hi >> 5) <= w_end) return false;
@@ -756,7 +756,7 @@ __global__ void __launch_bounds__(EXPAND_ORFS) k_orf_expand(Planes pl, const uin
             const int c = o_contig[i], strand = (int)(o_sf[i] & 1u);
             const FindCtx cx = make_ctx(pl, strand, cwoff[c], clen[c], dm.stop_sel, dm.atg_only);
             const int f = o_t[i] % 3;
-            const int r = ((f - (w * 32) % 3) % 3 + 3) % 3;
+            const int r = (f + w) % 3;   // (f - 32 w) mod 3: 32 = 2 = -1 (mod 3); w >= 0
             mask = starts_at(cx, w) & frame_pattern(r) & bit_range(o_slo[i] - 32 * w, o_shi[i] - 32 * w);
             virt_here = j == 0 && (o_sf[i] & 2u) != 0;
         };
