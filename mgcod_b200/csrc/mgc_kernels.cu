@@ -4,6 +4,7 @@
 // synchronisation until the final counters are read):
 //
 //   k_groups         word-group -> contig map                                  (once per upload)
+//   k_clear          every per-decode counter / histogram in one launch (no cudaMemset: it runs on a copy engine)
 //   k_pack           ASCII -> 2-bit planes + ambiguity plane for both strands, GC / N counts per word; scan x2
 //   k_codon_planes   start / ATG / TAA / TAG / TGA bit per letter, shared by the models
 //   k_laststop_*     per model: last in-frame stop before every word (max-scan)
@@ -11,10 +12,15 @@
 //   k_orf_expand     per model: start records (position, GC bin, section pair) of every ORF, load-balanced per block
 //   k_start_link     chains the starts of an ORF that share a section pair; one walk item per chain
 //   k_item_plan / k_item_scatter   counting sort of the items by (position tile, section pair, length class)
-//   k_walk           thread per item: 3-periodic Markov log-likelihood sums from the stop down, the pair's tables in shared memory
+//   k_walk_pair      thread per item: 3-periodic Markov log-likelihood sums from the stop down, two positions per lookup, the
+//                    pair's tables (brought in by cp.async.bulk) in the SM's whole shared memory; k_walk: single positions (order 5)
 //   k_final          per start: order ramp, duration / start / stop terms, domain choice, pruning (total > 0), bucket histogram
 //   scan + k_scatter survivors into position buckets (128 nt) -> right-end order per contig
-//   k_bucket_order / k_chain_plan / k_chain_flat (k_chain)   cut points, then one warp per piece: max-plus chain with overlap penalties, traceback
+//   k_bucket_order   candidates into chain order inside their buckets (rank among the bucket's members)
+//   k_chain_plan     cut points: pieces that no candidate spans
+//   k_chain_flat     max-plus chain with overlap penalties, a THREAD per piece, the lanes of a warp as state machines that take
+//                    turns section by section; k_chain (a warp per piece, round 1) for small batches / their long pieces
+//   k_chain_trace    traceback, thread per piece
 //   scan + k_gather + k_contig_finish   genes ordered by (contig, left), per-model sums in 1/100 units, per-contig totals
 //   on request: k_windows, k_merge_labels (window labels), k_recoded_stops (in-frame stops per gene), k_find_gaps
 //
