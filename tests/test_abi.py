@@ -105,6 +105,16 @@ def test_native_fasta_reader_matches_python_reader(tmp_path):
     assert [r.seq for r in recs] == [w[2] for w in want] == ["ACGTACGGTT", "acgtnnTTAA", "", "ACG"]
     assert [len(r) for r in recs] == [10, 10, 0, 3]
     assert f.offsets.tolist() == [0, 10, 20, 20, 23]
+    # records cut their letters on first use: lengths are known at once, a record nobody asked for loses its letters with the
+    # reader's buffer (Data.close detaches the records first), one that was read keeps its string
+    g = Fasta(str(p), page_locked=False)
+    lazy = g.records()
+    assert [len(r) for r in lazy] == [10, 10, 0, 3] and all(r._seq is None for r in lazy)
+    assert lazy[1].seq == "acgtnnTTAA"
+    for r in lazy:
+        r.detach()
+    g.close()
+    assert [r.seq for r in lazy] == ["", "acgtnnTTAA", "", ""] and [len(r) for r in lazy] == [10, 10, 0, 3]
     f.close()
     empty = tmp_path / "e.fa"
     empty.write_bytes(b"")
