@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <chrono>
 #include <cstring>
+#include <future>
 #include <memory>
 #include <mutex>
 #include <numeric>
@@ -195,6 +196,23 @@ struct mgc_engine {
     cudaEvent_t copy_done = nullptr, main_done = nullptr, d2h_begin = nullptr, d2h_end = nullptr;
     std::shared_ptr<Ready> last_ready;   // copy of the previous result: the next gather must not overwrite its source
     bool d2h_timed = true;
+    // host side of a batch's slot tables (set_slots), computable before the batch is adopted
+    struct SlotTables {
+        std::vector<int32_t> clen, slotbase, slot_contig;
+        std::vector<int64_t> cwoff, aoff;
+        std::vector<uint8_t> cflags;
+        int32_t n = 0, n_slots = 0;
+        int64_t W = 0, total_nt = 0;
+    };
+    // what do_upload derives from the caller's offsets, prepared by a background thread while the previous batch is decoded
+    struct Prepared {
+        std::vector<Seg> segs;
+        std::vector<int64_t> parent_aoff;
+        std::vector<int32_t> parent_len;
+        SlotTables tables;
+        std::future<void> ready;
+        bool valid = false;
+    } prepared;
     struct {
         bool valid = false;
         const char *seq = nullptr;
@@ -613,38 +631,68 @@ static double now_ms() { return std::chrono::duration<double, std::milli>(std::c
 // 3.0 -> 2.2 ms, 1 Gbp x 4 7.5 -> 10.6 ms: there the threads have several pieces each and the long ones, started first, hide)
 constexpr int64_t kChainHybridMaxUnits = 1200000000;
 constexpr int64_t kChainWarpMaxUnits = 600000000;    // up to 150 Mbp x 4: all pieces to the warp-per-piece kernel (20 Mbp x 4: chain 1.36 -> 0.69 ms, 125 Mbp x 4: 2.19 -> 2.02)
-void set_slots(mgc_engine *e) {
-    const bool trace = std::getenv("MGCOD_TRACE") != nullptr;
-    const double t0 = now_ms();
-    const int32_t n = (int32_t)e->segs.size();
-    e->n_contigs = n;
-    e->h_clen.resize(n);
-    e->h_cwoff.resize(n + 1);
-    e->h_aoff.resize(n + 1);
-    std::vector<uint8_t> cflags(n);
-    std::vector<int32_t> slotbase(n + 1), slot_contig;
+// the caller's contigs as slots, one each (gaps re-slot later: do_decode)
+static void segs_from_offsets(const int64_t *offsets, int32_t n, std::vector<mgc_engine::Seg> &segs, std::vector<int32_t> &parent_len,
+                              std::vector<int64_t> &parent_aoff) {
+    parent_len.resize(n);
+    parent_aoff.resize(n + 1);
+    segs.resize(n);
+    const int64_t a0 = offsets[0], a1 = offsets[n];
+    for (int32_t c = 0; c < n; c++) {
+        const int64_t L = offsets[c + 1] - offsets[c];
+        if (L < 0 || L > 0x7ffffff0) throw std::invalid_argument("contig length out of range");
+        parent_len[c] = (int32_t)L;
+        parent_aoff[c] = offsets[c] - a0;
+        segs[c] = mgc_engine::Seg{c, offsets[c] - a0, (int32_t)L, 0, 1};
+    }
+    parent_aoff[n] = a1 - a0;
+}
+
+// host-only half of set_slots: word offsets of the slots, chain piece slots, totals
+static void compute_slot_tables(const std::vector<mgc_engine::Seg> &segs, mgc_engine::SlotTables &T) {
+    const int32_t n = (int32_t)segs.size();
+    T.n = n;
+    T.clen.resize(n);
+    T.cwoff.resize(n + 1);
+    T.aoff.resize(n + 1);
+    T.cflags.resize(n);
+    T.slotbase.resize(n + 1);
+    T.slot_contig.clear();
     int64_t w = 0, nt = 0;
     for (int32_t c = 0; c < n; c++) {
-        const int64_t L = e->segs[c].len;
-        slotbase[c] = (int32_t)slot_contig.size();
+        const int64_t L = segs[c].len;
+        T.slotbase[c] = (int32_t)T.slot_contig.size();
         const int64_t nbk = ((L > 0 ? L - 1 : 0) >> 7) + 1;
-        slot_contig.insert(slot_contig.end(), (size_t)((nbk + PIECE_BUCKETS - 1) / PIECE_BUCKETS), c);
-        e->h_clen[c] = (int32_t)L;
-        e->h_cwoff[c] = w;
-        e->h_aoff[c] = e->segs[c].aoff;
-        cflags[c] = e->segs[c].right_end;
+        T.slot_contig.insert(T.slot_contig.end(), (size_t)((nbk + PIECE_BUCKETS - 1) / PIECE_BUCKETS), c);
+        T.clen[c] = (int32_t)L;
+        T.cwoff[c] = w;
+        T.aoff[c] = segs[c].aoff;
+        T.cflags[c] = segs[c].right_end;
         const int64_t words = (L + 31) / 32 + 1;
         w += (words + 3) / 4 * 4;
         nt += L;
     }
-    slotbase[n] = (int32_t)slot_contig.size();
-    e->n_slots = slotbase[n];
-    e->h_cwoff[n] = w;
-    e->h_aoff[n] = 0;
+    T.slotbase[n] = (int32_t)T.slot_contig.size();
+    T.n_slots = T.slotbase[n];
+    T.cwoff[n] = w;
+    T.aoff[n] = 0;
     if (w * 64 >= 0xffffffffLL) throw std::invalid_argument("batch too large: at most ~2e9 nt per decode call");
-    e->W = w;
-    e->total_nt = nt;
+    T.W = w;
+    T.total_nt = nt;
+}
+
+// device half: buffers for a batch of this size, the six tables through the page-locked staging block
+static void apply_slot_tables(mgc_engine *e, mgc_engine::SlotTables &T) {
+    const bool trace = std::getenv("MGCOD_TRACE") != nullptr;
     const double t1 = now_ms();
+    const int32_t n = T.n;
+    e->n_contigs = n;
+    e->h_clen.swap(T.clen);
+    e->h_cwoff.swap(T.cwoff);
+    e->h_aoff.swap(T.aoff);
+    e->n_slots = T.n_slots;
+    e->W = T.W;
+    e->total_nt = T.total_nt;
     ensure_batch_buffers(e);
     const double t2 = now_ms();
     e->aoff.ensure((size_t)(n + 1) * 8);
@@ -658,9 +706,9 @@ void set_slots(mgc_engine *e) {
     // previous result's device-to-host copy (2 ms per step of a stream of batches), a page-locked one is queued at once
     {
         struct Part { void *dst; const void *src; size_t bytes; };
-        const Part parts[6] = {{e->slotbase.p, slotbase.data(), (size_t)(n + 1) * 4}, {e->slot_contig.p, slot_contig.data(), (size_t)e->n_slots * 4},
-                               {e->aoff.p, e->h_aoff.data(), (size_t)(n + 1) * 8},     {e->cwoff.p, e->h_cwoff.data(), (size_t)(n + 1) * 8},
-                               {e->clen.p, e->h_clen.data(), (size_t)n * 4},           {e->cflags.p, cflags.data(), (size_t)n}};
+        const Part parts[6] = {{e->slotbase.p, T.slotbase.data(), (size_t)(n + 1) * 4}, {e->slot_contig.p, T.slot_contig.data(), (size_t)e->n_slots * 4},
+                               {e->aoff.p, e->h_aoff.data(), (size_t)(n + 1) * 8},       {e->cwoff.p, e->h_cwoff.data(), (size_t)(n + 1) * 8},
+                               {e->clen.p, e->h_clen.data(), (size_t)n * 4},             {e->cflags.p, T.cflags.data(), (size_t)n}};
         size_t total = 0;
         for (const Part &q : parts) total += (q.bytes + 63) / 64 * 64;
         if (e->table_stage.bytes < total) {
@@ -677,10 +725,16 @@ void set_slots(mgc_engine *e) {
     }
     launch_groups(e->cwoff.as<int64_t>(), n, e->W / 4, e->grp2contig.as<int32_t>(), st);
     const double t3 = now_ms();
-    CUDA_TRY(cudaStreamSynchronize(st));  // cflags and the slot tables are local staging buffers
+    CUDA_TRY(cudaStreamSynchronize(st));  // the staging block is reused by the next batch
     CUDA_TRY(cudaGetLastError());
-    const double t4 = now_ms();
-    if (trace) std::fprintf(stderr, "set_slots: tables %.2f ms, ensure %.2f ms, uploads %.2f ms, sync %.2f ms (entered %.3f, left %.3f)\n", t1 - t0, t2 - t1, t3 - t2, t4 - t3, t0, t4);
+    if (trace) std::fprintf(stderr, "slot tables applied: ensure %.2f ms, uploads %.2f ms, sync %.2f ms\n", t2 - t1, t3 - t2, now_ms() - t3);
+}
+
+// (re)builds the slot table from e->segs and uploads it; the ASCII letters stay where they are
+void set_slots(mgc_engine *e) {
+    mgc_engine::SlotTables T;
+    compute_slot_tables(e->segs, T);
+    apply_slot_tables(e, T);
 }
 
 void do_upload(mgc_engine *e, const char *seq, const int64_t *offsets, int32_t n) {
@@ -691,18 +745,24 @@ void do_upload(mgc_engine *e, const char *seq, const int64_t *offsets, int32_t n
     e->have_batch = e->have_genes = false;
     e->segmented = false;
     e->n_parents = n;
-    e->h_parent_len.resize(n);
-    e->h_parent_aoff.resize(n + 1);
-    e->segs.resize(n);
-    const int64_t a0 = offsets[0], a1 = offsets[n];
-    for (int32_t c = 0; c < n; c++) {
-        const int64_t L = offsets[c + 1] - offsets[c];
-        if (L < 0 || L > 0x7ffffff0) throw std::invalid_argument("contig length out of range");
-        e->h_parent_len[c] = (int32_t)L;
-        e->h_parent_aoff[c] = offsets[c] - a0;
-        e->segs[c] = mgc_engine::Seg{c, offsets[c] - a0, (int32_t)L, 0, 1};
+    const bool adopted = e->pending.valid && e->pending.seq == seq && (int32_t)e->pending.offsets.size() == n + 1 &&
+                         std::memcmp(e->pending.offsets.data(), offsets, (size_t)(n + 1) * 8) == 0;
+    e->pending.valid = false;
+    // the host tables of an adopted batch were prepared by a background thread while the previous batch was decoded
+    bool prepared = false;
+    if (e->prepared.valid) {
+        e->prepared.valid = false;
+        e->prepared.ready.get();   // rethrows what the preparation threw (contig too long, batch too large)
+        prepared = adopted;
     }
-    e->h_parent_aoff[n] = a1 - a0;
+    if (prepared) {
+        e->segs.swap(e->prepared.segs);
+        e->h_parent_len.swap(e->prepared.parent_len);
+        e->h_parent_aoff.swap(e->prepared.parent_aoff);
+    } else {
+        segs_from_offsets(offsets, n, e->segs, e->h_parent_len, e->h_parent_aoff);
+    }
+    const int64_t a0 = offsets[0], a1 = offsets[n];
     cudaStream_t st = e->stream;
     e->plen.ensure((size_t)n * 4 + 16);
     {   // a kernel first: an event recorded as the first operation after the last step's read-back copies would wait for the
@@ -713,9 +773,6 @@ void do_upload(mgc_engine *e, const char *seq, const int64_t *offsets, int32_t n
         launch_clear(cl, 1, st);
     }
     CUDA_TRY(cudaEventRecord(e->ev[0], st));
-    const bool adopted = e->pending.valid && e->pending.seq == seq && (int32_t)e->pending.offsets.size() == n + 1 &&
-                         std::memcmp(e->pending.offsets.data(), offsets, (size_t)(n + 1) * 8) == 0;
-    e->pending.valid = false;
     if (adopted) {  // the letters are already on their way (or there): take the buffer over
         std::swap(e->ascii, e->ascii_next);
         CUDA_TRY(cudaStreamWaitEvent(st, e->copy_done, 0));
@@ -727,7 +784,8 @@ void do_upload(mgc_engine *e, const char *seq, const int64_t *offsets, int32_t n
     const double tu1 = now_ms();
     CUDA_TRY(cudaMemcpyAsync(e->plen.p, e->h_parent_len.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
     const double tu2 = now_ms();
-    set_slots(e);
+    if (prepared) apply_slot_tables(e, e->prepared.tables);
+    else set_slots(e);
     const double tu3 = now_ms();
     CUDA_TRY(cudaEventRecord(e->ev[1], st));
     CUDA_TRY(cudaStreamSynchronize(st));
@@ -1137,6 +1195,7 @@ int mgc_engine_create(int device, const mgc_model *const *models, int n_models, 
 
 void mgc_engine_destroy(mgc_engine *e) {
     if (!e) return;
+    if (e->prepared.valid) { e->prepared.valid = false; try { e->prepared.ready.get(); } catch (...) {} }   // it reads members of *e
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
     for (auto &p : e->pm) {
@@ -1202,9 +1261,21 @@ int mgc_prefetch_batch(mgc_engine *e, const char *seq, const int64_t *offsets, i
         e->ascii_next.ensure((size_t)(a1 - a0) + 2 * PACK_SLACK);
         CUDA_TRY(cudaMemcpyAsync(e->ascii_next.as<char>() + PACK_SLACK, seq + a0, (size_t)(a1 - a0), cudaMemcpyHostToDevice, e->copy_stream));
         CUDA_TRY(cudaEventRecord(e->copy_done, e->copy_stream));
+        // a preparation still running reads the previous offsets: let it finish before they are replaced
+        if (e->prepared.valid) { e->prepared.valid = false; try { e->prepared.ready.get(); } catch (...) {} }
         e->pending.valid = true;
         e->pending.seq = seq;
         e->pending.offsets.assign(offsets, offsets + n_contigs + 1);
+        // the batch's host tables (slots, word offsets, chain piece slots: ~1 ms for 43 k contigs) are built by a background
+        // thread now, not between two decodes with the device idle
+        mgc_engine::Prepared *pp = &e->prepared;
+        const int64_t *offs = e->pending.offsets.data();      // stays untouched until the batch is adopted or replaced
+        const int32_t nn = n_contigs;
+        pp->ready = std::async(std::launch::async, [pp, offs, nn] {
+            segs_from_offsets(offs, nn, pp->segs, pp->parent_len, pp->parent_aoff);
+            compute_slot_tables(pp->segs, pp->tables);
+        });
+        pp->valid = true;
     });
 }
 
