@@ -186,6 +186,61 @@ class Record:
         return self._len
 
 
+def record_ids(recs) -> list:
+    """ids of a record sequence without touching the records where it is a :class:`Records`"""
+    return recs.ids if isinstance(recs, Records) else [r.id for r in recs]
+
+
+def record_lengths(recs) -> np.ndarray:
+    return (np.asarray(recs.lengths, dtype=np.int64) if isinstance(recs, Records)
+            else np.fromiter((len(r) for r in recs), dtype=np.int64, count=len(recs)))
+
+
+class Records:
+    """The records of a :class:`Fasta` as a read-only sequence (``len``, indexing, slicing to a list, iteration) that makes a
+    :class:`Record` when one is asked for — a metagenome run touches the few contigs with a switch, not 20 000 objects.
+    ``ids`` and ``lengths`` give the two columns the pipeline needs of every record without making any.
+    ``order``: positions in the file, e.g. the records sorted by id (bin/data.py:122)."""
+
+    def __init__(self, fasta, order=None):
+        self._fasta = fasta
+        self._order = None if order is None else np.asarray(order, dtype=np.int64)
+        lens = np.diff(fasta.offsets)
+        if self._order is None:
+            self.ids, self._deflines, self.lengths = fasta.ids, fasta.deflines, lens
+        else:
+            o = self._order.tolist()
+            self.ids, self._deflines, self.lengths = [fasta.ids[k] for k in o], [fasta.deflines[k] for k in o], lens[self._order]
+        self._made: dict = {}
+
+    def __len__(self):
+        return len(self.ids)
+
+    def _make(self, i):
+        r = self._made.get(i)
+        if r is None:
+            k = i if self._order is None else int(self._order[i])
+            r = self._made[i] = self._fasta._record(k)
+        return r
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self._make(j) for j in range(*i.indices(len(self)))]
+        i = int(i)
+        if i < 0:
+            i += len(self)
+        if not 0 <= i < len(self):
+            raise IndexError(i)
+        return self._make(i)
+
+    def __iter__(self):
+        return (self._make(i) for i in range(len(self)))
+
+    def detach(self):
+        for r in self._made.values():
+            r.detach()
+
+
 class Fasta:
     """A FASTA file read by the native reader (``mgc_fasta_read``): one contiguous letter buffer (page-locked when a GPU is
     present) + offsets, ready for ``Engine.decode_buffer`` without a Python-side copy.  Replaces ``SeqIO.parse`` at
@@ -212,9 +267,16 @@ class Fasta:
         self.buffer = (np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(max(total, 1),))[:total]
                        if ptr else np.zeros(0, np.uint8))
 
-    def records(self) -> list:
-        lens = np.diff(self.offsets).tolist()
-        return [Record(i, d, None, self, k, n) for k, (i, d, n) in enumerate(zip(self.ids, self.deflines, lens))]
+    def _record(self, k: int) -> Record:
+        """the one Record object of record k (shared by every :class:`Records` view of this file)"""
+        made = self.__dict__.setdefault("_records_made", {})
+        r = made.get(k)
+        if r is None:
+            r = made[k] = Record(self.ids[k], self.deflines[k], None, self, k, int(self.offsets[k + 1] - self.offsets[k]))
+        return r
+
+    def records(self, order=None) -> Records:
+        return Records(self, order)
 
     def close(self):
         if getattr(self, "_h", None) and _lib is not None and getattr(_lib, "lib", None):   # None during interpreter shutdown
@@ -268,7 +330,7 @@ class Data:
         self._sorted_to_file = np.arange(len(recs), dtype=np.int64)
         if len(recs) > 1:
             self._sorted_to_file = np.argsort(self._fasta.ids)            # the reference's very call
-            recs = [recs[x] for x in self._sorted_to_file.tolist()]
+            recs = self._fasta.records(self._sorted_to_file)
         self.records = recs
         return recs
 
@@ -318,7 +380,8 @@ class Data:
         """releases the letter buffer (back to the reader's page-locked pool) and the decode result; the records' sequences
         are detached first (materialised as str only where somebody already asked for them)"""
         self.finish_writes()
-        for r in getattr(self, "_file_order", None) or []:
+        made = getattr(getattr(self, "_fasta", None), "_records_made", None) or {}
+        for r in made.values():
             r.detach()
         self.result = None
         f = getattr(self, "_fasta", None)
@@ -354,7 +417,7 @@ class Data:
                                    f"resident — split the file (bin/multiprocess_mgcod.py usage) or run the default mode")
             self.result = self.engine.decode_buffer(self._fasta.buffer, self._fasta.offsets)
         self.engine._resident_owner = self
-        return self.engine, [r.id for r in recs]
+        return self.engine, list(record_ids(recs))
 
     def gene_frames(self):
         """label → DataFrame of that model's genes (the reference's ``label_to_gene_coords``).  From the decoded arrays when

@@ -30,7 +30,7 @@ import numpy as np
 import pandas as pd
 
 from . import labels as L
-from .data import GeneFrames, contig_rows, frame_columns, rows_by_contig
+from .data import GeneFrames, contig_rows, frame_columns, record_ids, rows_by_contig
 from .percontig import PerContig
 
 
@@ -431,7 +431,7 @@ def compare_sets_of_predicted_genes(P):
     with_isoforms: list[dict] = []
     code_of = {int(k): v for k, v in P.label_to_gcode.items()}
     messages = []
-    seq_ids = getattr(P, "_ids", None) or [rec.id for rec in P.sequence]
+    seq_ids = getattr(P, "_ids", None) or list(record_ids(P.sequence))
     for n in np.flatnonzero(lmin != lmax).tolist():          # contigs whose smoothed labels name two genetic codes
         rec = P.sequence[n]
         labs = np.unique(P.updated_genome_labels[n])
@@ -465,7 +465,7 @@ def compare_sets_of_predicted_genes(P):
         if P.verbose:
             print("\n".join(messages))
 
-    ids = [rec.id for rec in P.sequence]      # the closure below must not hold P: P.coords -> closure -> P would be a cycle, and the
+    ids = list(record_ids(P.sequence))      # the closure below must not hold P: P.coords -> closure -> P would be a cycle, and the
     #                                           FASTA buffer and gene tables of a finished run would wait for the cyclic collector
 
     def build_coords():       # one block per contig, in contig order

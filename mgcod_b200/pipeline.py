@@ -23,7 +23,7 @@ import numpy as np
 
 from . import isoforms as iso_compare
 from . import labels as L
-from .data import Data, GeneFrames, rows_by_contig
+from .data import Data, GeneFrames, record_ids, record_lengths, rows_by_contig
 from .engine import MGCOD_CODES
 from .percontig import PerContig, Ragged
 
@@ -143,10 +143,9 @@ class Pipeline:
                 print(f"{self.species} is genetic code {code}")
             self.genome_label = code
             self.coords_w_isoforms = self.label_to_gene_coords[self.gcode_to_label[code]]
-            self.predicted_switch_regions = {seq.id: None for seq in self.sequence}
+            self.predicted_switch_regions = {rid: None for rid in record_ids(self.sequence)}
             return
-        self._ids = [seq.id for seq in self.sequence]
-        self._lens = np.fromiter((len(seq) for seq in self.sequence), dtype=np.int64, count=len(self.sequence))
+        self._ids, self._lens = list(record_ids(self.sequence)), record_lengths(self.sequence)   # no 20 000 record objects
         self.coords, self.gene_label_to_gcode, self.coords_w_isoforms = self.compare_sets_of_predicted_genes()
         self.confident_1, self.confident_2, self.segment_labels = self.segment_genome_based_on_window_labels()
         explicit = {}
@@ -182,7 +181,7 @@ class Pipeline:
             print(f"Identifying most common genetic codes in {self.species}")
         engine, _ = self.data.ensure_resident()            # decodes (again) when run_mgm was served from cached GFF files
         recs = self.data._file_order
-        lens_file = np.fromiter((len(r) for r in recs), dtype=np.int64, count=len(recs))
+        lens_file = record_lengths(recs)
         if self.stride is not None:
             stride_file = np.full(len(recs), int(self.stride), dtype=np.int32)
         else:
@@ -230,10 +229,10 @@ class Pipeline:
         if self.verbose:
             print(f"Segmenting genome of {self.species}")
         frames = self.label_to_gene_coords
-        ids = getattr(self, "_ids", None) or [seq.id for seq in self.sequence]
+        ids = getattr(self, "_ids", None) or list(record_ids(self.sequence))
         lens = getattr(self, "_lens", None)
         if lens is None:
-            lens = np.fromiter((len(seq) for seq in self.sequence), dtype=np.int64, count=len(self.sequence))
+            lens = record_lengths(self.sequence)
         lmin, lmax = getattr(self, "_label_min", None), getattr(self, "_label_max", None)
         if lmin is None:
             lmin = np.array([int(np.min(u)) if len(u) else -1 for u in self.updated_genome_labels], dtype=np.int64)

@@ -25,7 +25,7 @@ import warnings
 
 import numpy as np
 
-from .data import contig_rows, frame_columns, rows_by_contig
+from .data import contig_rows, frame_columns, record_ids, rows_by_contig
 from .engine import GENE_DTYPE, MGCOD_CODES
 
 VERSION_BANNER = "GeneMark.hmm-2 version 1.17"   # line 2 of the binary's usage text (bin/results.py:185)
@@ -97,9 +97,10 @@ class Results:
         # rows in the order the reference visits them: contig by contig in sorted-id order, frame order inside a contig,
         # parents of isoform pairs (logodd '.') left out (bin/results.py:362-372)
         index = rows_by_contig(coords)
-        present = [(n, index[seq.id]) for n, seq in enumerate(P.sequence) if seq.id in index] if len(index) else []
+        seq_ids = record_ids(P.sequence)
+        present = [(n, index[rid]) for n, rid in enumerate(seq_ids) if rid in index] if len(index) else []
         rows = np.concatenate([pos for _, pos in present]) if present else np.zeros(0, dtype=np.int64)
-        contig_file = (np.concatenate([np.full(len(pos), index_of[P.sequence[n].id], dtype=np.int32) for n, pos in present])
+        contig_file = (np.concatenate([np.full(len(pos), index_of[seq_ids[n]], dtype=np.int32) for n, pos in present])
                        if present else np.zeros(0, dtype=np.int32))
         logodd = coords.logodd.values
         if logodd.dtype == object and len(rows):
@@ -201,7 +202,7 @@ class Results:
         # a switch somewhere: one column per segment.  The reference fills a DataFrame cell by cell; _Table keeps what
         # decides the bytes of its to_csv: row and column order of first use, and whether a column started numeric
         # (floats, "22.0") or with text (values kept as they are, "22").
-        level_1 = getattr(P, "_ids", None) or [seq.id for seq in P.sequence]
+        level_1 = getattr(P, "_ids", None) or list(record_ids(P.sequence))
         coords_all = P.coords_w_isoforms
         index = rows_by_contig(coords_all)
         lmin, lmax = getattr(P, "_label_min", None), getattr(P, "_label_max", None)
@@ -305,9 +306,10 @@ class Results:
             out.write(f"# translation table: {', '.join(tables)}\n")
             out.write(f"# output date start: {self.date.strftime('%a %b %d %Y %H:%M:%S')}\n")
             index = rows_by_contig(coords)
-            for n, seq in enumerate(P.sequence):
-                if seq.id not in index:       # no genes on this contig: no block in the file
+            for n, rid in enumerate(record_ids(P.sequence)):
+                if rid not in index:          # no genes on this contig: no block in the file
                     continue
+                seq = P.sequence[n]
                 size = len(seq)
                 cur = contig_rows(coords, index, seq.id).copy()
                 cur = cur.loc[:, columns]
