@@ -193,6 +193,9 @@ const char *mgc_fasta_id(const mgc_fasta *f, int32_t i);
 const char *mgc_fasta_defline(const mgc_fasta *f, int32_t i);
 /* all ids (deflines != 0: all deflines) in one buffer, each followed by '\n'; *len = its size.  Valid until mgc_fasta_free. */
 const char *mgc_fasta_ids_joined(const mgc_fasta *f, int deflines, int64_t *len);
+/* the ids as an array of n C strings — what mgc_write_gff takes as contig_ids — without a string per record on the caller's
+ * side.  Valid until mgc_fasta_free. */
+const char *const *mgc_fasta_id_array(const mgc_fasta *f);
 const char *mgc_fasta_sequence(const mgc_fasta *f);      /* concatenated letters, no separators */
 const int64_t *mgc_fasta_offsets(const mgc_fasta *f);    /* n + 1 entries */
 void mgc_fasta_free(mgc_fasta *f);

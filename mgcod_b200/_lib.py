@@ -41,7 +41,7 @@ EXPORTS = (
     "mgc_engine_stats", "mgc_result_num_genes", "mgc_result_genes", "mgc_result_contig_totals",
     "mgc_result_model_cents", "mgc_result_min_gene_length", "mgc_result_set_min_gene_length", "mgc_result_free", "mgc_result_create", "mgc_recoded_stops", "mgc_window_counts", "mgc_window_labels", "mgc_isoform_labels", "mgc_merge_labels", "mgc_debug_candidates",
     "mgc_write_gff", "mgc_engine_device_genes",
-    "mgc_fasta_read", "mgc_fasta_num_records", "mgc_fasta_id", "mgc_fasta_defline", "mgc_fasta_ids_joined", "mgc_fasta_sequence", "mgc_fasta_offsets", "mgc_fasta_free",
+    "mgc_fasta_read", "mgc_fasta_num_records", "mgc_fasta_id", "mgc_fasta_defline", "mgc_fasta_ids_joined", "mgc_fasta_id_array", "mgc_fasta_sequence", "mgc_fasta_offsets", "mgc_fasta_free",
 )
 
 _LIB = None
@@ -110,6 +110,8 @@ def lib():
     L.mgc_fasta_defline.restype = cp
     L.mgc_fasta_ids_joined.argtypes = [vp, C.c_int, C.POINTER(i64)]
     L.mgc_fasta_ids_joined.restype = vp
+    L.mgc_fasta_id_array.argtypes = [vp]
+    L.mgc_fasta_id_array.restype = vp
     L.mgc_fasta_sequence.argtypes = [vp]
     L.mgc_fasta_sequence.restype = vp
     L.mgc_fasta_offsets.argtypes = [vp]

@@ -379,6 +379,8 @@ LetterBuffers &letter_buffers() {
 struct mgc_fasta {
     std::vector<std::string> ids, deflines;
     std::string ids_joined, deflines_joined;   // '\n'-separated, for one-call retrieval
+    std::vector<const char *> id_ptrs;         // mgc_fasta_id_array, built on first use
+    std::mutex mu;
     std::vector<int64_t> offsets;
     char *seq = nullptr;
     size_t seq_bytes = 0;
@@ -564,6 +566,16 @@ const char *mgc_fasta_ids_joined(const mgc_fasta *f, int deflines, int64_t *len)
     const std::string &s = deflines ? f->deflines_joined : f->ids_joined;
     if (len) *len = (int64_t)s.size();
     return s.data();
+}
+const char *const *mgc_fasta_id_array(const mgc_fasta *cf) {
+    mgc_fasta *f = const_cast<mgc_fasta *>(cf);
+    if (!f) return nullptr;
+    std::lock_guard<std::mutex> lk(f->mu);
+    if (f->id_ptrs.size() != f->ids.size()) {
+        f->id_ptrs.resize(f->ids.size());
+        for (size_t i = 0; i < f->ids.size(); i++) f->id_ptrs[i] = f->ids[i].c_str();
+    }
+    return f->id_ptrs.data();
 }
 const char *mgc_fasta_sequence(const mgc_fasta *f) { return f ? f->seq : nullptr; }
 const int64_t *mgc_fasta_offsets(const mgc_fasta *f) { return f ? f->offsets.data() : nullptr; }

@@ -267,6 +267,11 @@ class Fasta:
         self.buffer = (np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(max(total, 1),))[:total]
                        if ptr else np.zeros(0, np.uint8))
 
+    def id_array(self):
+        """the ids as an array of C strings inside the reader (``Result.write`` takes it as it is); valid until close()"""
+        import ctypes as C
+        return C.c_void_p(_lib.lib().mgc_fasta_id_array(self._h))
+
     def _record(self, k: int) -> Record:
         """the one Record object of record k (shared by every :class:`Records` view of this file)"""
         made = self.__dict__.setdefault("_records_made", {})
@@ -356,7 +361,7 @@ class Data:
         self._decoded_order = recs
         if not missing:
             return
-        ids = self._fasta.ids if hasattr(self, "_fasta") else [r.id for r in recs]
+        ids = self._fasta.id_array() if hasattr(self, "_fasta") else [r.id for r in recs]
         lens = np.diff(self._fasta.offsets) if hasattr(self, "_fasta") else [len(r) for r in recs]
         # the four files are formatted side by side (the C writer runs without the GIL)
         from concurrent.futures import ThreadPoolExecutor

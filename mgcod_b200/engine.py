@@ -113,11 +113,16 @@ class Result:
         _check(_lib.lib().mgc_result_model_cents(self._h, out.ctypes.data_as(C.POINTER(C.c_int64))))
         return out
 
-    def write(self, model: int, contig_ids: Sequence[str], contig_len: Sequence[int], seq_file: str, mod_file: str,
+    def write(self, model: int, contig_ids, contig_len: Sequence[int], seq_file: str, mod_file: str,
               gcode: int, out_path: str, fmt: str = "gff") -> None:
-        ids = (C.c_char_p * len(contig_ids))(*[s.encode() for s in contig_ids])
+        """``contig_ids``: the ids as strings, or a ready array of C strings (``data.Fasta.id_array()``: the reader's own
+        storage — four writer threads encoding 20 000 ids each would hold the interpreter lock against the caller)."""
         lens = np.asarray(contig_len, dtype=np.int64)
-        _check(_lib.lib().mgc_write_gff(self._h, model, ids, lens.ctypes.data_as(C.POINTER(C.c_int64)), len(contig_ids),
+        if isinstance(contig_ids, C.c_void_p):
+            ids = C.cast(contig_ids, C.POINTER(C.c_char_p))
+        else:
+            ids = (C.c_char_p * len(contig_ids))(*[s.encode() for s in contig_ids])
+        _check(_lib.lib().mgc_write_gff(self._h, model, ids, lens.ctypes.data_as(C.POINTER(C.c_int64)), len(lens),
                                         seq_file.encode(), mod_file.encode(), gcode, out_path.encode(), fmt.encode()))
 
     def __del__(self):
